@@ -1,0 +1,186 @@
+"""ctypes binding of libb200tts.so (include/b200tts.h). No torch types cross this boundary.
+
+The library is built in-tree by build.py; importing this module never builds anything and fails loudly
+(`Libb200ttsMissing`) when the shared object is absent -- there is no CPU fallback.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200tts.so")
+
+F32, BF16 = 0, 1
+
+
+class Libb200ttsMissing(RuntimeError):
+    pass
+
+
+_c_f = ctypes.POINTER(ctypes.c_float)
+_c_i16 = ctypes.POINTER(ctypes.c_int16)
+_c_i32 = ctypes.POINTER(ctypes.c_int32)
+_c_i64 = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); every symbol include/b200tts.h declares (tests/test_capi_symbols.py checks the two agree)
+SIGNATURES = {
+    "b200tts_create": (_int, [_int, ctypes.POINTER(_vp)]),
+    "b200tts_destroy": (None, [_vp]),
+    "b200tts_last_error": (ctypes.c_char_p, []),
+    "b200tts_set_stream": (_int, [_vp, _vp]),
+    "b200tts_synchronize": (_int, [_vp]),
+    "b200tts_launch_count": (ctypes.c_ulonglong, []),
+    "b200tts_load_tensor": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
+    "b200tts_load_tensor_device": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
+    "b200tts_bigvgan_build": (_int, [_vp]),
+    "b200tts_bigvgan_run": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
+    "b200tts_bigvgan_run_device": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
+    "b200tts_aa_activation": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp]),
+    "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
+    "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
+    "b200tts_profile_begin": (_int, [_vp]),
+    "b200tts_profile_end": (ctypes.c_char_p, [_vp]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200tts.so and attach the prototypes. Works without a GPU (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Libb200ttsMissing(
+            f"{LIB_PATH} is missing: build it with `python text-to-speech-tts-onnx_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Engine:
+    """One engine per GPU (b200tts_create)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.b200tts_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("b200tts_create: " + self.lib.b200tts_last_error().decode())
+        self.handle = h
+        self.device = int(device)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: " + self.lib.b200tts_last_error().decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.b200tts_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.b200tts_set_stream(self.handle, _vp(cuda_stream_ptr or 0)), "set_stream")
+
+    def synchronize(self):
+        self._check(self.lib.b200tts_synchronize(self.handle), "synchronize")
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200tts_launch_count())
+
+    def profile_begin(self):
+        self._check(self.lib.b200tts_profile_begin(self.handle), "profile_begin")
+
+    def profile_end(self) -> dict:
+        return json.loads(self.lib.b200tts_profile_end(self.handle).decode())
+
+    # -- weights ---------------------------------------------------------------------------------
+    def load_tensor(self, name: str, array):
+        a = _f32(array)
+        shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+        self._check(self.lib.b200tts_load_tensor(self.handle, name.encode(), _ptr(a), shape, a.ndim), f"load_tensor({name})")
+
+    def load_tensor_device(self, name: str, dev_ptr: int, shape):
+        shp = (ctypes.c_int64 * max(len(shape), 1))(*shape)
+        self._check(self.lib.b200tts_load_tensor_device(self.handle, name.encode(), _vp(dev_ptr), shp, len(shape)),
+                    f"load_tensor_device({name})")
+
+    def load_state(self, prefix: str, state: dict):
+        for k, v in state.items():
+            self.load_tensor(f"{prefix}.{k}", v)
+
+    def bigvgan_build(self):
+        self._check(self.lib.b200tts_bigvgan_build(self.handle), "bigvgan_build")
+
+    # -- BigVGAN ---------------------------------------------------------------------------------
+    def bigvgan_run(self, mel, precision=F32, return_wave=False, hop=256):
+        mel = _f32(mel)
+        assert mel.ndim == 3, "mel_features must be (B, n_mels, T)"
+        B, _, T = mel.shape
+        n_out = hop * T + 30
+        pcm = np.empty((B, 1, n_out), dtype=np.int16)
+        wave = np.empty((B, 1, n_out), dtype=np.float32) if return_wave else None
+        self._check(self.lib.b200tts_bigvgan_run(self.handle, _ptr(mel), B, T, int(precision), _ptr(pcm), _ptr(wave)),
+                    "bigvgan_run")
+        return (pcm, wave) if return_wave else pcm
+
+    def bigvgan_run_device(self, mel_ptr: int, B: int, T: int, pcm_ptr: int, precision=BF16, wave_ptr: int = 0):
+        self._check(self.lib.b200tts_bigvgan_run_device(self.handle, _vp(mel_ptr), B, T, int(precision), _vp(pcm_ptr),
+                                                        _vp(wave_ptr or 0)), "bigvgan_run_device")
+
+    # -- single ops (reference layouts) --------------------------------------------------------------
+    def aa_activation(self, x, alpha_log, beta_log, taps12, precise=True, post=False):
+        x = _f32(x)
+        B, C, L = x.shape
+        y = np.empty((B, C, L + 30 if post else L), dtype=np.float32)
+        a, b, t = _f32(alpha_log), _f32(beta_log), _f32(taps12)
+        assert a.shape == (C,) and b.shape == (C,) and t.shape == (12,)
+        self._check(self.lib.b200tts_aa_activation(self.handle, _ptr(x), B, C, L, _ptr(a), _ptr(b), _ptr(t),
+                                                   int(precise), int(post), _ptr(y)), "aa_activation")
+        return y
+
+    def conv1d(self, x, w, bias=None, dilation=1, groups=1, precision=F32):
+        x, w = _f32(x), _f32(w)
+        B, Cin, L = x.shape
+        Cout, cg, k = w.shape
+        assert cg * groups == Cin
+        b = None if bias is None else _f32(bias)
+        y = np.empty((B, Cout, L), dtype=np.float32)
+        self._check(self.lib.b200tts_conv1d(self.handle, _ptr(x), B, Cin, L, _ptr(w), Cout, k, int(dilation), int(groups),
+                                            _ptr(b), int(precision), _ptr(y)), "conv1d")
+        return y
+
+    def conv_transpose1d(self, x, w, bias=None, stride=2, precision=F32):
+        x, w = _f32(x), _f32(w)
+        B, Cin, L = x.shape
+        cin2, Cout, k = w.shape
+        assert cin2 == Cin and k == 2 * stride
+        b = None if bias is None else _f32(bias)
+        y = np.empty((B, Cout, L * stride), dtype=np.float32)
+        self._check(self.lib.b200tts_conv_transpose1d(self.handle, _ptr(x), B, Cin, L, _ptr(w), Cout, int(stride), _ptr(b),
+                                                      int(precision), _ptr(y)), "conv_transpose1d")
+        return y

@@ -1,0 +1,65 @@
+"""Hyper-parameters of the two graphs on the hot path.
+
+The values the reference pins itself are cited; the rest come from the un-vendored upstream
+configs and are confirmed by parameter count.
+"""
+from dataclasses import dataclass, field
+from typing import List
+
+
+@dataclass(frozen=True)
+class BigVGANConfig:
+    """bigvgan_v2_24khz_100band_256x (reference: BigVGAN/Export_BigVGAN.py:9, bigvgan.py:282-357)."""
+    num_mels: int = 100
+    upsample_initial_channel: int = 1536
+    upsample_rates: tuple = (4, 4, 2, 2, 2, 2)
+    upsample_kernel_sizes: tuple = (8, 8, 4, 4, 4, 4)
+    resblock_kernel_sizes: tuple = (3, 7, 11)
+    resblock_dilation_sizes: tuple = ((1, 3, 5), (1, 3, 5), (1, 3, 5))
+    aa_taps: int = 12            # act.py:12-15
+    post_pad: int = 15           # bigvgan.py:370,381-382 (the index -1 tables)
+    sample_rate: int = 24000
+
+    @property
+    def hop(self) -> int:
+        h = 1
+        for r in self.upsample_rates:
+            h *= r
+        return h
+
+    def stage_channels(self) -> List[int]:
+        return [self.upsample_initial_channel // (2 ** (i + 1)) for i in range(len(self.upsample_rates))]
+
+    def out_samples(self, frames: int) -> int:
+        return frames * self.hop + 2 * self.post_pad
+
+
+@dataclass(frozen=True)
+class F5Config:
+    """F5TTS_v1_Base + vocos-mel-24khz (reference: F5_TTS/Export_F5.py:44-65)."""
+    dim: int = 1024
+    depth: int = 22
+    heads: int = 16
+    head_dim: int = 64
+    ff_mult: int = 2
+    text_dim: int = 512
+    text_conv_layers: int = 4
+    vocab: int = 2545            # text_num_embeds; embedding table has vocab + 1 rows
+    n_mels: int = 100
+    nfft: int = 1024
+    hop: int = 256
+    sample_rate: int = 24000
+    max_frames: int = 4096       # MAX_SIGNAL_LENGTH, Export_F5.py:59
+    nfe: int = 32                # NFE_STEP -> 31 Euler steps
+    cfg_strength: float = 2.0
+    sway: float = -1.0
+    convpos_kernel: int = 31
+    convpos_groups: int = 16
+    # vocos-mel-24khz
+    vocos_dim: int = 512
+    vocos_inter: int = 1536
+    vocos_layers: int = 8
+
+
+BIGVGAN = BigVGANConfig()
+F5 = F5Config()

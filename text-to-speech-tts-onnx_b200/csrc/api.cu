@@ -1,0 +1,318 @@
+// extern "C" boundary of libb200tts (include/b200tts.h). Exceptions never cross it: every entry point
+// catches, stores the message thread-locally and returns a non-zero code.
+#include "../../include/b200tts.h"
+
+#include <cstring>
+#include <sstream>
+
+#include "aa_act.cuh"
+#include "bigvgan.cuh"
+#include "engine.cuh"
+#include "layout.cuh"
+#include "rowgemm.cuh"
+#include "rowgemm_tc.cuh"
+
+using namespace b200tts;
+
+struct b200tts_engine {
+  Engine impl;
+};
+
+namespace b200tts {
+Engine::~Engine() {
+  if (bigvgan) bigvgan_free(bigvgan);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+}  // namespace b200tts
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_last_error = ex.what();
+    return 1;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return 2;
+  }
+}
+
+Engine& eng(b200tts_engine* e) {
+  if (!e) fail("null engine handle");
+  B2_CUDA(cudaSetDevice(e->impl.device));
+  return e->impl;
+}
+
+void store_tensor(Engine& E, const char* name, const float* data, const int64_t* shape, int ndim, bool from_device) {
+  B2_CHECK(name && data && (shape || ndim == 0), "load_tensor: null argument");
+  B2_CHECK(ndim >= 0 && ndim <= 4, "load_tensor: rank must be <= 4");
+  Tensor t;
+  long n = 1;
+  for (int i = 0; i < ndim; ++i) { B2_CHECK(shape[i] > 0, "load_tensor: non-positive dimension"); t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.alloc((size_t)n);
+  B2_CUDA(cudaMemcpyAsync(t.data.p, data, (size_t)n * sizeof(float),
+                          from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.stream));
+  B2_CUDA(cudaStreamSynchronize(E.stream));
+  E.weights[name] = std::move(t);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200tts_last_error(void) { return g_last_error.c_str(); }
+
+unsigned long long b200tts_launch_count(void) { return g_launch_count; }
+
+int b200tts_create(int device, b200tts_engine** out) {
+  return guarded([&] {
+    B2_CHECK(out != nullptr, "create: null out pointer");
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) fail("no CUDA device available (libb200tts has no CPU fallback)");
+    B2_CHECK(device >= 0 && device < n, "create: device index out of range");
+    B2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) fail(std::string("libb200tts is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+    std::unique_ptr<b200tts_engine> e(new b200tts_engine());
+    e->impl.device = device;
+    B2_CUDA(cudaStreamCreateWithFlags(&e->impl.stream, cudaStreamNonBlocking));
+    e->impl.own_stream = true;
+    *out = e.release();
+  });
+}
+
+void b200tts_destroy(b200tts_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->impl.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int b200tts_set_stream(b200tts_engine* e, void* cuda_stream) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CUDA(cudaStreamSynchronize(E.stream));
+    if (E.own_stream && E.stream) { cudaStreamDestroy(E.stream); E.stream = nullptr; E.own_stream = false; }
+    if (cuda_stream) {
+      E.stream = (cudaStream_t)cuda_stream;
+    } else {
+      B2_CUDA(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+      E.own_stream = true;
+    }
+  });
+}
+
+int b200tts_synchronize(b200tts_engine* e) {
+  return guarded([&] { Engine& E = eng(e); B2_CUDA(cudaStreamSynchronize(E.stream)); });
+}
+
+int b200tts_load_tensor(b200tts_engine* e, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  return guarded([&] { store_tensor(eng(e), name, host_data, shape, ndim, false); });
+}
+
+int b200tts_load_tensor_device(b200tts_engine* e, const char* name, const float* dev_data, const int64_t* shape, int ndim) {
+  return guarded([&] { store_tensor(eng(e), name, dev_data, shape, ndim, true); });
+}
+
+int b200tts_bigvgan_build(b200tts_engine* e) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    if (E.bigvgan) { bigvgan_free(E.bigvgan); E.bigvgan = nullptr; }
+    E.bigvgan = bigvgan_build(E);
+  });
+}
+
+int b200tts_bigvgan_run_device(b200tts_engine* e, const float* mel_dev, int B, int T, int precision, int16_t* pcm_dev,
+                               float* wave_dev) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(mel_dev && pcm_dev, "bigvgan_run_device: null buffer");
+    bigvgan_forward(E, mel_dev, B, T, precision, pcm_dev, wave_dev);
+  });
+}
+
+int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, int precision, int16_t* pcm_host,
+                        float* wave_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(mel_host && pcm_host, "bigvgan_run: null buffer");
+    B2_CHECK(E.bigvgan != nullptr, "BigVGAN weights are not built (call b200tts_bigvgan_build)");
+    B2_CHECK(B > 0 && T > 0, "bigvgan_run: empty input");
+    const long n_mel = (long)B * T * bigvgan_num_mels(E);
+    const long n_out = (long)B * bigvgan_out_samples(E, T);
+    DevBuf<float> d_mel((size_t)n_mel), d_wave;
+    DevBuf<int16_t> d_pcm((size_t)n_out);
+    if (wave_host) d_wave.alloc((size_t)n_out);
+    B2_CUDA(cudaMemcpyAsync(d_mel.p, mel_host, n_mel * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    bigvgan_forward(E, d_mel.p, B, T, precision, d_pcm.p, wave_host ? d_wave.p : nullptr);
+    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, n_out * sizeof(int16_t), cudaMemcpyDeviceToHost, E.stream));
+    if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    B2_CUDA(cudaStreamSynchronize(E.stream));
+  });
+}
+
+int b200tts_aa_activation(b200tts_engine* e, const float* x_host, int B, int C, int L, const float* alpha_log,
+                          const float* beta_log, const float* taps12, int precise, int post, float* y_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(x_host && alpha_log && beta_log && taps12 && y_host, "aa_activation: null buffer");
+    B2_CHECK(B > 0 && C > 0 && L > 0, "aa_activation: empty input");
+    cudaStream_t s = E.stream;
+    const int Lo = post ? L + 30 : L;
+    DevBuf<float> x((size_t)B * C * L), xt((size_t)B * C * L), y((size_t)B * C * Lo), yt((size_t)B * C * Lo), al(C), ib(C);
+    std::vector<float> ha(C), hb(C);
+    for (int i = 0; i < C; ++i) { ha[i] = expf(alpha_log[i]); hb[i] = 1.0f / (expf(beta_log[i]) + 1e-9f); }
+    B2_CUDA(cudaMemcpyAsync(x.p, x_host, x.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(al.p, ha.data(), C * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(ib.p, hb.data(), C * sizeof(float), cudaMemcpyHostToDevice, s));
+    aa_set_filter(taps12);
+    batched_transpose(x.p, xt.p, B, C, L, s);                       // (B,C,L) -> (B,L,C)
+    aa_snake(xt.p, 0, yt.p, 0, al.p, ib.p, B, C, L, precise != 0, post != 0, s);
+    batched_transpose(yt.p, y.p, B, Lo, C, s);                      // (B,Lo,C) -> (B,C,Lo)
+    B2_CUDA(cudaMemcpyAsync(y_host, y.p, y.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_conv1d(b200tts_engine* e, const float* x_host, int B, int Cin, int L, const float* w_host, int Cout, int k,
+                   int dil, int groups, const float* bias_host, int precision, float* y_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(x_host && w_host && y_host, "conv1d: null buffer");
+    B2_CHECK(B > 0 && Cin > 0 && L > 0 && Cout > 0 && k > 0 && dil > 0 && groups > 0, "conv1d: bad shape");
+    B2_CHECK(Cin % groups == 0 && Cout % groups == 0, "conv1d: channels must divide by groups");
+    B2_CHECK(k % 2 == 1, "conv1d: 'same' padding needs an odd kernel");
+    cudaStream_t s = E.stream;
+    const int cg = Cin / groups, ng = Cout / groups;
+    // weights (Cout, cg, k) -> [g][j][c][n]
+    std::vector<float> wf((size_t)groups * k * cg * ng), wt((size_t)groups * k * ng * cg);
+    for (int g = 0; g < groups; ++g)
+      for (int n = 0; n < ng; ++n)
+        for (int c = 0; c < cg; ++c)
+          for (int j = 0; j < k; ++j) {
+            const float v = w_host[((size_t)(g * ng + n) * cg + c) * k + j];
+            wf[(((size_t)g * k + j) * cg + c) * ng + n] = v;
+            wt[(((size_t)g * k + j) * ng + n) * cg + c] = v;
+          }
+    DevBuf<float> x((size_t)B * Cin * L), xt((size_t)B * Cin * L), y((size_t)B * Cout * L), yt((size_t)B * Cout * L), w(wf.size()), bias;
+    B2_CUDA(cudaMemcpyAsync(x.p, x_host, x.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (bias_host) { bias.alloc(Cout); B2_CUDA(cudaMemcpyAsync(bias.p, bias_host, Cout * sizeof(float), cudaMemcpyHostToDevice, s)); }
+    batched_transpose(x.p, xt.p, B, Cin, L, s);
+    RowGemm p;
+    p.x_bstride = (long)L * Cin; p.ldx = Cin; p.Lin = L;
+    p.Cin = cg; p.N = ng; p.taps = k; p.dil = dil; p.center = (k - 1) / 2; p.groups = groups;
+    p.M = L; p.B = B;
+    p.out = yt.p; p.o_bstride = (long)L * Cout; p.ldo = Cout;
+    p.bias = bias_host ? bias.p : nullptr;
+    if (precision == PREC_F32) {
+      B2_CUDA(cudaMemcpyAsync(w.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      p.x = xt.p; p.w = w.p; p.ldw = ng;
+      rowgemm_f32(p, s);
+    } else {
+      B2_CUDA(cudaMemcpyAsync(w.p, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      TcWeight tw;
+      tc_weight_from_f32(tw, w.p, groups, k, ng, cg, s);
+      const int ld = (int)round_up(Cin, 8);
+      DevBuf<__nv_bfloat16> x16((size_t)B * L * ld);
+      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s);
+      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld;
+      rowgemm_tc(p, tw, s);
+      B2_CUDA(cudaStreamSynchronize(s));   // tw / x16 are freed at scope exit
+    }
+    batched_transpose(yt.p, y.p, B, L, Cout, s);
+    B2_CUDA(cudaMemcpyAsync(y_host, y.p, y.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int Cin, int L, const float* w_host,
+                             int Cout, int stride, const float* bias_host, int precision, float* y_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(x_host && w_host && y_host, "conv_transpose1d: null buffer");
+    B2_CHECK(B > 0 && Cin > 0 && L > 0 && Cout > 0 && stride > 0 && stride % 2 == 0, "conv_transpose1d: bad shape");
+    cudaStream_t s = E.stream;
+    const int u = stride;
+    const long N = (long)u * Cout, Lo = (long)L * u;
+    // w (Cin, Cout, 2u) -> [tap][c][r*Cout+n] and its [tap][r*Cout+n][c] transpose
+    std::vector<float> wf(2 * (size_t)Cin * N), wt(2 * (size_t)Cin * N), bf((size_t)N, 0.f);
+    for (int tap = 0; tap < 2; ++tap)
+      for (int c = 0; c < Cin; ++c)
+        for (int r = 0; r < u; ++r)
+          for (int n = 0; n < Cout; ++n) {
+            const float v = w_host[((size_t)c * Cout + n) * (2 * u) + (tap == 0 ? r + u : r)];
+            wf[((size_t)tap * Cin + c) * N + (size_t)r * Cout + n] = v;
+            wt[((size_t)tap * N + (size_t)r * Cout + n) * Cin + c] = v;
+          }
+    if (bias_host)
+      for (long i = 0; i < N; ++i) bf[i] = bias_host[i % Cout];
+    DevBuf<float> x((size_t)B * Cin * L), xt((size_t)B * Cin * L), y((size_t)B * Cout * Lo), yt((size_t)B * Cout * Lo), w(wf.size()), bias((size_t)N);
+    B2_CUDA(cudaMemcpyAsync(x.p, x_host, x.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(bias.p, bf.data(), N * sizeof(float), cudaMemcpyHostToDevice, s));
+    batched_transpose(x.p, xt.p, B, Cin, L, s);
+    RowGemm p;
+    p.x_bstride = (long)L * Cin; p.ldx = Cin; p.Lin = L;
+    p.Cin = Cin; p.N = (int)N; p.taps = 2; p.dil = 1; p.center = 1;
+    p.M = L + 1; p.B = B;
+    p.out = yt.p; p.o_bstride = Lo * Cout; p.ldo = (int)N;
+    p.o_shift = -(long)(u / 2) * Cout; p.o_limit = Lo * Cout;
+    p.bias = bias.p;
+    if (precision == PREC_F32) {
+      B2_CUDA(cudaMemcpyAsync(w.p, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      p.x = xt.p; p.w = w.p; p.ldw = (int)N;
+      rowgemm_f32(p, s);
+    } else {
+      B2_CUDA(cudaMemcpyAsync(w.p, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      TcWeight tw;
+      tc_weight_from_f32(tw, w.p, 1, 2, (int)N, Cin, s);
+      const int ld = (int)round_up(Cin, 8);
+      DevBuf<__nv_bfloat16> x16((size_t)B * L * ld);
+      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s);
+      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld;
+      rowgemm_tc(p, tw, s);
+      B2_CUDA(cudaStreamSynchronize(s));
+    }
+    batched_transpose(yt.p, y.p, B, (int)Lo, Cout, s);
+    B2_CUDA(cudaMemcpyAsync(y_host, y.p, y.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_profile_begin(b200tts_engine* e) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CUDA(cudaStreamSynchronize(E.stream));
+    E.prof.collect();
+    E.prof.enabled = true;
+  });
+}
+
+const char* b200tts_profile_end(b200tts_engine* e) {
+  if (!e) return "{}";
+  int rc = guarded([&] {
+    Engine& E = eng(e);
+    E.prof.enabled = false;
+    auto m = E.prof.collect();
+    std::ostringstream os;
+    os << "{";
+    bool first = true;
+    for (auto& kv : m) {
+      if (!first) os << ", ";
+      first = false;
+      os << "\"" << kv.first << "\": {\"launches\": " << kv.second.first << ", \"ms\": " << kv.second.second << "}";
+    }
+    os << "}";
+    E.prof_report = os.str();
+  });
+  return rc == 0 ? e->impl.prof_report.c_str() : "{}";
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Shared helpers for libb200tts (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace b200tts {
+
+struct Error : public std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] inline void fail(const std::string& msg) { throw Error(msg); }
+
+#define B2_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::b200tts::fail(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                      __FILE__ + ":" + std::to_string(__LINE__));                          \
+    }                                                                                       \
+  } while (0)
+
+#define B2_CHECK(cond, msg)                                                       \
+  do {                                                                            \
+    if (!(cond)) ::b200tts::fail(std::string("check failed: ") + #cond + ": " + (msg)); \
+  } while (0)
+
+#define B2_LAUNCH_CHECK() B2_CUDA(cudaGetLastError())
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// Every kernel launch of ours goes through this counter (bench.py reports it as gpu_launches).
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+// Device buffer with RAII.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) B2_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+  }
+  // grow-only (never shrinks): workspaces are sized by the largest request seen
+  void reserve(size_t count) { if (count > n) alloc(count); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// Epilogue activation selectors shared by the fp32 and tcgen05 GEMMs.
+enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_MISH = 3 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_GELU_TANH: {   // torch GELU(approximate="tanh"): F5 modules.py:597
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      float u = k0 * (v + k1 * v * v * v);
+      return 0.5f * v * (1.0f + tanhf(u));
+    }
+    case ACT_GELU_ERF:      // torch nn.GELU(): F5 modules.py:249, vocos modules.py:37
+      return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
+    case ACT_MISH: {        // nn.Mish: x * tanh(softplus(x)), softplus threshold 20 (F5 modules.py:172)
+      float sp = v > 20.0f ? v : log1pf(expf(v));
+      return v * tanhf(sp);
+    }
+    default:
+      return v;
+  }
+}
+
+}  // namespace b200tts

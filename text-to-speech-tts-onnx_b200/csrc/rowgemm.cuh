@@ -1,0 +1,51 @@
+// "Shifted-row GEMM": the one dense contraction of the whole hot path, on channels-last tensors.
+//
+//   out[b, t, g*N + n] = epi( sum_{j<taps} sum_{c<Cin} X[b, t + (j-center)*dil, g*Cin + c] * W[g][j][c][n] )
+//
+// with X rows outside [0, Lin) reading as zero. It covers
+//   * Linear layers                     taps=1                      (DiT, Vocos pointwise, mel fbank)
+//   * dilated "same" Conv1d             taps=k, center=(k-1)/2      (BigVGAN resblocks, conv_pre, Vocos embed)
+//   * grouped Conv1d                    groups=16                   (DiT conv position embedding)
+//   * ConvTranspose1d stride u, k=2u    taps=2, center=1, N=u*Cout, flat output shift -(u/2)*Cout
+//                                                                   (BigVGAN upsamplers, see bigvgan.cu)
+//   * STFT / ISTFT bases                taps=1 with ldx = hop (overlapping rows)
+// Two implementations share this parameter block: rowgemm_f32 (SIMT fp32, the parity engine) and
+// rowgemm_tc (tcgen05 + TMA, bf16 operands / fp32 accumulate, the fast engine).
+#pragma once
+#include "common.cuh"
+
+namespace b200tts {
+
+struct RowGemm {
+  // A operand (activations), fp32 for rowgemm_f32, bf16 for rowgemm_tc
+  const void* x = nullptr;
+  long x_bstride = 0;     // elements between batches
+  int ldx = 0;            // elements between rows
+  int Lin = 0;            // valid input rows per batch: [0, Lin)
+  // B operand (weights): f32 path W[g][j][c][n] (n contiguous, row stride ldw);
+  //                      tc  path W[g][j][n][c] bf16 (c contiguous), described by a tensor map
+  const void* w = nullptr;
+  int ldw = 0;
+  int Cin = 0, N = 0, taps = 1, dil = 1, center = 0, groups = 1;
+  int M = 0;              // output rows per batch
+  int B = 1;
+  // output: flat index = b*o_bstride + t*ldo + g*N + n + o_shift, written iff 0 <= (t*ldo + g*N + n + o_shift) < o_limit
+  void* out = nullptr;
+  long o_bstride = 0;
+  int ldo = 0;
+  long o_shift = 0;
+  long o_limit = 0;       // 0 -> M*ldo
+  int out_bf16 = 0;
+  // epilogue: v = acc + bias[n]; v = act(v); v *= gate[n]; v += res[idx]; if (accumulate) v += out[idx]; v *= scale
+  const float* bias = nullptr;    // [groups*N]
+  const float* gate = nullptr;    // [groups*N]
+  const float* res = nullptr;     // indexed like out (fp32)
+  int accumulate = 0;
+  float scale = 1.0f;
+  int act = ACT_NONE;
+};
+
+// SIMT fp32 implementation (rowgemm_f32.cu). Requires Cin % 4 == 0, N % 4 == 0, ldx/ldw/ldo % 4 == 0.
+void rowgemm_f32(const RowGemm& p, cudaStream_t stream);
+
+}  // namespace b200tts

@@ -1,0 +1,30 @@
+// tcgen05 + TMA implementation of the shifted-row GEMM (rowgemm.cuh): bf16 operands, fp32 accumulation
+// in TMEM. See rowgemm_tc.cu for the kernel.
+#pragma once
+#include <cuda.h>
+
+#include "engine.cuh"
+#include "rowgemm.cuh"
+
+namespace b200tts {
+
+// Weights for the tensor-core path: bf16 W[g*taps + j][n][c] (c contiguous, row stride ldc) + its TMA map.
+struct TcWeight {
+  DevBuf<__nv_bfloat16> w;
+  CUtensorMap map;
+  int Cin = 0, ldc = 0, N = 0, taps = 0, groups = 1;
+  int BN = 0;                 // N tile (multiple of 16, <= 256)
+  bool ready = false;
+};
+
+// Build from an fp32 device tensor already laid out as [groups*taps][N][Cin] (c contiguous).
+void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps, int N, int Cin, cudaStream_t s);
+
+// A operand: bf16, rows of p.ldx elements (ldx % 8 == 0). Output fp32 or bf16 (p.out_bf16).
+void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream);
+
+void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s);
+// (rows, C) fp32 -> (rows, ldo) bf16 with zero-filled padding columns
+void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s);
+
+}  // namespace b200tts
