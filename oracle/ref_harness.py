@@ -112,3 +112,114 @@ def build_bigvgan(sd: dict, cfg):
             return w.to(torch.int16)
 
     return BIGVGAN(model, True)
+
+
+# ----------------------------------------------------------------------------------------------
+# F5-TTS: DiT, STFT_Process, Vocos and the three export wrappers
+# ----------------------------------------------------------------------------------------------
+def load_f5_modules():
+    """-> (dit module, STFT_Process class, vocos pretrained module), loaded from the reference tree."""
+    d = os.path.join(REF, "F5_TTS")
+    mm = os.path.join(d, "modeling_modified")
+    _stub("librosa")
+    _stub("librosa.filters", mel=lambda *a, **k: None)
+    _stub("x_transformers")
+
+    class _Rotary(torch.nn.Module):          # only constructed, never called on the exported path (dit.py:130)
+        def __init__(self, dim):
+            super().__init__()
+
+    _stub("x_transformers.x_transformers", apply_rotary_pos_emb=lambda *a, **k: None, RotaryEmbedding=_Rotary)
+    _stub("f5_tts")
+    _stub("f5_tts.model")
+    _load("f5_tts.model.modules", os.path.join(mm, "F5", "modules.py"))
+    dit = _load("ref_f5_dit", os.path.join(mm, "F5", "dit.py"))
+    if "onnxruntime" not in sys.modules:
+        _stub("onnxruntime")                 # STFT_Process.py:4 imports it for its own print-only tests
+    stft = _load("ref_stft_process", os.path.join(d, "STFT_Process.py"))
+    _stub("vocos")
+    _stub("vocos.spectral_ops", ISTFT=lambda **k: None, IMDCT=lambda **k: None)
+    _stub("vocos.feature_extractors", FeatureExtractor=torch.nn.Module, EncodecFeatures=type("EncodecFeatures", (), {}))
+    _load("vocos.modules", os.path.join(mm, "vocos", "modules.py"))
+    _load("vocos.models", os.path.join(mm, "vocos", "models.py"))
+    _load("vocos.heads", os.path.join(mm, "vocos", "heads.py"))
+    voc = _load("vocos.pretrained", os.path.join(mm, "vocos", "pretrained.py"))
+    return dit, stft.STFT_Process, voc
+
+
+def _export_wrappers(namespace):
+    """Compile the three wrapper classes straight from the reference's Export_F5.py source (lines 98-203). The
+    script itself cannot be imported (top-level file copies and checkpoint loads), and nothing is copied into this
+    repo: the class definitions are extracted from the file where it lies and exec'd in ``namespace``."""
+    import ast
+    path = os.path.join(REF, "F5_TTS", "Export_F5.py")
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    wanted = {"F5Preprocess", "F5Transformer", "F5Decode"}
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def build_f5(dit_sd: dict, vocos_sd: dict, cfg):
+    """Reference F5Preprocess / F5Transformer / F5Decode modules on synthetic checkpoints, transformed exactly as
+    Export_F5.py does (Q/K pre-scale :321-333 between exporting A and B, Vocos folding :389-402)."""
+    import math
+    import torchaudio
+    dit_mod, STFT_Process, voc = load_f5_modules()
+    ns = _export_wrappers({"torch": torch, "torchaudio": torchaudio, "math": math, "MAX_SIGNAL_LENGTH": cfg.max_frames})
+
+    transformer = dit_mod.DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, text_dim=cfg.text_dim,
+                              conv_layers=cfg.text_conv_layers, text_num_embeds=cfg.vocab, mel_dim=cfg.n_mels)
+    missing, unexpected = transformer.load_state_dict({k: torch.from_numpy(v) for k, v in dit_sd.items()}, strict=False)
+    assert not unexpected and all("rotary" in m or "freqs_cis" in m for m in missing), (missing, unexpected)
+    transformer = transformer.eval().float()
+
+    class _CFM:                       # the wrappers only touch f5_model.transformer (Export_F5.py:101,147-148)
+        pass
+
+    f5_model = _CFM()
+    f5_model.transformer = transformer
+    with torch.inference_mode():
+        stft = STFT_Process(model_type="stft_B", n_fft=cfg.nfft, win_length=cfg.nfft, hop_len=cfg.hop, max_frames=0,
+                            window_type="hann").eval()
+        pre = ns["F5Preprocess"](f5_model, stft, nfft=cfg.nfft, n_mels=cfg.n_mels, sample_rate=cfg.sample_rate,
+                                 num_head=cfg.heads, head_dim=cfg.head_dim, target_rms=0.15, use_fp16=False)
+        scale = math.pow(cfg.head_dim, -0.25)
+        for blk in transformer.transformer_blocks:          # Export_F5.py:329-333
+            blk.attn.to_q.weight.data *= scale
+            blk.attn.to_q.bias.data *= scale
+            blk.attn.to_k.weight.data *= scale
+            blk.attn.to_k.bias.data *= scale
+        trans = ns["F5Transformer"](f5_model, cfg=cfg.cfg_strength, steps=cfg.nfe, sway_coef=cfg.sway, dtype=torch.float32,
+                                    fuse_step=1)
+
+        istft = STFT_Process(model_type="istft_A", n_fft=cfg.nfft, win_length=cfg.nfft, hop_len=cfg.hop,
+                             max_frames=cfg.max_frames, window_type="hann").eval()
+        import vocos.heads as vh
+        import vocos.models as vm
+        backbone = vm.VocosBackbone(input_channels=cfg.n_mels, dim=cfg.vocos_dim, intermediate_dim=cfg.vocos_inter,
+                                    num_layers=cfg.vocos_layers)
+        vh.ISTFT = lambda **k: torch.nn.Identity()
+        head = vh.ISTFTHead(dim=cfg.vocos_dim, n_fft=cfg.nfft, hop_length=cfg.hop, padding="center")
+        vocos = voc.Vocos(feature_extractor=torch.nn.Identity(), backbone=backbone, head=head)
+        missing, unexpected = vocos.load_state_dict({k: torch.from_numpy(v) for k, v in vocos_sd.items()}, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        vocos.eval()
+        # Export_F5.py:390-402, verbatim semantics
+        rt = lambda w: torch.sqrt(torch.tensor(w.shape[0], dtype=torch.float32))
+        bb = vocos.backbone
+        bb.norm.weight.data = (bb.norm.weight.data * rt(bb.norm.weight.data)).view(1, -1, 1)
+        bb.norm.bias.data = bb.norm.bias.data.view(1, -1, 1)
+        bb.final_layer_norm.weight.data = (bb.final_layer_norm.weight.data * rt(bb.final_layer_norm.weight.data)).view(1, -1, 1)
+        bb.final_layer_norm.bias.data = bb.final_layer_norm.bias.data.view(1, -1, 1)
+        vocos.head.out.bias.data = vocos.head.out.bias.data.view(1, -1, 1)
+        for block in bb.convnext:
+            block.norm.weight.data = (block.norm.weight.data * rt(block.norm.weight.data)).view(1, -1, 1)
+            block.norm.bias.data = block.norm.bias.data.view(1, -1, 1)
+            block.pwconv1.weight.data = block.pwconv1.weight.data.unsqueeze(0)
+            block.pwconv1.bias.data = block.pwconv1.bias.data.view(1, -1, 1)
+            block.pwconv2.weight.data = (block.gamma.data.unsqueeze(-1) * block.pwconv2.weight.data).unsqueeze(0)
+            block.pwconv2.bias.data = (block.gamma.data * block.pwconv2.bias.data).view(1, -1, 1)
+        dec = ns["F5Decode"](vocos, istft, target_rms=0.15, use_fp16=False)
+    return pre.eval(), trans.eval(), dec.eval()

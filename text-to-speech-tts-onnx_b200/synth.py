@@ -137,7 +137,7 @@ def vocos_state(seed: int = 2468, cfg: F5Config = F5) -> dict:
     sd["backbone.final_layer_norm.bias"] = _n(rng, (C,), 0.05)
     sd["head.out.weight"] = _n(rng, (cfg.nfft + 2, C), 0.7 / np.sqrt(C))
     b = _n(rng, (cfg.nfft + 2,), 0.05)
-    b[: cfg.nfft // 2 + 1] -= 3.0      # log-magnitude rows: keep exp(.) well under the clip at 100
+    b[: cfg.nfft // 2 + 1] += 1.0      # log-magnitude rows: PCM RMS ~0.1, exp(.) mostly under the clip at 100
     sd["head.out.bias"] = b
     return sd
 
