@@ -55,6 +55,36 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
 int b200tts_bigvgan_run_device(b200tts_engine* e, const float* mel_dev, int B, int T, int precision,
                                int16_t* pcm_dev, float* wave_dev);
 
+/* ---- F5-TTS sessions (F5_TTS/Export_F5.py:98-203, host loop F5-TTS-ONNX-Inference.py:247-311) ----------------
+ * Tensors "dit.*" (EMA DiT state dict, Q/K pre-scaled), "vocos.*" (folded) and "f5.*" (export-time constants:
+ * time_expand, delta_t, rope_cos/sin, text_pos, stft_basis, fbank, istft_basis, window_sum_inv) must be loaded. */
+int b200tts_f5_build(b200tts_engine* e);
+/* F5_Preprocess: audio int16 (1,1,L), text_ids int32 (1,n_text), max_duration -> cat_mel_text, cat_mel_text_drop
+ * (1,N,612) fp32 and ref_signal_len. noise / rope tables are produced by the caller (session.py) exactly as the
+ * graph would: noise is a seeded normal draw, the rope outputs are rows of the constant "f5.rope_*" tables. */
+int b200tts_f5_preprocess(b200tts_engine* e, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host,
+                          int n_text, int64_t max_duration, float* cat_mel_text_host, float* cat_mel_text_drop_host,
+                          int64_t* ref_signal_len);
+/* F5_Transformer: n_steps fused NFE steps (FUSE_NFE) from *time_step; noise (1,N,100) updated in place,
+ * *time_step += n_steps. rope_cos/rope_sin are the (N,64) rows of rope_cos_q / rope_sin_q [0,0]. */
+int b200tts_f5_transformer(b200tts_engine* e, float* noise_host, const float* rope_cos_host, const float* rope_sin_host,
+                           const float* cat_mel_text_host, const float* cat_mel_text_drop_host, int N,
+                           int32_t* time_step, int n_steps, int precision);
+/* F5_Decode: denoised (1,N,100), ref_signal_len -> output_audio int16 (1,1,256*(N-ref-1)); *n_out = sample count.
+ * wave_host (optional) receives the pre-cast float (clamped, x32767). */
+int b200tts_f5_decode(b200tts_engine* e, const float* denoised_host, int N, int64_t ref_signal_len, int16_t* pcm_host,
+                      float* wave_host, int64_t* n_out);
+/* Fused fast path = A, then n_steps x B (n_steps < 0: NFE-1), then C with every intermediate resident in HBM.
+ * noise_host (N,100) is the Euler start; mel_host (optional, N x 100) receives the denoised mel. */
+int b200tts_f5_synthesize(b200tts_engine* e, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host,
+                          int n_text, int64_t max_duration, const float* noise_host, int precision, int n_steps,
+                          int16_t* pcm_host, int64_t* n_out, float* mel_host);
+/* Same with device buffers, enqueued on the engine stream without synchronising (pcm_dev must hold
+ * 256*(max_duration - (L/256+1) - 1) samples). */
+int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
+                                 int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
+                                 int16_t* pcm_dev, float* mel_dev);
+
 /* ---- single-op entry points (parity tests of the kernels through the boundary) -------------------------
  * Anti-aliased SnakeBeta (BigVGAN/modeling_modified/act.py:25-29): x (B, C, L) fp32 host in the reference
  * layout -> y (B, C, L) (post=0) or (B, C, L+30) (post=1, the bigvgan.py:370,381-382 tables). alpha_log /
@@ -70,6 +100,11 @@ int b200tts_conv1d(b200tts_engine* e, const float* x_host, int B, int Cin, int L
  * x (B, Cin, L), w (Cin, Cout, 2*stride) -> y (B, Cout, stride*L). */
 int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int Cin, int L, const float* w_host,
                              int Cout, int stride, const float* bias_host, int precision, float* y_host);
+
+/* The DiT attention kernel alone (F5 modules.py:467: softmax(q @ k, fp32) @ v, no scale, no mask) on the tcgen05
+ * path: q, k, v (2, H, N, 64) fp32 host (already roped / pre-scaled) -> out (2, N, H*64) fp32 host. */
+int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
+                      float* out_host);
 
 /* ---- profiling (bench.py roofline leg) ------------------------------------------------------------------
  * Between begin and end every kernel launch is bracketed by CUDA events on the engine stream; end returns a

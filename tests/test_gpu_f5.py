@@ -1,0 +1,189 @@
+"""GPU parity for the F5-TTS path: CUDA engine (through the C ABI / the drop-in sessions) vs the vectors made by the
+reference's own F5Preprocess / F5Transformer / F5Decode (tests/golden/f5_ref.npz) and vs the oracle at other sizes.
+
+Stated tolerances (confirmed empirically on B200):
+  fp32 engine : mel max-abs <= 1e-3 after all 31 Euler steps; PCM within a few LSB of the reference's int16
+  bf16 engine : mel cosine >= 0.999 after 31 steps; PCM SNR >= 25 dB vs the fp32 reference
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200tts  # noqa: F401
+from b200tts import capi, config, synth, weights
+from conftest import GOLDEN, snr_db
+from oracle import f5_ref as R
+
+pytestmark = pytest.mark.gpu
+CFG = config.F5
+
+
+@pytest.fixture(scope="module")
+def g():
+    return dict(np.load(os.path.join(GOLDEN, "f5_ref.npz")))
+
+
+@pytest.fixture(scope="module")
+def f5(engine, g):
+    dsd = synth.f5_dit_state(int(g["dit_seed"]))
+    engine.load_state("dit", weights.dit_engine_tensors(dsd, CFG))
+    engine.load_state("vocos", weights.vocos_engine_tensors(synth.vocos_state(int(g["vocos_seed"])), CFG))
+    engine.load_state("f5", weights.f5_export_constants(dsd, CFG))
+    engine.f5_build()
+    return engine
+
+
+def _inputs(g):
+    return synth.f5_inputs(int(g["input_seed"]), int(g["audio_len"]), int(g["n_text"]))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+# ---- attention kernel alone -----------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1, 64, 128, 130, 257, 1126])
+def test_attention_tcgen05(engine, N):
+    rng = np.random.default_rng(N)
+    H = 16
+    q, k, v = (rng.standard_normal((2, H, N, 64)).astype(np.float32) for _ in range(3))
+    q *= 0.35
+    k *= 0.35                                     # logits ~ N(0, 1): the regime the pre-scaled weights produce
+    got = engine.attention(q, k, v)
+    qb, kb, vb = (torch.from_numpy(t).bfloat16().float() for t in (q, k, v))
+    want = torch.matmul(torch.softmax(torch.matmul(qb, kb.transpose(-1, -2)), dim=-1), vb).transpose(1, 2).reshape(2, N, H * 64)
+    # P and the output are rounded to bf16 (2^-9 relative); accumulation is fp32
+    np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=2.5e-2)
+    assert cosine(got, want.numpy()) > 0.9995
+
+
+# ---- graph A ------------------------------------------------------------------------------------------------
+def test_preprocess_vs_reference(f5, g):
+    audio, text_ids, maxd, _ = _inputs(g)
+    cond, cond_drop, ref_len = f5.f5_preprocess(audio, text_ids, int(maxd[0]))
+    assert ref_len == int(g["ref_signal_len"])
+    assert cond.shape == g["cat_mel_text"].shape == (1, 130, 612)
+    # log-mel half: STFT as an fp32 GEMM re-associates sums; log() amplifies that only where |X| is tiny
+    np.testing.assert_allclose(cond[..., :100], g["cat_mel_text"][..., :100], rtol=0, atol=5e-3)
+    assert np.abs(cond[..., :100] - g["cat_mel_text"][..., :100]).mean() < 1e-4
+    np.testing.assert_allclose(cond[..., 100:], g["cat_mel_text"][..., 100:], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(cond_drop[..., 100:], g["cat_mel_text_drop"][..., 100:], rtol=0, atol=2e-4)
+    assert np.abs(cond_drop[..., :100]).max() == 0.0
+    nt = int(g["n_text"])
+    assert np.abs(cond[0, nt:, 100:]).max() == 0.0 and np.abs(cond_drop[0, nt:, 100:]).max() == 0.0   # masked filler rows
+
+
+# ---- graph B ------------------------------------------------------------------------------------------------
+def test_transformer_f32_steps_vs_reference(f5, g):
+    _, _, _, noise = _inputs(g)
+    x, ts = noise, 0
+    for want_ts in (1, 2):
+        x, ts = f5.f5_transformer(x, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], ts,
+                                  n_steps=1, precision=capi.F32)
+        assert ts == want_ts
+        np.testing.assert_allclose(x, g[f"noise_after_{ts}"], rtol=0, atol=2e-5)
+    x, ts = f5.f5_transformer(x, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], ts,
+                              n_steps=6, precision=capi.F32)
+    np.testing.assert_allclose(x, g["noise_after_8"], rtol=0, atol=1e-4)
+    x, ts = f5.f5_transformer(x, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], ts,
+                              n_steps=23, precision=capi.F32)
+    assert ts == 31
+    assert np.abs(x - g["noise_after_31"]).max() <= 1e-3          # the stated fp32 tolerance after 31 Euler steps
+    with pytest.raises(RuntimeError, match="time_step out of range"):
+        f5.f5_transformer(x, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], ts, 1, capi.F32)
+
+
+def test_transformer_bf16_vs_reference(f5, g):
+    _, _, _, noise = _inputs(g)
+    x1, _ = f5.f5_transformer(noise, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], 0,
+                              n_steps=1, precision=capi.BF16)
+    # one step: the update is delta_t[0] ~ 1.3e-3 times the prediction, so compare the prediction itself
+    dt0 = float(g["delta_t"][0])
+    pred_ref = (g["noise_after_1"] - noise) / dt0
+    pred_got = (x1 - noise) / dt0
+    assert cosine(pred_got, pred_ref) > 0.995
+    x, ts = f5.f5_transformer(noise, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], 0,
+                              n_steps=31, precision=capi.BF16)
+    assert ts == 31
+    assert cosine(x, g["noise_after_31"]) >= 0.999                # the stated bf16 tolerance
+    # fused n_steps == loop of single steps, bit for bit (same kernels, same order)
+    y, t2 = noise, 0
+    for _ in range(3):
+        y, t2 = f5.f5_transformer(y, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], t2, 1, capi.BF16)
+    z, _ = f5.f5_transformer(noise, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], 0, 3, capi.BF16)
+    np.testing.assert_array_equal(y, z)
+
+
+# ---- graph C ------------------------------------------------------------------------------------------------
+def test_decode_vs_reference(f5, g):
+    pcm, wave = f5.f5_decode(g["decode_in"], 12, return_wave=True)
+    assert pcm.dtype == np.int16 and pcm.shape == g["decode_pcm"].shape
+    d = np.abs(pcm.astype(np.int32) - g["decode_pcm"])
+    assert d.max() <= 3 and (d <= 1).mean() > 0.99
+    pcm = f5.f5_decode(g["noise_after_31"], int(g["ref_signal_len"]))
+    d = np.abs(pcm.astype(np.int32) - g["pcm"])
+    assert d.max() <= 3 and (d <= 1).mean() > 0.99
+    with pytest.raises(RuntimeError, match="ref_signal_len"):
+        f5.f5_decode(g["decode_in"], 40)
+    assert f5.f5_decode(g["decode_in"], 39).shape == (1, 1, 0)    # a single frame decodes to 256*(1-1) = 0 samples
+
+
+# ---- A + 31 x B + C ------------------------------------------------------------------------------------------
+def test_synthesize_vs_reference(f5, g):
+    audio, text_ids, maxd, noise = _inputs(g)
+    pcm32, mel32 = f5.f5_synthesize(audio, text_ids, int(maxd[0]), noise, precision=capi.F32, return_mel=True)
+    assert pcm32.shape == g["pcm"].shape
+    assert np.abs(mel32 - g["noise_after_31"]).max() <= 1e-3
+    assert snr_db(g["pcm"], pcm32) > 55.0
+    pcm16, mel16 = f5.f5_synthesize(audio, text_ids, int(maxd[0]), noise, precision=capi.BF16, return_mel=True)
+    assert cosine(mel16, g["noise_after_31"]) >= 0.999
+    assert snr_db(g["pcm"], pcm16) > 25.0
+
+
+def test_synthesize_other_sizes_vs_oracle(f5, g):
+    """Ragged sizes (N not a multiple of anything, ref != gen length) against the oracle run here on the CPU."""
+    dsd, vsd = synth.f5_dit_state(int(g["dit_seed"])), synth.vocos_state(int(g["vocos_seed"]))
+    audio, text_ids, _, _ = synth.f5_inputs(5, audio_len=9000, n_text=13)
+    N = 36 + 41
+    noise = np.random.default_rng(9).standard_normal((1, N, 100), dtype=np.float32)
+    want_pcm, want_mel, ref_len = R.f5_synthesize(audio, text_ids, [N], noise, dsd, vsd, CFG, steps=4, return_mel=True)
+    pcm, mel = f5.f5_synthesize(audio, text_ids, N, noise, precision=capi.F32, n_steps=4, return_mel=True)
+    assert ref_len == 9000 // 256 + 1 and pcm.shape == tuple(want_pcm.shape)
+    np.testing.assert_allclose(mel, want_mel.numpy(), rtol=0, atol=2e-4)
+    assert snr_db(want_pcm.numpy(), pcm) > 55.0
+
+
+def test_f5_session_surface(f5, g):
+    """The reference's own loop (F5-TTS-ONNX-Inference.py:247-311) against the drop-in sessions."""
+    from b200tts import session as onnxruntime
+    onnxruntime._engines[0] = f5
+    onnxruntime._f5_ready[id(f5)] = True
+    onnxruntime.set_seed(9527)
+    opts = onnxruntime.SessionOptions()
+    A = onnxruntime.InferenceSession("F5_Preprocess.onnx", sess_options=opts, providers=["CPUExecutionProvider"])
+    B = onnxruntime.InferenceSession("F5_Transformer.onnx", sess_options=opts, providers=[], precision="fp32")
+    C = onnxruntime.InferenceSession("F5_Decode.onnx", sess_options=opts, providers=["CPUExecutionProvider"])
+    assert [i.name for i in A.get_inputs()] == ["audio", "text_ids", "max_duration"]
+    assert [o.name for o in A.get_outputs()] == ["noise", "rope_cos_q", "rope_sin_q", "rope_cos_k", "rope_sin_k",
+                                                 "cat_mel_text", "cat_mel_text_drop", "ref_signal_len"]
+    assert [i.name for i in B.get_inputs()][-1] == "time_step" and [o.name for o in B.get_outputs()] == ["denoised", "time_step"]
+    audio, text_ids, maxd, noise_in = _inputs(g)
+    outs = A.run([o.name for o in A.get_outputs()], {"audio": audio, "text_ids": text_ids, "max_duration": maxd})
+    noise, rcq, rsq, rck, rsk, cmt, cmtd, ref_len = outs
+    assert noise.shape == (1, 130, 100) and rcq.shape == (2, 16, 130, 64) and rck.shape == (2, 16, 64, 130)
+    np.testing.assert_array_equal(rcq[1, 7], g["rope_cos_row"])
+    noise = noise_in                                   # parity: inject the Euler start (ORT's RNG is irreproducible)
+    time_step = np.array([0], dtype=np.int32)
+    in_B = [i.name for i in B.get_inputs()]
+    for _ in range(0, 32 - 1, 1):
+        noise, time_step = B.run(["denoised", "time_step"], dict(zip(in_B, [noise, rcq, rsq, rck, rsk, cmt, cmtd, time_step])))
+    assert int(time_step[0]) == 31
+    assert np.abs(noise - g["noise_after_31"]).max() <= 1e-3
+    fused, ts = B.run_all_steps(dict(zip(in_B, [noise_in, rcq, rsq, rck, rsk, cmt, cmtd, np.array([0], dtype=np.int32)])))
+    np.testing.assert_array_equal(fused, noise)        # per-step calls stay bit-compatible with the fused path
+    wav = C.run(["output_audio"], {"denoised": noise, "ref_signal_len": ref_len})[0]
+    assert wav.dtype == np.int16 and wav.shape == g["pcm"].shape
+    assert snr_db(g["pcm"], wav) > 55.0

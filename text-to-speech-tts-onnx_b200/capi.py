@@ -39,9 +39,16 @@ SIGNATURES = {
     "b200tts_bigvgan_build": (_int, [_vp]),
     "b200tts_bigvgan_run": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
     "b200tts_bigvgan_run_device": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
+    "b200tts_f5_build": (_int, [_vp]),
+    "b200tts_f5_preprocess": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _vp, _c_i64]),
+    "b200tts_f5_transformer": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _c_i32, _int, _int]),
+    "b200tts_f5_decode": (_int, [_vp, _vp, _int, ctypes.c_int64, _vp, _vp, _c_i64]),
+    "b200tts_f5_synthesize": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _c_i64, _vp]),
+    "b200tts_f5_synthesize_device": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
     "b200tts_aa_activation": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp]),
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
+    "b200tts_attention": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp]),
     "b200tts_profile_begin": (_int, [_vp]),
     "b200tts_profile_end": (ctypes.c_char_p, [_vp]),
 }
@@ -152,6 +159,68 @@ class Engine:
         self._check(self.lib.b200tts_bigvgan_run_device(self.handle, _vp(mel_ptr), B, T, int(precision), _vp(pcm_ptr),
                                                         _vp(wave_ptr or 0)), "bigvgan_run_device")
 
+    # -- F5-TTS ----------------------------------------------------------------------------------
+    def f5_build(self):
+        self._check(self.lib.b200tts_f5_build(self.handle), "f5_build")
+
+    def f5_preprocess(self, audio, text_ids, max_duration: int, cond_dim: int = 612):
+        """audio int16 (1,1,L), text_ids int32 (1,n) -> cat_mel_text, cat_mel_text_drop (1,N,cond_dim), ref_signal_len."""
+        audio = np.ascontiguousarray(audio, dtype=np.int16).reshape(-1)
+        ids = np.ascontiguousarray(text_ids, dtype=np.int32).reshape(-1)
+        N = int(max_duration)
+        c = np.empty((1, N, cond_dim), dtype=np.float32)
+        cd = np.empty((1, N, cond_dim), dtype=np.float32)
+        ref = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_f5_preprocess(self.handle, _ptr(audio), audio.size, _ptr(ids), ids.size, N, _ptr(c),
+                                                   _ptr(cd), ctypes.byref(ref)), "f5_preprocess")
+        return c, cd, int(ref.value)
+
+    def f5_transformer(self, noise, rope_cos, rope_sin, cond, cond_drop, time_step: int, n_steps: int = 1, precision=F32):
+        """One (or n_steps fused) NFE step(s). noise (1,N,100) is copied, updated and returned with the new time_step."""
+        noise = np.array(noise, dtype=np.float32, order="C", copy=True)
+        N = noise.shape[-2]
+        rc, rs, c, cd = _f32(rope_cos), _f32(rope_sin), _f32(cond), _f32(cond_drop)
+        assert rc.shape[-2:] == (N, 64) and rc.size == N * 64 and c.shape[-2] == N and cd.shape == c.shape
+        ts = ctypes.c_int32(int(time_step))
+        self._check(self.lib.b200tts_f5_transformer(self.handle, _ptr(noise), _ptr(rc), _ptr(rs), _ptr(c), _ptr(cd), N,
+                                                    ctypes.byref(ts), int(n_steps), int(precision)), "f5_transformer")
+        return noise, int(ts.value)
+
+    def f5_decode(self, denoised, ref_signal_len: int, return_wave=False, hop: int = 256):
+        d = _f32(denoised)
+        N = d.shape[-2]
+        ns = max(hop * (N - int(ref_signal_len) - 1), 0)
+        pcm = np.empty((1, 1, max(ns, 1)), dtype=np.int16)
+        wave = np.empty((1, 1, max(ns, 1)), dtype=np.float32) if return_wave else None
+        n_out = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_f5_decode(self.handle, _ptr(d), N, int(ref_signal_len), _ptr(pcm), _ptr(wave),
+                                               ctypes.byref(n_out)), "f5_decode")
+        assert n_out.value == ns
+        pcm = pcm[..., :ns]
+        return (pcm, wave[..., :ns]) if return_wave else pcm
+
+    def f5_synthesize(self, audio, text_ids, max_duration: int, noise, precision=BF16, n_steps: int = -1, return_mel=False,
+                      hop: int = 256):
+        audio = np.ascontiguousarray(audio, dtype=np.int16).reshape(-1)
+        ids = np.ascontiguousarray(text_ids, dtype=np.int32).reshape(-1)
+        noise = _f32(noise)
+        N = int(max_duration)
+        assert noise.size == N * 100
+        ns = hop * (N - (audio.size // hop + 1) - 1)
+        pcm = np.empty((1, 1, max(ns, 0)), dtype=np.int16)
+        mel = np.empty((1, N, 100), dtype=np.float32) if return_mel else None
+        n_out = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_f5_synthesize(self.handle, _ptr(audio), audio.size, _ptr(ids), ids.size, N, _ptr(noise),
+                                                   int(precision), int(n_steps), _ptr(pcm), ctypes.byref(n_out), _ptr(mel)),
+                    "f5_synthesize")
+        return (pcm, mel) if return_mel else pcm
+
+    def f5_synthesize_device(self, audio_ptr, L, ids_ptr, n_text, max_duration, noise_ptr, pcm_ptr, precision=BF16,
+                             n_steps: int = -1, mel_ptr: int = 0):
+        self._check(self.lib.b200tts_f5_synthesize_device(self.handle, _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
+                                                          int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
+                                                          _vp(pcm_ptr), _vp(mel_ptr or 0)), "f5_synthesize_device")
+
     # -- single ops (reference layouts) --------------------------------------------------------------
     def aa_activation(self, x, alpha_log, beta_log, taps12, precise=True, post=False):
         x = _f32(x)
@@ -162,6 +231,15 @@ class Engine:
         self._check(self.lib.b200tts_aa_activation(self.handle, _ptr(x), B, C, L, _ptr(a), _ptr(b), _ptr(t),
                                                    int(precise), int(post), _ptr(y)), "aa_activation")
         return y
+
+    def attention(self, q, k, v):
+        """q, k, v (2, H, N, 64) fp32 -> softmax(q k^T) v as (2, N, H*64), tcgen05 path (bf16 operands)."""
+        q, k, v = _f32(q), _f32(k), _f32(v)
+        two, H, N, hd = q.shape
+        assert two == 2 and hd == 64 and k.shape == q.shape and v.shape == q.shape
+        out = np.empty((2, N, H * 64), dtype=np.float32)
+        self._check(self.lib.b200tts_attention(self.handle, _ptr(q), _ptr(k), _ptr(v), H, N, _ptr(out)), "attention")
+        return out
 
     def conv1d(self, x, w, bias=None, dilation=1, groups=1, precision=F32):
         x, w = _f32(x), _f32(w)

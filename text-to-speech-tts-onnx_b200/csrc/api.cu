@@ -6,8 +6,10 @@
 #include <sstream>
 
 #include "aa_act.cuh"
+#include "attention_tc.cuh"
 #include "bigvgan.cuh"
 #include "engine.cuh"
+#include "f5.cuh"
 #include "layout.cuh"
 #include "rowgemm.cuh"
 #include "rowgemm_tc.cuh"
@@ -21,6 +23,7 @@ struct b200tts_engine {
 namespace b200tts {
 Engine::~Engine() {
   if (bigvgan) bigvgan_free(bigvgan);
+  if (f5) f5_free(f5);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 }  // namespace b200tts
@@ -159,6 +162,130 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
   });
 }
 
+int b200tts_f5_build(b200tts_engine* e) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    if (E.f5) { f5_free(E.f5); E.f5 = nullptr; }
+    E.f5 = f5_build(E);
+  });
+}
+
+int b200tts_f5_preprocess(b200tts_engine* e, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host, int n_text,
+                          int64_t max_duration, float* cat_mel_text_host, float* cat_mel_text_drop_host,
+                          int64_t* ref_signal_len) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_host && text_ids_host && cat_mel_text_host && cat_mel_text_drop_host && ref_signal_len, "f5_preprocess: null buffer");
+    B2_CHECK(L > 0 && n_text > 0 && max_duration > 0 && max_duration < (1 << 30), "f5_preprocess: bad sizes");
+    cudaStream_t s = E.stream;
+    DevBuf<int16_t> d_audio((size_t)L);
+    DevBuf<int> d_ids((size_t)n_text);
+    B2_CUDA(cudaMemcpyAsync(d_audio.p, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids.p, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    f5_preprocess(E, d_audio.p, L, d_ids.p, n_text, (int)max_duration);
+    const size_t nb = (size_t)max_duration * f5_cond_dim(E) * sizeof(float);
+    B2_CUDA(cudaMemcpyAsync(cat_mel_text_host, f5_cond(E), nb, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(cat_mel_text_drop_host, f5_cond_drop(E), nb, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *ref_signal_len = f5_ref_len(E);
+  });
+}
+
+int b200tts_f5_transformer(b200tts_engine* e, float* noise_host, const float* rope_cos_host, const float* rope_sin_host,
+                           const float* cat_mel_text_host, const float* cat_mel_text_drop_host, int N, int32_t* time_step,
+                           int n_steps, int precision) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(noise_host && rope_cos_host && rope_sin_host && cat_mel_text_host && cat_mel_text_drop_host && time_step, "f5_transformer: null buffer");
+    cudaStream_t s = E.stream;
+    f5_begin(E, N);
+    const size_t nc = (size_t)N * f5_cond_dim(E) * sizeof(float), nn = (size_t)N * f5_n_mels(E) * sizeof(float);
+    DevBuf<float> rc((size_t)N * 64), rs((size_t)N * 64);
+    B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_host, nn, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(f5_cond(E), cat_mel_text_host, nc, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(f5_cond_drop(E), cat_mel_text_drop_host, nc, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(rc.p, rope_cos_host, rc.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(rs.p, rope_sin_host, rs.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    f5_set_rope(E, rc.p, rs.p);
+    f5_prepare_cond(E);
+    f5_steps(E, *time_step, n_steps, precision);
+    B2_CUDA(cudaMemcpyAsync(noise_host, f5_noise(E), nn, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *time_step += n_steps;
+  });
+}
+
+int b200tts_f5_decode(b200tts_engine* e, const float* denoised_host, int N, int64_t ref_signal_len, int16_t* pcm_host,
+                      float* wave_host, int64_t* n_out) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(denoised_host && pcm_host && n_out, "f5_decode: null buffer");
+    B2_CHECK(N > 0 && ref_signal_len >= 0 && ref_signal_len < N, "f5_decode: ref_signal_len must be in [0, N)");
+    cudaStream_t s = E.stream;
+    const long ns = 256L * (N - ref_signal_len - 1);
+    DevBuf<float> d_mel((size_t)N * f5_n_mels(E)), d_wave;
+    DevBuf<int16_t> d_pcm((size_t)(ns > 0 ? ns : 1));
+    if (wave_host) d_wave.alloc((size_t)(ns > 0 ? ns : 1));
+    B2_CUDA(cudaMemcpyAsync(d_mel.p, denoised_host, d_mel.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    const long got = f5_decode(E, d_mel.p, N, (int)ref_signal_len, d_pcm.p, wave_host ? d_wave.p : nullptr);
+    B2_CHECK(got == ns, "f5_decode: unexpected output length");
+    if (ns > 0) {
+      B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+      if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    B2_CUDA(cudaStreamSynchronize(s));
+    *n_out = ns;
+  });
+}
+
+static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const int32_t* ids_dev, int n_text, int64_t N,
+                         const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev) {
+  cudaStream_t s = E.stream;
+  f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N);
+  B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  f5_prepare_cond(E);
+  f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
+  f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr);
+  if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
+                                 int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
+                                 int16_t* pcm_dev, float* mel_dev) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_dev && text_ids_dev && noise_dev && pcm_dev, "f5_synthesize_device: null buffer");
+    synth_device(E, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, pcm_dev, mel_dev);
+  });
+}
+
+int b200tts_f5_synthesize(b200tts_engine* e, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host, int n_text,
+                          int64_t max_duration, const float* noise_host, int precision, int n_steps, int16_t* pcm_host,
+                          int64_t* n_out, float* mel_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_host && text_ids_host && noise_host && pcm_host && n_out, "f5_synthesize: null buffer");
+    B2_CHECK(L > 0 && n_text > 0 && max_duration > 0 && max_duration < (1 << 30), "f5_synthesize: bad sizes");
+    cudaStream_t s = E.stream;
+    const int64_t N = max_duration, F = L / 256 + 1;
+    const long ns = 256L * (N - F - 1);
+    B2_CHECK(ns > 0, "f5_synthesize: max_duration leaves no frames to generate");
+    const int nm = f5_n_mels(E);
+    DevBuf<int16_t> d_audio((size_t)L), d_pcm((size_t)ns);
+    DevBuf<int> d_ids((size_t)n_text);
+    DevBuf<float> d_noise((size_t)N * nm), d_mel;
+    if (mel_host) d_mel.alloc((size_t)N * nm);
+    B2_CUDA(cudaMemcpyAsync(d_audio.p, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids.p, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_noise.p, noise_host, d_noise.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    synth_device(E, d_audio.p, L, d_ids.p, n_text, N, d_noise.p, precision, n_steps, d_pcm.p, mel_host ? d_mel.p : nullptr);
+    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel.p, d_mel.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *n_out = ns;
+  });
+}
+
 int b200tts_aa_activation(b200tts_engine* e, const float* x_host, int B, int C, int L, const float* alpha_log,
                           const float* beta_log, const float* taps12, int precise, int post, float* y_host) {
   return guarded([&] {
@@ -282,6 +409,38 @@ int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int 
     }
     batched_transpose(yt.p, y.p, B, (int)Lo, Cout, s);
     B2_CUDA(cudaMemcpyAsync(y_host, y.p, y.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
+                      float* out_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(q_host && k_host && v_host && out_host, "attention: null buffer");
+    B2_CHECK(H > 0 && N > 0, "attention: empty problem");
+    cudaStream_t s = E.stream;
+    const int D = H * 64, Np = (int)round_up(N, 8);
+    // host-side relayout into the engine's operand formats: qk [2][N][2D] (q | k), vT [2H][64][Np]
+    std::vector<float> qk((size_t)2 * N * 2 * D), vt((size_t)2 * H * 64 * Np, 0.f);
+    for (int b = 0; b < 2; ++b)
+      for (int h = 0; h < H; ++h)
+        for (int t = 0; t < N; ++t)
+          for (int d = 0; d < 64; ++d) {
+            const size_t src = (((size_t)b * H + h) * N + t) * 64 + d;
+            qk[((size_t)b * N + t) * 2 * D + h * 64 + d] = q_host[src];
+            qk[((size_t)b * N + t) * 2 * D + D + h * 64 + d] = k_host[src];
+            vt[(((size_t)b * H + h) * 64 + d) * Np + t] = v_host[src];
+          }
+    DevBuf<float> d_qk(qk.size()), d_vt(vt.size()), d_o32((size_t)2 * N * D);
+    DevBuf<__nv_bfloat16> qk16(qk.size()), vt16(vt.size()), o16((size_t)2 * N * D);
+    B2_CUDA(cudaMemcpyAsync(d_qk.p, qk.data(), qk.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_vt.p, vt.data(), vt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    cast_f32_to_bf16(d_qk.p, qk16.p, (long)qk.size(), s);
+    cast_f32_to_bf16(d_vt.p, vt16.p, (long)vt.size(), s);
+    attention_tc(qk16.p, vt16.p, Np, o16.p, N, H, s);
+    cast_bf16_to_f32(o16.p, d_o32.p, (long)2 * N * D, s);
+    B2_CUDA(cudaMemcpyAsync(out_host, d_o32.p, d_o32.n * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
   });
 }

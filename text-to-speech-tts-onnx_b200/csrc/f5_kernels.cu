@@ -1,0 +1,351 @@
+#include "f5_kernels.cuh"
+
+namespace b200tts {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// One warp per row, D <= 2048, D % 128 == 0. MODE 0: (1+a)*n + b ; MODE 1: a*n + b (affine LayerNorm)
+template <int MODE, typename OutT>
+__global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                      const float* __restrict__ b, OutT* __restrict__ out, int R, int D,
+                                                      float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)row * D);
+  const int nv = D >> 7;                      // float4 per lane
+  float4 v[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < nv) { v[i] = xr[lane + i * 32]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < nv) {
+      const int c = (lane + i * 32) * 4;
+      const float4 aa = __ldg(reinterpret_cast<const float4*>(a + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      float o[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      const float av[4] = {aa.x, aa.y, aa.z, aa.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = MODE == 0 ? o[k] * (1.0f + av[k]) + bv[k] : o[k] * av[k] + bv[k];
+      if constexpr (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long)row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (long)row * D + c) = pk;
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ b, float* __restrict__ out, int R, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (long)row * C;
+  float sq = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = xr[c]; sq += v * v; }
+  const float nrm = sqrtf(warp_sum(sq));
+  for (int c = lane; c < C; c += 32) out[(long)row * C + c] = __ldg(w + c) * xr[c] / nrm + __ldg(b + c);
+}
+
+__global__ void dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ out, int L, int C) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)L * C) return;
+  const int b = blockIdx.y;
+  const int t = (int)(i / C), c = (int)(i - (long)t * C);
+  const float* xb = x + (long)b * L * C;
+  float acc = __ldg(bias + c);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t + j - 3;
+    if (tt >= 0 && tt < L) acc = fmaf(__ldg(w + j * C + c), xb[(long)tt * C + c], acc);
+  }
+  out[(long)b * L * C + i] = acc;
+}
+
+// block = (32 cols, 8 row lanes); gx[c] = sqrt(sum_r x[r][c]^2)
+__global__ void __launch_bounds__(256) grn_colnorm_kernel(const float* __restrict__ x, float* __restrict__ gx, int R, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < R; r += 8) { const float v = x[(long)r * C + c]; s += v * v; }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    gx[c] = sqrtf(t);
+  }
+}
+__global__ void __launch_bounds__(256) grn_mean_kernel(const float* __restrict__ gx, float* __restrict__ mean_out, int C) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) s += gx[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    *mean_out = t / (float)C;
+  }
+}
+__global__ void grn_apply_kernel(float* __restrict__ x, const float* __restrict__ gx, const float* __restrict__ mean,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, long total, int C) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const float nx = gx[c] / (*mean + 1e-6f);
+  const float v = x[i];
+  x[i] = __ldg(gamma + c) * (v * nx) + __ldg(beta + c) + v;
+}
+
+__global__ void text_gather_kernel(const int* __restrict__ ids, const float* __restrict__ table, const float* __restrict__ pos,
+                                   float* __restrict__ out, int N, int D, int use_ids) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * D) return;
+  const int n = (int)(i / D), d = (int)(i - (long)n * D);
+  const int id = ids[n];
+  out[i] = id == 0 ? 0.f : table[(long)(use_ids ? id : 0) * D + d] + pos[(long)n * D + d];
+}
+__global__ void mask_rows_kernel(float* __restrict__ x, const int* __restrict__ ids, int N, int D) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * D) return;
+  if (ids[i / D] == 0) x[i] = 0.f;
+}
+__global__ void pad_ids_kernel(const int* __restrict__ text_ids, int n_text, int* __restrict__ out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = i < n_text ? text_ids[i] + 1 : 0;
+}
+__global__ void reflect_pad_kernel(const int16_t* __restrict__ a, float* __restrict__ out, long L, int pad) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L + 2 * pad) return;
+  long j = i - pad;
+  if (j < 0) j = -j;
+  if (j >= L) j = 2 * (L - 1) - j;
+  out[i] = (float)a[j] * (1.0f / 32768.0f);
+}
+__global__ void magnitude_kernel(const float* __restrict__ spec, int ld, float* __restrict__ mag, int ldm, int F, int bins) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)F * ldm) return;
+  const int f = (int)(i / ldm), c = (int)(i - (long)f * ldm);
+  float v = 0.f;
+  if (c < bins) {
+    const float re = spec[(long)f * ld + c], im = spec[(long)f * ld + bins + c];
+    v = sqrtf(re * re + im * im);
+  }
+  mag[i] = v;
+}
+__global__ void logmel_kernel(const float* __restrict__ mel, int F, float* __restrict__ dst, int ld, int col0, int N, int C) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * C) return;
+  const int n = (int)(i / C), c = (int)(i - (long)n * C);
+  dst[(long)n * ld + col0 + c] = n < F ? logf(fmaxf(mel[i], 1e-5f)) : 0.f;
+}
+__global__ void copy_cols_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst, int col0, int N, int C) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)N * C) return;
+  const int n = (int)(i / C), c = (int)(i - (long)n * C);
+  dst[(long)n * ld_dst + col0 + c] = src ? src[(long)n * ld_src + c] : 0.f;
+}
+__global__ void euler_kernel(float* __restrict__ noise, const float* __restrict__ pred, long n, float cfg, float dt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p0 = pred[i], p1 = pred[n + i];
+  noise[i] += (p0 + (p0 - p1) * cfg) * dt;
+}
+__global__ void istft_input_kernel(const float* __restrict__ head, float* __restrict__ out, int G, int bins, int ld) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)G * ld) return;
+  const int g = (int)(i / ld), c = (int)(i - (long)g * ld);
+  float v = 0.f;
+  if (c < 2 * bins) {
+    const int k = c < bins ? c : c - bins;
+    const float mag = fminf(expf(head[(long)g * ld + k]), 100.0f);
+    const float ph = head[(long)g * ld + bins + k];
+    v = c < bins ? mag * cosf(ph) : mag * sinf(ph);
+  }
+  out[i] = v;
+}
+__global__ void overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ wsi, int G, int nfft, int hop,
+                                   int16_t* __restrict__ pcm, float* __restrict__ wave) {
+  const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n_out = (long)hop * (G - 1);
+  if (o >= n_out) return;
+  const long tp = o + nfft / 2;
+  long f_lo = (tp - nfft + hop) / hop;        // ceil((tp - nfft + 1) / hop) for tp - nfft + 1 > 0
+  if (tp - nfft + 1 <= 0) f_lo = 0;
+  long f_hi = tp / hop;
+  if (f_hi > G - 1) f_hi = G - 1;
+  float acc = 0.f;
+  for (long f = f_lo; f <= f_hi; ++f) acc += frames[f * nfft + (tp - f * hop)];
+  float v = acc * wsi[tp];
+  v = fminf(fmaxf(v, -1.0f), 1.0f) * 32767.0f;
+  pcm[o] = (int16_t)v;
+  if (wave) wave[o] = v;
+}
+
+// one thread per (row, head, pair): rope q and k (interleaved pairs), scatter kT and v
+__global__ void rope_split_kernel(float* __restrict__ qkv, const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                  float* __restrict__ kT, float* __restrict__ v, int N, int H, int hd, int ldk) {
+  const int D = H * hd;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = 2L * N * (D / 2);
+  if (i >= total) return;
+  const int pair = (int)(i % (D / 2));
+  const long row = i / (D / 2);
+  const int b = (int)(row / N), t = (int)(row % N);
+  const int col = pair * 2, h = col / hd, d = col % hd;
+  float* r = qkv + row * 3 * D;
+  const float c0 = cosT[(long)t * hd + d], c1 = cosT[(long)t * hd + d + 1];
+  const float s0 = sinT[(long)t * hd + d], s1 = sinT[(long)t * hd + d + 1];
+  const float q0 = r[col], q1 = r[col + 1];
+  r[col] = q0 * c0 + (-q1) * s0;             // x*cos + rotate_half(x)*sin with (x0,x1) -> (-x1, x0)
+  r[col + 1] = q1 * c1 + q0 * s1;
+  const float k0 = r[D + col], k1 = r[D + col + 1];
+  const long kb = ((long)(b * H + h) * hd + d) * ldk + t;
+  kT[kb] = k0 * c0 + (-k1) * s0;
+  kT[kb + ldk] = k1 * c1 + k0 * s1;
+  const long vb = ((long)(b * H + h) * ldk + t) * hd + d;      // v rows padded to ldk like kT's columns
+  v[vb] = r[2 * D + col];
+  v[vb + 1] = r[2 * D + col + 1];
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long rows, int n, int ld) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* xr = x + row * ld;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, xr[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < n; c += 32) { const float e = expf(xr[c] - m); xr[c] = e; s += e; }
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  for (int c = lane; c < ld; c += 32) xr[c] = c < n ? xr[c] * inv : 0.f;
+}
+
+__global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float v = x[i]; y[i] = v / (1.0f + expf(-v)); }
+}
+
+inline dim3 g1(long n, int bs = 256) { return dim3(ceil_div(n, bs)); }
+
+}  // namespace
+
+#define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
+
+void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s) {
+  B2_CHECK(D % 128 == 0 && D <= 2048, "ln_modulate: D must be a multiple of 128, <= 2048");
+  if (out_bf16) rownorm_kernel<0, __nv_bfloat16><<<ceil_div(R, 8), 256, 0, s>>>(x, scale, shift, (__nv_bfloat16*)out, R, D, 1e-6f);
+  else rownorm_kernel<0, float><<<ceil_div(R, 8), 256, 0, s>>>(x, scale, shift, (float*)out, R, D, 1e-6f);
+  LAUNCHED();
+}
+void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s) {
+  B2_CHECK(D % 128 == 0 && D <= 2048, "layernorm_affine: D must be a multiple of 128, <= 2048");
+  rownorm_kernel<1, float><<<ceil_div(R, 8), 256, 0, s>>>(x, w, b, out, R, D, eps);
+  LAUNCHED();
+}
+void l2_norm_affine(const float* x, const float* w, const float* b, float* out, int R, int C, cudaStream_t s) {
+  l2norm_kernel<<<ceil_div(R, 8), 256, 0, s>>>(x, w, b, out, R, C);
+  LAUNCHED();
+}
+void dwconv7(const float* x, const float* w, const float* bias, float* out, int B, int L, int C, cudaStream_t s) {
+  dim3 grid(ceil_div((long)L * C, 256), B);
+  dwconv7_kernel<<<grid, 256, 0, s>>>(x, w, bias, out, L, C);
+  LAUNCHED();
+}
+void grn_inplace(float* x, const float* gamma, const float* beta, float* scratch, int R, int C, cudaStream_t s) {
+  grn_colnorm_kernel<<<ceil_div(C, 32), dim3(32, 8), 0, s>>>(x, scratch, R, C);
+  LAUNCHED();
+  grn_mean_kernel<<<1, 256, 0, s>>>(scratch, scratch + C, C);
+  LAUNCHED();
+  grn_apply_kernel<<<g1((long)R * C), 256, 0, s>>>(x, scratch, scratch + C, gamma, beta, (long)R * C, C);
+  LAUNCHED();
+}
+void text_embed_gather(const int* ids, const float* table, const float* pos, float* out, int N, int D, int use_ids, cudaStream_t s) {
+  text_gather_kernel<<<g1((long)N * D), 256, 0, s>>>(ids, table, pos, out, N, D, use_ids);
+  LAUNCHED();
+}
+void mask_rows(float* x, const int* ids, int N, int D, cudaStream_t s) {
+  mask_rows_kernel<<<g1((long)N * D), 256, 0, s>>>(x, ids, N, D);
+  LAUNCHED();
+}
+void pad_text_ids(const int* text_ids, int n_text, int* ids_out, int N, cudaStream_t s) {
+  pad_ids_kernel<<<g1(N), 256, 0, s>>>(text_ids, n_text, ids_out, N);
+  LAUNCHED();
+}
+void audio_reflect_pad(const int16_t* audio, float* out, long L, int pad, cudaStream_t s) {
+  B2_CHECK(L > pad, "audio shorter than the reflect padding");
+  reflect_pad_kernel<<<g1(L + 2 * pad), 256, 0, s>>>(audio, out, L, pad);
+  LAUNCHED();
+}
+void stft_magnitude(const float* spec, int ld, float* mag, int ldm, int F, int bins, cudaStream_t s) {
+  magnitude_kernel<<<g1((long)F * ldm), 256, 0, s>>>(spec, ld, mag, ldm, F, bins);
+  LAUNCHED();
+}
+void logmel_into(const float* mel, int F, float* dst, int ld_dst, int col0, int N, int C, cudaStream_t s) {
+  logmel_kernel<<<g1((long)N * C), 256, 0, s>>>(mel, F, dst, ld_dst, col0, N, C);
+  LAUNCHED();
+}
+void copy_cols(const float* src, int ld_src, float* dst, int ld_dst, int col0, int N, int C, cudaStream_t s) {
+  copy_cols_kernel<<<g1((long)N * C), 256, 0, s>>>(src, ld_src, dst, ld_dst, col0, N, C);
+  LAUNCHED();
+}
+void euler_cfg_update(float* noise, const float* pred, long n, float cfg, float dt, cudaStream_t s) {
+  euler_kernel<<<g1(n), 256, 0, s>>>(noise, pred, n, cfg, dt);
+  LAUNCHED();
+}
+void istft_input(const float* head, float* out, int G, int bins, int ld, cudaStream_t s) {
+  istft_input_kernel<<<g1((long)G * ld), 256, 0, s>>>(head, out, G, bins, ld);
+  LAUNCHED();
+}
+void istft_overlap_add(const float* frames, const float* wsi, int G, int nfft, int hop, int16_t* pcm, float* wave, cudaStream_t s) {
+  if (G <= 1) return;
+  overlap_add_kernel<<<g1((long)hop * (G - 1)), 256, 0, s>>>(frames, wsi, G, nfft, hop, pcm, wave);
+  LAUNCHED();
+}
+void rope_split_f32(float* qkv, const float* cos, const float* sin, float* kT, float* v, int N, int H, int hd, int ldk, cudaStream_t s) {
+  rope_split_kernel<<<g1(2L * N * (H * hd / 2)), 256, 0, s>>>(qkv, cos, sin, kT, v, N, H, hd, ldk);
+  LAUNCHED();
+}
+void softmax_rows(float* x, long rows, int n, int ld, cudaStream_t s) {
+  softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, n, ld);
+  LAUNCHED();
+}
+void silu(const float* x, float* y, long n, cudaStream_t s) {
+  silu_kernel<<<g1(n), 256, 0, s>>>(x, y, n);
+  LAUNCHED();
+}
+
+}  // namespace b200tts

@@ -43,6 +43,14 @@ struct RowGemm {
   int accumulate = 0;
   float scale = 1.0f;
   int act = ACT_NONE;
+  // tensor-core path only: fused q/k/v epilogue of the DiT attention (F5 modules.py:459-466).
+  //   columns [0, rope_cols): interleaved-pair RoPE with tables [rope_rows][64] at t = row % rope_rows
+  //   columns >= vt_col0    : written transposed, vt_out[((row / rope_rows) * heads + h) * 64 + d][t] (row stride vt_ld)
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_cols = 0, rope_rows = 1;
+  __nv_bfloat16* vt_out = nullptr;
+  int vt_col0 = 0, vt_ld = 0, vt_heads = 0;
 };
 
 // SIMT fp32 implementation (rowgemm_f32.cu). Requires Cin % 4 == 0, N % 4 == 0, ldx/ldw/ldo % 4 == 0.

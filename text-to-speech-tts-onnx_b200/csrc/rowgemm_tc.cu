@@ -15,6 +15,8 @@
 
 #include <mutex>
 
+#include "tc_ptx.cuh"
+
 namespace b200tts {
 
 namespace {
@@ -26,89 +28,15 @@ constexpr int NTHREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int MAX_STAGES = 8;
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_out, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp field layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row
-// groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
+using namespace tc;
 
 struct TcArgs {
   int Cin, N, taps, dil, center, groups, M;
   int BN, stages, kchunks;      // kchunks = ceil(Cin / 64)
   void* out; long o_bstride; int ldo; long o_shift; long o_limit; int out_bf16;
   const float* bias; const float* gate; const float* res; int accumulate; float scale; int act;
+  const float* rope_cos; const float* rope_sin; int rope_cols, rope_rows;
+  __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
 };
 
 __global__ void __launch_bounds__(NTHREADS) rowgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -214,6 +142,25 @@ __global__ void __launch_bounds__(NTHREADS) rowgemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
         }
+        if (a.rope_cos != nullptr) {
+          const int tt = t % a.rope_rows;
+          if (nn < a.rope_cols) {            // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+            const int d = nn & 63;
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
+            const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
+            const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
+            v[0] = x0 * cc.x - x1 * ss.x; v[1] = x1 * cc.y + x0 * ss.y;
+            v[2] = x2 * cc.z - x3 * ss.z; v[3] = x3 * cc.w + x2 * ss.w;
+          }
+          if (a.vt_out != nullptr && nn >= a.vt_col0) {
+            const int cv = nn - a.vt_col0;
+            const int hh = cv >> 6, d = cv & 63;
+            __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
+            continue;
+          }
+        }
         if (a.gate) {
           const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gate + gn + v4 * 4));
           v[0] *= gg.x; v[1] *= gg.y; v[2] *= gg.z; v[3] *= gg.w;
@@ -275,9 +222,11 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+}  // namespace
+
 // bf16 3-D map: dims {d0 (contiguous), d1, d2}, strides in elements {ld1, ld2}, box {64, box1, 1}, 128B swizzle
-void encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
-                uint64_t ld2, uint32_t box1) {
+void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1,
+                   uint64_t ld2, uint32_t box1) {
   B2_CHECK(((uintptr_t)base & 15) == 0, "TMA base must be 16-byte aligned");
   B2_CHECK((ld1 * 2) % 16 == 0 && (ld2 * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -289,6 +238,8 @@ void encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, ui
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
+
+namespace {
 
 int pick_bn(int N) {
   if (N % 128 == 0) return 128;
@@ -312,6 +263,11 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
   }
 }
 
+__global__ void uncast_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
 __global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int C, int ldo) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ldo) return;
@@ -329,6 +285,12 @@ void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t 
   B2_LAUNCH_CHECK(); count_launch();
 }
 
+void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s) {
+  if (n <= 0) return;
+  uncast_kernel<<<ceil_div(n, 256), 256, 0, s>>>(in, out, n);
+  B2_LAUNCH_CHECK(); count_launch();
+}
+
 void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s) {
   if (rows <= 0) return;
   cast_pad_kernel<<<ceil_div(rows * ldo, 256), 256, 0, s>>>(in, out, rows, C, ldo);
@@ -342,7 +304,7 @@ void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps,
   tw.w.alloc((size_t)rows * tw.ldc);
   cast_pad_f32_to_bf16(w_gjnc, tw.w.p, rows, Cin, tw.ldc, s);
   tw.BN = pick_bn(N);
-  encode_map(&tw.map, tw.w.p, (uint64_t)Cin, (uint64_t)N, (uint64_t)groups * taps, (uint64_t)tw.ldc,
+  tc_encode_map(&tw.map, tw.w.p, (uint64_t)Cin, (uint64_t)N, (uint64_t)groups * taps, (uint64_t)tw.ldc,
              (uint64_t)N * tw.ldc, (uint32_t)tw.BN);
   tw.ready = true;
 }
@@ -356,7 +318,7 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   B2_CHECK(p.M > 0 && p.B > 0, "rowgemm_tc: empty problem");
 
   CUtensorMap map_a;
-  encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
+  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
              (uint64_t)p.x_bstride, (uint32_t)BM);
 
   TcArgs a;
@@ -366,6 +328,10 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   a.o_limit = p.o_limit ? p.o_limit : (long)p.M * p.ldo;
   a.out_bf16 = p.out_bf16;
   a.bias = p.bias; a.gate = p.gate; a.res = p.res; a.accumulate = p.accumulate; a.scale = p.scale; a.act = p.act;
+  a.rope_cos = p.rope_cos; a.rope_sin = p.rope_sin; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
+  a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
+  B2_CHECK(p.rope_cos == nullptr || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.groups == 1 && p.B == 1),
+           "rowgemm_tc: malformed rope epilogue");
 
   const int stage_bytes = A_STAGE_BYTES + w.BN * BK * 2;
   // keep <= ~110 KB so that two CTAs fit one SM (227 KB): the co-resident CTA hides this one's epilogue

@@ -23,7 +23,12 @@ void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps,
 // A operand: bf16, rows of p.ldx elements (ldx % 8 == 0). Output fp32 or bf16 (p.out_bf16).
 void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream);
 
+// bf16 3-D TMA map: dims {d0 (contiguous), d1, d2}, element strides {ld1, ld2}, box {64, box1, 1}, SWIZZLE_128B, zero OOB fill
+void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2,
+                   uint32_t box1);
+
 void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s);
+void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s);
 // (rows, C) fp32 -> (rows, ldo) bf16 with zero-filled padding columns
 void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s);
 

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from . import capi, weights
-from .config import BIGVGAN
+from .config import BIGVGAN, F5
 
 _engines = {}
 _checkpoints = {}
@@ -109,7 +109,114 @@ class _BigVGANGraph(_Graph):
         return [self.engine.bigvgan_run(mel, precision=self.precision, hop=self.cfg.hop)]
 
 
-_GRAPHS = {"bigvgan": _BigVGANGraph}
+_f5_ready = {}
+
+
+def load_f5(engine, dit_state=None, vocos_state=None, cfg=F5):
+    """Load + build the three F5 graphs' weights once per engine (the sessions share them)."""
+    if _f5_ready.get(id(engine)):
+        return
+    dit_state = dit_state if dit_state is not None else _checkpoints.get("dit")
+    vocos_state = vocos_state if vocos_state is not None else _checkpoints.get("vocos")
+    if dit_state is None or vocos_state is None:
+        raise RuntimeError("no F5 checkpoint registered: call session.register_checkpoint('dit', ...) and ('vocos', ...)")
+    engine.load_state("dit", weights.dit_engine_tensors(dit_state, cfg))
+    engine.load_state("vocos", weights.vocos_engine_tensors(vocos_state, cfg))
+    engine.load_state("f5", weights.f5_export_constants(dit_state, cfg))
+    engine.f5_build()
+    _f5_ready[id(engine)] = True
+
+
+def _rope_rows(cfg, N):
+    c = weights.f5_rope_rows(cfg)
+    return c[0][:N], c[1][:N]
+
+
+class _F5PreprocessGraph(_Graph):
+    """F5_TTS/Export_F5.py:117-141, I/O names :294-306."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine, self.cfg = engine, F5
+        load_f5(engine)
+        f = "tensor(float)"
+        self.inputs = (NodeArg("audio", "tensor(int16)", [1, 1, "audio_len"]), NodeArg("text_ids", "tensor(int32)", [1, "text_ids_len"]),
+                       NodeArg("max_duration", "tensor(int64)", [1]))
+        names = ["noise", "rope_cos_q", "rope_sin_q", "rope_cos_k", "rope_sin_k", "cat_mel_text", "cat_mel_text_drop", "ref_signal_len"]
+        self.outputs = tuple(NodeArg(n, "tensor(int64)" if n == "ref_signal_len" else f, None) for n in names)
+
+    def run(self, feed):
+        cfg = self.cfg
+        audio = _as_numpy(feed["audio"])
+        text_ids = _as_numpy(feed["text_ids"])
+        N = int(np.asarray(_as_numpy(feed["max_duration"])).reshape(-1)[0])
+        if audio.dtype != np.int16 or audio.ndim != 3:
+            raise ValueError("audio must be int16 (1, 1, L)")
+        if not (0 < N <= cfg.max_frames):
+            raise ValueError(f"max_duration must be in [1, {cfg.max_frames}]")
+        cond, cond_drop, ref_len = self.engine.f5_preprocess(audio, text_ids, N, cfg.n_mels + cfg.text_dim)
+        # noise = randn_like(zeros) (Export_F5.py:131): ORT's RandomNormalLike stream cannot be reproduced outside ORT;
+        # a seeded numpy draw stands in (set_seed), and parity runs inject their own noise at graph B
+        rng = np.random.default_rng(_seed[0])
+        noise = rng.standard_normal((1, N, cfg.n_mels), dtype=np.float32)
+        cos, sin = _rope_rows(cfg, N)
+        rope_cos_q = np.broadcast_to(cos[None, None], (2, cfg.heads, N, cfg.head_dim))
+        rope_sin_q = np.broadcast_to(sin[None, None], (2, cfg.heads, N, cfg.head_dim))
+        return [noise, rope_cos_q, rope_sin_q, rope_cos_q.transpose(0, 1, 3, 2), rope_sin_q.transpose(0, 1, 3, 2),
+                cond, cond_drop, np.array(ref_len, dtype=np.int64)]
+
+
+class _F5TransformerGraph(_Graph):
+    """F5_TTS/Export_F5.py:167-182 (FUSE_NFE = 1), I/O names :354-365. ``run_all_steps`` is the fused fast path;
+    a loop of ``run`` gives the same numbers (same kernels, same order)."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine, self.cfg, self.precision = engine, F5, precision
+        load_f5(engine)
+        f = "tensor(float)"
+        names = ["noise", "rope_cos_q", "rope_sin_q", "rope_cos_k", "rope_sin_k", "cat_mel_text", "cat_mel_text_drop"]
+        self.inputs = tuple(NodeArg(n, f, None) for n in names) + (NodeArg("time_step", "tensor(int32)", [1]),)
+        self.outputs = (NodeArg("denoised", f, [1, "max_duration", self.cfg.n_mels]), NodeArg("time_step", "tensor(int32)", [1]))
+
+    def _step(self, feed, n_steps):
+        noise = _as_numpy(feed["noise"]).astype(np.float32)
+        cq, sq = _as_numpy(feed["rope_cos_q"]), _as_numpy(feed["rope_sin_q"])
+        if cq.ndim != 4 or cq.shape[-1] != self.cfg.head_dim or cq.shape[2] != noise.shape[1]:
+            raise ValueError("rope_cos_q must be (2, heads, max_duration, head_dim)")
+        ts = int(np.asarray(_as_numpy(feed["time_step"])).reshape(-1)[0])
+        out, ts2 = self.engine.f5_transformer(noise, np.ascontiguousarray(cq[0, 0], dtype=np.float32),
+                                              np.ascontiguousarray(sq[0, 0], dtype=np.float32),
+                                              _as_numpy(feed["cat_mel_text"]), _as_numpy(feed["cat_mel_text_drop"]), ts,
+                                              n_steps=n_steps, precision=self.precision)
+        return [out, np.array([ts2], dtype=np.int32)]
+
+    def run(self, feed):
+        return self._step(feed, 1)
+
+    def run_all_steps(self, feed):
+        ts = int(np.asarray(_as_numpy(feed["time_step"])).reshape(-1)[0])
+        return self._step(feed, self.cfg.nfe - 1 - ts)
+
+
+class _F5DecodeGraph(_Graph):
+    """F5_TTS/Export_F5.py:193-203, I/O names :409-414."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine, self.cfg = engine, F5
+        load_f5(engine)
+        self.inputs = (NodeArg("denoised", "tensor(float)", [1, "max_duration", self.cfg.n_mels]),
+                       NodeArg("ref_signal_len", "tensor(int64)", []))
+        self.outputs = (NodeArg("output_audio", "tensor(int16)", [1, 1, "generated_len"]),)
+
+    def run(self, feed):
+        d = _as_numpy(feed["denoised"]).astype(np.float32)
+        ref = int(np.asarray(_as_numpy(feed["ref_signal_len"])).reshape(-1)[0])
+        if d.ndim != 3 or d.shape[2] != self.cfg.n_mels:
+            raise ValueError("denoised must be (1, max_duration, n_mels)")
+        return [self.engine.f5_decode(d, ref, hop=self.cfg.hop)]
+
+
+_GRAPHS = {"bigvgan": _BigVGANGraph, "f5_preprocess": _F5PreprocessGraph, "f5_transformer": _F5TransformerGraph,
+           "f5_decode": _F5DecodeGraph}
 
 
 def _kind_of(path: str) -> str:
@@ -154,3 +261,7 @@ class InferenceSession:
 
     def run_with_ort_values(self, output_names, input_feed, run_options=None):
         return [OrtValue(o) for o in self.run(output_names, input_feed)]
+
+    def run_all_steps(self, input_feed):
+        """F5_Transformer only: all remaining NFE steps in one call, intermediates resident in HBM."""
+        return self._graph.run_all_steps(input_feed)
