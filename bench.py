@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- the driver's measurement contract for the B200 TTS hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bigvgan|f5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bigvgan|f5|pipeline]
 
-One "step" = one pass of the hot path over one batch of synthetic input. Default workload (N = 1): BASELINE.json
-configs[1], BigVGAN-v2 24khz_100band_256x on mels (8, 100, 512), tensor-core (bf16 operand / fp32 accumulate) path.
-Each rank runs the same per-GPU batch (utterances shard with no data-path collective: weak scaling); NCCL is used
-once, to broadcast the weights from rank 0 at load. Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of synthetic input.
+  bigvgan  (default) BASELINE.json configs[1]: BigVGAN-v2 24khz_100band_256x, mels (8,100,512) -> int16 PCM.
+  f5       configs[2]: F5-TTS NFE=32 (31 Euler steps), 6 s reference / 150 text ids, N = 1126, preprocess (STFT/mel/text
+           embed) + DiT loop + Vocos/ISTFT decode, one utterance per step.
+  pipeline configs[3] per-GPU share: U utterances of config-3 shape, each F5 (mel) then BigVGAN on the generated frames.
+The default run times `bigvgan` as the headline line and attaches a short `f5` measurement under the key "f5".
+Each rank runs the same per-GPU batch (utterances shard with no data-path collective: weak scaling); NCCL is used once,
+to broadcast the weights from rank 0 at load. Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -20,11 +24,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-# algorithmic work per mel frame (DESIGN.md "Work model")
-BIGVGAN_RESCONV_MFLOP_PER_FRAME = 1746.47      # the 108 dilated resblock convs
-BIGVGAN_TOTAL_MFLOP_PER_FRAME = 1804.0         # + conv_pre, upsamplers, conv_post
-BIGVGAN_AA_ELEMS_PER_FRAME = 18 * 2 * 33792 / 6.0 * 0 + 0  # placeholder, computed below
 
 
 def peaks():
@@ -71,9 +70,11 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------------
+# work models (DESIGN.md "Work model")
+# ------------------------------------------------------------------------------------------------------
 def bigvgan_work(cfg, B, T):
-    """Algorithmic FLOPs / bytes of one step (B mels of T frames)."""
-    frames = B * T
+    """Algorithmic FLOPs / elements of one BigVGAN pass over B mels of T frames."""
     L, C = T, cfg.upsample_initial_channel
     flops_res = flops_up = 0.0
     aa_elems = 0
@@ -87,45 +88,309 @@ def bigvgan_work(cfg, B, T):
     flops_pre = 2.0 * cfg.num_mels * cfg.upsample_initial_channel * 7 * T
     flops_post = 2.0 * C * 7 * (L + 30)
     aa_elems += C * (L + 30)
-    return {"frames": frames, "flops_resconv": B * flops_res, "flops_total": B * (flops_res + flops_up + flops_pre + flops_post),
+    return {"frames": B * T, "flops_resconv": B * flops_res, "flops_total": B * (flops_res + flops_up + flops_pre + flops_post),
             "aa_elems": B * aa_elems, "audio_s": B * cfg.out_samples(T) / cfg.sample_rate}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (the oracle restatement of its PyTorch modules -- onnxruntime is
-    not installable offline) on the host cores, bounded sample of the same workload."""
-    if rank != 0:
-        return
+def f5_work(cfg, N, ref_len):
+    """Algorithmic FLOPs of the DiT loop for one utterance of N frames (both CFG rows)."""
+    D, FF = cfg.dim, cfg.dim * cfg.ff_mult
+    per_tok_layer_gemm = 2.0 * (3 * D * D + D * D + 2 * D * FF)         # qkv, out, ff1, ff2
+    per_tok_layer_attn = 4.0 * D * N                                    # QK^T and PV over all heads
+    gc = D // cfg.convpos_groups
+    per_tok_embed = 2.0 * cfg.n_mels * D + 2 * 2.0 * gc * cfg.convpos_kernel * D + 2.0 * D * cfg.n_mels
+    per_tok = cfg.depth * (per_tok_layer_gemm + per_tok_layer_attn) + per_tok_embed
+    steps = cfg.nfe - 1
+    G = N - ref_len
+    return {"frames": G, "flops_step": 2 * N * per_tok, "flops_gemm_step": 2 * N * cfg.depth * per_tok_layer_gemm,
+            "flops_attn_step": 2 * N * cfg.depth * per_tok_layer_attn, "flops_total": steps * 2 * N * per_tok,
+            "steps": steps, "audio_s": cfg.hop * (G - 1) / cfg.sample_rate}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU path (oracle restatement of its PyTorch modules; ORT is not installable
+# offline -- BASELINE.md section 2), all host threads, bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------
+def cpu_bigvgan(T, reps, cores):
     import torch
     import b200tts  # noqa: F401
     from b200tts import config, synth
     from oracle import bigvgan_ref
-    cfg = config.BIGVGAN
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B, T = 1, args.frames                      # sample: ONE mel of the (8,100,512) batch per step
+    cfg = config.BIGVGAN
     sd = synth.bigvgan_state(1234)
-    mel = synth.bigvgan_mel(100, B, T)
-    for _ in range(args.warmup):
-        bigvgan_ref.bigvgan_pcm(mel, sd, cfg)
+    mel = synth.bigvgan_mel(100, 1, T)
+    bigvgan_ref.bigvgan_pcm(mel[:, :, :32], sd, cfg)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(reps):
         bigvgan_ref.bigvgan_pcm(mel, sd, cfg)
-    dt = time.perf_counter() - t0
-    v = B * T * args.steps / dt
-    line = {
-        "impl": "reference", "metric": "mel_frames_per_s", "value": v, "unit": "mel-frames/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BigVGAN-v2 24khz_100band_256x, mels ({args.batch},100,{T}) [configs[1]]; "
-                               f"each reference step = 1 mel of that batch", "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-                         "sample": f"1 mel (1,100,{T}) per step, torch-CPU fp32 eager restatement of the reference modules "
-                                   f"(stand-in for ORT CPUExecutionProvider)"},
-        "e2e": {"value": v, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rtf": dt / args.steps / (B * cfg.out_samples(T) / cfg.sample_rate),
-    }
+    return (time.perf_counter() - t0) / reps
+
+
+def cpu_f5(N_audio, n_text, dit_steps, cores):
+    """Times graph A, `dit_steps` DiT steps and graph C of the oracle; returns seconds per part."""
+    import torch
+    import b200tts  # noqa: F401
+    from b200tts import config, synth
+    from oracle import f5_ref as R
+    torch.set_num_threads(cores)
+    cfg = config.F5
+    dsd, vsd = synth.f5_dit_state(4321), synth.vocos_state(2468)
+    audio, text_ids, maxd, noise = synth.f5_inputs(1, N_audio, n_text)
+    with torch.inference_mode():
+        sd = R.prescale_qk(dsd, cfg)
+        tables = R.time_tables(sd, cfg)
+        t0 = time.perf_counter()
+        x, cq, sq, _, _, cond, cond_drop, ref_len = R.f5_preprocess(audio, text_ids, maxd, sd, cfg, noise)
+        t_pre = time.perf_counter() - t0
+        cos, sin = cq[0, 0], sq[0, 0]
+        ts = 0
+        t0 = time.perf_counter()
+        for _ in range(dit_steps):
+            x, ts = R.f5_transformer_step(sd, x, cond, cond_drop, ts, tables, cfg, cos, sin)
+        t_step = (time.perf_counter() - t0) / max(dit_steps, 1)
+        fv = R.fold_vocos(vsd, cfg)
+        t0 = time.perf_counter()
+        R.f5_decode(x, ref_len, fv, cfg)
+        t_dec = time.perf_counter() - t0
+    return {"pre_s": t_pre, "step_s": t_step, "decode_s": t_dec, "N": int(maxd[0]), "ref_len": int(ref_len)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import b200tts  # noqa: F401
+    from b200tts import config
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 3))
+    if args.workload == "bigvgan":
+        cfg = config.BIGVGAN
+        T = args.frames
+        dt = cpu_bigvgan(T, steps, cores)
+        v = T / dt
+        line = {"metric": "mel_frames_per_s", "value": v, "unit": "mel-frames/s", "ms_per_step": 1e3 * dt, "dtype": "f32",
+                "config": {"workload": f"BigVGAN-v2 24khz_100band_256x, mels ({args.batch},100,{T}) [BASELINE.json configs[1]]; "
+                                       f"each reference step = 1 mel of that batch", "parallelism": "cpu"},
+                "rtf": dt / (cfg.out_samples(T) / cfg.sample_rate),
+                "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} x 1 mel (1,100,{T}), torch-CPU fp32 eager restatement of the reference "
+                                           "modules (stand-in for ORT CPUExecutionProvider, not installable offline)"}}
+    else:
+        cfg = config.F5
+        r = cpu_f5(args.audio_len, args.n_text, steps, cores)
+        G = r["N"] - r["ref_len"]
+        total = r["pre_s"] + (cfg.nfe - 1) * r["step_s"] + r["decode_s"]
+        if args.workload == "pipeline":
+            tv = cpu_bigvgan(G, 1, cores)
+            total += tv
+        v = G / total
+        line = {"metric": "mel_frames_per_s", "value": v, "unit": "mel-frames/s", "ms_per_step": 1e3 * total, "dtype": "f32",
+                "config": {"workload": f"F5-TTS NFE={cfg.nfe} N={r['N']} (ref {r['ref_len']} frames)"
+                                       + (" + BigVGAN" if args.workload == "pipeline" else " + Vocos/ISTFT")
+                                       + " [BASELINE.json configs[2]]; one utterance", "parallelism": "cpu"},
+                "rtf": total / (cfg.hop * (G - 1) / cfg.sample_rate),
+                "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"graph A once, {steps} of {cfg.nfe - 1} DiT steps (x{cfg.nfe - 1} extrapolated), graph C once; "
+                                           "torch-CPU fp32 eager restatement of the reference modules", "parts_s": r}}
+    line.update({"impl": "reference", "n_gpus": world, "steps": steps, "warmup": 1, "higher_is_better": True, "scaling": "weak",
+                 "vs_baseline": None, "data": "synthetic",
+                 "e2e": {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+class Harness:
+    def __init__(self, torch, dist, stream, world):
+        self.torch, self.dist, self.stream, self.world = torch, dist, stream, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        with torch.cuda.stream(self.stream):
+            ev0.record(self.stream)
+            for _ in range(steps):
+                fn()
+            ev1.record(self.stream)
+        self.barrier()
+        ms = ev0.elapsed_time(ev1)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+
+def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
+    torch = H.torch
+    from b200tts import capi, config, synth
+    cfg = config.BIGVGAN
+    n_out = cfg.out_samples(T)
+    work = bigvgan_work(cfg, B, T)
+    mel_host = torch.from_numpy(synth.bigvgan_mel(100 + rank, B, T)).pin_memory()
+    pcm_host = torch.empty((B, 1, n_out), dtype=torch.int16).pin_memory()
+    mel_dev = mel_host.cuda(non_blocking=True)
+    pcm_dev = torch.empty((B, 1, n_out), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_device():
+        eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
+
+    def step_e2e():
+        mel_dev.copy_(mel_host, non_blocking=True)
+        eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
+        pcm_host.copy_(pcm_dev, non_blocking=True)
+
+    with torch.cuda.stream(H.stream):
+        for _ in range(warmup):
+            step_device()
+            step_e2e()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    ms = H.timed(step_device, steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = H.timed(step_e2e, steps)
+    eng.profile_begin()
+    with torch.cuda.stream(H.stream):
+        step_device()
+    prof = eng.profile_end()
+    pk = peaks()
+    frames = work["frames"] * H.world * steps
+    res = {
+        "value": frames / (ms / 1e3), "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / work["audio_s"],
+        "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),
+                "d2h_bytes_per_step": int(pcm_host.numel() * 2), "ms_per_step": ms_e2e / steps,
+                "rtf": (ms_e2e / 1e3 / steps) / work["audio_s"]},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        "workload": f"BigVGAN-v2 24khz_100band_256x, mels ({B},100,{T}) per GPU -> int16 PCM ({B},1,{n_out}) [BASELINE.json configs[1]]",
+    }
+    def _sum(prefix):
+        sel = [v for k, v in prof.items() if k.startswith(prefix)]
+        return {"launches": sum(v["launches"] for v in sel), "ms": sum(v["ms"] for v in sel)}
+    conv, aa = _sum("bigvgan.resconv"), _sum("bigvgan.aa_snake.")
+    if conv["ms"] > 0:
+        ach = work["flops_resconv"] / (conv["ms"] / 1e3) / 1e12
+        kern = "rowgemm_tc_kernel (108 resblock convs)" if prec == capi.BF16 else "rowgemm_f32_kernel (SIMT parity engine)"
+        res["roofline"] = {"bound": "tensor", "kernel": kern, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                           "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                           "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                           "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
+                           "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
+    if aa["ms"] > 0:
+        per_elem = 4.0 if prec == capi.BF16 else 8.0          # bf16 in + bf16 out on the fast path
+        gbs = work["aa_elems"] * per_elem / (aa["ms"] / 1e3) / 1e9
+        res["roofline_hbm"] = {"bound": "hbm", "kernel": "aa_snake_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": gbs / pk["hbm_gbs"], "traffic": None, "avg_launch_ms": aa["ms"] / max(aa["launches"], 1)}
+    return res
+
+
+def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, sampler=None):
+    """U utterances per step, each: A + 31 x B + C (Vocos) [+ BigVGAN on the generated mel frames when with_vocoder]."""
+    torch = H.torch
+    from b200tts import capi, config, synth
+    cfg, vcfg = config.F5, config.BIGVGAN
+    ins = [synth.f5_inputs(1000 + rank * U + i, args.audio_len, args.n_text) for i in range(U)]
+    N = int(ins[0][2][0])
+    L = args.audio_len
+    ref_len = L // cfg.hop + 1
+    G = N - ref_len
+    ns = cfg.hop * (G - 1)
+    work = f5_work(cfg, N, ref_len)
+    audio_h = [torch.from_numpy(a.reshape(-1)).pin_memory() for a, _, _, _ in ins]
+    ids_h = [torch.from_numpy(t.reshape(-1)).pin_memory() for _, t, _, _ in ins]
+    noise_h = [torch.from_numpy(n.reshape(-1)).pin_memory() for _, _, _, n in ins]
+    audio_d = [a.cuda() for a in audio_h]
+    ids_d = [t.cuda() for t in ids_h]
+    noise_d = [n.cuda() for n in noise_h]
+    pcm_d = torch.empty((U, ns), dtype=torch.int16, device="cuda")
+    pcm_h = torch.empty((U, ns), dtype=torch.int16).pin_memory()
+    mel_d = torch.empty((U, N, cfg.n_mels), dtype=torch.float32, device="cuda")
+    if with_vocoder:
+        vmel_d = torch.empty((U, vcfg.num_mels, G), dtype=torch.float32, device="cuda")
+        vpcm_d = torch.empty((U, 1, vcfg.out_samples(G)), dtype=torch.int16, device="cuda")
+        vpcm_h = torch.empty((U, 1, vcfg.out_samples(G)), dtype=torch.int16).pin_memory()
+    torch.cuda.synchronize()
+
+    def core():
+        for i in range(U):
+            eng.f5_synthesize_device(audio_d[i].data_ptr(), L, ids_d[i].data_ptr(), args.n_text, N, noise_d[i].data_ptr(),
+                                     pcm_d[i].data_ptr(), precision=prec, mel_ptr=mel_d[i].data_ptr() if with_vocoder else 0)
+        if with_vocoder:
+            vmel_d.copy_(mel_d[:, ref_len:, :].transpose(1, 2))          # (U, 100, G): BigVGAN's mel_features layout
+            eng.bigvgan_run_device(vmel_d.data_ptr(), U, G, vpcm_d.data_ptr(), precision=prec)
+
+    def step_e2e():
+        for i in range(U):
+            audio_d[i].copy_(audio_h[i], non_blocking=True)
+            ids_d[i].copy_(ids_h[i], non_blocking=True)
+            noise_d[i].copy_(noise_h[i], non_blocking=True)
+        core()
+        if with_vocoder:
+            vpcm_h.copy_(vpcm_d, non_blocking=True)
+        else:
+            pcm_h.copy_(pcm_d, non_blocking=True)
+
+    with torch.cuda.stream(H.stream):
+        for _ in range(warmup):
+            core()
+        step_e2e()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    ms = H.timed(core, steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = H.timed(step_e2e, steps)
+    eng.profile_begin()
+    with torch.cuda.stream(H.stream):
+        core()
+    prof = eng.profile_end()
+    pk = peaks()
+    frames = U * G * H.world * steps
+    audio_s = U * (vcfg.out_samples(G) / vcfg.sample_rate if with_vocoder else work["audio_s"])
+    h2d = U * (L * 2 + args.n_text * 4 + N * cfg.n_mels * 4)
+    d2h = U * (vcfg.out_samples(G) * 2 if with_vocoder else ns * 2)
+    res = {
+        "value": frames / (ms / 1e3), "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / audio_s,
+        "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / steps, "rtf": (ms_e2e / 1e3 / steps) / audio_s},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        "workload": (f"F5-TTS NFE={cfg.nfe} ({cfg.nfe - 1} Euler steps, CFG pair), {L / cfg.sample_rate:.0f} s ref / {args.n_text} text ids, "
+                     f"N={N}, G={G} generated frames, {U} utterance(s) per GPU per step, preprocess + DiT + "
+                     + ("Vocos/ISTFT decode and BigVGAN on the generated mel [BASELINE.json configs[3] per-GPU share]" if with_vocoder
+                        else "Vocos/ISTFT decode [BASELINE.json configs[2]]")),
+    }
+    gemm_tags = ("f5.qkv_gemm", "f5.out_gemm", "f5.ff1_gemm", "f5.ff2_gemm")
+    gemm_ms = sum(prof[t]["ms"] for t in gemm_tags if t in prof)
+    gemm_n = sum(prof[t]["launches"] for t in gemm_tags if t in prof)
+    total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
+    if gemm_ms > 0:
+        ach = U * work["steps"] * work["flops_gemm_step"] / (gemm_ms / 1e3) / 1e12
+        res["roofline"] = {"bound": "tensor", "kernel": "rowgemm_tc_kernel (DiT qkv/out/ff1/ff2 GEMMs)", "achieved": ach,
+                           "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                           "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                           "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms}
+    att = prof.get("f5.attention")
+    if att and att["ms"] > 0:
+        ach = U * work["steps"] * work["flops_attn_step"] / (att["ms"] / 1e3) / 1e12
+        res["roofline_attention"] = {"bound": "tensor", "kernel": "attn_tc_kernel", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                                     "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                                     "avg_launch_ms": att["ms"] / max(att["launches"], 1), "share_of_step": att["ms"] / total_ms}
+    res["dit_tflops_overall"] = U * work["flops_total"] / (ms / steps / 1e3) / 1e12
+    return res
 
 
 def main():
@@ -134,11 +399,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan"])
+    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=512)
+    ap.add_argument("--audio-len", type=int, default=144000)
+    ap.add_argument("--n-text", type=int, default=150)
+    ap.add_argument("--utterances", type=int, default=8, help="pipeline workload: utterances per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the attached F5 measurement of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -147,9 +416,6 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5                     # ~6 s of CPU work per step: keep the arm within minutes
-        args.warmup = min(args.warmup, 1)
         run_reference(args, rank, world)
         return
 
@@ -164,137 +430,69 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    cfg = config.BIGVGAN
     prec = capi.BF16 if args.precision == "bf16" else capi.F32
     eng = capi.Engine(local_rank)
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
+    H = Harness(torch, dist, stream, world)
+    need_f5 = args.workload in ("f5", "pipeline") or (args.workload == "bigvgan" and not args.no_extras)
+    need_vgan = args.workload in ("bigvgan", "pipeline")
 
     # weights: rank 0 makes them, NCCL broadcast over NVLink to the others (the only collective of the job)
-    state = weights.bigvgan_engine_tensors(synth.bigvgan_state(1234)) if rank == 0 else None
-    distributed.load_state_broadcast(eng, "bigvgan", state, src=0)
-    eng.bigvgan_build()
+    if need_vgan:
+        state = weights.bigvgan_engine_tensors(synth.bigvgan_state(1234)) if rank == 0 else None
+        distributed.load_state_broadcast(eng, "bigvgan", state, src=0)
+        eng.bigvgan_build()
+    if need_f5:
+        cfg5 = config.F5
+        if rank == 0:
+            dsd = synth.f5_dit_state(4321)
+            parts = {"dit": weights.dit_engine_tensors(dsd, cfg5), "vocos": weights.vocos_engine_tensors(synth.vocos_state(2468), cfg5),
+                     "f5": weights.f5_export_constants(dsd, cfg5)}
+        else:
+            parts = {"dit": None, "vocos": None, "f5": None}
+        for k in ("dit", "vocos", "f5"):
+            distributed.load_state_broadcast(eng, k, parts[k], src=0)
+        eng.f5_build()
 
-    B, T = args.batch, args.frames
-    n_out = cfg.out_samples(T)
-    work = bigvgan_work(cfg, B, T)
-    mel_host = torch.from_numpy(synth.bigvgan_mel(100 + rank, B, T)).pin_memory()
-    pcm_host = torch.empty((B, 1, n_out), dtype=torch.int16).pin_memory()
-    mel_dev = mel_host.cuda(non_blocking=True)
-    pcm_dev = torch.empty((B, 1, n_out), dtype=torch.int16, device="cuda")
-    torch.cuda.synchronize()
-
-    def step_device():
-        eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
-
-    def step_e2e():
-        with torch.cuda.stream(stream):
-            mel_dev.copy_(mel_host, non_blocking=True)
-            eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
-            pcm_host.copy_(pcm_dev, non_blocking=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for _ in range(steps):
-                fn()
-            ev1.record(stream)
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step_device()
-            step_e2e()
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.launch_count()
-    ms = timed(step_device, args.steps)
-    launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps)
-
-    # per-kernel CUDA-event timing of one more step (roofline leg; not part of the throughput number)
-    eng.profile_begin()
-    with torch.cuda.stream(stream):
-        step_device()
-    prof = eng.profile_end()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    extra = {}
+    if args.workload == "bigvgan":
+        res = bench_bigvgan(args, H, eng, rank, args.batch, args.frames, prec, args.steps, args.warmup, sampler)
+        if need_f5:
+            f5r = bench_f5(args, H, eng, rank, prec, steps=3, warmup=3)
+            extra["f5"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **f5r}
+        dtype = "bf16" if prec == capi.BF16 else "f32"
+    elif args.workload == "f5":
+        res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
+        dtype = "bf16" if prec == capi.BF16 else "f32"
+    else:
+        res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, with_vocoder=True, U=args.utterances, sampler=sampler)
+        dtype = "bf16" if prec == capi.BF16 else "f32"
 
     if rank == 0:
-        pk = peaks()
-        frames_job = work["frames"] * world * args.steps
-        value = frames_job / (ms / 1e3)
-        e2e = frames_job / (ms_e2e / 1e3)
-        conv = prof.get("bigvgan.resconv", {"launches": 0, "ms": 0.0})
-        aa = prof.get("bigvgan.aa_snake", {"launches": 0, "ms": 0.0})
-        line = {
-            "metric": "mel_frames_per_s", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if prec == capi.BF16 else "f32", "data": "synthetic",
-            "config": {"workload": f"BigVGAN-v2 24khz_100band_256x, mels ({B},100,{T}) per GPU -> int16 PCM ({B},1,{n_out}) "
-                                   f"[BASELINE.json configs[1]]",
-                       "parallelism": f"dp{world} (utterance sharding, weights NCCL-broadcast at load)",
-                       "l2": "per-step working set ~0.6 GB >> 126 MB L2, no explicit flush"},
-            "rtf": (ms / 1e3 / args.steps) / work["audio_s"],
-            "e2e": {"value": e2e, "unit": "mel-frames/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),
-                    "d2h_bytes_per_step": int(pcm_host.numel() * 2), "ms_per_step": ms_e2e / args.steps,
-                    "rtf": (ms_e2e / 1e3 / args.steps) / work["audio_s"]},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
-        }
-        if conv["ms"] > 0:
-            if prec == capi.BF16:
-                ach = work["flops_resconv"] / (conv["ms"] / 1e3) / 1e12
-                line["roofline"] = {"bound": "tensor", "kernel": "rowgemm_tc_kernel (108 resblock convs)",
-                                    "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                                    "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                                    "avg_launch_ms": conv["ms"] / max(conv["launches"], 1)}
-            else:
-                ach = work["flops_resconv"] / (conv["ms"] / 1e3) / 1e12
-                line["roofline"] = {"bound": "tensor", "kernel": "rowgemm_f32_kernel (SIMT parity engine)", "achieved": ach,
-                                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"]}
-        if aa["ms"] > 0:
-            bytes_aa = work["aa_elems"] * (4 + 2 if prec == capi.BF16 else 8) * 0  # refined below
-            # aa_snake reads fp32 or bf16 and writes bf16 (fast path): 108 launches, half read fp32 (4 B) and half bf16 (2 B)
-            per_elem = (3.0 + 2.0) if prec == capi.BF16 else 8.0
-            gbs = work["aa_elems"] * per_elem / (aa["ms"] / 1e3) / 1e9
-            line["roofline_hbm"] = {"bound": "hbm", "kernel": "aa_snake_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
-                                    "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
-                                    "avg_launch_ms": aa["ms"] / max(aa["launches"], 1)}
+        workload = res.pop("workload")
+        line = {"metric": "mel_frames_per_s", "value": res.pop("value"), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": workload, "parallelism": f"dp{world} (utterance sharding, weights NCCL-broadcast at load)",
+                           "l2": "per-step working set (activations + weights, > 0.5 GB) exceeds the 126 MB L2; no explicit flush"}}
+        line.update(res)
+        line.update(extra)
         if not args.no_cpu_baseline:
-            import torch as _t
-            from oracle import bigvgan_ref
             cores = os.cpu_count() or 1
-            _t.set_num_threads(cores)
-            sd = synth.bigvgan_state(1234)
-            m1 = synth.bigvgan_mel(100, 1, T)
-            bigvgan_ref.bigvgan_pcm(m1[:, :, :32], sd, cfg)
-            t0 = time.perf_counter()
-            reps = 2
-            for _ in range(reps):
-                bigvgan_ref.bigvgan_pcm(m1, sd, cfg)
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": T / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{reps} x 1 mel (1,100,{T}), oracle (torch-CPU fp32 restatement of the reference "
-                                              f"modules; ORT is not installable offline)", "s_per_mel": dt}
+            if args.workload == "bigvgan":
+                dt = cpu_bigvgan(args.frames, 2, cores)
+                line["cpu_baseline"] = {"value": args.frames / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+                                        "sample": f"2 x 1 mel (1,100,{args.frames}), oracle (torch-CPU fp32 restatement of the reference "
+                                                  "modules; ORT is not installable offline)", "s_per_mel": dt}
+            else:
+                r = cpu_f5(args.audio_len, args.n_text, 2, cores)
+                G = r["N"] - r["ref_len"]
+                tot = r["pre_s"] + (config.F5.nfe - 1) * r["step_s"] + r["decode_s"]
+                line["cpu_baseline"] = {"value": G / tot, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+                                        "sample": f"graph A, 2 of {config.F5.nfe - 1} DiT steps (extrapolated), graph C of ONE utterance; oracle "
+                                                  "(torch-CPU fp32 restatement of the reference modules)", "parts_s": r}
         print(json.dumps(line), flush=True)
 
     if world > 1:

@@ -360,8 +360,14 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
   run_conv(c, "bigvgan.conv_pre", m.pre, conv_in, T, 1, m.xs.p, 0, nullptr, 0, 1.0f, mel_ld);
 
   int L = T;
+  static const char* kConvTag[8] = {"bigvgan.resconv.s0", "bigvgan.resconv.s1", "bigvgan.resconv.s2", "bigvgan.resconv.s3",
+                                    "bigvgan.resconv.s4", "bigvgan.resconv.s5", "bigvgan.resconv.s6", "bigvgan.resconv.s7"};
+  static const char* kActTag[8] = {"bigvgan.aa_snake.s0", "bigvgan.aa_snake.s1", "bigvgan.aa_snake.s2", "bigvgan.aa_snake.s3",
+                                   "bigvgan.aa_snake.s4", "bigvgan.aa_snake.s5", "bigvgan.aa_snake.s6", "bigvgan.aa_snake.s7"};
   for (int i = 0; i < m.nstages; ++i) {
     Stage& st = m.stages[i];
+    const char* ctag = kConvTag[i < 8 ? i : 7];
+    const char* atag = kActTag[i < 8 ? i : 7];
     const void* up_in = m.xs.p;
     if (c.fast) {
       ProfScope ps(e.prof, "bigvgan.cast", s);
@@ -375,25 +381,25 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
       for (int mm = 0; mm < 3; ++mm) {
         const bool last = (mm == 2);
         {
-          ProfScope ps(e.prof, "bigvgan.aa_snake", s);
+          ProfScope ps(e.prof, atag, s);
           if (c.fast) aa_snake(xcur, 0, m.abuf16.p, 1, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, false, false, s);
           else aa_snake(xcur, 0, m.abuf.p, 0, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, true, false, s);
         }
-        if (c.fast) run_conv(c, "bigvgan.resconv", st.c1[j][mm], m.abuf16.p, L, st.dil[j][mm], m.cbuf16.p, 1, nullptr, 0, 1.0f);
-        else run_conv(c, "bigvgan.resconv", st.c1[j][mm], m.abuf.p, L, st.dil[j][mm], m.cbuf.p, 0, nullptr, 0, 1.0f);
+        if (c.fast) run_conv(c, ctag, st.c1[j][mm], m.abuf16.p, L, st.dil[j][mm], m.cbuf16.p, 1, nullptr, 0, 1.0f);
+        else run_conv(c, ctag, st.c1[j][mm], m.abuf.p, L, st.dil[j][mm], m.cbuf.p, 0, nullptr, 0, 1.0f);
         {
-          ProfScope ps(e.prof, "bigvgan.aa_snake", s);
+          ProfScope ps(e.prof, atag, s);
           if (c.fast) aa_snake(m.cbuf16.p, 1, m.abuf16.p, 1, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, false, false, s);
           else aa_snake(m.cbuf.p, 0, m.abuf.p, 0, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, true, false, s);
         }
         const void* a2 = c.fast ? (const void*)m.abuf16.p : (const void*)m.abuf.p;
         if (!last) {
           float* xnext = (mm == 0) ? m.xa.p : m.xb.p;
-          run_conv(c, "bigvgan.resconv", st.c2[j][mm], a2, L, 1, xnext, 0, xcur, 0, 1.0f);   // x = xt + x
+          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, xnext, 0, xcur, 0, 1.0f);   // x = xt + x
           xcur = xnext;
         } else {
           // xs (+)= conv + x ; the MRF mean (x 1/3, bigvgan.py:399) is folded into the third block's epilogue
-          run_conv(c, "bigvgan.resconv", st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f);
+          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f);
         }
       }
     }

@@ -21,16 +21,18 @@ struct Profiler {
   bool enabled = false;
   struct Rec { std::string tag; cudaEvent_t a, b; };
   std::vector<Rec> recs;
-  void begin(const char* tag, cudaStream_t s) {
-    if (!enabled) return;
+  // -> index of the record (scopes may nest: each one closes its own record), -1 when disabled
+  int begin(const char* tag, cudaStream_t s) {
+    if (!enabled) return -1;
     Rec r; r.tag = tag;
     B2_CUDA(cudaEventCreate(&r.a)); B2_CUDA(cudaEventCreate(&r.b));
     B2_CUDA(cudaEventRecord(r.a, s));
     recs.push_back(r);
+    return (int)recs.size() - 1;
   }
-  void end(cudaStream_t s) {
-    if (!enabled) return;
-    B2_CUDA(cudaEventRecord(recs.back().b, s));
+  void end(int idx, cudaStream_t s) {
+    if (idx < 0 || idx >= (int)recs.size()) return;
+    cudaEventRecord(recs[idx].b, s);
   }
   // -> map tag -> (count, total ms); destroys the events
   std::map<std::string, std::pair<long, double>> collect() {
@@ -49,9 +51,9 @@ struct Profiler {
 };
 
 struct ProfScope {
-  Profiler& p; cudaStream_t s;
-  ProfScope(Profiler& p_, const char* tag, cudaStream_t s_) : p(p_), s(s_) { p.begin(tag, s); }
-  ~ProfScope() { if (p.enabled) cudaEventRecord(p.recs.back().b, s); }
+  Profiler& p; cudaStream_t s; int idx;
+  ProfScope(Profiler& p_, const char* tag, cudaStream_t s_) : p(p_), s(s_), idx(p_.begin(tag, s_)) {}
+  ~ProfScope() { p.end(idx, s); }
 };
 
 struct BigVGANModel;

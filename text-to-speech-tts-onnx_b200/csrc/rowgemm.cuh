@@ -36,6 +36,7 @@ struct RowGemm {
   long o_shift = 0;
   long o_limit = 0;       // 0 -> M*ldo
   int out_bf16 = 0;
+  __nv_bfloat16* out2 = nullptr;   // tensor-core path only: optional second, bf16, copy of the output (same indexing)
   // epilogue: v = acc + bias[n]; v = act(v); v *= gate[n]; v += res[idx]; if (accumulate) v += out[idx]; v *= scale
   const float* bias = nullptr;    // [groups*N]
   const float* gate = nullptr;    // [groups*N]

@@ -8,12 +8,20 @@
 // are zero-filled by the TMA unit, which IS the convolution's zero padding - no im2col, no halo code.
 // B tiles are boxes {64 ch, BN, 1} of W[g*taps + tap][n][c].
 //
-// CTA = 192 threads: warp 0 = TMA producer (1 lane), warp 1 = TMEM allocator + MMA issuer (1 lane),
-// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4). One output tile per CTA; shared memory is sized so
-// two CTAs co-reside per SM, which overlaps one CTA's epilogue with the other's main loop.
+// Two kernels share the epilogue:
+//  * rowgemm_tc2_kernel (default): persistent, one CTA per SM, 256 x BN output tiles (two M=128 accumulators that
+//    share every B tile), double-buffered accumulators in TMEM (512 columns) so the epilogue of tile i overlaps the
+//    main loop of tile i+1. The A operand of a convolution is fetched ONCE per 64-channel chunk as a
+//    (256 + (taps-1)*dil)-row halo tile; every tap is an MMA whose A descriptor starts (tap*dil) rows further down
+//    that tile (plain descriptor start-address shift; the swizzle XOR is a function of the absolute smem address), so L2->SMEM traffic per FLOP
+//    is ~1/256 + 1/(taps*BN) B instead of v1's 1/128 + 1/128 (which made v1 L2-bandwidth-bound at ~25 % of peak).
+//    320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue.
+//  * rowgemm_tc_kernel (v1, B200TTS_GEMM=v1): one 128 x BN tile per 192-thread CTA, per-tap A tiles.
 #include "rowgemm_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
+#include <string>
 
 #include "tc_ptx.cuh"
 
@@ -37,7 +45,253 @@ struct TcArgs {
   const float* bias; const float* gate; const float* res; int accumulate; float scale; int act;
   const float* rope_cos; const float* rope_sin; int rope_cols, rope_rows;
   __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
+  __nv_bfloat16* out2;          // optional bf16 copy of the output (same indexing)
 };
+
+// Epilogue of 16 consecutive output columns [n, n+16) of one output row t (registers r[] straight from tcgen05.ld):
+// bias, activation, fused q/k RoPE + transposed V store, gate, residual, accumulate, scale, fp32 or bf16 store.
+__device__ __forceinline__ void epilogue_chunk16(const TcArgs& a, const uint32_t (&r)[16], int b, int g, int t, int n,
+                                                 long obase, long rowflat) {
+  if (n >= a.N) return;
+  const int gn = g * a.N + n;
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    const int nn = n + v4 * 4;
+    if (nn >= a.N) break;
+    const long flat = rowflat + nn;
+    if (flat < 0 || flat >= a.o_limit) continue;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[v4 * 4 + i]);
+    if (a.bias) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + gn + v4 * 4));
+      v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+    }
+    if (a.act != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
+    }
+    if (a.rope_cos != nullptr) {
+      const int tt = t % a.rope_rows;
+      if (nn < a.rope_cols) {            // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+        const int d = nn & 63;
+        const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
+        const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
+        const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
+        v[0] = x0 * cc.x - x1 * ss.x; v[1] = x1 * cc.y + x0 * ss.y;
+        v[2] = x2 * cc.z - x3 * ss.z; v[3] = x3 * cc.w + x2 * ss.w;
+      }
+      if (a.vt_out != nullptr && nn >= a.vt_col0) {
+        const int cv = nn - a.vt_col0;
+        const int hh = cv >> 6, d = cv & 63;
+        __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
+        continue;
+      }
+    }
+    if (a.gate) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gate + gn + v4 * 4));
+      v[0] *= gg.x; v[1] *= gg.y; v[2] *= gg.z; v[3] *= gg.w;
+    }
+    if (a.res) {
+      const float4 rr = *reinterpret_cast<const float4*>(a.res + obase + flat);
+      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+    }
+    if (a.out_bf16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + flat;
+      if (a.accumulate) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += __bfloat162float(o[i]);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * a.scale, v[1] * a.scale);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2] * a.scale, v[3] * a.scale);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(o) = pk;
+    } else {
+      float* o = reinterpret_cast<float*>(a.out) + obase + flat;
+      if (a.accumulate) {
+        const float4 rr = *reinterpret_cast<const float4*>(o);
+        v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+      }
+      *reinterpret_cast<float4*>(o) = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
+    }
+    if (a.out2 != nullptr) {             // second copy of the result in bf16 (the next GEMM's A operand)
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * a.scale, v[1] * a.scale);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2] * a.scale, v[3] * a.scale);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(a.out2 + obase + flat) = pk;
+    }
+  }
+}
+
+// =============================================================================================
+// v2: persistent 256 x BN tiles, halo A tiles, double-buffered TMEM accumulators
+// =============================================================================================
+constexpr int BM2 = 256;
+constexpr int NTHREADS2 = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int A_BOX_ROWS = 64;
+constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+
+struct Tc2Sched {
+  int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
+  int a_rows;                           // rows per A stage (multiple of 64) = round_up(256 + (taps-1)*dil, 64)
+  int nA, nB;                           // ring depths
+  int half_stride, nacc;                // TMEM columns between the two M halves; accumulator stages (1 or 2)
+};
+
+// A tap's A tile starts (tap*dil) rows = (tap*dil)*128 bytes into the halo tile, i.e. generally NOT on a 1024-byte
+// swizzle-atom boundary. Measured on B200 (tools/debug_conv.py): the tensor core applies the 128B-swizzle XOR to the
+// absolute shared-memory address bits, exactly as the TMA unit did when it wrote the tile, so the plain descriptor with
+// the shifted start address is correct and the matrix-base-offset field must stay 0 (setting it to the row phase
+// (addr >> 7) & 7 double-applies the rotation and corrupts every tap whose shift is not a multiple of 8 rows).
+
+__global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                   const TcArgs a, const Tc2Sched sc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_stage_bytes = sc.a_rows * 128;
+  const int b_stage_bytes = a.BN * 128;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + sc.nA * a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + sc.nB * b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + MAX_A_STAGES;
+  uint64_t* b_full = a_empty + MAX_A_STAGES;
+  uint64_t* b_empty = b_full + MAX_B_STAGES;
+  uint64_t* acc_full = b_empty + MAX_B_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < sc.nA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < sc.nB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_bg = sc.m_tiles * sc.n_tiles;
+  const int halo_lo = a.center * a.dil;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      const int a_boxes = sc.a_rows / A_BOX_ROWS;
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
+        const int bg = tile / per_bg, rem = tile - bg * per_bg;
+        const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
+        const int b = bg / a.groups, g = bg - b * a.groups;
+        const int t0 = mt * BM2, n0 = nt * a.BN;
+        for (int c = 0; c < a.kchunks; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], (uint32_t)a_stage_bytes);
+          for (int rbx = 0; rbx < a_boxes; ++rbx)
+            tma_load_3d(smem_a + sa * a_stage_bytes + rbx * (A_BOX_ROWS * 128), &map_a, &a_full[sa], g * a.Cin + c * BK,
+                        t0 - halo_lo + rbx * A_BOX_ROWS, b);
+          if (++sa == sc.nA) { sa = 0; pa ^= 1; }
+          for (int j = 0; j < a.taps; ++j) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
+            tma_load_3d(smem_b + sb * b_stage_bytes, &map_b, &b_full[sb], c * BK, n0, g * a.taps + j);
+            if (++sb == sc.nB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
+        const int rem = tile % per_bg;
+        const int mt = rem % sc.m_tiles;
+        const int halves = (mt * BM2 + 128 < a.M) ? 2 : 1;          // skip the second M half of a ragged last tile
+        const int acc = sc.nacc == 2 ? (it & 1) : 0;
+        const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        mbar_wait(&acc_empty[acc], accphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * sc.half_stride);
+        for (int c = 0; c < a.kchunks; ++c) {
+          int ksteps = (a.Cin - c * BK + UMMA_K - 1) / UMMA_K;
+          if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_base = smem_u32(smem_a + sa * a_stage_bytes);
+          for (int j = 0; j < a.taps; ++j) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(smem_b + sb * b_stage_bytes);
+            const uint32_t a_tap = a_base + (uint32_t)(j * a.dil) * 128u;
+            for (int h = 0; h < halves; ++h) {
+              const uint32_t a_addr = a_tap + (uint32_t)h * (128u * 128u);
+              for (int k = 0; k < ksteps; ++k) {
+                umma_bf16(d0 + (uint32_t)(h * sc.half_stride), make_desc_sw128(a_addr + 32u * k),
+                          make_desc_sw128(b_base + 32u * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[sb]);
+            if (++sb == sc.nB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == sc.nA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4, M half = (warp - 2) / 4 =====
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
+      const int bg = tile / per_bg, rem = tile - bg * per_bg;
+      const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
+      const int b = bg / a.groups, g = bg - b * a.groups;
+      const int n0 = nt * a.BN;
+      const int t = mt * BM2 + h * 128 + q * 32 + lane;
+      const int acc = sc.nacc == 2 ? (it & 1) : 0;
+      const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+      mbar_wait(&acc_full[acc], accphase);
+      tc_fence_after();
+      if (mt * BM2 + h * 128 < a.M) {                       // warp-uniform: this half holds valid rows
+        const long obase = (long)b * a.o_bstride;
+        const long rowflat = (long)t * a.ldo + (long)g * a.N + a.o_shift;
+        const bool row_ok = t < a.M;
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * sc.half_stride + h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
+        for (int cb = 0; cb < a.BN; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)cb, r);
+          tmem_ld_wait();
+          if (row_ok) epilogue_chunk16(a, r, b, g, t, n0 + cb, obase, rowflat);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
 
 __global__ void __launch_bounds__(NTHREADS) rowgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
@@ -122,74 +376,7 @@ __global__ void __launch_bounds__(NTHREADS) rowgemm_tc_kernel(const __grid_const
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
       tmem_ld_wait();
-      const int n = n0 + cb;
-      if (!row_ok || n >= a.N) continue;
-      const int gn = g * a.N + n;
-#pragma unroll
-      for (int v4 = 0; v4 < 4; ++v4) {
-        const int nn = n + v4 * 4;
-        if (nn >= a.N) break;
-        const long flat = rowflat + nn;
-        if (flat < 0 || flat >= a.o_limit) continue;
-        float v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[v4 * 4 + i]);
-        if (a.bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + gn + v4 * 4));
-          v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
-        }
-        if (a.act != ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
-        }
-        if (a.rope_cos != nullptr) {
-          const int tt = t % a.rope_rows;
-          if (nn < a.rope_cols) {            // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
-            const int d = nn & 63;
-            const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
-            const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
-            const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
-            v[0] = x0 * cc.x - x1 * ss.x; v[1] = x1 * cc.y + x0 * ss.y;
-            v[2] = x2 * cc.z - x3 * ss.z; v[3] = x3 * cc.w + x2 * ss.w;
-          }
-          if (a.vt_out != nullptr && nn >= a.vt_col0) {
-            const int cv = nn - a.vt_col0;
-            const int hh = cv >> 6, d = cv & 63;
-            __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
-            continue;
-          }
-        }
-        if (a.gate) {
-          const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gate + gn + v4 * 4));
-          v[0] *= gg.x; v[1] *= gg.y; v[2] *= gg.z; v[3] *= gg.w;
-        }
-        if (a.res) {
-          const float4 rr = *reinterpret_cast<const float4*>(a.res + obase + flat);
-          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-        }
-        if (a.out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + flat;
-          if (a.accumulate) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += __bfloat162float(o[i]);
-          }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * a.scale, v[1] * a.scale);
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2] * a.scale, v[3] * a.scale);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(o) = pk;
-        } else {
-          float* o = reinterpret_cast<float*>(a.out) + obase + flat;
-          if (a.accumulate) {
-            const float4 rr = *reinterpret_cast<const float4*>(o);
-            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-          }
-          *reinterpret_cast<float4*>(o) = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
-        }
-      }
+      if (row_ok) epilogue_chunk16(a, r, b, g, t, n0 + cb, obase, rowflat);
     }
   }
 
@@ -309,30 +496,45 @@ void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps,
   tw.ready = true;
 }
 
-void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
-  B2_CHECK(w.ready, "rowgemm_tc: tensor-core weights not prepared");
-  B2_CHECK(p.Cin == w.Cin && p.N == w.N && p.taps == w.taps && p.groups == w.groups, "rowgemm_tc: weight/problem mismatch");
-  B2_CHECK(p.N % 4 == 0 && p.ldo % 4 == 0 && p.o_shift % 4 == 0, "rowgemm_tc: output alignment");
-  B2_CHECK(p.ldx % 8 == 0 && p.x_bstride % 8 == 0, "rowgemm_tc: A rows must be 16-byte aligned");
-  B2_CHECK(p.groups == 1 || p.Cin % BK == 0, "rowgemm_tc: grouped problems need Cin % 64 == 0");
-  B2_CHECK(p.M > 0 && p.B > 0, "rowgemm_tc: empty problem");
+namespace {
 
-  CUtensorMap map_a;
-  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
-             (uint64_t)p.x_bstride, (uint32_t)BM);
+bool use_v1() {
+  static const bool v1 = [] {
+    const char* e = getenv("B200TTS_GEMM");
+    return e != nullptr && std::string(e) == "v1";
+  }();
+  return v1;
+}
 
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
+  }();
+  return n;
+}
+
+TcArgs make_args(const RowGemm& p, const TcWeight& w) {
   TcArgs a;
   a.Cin = p.Cin; a.N = p.N; a.taps = p.taps; a.dil = p.dil; a.center = p.center; a.groups = p.groups; a.M = p.M;
-  a.BN = w.BN; a.kchunks = ceil_div(p.Cin, BK);
+  a.BN = w.BN; a.kchunks = ceil_div(p.Cin, BK); a.stages = 0;
   a.out = p.out; a.o_bstride = p.o_bstride; a.ldo = p.ldo; a.o_shift = p.o_shift;
   a.o_limit = p.o_limit ? p.o_limit : (long)p.M * p.ldo;
   a.out_bf16 = p.out_bf16;
   a.bias = p.bias; a.gate = p.gate; a.res = p.res; a.accumulate = p.accumulate; a.scale = p.scale; a.act = p.act;
   a.rope_cos = p.rope_cos; a.rope_sin = p.rope_sin; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
   a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
-  B2_CHECK(p.rope_cos == nullptr || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.groups == 1 && p.B == 1),
-           "rowgemm_tc: malformed rope epilogue");
+  a.out2 = p.out2;
+  return a;
+}
 
+void launch_v1(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
+  CUtensorMap map_a;
+  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
+                (uint64_t)p.x_bstride, (uint32_t)BM);
+  TcArgs a = make_args(p, w);
   const int stage_bytes = A_STAGE_BYTES + w.BN * BK * 2;
   // keep <= ~110 KB so that two CTAs fit one SM (227 KB): the co-resident CTA hides this one's epilogue
   int stages = (110 * 1024 - 1024 - 256) / stage_bytes;
@@ -342,7 +544,6 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   if (stages < 2 && num_kb >= 2) stages = 2;
   a.stages = stages;
   const int smem = stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
-
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     B2_CUDA(cudaFuncSetAttribute(rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -352,6 +553,58 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   rowgemm_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_a, w.map, a);
   B2_LAUNCH_CHECK();
   count_launch();
+}
+
+void launch_v2(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
+  CUtensorMap map_a;
+  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
+                (uint64_t)p.x_bstride, (uint32_t)A_BOX_ROWS);
+  TcArgs a = make_args(p, w);
+  Tc2Sched sc;
+  sc.m_tiles = ceil_div(p.M, BM2);
+  sc.n_tiles = ceil_div(p.N, w.BN);
+  const long tiles = (long)p.B * p.groups * sc.m_tiles * sc.n_tiles;
+  B2_CHECK(tiles < (1L << 30), "rowgemm_tc: too many tiles");
+  sc.num_tiles = (int)tiles;
+  const int halo = (p.taps - 1) * p.dil;
+  sc.a_rows = (int)round_up(BM2 + halo, A_BOX_ROWS);
+  sc.half_stride = w.BN <= 128 ? 128 : 256;
+  sc.nacc = w.BN <= 128 ? 2 : 1;
+  const int a_stage = sc.a_rows * 128, b_stage = w.BN * 128;
+  const int bar_bytes = (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * 8 + 16;
+  const int budget = 227 * 1024 - 1024 - bar_bytes;
+  int nA = p.taps == 1 ? MAX_A_STAGES : 2;
+  if (nA > a.kchunks + 1) nA = a.kchunks + 1;
+  if (nA < 1) nA = 1;
+  while (nA > 1 && budget - nA * a_stage < 2 * b_stage) --nA;
+  int nB = (budget - nA * a_stage) / b_stage;
+  if (nB > MAX_B_STAGES) nB = MAX_B_STAGES;
+  B2_CHECK(nB >= 1, "rowgemm_tc: halo tile does not fit shared memory (kernel too long / dilation too large)");
+  sc.nA = nA; sc.nB = nB;
+  const int smem = nA * a_stage + nB * b_stage + 1024 + bar_bytes;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  });
+  const int grid = sc.num_tiles < sm_count() ? sc.num_tiles : sm_count();
+  rowgemm_tc2_kernel<<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
+  B2_LAUNCH_CHECK();
+  count_launch();
+}
+
+}  // namespace
+
+void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
+  B2_CHECK(w.ready, "rowgemm_tc: tensor-core weights not prepared");
+  B2_CHECK(p.Cin == w.Cin && p.N == w.N && p.taps == w.taps && p.groups == w.groups, "rowgemm_tc: weight/problem mismatch");
+  B2_CHECK(p.N % 4 == 0 && p.ldo % 4 == 0 && p.o_shift % 4 == 0, "rowgemm_tc: output alignment");
+  B2_CHECK(p.ldx % 8 == 0 && p.x_bstride % 8 == 0, "rowgemm_tc: A rows must be 16-byte aligned");
+  B2_CHECK(p.groups == 1 || p.Cin % BK == 0, "rowgemm_tc: grouped problems need Cin % 64 == 0");
+  B2_CHECK(p.M > 0 && p.B > 0, "rowgemm_tc: empty problem");
+  B2_CHECK(p.rope_cos == nullptr || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.groups == 1 && p.B == 1),
+           "rowgemm_tc: malformed rope epilogue");
+  if (use_v1()) launch_v1(p, w, stream);
+  else launch_v2(p, w, stream);
 }
 
 }  // namespace b200tts
