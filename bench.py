@@ -353,6 +353,12 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     launches = eng.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms_e2e = H.timed(step_e2e, steps)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(H.stream):
+        core()
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t0)      # CPU time to enqueue one step (no sync): launch-bound check
+    torch.cuda.synchronize()
     eng.profile_begin()
     with torch.cuda.stream(H.stream):
         core()
@@ -366,7 +372,7 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
         "value": frames / (ms / 1e3), "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / audio_s,
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / steps, "rtf": (ms_e2e / 1e3 / steps) / audio_s},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms,
         "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         "workload": (f"F5-TTS NFE={cfg.nfe} ({cfg.nfe - 1} Euler steps, CFG pair), {L / cfg.sample_rate:.0f} s ref / {args.n_text} text ids, "
                      f"N={N}, G={G} generated frames, {U} utterance(s) per GPU per step, preprocess + DiT + "

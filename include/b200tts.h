@@ -106,6 +106,12 @@ int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int 
 int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
                       float* out_host);
 
+/* Micro-benchmark of the tensor-core shifted-row GEMM alone (tools/bench_gemm.py; not on any product path): B batches of
+ * M rows x Cin channels (bf16, synthetic) against taps x N x Cin weights, epilogue = bias (+ fp32 residual/gate when
+ * epilogue == 1, bf16 output when epilogue == 2); *ms_out = average CUDA-event milliseconds per launch over iters. */
+int b200tts_bench_rowgemm(b200tts_engine* e, int B, int M, int N, int Cin, int taps, int dil, int groups, int epilogue,
+                          int iters, float* ms_out);
+
 /* ---- profiling (bench.py roofline leg) ------------------------------------------------------------------
  * Between begin and end every kernel launch is bracketed by CUDA events on the engine stream; end returns a
  * JSON object {"tag": {"launches": n, "ms": total}, ...} valid until the next call on this engine. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
     "b200tts_attention": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp]),
+    "b200tts_bench_rowgemm": (_int, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _c_f]),
     "b200tts_profile_begin": (_int, [_vp]),
     "b200tts_profile_end": (ctypes.c_char_p, [_vp]),
 }
@@ -220,6 +221,13 @@ class Engine:
         self._check(self.lib.b200tts_f5_synthesize_device(self.handle, _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
                                                           int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
                                                           _vp(pcm_ptr), _vp(mel_ptr or 0)), "f5_synthesize_device")
+
+    def bench_rowgemm(self, B, M, N, Cin, taps=1, dil=1, groups=1, epilogue=0, iters=20) -> float:
+        """Average ms per launch of the tensor-core shifted-row GEMM on synthetic operands (tools/bench_gemm.py)."""
+        ms = ctypes.c_float(0)
+        self._check(self.lib.b200tts_bench_rowgemm(self.handle, B, M, N, Cin, taps, dil, groups, epilogue, iters, ctypes.byref(ms)),
+                    "bench_rowgemm")
+        return float(ms.value)
 
     # -- single ops (reference layouts) --------------------------------------------------------------
     def aa_activation(self, x, alpha_log, beta_log, taps12, precise=True, post=False):

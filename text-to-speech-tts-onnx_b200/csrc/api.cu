@@ -2,7 +2,10 @@
 // catches, stores the message thread-locally and returns a non-zero code.
 #include "../../include/b200tts.h"
 
+#include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <vector>
 #include <sstream>
 
 #include "aa_act.cuh"
@@ -88,6 +91,8 @@ int b200tts_create(int device, b200tts_engine** out) {
     e->impl.device = device;
     B2_CUDA(cudaStreamCreateWithFlags(&e->impl.stream, cudaStreamNonBlocking));
     e->impl.own_stream = true;
+    const char* g = getenv("B200TTS_GRAPHS");           // B200TTS_GRAPHS=0: always enqueue kernel by kernel
+    e->impl.graphs.enabled = !(g != nullptr && g[0] == '0');
     *out = e.release();
   });
 }
@@ -138,7 +143,8 @@ int b200tts_bigvgan_run_device(b200tts_engine* e, const float* mel_dev, int B, i
   return guarded([&] {
     Engine& E = eng(e);
     B2_CHECK(mel_dev && pcm_dev, "bigvgan_run_device: null buffer");
-    bigvgan_forward(E, mel_dev, B, T, precision, pcm_dev, wave_dev);
+    run_graphed(E, {10, (long long)(uintptr_t)mel_dev, B, T, precision, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)wave_dev},
+                [&] { bigvgan_forward(E, mel_dev, B, T, precision, pcm_dev, wave_dev); }, [] {});
   });
 }
 
@@ -151,13 +157,16 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
     B2_CHECK(B > 0 && T > 0, "bigvgan_run: empty input");
     const long n_mel = (long)B * T * bigvgan_num_mels(E);
     const long n_out = (long)B * bigvgan_out_samples(E, T);
-    DevBuf<float> d_mel((size_t)n_mel), d_wave;
-    DevBuf<int16_t> d_pcm((size_t)n_out);
-    if (wave_host) d_wave.alloc((size_t)n_out);
-    B2_CUDA(cudaMemcpyAsync(d_mel.p, mel_host, n_mel * sizeof(float), cudaMemcpyHostToDevice, E.stream));
-    bigvgan_forward(E, d_mel.p, B, T, precision, d_pcm.p, wave_host ? d_wave.p : nullptr);
-    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, n_out * sizeof(int16_t), cudaMemcpyDeviceToHost, E.stream));
-    if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    // persistent staging buffers: stable addresses let repeated calls of one shape replay a captured graph
+    E.io_f32a.reserve((size_t)n_mel);
+    E.io_i16.reserve((size_t)n_out);
+    if (wave_host) E.io_f32b.reserve((size_t)n_out);
+    float* d_mel = E.io_f32a.p; int16_t* d_pcm = E.io_i16.p; float* d_wave = wave_host ? E.io_f32b.p : nullptr;
+    B2_CUDA(cudaMemcpyAsync(d_mel, mel_host, n_mel * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    run_graphed(E, {11, (long long)(uintptr_t)d_mel, B, T, precision, (long long)(uintptr_t)d_pcm, (long long)(uintptr_t)d_wave},
+                [&] { bigvgan_forward(E, d_mel, B, T, precision, d_pcm, d_wave); }, [] {});
+    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm, n_out * sizeof(int16_t), cudaMemcpyDeviceToHost, E.stream));
+    if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave, n_out * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     B2_CUDA(cudaStreamSynchronize(E.stream));
   });
 }
@@ -178,11 +187,13 @@ int b200tts_f5_preprocess(b200tts_engine* e, const int16_t* audio_host, int64_t 
     B2_CHECK(audio_host && text_ids_host && cat_mel_text_host && cat_mel_text_drop_host && ref_signal_len, "f5_preprocess: null buffer");
     B2_CHECK(L > 0 && n_text > 0 && max_duration > 0 && max_duration < (1 << 30), "f5_preprocess: bad sizes");
     cudaStream_t s = E.stream;
-    DevBuf<int16_t> d_audio((size_t)L);
-    DevBuf<int> d_ids((size_t)n_text);
-    B2_CUDA(cudaMemcpyAsync(d_audio.p, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(d_ids.p, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
-    f5_preprocess(E, d_audio.p, L, d_ids.p, n_text, (int)max_duration);
+    E.io_i16.reserve((size_t)L);
+    E.io_f32b.reserve((size_t)n_text);
+    int16_t* d_audio = E.io_i16.p;
+    int* d_ids = reinterpret_cast<int*>(E.io_f32b.p);
+    B2_CUDA(cudaMemcpyAsync(d_audio, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    f5_preprocess(E, d_audio, L, d_ids, n_text, (int)max_duration);
     const size_t nb = (size_t)max_duration * f5_cond_dim(E) * sizeof(float);
     B2_CUDA(cudaMemcpyAsync(cat_mel_text_host, f5_cond(E), nb, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaMemcpyAsync(cat_mel_text_drop_host, f5_cond_drop(E), nb, cudaMemcpyDeviceToHost, s));
@@ -200,15 +211,16 @@ int b200tts_f5_transformer(b200tts_engine* e, float* noise_host, const float* ro
     cudaStream_t s = E.stream;
     f5_begin(E, N);
     const size_t nc = (size_t)N * f5_cond_dim(E) * sizeof(float), nn = (size_t)N * f5_n_mels(E) * sizeof(float);
-    DevBuf<float> rc((size_t)N * 64), rs((size_t)N * 64);
+    float *rc = nullptr, *rs = nullptr;
+    f5_rope_buffers(E, &rc, &rs);
     B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_host, nn, cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaMemcpyAsync(f5_cond(E), cat_mel_text_host, nc, cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaMemcpyAsync(f5_cond_drop(E), cat_mel_text_drop_host, nc, cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(rc.p, rope_cos_host, rc.n * sizeof(float), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(rs.p, rope_sin_host, rs.n * sizeof(float), cudaMemcpyHostToDevice, s));
-    f5_set_rope(E, rc.p, rs.p);
-    f5_prepare_cond(E);
-    f5_steps(E, *time_step, n_steps, precision);
+    B2_CUDA(cudaMemcpyAsync(rc, rope_cos_host, (size_t)N * 64 * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(rs, rope_sin_host, (size_t)N * 64 * sizeof(float), cudaMemcpyHostToDevice, s));
+    const int first = *time_step;
+    run_graphed(E, {20, N, first, n_steps, precision},
+                [&] { f5_prepare_cond(E); f5_steps(E, first, n_steps, precision); }, [] {});
     B2_CUDA(cudaMemcpyAsync(noise_host, f5_noise(E), nn, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *time_step += n_steps;
@@ -223,15 +235,17 @@ int b200tts_f5_decode(b200tts_engine* e, const float* denoised_host, int N, int6
     B2_CHECK(N > 0 && ref_signal_len >= 0 && ref_signal_len < N, "f5_decode: ref_signal_len must be in [0, N)");
     cudaStream_t s = E.stream;
     const long ns = 256L * (N - ref_signal_len - 1);
-    DevBuf<float> d_mel((size_t)N * f5_n_mels(E)), d_wave;
-    DevBuf<int16_t> d_pcm((size_t)(ns > 0 ? ns : 1));
-    if (wave_host) d_wave.alloc((size_t)(ns > 0 ? ns : 1));
-    B2_CUDA(cudaMemcpyAsync(d_mel.p, denoised_host, d_mel.n * sizeof(float), cudaMemcpyHostToDevice, s));
-    const long got = f5_decode(E, d_mel.p, N, (int)ref_signal_len, d_pcm.p, wave_host ? d_wave.p : nullptr);
+    const size_t nmel = (size_t)N * f5_n_mels(E), nsz = (size_t)(ns > 0 ? ns : 1);
+    E.io_f32a.reserve(nmel);
+    E.io_i16.reserve(nsz);
+    if (wave_host) E.io_f32b.reserve(nsz);
+    float* d_mel = E.io_f32a.p; int16_t* d_pcm = E.io_i16.p; float* d_wave = wave_host ? E.io_f32b.p : nullptr;
+    B2_CUDA(cudaMemcpyAsync(d_mel, denoised_host, nmel * sizeof(float), cudaMemcpyHostToDevice, s));
+    const long got = f5_decode(E, d_mel, N, (int)ref_signal_len, d_pcm, d_wave);
     B2_CHECK(got == ns, "f5_decode: unexpected output length");
     if (ns > 0) {
-      B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
-      if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+      if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     B2_CUDA(cudaStreamSynchronize(s));
     *n_out = ns;
@@ -241,12 +255,17 @@ int b200tts_f5_decode(b200tts_engine* e, const float* denoised_host, int N, int6
 static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const int32_t* ids_dev, int n_text, int64_t N,
                          const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev) {
   cudaStream_t s = E.stream;
-  f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N);
-  B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  f5_prepare_cond(E);
-  f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
-  f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr);
-  if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  run_graphed(E, {30, (long long)(uintptr_t)audio_dev, (long long)L, (long long)(uintptr_t)ids_dev, n_text, (long long)N,
+                  (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
+              [&] {
+                f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N);
+                B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                f5_prepare_cond(E);
+                f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
+                f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr);
+                if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+              },
+              [&] { f5_restore_shape(E, (int)N, (int)(L / 256 + 1)); });
 }
 
 int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
@@ -271,16 +290,20 @@ int b200tts_f5_synthesize(b200tts_engine* e, const int16_t* audio_host, int64_t 
     const long ns = 256L * (N - F - 1);
     B2_CHECK(ns > 0, "f5_synthesize: max_duration leaves no frames to generate");
     const int nm = f5_n_mels(E);
-    DevBuf<int16_t> d_audio((size_t)L), d_pcm((size_t)ns);
-    DevBuf<int> d_ids((size_t)n_text);
-    DevBuf<float> d_noise((size_t)N * nm), d_mel;
-    if (mel_host) d_mel.alloc((size_t)N * nm);
-    B2_CUDA(cudaMemcpyAsync(d_audio.p, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(d_ids.p, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(d_noise.p, noise_host, d_noise.n * sizeof(float), cudaMemcpyHostToDevice, s));
-    synth_device(E, d_audio.p, L, d_ids.p, n_text, N, d_noise.p, precision, n_steps, d_pcm.p, mel_host ? d_mel.p : nullptr);
-    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm.p, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
-    if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel.p, d_mel.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // persistent staging (stable addresses -> graph replay): [audio i16 | pcm i16] and [noise | mel | ids] blocks
+    const size_t Lp = (size_t)round_up(L, 8), nsp = (size_t)round_up(ns, 8), nmel = (size_t)N * nm;
+    E.io_i16.reserve(Lp + nsp);
+    E.io_f32a.reserve(nmel);
+    E.io_f32b.reserve(nmel + (size_t)round_up(n_text, 4));
+    int16_t* d_audio = E.io_i16.p; int16_t* d_pcm = E.io_i16.p + Lp;
+    float* d_noise = E.io_f32a.p; float* d_mel = mel_host ? E.io_f32b.p : nullptr;
+    int* d_ids = reinterpret_cast<int*>(E.io_f32b.p + nmel);
+    B2_CUDA(cudaMemcpyAsync(d_audio, audio_host, L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids, text_ids_host, n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_noise, noise_host, nmel * sizeof(float), cudaMemcpyHostToDevice, s));
+    synth_device(E, d_audio, L, d_ids, n_text, N, d_noise, precision, n_steps, d_pcm, d_mel);
+    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm, ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel, nmel * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *n_out = ns;
   });
@@ -294,17 +317,25 @@ int b200tts_aa_activation(b200tts_engine* e, const float* x_host, int B, int C, 
     B2_CHECK(B > 0 && C > 0 && L > 0, "aa_activation: empty input");
     cudaStream_t s = E.stream;
     const int Lo = post ? L + 30 : L;
-    DevBuf<float> x((size_t)B * C * L), xt((size_t)B * C * L), y((size_t)B * C * Lo), yt((size_t)B * C * Lo), al(C), ib(C);
-    std::vector<float> ha(C), hb(C);
+    const int Cp = (int)round_up(C, 2);          // the kernel walks channel pairs: an odd C gets one zero channel
+    DevBuf<float> x((size_t)B * Cp * L), xt((size_t)B * Cp * L), y((size_t)B * Cp * Lo), yt((size_t)B * Cp * Lo), al(Cp), ib(Cp);
+    std::vector<float> ha(Cp, 1.0f), hb(Cp, 1.0f);
     for (int i = 0; i < C; ++i) { ha[i] = expf(alpha_log[i]); hb[i] = 1.0f / (expf(beta_log[i]) + 1e-9f); }
-    B2_CUDA(cudaMemcpyAsync(x.p, x_host, x.n * sizeof(float), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(al.p, ha.data(), C * sizeof(float), cudaMemcpyHostToDevice, s));
-    B2_CUDA(cudaMemcpyAsync(ib.p, hb.data(), C * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (Cp == C) {
+      B2_CUDA(cudaMemcpyAsync(x.p, x_host, x.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    } else {
+      B2_CUDA(cudaMemsetAsync(x.p, 0, x.n * sizeof(float), s));
+      B2_CUDA(cudaMemcpy2DAsync(x.p, (size_t)Cp * L * sizeof(float), x_host, (size_t)C * L * sizeof(float), (size_t)C * L * sizeof(float),
+                                B, cudaMemcpyHostToDevice, s));
+    }
+    B2_CUDA(cudaMemcpyAsync(al.p, ha.data(), Cp * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(ib.p, hb.data(), Cp * sizeof(float), cudaMemcpyHostToDevice, s));
     aa_set_filter(taps12);
-    batched_transpose(x.p, xt.p, B, C, L, s);                       // (B,C,L) -> (B,L,C)
-    aa_snake(xt.p, 0, yt.p, 0, al.p, ib.p, B, C, L, precise != 0, post != 0, s);
-    batched_transpose(yt.p, y.p, B, Lo, C, s);                      // (B,Lo,C) -> (B,C,Lo)
-    B2_CUDA(cudaMemcpyAsync(y_host, y.p, y.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    batched_transpose(x.p, xt.p, B, Cp, L, s);                      // (B,C,L) -> (B,L,C)
+    aa_snake(xt.p, 0, yt.p, 0, al.p, ib.p, B, Cp, L, precise != 0, post != 0, s);
+    batched_transpose(yt.p, y.p, B, Lo, Cp, s);                     // (B,Lo,C) -> (B,C,Lo)
+    B2_CUDA(cudaMemcpy2DAsync(y_host, (size_t)C * Lo * sizeof(float), y.p, (size_t)Cp * Lo * sizeof(float), (size_t)C * Lo * sizeof(float),
+                              B, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
   });
 }
@@ -442,6 +473,49 @@ int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_hos
     cast_bf16_to_f32(o16.p, d_o32.p, (long)2 * N * D, s);
     B2_CUDA(cudaMemcpyAsync(out_host, d_o32.p, d_o32.n * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_bench_rowgemm(b200tts_engine* e, int B, int M, int N, int Cin, int taps, int dil, int groups, int epilogue,
+                          int iters, float* ms_out) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(ms_out && B > 0 && M > 0 && N > 0 && Cin > 0 && taps > 0 && dil > 0 && groups > 0 && iters > 0, "bench_rowgemm: bad arguments");
+    cudaStream_t s = E.stream;
+    const int ldx = (int)round_up((long)groups * Cin, 8);
+    const size_t xn = (size_t)B * M * ldx, wn = (size_t)groups * taps * N * Cin, on = (size_t)B * M * groups * N;
+    DevBuf<float> xf(xn), wf(wn), bias((size_t)groups * N), outf(on), resf(on);
+    DevBuf<__nv_bfloat16> x16(xn), out16(on);
+    std::vector<float> h(std::max(xn, wn));
+    unsigned st = 12345u;
+    auto rnd = [&] { st = st * 1664525u + 1013904223u; return ((st >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (size_t i = 0; i < xn; ++i) h[i] = rnd();
+    B2_CUDA(cudaMemcpyAsync(xf.p, h.data(), xn * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < wn; ++i) h[i] = rnd() * 0.05f;
+    B2_CUDA(cudaMemcpyAsync(wf.p, h.data(), wn * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemsetAsync(bias.p, 0, bias.n * sizeof(float), s));
+    B2_CUDA(cudaMemsetAsync(resf.p, 0, on * sizeof(float), s));
+    cast_f32_to_bf16(xf.p, x16.p, (long)xn, s);
+    TcWeight tw;
+    tc_weight_from_f32(tw, wf.p, groups, taps, N, Cin, s);
+    RowGemm p;
+    p.x = x16.p; p.x_bstride = (long)M * ldx; p.ldx = ldx; p.Lin = M;
+    p.Cin = Cin; p.N = N; p.taps = taps; p.dil = dil; p.center = (taps - 1) / 2; p.groups = groups; p.M = M; p.B = B;
+    p.out = epilogue == 2 ? (void*)out16.p : (void*)outf.p; p.out_bf16 = epilogue == 2;
+    p.o_bstride = (long)M * groups * N; p.ldo = groups * N; p.bias = bias.p;
+    if (epilogue == 1) { p.res = outf.p; p.gate = bias.p; }
+    for (int i = 0; i < 3; ++i) rowgemm_tc(p, tw, s);
+    cudaEvent_t a, b;
+    B2_CUDA(cudaEventCreate(&a)); B2_CUDA(cudaEventCreate(&b));
+    B2_CUDA(cudaEventRecord(a, s));
+    for (int i = 0; i < iters; ++i) rowgemm_tc(p, tw, s);
+    B2_CUDA(cudaEventRecord(b, s));
+    B2_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_out = ms / iters;
   });
 }
 

@@ -38,6 +38,10 @@ inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Bumped by every device (re)allocation / free of a DevBuf: captured CUDA graphs bake buffer addresses into their nodes,
+// so a cached graph is only replayed while the epoch it was captured under still holds (engine.cuh: GraphCache).
+extern unsigned long long g_alloc_epoch;
+
 // Device buffer with RAII.
 template <typename T>
 struct DevBuf {
@@ -56,11 +60,11 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) B2_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (count) { B2_CUDA(cudaMalloc((void**)&p, count * sizeof(T))); ++g_alloc_epoch; }
   }
   // grow-only (never shrinks): workspaces are sized by the largest request seen
   void reserve(size_t count) { if (count > n) alloc(count); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) { cudaFree(p); ++g_alloc_epoch; } p = nullptr; n = 0; }
 };
 
 // Epilogue activation selectors shared by the fp32 and tcgen05 GEMMs.

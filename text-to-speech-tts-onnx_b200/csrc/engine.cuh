@@ -56,6 +56,30 @@ struct ProfScope {
   ~ProfScope() { p.end(idx, s); }
 };
 
+// CUDA-graph cache: the hot path is thousands of short kernels per utterance (5138 for one F5 utterance), and enqueueing
+// them costs more host time (24 us / launch measured) than the GPU needs to run them. A call is identified by a key
+// (entry point, shapes, buffer addresses); the first call with a key runs eagerly (and grows workspaces / builds lazy weight
+// layouts), the second captures the same enqueue sequence into a graph, later ones replay it with one launch.
+struct GraphCache {
+  struct Entry {
+    std::vector<long long> key;
+    unsigned long long epoch = 0;      // g_alloc_epoch after the last eager run / at capture
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches = 0;   // kernels inside the graph (for b200tts_launch_count)
+  };
+  std::vector<Entry> entries;
+  bool enabled = true;
+  Entry* find(const std::vector<long long>& key) {
+    for (auto& e : entries) if (e.key == key) return &e;
+    return nullptr;
+  }
+  void clear() {
+    for (auto& e : entries) if (e.exec) cudaGraphExecDestroy(e.exec);
+    entries.clear();
+  }
+  ~GraphCache() { clear(); }
+};
+
 struct BigVGANModel;
 struct F5Model;
 
@@ -65,6 +89,9 @@ struct Engine {
   bool own_stream = false;
   std::map<std::string, Tensor> weights;   // reference state_dict names, prefixed "bigvgan." / "dit." / "vocos."
   Profiler prof;
+  GraphCache graphs;
+  DevBuf<float> io_f32a, io_f32b;          // persistent staging of the host-pointer entry points (stable addresses for graphs)
+  DevBuf<int16_t> io_i16;
   std::string prof_report;                 // last JSON report (owned here so the C ABI can hand out a pointer)
   BigVGANModel* bigvgan = nullptr;         // owned; freed by bigvgan_free / f5_free in ~Engine (api.cu)
   F5Model* f5 = nullptr;
@@ -79,5 +106,56 @@ struct Engine {
 };
 
 enum Precision : int { PREC_F32 = 0, PREC_BF16 = 1 };
+
+// Run `body` (a sequence of enqueues on e.stream, no host synchronisation inside) through the graph cache.
+// `on_replay` restores whatever host-side state `body` would have set (it does not run when the graph is replayed).
+template <typename Body, typename OnReplay>
+void run_graphed(Engine& e, const std::vector<long long>& key, Body&& body, OnReplay&& on_replay) {
+  if (!e.graphs.enabled || e.prof.enabled) { body(); return; }
+  GraphCache::Entry* en = e.graphs.find(key);
+  if (en == nullptr) {
+    if (e.graphs.entries.size() >= 64) e.graphs.clear();
+    body();
+    GraphCache::Entry ne; ne.key = key; ne.epoch = g_alloc_epoch;
+    e.graphs.entries.push_back(std::move(ne));
+    return;
+  }
+  if (en->epoch != g_alloc_epoch) {           // some buffer moved since: the addresses baked into the graph may be stale
+    if (en->exec) { cudaGraphExecDestroy(en->exec); en->exec = nullptr; }
+    body();
+    en = e.graphs.find(key);
+    if (en) en->epoch = g_alloc_epoch;
+    return;
+  }
+  if (en->exec == nullptr) {
+    const unsigned long long l0 = g_launch_count;
+    cudaGraph_t graph = nullptr;
+    B2_CUDA(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(e.stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    B2_CUDA(cudaStreamEndCapture(e.stream, &graph));
+    if (g_alloc_epoch != en->epoch) {           // body allocated while capturing: do not trust the capture, run eagerly
+      cudaGraphDestroy(graph);
+      en->epoch = g_alloc_epoch;
+      body();
+      return;
+    }
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) fail(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(err));
+    en->exec = exec;
+    en->launches = g_launch_count - l0;
+    g_launch_count = l0;                        // counted per replay below
+  }
+  B2_CUDA(cudaGraphLaunch(en->exec, e.stream));
+  g_launch_count += en->launches;
+  on_replay();
+}
 
 }  // namespace b200tts

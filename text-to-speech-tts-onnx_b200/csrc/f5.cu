@@ -370,6 +370,19 @@ void f5_set_rope(Engine& e, const float* d_cos, const float* d_sin) {
   m.cur_cos = m.rope_c.p; m.cur_sin = m.rope_s.p;
 }
 
+void f5_rope_buffers(Engine& e, float** d_cos, float** d_sin) {
+  F5Model& m = model(e);
+  m.rope_c.reserve((size_t)m.N * m.hd); m.rope_s.reserve((size_t)m.N * m.hd);
+  m.cur_cos = m.rope_c.p; m.cur_sin = m.rope_s.p;
+  *d_cos = m.rope_c.p; *d_sin = m.rope_s.p;
+}
+
+void f5_restore_shape(Engine& e, int N, int ref_len) {
+  F5Model& m = model(e);
+  m.N = N; m.Npad = (int)round_up(N, 8); m.ref_len = ref_len;
+  m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;
+}
+
 void f5_prepare_cond(Engine& e) {
   F5Model& m = model(e);
   Epi ep; ep.bias = m.wc.bias.p;

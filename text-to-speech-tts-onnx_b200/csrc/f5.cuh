@@ -28,6 +28,10 @@ float* f5_noise(Engine& e);
 void f5_begin(Engine& e, int N);
 // rope rows [N][64] fp32 device (cos, sin) -- defaults to the model's fp16-rounded tables, may be overridden
 void f5_set_rope(Engine& e, const float* d_cos, const float* d_sin);
+// same, but returns the device buffers ([N][64] each) for the caller to fill (then selects them)
+void f5_rope_buffers(Engine& e, float** d_cos, float** d_sin);
+// host-side shape state of the current utterance (what f5_preprocess sets), for graph replays that skip the enqueue code
+void f5_restore_shape(Engine& e, int N, int ref_len);
 // must be called after cond / cond_drop changed and before f5_steps: precomputes the step-invariant half of the
 // input embedding (W_c . cond + b for both CFG rows)
 void f5_prepare_cond(Engine& e);

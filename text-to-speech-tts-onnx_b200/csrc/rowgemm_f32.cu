@@ -5,6 +5,7 @@
 namespace b200tts {
 
 unsigned long long g_launch_count = 0;
+unsigned long long g_alloc_epoch = 0;
 
 namespace {
 

@@ -129,6 +129,107 @@ __device__ __forceinline__ void epilogue_chunk16(const TcArgs& a, const uint32_t
   }
 }
 
+// ---- v2 epilogue: 32 output columns [n, n+32) of one row per call, loads batched ahead of the math -------------------
+// The first version walked 4-column groups with bias -> gate -> residual loads each waiting on the previous group's
+// store (possible aliasing), which serialised ~3 L2 round trips per group: 70k cycles per 256x128 tile on the DiT
+// GEMMs (ncu source page, profiles/r01). Now: the residual of the NEXT chunk is prefetched into registers while this
+// chunk is processed (and the first chunk's before the accumulator is even complete), bias / gate / RoPE tables are
+// fetched through the read-only path in one batch, then math, then stores.
+__device__ __forceinline__ void epi_prefetch_res(const TcArgs& a, bool row_ok, long obase, long rowflat, int n, float4 (&res)[8]) {
+#pragma unroll
+  for (int v4 = 0; v4 < 8; ++v4) {
+    const int nn = n + v4 * 4;
+    const long flat = rowflat + nn;
+    const bool ok = row_ok && nn < a.N && flat >= 0 && flat < a.o_limit;
+    res[v4] = ok ? *reinterpret_cast<const float4*>(a.res + obase + flat) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(x, y), p1 = __floats2bfloat162_rn(z, w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  return pk;
+}
+
+// ROPE = true: the fused q/k/v epilogue (bias, interleaved RoPE on columns < rope_cols, V written transposed); otherwise the
+// general one (bias, activation, gate, residual, accumulate, scale, optional second bf16 copy). Two instantiations keep the
+// live register set of each under the 168-register cap of a 320-thread CTA.
+template <bool ROPE>
+__device__ __forceinline__ void epilogue_chunk32(const TcArgs& a, const uint32_t (&r)[32], const float4 (&res)[8], int g, int t,
+                                                 int n, long obase, long rowflat) {
+  if (n >= a.N) return;
+  const int gn = g * a.N + n;
+  const bool rope = ROPE && n < a.rope_cols;
+  const int tt = ROPE ? t % a.rope_rows : 0;
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {         // two sub-batches of 16 columns: loads first, then math + stores
+    float4 bias[4], gate[4], rc[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = hb * 16 + u * 4;
+      const bool in = n + c < a.N;
+      bias[u] = (a.bias && in) ? __ldg(reinterpret_cast<const float4*>(a.bias + gn + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!ROPE && a.gate) gate[u] = in ? __ldg(reinterpret_cast<const float4*>(a.gate + gn + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rope) {
+        const int d = (n + c) & 63;
+        rc[u] = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
+        rs[u] = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int v4 = hb * 4 + u;
+      const int nn = n + v4 * 4;
+      const long flat = rowflat + nn;
+      if (nn >= a.N || flat < 0 || flat >= a.o_limit) continue;
+      float v[4];
+      v[0] = __uint_as_float(r[v4 * 4 + 0]) + bias[u].x; v[1] = __uint_as_float(r[v4 * 4 + 1]) + bias[u].y;
+      v[2] = __uint_as_float(r[v4 * 4 + 2]) + bias[u].z; v[3] = __uint_as_float(r[v4 * 4 + 3]) + bias[u].w;
+      if (ROPE) {
+        if (rope) {                          // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+          const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
+          v[0] = x0 * rc[u].x - x1 * rs[u].x; v[1] = x1 * rc[u].y + x0 * rs[u].y;
+          v[2] = x2 * rc[u].z - x3 * rs[u].z; v[3] = x3 * rc[u].w + x2 * rs[u].w;
+        }
+        if (a.vt_out != nullptr && nn >= a.vt_col0) {
+          const int cv = nn - a.vt_col0;
+          const int hh = cv >> 6, d = cv & 63;
+          __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
+          continue;
+        }
+      } else {
+        if (a.act != ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
+        }
+        if (a.gate) { v[0] *= gate[u].x; v[1] *= gate[u].y; v[2] *= gate[u].z; v[3] *= gate[u].w; }
+        if (a.res) { v[0] += res[v4].x; v[1] += res[v4].y; v[2] += res[v4].z; v[3] += res[v4].w; }
+      }
+      if (a.out_bf16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + flat;
+        if (!ROPE && a.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] += __bfloat162float(o[i]);
+        }
+        *reinterpret_cast<uint2*>(o) = pack_bf16x4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
+      } else {
+        float* o = reinterpret_cast<float*>(a.out) + obase + flat;
+        if (!ROPE && a.accumulate) {
+          const float4 rr = *reinterpret_cast<const float4*>(o);
+          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
+      }
+      if (!ROPE && a.out2 != nullptr)      // second copy of the result in bf16 (the next GEMM's A operand)
+        *reinterpret_cast<uint2*>(a.out2 + obase + flat) = pack_bf16x4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
+    }
+  }
+}
+
 // =============================================================================================
 // v2: persistent 256 x BN tiles, halo A tiles, double-buffered TMEM accumulators
 // =============================================================================================
@@ -150,6 +251,7 @@ struct Tc2Sched {
 // the shifted start address is correct and the matrix-base-offset field must stay 0 (setting it to the row phase
 // (addr >> 7) & 7 double-applies the rotation and corrupts every tap whose shift is not a multiple of 8 rows).
 
+template <bool ROPE>
 __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const TcArgs a, const Tc2Sched sc) {
@@ -213,44 +315,58 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
-        const int rem = tile % per_bg;
-        const int mt = rem % sc.m_tiles;
-        const int halves = (mt * BM2 + 128 < a.M) ? 2 : 1;          // skip the second M half of a ragged last tile
-        const int acc = sc.nacc == 2 ? (it & 1) : 0;
-        const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
-        mbar_wait(&acc_empty[acc], accphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * sc.half_stride);
-        for (int c = 0; c < a.kchunks; ++c) {
-          int ksteps = (a.Cin - c * BK + UMMA_K - 1) / UMMA_K;
-          if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
-          mbar_wait(&a_full[sa], pa);
-          const uint32_t a_base = smem_u32(smem_a + sa * a_stage_bytes);
-          for (int j = 0; j < a.taps; ++j) {
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(smem_b + sb * b_stage_bytes);
-            const uint32_t a_tap = a_base + (uint32_t)(j * a.dil) * 128u;
-            for (int h = 0; h < halves; ++h) {
-              const uint32_t a_addr = a_tap + (uint32_t)h * (128u * 128u);
-              for (int k = 0; k < ksteps; ++k) {
-                umma_bf16(d0 + (uint32_t)(h * sc.half_stride), make_desc_sw128(a_addr + 32u * k),
-                          make_desc_sw128(b_base + 32u * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+    // ===== MMA issuer: the whole warp walks the (warp-uniform) loops, one elected lane issues =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a)), b_lo0 = desc_lo_sw128(smem_u32(smem_b));
+    const uint32_t a_stage_lo = (uint32_t)a_stage_bytes >> 4, b_stage_lo = (uint32_t)b_stage_bytes >> 4;
+    const uint32_t tap_lo = (uint32_t)a.dil * 8u;                   // dil rows x 128 B, in 16-byte units
+    const uint32_t hs = (uint32_t)sc.half_stride;
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
+      const int rem = tile % per_bg;
+      const int mt = rem % sc.m_tiles;
+      const bool two = (mt * BM2 + 128 < a.M);                      // skip the second M half of a ragged last tile
+      const int acc = sc.nacc == 2 ? (it & 1) : 0;
+      const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+      mbar_wait(&acc_empty[acc], accphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)acc * 2u * hs, d1 = d0 + hs;
+      for (int c = 0; c < a.kchunks; ++c) {
+        int ksteps = (a.Cin - c * BK + UMMA_K - 1) / UMMA_K;
+        if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+        mbar_wait(&a_full[sa], pa);
+        uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
+        for (int j = 0; j < a.taps; ++j, a_lo += tap_lo) {
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
+          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
+          if (elect_one()) {
+            if (ksteps == 4) {
+              umma_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, first);
+              umma_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
+              umma_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
+              umma_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
+              if (two) {
+                umma_bf16_lohi(d1, a_lo + 1024 + 0, b_lo + 0, idesc, first);      // +128 rows x 128 B = 1024 x 16 B
+                umma_bf16_lohi(d1, a_lo + 1024 + 2, b_lo + 2, idesc, 1u);
+                umma_bf16_lohi(d1, a_lo + 1024 + 4, b_lo + 4, idesc, 1u);
+                umma_bf16_lohi(d1, a_lo + 1024 + 6, b_lo + 6, idesc, 1u);
               }
+            } else {
+              for (int k = 0; k < ksteps; ++k) umma_bf16_lohi(d0, a_lo + 2 * k, b_lo + 2 * k, idesc, (first | (uint32_t)k) ? 1u : 0u);
+              if (two)
+                for (int k = 0; k < ksteps; ++k) umma_bf16_lohi(d1, a_lo + 1024 + 2 * k, b_lo + 2 * k, idesc, (first | (uint32_t)k) ? 1u : 0u);
             }
             umma_commit(&b_empty[sb]);
-            if (++sb == sc.nB) { sb = 0; pb ^= 1; }
+            if (j == a.taps - 1) umma_commit(&a_empty[sa]);
+            if (j == a.taps - 1 && c == a.kchunks - 1) umma_commit(&acc_full[acc]);
           }
-          umma_commit(&a_empty[sa]);
-          if (++sa == sc.nA) { sa = 0; pa ^= 1; }
+          __syncwarp();
+          if (++sb == sc.nB) { sb = 0; pb ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
+        if (++sa == sc.nA) { sa = 0; pa ^= 1; }
       }
     }
   } else {
@@ -265,18 +381,27 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
       const int t = mt * BM2 + h * 128 + q * 32 + lane;
       const int acc = sc.nacc == 2 ? (it & 1) : 0;
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+      const bool half_ok = mt * BM2 + h * 128 < a.M;          // warp-uniform: this half holds valid rows
+      const long obase = (long)b * a.o_bstride;
+      const long rowflat = (long)t * a.ldo + (long)g * a.N + a.o_shift;
+      const bool row_ok = t < a.M;
+      float4 res[8];
+      if (!ROPE && a.res != nullptr && half_ok) epi_prefetch_res(a, row_ok, obase, rowflat, n0, res);   // overlaps the main loop
       mbar_wait(&acc_full[acc], accphase);
       tc_fence_after();
-      if (mt * BM2 + h * 128 < a.M) {                       // warp-uniform: this half holds valid rows
-        const long obase = (long)b * a.o_bstride;
-        const long rowflat = (long)t * a.ldo + (long)g * a.N + a.o_shift;
-        const bool row_ok = t < a.M;
+      if (half_ok) {
         const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * sc.half_stride + h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
-        for (int cb = 0; cb < a.BN; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)cb, r);
+        float4 res_b[8];
+        auto chunk = [&](int cb, const float4 (&cur)[8], float4 (&nxt)[8]) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)cb, r);
+          if (!ROPE && a.res != nullptr && cb + 32 < a.BN) epi_prefetch_res(a, row_ok, obase, rowflat, n0 + cb + 32, nxt);
           tmem_ld_wait();
-          if (row_ok) epilogue_chunk16(a, r, b, g, t, n0 + cb, obase, rowflat);
+          if (row_ok) epilogue_chunk32<ROPE>(a, r, cur, g, t, n0 + cb, obase, rowflat);
+        };
+        for (int cb = 0; cb < a.BN; cb += 64) {              // ping-pong residual buffers: no register copies
+          chunk(cb, res, res_b);
+          if (cb + 32 < a.BN) chunk(cb + 32, res_b, res);
         }
       }
       tc_fence_before();
@@ -584,10 +709,17 @@ void launch_v2(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   const int smem = nA * a_stage + nB * b_stage + 1024 + bar_bytes;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   });
   const int grid = sc.num_tiles < sm_count() ? sc.num_tiles : sm_count();
-  rowgemm_tc2_kernel<<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
+  if (p.rope_cos != nullptr) {
+    B2_CHECK(p.gate == nullptr && p.res == nullptr && !p.accumulate && p.act == ACT_NONE && p.out2 == nullptr,
+             "rowgemm_tc: the rope epilogue takes bias only");
+    rowgemm_tc2_kernel<true><<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
+  } else {
+    rowgemm_tc2_kernel<false><<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
+  }
   B2_LAUNCH_CHECK();
   count_launch();
 }

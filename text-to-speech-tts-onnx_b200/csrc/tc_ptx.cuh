@@ -83,6 +83,37 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 }
 
 
+// One lane of a converged warp (CUTLASS elect_one_sync): keeps the surrounding code warp-uniform so that ptxas can hold
+// descriptors / addresses in uniform registers instead of wrapping every UTCHMMA in an ELECT + BRA.U.ANY loop.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred;
+}
+
+// tcgen05.mma with the two 64-bit shared-memory descriptors given as (lo, hi) halves: hi is a per-kernel constant and
+// lo = ((addr >> 4) & 0x3FFF) | 1 << 16 advances by plain 32-bit adds (+2 per 32-byte K step, +8 per 128-byte row).
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
