@@ -1,22 +1,29 @@
 // Shifted-row GEMM on the 5th-gen tensor cores (sm_100a): TMA -> 128B-swizzled shared memory ->
-// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld -> shared-memory transpose -> coalesced epilogue.
 //
-//   D[128 rows (time) x BN (out channels)] += A[128 x 64] . B[BN x 64]^T     per (tap, 64-channel chunk)
+//   D[BM rows (time) x BN (out channels)] += A[BM x 64] . B[BN x 64]^T     per (tap, 64-channel chunk)
 //
-// A tiles are boxes {64 ch, 128 rows, 1 batch} of the channels-last activation tensor, fetched at row
-// coordinate t0 + (tap - center) * dil: rows outside [0, Lin) (negative included) and channels beyond Cin
-// are zero-filled by the TMA unit, which IS the convolution's zero padding - no im2col, no halo code.
+// A tiles are boxes {64 ch, 64 rows, 1 batch} of the channels-last activation tensor, fetched at row
+// coordinate t0 - center*dil: rows outside [0, Lin) (negative included) and channels beyond Cin are zero-filled by
+// the TMA unit, which IS the convolution's zero padding - no im2col, no halo code.
 // B tiles are boxes {64 ch, BN, 1} of W[g*taps + tap][n][c].
 //
-// Two kernels share the epilogue:
-//  * rowgemm_tc2_kernel (default): persistent, one CTA per SM, 256 x BN output tiles (two M=128 accumulators that
-//    share every B tile), double-buffered accumulators in TMEM (512 columns) so the epilogue of tile i overlaps the
-//    main loop of tile i+1. The A operand of a convolution is fetched ONCE per 64-channel chunk as a
-//    (256 + (taps-1)*dil)-row halo tile; every tap is an MMA whose A descriptor starts (tap*dil) rows further down
-//    that tile (plain descriptor start-address shift; the swizzle XOR is a function of the absolute smem address), so L2->SMEM traffic per FLOP
-//    is ~1/256 + 1/(taps*BN) B instead of v1's 1/128 + 1/128 (which made v1 L2-bandwidth-bound at ~25 % of peak).
-//    320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue.
-//  * rowgemm_tc_kernel (v1, B200TTS_GEMM=v1): one 128 x BN tile per 192-thread CTA, per-tap A tiles.
+// Kernel (rowgemm_tc3_kernel): persistent, one CTA per SM, BM = 256 (two M=128 accumulators that share every B tile)
+// or BM = 128 (one accumulator; picked when 256-row tiles would leave SMs idle), accumulators double-buffered in TMEM
+// when they fit so the epilogue of tile i overlaps the main loop of tile i+1. The A operand of a convolution is
+// fetched ONCE per 64-channel chunk as a (BM + (taps-1)*dil)-row halo tile; every tap is an MMA whose A descriptor
+// starts (tap*dil) rows further down that tile (plain descriptor start-address shift; the swizzle XOR is a function of
+// the absolute smem address).
+// 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue.
+//
+// Epilogue (r01c): the first two versions had every thread own one output ROW and walk its columns, which (a) made each
+// warp-wide global access touch 32 different 128-byte lines, and (b) unrolled into 11.6k SASS instructions executed
+// once per tile, so the warps sat in instruction-fetch (stall_no_inst 25 %) and L2-latency (stall_long_sb 39 %) stalls:
+// 70-120k cycles per tile against an 8k-cycle main loop (ncu, profiles/r01). Now each warp moves a 32x32 fp32 block
+// TMEM -> registers -> swizzled shared memory, re-reads it with 8 lanes across a row's 32 columns (4 rows per
+// instruction) and applies bias / activation / gate / residual / RoPE on that layout, so every global load and store
+// is a run of full 128-byte (fp32) or 64-byte (bf16) row segments; the residual of the next block is prefetched while
+// the current one is processed; the loop over blocks is not unrolled (~300 instructions per block).
 #include "rowgemm_tc.cuh"
 
 #include <cstdlib>
@@ -29,121 +36,35 @@ namespace b200tts {
 
 namespace {
 
-constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int MAX_STAGES = 8;
+constexpr int NTHREADS3 = 320;         // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int A_BOX_ROWS = 64;
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;      // one 32x32 fp32 block per epilogue warp
+constexpr int EPI_BYTES = 8 * EPI_STAGE_BYTES;
 
 using namespace tc;
 
+enum EpiKind : int { EPI_STD = 0, EPI_ROPE = 1 };
+
 struct TcArgs {
   int Cin, N, taps, dil, center, groups, M;
-  int BN, stages, kchunks;      // kchunks = ceil(Cin / 64)
+  int BN, kchunks;              // kchunks = ceil(Cin / 64)
   void* out; long o_bstride; int ldo; long o_shift; long o_limit; int out_bf16;
-  const float* bias; const float* gate; const float* res; int accumulate; float scale; int act;
+  const float* bias; const float* gate; const float* res; int accumulate; float scale;
   const float* rope_cos; const float* rope_sin; int rope_cols, rope_rows;
   __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
   __nv_bfloat16* out2;          // optional bf16 copy of the output (same indexing)
 };
 
-// Epilogue of 16 consecutive output columns [n, n+16) of one output row t (registers r[] straight from tcgen05.ld):
-// bias, activation, fused q/k RoPE + transposed V store, gate, residual, accumulate, scale, fp32 or bf16 store.
-__device__ __forceinline__ void epilogue_chunk16(const TcArgs& a, const uint32_t (&r)[16], int b, int g, int t, int n,
-                                                 long obase, long rowflat) {
-  if (n >= a.N) return;
-  const int gn = g * a.N + n;
-#pragma unroll
-  for (int v4 = 0; v4 < 4; ++v4) {
-    const int nn = n + v4 * 4;
-    if (nn >= a.N) break;
-    const long flat = rowflat + nn;
-    if (flat < 0 || flat >= a.o_limit) continue;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[v4 * 4 + i]);
-    if (a.bias) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + gn + v4 * 4));
-      v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
-    }
-    if (a.act != ACT_NONE) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
-    }
-    if (a.rope_cos != nullptr) {
-      const int tt = t % a.rope_rows;
-      if (nn < a.rope_cols) {            // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
-        const int d = nn & 63;
-        const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
-        const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
-        const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
-        v[0] = x0 * cc.x - x1 * ss.x; v[1] = x1 * cc.y + x0 * ss.y;
-        v[2] = x2 * cc.z - x3 * ss.z; v[3] = x3 * cc.w + x2 * ss.w;
-      }
-      if (a.vt_out != nullptr && nn >= a.vt_col0) {
-        const int cv = nn - a.vt_col0;
-        const int hh = cv >> 6, d = cv & 63;
-        __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
-        continue;
-      }
-    }
-    if (a.gate) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(a.gate + gn + v4 * 4));
-      v[0] *= gg.x; v[1] *= gg.y; v[2] *= gg.z; v[3] *= gg.w;
-    }
-    if (a.res) {
-      const float4 rr = *reinterpret_cast<const float4*>(a.res + obase + flat);
-      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-    }
-    if (a.out_bf16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + flat;
-      if (a.accumulate) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] += __bfloat162float(o[i]);
-      }
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * a.scale, v[1] * a.scale);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2] * a.scale, v[3] * a.scale);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(o) = pk;
-    } else {
-      float* o = reinterpret_cast<float*>(a.out) + obase + flat;
-      if (a.accumulate) {
-        const float4 rr = *reinterpret_cast<const float4*>(o);
-        v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-      }
-      *reinterpret_cast<float4*>(o) = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
-    }
-    if (a.out2 != nullptr) {             // second copy of the result in bf16 (the next GEMM's A operand)
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0] * a.scale, v[1] * a.scale);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2] * a.scale, v[3] * a.scale);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(a.out2 + obase + flat) = pk;
-    }
-  }
-}
-
-// ---- v2 epilogue: 32 output columns [n, n+32) of one row per call, loads batched ahead of the math -------------------
-// The first version walked 4-column groups with bias -> gate -> residual loads each waiting on the previous group's
-// store (possible aliasing), which serialised ~3 L2 round trips per group: 70k cycles per 256x128 tile on the DiT
-// GEMMs (ncu source page, profiles/r01). Now: the residual of the NEXT chunk is prefetched into registers while this
-// chunk is processed (and the first chunk's before the accumulator is even complete), bias / gate / RoPE tables are
-// fetched through the read-only path in one batch, then math, then stores.
-__device__ __forceinline__ void epi_prefetch_res(const TcArgs& a, bool row_ok, long obase, long rowflat, int n, float4 (&res)[8]) {
-#pragma unroll
-  for (int v4 = 0; v4 < 8; ++v4) {
-    const int nn = n + v4 * 4;
-    const long flat = rowflat + nn;
-    const bool ok = row_ok && nn < a.N && flat >= 0 && flat < a.o_limit;
-    res[v4] = ok ? *reinterpret_cast<const float4*>(a.res + obase + flat) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
+struct Tc3Sched {
+  int bm;                               // 256 or 128 output rows per tile
+  int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
+  int a_rows;                           // rows per A stage (multiple of 64) = round_up(bm + (taps-1)*dil, 64)
+  int nA, nB;                           // ring depths
+  int half_stride, nacc;                // TMEM columns per 128-row accumulator; accumulator stages (1 or 2)
+};
 
 __device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w) {
   __nv_bfloat162 p0 = __floats2bfloat162_rn(x, y), p1 = __floats2bfloat162_rn(z, w);
@@ -153,97 +74,149 @@ __device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w)
   return pk;
 }
 
-// ROPE = true: the fused q/k/v epilogue (bias, interleaved RoPE on columns < rope_cols, V written transposed); otherwise the
-// general one (bias, activation, gate, residual, accumulate, scale, optional second bf16 copy). Two instantiations keep the
-// live register set of each under the 168-register cap of a 320-thread CTA.
-template <bool ROPE>
-__device__ __forceinline__ void epilogue_chunk32(const TcArgs& a, const uint32_t (&r)[32], const float4 (&res)[8], int g, int t,
-                                                 int n, long obase, long rowflat) {
-  if (n >= a.N) return;
-  const int gn = g * a.N + n;
-  const bool rope = ROPE && n < a.rope_cols;
-  const int tt = ROPE ? t % a.rope_rows : 0;
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Activations of the bf16 engine (operands are already rounded to 8 mantissa bits, so the 2^-11 MUFU error is noise).
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+  if (ACT == ACT_GELU_TANH) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float u = k0 * (v + k1 * v * v * v);
+    return 0.5f * v * (1.0f + tanh_fast(u));
+  } else if (ACT == ACT_MISH) {            // x * tanh(softplus(x)), softplus threshold 20 (F5 modules.py:172)
+    const float sp = v > 20.0f ? v : __logf(1.0f + __expf(v));
+    return v * tanh_fast(sp);
+  } else if (ACT == ACT_GELU_ERF) {
+    return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
+  }
+  return v;
+}
+
+// One epilogue warp, one accumulator (128 TMEM lanes x BN columns): this warp owns lanes [32q, 32q+32) = tile rows
+// row0 .. row0+31 and walks the 32-column blocks cb = cb_first, cb_first + cb_step, ... < BN.
+//   phase 1  tcgen05.ld 32 columns of the lane's row -> 8 x STS.128 into the warp's swizzled 4 KB staging block
+//   phase 2  lane = (sub = lane/8, c4 = lane%8): rows i*4 + sub (i < 8), columns c4*4 .. c4*4+3 : LDS.128, math, global I/O
+struct EpiPos {
+  int sub, c4, t_row0, n0;
+  long obase, gshift;
+};
+
+__device__ __forceinline__ long epi_flat(const TcArgs& a, const EpiPos& p, int i, int n) {
+  return (long)(p.t_row0 + i * 4 + p.sub) * a.ldo + p.gshift + n;
+}
+__device__ __forceinline__ bool epi_ok(const TcArgs& a, const EpiPos& p, int i, int n, long flat) {
+  return (p.t_row0 + i * 4 + p.sub) < a.M && n < a.N && flat >= 0 && flat < a.o_limit;
+}
+// residual operand of block cb, in the phase-2 layout (issued one block ahead: the first before the accumulator is ready,
+// the next ones at the end of the previous block's phase 2)
+__device__ __forceinline__ void epi_load_res(const TcArgs& a, const EpiPos& p, int cb, float4 (&res)[8]) {
+  const int n = p.n0 + cb + p.c4 * 4;
+  const bool in = cb < a.BN;
 #pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {         // two sub-batches of 16 columns: loads first, then math + stores
-    float4 bias[4], gate[4], rc[4], rs[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = hb * 16 + u * 4;
-      const bool in = n + c < a.N;
-      bias[u] = (a.bias && in) ? __ldg(reinterpret_cast<const float4*>(a.bias + gn + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!ROPE && a.gate) gate[u] = in ? __ldg(reinterpret_cast<const float4*>(a.gate + gn + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rope) {
-        const int d = (n + c) & 63;
-        rc[u] = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + d));
-        rs[u] = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + d));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int v4 = hb * 4 + u;
-      const int nn = n + v4 * 4;
-      const long flat = rowflat + nn;
-      if (nn >= a.N || flat < 0 || flat >= a.o_limit) continue;
-      float v[4];
-      v[0] = __uint_as_float(r[v4 * 4 + 0]) + bias[u].x; v[1] = __uint_as_float(r[v4 * 4 + 1]) + bias[u].y;
-      v[2] = __uint_as_float(r[v4 * 4 + 2]) + bias[u].z; v[3] = __uint_as_float(r[v4 * 4 + 3]) + bias[u].w;
-      if (ROPE) {
-        if (rope) {                          // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
-          const float x0 = v[0], x1 = v[1], x2 = v[2], x3 = v[3];
-          v[0] = x0 * rc[u].x - x1 * rs[u].x; v[1] = x1 * rc[u].y + x0 * rs[u].y;
-          v[2] = x2 * rc[u].z - x3 * rs[u].z; v[3] = x3 * rc[u].w + x2 * rs[u].w;
-        }
-        if (a.vt_out != nullptr && nn >= a.vt_col0) {
-          const int cv = nn - a.vt_col0;
-          const int hh = cv >> 6, d = cv & 63;
-          __nv_bfloat16* o = a.vt_out + ((long)((t / a.rope_rows) * a.vt_heads + hh) * 64 + d) * a.vt_ld + tt;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o[(long)i * a.vt_ld] = __float2bfloat16_rn(v[i]);
-          continue;
-        }
-      } else {
-        if (a.act != ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = act_apply(v[i], a.act);
-        }
-        if (a.gate) { v[0] *= gate[u].x; v[1] *= gate[u].y; v[2] *= gate[u].z; v[3] *= gate[u].w; }
-        if (a.res) { v[0] += res[v4].x; v[1] += res[v4].y; v[2] += res[v4].z; v[3] += res[v4].w; }
-      }
-      if (a.out_bf16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + flat;
-        if (!ROPE && a.accumulate) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] += __bfloat162float(o[i]);
-        }
-        *reinterpret_cast<uint2*>(o) = pack_bf16x4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
-      } else {
-        float* o = reinterpret_cast<float*>(a.out) + obase + flat;
-        if (!ROPE && a.accumulate) {
-          const float4 rr = *reinterpret_cast<const float4*>(o);
-          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-        }
-        *reinterpret_cast<float4*>(o) = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
-      }
-      if (!ROPE && a.out2 != nullptr)      // second copy of the result in bf16 (the next GEMM's A operand)
-        *reinterpret_cast<uint2*>(a.out2 + obase + flat) = pack_bf16x4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const long flat = epi_flat(a, p, i, n);
+    res[i] = (in && epi_ok(a, p, i, n, flat)) ? *reinterpret_cast<const float4*>(a.res + p.obase + flat) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-// =============================================================================================
-// v2: persistent 256 x BN tiles, halo A tiles, double-buffered TMEM accumulators
-// =============================================================================================
-constexpr int BM2 = 256;
-constexpr int NTHREADS2 = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int A_BOX_ROWS = 64;
-constexpr int MAX_A_STAGES = 4, MAX_B_STAGES = 8;
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, uint32_t taddr, float* stg, int lane, int g,
+                                              int cb_first, int cb_step, float4 (&res)[8]) {
+  const int sub = p.sub, c4 = p.c4, n0 = p.n0;
+  const bool has_res = KIND == EPI_STD && a.res != nullptr;
+#pragma unroll 1
+  for (int cb = cb_first; cb < a.BN; cb += cb_step) {
+    if (n0 + cb >= a.N) break;
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)cb, r);
+    tmem_ld_wait();
 
-struct Tc2Sched {
-  int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
-  int a_rows;                           // rows per A stage (multiple of 64) = round_up(256 + (taps-1)*dil, 64)
-  int nA, nB;                           // ring depths
-  int half_stride, nacc;                // TMEM columns between the two M halves; accumulator stages (1 or 2)
-};
+    if (KIND == EPI_ROPE && a.vt_out != nullptr && n0 + cb >= a.vt_col0) {
+      // V columns: written transposed, vt[(batch*heads + h)*64 + d][t]; in the row-per-lane layout consecutive lanes are
+      // consecutive t, so each store instruction writes one 64-byte run.
+      const int t = p.t_row0 + lane;
+      if (t < a.M) {
+        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int n = n0 + cb + k * 4;
+          if (n < a.N) {
+            const float4 bi = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cv = n - a.vt_col0;
+            __nv_bfloat16* o = a.vt_out + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
+            o[0] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 0]) + bi.x);
+            o[(long)a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 1]) + bi.y);
+            o[2L * a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 2]) + bi.z);
+            o[3L * a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 3]) + bi.w);
+          }
+        }
+      }
+      continue;
+    }
+
+    // phase 1: row `lane`, 16-byte chunk k goes to chunk slot k ^ (lane & 7) (conflict-free per quarter warp)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      *reinterpret_cast<uint4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
+    __syncwarp();
+
+    // phase 2
+    const int n = n0 + cb + c4 * 4;
+    const bool n_ok = n < a.N;
+    const float4 bias = (a.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(a.bias + (long)g * a.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gate = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (KIND == EPI_STD && a.gate && n_ok) gate = __ldg(reinterpret_cast<const float4*>(a.gate + (long)g * a.N + n));
+    const bool rope = KIND == EPI_ROPE && n < a.rope_cols;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + sub;
+      const long flat = epi_flat(a, p, i, n);
+      const bool ok = epi_ok(a, p, i, n, flat);
+      const float4 acc = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
+      float v0 = acc.x + bias.x, v1 = acc.y + bias.y, v2 = acc.z + bias.z, v3 = acc.w + bias.w;
+      if (KIND == EPI_ROPE) {
+        if (rope && ok) {                       // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+          const int tt = (p.t_row0 + row) % a.rope_rows;
+          const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + (n & 63)));
+          const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + (n & 63)));
+          const float x0 = v0, x1 = v1, x2 = v2, x3 = v3;
+          v0 = x0 * cc.x - x1 * ss.x; v1 = x1 * cc.y + x0 * ss.y;
+          v2 = x2 * cc.z - x3 * ss.z; v3 = x3 * cc.w + x2 * ss.w;
+        }
+      } else {
+        if (ACT != ACT_NONE) { v0 = act_fast<ACT>(v0); v1 = act_fast<ACT>(v1); v2 = act_fast<ACT>(v2); v3 = act_fast<ACT>(v3); }
+        v0 *= gate.x; v1 *= gate.y; v2 *= gate.z; v3 *= gate.w;
+        if (has_res) { v0 += res[i].x; v1 += res[i].y; v2 += res[i].z; v3 += res[i].w; }
+      }
+      if (ok) {
+        if (a.out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + p.obase + flat;
+          if (KIND == EPI_STD && a.accumulate) {
+            const uint2 pv = *reinterpret_cast<const uint2*>(o);
+            v0 += __uint_as_float(pv.x << 16); v1 += __uint_as_float(pv.x & 0xFFFF0000u);
+            v2 += __uint_as_float(pv.y << 16); v3 += __uint_as_float(pv.y & 0xFFFF0000u);
+          }
+          *reinterpret_cast<uint2*>(o) = pack_bf16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
+        } else {
+          float* o = reinterpret_cast<float*>(a.out) + p.obase + flat;
+          if (KIND == EPI_STD && a.accumulate) {
+            const float4 pv = *reinterpret_cast<const float4*>(o);
+            v0 += pv.x; v1 += pv.y; v2 += pv.z; v3 += pv.w;
+          }
+          *reinterpret_cast<float4*>(o) = make_float4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
+        }
+        if (KIND == EPI_STD && a.out2 != nullptr)      // second copy of the result in bf16 (the next GEMM's A operand)
+          *reinterpret_cast<uint2*>(a.out2 + p.obase + flat) = pack_bf16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
+      }
+    }
+    if (has_res) epi_load_res(a, p, cb + cb_step, res);      // flies during the next block's TMEM load + transpose
+    __syncwarp();                                // the staging block is rewritten by the next iteration's phase 1
+  }
+}
 
 // A tap's A tile starts (tap*dil) rows = (tap*dil)*128 bytes into the halo tile, i.e. generally NOT on a 1024-byte
 // swizzle-atom boundary. Measured on B200 (tools/debug_conv.py): the tensor core applies the 128B-swizzle XOR to the
@@ -251,17 +224,18 @@ struct Tc2Sched {
 // the shifted start address is correct and the matrix-base-offset field must stay 0 (setting it to the row phase
 // (addr >> 7) & 7 double-applies the rotation and corrupts every tap whose shift is not a multiple of 8 rows).
 
-template <bool ROPE>
-__global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int KIND, int ACT>
+__global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
-                                                                   const TcArgs a, const Tc2Sched sc) {
+                                                                   const TcArgs a, const Tc3Sched sc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int a_stage_bytes = sc.a_rows * 128;
   const int b_stage_bytes = a.BN * 128;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + sc.nA * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + sc.nB * b_stage_bytes);
+  float* smem_epi = reinterpret_cast<float*>(smem_b + sc.nB * b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_epi) + EPI_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + MAX_A_STAGES;
   uint64_t* b_full = a_empty + MAX_A_STAGES;
@@ -287,6 +261,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr;
   const int per_bg = sc.m_tiles * sc.n_tiles;
   const int halo_lo = a.center * a.dil;
+  const int halves = sc.bm >> 7;                 // 128-row accumulators per tile (1 or 2)
+  const uint32_t acc_stride = (uint32_t)(halves * sc.half_stride);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -297,7 +273,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
         const int bg = tile / per_bg, rem = tile - bg * per_bg;
         const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
         const int b = bg / a.groups, g = bg - b * a.groups;
-        const int t0 = mt * BM2, n0 = nt * a.BN;
+        const int t0 = mt * sc.bm, n0 = nt * a.BN;
         for (int c = 0; c < a.kchunks; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], (uint32_t)a_stage_bytes);
@@ -326,12 +302,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
       const int rem = tile % per_bg;
       const int mt = rem % sc.m_tiles;
-      const bool two = (mt * BM2 + 128 < a.M);                      // skip the second M half of a ragged last tile
+      const bool two = halves == 2 && (mt * sc.bm + 128 < a.M);     // skip the second M half of a ragged last tile
       const int acc = sc.nacc == 2 ? (it & 1) : 0;
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       mbar_wait(&acc_empty[acc], accphase ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)acc * 2u * hs, d1 = d0 + hs;
+      const uint32_t d0 = tmem_base + (uint32_t)acc * acc_stride, d1 = d0 + hs;
       for (int c = 0; c < a.kchunks; ++c) {
         int ksteps = (a.Cin - c * BK + UMMA_K - 1) / UMMA_K;
         if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
@@ -370,39 +346,34 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
       }
     }
   } else {
-    // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4, M half = (warp - 2) / 4 =====
-    const int q = warp & 3, h = (warp - 2) >> 2;
+    // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4; e = (warp - 2) / 4 selects the M half (bm = 256) or
+    // the odd / even 32-column blocks (bm = 128) =====
+    const int q = warp & 3, e = (warp - 2) >> 2;
+    float* stg = smem_epi + (warp - 2) * (EPI_STAGE_BYTES / 4);
+    const int h = halves == 2 ? e : 0;
+    const int cb_first = halves == 2 ? 0 : e * 32, cb_step = halves == 2 ? 32 : 64;
+    const bool has_res = KIND == EPI_STD && a.res != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
       const int bg = tile / per_bg, rem = tile - bg * per_bg;
       const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
       const int b = bg / a.groups, g = bg - b * a.groups;
-      const int n0 = nt * a.BN;
-      const int t = mt * BM2 + h * 128 + q * 32 + lane;
+      EpiPos p;
+      p.sub = lane >> 3; p.c4 = lane & 7;
+      p.n0 = nt * a.BN;
+      p.t_row0 = mt * sc.bm + h * 128 + q * 32;
+      p.obase = (long)b * a.o_bstride;
+      p.gshift = (long)g * a.N + a.o_shift;
+      const bool rows_ok = p.t_row0 < a.M;                  // warp-uniform: this 32-row block holds valid rows
+      float4 res[8];
+      if (has_res && rows_ok) epi_load_res(a, p, cb_first, res);      // overlaps the main loop
       const int acc = sc.nacc == 2 ? (it & 1) : 0;
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
-      const bool half_ok = mt * BM2 + h * 128 < a.M;          // warp-uniform: this half holds valid rows
-      const long obase = (long)b * a.o_bstride;
-      const long rowflat = (long)t * a.ldo + (long)g * a.N + a.o_shift;
-      const bool row_ok = t < a.M;
-      float4 res[8];
-      if (!ROPE && a.res != nullptr && half_ok) epi_prefetch_res(a, row_ok, obase, rowflat, n0, res);   // overlaps the main loop
       mbar_wait(&acc_full[acc], accphase);
       tc_fence_after();
-      if (half_ok) {
-        const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * sc.half_stride + h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
-        float4 res_b[8];
-        auto chunk = [&](int cb, const float4 (&cur)[8], float4 (&nxt)[8]) {
-          uint32_t r[32];
-          tmem_ld32(taddr + (uint32_t)cb, r);
-          if (!ROPE && a.res != nullptr && cb + 32 < a.BN) epi_prefetch_res(a, row_ok, obase, rowflat, n0 + cb + 32, nxt);
-          tmem_ld_wait();
-          if (row_ok) epilogue_chunk32<ROPE>(a, r, cur, g, t, n0 + cb, obase, rowflat);
-        };
-        for (int cb = 0; cb < a.BN; cb += 64) {              // ping-pong residual buffers: no register copies
-          chunk(cb, res, res_b);
-          if (cb + 32 < a.BN) chunk(cb + 32, res_b, res);
-        }
+      if (rows_ok) {
+        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_stride + (uint32_t)(h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
+        epilogue_warp<KIND, ACT>(a, p, taddr, stg, lane, g, cb_first, cb_step, res);
       }
       tc_fence_before();
       __syncwarp();
@@ -415,101 +386,6 @@ __global__ void __launch_bounds__(NTHREADS2, 1) rowgemm_tc2_kernel(const __grid_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-}
-
-__global__ void __launch_bounds__(NTHREADS) rowgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                              const __grid_constant__ CUtensorMap map_b,
-                                                              const TcArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms): [A stages][B stages][barriers][tmem ptr]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_stage_bytes = a.BN * BK * 2;
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + a.stages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + a.stages * b_stage_bytes);
-  uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z / a.groups, g = blockIdx.z % a.groups;
-  const int t0 = blockIdx.x * BM, n0 = blockIdx.y * a.BN;
-  const int num_kb = a.taps * a.kchunks;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)a.BN) tmem_cols <<= 1;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_a);
-    prefetch_tmap(&map_b);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-      int s = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int j = kb / a.kchunks, c0 = (kb - j * a.kchunks) * BK;
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], g * a.Cin + c0, t0 + (j - a.center) * a.dil, b);
-        tma_load_3d(smem_b + s * b_stage_bytes, &map_b, &full_bar[s], c0, n0, g * a.taps + j);
-        if (++s == a.stages) { s = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int s = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], phase);
-        tc_fence_after();
-        const uint64_t da = make_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
-        const uint64_t db = make_desc_sw128(smem_u32(smem_b + s * b_stage_bytes));
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: start-address field += 2
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
-        if (++s == a.stages) { s = 0; phase ^= 1; }
-      }
-      umma_commit(tmem_full_bar);            // accumulator complete
-    }
-  } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter q = warp % 4 =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int t = t0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const long obase = (long)b * a.o_bstride;
-    const long rowflat = (long)t * a.ldo + (long)g * a.N + a.o_shift;
-    const bool row_ok = t < a.M;
-    for (int cb = 0; cb < a.BN; cb += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
-      tmem_ld_wait();
-      if (row_ok) epilogue_chunk16(a, r, b, g, t, n0 + cb, obase, rowflat);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -553,23 +429,11 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
 
 namespace {
 
-int pick_bn(int N) {
-  if (N % 128 == 0) return 128;
-  if (N < 128) return (int)round_up(N, 16);    // e.g. 96, 48, 24 -> 32 (rows beyond N are TMA zero fill)
-  if (N % 96 == 0) return 96;                  // 192
-  if (N % 64 == 0) return 64;
-  return 128;                                  // ragged tail tile
-}
-
 __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&p0);
-    pk.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(out + i) = pk;
+    *reinterpret_cast<uint2*>(out + i) = pack_bf16x4(v.x, v.y, v.z, v.w);
   } else {
     for (long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
   }
@@ -615,21 +479,10 @@ void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps,
   const long rows = (long)groups * taps * N;
   tw.w.alloc((size_t)rows * tw.ldc);
   cast_pad_f32_to_bf16(w_gjnc, tw.w.p, rows, Cin, tw.ldc, s);
-  tw.BN = pick_bn(N);
-  tc_encode_map(&tw.map, tw.w.p, (uint64_t)Cin, (uint64_t)N, (uint64_t)groups * taps, (uint64_t)tw.ldc,
-             (uint64_t)N * tw.ldc, (uint32_t)tw.BN);
   tw.ready = true;
 }
 
 namespace {
-
-bool use_v1() {
-  static const bool v1 = [] {
-    const char* e = getenv("B200TTS_GEMM");
-    return e != nullptr && std::string(e) == "v1";
-  }();
-  return v1;
-}
 
 int sm_count() {
   static const int n = [] {
@@ -641,87 +494,67 @@ int sm_count() {
   return n;
 }
 
-TcArgs make_args(const RowGemm& p, const TcWeight& w) {
+// Tile shape (bm, BN) for a problem of `units` = B*groups independent (M x N) outputs on `sms` SMs.
+// Cost model: waves x tile area (a tile's main loop is proportional to bm*BN*K; K is common), then prefer the shape with
+// the smaller L2->SMEM traffic per FLOP (1/bm + 1/BN) and, on a tie, double-buffered accumulators.
+struct TileShape { int bm, bn; };
+TileShape pick_tile(int M, int N, long units, int sms, bool rope) {
+  int cands[8]; int nc = 0;
+  if (N < 64) {
+    cands[nc++] = (int)round_up(N, 16);                    // one N tile; rows beyond N are TMA zero fill
+  } else {
+    for (int bn : {256, 192, 128, 96, 64})
+      if (N % bn == 0 || (bn == 128 && N % 64 != 0 && N % 96 != 0)) cands[nc++] = bn;     // 128: ragged-tail fallback
+  }
+  {                                                          // experiment override (tools/bench_gemm.py)
+    const char* ebm = getenv("B200TTS_BM");
+    const char* ebn = getenv("B200TTS_BN");
+    if (ebm && ebn) {
+      const int bm = atoi(ebm), bn = atoi(ebn);
+      if ((bm == 128 || bm == 256) && bn >= 16 && bn <= 256 && bn % 16 == 0 && (!rope || bn % 64 == 0)) return TileShape{bm, bn};
+    }
+  }
+  TileShape best{256, cands[0]};
+  double best_cost = 1e300, best_traffic = 1e300;
+  for (int ci = 0; ci < nc; ++ci) {
+    const int bn = cands[ci];
+    for (int bm : {256, 128}) {
+      if (bm == 256 && bn > 256) continue;
+      if (rope && bn % 64 != 0) continue;
+      const long tiles = units * ceil_div(M, bm) * ceil_div(N, bn);
+      const long waves = (tiles + sms - 1) / sms;
+      const double cost = (double)waves * bm * bn;
+      const double traffic = 1.0 / bm + 1.0 / bn;
+      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && traffic < best_traffic)) {
+        best_cost = cost; best_traffic = traffic; best = TileShape{bm, bn};
+      }
+    }
+  }
+  return best;
+}
+
+TcArgs make_args(const RowGemm& p, int BN) {
   TcArgs a;
   a.Cin = p.Cin; a.N = p.N; a.taps = p.taps; a.dil = p.dil; a.center = p.center; a.groups = p.groups; a.M = p.M;
-  a.BN = w.BN; a.kchunks = ceil_div(p.Cin, BK); a.stages = 0;
+  a.BN = BN; a.kchunks = ceil_div(p.Cin, BK);
   a.out = p.out; a.o_bstride = p.o_bstride; a.ldo = p.ldo; a.o_shift = p.o_shift;
   a.o_limit = p.o_limit ? p.o_limit : (long)p.M * p.ldo;
   a.out_bf16 = p.out_bf16;
-  a.bias = p.bias; a.gate = p.gate; a.res = p.res; a.accumulate = p.accumulate; a.scale = p.scale; a.act = p.act;
+  a.bias = p.bias; a.gate = p.gate; a.res = p.res; a.accumulate = p.accumulate; a.scale = p.scale;
   a.rope_cos = p.rope_cos; a.rope_sin = p.rope_sin; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
   a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
   a.out2 = p.out2;
   return a;
 }
 
-void launch_v1(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
-  CUtensorMap map_a;
-  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
-                (uint64_t)p.x_bstride, (uint32_t)BM);
-  TcArgs a = make_args(p, w);
-  const int stage_bytes = A_STAGE_BYTES + w.BN * BK * 2;
-  // keep <= ~110 KB so that two CTAs fit one SM (227 KB): the co-resident CTA hides this one's epilogue
-  int stages = (110 * 1024 - 1024 - 256) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  const int num_kb = p.taps * a.kchunks;
-  if (stages > num_kb) stages = num_kb;
-  if (stages < 2 && num_kb >= 2) stages = 2;
-  a.stages = stages;
-  const int smem = stages * stage_bytes + 1024 /*alignment slack*/ + (2 * MAX_STAGES + 1) * 8 + 16;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+template <int KIND, int ACT>
+void launch_kernel(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& a,
+                   const Tc3Sched& sc) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc3_kernel<KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   });
-  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, w.BN), p.B * p.groups);
-  B2_CHECK(grid.y <= 65535 && grid.z <= 65535, "rowgemm_tc grid too large");
-  rowgemm_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_a, w.map, a);
-  B2_LAUNCH_CHECK();
-  count_launch();
-}
-
-void launch_v2(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
-  CUtensorMap map_a;
-  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
-                (uint64_t)p.x_bstride, (uint32_t)A_BOX_ROWS);
-  TcArgs a = make_args(p, w);
-  Tc2Sched sc;
-  sc.m_tiles = ceil_div(p.M, BM2);
-  sc.n_tiles = ceil_div(p.N, w.BN);
-  const long tiles = (long)p.B * p.groups * sc.m_tiles * sc.n_tiles;
-  B2_CHECK(tiles < (1L << 30), "rowgemm_tc: too many tiles");
-  sc.num_tiles = (int)tiles;
-  const int halo = (p.taps - 1) * p.dil;
-  sc.a_rows = (int)round_up(BM2 + halo, A_BOX_ROWS);
-  sc.half_stride = w.BN <= 128 ? 128 : 256;
-  sc.nacc = w.BN <= 128 ? 2 : 1;
-  const int a_stage = sc.a_rows * 128, b_stage = w.BN * 128;
-  const int bar_bytes = (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * 8 + 16;
-  const int budget = 227 * 1024 - 1024 - bar_bytes;
-  int nA = p.taps == 1 ? MAX_A_STAGES : 2;
-  if (nA > a.kchunks + 1) nA = a.kchunks + 1;
-  if (nA < 1) nA = 1;
-  while (nA > 1 && budget - nA * a_stage < 2 * b_stage) --nA;
-  int nB = (budget - nA * a_stage) / b_stage;
-  if (nB > MAX_B_STAGES) nB = MAX_B_STAGES;
-  B2_CHECK(nB >= 1, "rowgemm_tc: halo tile does not fit shared memory (kernel too long / dilation too large)");
-  sc.nA = nA; sc.nB = nB;
-  const int smem = nA * a_stage + nB * b_stage + 1024 + bar_bytes;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  });
-  const int grid = sc.num_tiles < sm_count() ? sc.num_tiles : sm_count();
-  if (p.rope_cos != nullptr) {
-    B2_CHECK(p.gate == nullptr && p.res == nullptr && !p.accumulate && p.act == ACT_NONE && p.out2 == nullptr,
-             "rowgemm_tc: the rope epilogue takes bias only");
-    rowgemm_tc2_kernel<true><<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
-  } else {
-    rowgemm_tc2_kernel<false><<<grid, NTHREADS2, smem, stream>>>(map_a, w.map, a, sc);
-  }
-  B2_LAUNCH_CHECK();
-  count_launch();
+  rowgemm_tc3_kernel<KIND, ACT><<<grid, NTHREADS3, smem, stream>>>(map_a, map_b, a, sc);
 }
 
 }  // namespace
@@ -733,10 +566,66 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   B2_CHECK(p.ldx % 8 == 0 && p.x_bstride % 8 == 0, "rowgemm_tc: A rows must be 16-byte aligned");
   B2_CHECK(p.groups == 1 || p.Cin % BK == 0, "rowgemm_tc: grouped problems need Cin % 64 == 0");
   B2_CHECK(p.M > 0 && p.B > 0, "rowgemm_tc: empty problem");
-  B2_CHECK(p.rope_cos == nullptr || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.groups == 1 && p.B == 1),
+  const bool rope = p.rope_cos != nullptr;
+  B2_CHECK(!rope || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.vt_col0 % 32 == 0 && p.groups == 1 && p.B == 1),
            "rowgemm_tc: malformed rope epilogue");
-  if (use_v1()) launch_v1(p, w, stream);
-  else launch_v2(p, w, stream);
+  B2_CHECK(!rope || (p.gate == nullptr && p.res == nullptr && !p.accumulate && p.act == ACT_NONE && p.out2 == nullptr),
+           "rowgemm_tc: the rope epilogue takes bias only");
+
+  const int sms = sm_count();
+  const TileShape ts = pick_tile(p.M, p.N, (long)p.B * p.groups, sms, rope);
+  CUtensorMap map_a, map_b;
+  tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
+                (uint64_t)p.x_bstride, (uint32_t)A_BOX_ROWS);
+  tc_encode_map(&map_b, w.w.p, (uint64_t)w.Cin, (uint64_t)w.N, (uint64_t)w.groups * w.taps, (uint64_t)w.ldc,
+                (uint64_t)w.N * w.ldc, (uint32_t)ts.bn);
+  TcArgs a = make_args(p, ts.bn);
+  Tc3Sched sc;
+  sc.bm = ts.bm;
+  sc.m_tiles = ceil_div(p.M, ts.bm);
+  sc.n_tiles = ceil_div(p.N, ts.bn);
+  const long tiles = (long)p.B * p.groups * sc.m_tiles * sc.n_tiles;
+  B2_CHECK(tiles < (1L << 30), "rowgemm_tc: too many tiles");
+  sc.num_tiles = (int)tiles;
+  const int halo = (p.taps - 1) * p.dil;
+  sc.a_rows = (int)round_up(ts.bm + halo, A_BOX_ROWS);
+  sc.half_stride = ts.bn <= 128 ? 128 : 256;
+  const int halves = ts.bm / 128;
+  sc.nacc = (2 * halves * sc.half_stride <= 512) ? 2 : 1;
+  const int a_stage = sc.a_rows * 128, b_stage = ts.bn * 128;
+  const int bar_bytes = (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * 8 + 16;
+  const int budget = 227 * 1024 - 1024 - bar_bytes - EPI_BYTES;
+  // ring depths: a plain GEMM consumes one A and one B stage per 64-channel chunk -> equal depths; a convolution
+  // consumes `taps` B stages per A stage -> two A stages, the rest of shared memory for B
+  int nA, nB;
+  if (p.taps == 1) {
+    nA = budget / (a_stage + b_stage);
+    if (nA > 6) nA = 6;
+    if (nA < 1) nA = 1;
+    nB = nA;
+  } else {
+    nA = 2;
+    while (nA > 1 && budget - nA * a_stage < 2 * b_stage) --nA;
+    nB = (budget - nA * a_stage) / b_stage;
+    if (nB > MAX_B_STAGES) nB = MAX_B_STAGES;
+  }
+  B2_CHECK(nB >= 1, "rowgemm_tc: halo tile does not fit shared memory (kernel too long / dilation too large)");
+  sc.nA = nA; sc.nB = nB;
+  const int smem = nA * a_stage + nB * b_stage + EPI_BYTES + 1024 + bar_bytes;
+  const int grid = sc.num_tiles < sms ? sc.num_tiles : sms;
+  if (rope) {
+    launch_kernel<EPI_ROPE, ACT_NONE>(grid, smem, stream, map_a, map_b, a, sc);
+  } else {
+    switch (p.act) {
+      case ACT_NONE: launch_kernel<EPI_STD, ACT_NONE>(grid, smem, stream, map_a, map_b, a, sc); break;
+      case ACT_GELU_TANH: launch_kernel<EPI_STD, ACT_GELU_TANH>(grid, smem, stream, map_a, map_b, a, sc); break;
+      case ACT_GELU_ERF: launch_kernel<EPI_STD, ACT_GELU_ERF>(grid, smem, stream, map_a, map_b, a, sc); break;
+      case ACT_MISH: launch_kernel<EPI_STD, ACT_MISH>(grid, smem, stream, map_a, map_b, a, sc); break;
+      default: fail("rowgemm_tc: unknown activation");
+    }
+  }
+  B2_LAUNCH_CHECK();
+  count_launch();
 }
 
 }  // namespace b200tts

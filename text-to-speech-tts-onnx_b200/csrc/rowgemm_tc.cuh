@@ -8,12 +8,11 @@
 
 namespace b200tts {
 
-// Weights for the tensor-core path: bf16 W[g*taps + j][n][c] (c contiguous, row stride ldc) + its TMA map.
+// Weights for the tensor-core path: bf16 W[g*taps + j][n][c] (c contiguous, row stride ldc). The TMA map over it is
+// encoded per launch, because its box height is the N tile the launch picks for the problem's M (rowgemm_tc.cu: pick_tile).
 struct TcWeight {
   DevBuf<__nv_bfloat16> w;
-  CUtensorMap map;
   int Cin = 0, ldc = 0, N = 0, taps = 0, groups = 1;
-  int BN = 0;                 // N tile (multiple of 16, <= 256)
   bool ready = false;
 };
 
