@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200tts.so")
+LIB_PATH = os.environ.get("B200TTS_LIB") or os.path.join(HERE, "libb200tts.so")   # override: A/B runs of two builds
 
 F32, BF16 = 0, 1
 

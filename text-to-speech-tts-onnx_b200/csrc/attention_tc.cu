@@ -1,14 +1,22 @@
 // Non-causal, unmasked, unscaled flash attention for the F5 DiT (modules.py:449-468: softmax(q @ k) @ v in
 // fp32, the 1/sqrt(d) scale already folded into Wq/Wk at export) on tcgen05 tensor cores.
 //
-// One CTA = one (batch, head, 128-query tile). Per 128-key block:
-//   S  = Q K^T   tcgen05.mma  M=128 N=128 K=64   (Q, K tiles: TMA boxes of the [2N][2048] q|k tensor, SWIZZLE_128B)
-//   P  = exp2((S - m) log2e)   128 softmax threads, one row each, read S from TMEM, online max/sum in fp32,
-//        write P (bf16) to shared memory in the K-major SWIZZLE_128B layout the next MMA wants
-//   PV = P V     tcgen05.mma  M=128 N=64 K=128  (V^T tiles [64 d][keys] from the transposed-V buffer the QKV GEMM
-//        epilogue wrote) into a second TMEM buffer; the softmax threads fold it into register accumulators
-//        O = O * alpha + PV, so no TMEM read-modify-write correction pass is needed.
-// 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = softmax/epilogue.
+// One CTA = one (batch, head, 128-query tile). Per 128-key block j:
+//   S_j  = Q K_j^T   tcgen05.mma  M=128 N=128 K=64   (Q, K tiles: TMA boxes of the [2N][2048] q|k tensor, SWIZZLE_128B)
+//   P_j  = exp2(S_j log2e - m)   256 softmax threads: thread (row r, key half g) owns 64 keys of its row in ONE pass
+//          (the 64 scores are pulled from TMEM into registers, which also frees the S buffer so that S_{j+1} is computed
+//          while the exponentials run), packed FFMA2 / FADD2 arithmetic, P (bf16) to shared memory in the K-major
+//          SWIZZLE_128B layout the next MMA wants
+//   O_g += P_jg V_jg tcgen05.mma  M=128 N=64 K=64 per key half, accumulated IN TMEM across blocks.
+// The two key halves of a row are independent split-KV streams: each has its own running maximum, row sum and O
+// accumulator, so the two threads of a row never synchronise inside the loop; they are merged once at the end
+// (O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m))) through shared memory.
+// The running maximum is lazy (FlashAttention-4 style): it only moves when a block's maximum exceeds it by more than 8
+// (log2 units), and only then is O_g rescaled in TMEM (tcgen05.ld / multiply / tcgen05.st, warp-voted); P stays below
+// 2^8, which bf16 and the fp32 accumulators hold without loss.
+// The first version (r01b: 30.5 us per call, 16.8 M instructions, issue-bound) walked S twice with 128 threads, kept O
+// in registers and folded PV into it every block (64 FFMA + 2 TMEM loads per row per block).
+// 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = softmax/epilogue.
 // Shared memory 112 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA phases.
 #include "attention_tc.cuh"
 
@@ -24,13 +32,14 @@ namespace {
 using namespace tc;
 
 constexpr int BQ = 128, BKEY = 128, HD = 64;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
 constexpr int K_BYTES = BKEY * HD * 2;          // 16 KB
 constexpr int V_BYTES = HD * BKEY * 2;          // 16 KB = two [64 d][64 keys] chunks
 constexpr int P_BYTES = BQ * BKEY * 2;          // 32 KB = two [128 rows][64 keys] chunks
 constexpr int KV_STAGES = 2;
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 128;
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 128;      // x2 CTAs + 2 KB reserved <= 228 KB
+constexpr float RESCALE_TAU = 8.0f;             // log2 units
 
 struct AttnArgs {
   int N, H;
@@ -43,6 +52,31 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+// packed fp32 pairs (FFMA2 / FADD2)
+__device__ __forceinline__ unsigned long long pk2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void up2(unsigned long long r, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(r));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,
                                                               const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
@@ -51,14 +85,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + KV_STAGES * K_BYTES;
   uint8_t* sP = sV + KV_STAGES * V_BYTES;
+  float* stat = reinterpret_cast<float*>(sQ);                      // [2 halves][m, l][128 rows]: reuses the Q tile once the
+                                                                   // last S MMA has completed (pv_done of the last block)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;                 // [2]
   uint64_t* kv_empty = bars + 3;                // [2]
   uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_free = bars + 6;                  // softmax threads hold S in registers: the S buffer may be overwritten
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -72,8 +109,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 256);
@@ -81,7 +119,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base, tmem_PV = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // O_a: +128..191, O_b: +192..255
 
   if (warp == 0) {
     if (lane == 0) {
@@ -104,117 +142,168 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint64_t dQ = make_desc_sw128(smem_u32(sQ));
       const uint64_t dP0 = make_desc_sw128(smem_u32(sP)), dP1 = make_desc_sw128(smem_u32(sP + P_BYTES / 2));
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nblocks; ++j) {
+      auto issue_s = [&](int j) {
         const int s = j % KV_STAGES;
-        const uint32_t ph = (uint32_t)(j / KV_STAGES) & 1u;
-        mbar_wait(&kv_full[s], ph);
+        mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
+        if (j > 0) mbar_wait(s_free, (uint32_t)(j - 1) & 1u);       // S_{j-1} is in the softmax threads' registers
         tc_fence_after();
         const uint64_t dK = make_desc_sw128(smem_u32(sK + s * K_BYTES));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_S, dQ + (uint64_t)(2 * k), dK + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nblocks; ++j) {
+        if (j + 1 < nblocks) issue_s(j + 1);                        // runs under the exponentials of block j
+        const int s = j % KV_STAGES;
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
         const uint64_t dV0 = make_desc_sw128(smem_u32(sV + s * V_BYTES));
         const uint64_t dV1 = make_desc_sw128(smem_u32(sV + s * V_BYTES + V_BYTES / 2));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_PV, dP0 + (uint64_t)(2 * k), dV0 + (uint64_t)(2 * k), idesc_pv, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_PV, dP1 + (uint64_t)(2 * k), dV1 + (uint64_t)(2 * k), idesc_pv, 1u);
-        umma_commit(pv_full);
+        for (int k = 0; k < 4; ++k) {                               // the two key halves are independent accumulators
+          umma_bf16(tmem_O, dP0 + (uint64_t)(2 * k), dV0 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_O + 64, dP1 + (uint64_t)(2 * k), dV1 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(pv_done);
         umma_commit(&kv_empty[s]);
       }
     }
   } else {
-    // ===== softmax + epilogue: row r of the query tile =====
-    const int qd = warp & 3;
+    // ===== softmax + epilogue: row r of the query tile, key half g of every block =====
+    const int qd = warp & 3, g = (warp - 2) >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const uint32_t tmem_Og = tmem_O + (uint32_t)(g * 64);
     const float LOG2E = 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    float m_ref = -INFINITY, l_run = 0.f;        // m_ref in log2 units
+    uint8_t* prow = sP + g * (P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
 
     for (int j = 0; j < nblocks; ++j) {
-      const int kvalid = a.N - j * BKEY;          // >= 1
+      const int kvalid = a.N - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cb = 0; cb < BKEY; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)cb, v);
-        tmem_ld_wait();
+      uint32_t v[2][32];
+      tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64), v[0]);
+      tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64 + 32), v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      if (kvalid < 64) {                          // last, ragged block: keys beyond N do not exist
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = __uint_as_float(v[i]);
-          mx = (cb + i < kvalid) ? fmaxf(mx, sv) : mx;
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kvalid) v[c][i] = 0xff800000u;        // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+      mx *= LOG2E;
+      // lazy running maximum
+      const bool move = mx > m_ref + RESCALE_TAU;
+      const float m_new = move ? mx : m_ref;
+      const float alpha = move ? ex2(m_ref - m_new) : 1.0f;          // exp2(-inf) = 0 on the first block
+      m_ref = m_new;
+      l_run *= alpha;
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);                 // O += P_{j-1} V_{j-1} has landed; P buffer is free again
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, move)) {                         // rescale O_g in TMEM (rare after the first blocks)
+#pragma unroll 1
+          for (int cb = 0; cb < HD; cb += 16) {                      // 16 columns at a time: the 64 scores stay live
+            uint32_t o[16];
+            tmem_ld16(tmem_Og + lane_addr + (uint32_t)cb, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_Og + lane_addr + (uint32_t)cb, o);
+          }
+          tmem_st_wait();
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2((m_run - m_new) * LOG2E);     // exp2(-inf) = 0 on the first block
-      const float mb = m_new * LOG2E;
-      // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled smem; fp32 row sum
-      float sum = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < BKEY; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)cb, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      // P = exp2(s*log2e - m) -> bf16 -> swizzled smem; fp32 row sum (packed accumulator). No key seen yet (m = -inf) -> P = 0
+      const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+      const unsigned long long sc2 = pk2(LOG2E, LOG2E), nm2 = pk2(-m_use, -m_use);
+      unsigned long long sum2 = pk2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (cb + i < kvalid) ? ex2(fmaf(__uint_as_float(v[i]), LOG2E, -mb)) : 0.f;
-          float p1 = (cb + i + 1 < kvalid) ? ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mb)) : 0.f;
-          sum += p0 + p1;
-          __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pp);
-        }
-        // 32 keys = four 16-byte chunks; chunk index within the 64-key (128 B) row: (cb % 64) / 8 + q
-        uint8_t* base = prow + (cb >> 6) * (P_BYTES / 2);
-        const int c0 = (cb & 63) >> 3;
+      for (int c = 0; c < 2; ++c) {
+        // 32 keys = four 16-byte chunks of this row's 128-byte (64-key) line: chunk index c*4 + q, swizzled by the row
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          const int chunk = (c0 + qq) ^ sw;
-          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[qq * 4 + 0], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+          uint32_t pkd[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = qq * 8 + u * 2;
+            float e0, e1;
+            up2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), e0, e1);
+            const float p0 = ex2(e0), p1 = ex2(e1);
+            sum2 = add2(sum2, pk2(p0, p1));
+            __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+            pkd[u] = *reinterpret_cast<uint32_t*>(&pp);
+          }
+          const int chunk = (c * 4 + qq) ^ sw;
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
         }
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      tc_fence_before();                 // order our TMEM reads of S before the MMA warp's next write to it
+      float s0, s1;
+      up2(sum2, s0, s1);
+      l_run += s0 + s1;
+      tc_fence_before();                 // order our TMEM accesses before the MMA warp's next writes
       fence_proxy_async();               // make the generic-proxy smem writes of P visible to the tensor core
       mbar_arrive(p_full);
-      // fold PV into the register accumulator
-      mbar_wait(pv_full, (uint32_t)j & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int cb = 0; cb < HD; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_PV + lane_addr + (uint32_t)cb, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[cb + i] = fmaf(o[cb + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
     }
+    // ---- merge the two key halves of each row, normalise, store ----
+    mbar_wait(pv_done, (uint32_t)(nblocks - 1) & 1u);
+    tc_fence_after();
+    stat[(g * 2 + 0) * BQ + r] = m_ref;
+    stat[(g * 2 + 1) * BQ + r] = l_run;
+    softmax_bar();
+    const float m_o = stat[((g ^ 1) * 2 + 0) * BQ + r], l_o = stat[((g ^ 1) * 2 + 1) * BQ + r];
+    const float m_all = fmaxf(m_ref, m_o);       // finite: key half 0 always holds at least one valid key
+    const float w_me = m_ref == -INFINITY ? 0.f : ex2(m_ref - m_all);
+    const float w_ot = m_o == -INFINITY ? 0.f : ex2(m_o - m_all);
+    const float scale = w_me / (l_run * w_me + l_o * w_ot);
+    // thread (r, g) stores output columns [32g, 32g+32); the other 32 columns of its O_g go to the partner through the
+    // (now idle) P buffer: [2 halves][128 rows][32 floats], 16-byte chunks swizzled by the row
+    float* xch = reinterpret_cast<float*>(sP);
+    uint32_t mine[32];
+    {
+      uint32_t o[32];
+      tmem_ld32(tmem_Og + lane_addr + (uint32_t)((g ^ 1) * 32), o);        // the partner's columns
+      tmem_ld32(tmem_Og + lane_addr + (uint32_t)(g * 32), mine);
+      tmem_ld_wait();
+      float* dstx = xch + ((g ^ 1) * BQ + r) * 32;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(dstx + ((k ^ sw) << 2)) =
+            make_float4(__uint_as_float(o[k * 4]) * scale, __uint_as_float(o[k * 4 + 1]) * scale, __uint_as_float(o[k * 4 + 2]) * scale,
+                        __uint_as_float(o[k * 4 + 3]) * scale);
+    }
+    softmax_bar();
     const int q = q0 + r;
     if (q < a.N) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = a.out + ((long)b * a.N + q) * a.ldo + h * HD;
+      const float* srcx = xch + (g * BQ + r) * 32;
+      __nv_bfloat16* dst = a.out + ((long)b * a.N + q) * a.ldo + h * HD + g * 32;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
+      for (int k = 0; k < 8; k += 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(srcx + ((k ^ sw) << 2));
+        const float4 x1 = *reinterpret_cast<const float4*>(srcx + (((k + 1) ^ sw) << 2));
         uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          __nv_bfloat162 pp = __floats2bfloat162_rn(o[i + 2 * k] * inv, o[i + 2 * k + 1] * inv);
-          w[k] = *reinterpret_cast<uint32_t*>(&pp);
-        }
-        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        __nv_bfloat162 pp;
+        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 0]) * scale + x0.x, __uint_as_float(mine[k * 4 + 1]) * scale + x0.y);
+        w[0] = *reinterpret_cast<uint32_t*>(&pp);
+        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 2]) * scale + x0.z, __uint_as_float(mine[k * 4 + 3]) * scale + x0.w);
+        w[1] = *reinterpret_cast<uint32_t*>(&pp);
+        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 4]) * scale + x1.x, __uint_as_float(mine[k * 4 + 5]) * scale + x1.y);
+        w[2] = *reinterpret_cast<uint32_t*>(&pp);
+        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 6]) * scale + x1.z, __uint_as_float(mine[k * 4 + 7]) * scale + x1.w);
+        w[3] = *reinterpret_cast<uint32_t*>(&pp);
+        *reinterpret_cast<uint4*>(dst + k * 4) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }

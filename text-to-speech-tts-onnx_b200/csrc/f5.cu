@@ -91,6 +91,7 @@ struct F5Model {
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
   DevBuf<__nv_bfloat16> h16, c16, n16, qk16, vT16, att16, ff16;        // tensor-core engine
+  DevBuf<__half2> rope_cs16;                                           // [N][64] (cos, sin): exact, the tables are fp16-rounded (q5)
   // preprocess / decode scratch
   DevBuf<float> audio_f, spec, mag, mel, t_a, t_b, t_c, t_wide, grn_scratch;
   DevBuf<int> ids;
@@ -496,6 +497,7 @@ void reserve_step(F5Model& m, bool fast) {
   if (fast) {
     m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.att16.reserve(R * m.D);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
+    m.rope_cs16.reserve((size_t)m.N * m.hd);
   } else {
     m.c32.reserve(R * m.D); m.n32.reserve(R * m.D); m.att32.reserve(R * m.D); m.qkv32.reserve(R * 3 * m.D);
     m.ff32.reserve(R * m.FF);
@@ -539,6 +541,10 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     B2_CUDA(cudaMemsetAsync(m.kT32.p, 0, (size_t)2 * m.H * m.hd * m.Npad * sizeof(float), s));
     B2_CUDA(cudaMemsetAsync(m.v32.p, 0, (size_t)2 * m.H * m.Npad * m.hd * sizeof(float), s));
   }
+  if (fast) {
+    ProfScope ps(e.prof, "f5.cast", s);
+    rope_pack_half(m.cur_cos, m.cur_sin, m.rope_cs16.p, (long)N * m.hd, s);
+  }
   for (int step = first; step < first + count; ++step) {
     // ---- input embedding: h[b] = Wx x + (Wc c_b + bias) ; x = conv_pos(h) + h ----
     for (int b = 0; b < 2; ++b) {
@@ -567,7 +573,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
         p.x = m.n16.p; p.ldx = D; p.Lin = R; p.Cin = D; p.N = 3 * D; p.taps = 1; p.M = R; p.B = 1;
         p.out = m.qk16.p; p.ldo = 2 * D; p.out_bf16 = 1; p.o_limit = (long)R * 2 * D + 3 * D;
         p.bias = L.qkv.bias.p;
-        p.rope_cos = m.cur_cos; p.rope_sin = m.cur_sin; p.rope_cols = 2 * D; p.rope_rows = N;
+        p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N;
         p.vt_out = m.vT16.p; p.vt_col0 = 2 * D; p.vt_ld = m.Npad; p.vt_heads = m.H;
         { ProfScope ps(e.prof, "f5.qkv_gemm", s); rowgemm_tc(p, L.qkv.tc, s); }
         { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, N, m.H, s); }

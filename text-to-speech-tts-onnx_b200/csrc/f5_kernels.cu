@@ -1,5 +1,7 @@
 #include "f5_kernels.cuh"
 
+#include <cuda_fp16.h>
+
 namespace b200tts {
 
 namespace {
@@ -259,6 +261,11 @@ __global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ y, 
   if (i < n) { const float v = x[i]; y[i] = v / (1.0f + expf(-v)); }
 }
 
+__global__ void rope_pack_kernel(const float* __restrict__ c, const float* __restrict__ sn, __half2* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __floats2half2_rn(c[i], sn[i]);
+}
+
 inline dim3 g1(long n, int bs = 256) { return dim3(ceil_div(n, bs)); }
 
 }  // namespace
@@ -341,6 +348,10 @@ void rope_split_f32(float* qkv, const float* cos, const float* sin, float* kT, f
 }
 void softmax_rows(float* x, long rows, int n, int ld, cudaStream_t s) {
   softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, n, ld);
+  LAUNCHED();
+}
+void rope_pack_half(const float* cos, const float* sin, __half2* out, long n, cudaStream_t s) {
+  rope_pack_kernel<<<g1(n), 256, 0, s>>>(cos, sin, out, n);
   LAUNCHED();
 }
 void silu(const float* x, float* y, long n, cudaStream_t s) {

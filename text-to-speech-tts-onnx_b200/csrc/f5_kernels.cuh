@@ -1,6 +1,7 @@
 // Element-wise / reduction kernels of the F5-TTS graphs (everything that is not a GEMM or attention).
 // All tensors are row-major (rows = time, columns = channels), fp32 unless noted.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace b200tts {
@@ -41,6 +42,8 @@ void istft_overlap_add(const float* frames, const float* window_sum_inv, int G, 
 void rope_split_f32(float* qkv, const float* cos, const float* sin, float* kT, float* v, int N, int H, int hd, int ldk, cudaStream_t s);
 // softmax over the first n of ld columns of every row (rest set to 0), in place
 void softmax_rows(float* x, long rows, int n, int ld, cudaStream_t s);
+// out[i] = (cos[i], sin[i]) as an fp16 pair (the RoPE tables are fp16-rounded by the export, Export_F5.py:111-112: exact)
+void rope_pack_half(const float* cos, const float* sin, __half2* out, long n, cudaStream_t s);
 // y = silu(x)
 void silu(const float* x, float* y, long n, cudaStream_t s);
 

@@ -12,6 +12,8 @@
 // Two implementations share this parameter block: rowgemm_f32 (SIMT fp32, the parity engine) and
 // rowgemm_tc (tcgen05 + TMA, bf16 operands / fp32 accumulate, the fast engine).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace b200tts {
@@ -45,10 +47,10 @@ struct RowGemm {
   float scale = 1.0f;
   int act = ACT_NONE;
   // tensor-core path only: fused q/k/v epilogue of the DiT attention (F5 modules.py:459-466).
-  //   columns [0, rope_cols): interleaved-pair RoPE with tables [rope_rows][64] at t = row % rope_rows
+  //   columns [0, rope_cols): interleaved-pair RoPE with the packed table rope_cs[rope_rows][64] of (cos, sin) fp16 pairs
+  //                           (exact: the reference rounds its tables through fp16, Export_F5.py:111-112) at t = row % rope_rows
   //   columns >= vt_col0    : written transposed, vt_out[((row / rope_rows) * heads + h) * 64 + d][t] (row stride vt_ld)
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
+  const __half2* rope_cs = nullptr;
   int rope_cols = 0, rope_rows = 1;
   __nv_bfloat16* vt_out = nullptr;
   int vt_col0 = 0, vt_ld = 0, vt_heads = 0;

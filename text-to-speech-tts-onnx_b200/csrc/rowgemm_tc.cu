@@ -26,6 +26,8 @@
 // the current one is processed; the loop over blocks is not unrolled (~300 instructions per block).
 #include "rowgemm_tc.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -53,16 +55,20 @@ struct TcArgs {
   int BN, kchunks;              // kchunks = ceil(Cin / 64)
   void* out; long o_bstride; int ldo; long o_shift; long o_limit; int out_bf16;
   const float* bias; const float* gate; const float* res; int accumulate; float scale;
-  const float* rope_cos; const float* rope_sin; int rope_cols, rope_rows;
+  const __half2* rope_cs; int rope_cols, rope_rows;
   __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
   __nv_bfloat16* out2;          // optional bf16 copy of the output (same indexing)
 };
 
 struct Tc3Sched {
-  int bm;                               // 256 or 128 output rows per tile
+  int bm;                               // output rows per tile = 128 * halves
+  int halves;                           // 128-row accumulators per tile (1, 2 or 4): independent MMA chains
+  int ksplit;                           // 1 or 2: even / odd 64-channel chunks accumulate into separate TMEM accumulators
+                                        // (two independent MMA chains for one output tile), summed in the epilogue
   int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
   int a_rows;                           // rows per A stage (multiple of 64) = round_up(bm + (taps-1)*dil, 64)
-  int nA, nB;                           // ring depths
+  int nA, nB;                           // ring depths (bres: nB = kchunks*taps resident B tiles)
+  int bres;                             // 1: the whole weight tensor stays in shared memory for the life of the CTA
   int half_stride, nacc;                // TMEM columns per 128-row accumulator; accumulator stages (1 or 2)
 };
 
@@ -124,8 +130,8 @@ __device__ __forceinline__ void epi_load_res(const TcArgs& a, const EpiPos& p, i
 }
 
 template <int KIND, int ACT>
-__device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, uint32_t taddr, float* stg, int lane, int g,
-                                              int cb_first, int cb_step, float4 (&res)[8]) {
+__device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, uint32_t taddr, uint32_t ks_off, float* stg, int lane,
+                                              int g, int cb_first, int cb_step, float4 (&res)[8]) {
   const int sub = p.sub, c4 = p.c4, n0 = p.n0;
   const bool has_res = KIND == EPI_STD && a.res != nullptr;
 #pragma unroll 1
@@ -133,7 +139,25 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, 
     if (n0 + cb >= a.N) break;
     uint32_t r[32];
     tmem_ld32(taddr + (uint32_t)cb, r);
+    // RoPE block: the (cos, sin) pairs of this lane's 8 phase-2 rows x 4 columns, one 16-byte load each, issued before the
+    // TMEM wait (they were 16 dependent L2 round trips inside phase 2: +12 us on the q|k|v GEMM, ncu r01d)
+    uint4 cs[8];
+    if (KIND == EPI_ROPE && n0 + cb < a.rope_cols) {
+      const int d = (n0 + cb + c4 * 4) & 63;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = p.t_row0 + i * 4 + sub;
+        cs[i] = t < a.M ? __ldg(reinterpret_cast<const uint4*>(a.rope_cs + (long)(t % a.rope_rows) * 64 + d)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
     tmem_ld_wait();
+    if (ks_off != 0u) {                          // K-split: add the second accumulator (odd channel chunks)
+      uint32_t r2[32];
+      tmem_ld32(taddr + ks_off + (uint32_t)cb, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+    }
 
     if (KIND == EPI_ROPE && a.vt_out != nullptr && n0 + cb >= a.vt_col0) {
       // V columns: written transposed, vt[(batch*heads + h)*64 + d][t]; in the row-per-lane layout consecutive lanes are
@@ -179,13 +203,14 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, 
       const float4 acc = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
       float v0 = acc.x + bias.x, v1 = acc.y + bias.y, v2 = acc.z + bias.z, v3 = acc.w + bias.w;
       if (KIND == EPI_ROPE) {
-        if (rope && ok) {                       // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
-          const int tt = (p.t_row0 + row) % a.rope_rows;
-          const float4 cc = __ldg(reinterpret_cast<const float4*>(a.rope_cos + (long)tt * 64 + (n & 63)));
-          const float4 ss = __ldg(reinterpret_cast<const float4*>(a.rope_sin + (long)tt * 64 + (n & 63)));
+        if (rope) {                             // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+          const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].x));
+          const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].y));
+          const float2 cs2 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].z));
+          const float2 cs3 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].w));
           const float x0 = v0, x1 = v1, x2 = v2, x3 = v3;
-          v0 = x0 * cc.x - x1 * ss.x; v1 = x1 * cc.y + x0 * ss.y;
-          v2 = x2 * cc.z - x3 * ss.z; v3 = x3 * cc.w + x2 * ss.w;
+          v0 = x0 * cs0.x - x1 * cs0.y; v1 = x1 * cs1.x + x0 * cs1.y;
+          v2 = x2 * cs2.x - x3 * cs2.y; v3 = x3 * cs3.x + x2 * cs3.y;
         }
       } else {
         if (ACT != ACT_NONE) { v0 = act_fast<ACT>(v0); v1 = act_fast<ACT>(v1); v2 = act_fast<ACT>(v2); v3 = act_fast<ACT>(v3); }
@@ -216,6 +241,16 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, 
     if (has_res) epi_load_res(a, p, cb + cb_step, res);      // flies during the next block's TMEM load + transpose
     __syncwarp();                                // the staging block is rewritten by the next iteration's phase 1
   }
+}
+
+// The 4 x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost.
+template <int NH>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      umma_bf16_lohi(d + (uint32_t)h * hstep, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc, k == 0 ? accum : 1u);
 }
 
 // A tap's A tile starts (tap*dil) rows = (tap*dil)*128 bytes into the halo tile, i.e. generally NOT on a 1024-byte
@@ -250,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
     for (int s = 0; s < sc.nA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < sc.nB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < (sc.bres ? 1 : sc.nB); ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_barrier_init();
   }
@@ -261,14 +296,20 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr;
   const int per_bg = sc.m_tiles * sc.n_tiles;
   const int halo_lo = a.center * a.dil;
-  const int halves = sc.bm >> 7;                 // 128-row accumulators per tile (1 or 2)
-  const uint32_t acc_stride = (uint32_t)(halves * sc.half_stride);
+  const int halves = sc.halves;
+  const uint32_t acc_stride = (uint32_t)(halves * sc.ksplit * sc.half_stride);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       const int a_boxes = sc.a_rows / A_BOX_ROWS;
+      if (sc.bres) {                    // small convolutions: every (chunk, tap) weight tile is fetched once per CTA
+        mbar_expect_tx(&b_full[0], (uint32_t)(a.kchunks * a.taps * b_stage_bytes));
+        for (int c = 0; c < a.kchunks; ++c)
+          for (int j = 0; j < a.taps; ++j)
+            tma_load_3d(smem_b + (c * a.taps + j) * b_stage_bytes, &map_b, &b_full[0], c * BK, 0, j);
+      }
       for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x) {
         const int bg = tile / per_bg, rem = tile - bg * per_bg;
         const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
@@ -281,6 +322,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
             tma_load_3d(smem_a + sa * a_stage_bytes + rbx * (A_BOX_ROWS * 128), &map_a, &a_full[sa], g * a.Cin + c * BK,
                         t0 - halo_lo + rbx * A_BOX_ROWS, b);
           if (++sa == sc.nA) { sa = 0; pa ^= 1; }
+          if (sc.bres) continue;
           for (int j = 0; j < a.taps; ++j) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
@@ -302,57 +344,58 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
       const int rem = tile % per_bg;
       const int mt = rem % sc.m_tiles;
-      const bool two = halves == 2 && (mt * sc.bm + 128 < a.M);     // skip the second M half of a ragged last tile
+      int nh = (a.M - mt * sc.bm + 127) >> 7;                        // valid 128-row halves of a ragged last tile
+      if (nh > halves) nh = halves;
       const int acc = sc.nacc == 2 ? (it & 1) : 0;
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       mbar_wait(&acc_empty[acc], accphase ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)acc * acc_stride, d1 = d0 + hs;
+      const uint32_t dbase = tmem_base + (uint32_t)acc * acc_stride;
       for (int c = 0; c < a.kchunks; ++c) {
         int ksteps = (a.Cin - c * BK + UMMA_K - 1) / UMMA_K;
         if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
+        const uint32_t dsplit = dbase + (sc.ksplit == 2 ? (uint32_t)(c & 1) * hs : 0u);
+        const uint32_t hstep = (uint32_t)sc.ksplit * hs;                // TMEM columns between consecutive halves
         mbar_wait(&a_full[sa], pa);
         uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
         for (int j = 0; j < a.taps; ++j, a_lo += tap_lo) {
-          mbar_wait(&b_full[sb], pb);
+          if (sc.bres) { if (it == 0 && c == 0 && j == 0) mbar_wait(&b_full[0], 0); }
+          else mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
-          const uint32_t first = (c > 0 || j > 0) ? 1u : 0u;
+          const uint32_t b_lo = b_lo0 + (uint32_t)(sc.bres ? c * a.taps + j : sb) * b_stage_lo;
+          const uint32_t accum = (c >= sc.ksplit || j > 0) ? 1u : 0u;
           if (elect_one()) {
-            if (ksteps == 4) {
-              umma_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, first);
-              umma_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
-              umma_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
-              umma_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
-              if (two) {
-                umma_bf16_lohi(d1, a_lo + 1024 + 0, b_lo + 0, idesc, first);      // +128 rows x 128 B = 1024 x 16 B
-                umma_bf16_lohi(d1, a_lo + 1024 + 2, b_lo + 2, idesc, 1u);
-                umma_bf16_lohi(d1, a_lo + 1024 + 4, b_lo + 4, idesc, 1u);
-                umma_bf16_lohi(d1, a_lo + 1024 + 6, b_lo + 6, idesc, 1u);
-              }
-            } else {
-              for (int k = 0; k < ksteps; ++k) umma_bf16_lohi(d0, a_lo + 2 * k, b_lo + 2 * k, idesc, (first | (uint32_t)k) ? 1u : 0u);
-              if (two)
-                for (int k = 0; k < ksteps; ++k) umma_bf16_lohi(d1, a_lo + 1024 + 2 * k, b_lo + 2 * k, idesc, (first | (uint32_t)k) ? 1u : 0u);
-            }
-            umma_commit(&b_empty[sb]);
+            // halves innermost: consecutive MMAs go to different accumulators, so the chain of dependent accumulations
+            // into one accumulator never stalls the tensor pipe (matters when an MMA is short: small BN). The common
+            // shapes are fully unrolled: ONE thread issues every MMA of the CTA, and a generic double loop here cost
+            // 40 % of the GEMM throughput (sweep_e.log).
+            if (ksteps == 4 && nh == 1) issue_tap<1>(dsplit, hstep, a_lo, b_lo, idesc, accum);
+            else if (ksteps == 4 && nh == 2) issue_tap<2>(dsplit, hstep, a_lo, b_lo, idesc, accum);
+            else if (ksteps == 4 && nh == 4) issue_tap<4>(dsplit, hstep, a_lo, b_lo, idesc, accum);
+            else
+              for (int k = 0; k < ksteps; ++k)
+                for (int h = 0; h < nh; ++h)
+                  umma_bf16_lohi(dsplit + (uint32_t)h * hstep, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc,
+                                 (accum | (uint32_t)k) ? 1u : 0u);      // +128 rows x 128 B = 1024 x 16 B per half
+            if (!sc.bres) umma_commit(&b_empty[sb]);
             if (j == a.taps - 1) umma_commit(&a_empty[sa]);
             if (j == a.taps - 1 && c == a.kchunks - 1) umma_commit(&acc_full[acc]);
           }
           __syncwarp();
-          if (++sb == sc.nB) { sb = 0; pb ^= 1; }
+          if (!sc.bres && ++sb == sc.nB) { sb = 0; pb ^= 1; }
         }
         if (++sa == sc.nA) { sa = 0; pa ^= 1; }
       }
     }
   } else {
-    // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4; e = (warp - 2) / 4 selects the M half (bm = 256) or
-    // the odd / even 32-column blocks (bm = 128) =====
+    // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4; e = (warp - 2) / 4 selects the odd / even 32-column
+    // blocks (1 half), the M half (2 halves) or the pair of halves {e, e+2} (4 halves) =====
     const int q = warp & 3, e = (warp - 2) >> 2;
     float* stg = smem_epi + (warp - 2) * (EPI_STAGE_BYTES / 4);
-    const int h = halves == 2 ? e : 0;
-    const int cb_first = halves == 2 ? 0 : e * 32, cb_step = halves == 2 ? 32 : 64;
+    const int cb_first = halves == 1 ? e * 32 : 0, cb_step = halves == 1 ? 64 : 32;
+    const int h_first = halves == 1 ? 0 : e, h_step = 2;
     const bool has_res = KIND == EPI_STD && a.res != nullptr;
+    const uint32_t ks_off = sc.ksplit == 2 ? (uint32_t)sc.half_stride : 0u;
     int it = 0;
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
       const int bg = tile / per_bg, rem = tile - bg * per_bg;
@@ -361,19 +404,21 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
       EpiPos p;
       p.sub = lane >> 3; p.c4 = lane & 7;
       p.n0 = nt * a.BN;
-      p.t_row0 = mt * sc.bm + h * 128 + q * 32;
+      p.t_row0 = mt * sc.bm + h_first * 128 + q * 32;
       p.obase = (long)b * a.o_bstride;
       p.gshift = (long)g * a.N + a.o_shift;
-      const bool rows_ok = p.t_row0 < a.M;                  // warp-uniform: this 32-row block holds valid rows
       float4 res[8];
-      if (has_res && rows_ok) epi_load_res(a, p, cb_first, res);      // overlaps the main loop
+      if (has_res && p.t_row0 < a.M) epi_load_res(a, p, cb_first, res);      // overlaps the main loop
       const int acc = sc.nacc == 2 ? (it & 1) : 0;
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       mbar_wait(&acc_full[acc], accphase);
       tc_fence_after();
-      if (rows_ok) {
-        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_stride + (uint32_t)(h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
-        epilogue_warp<KIND, ACT>(a, p, taddr, stg, lane, g, cb_first, cb_step, res);
+      for (int h = h_first; h < halves; h += h_step) {
+        p.t_row0 = mt * sc.bm + h * 128 + q * 32;
+        if (p.t_row0 >= a.M) break;                         // warp-uniform: no valid rows in this 32-row block
+        if (has_res && h != h_first) epi_load_res(a, p, cb_first, res);
+        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_stride + (uint32_t)(h * sc.ksplit * sc.half_stride) + ((uint32_t)(q * 32) << 16);
+        epilogue_warp<KIND, ACT>(a, p, taddr, ks_off, stg, lane, g, cb_first, cb_step, res);
       }
       tc_fence_before();
       __syncwarp();
@@ -495,10 +540,20 @@ int sm_count() {
 }
 
 // Tile shape (bm, BN) for a problem of `units` = B*groups independent (M x N) outputs on `sms` SMs.
-// Cost model: waves x tile area (a tile's main loop is proportional to bm*BN*K; K is common), then prefer the shape with
-// the smaller L2->SMEM traffic per FLOP (1/bm + 1/BN) and, on a tie, double-buffered accumulators.
-struct TileShape { int bm, bn; };
-TileShape pick_tile(int M, int N, long units, int sms, bool rope) {
+// Cost model fitted to the tile sweep of profiles/r01/sweep_gemm_c.log (B200, 148 SMs):
+//   time ~ waves x (bm x BN) x f,   f = max(1, (1/bm + 1/BN) / (1/128 + 1/256)) x mma(BN)
+// The first factor is the L2->SMEM operand traffic per FLOP relative to a 128x256 tile (smaller tiles are L2-bandwidth
+// bound), the second the shared-memory read rate of the MMA itself: an M=128 UMMA re-reads its B operand, so N=128 needs
+// 128 B/clk of shared memory against 96 B/clk at N=256 (measured 1.2x slower per FLOP, N=192 1.07x).
+// A single accumulator stage (no epilogue / main-loop overlap) is charged when a CTA runs more than one tile.
+struct TileShape { int halves, bn, ksplit; };
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+int half_stride_of(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
+TileShape pick_tile(int M, int N, int kchunks, int taps, long units, int sms, bool rope) {
   int cands[8]; int nc = 0;
   if (N < 64) {
     cands[nc++] = (int)round_up(N, 16);                    // one N tile; rows beyond N are TMA zero fill
@@ -506,30 +561,33 @@ TileShape pick_tile(int M, int N, long units, int sms, bool rope) {
     for (int bn : {256, 192, 128, 96, 64})
       if (N % bn == 0 || (bn == 128 && N % 64 != 0 && N % 96 != 0)) cands[nc++] = bn;     // 128: ragged-tail fallback
   }
-  {                                                          // experiment override (tools/bench_gemm.py)
-    const char* ebm = getenv("B200TTS_BM");
-    const char* ebn = getenv("B200TTS_BN");
-    if (ebm && ebn) {
-      const int bm = atoi(ebm), bn = atoi(ebn);
-      if ((bm == 128 || bm == 256) && bn >= 16 && bn <= 256 && bn % 16 == 0 && (!rope || bn % 64 == 0)) return TileShape{bm, bn};
-    }
-  }
-  TileShape best{256, cands[0]};
-  double best_cost = 1e300, best_traffic = 1e300;
+  TileShape best{1, cands[0], 1};
+  double best_cost = 1e300;
   for (int ci = 0; ci < nc; ++ci) {
     const int bn = cands[ci];
-    for (int bm : {256, 128}) {
-      if (bm == 256 && bn > 256) continue;
-      if (rope && bn % 64 != 0) continue;
+    if (rope && bn % 64 != 0) continue;
+    for (int halves : {1, 2, 4}) {
+      const int hs = half_stride_of(bn);
+      if (halves * hs > 512) continue;
+      if (halves == 4 && bn > 64) continue;                // 512-row tiles only for the thin (HBM-bound) convolutions
+      const int bm = 128 * halves;
       const long tiles = units * ceil_div(M, bm) * ceil_div(N, bn);
       const long waves = (tiles + sms - 1) / sms;
-      const double cost = (double)waves * bm * bn;
-      const double traffic = 1.0 / bm + 1.0 / bn;
-      if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && traffic < best_traffic)) {
-        best_cost = cost; best_traffic = traffic; best = TileShape{bm, bn};
-      }
+      const double traffic = (1.0 / bm + 1.0 / bn) / (1.0 / 128 + 1.0 / 256);
+      const double mma = bn >= 256 ? 1.0 : bn >= 192 ? 1.07 : 1.2;
+      const bool single_acc = 2 * halves * hs > 512;
+      double cost = (double)waves * bm * bn * (traffic > 1.0 ? traffic : 1.0) * mma;
+      if (single_acc && waves > 1) cost *= 1.1;
+      if (cost < best_cost) { best_cost = cost; best = TileShape{halves, bn, 1}; }
     }
   }
+  // experiment overrides (tools/sweep_gemm.sh)
+  const int ebm = env_int("B200TTS_BM", 0), ebn = env_int("B200TTS_BN", 0);
+  if (ebm && ebn && (ebm == 128 || ebm == 256 || ebm == 512) && ebn >= 16 && ebn <= 256 && ebn % 16 == 0 && (!rope || ebn % 64 == 0) &&
+      (ebm / 128) * half_stride_of(ebn) <= 512)
+    best = TileShape{ebm / 128, ebn, 1};
+  const int eks = env_int("B200TTS_KSPLIT", 0);
+  if (eks == 2 && taps == 1 && kchunks >= 2 && 2 * best.halves * half_stride_of(best.bn) <= 512) best.ksplit = 2;
   return best;
 }
 
@@ -541,7 +599,7 @@ TcArgs make_args(const RowGemm& p, int BN) {
   a.o_limit = p.o_limit ? p.o_limit : (long)p.M * p.ldo;
   a.out_bf16 = p.out_bf16;
   a.bias = p.bias; a.gate = p.gate; a.res = p.res; a.accumulate = p.accumulate; a.scale = p.scale;
-  a.rope_cos = p.rope_cos; a.rope_sin = p.rope_sin; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
+  a.rope_cs = p.rope_cs; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
   a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
   a.out2 = p.out2;
   return a;
@@ -566,14 +624,16 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   B2_CHECK(p.ldx % 8 == 0 && p.x_bstride % 8 == 0, "rowgemm_tc: A rows must be 16-byte aligned");
   B2_CHECK(p.groups == 1 || p.Cin % BK == 0, "rowgemm_tc: grouped problems need Cin % 64 == 0");
   B2_CHECK(p.M > 0 && p.B > 0, "rowgemm_tc: empty problem");
-  const bool rope = p.rope_cos != nullptr;
-  B2_CHECK(!rope || (p.rope_sin != nullptr && p.rope_cols % 64 == 0 && p.vt_col0 % 32 == 0 && p.groups == 1 && p.B == 1),
+  const bool rope = p.rope_cs != nullptr;
+  B2_CHECK(!rope || (p.rope_cols % 64 == 0 && p.vt_col0 % 32 == 0 && p.groups == 1 && p.B == 1),
            "rowgemm_tc: malformed rope epilogue");
   B2_CHECK(!rope || (p.gate == nullptr && p.res == nullptr && !p.accumulate && p.act == ACT_NONE && p.out2 == nullptr),
            "rowgemm_tc: the rope epilogue takes bias only");
 
   const int sms = sm_count();
-  const TileShape ts = pick_tile(p.M, p.N, (long)p.B * p.groups, sms, rope);
+  const int kchunks = ceil_div(p.Cin, BK);
+  const TileShape ts = pick_tile(p.M, p.N, kchunks, p.taps, (long)p.B * p.groups, sms, rope);
+  const int bm = 128 * ts.halves;
   CUtensorMap map_a, map_b;
   tc_encode_map(&map_a, p.x, (uint64_t)p.groups * p.Cin, (uint64_t)p.Lin, (uint64_t)p.B, (uint64_t)p.ldx,
                 (uint64_t)p.x_bstride, (uint32_t)A_BOX_ROWS);
@@ -581,24 +641,31 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
                 (uint64_t)w.N * w.ldc, (uint32_t)ts.bn);
   TcArgs a = make_args(p, ts.bn);
   Tc3Sched sc;
-  sc.bm = ts.bm;
-  sc.m_tiles = ceil_div(p.M, ts.bm);
+  sc.bm = bm; sc.halves = ts.halves; sc.ksplit = ts.ksplit;
+  sc.m_tiles = ceil_div(p.M, bm);
   sc.n_tiles = ceil_div(p.N, ts.bn);
   const long tiles = (long)p.B * p.groups * sc.m_tiles * sc.n_tiles;
   B2_CHECK(tiles < (1L << 30), "rowgemm_tc: too many tiles");
   sc.num_tiles = (int)tiles;
   const int halo = (p.taps - 1) * p.dil;
-  sc.a_rows = (int)round_up(ts.bm + halo, A_BOX_ROWS);
-  sc.half_stride = ts.bn <= 128 ? 128 : 256;
-  const int halves = ts.bm / 128;
-  sc.nacc = (2 * halves * sc.half_stride <= 512) ? 2 : 1;
+  sc.a_rows = (int)round_up(bm + halo, A_BOX_ROWS);
+  sc.half_stride = half_stride_of(ts.bn);
+  sc.nacc = (2 * ts.halves * ts.ksplit * sc.half_stride <= 512) ? 2 : 1;
   const int a_stage = sc.a_rows * 128, b_stage = ts.bn * 128;
   const int bar_bytes = (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * 8 + 16;
   const int budget = 227 * 1024 - 1024 - bar_bytes - EPI_BYTES;
   // ring depths: a plain GEMM consumes one A and one B stage per 64-channel chunk -> equal depths; a convolution
-  // consumes `taps` B stages per A stage -> two A stages, the rest of shared memory for B
+  // consumes `taps` B stages per A stage -> two A stages, the rest of shared memory for B. A thin convolution whose whole
+  // weight tensor fits beside two A stages keeps it resident (one fetch per CTA, no per-tap barrier traffic).
   int nA, nB;
-  if (p.taps == 1) {
+  sc.bres = 0;
+  const long w_bytes = (long)kchunks * p.taps * b_stage;
+  if (p.taps > 1 && p.groups == 1 && sc.n_tiles == 1 && w_bytes + 2L * a_stage <= budget && env_int("B200TTS_BRES", 1) != 0) {
+    sc.bres = 1;
+    nB = kchunks * p.taps;
+    nA = (int)((budget - w_bytes) / a_stage);
+    if (nA > 4) nA = 4;
+  } else if (p.taps == 1) {
     nA = budget / (a_stage + b_stage);
     if (nA > 6) nA = 6;
     if (nA < 1) nA = 1;
