@@ -307,12 +307,11 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     G = N - ref_len
     ns = cfg.hop * (G - 1)
     work = f5_work(cfg, N, ref_len)
-    audio_h = [torch.from_numpy(a.reshape(-1)).pin_memory() for a, _, _, _ in ins]
-    ids_h = [torch.from_numpy(t.reshape(-1)).pin_memory() for _, t, _, _ in ins]
-    noise_h = [torch.from_numpy(n.reshape(-1)).pin_memory() for _, _, _, n in ins]
-    audio_d = [a.cuda() for a in audio_h]
-    ids_d = [t.cuda() for t in ids_h]
-    noise_d = [n.cuda() for n in noise_h]
+    # contiguous per-utterance blocks: audio [U][L] i16, text ids [U][n_text] i32, Euler-start noise [U][N*100] f32
+    audio_h = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).pin_memory()
+    ids_h = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).pin_memory()
+    noise_h = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).pin_memory()
+    audio_d, ids_d, noise_d = audio_h.cuda(), ids_h.cuda(), noise_h.cuda()
     pcm_d = torch.empty((U, ns), dtype=torch.int16, device="cuda")
     pcm_h = torch.empty((U, ns), dtype=torch.int16).pin_memory()
     mel_d = torch.empty((U, N, cfg.n_mels), dtype=torch.float32, device="cuda")
@@ -323,18 +322,17 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     torch.cuda.synchronize()
 
     def core():
-        for i in range(U):
-            eng.f5_synthesize_device(audio_d[i].data_ptr(), L, ids_d[i].data_ptr(), args.n_text, N, noise_d[i].data_ptr(),
-                                     pcm_d[i].data_ptr(), precision=prec, mel_ptr=mel_d[i].data_ptr() if with_vocoder else 0)
+        # one batched DiT loop over the U utterances of this GPU (they share N: length-bucketed batching)
+        eng.f5_synthesize_batch_device(U, audio_d.data_ptr(), L, ids_d.data_ptr(), args.n_text, N, noise_d.data_ptr(),
+                                       pcm_d.data_ptr(), precision=prec, mel_ptr=mel_d.data_ptr() if with_vocoder else 0)
         if with_vocoder:
             vmel_d.copy_(mel_d[:, ref_len:, :].transpose(1, 2))          # (U, 100, G): BigVGAN's mel_features layout
             eng.bigvgan_run_device(vmel_d.data_ptr(), U, G, vpcm_d.data_ptr(), precision=prec)
 
     def step_e2e():
-        for i in range(U):
-            audio_d[i].copy_(audio_h[i], non_blocking=True)
-            ids_d[i].copy_(ids_h[i], non_blocking=True)
-            noise_d[i].copy_(noise_h[i], non_blocking=True)
+        audio_d.copy_(audio_h, non_blocking=True)
+        ids_d.copy_(ids_h, non_blocking=True)
+        noise_d.copy_(noise_h, non_blocking=True)
         core()
         if with_vocoder:
             vpcm_h.copy_(vpcm_d, non_blocking=True)

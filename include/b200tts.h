@@ -85,6 +85,15 @@ int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, in
                                  int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
                                  int16_t* pcm_dev, float* mel_dev);
 
+/* Batched fast path: U utterances that share (L, n_text, max_duration) -- the caller buckets by length, which is how the
+ * reference's one-utterance-per-run loop (F5-TTS-ONNX-Inference.py:247-311) is widened for config 4 (many utterances per
+ * GPU). Buffers are contiguous per utterance: audio [U][L], text_ids [U][n_text], noise [U][N][100], pcm [U][256*(N-F-1)],
+ * mel (optional) [U][N][100]. Results are identical to U calls of b200tts_f5_synthesize_device (the utterances never mix:
+ * every kernel is row-wise or per-sequence). bf16 engine only for U > 1. */
+int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* audio_dev, int64_t L,
+                                       const int32_t* text_ids_dev, int n_text, int64_t max_duration, const float* noise_dev,
+                                       int precision, int n_steps, int16_t* pcm_dev, float* mel_dev);
+
 /* ---- single-op entry points (parity tests of the kernels through the boundary) -------------------------
  * Anti-aliased SnakeBeta (BigVGAN/modeling_modified/act.py:25-29): x (B, C, L) fp32 host in the reference
  * layout -> y (B, C, L) (post=0) or (B, C, L+30) (post=1, the bigvgan.py:370,381-382 tables). alpha_log /

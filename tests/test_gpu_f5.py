@@ -156,6 +156,35 @@ def test_synthesize_other_sizes_vs_oracle(f5, g):
     assert snr_db(want_pcm.numpy(), pcm) > 55.0
 
 
+def test_synthesize_batch_matches_single(f5, g):
+    """Length-bucketed batching (config 4): U utterances through ONE batched DiT loop give what U single calls give."""
+    import torch
+    U, L, n_text = 3, 9000, 20
+    ins = [synth.f5_inputs(50 + i, L, n_text) for i in range(U)]
+    N = int(ins[0][2][0])
+    ns = 256 * (N - (L // 256 + 1) - 1)
+    audio = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).cuda()
+    ids = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).cuda()
+    noise = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).cuda()
+    pcm_b = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
+    mel_b = torch.zeros((U, N, CFG.n_mels), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    f5.f5_synthesize_batch_device(U, audio.data_ptr(), L, ids.data_ptr(), n_text, N, noise.data_ptr(), pcm_b.data_ptr(),
+                                  precision=capi.BF16, n_steps=4, mel_ptr=mel_b.data_ptr())
+    f5.synchronize()
+    for u in range(U):
+        pcm_1 = torch.zeros((ns,), dtype=torch.int16, device="cuda")
+        mel_1 = torch.zeros((N, CFG.n_mels), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        f5.f5_synthesize_device(audio[u].data_ptr(), L, ids[u].data_ptr(), n_text, N, noise[u].data_ptr(), pcm_1.data_ptr(),
+                                precision=capi.BF16, n_steps=4, mel_ptr=mel_1.data_ptr())
+        f5.synchronize()
+        # every kernel is row-wise or per-sequence and accumulates over K in the same order whatever the tile shape
+        np.testing.assert_allclose(mel_b[u].cpu().numpy(), mel_1.cpu().numpy(), rtol=0, atol=1e-5)
+        assert np.abs(pcm_b[u].cpu().numpy().astype(np.int32) - pcm_1.cpu().numpy().astype(np.int32)).max() <= 1
+    assert float(mel_b.abs().max()) > 0.1 and not bool(torch.equal(mel_b[0], mel_b[1]))
+
+
 def test_f5_session_surface(f5, g):
     """The reference's own loop (F5-TTS-ONNX-Inference.py:247-311) against the drop-in sessions."""
     from b200tts import session as onnxruntime

@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200tts_f5_decode": (_int, [_vp, _vp, _int, ctypes.c_int64, _vp, _vp, _c_i64]),
     "b200tts_f5_synthesize": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _c_i64, _vp]),
     "b200tts_f5_synthesize_device": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
+    "b200tts_f5_synthesize_batch_device": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
     "b200tts_aa_activation": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp]),
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
@@ -221,6 +222,13 @@ class Engine:
         self._check(self.lib.b200tts_f5_synthesize_device(self.handle, _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
                                                           int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
                                                           _vp(pcm_ptr), _vp(mel_ptr or 0)), "f5_synthesize_device")
+
+    def f5_synthesize_batch_device(self, U, audio_ptr, L, ids_ptr, n_text, max_duration, noise_ptr, pcm_ptr, precision=BF16,
+                                   n_steps: int = -1, mel_ptr: int = 0):
+        """U utterances sharing (L, n_text, max_duration) through one batched DiT loop (device buffers, no sync)."""
+        self._check(self.lib.b200tts_f5_synthesize_batch_device(self.handle, int(U), _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
+                                                                int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
+                                                                _vp(pcm_ptr), _vp(mel_ptr or 0)), "f5_synthesize_batch_device")
 
     def bench_rowgemm(self, B, M, N, Cin, taps=1, dil=1, groups=1, epilogue=0, iters=20) -> float:
         """Average ms per launch of the tensor-core shifted-row GEMM on synthetic operands (tools/bench_gemm.py)."""

@@ -268,6 +268,41 @@ static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const i
               [&] { f5_restore_shape(E, (int)N, (int)(L / 256 + 1)); });
 }
 
+// U utterances that share (L, n_text, max_duration): graph A per utterance, ONE batched DiT loop over all 2U sequences
+// (the GEMMs see M = 2*U*N rows instead of 2*N), graph C per utterance.
+static void synth_batch_device(Engine& E, int U, const int16_t* audio_dev, int64_t L, const int32_t* ids_dev, int n_text, int64_t N,
+                               const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev) {
+  cudaStream_t s = E.stream;
+  const int nm = f5_n_mels(E);
+  const int F = (int)(L / 256 + 1);
+  const long ns = 256L * (N - F - 1);
+  run_graphed(E, {31, U, (long long)(uintptr_t)audio_dev, (long long)L, (long long)(uintptr_t)ids_dev, n_text, (long long)N,
+                  (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
+              [&] {
+                for (int u = 0; u < U; ++u)
+                  f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U);
+                B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                f5_prepare_cond(E);
+                f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
+                for (int u = 0; u < U; ++u)
+                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr);
+                if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+              },
+              [&] { f5_restore_shape(E, (int)N, F, U); });
+}
+
+int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
+                                       int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
+                                       int16_t* pcm_dev, float* mel_dev) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_dev && text_ids_dev && noise_dev && pcm_dev, "f5_synthesize_batch_device: null buffer");
+    B2_CHECK(U >= 1 && L > 0 && n_text > 0 && max_duration > L / 256 + 2, "f5_synthesize_batch_device: bad sizes");
+    B2_CHECK(precision == PREC_BF16 || U == 1, "f5_synthesize_batch_device: the fp32 parity engine takes one utterance at a time");
+    synth_batch_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, pcm_dev, mel_dev);
+  });
+}
+
 int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
                                  int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
                                  int16_t* pcm_dev, float* mel_dev) {
@@ -469,7 +504,7 @@ int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_hos
     B2_CUDA(cudaMemcpyAsync(d_vt.p, vt.data(), vt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     cast_f32_to_bf16(d_qk.p, qk16.p, (long)qk.size(), s);
     cast_f32_to_bf16(d_vt.p, vt16.p, (long)vt.size(), s);
-    attention_tc(qk16.p, vt16.p, Np, o16.p, N, H, s);
+    attention_tc(qk16.p, vt16.p, Np, o16.p, 2, N, H, s);
     cast_bf16_to_f32(o16.p, d_o32.p, (long)2 * N * D, s);
     B2_CUDA(cudaMemcpyAsync(out_host, d_o32.p, d_o32.n * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));

@@ -16,7 +16,7 @@
 // 2^8, which bf16 and the fp32 accumulators hold without loss.
 // The first version (r01b: 30.5 us per call, 16.8 M instructions, issue-bound) walked S twice with 128 threads, kept O
 // in registers and folded PV into it every block (64 FFMA + 2 TMEM loads per row per block).
-// 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = softmax/epilogue.
+// 320 threads: warps 0-7 = softmax/epilogue, warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.
 // Shared memory 112 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA phases.
 #include "attention_tc.cuh"
 
@@ -33,6 +33,7 @@ using namespace tc;
 
 constexpr int BQ = 128, BKEY = 128, HD = 64;
 constexpr int NTHREADS = 320;
+constexpr int WARP_TMA = 8, WARP_MMA = 9;       // highest warp ids: the SMSP arbiter favours them over the softmax warps
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
 constexpr int K_BYTES = BKEY * HD * 2;          // 16 KB
 constexpr int V_BYTES = HD * BKEY * 2;          // 16 KB = two [64 d][64 keys] chunks
@@ -114,14 +115,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  if (warp == WARP_MMA) tmem_alloc(tmem_ptr, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // O_a: +128..191, O_b: +192..255
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     if (lane == 0) {
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_3d(sQ, &map_qk, q_full, h * HD, q0, b);
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         tma_load_3d(sV + s * V_BYTES + V_BYTES / 2, &map_v, &kv_full[s], j * BKEY + 64, 0, bh);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKEY >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     }
   } else {
     // ===== softmax + epilogue: row r of the query tile, key half g of every block =====
-    const int qd = warp & 3, g = (warp - 2) >> 2;
+    const int qd = warp & 3, g = warp >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const uint32_t tmem_Og = tmem_O + (uint32_t)(g * 64);
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -318,20 +319,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
 
 }  // namespace
 
-void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int N, int H, cudaStream_t stream) {
-  B2_CHECK(N > 0 && H > 0, "attention_tc: empty problem");
+void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream) {
+  B2_CHECK(S > 0 && N > 0 && H > 0, "attention_tc: empty problem");
   B2_CHECK(ldv % 8 == 0 && ldv >= N, "attention_tc: V^T row stride must be a multiple of 8 and >= N");
   CUtensorMap map_qk, map_v;
-  // q|k: [2][N][2*H*64] bf16 -> dims {2*H*64, N, 2}, box {64, 128, 1}
-  tc_encode_map(&map_qk, qk, (uint64_t)2 * H * HD, (uint64_t)N, 2, (uint64_t)2 * H * HD, (uint64_t)N * 2 * H * HD, BQ);
-  // V^T: [2*H][64][ldv] bf16 -> dims {N keys, 64 d, 2H}, box {64 keys, 64 d, 1}
-  tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)2 * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
+  // q|k: [S][N][2*H*64] bf16 -> dims {2*H*64, N, S}, box {64, 128, 1}
+  tc_encode_map(&map_qk, qk, (uint64_t)2 * H * HD, (uint64_t)N, (uint64_t)S, (uint64_t)2 * H * HD, (uint64_t)N * 2 * H * HD, BQ);
+  // V^T: [S*H][64][ldv] bf16 -> dims {N keys, 64 d, S*H}, box {64 keys, 64 d, 1}
+  tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
   static std::once_flag once;
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
   AttnArgs a{N, H, out, H * HD};
-  dim3 grid(ceil_div(N, BQ), H, 2);
+  B2_CHECK(S <= 65535, "attention_tc: too many sequences");
+  dim3 grid(ceil_div(N, BQ), H, S);
   attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map_qk, map_v, a);
   B2_LAUNCH_CHECK();
   count_launch();

@@ -4,9 +4,10 @@
 
 namespace b200tts {
 
-// qk : bf16 [2][N][2*H*64] -- roped q in columns [0, H*64), roped k in [H*64, 2*H*64) (head h = 64-column group)
-// vT : bf16 [2*H][64][ldv] -- V transposed per (batch, head): vT[b*H + h][d][t]
-// out: bf16 [2][N][H*64]   -- softmax(q k^T) v, heads concatenated (the layout the out-projection GEMM reads)
-void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int N, int H, cudaStream_t stream);
+// S independent sequences of N tokens (F5: the CFG pair of each utterance of the batch, S = 2U)
+// qk : bf16 [S][N][2*H*64] -- roped q in columns [0, H*64), roped k in [H*64, 2*H*64) (head h = 64-column group)
+// vT : bf16 [S*H][64][ldv] -- V transposed per (sequence, head): vT[s*H + h][d][t]
+// out: bf16 [S][N][H*64]   -- softmax(q k^T) v, heads concatenated (the layout the out-projection GEMM reads)
+void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream);
 
 }  // namespace b200tts

@@ -87,6 +87,7 @@ struct F5Model {
 
   // ---- per-utterance state + workspaces (grow-only) ----
   int N = 0, ref_len = 0, Npad = 0;
+  int U = 1;                 // utterances in flight (equal N): rows of every DiT tensor are [u][cfg row][t]
   DevBuf<float> noise, cond, cond_drop, cproj, x, h, pred, rope_c, rope_s;
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
@@ -345,21 +346,23 @@ int f5_seq_len(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); ret
 int f5_cond_dim(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->cond_dim; }
 int f5_n_mels(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->n_mels; }
 int f5_nfe(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->nfe; }
-float* f5_cond(Engine& e) { return model(e).cond.p; }
-float* f5_cond_drop(Engine& e) { return model(e).cond_drop.p; }
-float* f5_noise(Engine& e) { return model(e).noise.p; }
+float* f5_cond(Engine& e, int u) { F5Model& m = model(e); return m.cond.p + (size_t)u * m.N * m.cond_dim; }
+float* f5_cond_drop(Engine& e, int u) { F5Model& m = model(e); return m.cond_drop.p + (size_t)u * m.N * m.cond_dim; }
+float* f5_noise(Engine& e, int u) { F5Model& m = model(e); return m.noise.p + (size_t)u * m.N * m.n_mels; }
 
-void f5_begin(Engine& e, int N) {
+void f5_begin(Engine& e, int N, int U) {
   F5Model& m = model(e);
   B2_CHECK(N > 0 && N <= m.max_frames, "max_duration must be in [1, MAX_SIGNAL_LENGTH]");
-  m.N = N; m.Npad = (int)round_up(N, 8);
-  m.noise.reserve((size_t)N * m.n_mels);
-  m.cond.reserve((size_t)N * m.cond_dim);
-  m.cond_drop.reserve((size_t)N * m.cond_dim);
-  m.cproj.reserve((size_t)2 * N * m.D);
-  m.x.reserve((size_t)2 * N * m.D);
-  m.h.reserve((size_t)2 * N * m.D);
-  m.pred.reserve((size_t)2 * N * m.n_mels);
+  B2_CHECK(U >= 1 && U <= 4096, "batch of utterances must be in [1, 4096]");
+  m.N = N; m.Npad = (int)round_up(N, 8); m.U = U;
+  const size_t S = (size_t)2 * U;
+  m.noise.reserve((size_t)U * N * m.n_mels);
+  m.cond.reserve((size_t)U * N * m.cond_dim);
+  m.cond_drop.reserve((size_t)U * N * m.cond_dim);
+  m.cproj.reserve(S * N * m.D);
+  m.x.reserve(S * N * m.D);
+  m.h.reserve(S * N * m.D);
+  m.pred.reserve(S * N * m.n_mels);
   m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;     // rows [0, N) of the fp16-rounded tables
 }
 
@@ -378,31 +381,38 @@ void f5_rope_buffers(Engine& e, float** d_cos, float** d_sin) {
   *d_cos = m.rope_c.p; *d_sin = m.rope_s.p;
 }
 
-void f5_restore_shape(Engine& e, int N, int ref_len) {
+void f5_restore_shape(Engine& e, int N, int ref_len, int U) {
   F5Model& m = model(e);
-  m.N = N; m.Npad = (int)round_up(N, 8); m.ref_len = ref_len;
+  m.N = N; m.Npad = (int)round_up(N, 8); m.ref_len = ref_len; m.U = U;
   m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;
 }
 
 void f5_prepare_cond(Engine& e) {
   F5Model& m = model(e);
   Epi ep; ep.bias = m.wc.bias.p;
-  linear(e, "f5.cond_proj", m.wc, false, m.cond.p, m.cond_dim, m.N, m.cproj.p, m.D, ep);
-  linear(e, "f5.cond_proj", m.wc, false, m.cond_drop.p, m.cond_dim, m.N, m.cproj.p + (size_t)m.N * m.D, m.D, ep);
+  for (int u = 0; u < m.U; ++u) {             // sequence 2u = cond, 2u+1 = cond_drop of utterance u
+    const size_t co = (size_t)u * m.N * m.cond_dim, po = (size_t)2 * u * m.N * m.D;
+    linear(e, "f5.cond_proj", m.wc, false, m.cond.p + co, m.cond_dim, m.N, m.cproj.p + po, m.D, ep);
+    linear(e, "f5.cond_proj", m.wc, false, m.cond_drop.p + co, m.cond_dim, m.N, m.cproj.p + po + (size_t)m.N * m.D, m.D, ep);
+  }
 }
 
 // =============================================================================================
 // graph A
 // =============================================================================================
-void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N) {
+void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u, int U) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   const int F = (int)(L / m.hop) + 1;
   B2_CHECK(L > m.nfft / 2, "audio too short for the reflect-padded STFT");
   B2_CHECK(n_text >= 0 && n_text <= N, "text_ids longer than max_duration");
   B2_CHECK(F <= N, "max_duration shorter than the reference audio");
-  f5_begin(e, N);
+  B2_CHECK(u >= 0 && u < U, "utterance index outside the batch");
+  if (u == 0) f5_begin(e, N, U);
+  B2_CHECK(m.N == N && m.U == U, "utterances of one batch must share max_duration");
   m.ref_len = F;
+  float* cond = m.cond.p + (size_t)u * N * m.cond_dim;
+  float* cond_drop = m.cond_drop.p + (size_t)u * N * m.cond_dim;
   // ---- STFT -> |X| -> mel -> log : cond[:, :n_mels] ----
   {
     ProfScope ps(e.prof, "f5.pre_elementwise", s);
@@ -428,8 +438,8 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
   }
   {
     ProfScope ps(e.prof, "f5.pre_elementwise", s);
-    logmel_into(m.mel.p, F, m.cond.p, m.cond_dim, 0, N, m.n_mels, s);
-    copy_cols(nullptr, 0, m.cond_drop.p, m.cond_dim, 0, N, m.n_mels, s);         // zeros
+    logmel_into(m.mel.p, F, cond, m.cond_dim, 0, N, m.n_mels, s);
+    copy_cols(nullptr, 0, cond_drop, m.cond_dim, 0, N, m.n_mels, s);         // zeros
   }
   // ---- text embedding (dit.py:49-73), text then text_drop ----
   const int TD = m.text_dim, TW = m.text_blocks.empty() ? TD : m.text_blocks[0].pw1.N;
@@ -454,7 +464,7 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
       mask_rows(m.t_b.p, m.ids.p, N, TD, s);
       std::swap(m.t_a, m.t_b);
     }
-    copy_cols(m.t_a.p, TD, drop == 0 ? m.cond.p : m.cond_drop.p, m.cond_dim, m.n_mels, N, TD, s);
+    copy_cols(m.t_a.p, TD, drop == 0 ? cond : cond_drop, m.cond_dim, m.n_mels, N, TD, s);
   }
 }
 
@@ -469,7 +479,7 @@ void gconv(Engine& e, GConv& g, bool fast, const void* x, int N, void* out, int 
   RowGemm p;
   p.x = x; p.x_bstride = (long)N * g.C; p.ldx = g.C; p.Lin = N;
   p.Cin = cg; p.N = cg; p.taps = g.k; p.dil = 1; p.center = (g.k - 1) / 2; p.groups = g.groups;
-  p.M = N; p.B = 2;
+  p.M = N; p.B = 2 * m.U;
   p.out = out; p.o_bstride = (long)N * g.C; p.ldo = g.C; p.out_bf16 = out_bf16;
   p.bias = g.bias.p; p.act = act; p.res = res;
   (void)m;
@@ -493,10 +503,10 @@ void gconv(Engine& e, GConv& g, bool fast, const void* x, int N, void* out, int 
 }
 
 void reserve_step(F5Model& m, bool fast) {
-  const size_t R = (size_t)2 * m.N;
+  const size_t R = (size_t)2 * m.U * m.N;
   if (fast) {
     m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.att16.reserve(R * m.D);
-    m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
+    m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
   } else {
     m.c32.reserve(R * m.D); m.n32.reserve(R * m.D); m.att32.reserve(R * m.D); m.qkv32.reserve(R * 3 * m.D);
@@ -535,7 +545,8 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   B2_CHECK(first >= 0 && count >= 0 && first + count <= m.nfe - 1, "f5_steps: time_step out of range");
   B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "f5_steps: unknown precision");
   const bool fast = precision == PREC_BF16;
-  const int N = m.N, D = m.D, R = 2 * N;
+  const int N = m.N, D = m.D, S = 2 * m.U, R = S * N;
+  B2_CHECK(fast || m.U == 1, "the fp32 parity engine runs one utterance at a time");
   reserve_step(m, fast);
   if (!fast) {   // padding rows / columns (t in [N, Npad)) of the fp32 attention operands must read as zero
     B2_CUDA(cudaMemsetAsync(m.kT32.p, 0, (size_t)2 * m.H * m.hd * m.Npad * sizeof(float), s));
@@ -547,9 +558,9 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   }
   for (int step = first; step < first + count; ++step) {
     // ---- input embedding: h[b] = Wx x + (Wc c_b + bias) ; x = conv_pos(h) + h ----
-    for (int b = 0; b < 2; ++b) {
-      Epi ep; ep.res = m.cproj.p + (size_t)b * N * D;
-      linear(e, "f5.embed_x", m.wx, false, m.noise.p, m.n_mels, N, m.h.p + (size_t)b * N * D, D, ep);
+    for (int sq = 0; sq < S; ++sq) {             // sequence sq = (utterance sq/2, CFG row sq%2): both rows share x
+      Epi ep; ep.res = m.cproj.p + (size_t)sq * N * D;
+      linear(e, "f5.embed_x", m.wx, false, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
     }
     if (fast) {
       { ProfScope ps(e.prof, "f5.cast", s); cast_f32_to_bf16(m.h.p, m.h16.p, (long)R * D, s); }
@@ -576,7 +587,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
         p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N;
         p.vt_out = m.vT16.p; p.vt_col0 = 2 * D; p.vt_ld = m.Npad; p.vt_heads = m.H;
         { ProfScope ps(e.prof, "f5.qkv_gemm", s); rowgemm_tc(p, L.qkv.tc, s); }
-        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, N, m.H, s); }
+        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s); }
       } else {
         Epi ep; ep.bias = L.qkv.bias.p;
         linear(e, "f5.qkv_gemm", L.qkv, false, m.n32.p, D, R, m.qkv32.p, 3 * D, ep);
@@ -611,7 +622,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     }
     {
       ProfScope ps(e.prof, "f5.euler", s);
-      euler_cfg_update(m.noise.p, m.pred.p, (long)N * m.n_mels, m.cfg_strength, m.delta_t[step], s);
+      euler_cfg_update(m.noise.p, m.pred.p, (long)N * m.n_mels, m.U, m.cfg_strength, m.delta_t[step], s);
     }
   }
 }

@@ -14,24 +14,25 @@ void f5_free(F5Model* m);
 // Graph A (Export_F5.py:117-141): audio int16 [L] (device), text_ids int32 [n_text] (device), N = max_duration.
 // Fills the state's cond / cond_drop [N][612], ref_signal_len, rope rows. `noise` is NOT drawn here: the caller
 // supplies it through f5_set_noise (the reference draws it with ORT's RandomNormalLike, irreproducible elsewhere).
-void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N);
+// u / U: slot of this utterance in a batch of U utterances that share N (length-bucketed batching; default: one utterance).
+void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u = 0, int U = 1);
 int f5_ref_len(const Engine& e);
 int f5_seq_len(const Engine& e);
 int f5_cond_dim(const Engine& e);   // n_mels + text_dim (612)
 int f5_n_mels(const Engine& e);
 int f5_nfe(const Engine& e);
 // device pointers of the current utterance's tensors (fp32): cond / cond_drop [N][612], noise [N][100]
-float* f5_cond(Engine& e);
-float* f5_cond_drop(Engine& e);
-float* f5_noise(Engine& e);
+float* f5_cond(Engine& e, int u = 0);
+float* f5_cond_drop(Engine& e, int u = 0);
+float* f5_noise(Engine& e, int u = 0);
 // Set up state for externally supplied graph-B inputs (the per-step session path): allocates for N rows.
-void f5_begin(Engine& e, int N);
+void f5_begin(Engine& e, int N, int U = 1);
 // rope rows [N][64] fp32 device (cos, sin) -- defaults to the model's fp16-rounded tables, may be overridden
 void f5_set_rope(Engine& e, const float* d_cos, const float* d_sin);
 // same, but returns the device buffers ([N][64] each) for the caller to fill (then selects them)
 void f5_rope_buffers(Engine& e, float** d_cos, float** d_sin);
 // host-side shape state of the current utterance (what f5_preprocess sets), for graph replays that skip the enqueue code
-void f5_restore_shape(Engine& e, int N, int ref_len);
+void f5_restore_shape(Engine& e, int N, int ref_len, int U = 1);
 // must be called after cond / cond_drop changed and before f5_steps: precomputes the step-invariant half of the
 // input embedding (W_c . cond + b for both CFG rows)
 void f5_prepare_cond(Engine& e);

@@ -30,8 +30,8 @@ void stft_magnitude(const float* spec, int ld, float* mag, int ldm, int F, int b
 void logmel_into(const float* mel, int F, float* dst, int ld_dst, int col0, int N, int C, cudaStream_t s);
 // dst[n][col0 + c] = src[n][c] (copy a column block), or zeros when src == nullptr
 void copy_cols(const float* src, int ld_src, float* dst, int ld_dst, int col0, int N, int C, cudaStream_t s);
-// Euler + CFG (Export_F5.py:179-181): noise += (p0 + (p0 - p1) * cfg) * dt ; pred [2][N*C]
-void euler_cfg_update(float* noise, const float* pred, long n, float cfg, float dt, cudaStream_t s);
+// Euler + CFG (Export_F5.py:179-181): noise += (p0 + (p0 - p1) * cfg) * dt ; pred [U][2][n], noise [U][n]
+void euler_cfg_update(float* noise, const float* pred, long n, int U, float cfg, float dt, cudaStream_t s);
 // head [G][ld] (log-mag cols [0,bins), phase cols [bins, 2 bins)) -> out [G][ld] = [min(exp(m),100)*cos p | ..*sin p | 0]
 void istft_input(const float* head, float* out, int G, int bins, int ld, cudaStream_t s);
 // frames [G][nfft] -> pcm [hop*(G-1)]: overlap-add, crop nfft/2 both sides, * window_sum_inv, clamp +-1, *32767, truncate
