@@ -74,6 +74,11 @@ __device__ __forceinline__ float2 fma2v(float2 a, float2 b, float2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
   return up2(d);
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(d);
+}
 __device__ __forceinline__ float2 mul2(float2 a, float s) {
   unsigned long long d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(make_float2(s, s))));
@@ -93,6 +98,9 @@ template <typename InT, typename OutT, bool PRECISE, bool POST, bool EDGE>
 __device__ __forceinline__ void aa_segment(const InT* __restrict__ xb, OutT* __restrict__ yb, int C, int L, int t0, int t1,
                                            int t_first, float2 av, float2 ibv) {
   auto ldx = [&](int t) { return ldraw(xb + (long)t * C, !EDGE || (t >= 0 && t < L)); };
+  // moving pointers for the main loop (one 64-bit bump per 6 steps; row k of the iteration is +k*C)
+  const InT* xp = xb + (long)(t0 + 13) * C;        // first row prefetched by the first main iteration
+  OutT* yp = yb + (long)(t0 - t_first) * C;
   auto snake = [&](float2 u) {                     // u + sin^2(a u) / (b + 1e-9), both channels
     const float2 arg = mul2v(u, av);
     float2 sn;
@@ -120,7 +128,8 @@ __device__ __forceinline__ void aa_segment(const InT* __restrict__ xb, OutT* __r
         oa = fma2(w[(j + 2 * K) % 12], c_aa_f[j], oa);                                                               \
         ob = fma2(w[(j + 1 + 2 * K) % 12], c_aa_f[j + 1], ob);                                                       \
       }                                                                                                              \
-      st2(yb + (long)((t) - t_first) * C, oa.x + ob.x, oa.y + ob.y);                                                 \
+      const float2 o = add2(oa, ob);                                                                                 \
+      st2(yp + (K) * (long)C, o.x, o.y);                                                                             \
     }                                                                                                                \
     float2 uo = mul2(xw[(0 + K) % 6], c_aa_f2[10]);                                                                  \
     float2 ue = mul2(xw[(0 + K) % 6], c_aa_f2[11]);                                                                  \
@@ -150,14 +159,16 @@ __device__ __forceinline__ void aa_segment(const InT* __restrict__ xb, OutT* __r
     for (int i = 0; i < 6; ++i) xn[i] = xf[i];
     if (!EDGE || t + 6 < t1) {                   // (interior: the rows read past t1 exist, the values are simply unused)
 #pragma unroll
-      for (int i = 0; i < 6; ++i) xf[i] = ldx(t + 13 + i);
+      for (int i = 0; i < 6; ++i) xf[i] = ldraw(xp + i * (long)C, !EDGE || (t + 13 + i >= 0 && t + 13 + i < L));
     }
+    xp += 6 * (long)C;
     AA_STEP(0, t + 0, true)
     AA_STEP(1, t + 1, (!EDGE || t + 1 < t1))
     AA_STEP(2, t + 2, (!EDGE || t + 2 < t1))
     AA_STEP(3, t + 3, (!EDGE || t + 3 < t1))
     AA_STEP(4, t + 4, (!EDGE || t + 4 < t1))
     AA_STEP(5, t + 5, (!EDGE || t + 5 < t1))
+    yp += 6 * (long)C;
   }
 #undef AA_STEP
 }

@@ -537,9 +537,13 @@ int b200tts_bench_rowgemm(b200tts_engine* e, int B, int M, int N, int Cin, int t
     RowGemm p;
     p.x = x16.p; p.x_bstride = (long)M * ldx; p.ldx = ldx; p.Lin = M;
     p.Cin = Cin; p.N = N; p.taps = taps; p.dil = dil; p.center = (taps - 1) / 2; p.groups = groups; p.M = M; p.B = B;
-    p.out = epilogue == 2 ? (void*)out16.p : (void*)outf.p; p.out_bf16 = epilogue == 2;
+    // epilogue: 0 bias, fp32 out | 1 + fp32 residual + gate | 2 bf16 out | 3 fp32 out + residual from a separate buffer |
+    //           4 bf16 out + fp32 residual
+    const bool o16 = epilogue == 2 || epilogue == 4;
+    p.out = o16 ? (void*)out16.p : (void*)outf.p; p.out_bf16 = o16;
     p.o_bstride = (long)M * groups * N; p.ldo = groups * N; p.bias = bias.p;
     if (epilogue == 1) { p.res = outf.p; p.gate = bias.p; }
+    if (epilogue == 3 || epilogue == 4) p.res = resf.p;
     for (int i = 0; i < 3; ++i) rowgemm_tc(p, tw, s);
     cudaEvent_t a, b;
     B2_CUDA(cudaEventCreate(&a)); B2_CUDA(cudaEventCreate(&b));

@@ -131,10 +131,15 @@ __device__ __forceinline__ void epi_load_res(const TcArgs& a, const EpiPos& p, i
 }
 
 template <int KIND, int ACT>
-__device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, uint32_t taddr, float* stg, int lane, int g,
-                                              int cb_first, int cb_step, float4 (&res)[8]) {
+__device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_t taddr, uint32_t taddr_hstep, int n_mine, float* stg,
+                                              int lane, int g, int cb_first, int cb_step, float4 (&res)[8]) {
+  // n_mine 128-row halves belong to this warp (rows +256 and TMEM columns +taddr_hstep apart); their 32-column blocks form
+  // ONE sequence for the residual look-ahead, so the first block of the second half is prefetched like any other.
   const int sub = p.sub, c4 = p.c4, n0 = p.n0;
   const bool has_res = KIND == EPI_STD && a.res != nullptr;
+#pragma unroll 1
+  for (int hh = 0; hh < n_mine; ++hh, p.t_row0 += 256, taddr += taddr_hstep) {
+  if (p.t_row0 >= a.M) break;                                // warp-uniform: no valid rows in this 32-row block
 #pragma unroll 1
   for (int cb = cb_first; cb < a.BN; cb += cb_step) {
     if (n0 + cb >= a.N) break;
@@ -181,6 +186,16 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, 
     for (int k = 0; k < 8; ++k)
       *reinterpret_cast<uint4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
     __syncwarp();
+
+    // the next block's residual: issued here, once r[] is dead, so it has the whole of phase 2 plus the next block's TMEM
+    // load and transpose to arrive (issued after phase 2 it was exposed: the thin BigVGAN conv2 ran at half speed)
+    float4 res_n[8];
+    if (has_res) {
+      const bool last_cb = cb + cb_step >= a.BN || n0 + cb + cb_step >= a.N;
+      EpiPos pn = p;
+      if (last_cb) pn.t_row0 += 256;                         // (rows beyond M / a half that is not ours load zeros)
+      epi_load_res(a, pn, (last_cb && hh + 1 < n_mine) ? cb_first : cb + cb_step, res_n);
+    }
 
     // phase 2
     const int n = n0 + cb + c4 * 4;
@@ -232,8 +247,12 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, const EpiPos& p, 
           *reinterpret_cast<uint2*>(a.out2 + p.obase + flat) = pack_bf16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
       }
     }
-    if (has_res) epi_load_res(a, p, cb + cb_step, res);      // flies during the next block's TMEM load + transpose
+    if (has_res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = res_n[i];
+    }
     __syncwarp();                                // the staging block is rewritten by the next iteration's phase 1
+  }
   }
 }
 
@@ -310,6 +329,26 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
         const int nt = rem / sc.m_tiles, mt = rem - nt * sc.m_tiles;
         const int b = bg / a.groups, g = bg - b * a.groups;
         const int t0 = mt * sc.bm, n0 = nt * a.BN;
+        if (KIND == EPI_STD && a.o_shift == 0 && (a.res != nullptr || (a.accumulate && !a.out_bf16))) {
+          // The epilogue reads this tile's residual (and, when accumulating, the old output) one 32x32 block ahead of its
+          // use, which covers an L2 hit but not a DRAM miss (conv2 of the thin BigVGAN stages ran at 2 TB/s, ncu r01l).
+          // The producer runs a tile or two ahead of the epilogue: it pulls those tiles into L2 here, for free.
+          int rows = a.M - t0; if (rows > sc.bm) rows = sc.bm;
+          int cols = a.N - n0; if (cols > a.BN) cols = a.BN;
+          const long toff = (long)b * a.o_bstride + (long)t0 * a.ldo + (long)g * a.N + n0;
+          for (int which = 0; which < 2; ++which) {
+            const float* rp = which == 0 ? a.res : (a.accumulate && !a.out_bf16 ? reinterpret_cast<const float*>(a.out) : nullptr);
+            if (rp == nullptr) continue;
+            rp += toff;
+            if (cols == a.ldo) {                                // one N tile spans the row: the tile is contiguous
+              const long bytes = (long)rows * a.ldo * 4;
+              for (long off = 0; off < bytes; off += 65536)
+                prefetch_l2_bulk(reinterpret_cast<const char*>(rp) + off, (uint32_t)(bytes - off < 65536 ? bytes - off : 65536));
+            } else if (sc.num_tiles > (int)gridDim.x) {          // (a one-tile CTA has no lead time to gain)
+              for (int r = 0; r < rows; ++r) prefetch_l2_bulk(rp + (long)r * a.ldo, (uint32_t)cols * 4u);
+            }
+          }
+        }
         for (int c = 0; c < a.kchunks; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], (uint32_t)a_stage_bytes);
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
     const int q = warp & 3, e = warp >> 2;
     float* stg = smem_epi + warp * (EPI_STAGE_BYTES / 4);
     const int cb_first = halves == 1 ? e * 32 : 0, cb_step = halves == 1 ? 64 : 32;
-    const int h_first = halves == 1 ? 0 : e, h_step = 2;
+    const int h_first = halves == 1 ? 0 : e;
     const bool has_res = KIND == EPI_STD && a.res != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < sc.num_tiles; tile += gridDim.x, ++it) {
@@ -407,12 +446,9 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
       const uint32_t accphase = sc.nacc == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
       mbar_wait(&acc_full[acc], accphase);
       tc_fence_after();
-      for (int h = h_first; h < halves; h += h_step) {
-        p.t_row0 = mt * sc.bm + h * 128 + q * 32;
-        if (p.t_row0 >= a.M) break;                         // warp-uniform: no valid rows in this 32-row block
-        if (has_res && h != h_first) epi_load_res(a, p, cb_first, res);
-        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_stride + (uint32_t)(h * sc.half_stride) + ((uint32_t)(q * 32) << 16);
-        epilogue_warp<KIND, ACT>(a, p, taddr, stg, lane, g, cb_first, cb_step, res);
+      {
+        const uint32_t taddr = tmem_base + (uint32_t)acc * acc_stride + (uint32_t)(h_first * sc.half_stride) + ((uint32_t)(q * 32) << 16);
+        epilogue_warp<KIND, ACT>(a, p, taddr, 2u * (uint32_t)sc.half_stride, halves == 4 ? 2 : 1, stg, lane, g, cb_first, cb_step, res);
       }
       tc_fence_before();
       __syncwarp();

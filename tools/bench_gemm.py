@@ -26,6 +26,19 @@ SHAPES = [
     ("vgan.s4 k7", 8, 65536, 48, 48, 7, 1, 1, 2),
     ("vgan.s5 k7", 8, 131072, 24, 24, 7, 1, 1, 2),
     ("vgan.s5 k11", 8, 131072, 24, 24, 11, 1, 1, 2),
+    # conv2 of a resblock unit: fp32 residual in, fp32 out (epilogue 1)
+    ("res.s1 k7", 8, 8192, 384, 384, 7, 1, 1, 1),
+    ("res.s2 k7", 8, 16384, 192, 192, 7, 1, 1, 1),
+    ("res.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 1),
+    ("res.s4 k7", 8, 65536, 48, 48, 7, 1, 1, 1),
+    ("res.s5 k7", 8, 131072, 24, 24, 7, 1, 1, 1),
+    # epilogue dissection on one thin and one wide stage: 0 fp32 out | 3 fp32 out + residual | 4 bf16 out + residual
+    ("epi0.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 0),
+    ("epi3.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 3),
+    ("epi4.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 4),
+    ("epi0.s1 k7", 8, 8192, 384, 384, 7, 1, 1, 0),
+    ("epi3.s1 k7", 8, 8192, 384, 384, 7, 1, 1, 3),
+    ("epi4.s1 k7", 8, 8192, 384, 384, 7, 1, 1, 4),
 ]
 only = sys.argv[1:] 
 for name, B, M, N, Cin, taps, dil, groups, epi in SHAPES:
