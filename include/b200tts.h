@@ -55,6 +55,19 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
 int b200tts_bigvgan_run_device(b200tts_engine* e, const float* mel_dev, int B, int T, int precision,
                                int16_t* pcm_dev, float* wave_dev);
 
+/* ---- IndexTTS_F session: the vocoder half of IndexTTS (IndexTTS/Export_IndexTTS.py:292-314, run at
+ * IndexTTS/Inference_IndexTTS_ONNX.py:787) -- generality check of the BigVGAN kernels on a second model (config 5).
+ * Tensors "ivgan.<IndexTTS bigvgan state_dict name>" (weight norm removed), "ivgan.final_norm.weight/bias" (gpt.final_norm),
+ * "ivgan.aa_filter" (12 taps) and "ivgan.upsample_rates" (one float per stage; the state dict does not carry the strides)
+ * must be loaded before the build.
+ * save_hidden_state (S, gpt_dim) fp32 -- the last two rows are dropped as the graph does -- plus the six per-stage
+ * conditioning vectors save_bigvgan_conds_i (C_i floats) and bigvgan_cond_layer_speaker_embedding (C0 floats)
+ * -> generated_wav int16 (1, 1, hop*(S-2)+30); *n_out = sample count; wave_host optional as in b200tts_bigvgan_run. */
+int b200tts_indextts_vocoder_build(b200tts_engine* e);
+int b200tts_indextts_vocoder_run(b200tts_engine* e, const float* hidden_host, int S, const float* const* conds_host,
+                                 const float* cond_layer_host, int precision, int16_t* pcm_host, float* wave_host,
+                                 int64_t* n_out);
+
 /* ---- F5-TTS sessions (F5_TTS/Export_F5.py:98-203, host loop F5-TTS-ONNX-Inference.py:247-311) ----------------
  * Tensors "dit.*" (EMA DiT state dict, Q/K pre-scaled), "vocos.*" (folded) and "f5.*" (export-time constants:
  * time_expand, delta_t, rope_cos/sin, text_pos, stft_basis, fbank, istft_basis, window_sum_inv) must be loaded. */

@@ -115,6 +115,77 @@ def build_bigvgan(sd: dict, cfg):
 
 
 # ----------------------------------------------------------------------------------------------
+# IndexTTS_F: the vocoder half of IndexTTS
+# ----------------------------------------------------------------------------------------------
+def load_indextts_bigvgan_module():
+    d = os.path.join(REF, "IndexTTS", "modeling_modified")
+
+    class _ECAPA(torch.nn.Module):            # conditioning branch: not part of graph F (its outputs are graph inputs)
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    _stub("indextts")
+    _stub("indextts.BigVGAN")
+    _stub("indextts.BigVGAN.activations", SnakeBeta=_SnakeBeta, Snake=_SnakeBeta)
+    _stub("indextts.BigVGAN.ECAPA_TDNN", ECAPA_TDNN=_ECAPA)
+    _stub("indextts.BigVGAN.utils", init_weights=lambda m, mean=0.0, std=0.01: None,
+          get_padding=lambda k, dil=1: int((k * dil - dil) / 2))
+    pkg = _stub("indextts.BigVGAN.alias_free_torch")
+    pkg.__path__ = [d]                        # so that act.py / resample.py resolve their relative imports
+    _load("indextts.BigVGAN.alias_free_torch.filter", os.path.join(d, "filter.py"))
+    _load("indextts.BigVGAN.alias_free_torch.resample", os.path.join(d, "resample.py"))
+    act = _load("indextts.BigVGAN.alias_free_torch.act", os.path.join(d, "act.py"))
+    pkg.Activation1d = act.Activation1d
+    return _load("ref_indextts_models", os.path.join(d, "models.py"))
+
+
+def build_indextts_f(sd: dict, cfg):
+    """The reference IndexTTS BigVGAN (IndexTTS/modeling_modified/models.py) filled from a synthetic state dict, plus
+    gpt.final_norm, wrapped as IndexTTS/Export_IndexTTS.py:292-314 does (the script itself is not importable: it loads
+    checkpoints at import time)."""
+    mod = load_indextts_bigvgan_module()
+    h = _AttrDict(
+        num_mels=100, gpt_dim=cfg.gpt_dim, upsample_rates=list(cfg.upsample_rates),
+        upsample_kernel_sizes=list(cfg.upsample_kernel_sizes), upsample_initial_channel=cfg.upsample_initial_channel,
+        resblock="1", resblock_kernel_sizes=list(cfg.resblock_kernel_sizes),
+        resblock_dilation_sizes=[list(d) for d in cfg.resblock_dilation_sizes], activation="snakebeta", snake_logscale=True,
+        feat_upsample=False, cond_d_vector_in_each_upsampling_layer=True, speaker_embedding_dim=512)
+    model = mod.BigVGAN(h, use_cuda_kernel=False)
+    model.remove_weight_norm()
+    gen = {k: torch.from_numpy(v) for k, v in sd.items() if not k.startswith("final_norm.")}
+    missing, unexpected = model.load_state_dict(gen, strict=False)
+    bad = [m for m in missing if not m.endswith("filter") and not m.startswith(("cond_layer.", "conds.", "speaker_encoder."))]
+    assert not bad and not unexpected, (bad, unexpected)
+    model = model.eval().float()
+    final_norm = torch.nn.LayerNorm(cfg.gpt_dim, eps=cfg.ln_eps)
+    final_norm.load_state_dict({"weight": torch.from_numpy(sd["final_norm.weight"]), "bias": torch.from_numpy(sd["final_norm.bias"])})
+
+    class IndexTTS_F(torch.nn.Module):        # restated from Export_IndexTTS.py:292-314
+        def __init__(self):
+            super().__init__()
+            self.bigvgan, self.final_norm = model, final_norm.eval()
+            self.inv_num_kernels = float(1.0 / model.num_kernels)
+
+        def forward(self, *all_inputs):
+            latent = self.final_norm(all_inputs[-1][:-2].unsqueeze(0))
+            latent = self.bigvgan.conv_pre(latent.transpose(1, 2)) + all_inputs[-2]
+            for i in range(self.bigvgan.num_upsamples):
+                for i_up in range(len(self.bigvgan.ups[i])):
+                    latent = self.bigvgan.ups[i][i_up](latent)
+                if self.bigvgan.cond_in_each_up_layer:
+                    latent = latent + all_inputs[i]
+                x = self.bigvgan.resblocks[i * self.bigvgan.num_kernels](latent, i)
+                for j in range(1, self.bigvgan.num_kernels):
+                    x = x + self.bigvgan.resblocks[i * self.bigvgan.num_kernels + j](latent, i)
+                latent = x * self.inv_num_kernels
+            latent = self.bigvgan.conv_post(self.bigvgan.activation_post(latent, -1))
+            generated_wav = torch.tanh(latent)
+            return (generated_wav.clamp(min=-1.0, max=1.0) * 32767.0).to(torch.int16)
+
+    return IndexTTS_F()
+
+
+# ----------------------------------------------------------------------------------------------
 # F5-TTS: DiT, STFT_Process, Vocos and the three export wrappers
 # ----------------------------------------------------------------------------------------------
 def load_f5_modules():

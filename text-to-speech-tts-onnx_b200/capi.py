@@ -39,6 +39,8 @@ SIGNATURES = {
     "b200tts_bigvgan_build": (_int, [_vp]),
     "b200tts_bigvgan_run": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
     "b200tts_bigvgan_run_device": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
+    "b200tts_indextts_vocoder_build": (_int, [_vp]),
+    "b200tts_indextts_vocoder_run": (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "b200tts_f5_build": (_int, [_vp]),
     "b200tts_f5_preprocess": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _vp, _c_i64]),
     "b200tts_f5_transformer": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _c_i32, _int, _int]),
@@ -160,6 +162,28 @@ class Engine:
     def bigvgan_run_device(self, mel_ptr: int, B: int, T: int, pcm_ptr: int, precision=BF16, wave_ptr: int = 0):
         self._check(self.lib.b200tts_bigvgan_run_device(self.handle, _vp(mel_ptr), B, T, int(precision), _vp(pcm_ptr),
                                                         _vp(wave_ptr or 0)), "bigvgan_run_device")
+
+    # -- IndexTTS_F vocoder ----------------------------------------------------------------------
+    def indextts_vocoder_build(self):
+        self._check(self.lib.b200tts_indextts_vocoder_build(self.handle), "indextts_vocoder_build")
+
+    def indextts_vocoder_run(self, hidden, conds, cond_layer, precision=F32, return_wave=False, hop=1024):
+        """save_hidden_state (S, gpt_dim), [save_bigvgan_conds_i], bigvgan_cond_layer_speaker_embedding ->
+        generated_wav int16 (1, 1, hop*(S-2)+30)."""
+        hidden = _f32(hidden)
+        assert hidden.ndim == 2 and hidden.shape[0] >= 3, "save_hidden_state must be (S >= 3, gpt_dim)"
+        S = hidden.shape[0]
+        cs = [_f32(np.asarray(c).reshape(-1)) for c in conds]
+        cl = _f32(np.asarray(cond_layer).reshape(-1))
+        ptrs = (ctypes.c_void_p * len(cs))(*[c.ctypes.data for c in cs])
+        n_out = hop * (S - 2) + 30
+        pcm = np.empty((1, 1, n_out), dtype=np.int16)
+        wave = np.empty((1, 1, n_out), dtype=np.float32) if return_wave else None
+        got = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_indextts_vocoder_run(self.handle, _ptr(hidden), S, ptrs, _ptr(cl), int(precision), _ptr(pcm),
+                                                          _ptr(wave), ctypes.byref(got)), "indextts_vocoder_run")
+        assert got.value == n_out, (got.value, n_out)
+        return (pcm, wave) if return_wave else pcm
 
     # -- F5-TTS ----------------------------------------------------------------------------------
     def f5_build(self):

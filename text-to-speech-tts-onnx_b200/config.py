@@ -61,5 +61,22 @@ class F5Config:
     vocos_layers: int = 8
 
 
+@dataclass(frozen=True)
+class IndexTTSVocoderConfig(BigVGANConfig):
+    """The BigVGAN inside IndexTTS_F (reference: IndexTTS/Export_IndexTTS.py:292-314, IndexTTS/modeling_modified/models.py:
+    130-250). Stage channels 768..24 are pinned in-repo (IndexTTS/modeling_modified/filter.py:85); gpt_dim, rates and kernel
+    sizes come from the un-vendored index-tts config.yaml (rates [4,4,4,4,2,2] -> x1024; kernel sizes [8,8,4,4,4,4], i.e.
+    kernel = 2*stride for the first two upsamplers and kernel = stride afterwards -- the engine accepts either per stage)."""
+    num_mels: int = 1280         # conv_pre input width = gpt_dim (the GPT latent), not a mel count
+    upsample_rates: tuple = (4, 4, 4, 4, 2, 2)
+    upsample_kernel_sizes: tuple = (8, 8, 4, 4, 4, 4)
+    ln_eps: float = 1e-5         # gpt.final_norm = nn.LayerNorm(gpt_dim)
+
+    @property
+    def gpt_dim(self) -> int:
+        return self.num_mels
+
+
 BIGVGAN = BigVGANConfig()
 F5 = F5Config()
+INDEXTTS_VOCODER = IndexTTSVocoderConfig()

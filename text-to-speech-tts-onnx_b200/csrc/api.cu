@@ -26,6 +26,7 @@ struct b200tts_engine {
 namespace b200tts {
 Engine::~Engine() {
   if (bigvgan) bigvgan_free(bigvgan);
+  if (ivgan) bigvgan_free(ivgan);
   if (f5) f5_free(f5);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -134,7 +135,7 @@ int b200tts_bigvgan_build(b200tts_engine* e) {
   return guarded([&] {
     Engine& E = eng(e);
     if (E.bigvgan) { bigvgan_free(E.bigvgan); E.bigvgan = nullptr; }
-    E.bigvgan = bigvgan_build(E);
+    E.bigvgan = bigvgan_build(E, "bigvgan.");
   });
 }
 
@@ -143,8 +144,9 @@ int b200tts_bigvgan_run_device(b200tts_engine* e, const float* mel_dev, int B, i
   return guarded([&] {
     Engine& E = eng(e);
     B2_CHECK(mel_dev && pcm_dev, "bigvgan_run_device: null buffer");
+    B2_CHECK(E.bigvgan != nullptr, "BigVGAN weights are not built (call b200tts_bigvgan_build)");
     run_graphed(E, {10, (long long)(uintptr_t)mel_dev, B, T, precision, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)wave_dev},
-                [&] { bigvgan_forward(E, mel_dev, B, T, precision, pcm_dev, wave_dev); }, [] {});
+                [&] { bigvgan_forward(E, *E.bigvgan, mel_dev, B, T, precision, pcm_dev, wave_dev); }, [] {});
   });
 }
 
@@ -155,8 +157,8 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
     B2_CHECK(mel_host && pcm_host, "bigvgan_run: null buffer");
     B2_CHECK(E.bigvgan != nullptr, "BigVGAN weights are not built (call b200tts_bigvgan_build)");
     B2_CHECK(B > 0 && T > 0, "bigvgan_run: empty input");
-    const long n_mel = (long)B * T * bigvgan_num_mels(E);
-    const long n_out = (long)B * bigvgan_out_samples(E, T);
+    const long n_mel = (long)B * T * bigvgan_num_mels(*E.bigvgan);
+    const long n_out = (long)B * bigvgan_out_samples(*E.bigvgan, T);
     // persistent staging buffers: stable addresses let repeated calls of one shape replay a captured graph
     E.io_f32a.reserve((size_t)n_mel);
     E.io_i16.reserve((size_t)n_out);
@@ -164,10 +166,58 @@ int b200tts_bigvgan_run(b200tts_engine* e, const float* mel_host, int B, int T, 
     float* d_mel = E.io_f32a.p; int16_t* d_pcm = E.io_i16.p; float* d_wave = wave_host ? E.io_f32b.p : nullptr;
     B2_CUDA(cudaMemcpyAsync(d_mel, mel_host, n_mel * sizeof(float), cudaMemcpyHostToDevice, E.stream));
     run_graphed(E, {11, (long long)(uintptr_t)d_mel, B, T, precision, (long long)(uintptr_t)d_pcm, (long long)(uintptr_t)d_wave},
-                [&] { bigvgan_forward(E, d_mel, B, T, precision, d_pcm, d_wave); }, [] {});
+                [&] { bigvgan_forward(E, *E.bigvgan, d_mel, B, T, precision, d_pcm, d_wave); }, [] {});
     B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm, n_out * sizeof(int16_t), cudaMemcpyDeviceToHost, E.stream));
     if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave, n_out * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     B2_CUDA(cudaStreamSynchronize(E.stream));
+  });
+}
+
+int b200tts_indextts_vocoder_build(b200tts_engine* e) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    if (E.ivgan) { bigvgan_free(E.ivgan); E.ivgan = nullptr; }
+    B2_CHECK(E.has_weight("ivgan.final_norm.weight"), "ivgan.final_norm.weight (gpt.final_norm) is not loaded");
+    E.ivgan = bigvgan_build(E, "ivgan.");
+  });
+}
+
+int b200tts_indextts_vocoder_run(b200tts_engine* e, const float* hidden_host, int S, const float* const* conds_host,
+                                 const float* cond_layer_host, int precision, int16_t* pcm_host, float* wave_host, int64_t* n_out) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.ivgan != nullptr, "IndexTTS vocoder weights are not built (call b200tts_indextts_vocoder_build)");
+    B2_CHECK(hidden_host && conds_host && cond_layer_host && pcm_host && n_out, "indextts_vocoder_run: null buffer");
+    B2_CHECK(S >= 3, "indextts_vocoder_run: the latent needs at least 3 rows (the last two are dropped)");
+    BigVGANModel& M = *E.ivgan;
+    cudaStream_t s = E.stream;
+    const int T = S - 2, D = bigvgan_num_mels(M), ns = bigvgan_num_stages(M);
+    const long n_samples = bigvgan_out_samples(M, T);
+    // staging: [latent T*D | cond_0 .. cond_{n-1} | cond_layer] in one fp32 block, PCM in the int16 block
+    size_t ncond = (size_t)bigvgan_stage_channels(M, -1);
+    for (int i = 0; i < ns; ++i) ncond += (size_t)bigvgan_stage_channels(M, i);
+    E.io_f32a.reserve((size_t)T * D + ncond);
+    E.io_i16.reserve((size_t)n_samples);
+    if (wave_host) E.io_f32b.reserve((size_t)n_samples);
+    float* d_lat = E.io_f32a.p;
+    std::vector<const float*> d_conds(ns + 1);
+    float* cp = d_lat + (size_t)T * D;
+    B2_CUDA(cudaMemcpyAsync(d_lat, hidden_host, (size_t)T * D * sizeof(float), cudaMemcpyHostToDevice, s));     // hidden[:-2]
+    for (int i = 0; i <= ns; ++i) {
+      const int C = bigvgan_stage_channels(M, i < ns ? i : -1);
+      const float* src = i < ns ? conds_host[i] : cond_layer_host;
+      B2_CHECK(src != nullptr, "indextts_vocoder_run: null conditioning vector");
+      B2_CUDA(cudaMemcpyAsync(cp, src, (size_t)C * sizeof(float), cudaMemcpyHostToDevice, s));
+      d_conds[i] = cp;
+      cp += C;
+    }
+    int16_t* d_pcm = E.io_i16.p; float* d_wave = wave_host ? E.io_f32b.p : nullptr;
+    run_graphed(E, {12, (long long)(uintptr_t)d_lat, T, precision, (long long)(uintptr_t)d_pcm, (long long)(uintptr_t)d_wave},
+                [&] { bigvgan_forward(E, M, d_lat, 1, T, precision, d_pcm, d_wave, d_conds.data()); }, [] {});
+    B2_CUDA(cudaMemcpyAsync(pcm_host, d_pcm, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave, n_samples * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *n_out = n_samples;
   });
 }
 

@@ -12,6 +12,7 @@
 #include "bigvgan.cuh"
 
 #include "aa_act.cuh"
+#include "f5_kernels.cuh"
 #include "layout.cuh"
 #include "rowgemm.cuh"
 #include "rowgemm_tc.cuh"
@@ -31,18 +32,26 @@ __global__ void prep_conv_w_kernel(const float* __restrict__ W, float* __restric
   }
 }
 
-// ConvTranspose1d W (Cin, Cout, 2u) -> out[tap][c][r*Cout + n] = W[c][n][tap == 0 ? r + u : r]
-__global__ void prep_convtr_w_kernel(const float* __restrict__ W, float* __restrict__ out, int Cin, int Cout, int u) {
+// ConvTranspose1d W (Cin, Cout, k), k = taps*u:
+//   taps = 2 (k = 2u, padding u/2): out[tap][c][r*Cout + n] = W[c][n][tap == 0 ? r + u : r]
+//   taps = 1 (k = u,  padding 0)  : out[0][c][r*Cout + n]   = W[c][n][r]          (no overlap between input samples)
+__global__ void prep_convtr_w_kernel(const float* __restrict__ W, float* __restrict__ out, int Cin, int Cout, int u, int taps) {
   const long N = (long)u * Cout;
-  const long total = 2 * (long)Cin * N;
+  const long total = (long)taps * Cin * N;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int col = (int)(i % N);
     const int c = (int)((i / N) % Cin);
     const int tap = (int)(i / (N * Cin));
     const int r = col / Cout, n = col % Cout;
-    const int j = tap == 0 ? r + u : r;
-    out[i] = W[((long)c * Cout + n) * (2 * u) + j];
+    const int j = (taps == 2 && tap == 0) ? r + u : r;
+    out[i] = W[((long)c * Cout + n) * (taps * u) + j];
   }
+}
+
+// bias_out[r*C + n] = bias[n] + cond[n]  (r < reps): the per-call conditioning vector folded into a GEMM bias
+__global__ void cond_bias_kernel(const float* __restrict__ bias, const float* __restrict__ cond, float* __restrict__ out, int C, int reps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * reps) out[i] = bias[i % C] + (cond ? cond[i % C] : 0.f);
 }
 
 __global__ void replicate_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout, int u) {
@@ -62,7 +71,7 @@ __global__ void snake_params_kernel(const float* __restrict__ alpha_log, const f
 // conv_post (k=7, pad 3, C -> 1, no bias) + tanh + x32767 + clamp + truncating int16 cast.
 // x: (B, L, C) channels-last, so the 7xC window of one output sample is contiguous in memory.
 template <int C>
-__global__ void __launch_bounds__(256) post_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) post_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
                                                         int L, int16_t* __restrict__ pcm, float* __restrict__ wave) {
   __shared__ float ws[7 * C];
   for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) ws[i] = w[i];
@@ -71,7 +80,7 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const float* __restrict_
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= L) return;
   const float* xb = x + (long)b * L * C;
-  float acc = 0.f;
+  float acc = bias;
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
     const int tt = t + j - 3;
@@ -105,7 +114,8 @@ struct Snake {
 
 struct Stage {
   int u = 0, Cin = 0, C = 0;
-  ConvW up;                         // as 2-tap rowgemm with N = u*C
+  ConvW up;                         // as a 2-tap (k = 2u) or 1-tap (k = u) rowgemm with N = u*C
+  DevBuf<float> up_bias_c;          // u*C: bias + per-call conditioning vector (IndexTTS)
   ConvW c1[3][3], c2[3][3];         // [resblock][m]
   Snake act[3][6];
   int k[3] = {0, 0, 0};
@@ -116,6 +126,12 @@ struct Stage {
 
 struct BigVGANModel {
   int n_mels = 0, C0 = 0, nstages = 0, hop = 1;
+  std::string prefix;               // "bigvgan." (mel -> PCM session) or "ivgan." (IndexTTS_F: GPT latent -> PCM)
+  // IndexTTS_F extras (IndexTTS/Export_IndexTTS.py:300-314): final LayerNorm of the GPT latent, conditioning adds, conv_post bias
+  DevBuf<float> fn_w, fn_b;         // gpt.final_norm (empty for the mel vocoder)
+  DevBuf<float> pre_bias_c;         // conv_pre bias + cond_layer vector
+  DevBuf<float> latent;             // normalised latent (S-2, gpt_dim)
+  float post_bias = 0.f;
   ConvW pre;
   std::vector<Stage> stages;
   Snake post_act;
@@ -155,12 +171,12 @@ void prep_snake(Engine& e, const std::string& prefix, int C, Snake& s) {
 
 }  // namespace
 
-BigVGANModel* bigvgan_build(Engine& e) {
+BigVGANModel* bigvgan_build(Engine& e, const std::string& P) {
   std::unique_ptr<BigVGANModel> m(new BigVGANModel());
-  const std::string P = "bigvgan.";
+  m->prefix = P;
   {
     const Tensor& f = e.weight(P + "aa_filter");
-    B2_CHECK(f.numel() == 12, "bigvgan.aa_filter must hold 12 taps");
+    B2_CHECK(f.numel() == 12, P + "aa_filter must hold 12 taps");
     float taps[12];
     B2_CUDA(cudaMemcpy(taps, f.data.p, sizeof(taps), cudaMemcpyDeviceToHost));
     aa_set_filter(taps);
@@ -180,14 +196,25 @@ BigVGANModel* bigvgan_build(Engine& e) {
     B2_CHECK(W.shape.size() == 3 && W.shape[0] == C, "ups weight shape");
     st.Cin = C; st.C = (int)W.shape[1];
     const int k = (int)W.shape[2];
-    B2_CHECK(k % 2 == 0, "ConvTranspose1d kernel must be 2*stride");
-    st.u = k / 2;                       // upsample_kernel_sizes = 2 * upsample_rates, padding (k-u)/2 = u/2
-    B2_CHECK(st.u % 2 == 0, "upsample rate must be even");
+    // stride: k = 2u with padding u/2 (upsample_kernel_sizes = 2 * upsample_rates, the 24 kHz v2 config), or k = u with
+    // padding 0 (IndexTTS' later stages). The state dict does not carry the stride; "<prefix>upsample_rates" does when given.
+    int u = k / 2;
+    if (e.has_weight(P + "upsample_rates")) {
+      const Tensor& R = e.weight(P + "upsample_rates");
+      B2_CHECK(R.numel() >= ns, "upsample_rates shorter than the number of stages");
+      float ru = 0.f;
+      B2_CUDA(cudaMemcpy(&ru, R.data.p + i, sizeof(float), cudaMemcpyDeviceToHost));
+      u = (int)(ru + 0.5f);
+    }
+    B2_CHECK(u > 0 && (k == 2 * u || k == u), "ConvTranspose1d kernel must be the stride or twice the stride");
+    const int up_taps = k / u;
+    st.u = u;
+    B2_CHECK(up_taps == 1 || st.u % 2 == 0, "upsample rate must be even when kernel = 2*stride");
     m->hop *= st.u;
     const long N = (long)st.u * st.C;
-    st.up.Cin = st.Cin; st.up.N = (int)N; st.up.taps = 2;
-    st.up.w.alloc(2 * (size_t)st.Cin * N);
-    prep_convtr_w_kernel<<<ceil_div(2L * st.Cin * N, 256), 256, 0, e.stream>>>(W.data.p, st.up.w.p, st.Cin, st.C, st.u);
+    st.up.Cin = st.Cin; st.up.N = (int)N; st.up.taps = up_taps;
+    st.up.w.alloc((size_t)up_taps * st.Cin * N);
+    prep_convtr_w_kernel<<<ceil_div((long)up_taps * st.Cin * N, 256), 256, 0, e.stream>>>(W.data.p, st.up.w.p, st.Cin, st.C, st.u, up_taps);
     B2_LAUNCH_CHECK();
     const Tensor& bt = e.weight(P + "ups." + std::to_string(i) + ".0.bias");
     st.up.bias.alloc(N);
@@ -209,28 +236,37 @@ BigVGANModel* bigvgan_build(Engine& e) {
   m->Clast = C;
   prep_snake(e, P + "activation_post.act", C, m->post_act);
   {
-    const Tensor& W = e.weight(P + "conv_post.weight");   // (1, C, 7), no bias in the v2 config
+    const Tensor& W = e.weight(P + "conv_post.weight");   // (1, C, 7); no bias in the 24 kHz v2 config, one in IndexTTS'
     B2_CHECK(W.shape.size() == 3 && W.shape[0] == 1 && W.shape[1] == C && W.shape[2] == 7, "conv_post shape");
-    B2_CHECK(!e.has_weight(P + "conv_post.bias"), "conv_post bias is not supported (use_bias_at_final=False)");
+    if (e.has_weight(P + "conv_post.bias")) {
+      const Tensor& pb = e.weight(P + "conv_post.bias");
+      B2_CHECK(pb.numel() == 1, "conv_post bias must be a scalar");
+      B2_CUDA(cudaMemcpy(&m->post_bias, pb.data.p, sizeof(float), cudaMemcpyDeviceToHost));
+    }
     m->post_w.alloc(7 * C);
     prep_conv_w_kernel<<<1, 256, 0, e.stream>>>(W.data.p, m->post_w.p, 1, C, 7);   // -> [j][c][0]
     B2_LAUNCH_CHECK();
   }
+  if (e.has_weight(P + "final_norm.weight")) {           // IndexTTS_F: gpt.final_norm on the latent rows
+    const Tensor& fw = e.weight(P + "final_norm.weight");
+    const Tensor& fb = e.weight(P + "final_norm.bias");
+    B2_CHECK(fw.numel() == m->n_mels && fb.numel() == m->n_mels, "final_norm size must equal the conv_pre input width");
+    m->fn_w.alloc(m->n_mels); m->fn_b.alloc(m->n_mels);
+    B2_CUDA(cudaMemcpyAsync(m->fn_w.p, fw.data.p, m->n_mels * sizeof(float), cudaMemcpyDeviceToDevice, e.stream));
+    B2_CUDA(cudaMemcpyAsync(m->fn_b.p, fb.data.p, m->n_mels * sizeof(float), cudaMemcpyDeviceToDevice, e.stream));
+  }
+  m->pre_bias_c.alloc(m->C0);
+  for (auto& st : m->stages) st.up_bias_c.alloc((size_t)st.u * st.C);
   B2_CUDA(cudaStreamSynchronize(e.stream));
   return m.release();
 }
 
 void bigvgan_free(BigVGANModel* m) { delete m; }
 
-int bigvgan_num_mels(const Engine& e) {
-  B2_CHECK(e.bigvgan != nullptr, "BigVGAN weights are not built");
-  return e.bigvgan->n_mels;
-}
-
-long bigvgan_out_samples(const Engine& e, int T) {
-  B2_CHECK(e.bigvgan != nullptr, "BigVGAN weights are not built");
-  return (long)e.bigvgan->hop * T + 30;
-}
+int bigvgan_num_mels(const BigVGANModel& m) { return m.n_mels; }
+int bigvgan_num_stages(const BigVGANModel& m) { return m.nstages; }
+int bigvgan_stage_channels(const BigVGANModel& m, int i) { return i < 0 ? m.C0 : m.stages[i].C; }
+long bigvgan_out_samples(const BigVGANModel& m, int T) { return (long)m.hop * T + 30; }
 
 namespace {
 
@@ -256,9 +292,7 @@ void prep_tc(Engine& e, ConvW& cw, DevBuf<float>& tmp) {
 
 }  // namespace
 
-void bigvgan_tc_prepare(Engine& e) {
-  B2_CHECK(e.bigvgan != nullptr, "BigVGAN weights are not built");
-  BigVGANModel& m = *e.bigvgan;
+void bigvgan_tc_prepare(Engine& e, BigVGANModel& m) {
   if (m.pre.tc.ready) return;
   DevBuf<float> tmp;
   for (auto& st : m.stages) {
@@ -281,14 +315,14 @@ struct Ctx {
 
 // y = conv(x) with the shifted-row GEMM; x, out are (B, L, C) fp32 (or bf16 for the tc path's A operand)
 void run_conv(Ctx& c, const char* tag, const ConvW& cw, const void* x, int L, int dil, void* out, int out_bf16,
-              const float* res, int accumulate, float scale, int ldx = 0) {
+              const float* res, int accumulate, float scale, int ldx = 0, const float* bias = nullptr) {
   RowGemm p;
   if (ldx == 0) ldx = cw.Cin;
   p.x = x; p.x_bstride = (long)L * ldx; p.ldx = ldx; p.Lin = L;
   p.Cin = cw.Cin; p.N = cw.N; p.taps = cw.taps; p.dil = dil; p.center = (cw.taps - 1) / 2;
   p.M = L; p.B = c.B;
   p.out = out; p.o_bstride = (long)L * cw.N; p.ldo = cw.N; p.out_bf16 = out_bf16;
-  p.bias = cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale;
+  p.bias = bias ? bias : cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale;
   ProfScope ps(c.e.prof, tag, c.e.stream);
   if (c.fast) {
     rowgemm_tc(p, cw.tc, c.e.stream);
@@ -298,15 +332,19 @@ void run_conv(Ctx& c, const char* tag, const ConvW& cw, const void* x, int L, in
   }
 }
 
-void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out) {
+void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out, const float* bias) {
   const long N = (long)st.u * st.C;
   RowGemm p;
   p.x = x; p.x_bstride = (long)Lin * st.Cin; p.ldx = st.Cin; p.Lin = Lin;
-  p.Cin = st.Cin; p.N = (int)N; p.taps = 2; p.dil = 1; p.center = 1;
-  p.M = Lin + 1; p.B = c.B;
+  p.Cin = st.Cin; p.N = (int)N; p.taps = st.up.taps; p.dil = 1; p.B = c.B;
   p.out = out; p.o_bstride = (long)Lin * N; p.ldo = (int)N;
-  p.o_shift = -(long)(st.u / 2) * st.C; p.o_limit = (long)Lin * N;
-  p.bias = st.up.bias.p;
+  if (st.up.taps == 2) {            // k = 2u: input row t feeds output rows t-1 (upper half of the kernel) and t
+    p.center = 1; p.M = Lin + 1;
+    p.o_shift = -(long)(st.u / 2) * st.C; p.o_limit = (long)Lin * N;
+  } else {                          // k = u: one input sample -> u output samples, no overlap
+    p.center = 0; p.M = Lin;
+  }
+  p.bias = bias;
   ProfScope ps(c.e.prof, "bigvgan.ups", c.e.stream);
   if (c.fast) {
     rowgemm_tc(p, st.up.tc, c.e.stream);
@@ -318,11 +356,13 @@ void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out) {
 
 }  // namespace
 
-void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision, int16_t* d_pcm, float* d_wave) {
-  B2_CHECK(e.bigvgan != nullptr, "BigVGAN weights are not built (call b200tts_bigvgan_build)");
+void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T, int precision, int16_t* d_pcm, float* d_wave,
+                     const float* const* d_conds) {
   B2_CHECK(B > 0 && T > 0, "bigvgan: empty input");
   B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "bigvgan: unknown precision");
-  BigVGANModel& m = *e.bigvgan;
+  const bool latent_in = m.fn_w.p != nullptr;           // IndexTTS_F: d_in = GPT latent rows (T, gpt_dim), already channels-last
+  B2_CHECK(!latent_in || B == 1, "the IndexTTS vocoder takes one latent sequence per call");
+  B2_CHECK(latent_in == (d_conds != nullptr), "conditioning vectors go with the IndexTTS vocoder only");
   Ctx c{e, m, B, precision == PREC_BF16};
   cudaStream_t s = e.stream;
 
@@ -338,14 +378,28 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
   m.xu.reserve(ws); m.xs.reserve(ws); m.xa.reserve(ws); m.xb.reserve(ws); m.abuf.reserve(ws);
   if (c.fast) {
     m.abuf16.reserve(ws); m.cbuf16.reserve(ws); m.mel16.reserve((size_t)B * T * round_up(m.n_mels, 8)); m.xs16.reserve(ws);
-    bigvgan_tc_prepare(e);     // bf16 weight layouts + tensor maps (first fast call only)
+    bigvgan_tc_prepare(e, m);  // bf16 weight layouts (first fast call only)
   } else {
     m.cbuf.reserve(ws);
   }
 
-  {
+  const float* pre_bias = m.pre.bias.p;
+  if (latent_in) {
+    // latent = gpt.final_norm(hidden[:-2]) (Export_IndexTTS.py:301): T rows of gpt_dim, channels-last as the GEMM wants it;
+    // conv_pre(.) + cond_layer vector, ups[i](.) + cond_i (:302,:306-307): the vectors are folded into the GEMM biases
+    ProfScope ps(e.prof, "bigvgan.cond", s);
+    layernorm_affine(d_in, m.fn_w.p, m.fn_b.p, m.mel_cl.p, T, m.n_mels, 1e-5f, s);
+    cond_bias_kernel<<<ceil_div(m.C0, 128), 128, 0, s>>>(m.pre.bias.p, d_conds[m.nstages], m.pre_bias_c.p, m.C0, 1);
+    B2_LAUNCH_CHECK(); count_launch();
+    for (int i = 0; i < m.nstages; ++i) {
+      Stage& st = m.stages[i];
+      cond_bias_kernel<<<ceil_div(st.u * st.C, 128), 128, 0, s>>>(st.up.bias.p, d_conds[i], st.up_bias_c.p, st.C, st.u);
+      B2_LAUNCH_CHECK(); count_launch();
+    }
+    pre_bias = m.pre_bias_c.p;
+  } else {
     ProfScope ps(e.prof, "bigvgan.mel_transpose", s);
-    batched_transpose(d_mel, m.mel_cl.p, B, m.n_mels, T, s);
+    batched_transpose(d_in, m.mel_cl.p, B, m.n_mels, T, s);
   }
   const bool precise = !c.fast;
   const void* conv_in = m.mel_cl.p;
@@ -357,7 +411,7 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
     conv_in = m.mel16.p;
   }
   // conv_pre -> xs (B, T, C0)
-  run_conv(c, "bigvgan.conv_pre", m.pre, conv_in, T, 1, m.xs.p, 0, nullptr, 0, 1.0f, mel_ld);
+  run_conv(c, "bigvgan.conv_pre", m.pre, conv_in, T, 1, m.xs.p, 0, nullptr, 0, 1.0f, mel_ld, pre_bias);
 
   int L = T;
   static const char* kConvTag[8] = {"bigvgan.resconv.s0", "bigvgan.resconv.s1", "bigvgan.resconv.s2", "bigvgan.resconv.s3",
@@ -374,7 +428,7 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
       cast_f32_to_bf16(m.xs.p, m.xs16.p, (long)B * L * st.Cin, s);
       up_in = m.xs16.p;
     }
-    run_up(c, st, up_in, L, m.xu.p);
+    run_up(c, st, up_in, L, m.xu.p, latent_in ? st.up_bias_c.p : st.up.bias.p);
     L *= st.u;
     for (int j = 0; j < 3; ++j) {
       const float* xcur = m.xu.p;
@@ -413,7 +467,7 @@ void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision,
     const int Lo = L + 30;
     dim3 grid(ceil_div(Lo, 256), B);
     B2_CHECK(m.Clast == 24, "post_conv kernel is instantiated for 24 channels");
-    post_conv_kernel<24><<<grid, 256, 0, s>>>(m.abuf.p, m.post_w.p, Lo, d_pcm, d_wave);
+    post_conv_kernel<24><<<grid, 256, 0, s>>>(m.abuf.p, m.post_w.p, m.post_bias, Lo, d_pcm, d_wave);
     B2_LAUNCH_CHECK(); count_launch();
   }
 }

@@ -1,24 +1,33 @@
 // BigVGAN-v2 generator (mel -> int16 PCM) on channels-last tensors. See bigvgan.cu.
 #pragma once
+#include <string>
+
 #include "engine.cuh"
 
 namespace b200tts {
 
 struct BigVGANModel;
 
-// Build device-side layouts from engine.weights["bigvgan.*"] (reference state_dict names).
-BigVGANModel* bigvgan_build(Engine& e);
+// Build device-side layouts from engine.weights["<prefix>*"] (reference state_dict names). prefix "bigvgan." = the
+// mel -> PCM session (BigVGAN/Export_BigVGAN.py); "ivgan." = the vocoder half of IndexTTS_F (IndexTTS/Export_IndexTTS.py:
+// 292-314, IndexTTS/modeling_modified/models.py:130-250): same generator with a LayerNorm'd GPT latent as input, a
+// conditioning vector added after conv_pre and after every upsampler, kernel = stride upsamplers and a conv_post bias.
+BigVGANModel* bigvgan_build(Engine& e, const std::string& prefix);
 
-// d_mel: (B, n_mels, T) fp32 device (reference layout, BigVGAN/Export_BigVGAN.py:65-70);
-// d_pcm: (B, 256*T+30) int16 device; d_wave (optional): same shape fp32, the pre-cast value
-// tanh(.)*32767 clamped (for tolerance analysis in tests).
-void bigvgan_forward(Engine& e, const float* d_mel, int B, int T, int precision, int16_t* d_pcm, float* d_wave);
+// Mel vocoder (d_conds == nullptr): d_in = (B, n_mels, T) fp32 device (reference layout, Export_BigVGAN.py:65-70).
+// IndexTTS (d_conds = nstages + 1 device vectors: cond_0..cond_{n-1} of C_i floats, then the cond_layer vector of C0):
+//   d_in = latent rows (T, gpt_dim) fp32 device = hidden[:-2], B = 1.
+// d_pcm: (B, hop*T+30) int16 device; d_wave (optional): same shape fp32, the pre-cast value tanh(.)*32767 clamped.
+void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T, int precision, int16_t* d_pcm, float* d_wave,
+                     const float* const* d_conds = nullptr);
 
 void bigvgan_free(BigVGANModel* m);
-int bigvgan_num_mels(const Engine& e);
-long bigvgan_out_samples(const Engine& e, int T);   // hop*T + 30
+int bigvgan_num_mels(const BigVGANModel& m);        // conv_pre input width (n_mels, or gpt_dim for IndexTTS)
+int bigvgan_num_stages(const BigVGANModel& m);
+int bigvgan_stage_channels(const BigVGANModel& m, int i);   // i = -1: conv_pre output channels
+long bigvgan_out_samples(const BigVGANModel& m, int T);   // hop*T + 30
 
-// bf16 weight layouts + TMA maps for the tensor-core path (idempotent).
-void bigvgan_tc_prepare(Engine& e);
+// bf16 weight layouts for the tensor-core path (idempotent).
+void bigvgan_tc_prepare(Engine& e, BigVGANModel& m);
 
 }  // namespace b200tts

@@ -94,6 +94,7 @@ struct Engine {
   DevBuf<int16_t> io_i16;
   std::string prof_report;                 // last JSON report (owned here so the C ABI can hand out a pointer)
   BigVGANModel* bigvgan = nullptr;         // owned; freed by bigvgan_free / f5_free in ~Engine (api.cu)
+  BigVGANModel* ivgan = nullptr;           // the IndexTTS_F vocoder (same generator family, see bigvgan.cuh)
   F5Model* f5 = nullptr;
 
   const Tensor& weight(const std::string& name) const {

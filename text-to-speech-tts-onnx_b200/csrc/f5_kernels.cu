@@ -69,11 +69,13 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 template <int MODE, typename OutT>
 void launch_rownorm(const float* x, const float* a, const float* b, OutT* out, int R, int D, float eps, cudaStream_t s) {
   const dim3 grid(ceil_div(R, 8));
+  B2_CHECK(D % 128 == 0, "rownorm: row width must be a multiple of 128");
   switch (D / 128) {
     case 4: rownorm_kernel<MODE, OutT, 4><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;     // text embedding (512)
     case 8: rownorm_kernel<MODE, OutT, 8><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;     // DiT (1024)
+    case 10: rownorm_kernel<MODE, OutT, 10><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;   // IndexTTS GPT latent (1280)
     case 16: rownorm_kernel<MODE, OutT, 16><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;
-    default: fail("rownorm: row width must be 512, 1024 or 2048");
+    default: fail("rownorm: row width must be 512, 1024, 1280 or 2048");
   }
 }
 

@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
             tma_load_3d(smem_a + sa * a_stage_bytes + rbx * (A_BOX_ROWS * 128), &map_a, &a_full[sa], g * a.Cin + c * BK,
                         t0 - halo_lo + rbx * A_BOX_ROWS, b);
           if (++sa == sc.nA) { sa = 0; pa ^= 1; }
-          if (BRES) continue;
+          if constexpr (BRES) continue;
           for (int j = 0; j < a.taps; ++j) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);

@@ -109,6 +109,33 @@ class _BigVGANGraph(_Graph):
         return [self.engine.bigvgan_run(mel, precision=self.precision, hop=self.cfg.hop)]
 
 
+class _IndexTTSVocoderGraph(_Graph):
+    """IndexTTS_F: IndexTTS/Export_IndexTTS.py:292-314,497-520; called at IndexTTS/Inference_IndexTTS_ONNX.py:787."""
+
+    def __init__(self, engine, precision, state=None):
+        from .config import INDEXTTS_VOCODER
+        self.engine, self.precision = engine, precision
+        self.cfg = INDEXTTS_VOCODER
+        ch = self.cfg.stage_channels()
+        self.inputs = tuple(NodeArg(f"save_bigvgan_conds_{i}", "tensor(float)", [1, c, 1]) for i, c in enumerate(ch)) + (
+            NodeArg("bigvgan_cond_layer_speaker_embedding", "tensor(float)", [1, self.cfg.upsample_initial_channel, 1]),
+            NodeArg("save_hidden_state", "tensor(float)", ["hidden_len", self.cfg.gpt_dim]))
+        self.outputs = (NodeArg("generated_wav", "tensor(int16)", [1, 1, "generated_len"]),)
+        state = state if state is not None else _checkpoints.get("indextts_f")
+        if state is None:
+            raise RuntimeError("no IndexTTS_F checkpoint registered: call session.register_checkpoint('indextts_f', state)")
+        engine.load_state("ivgan", weights.ivgan_engine_tensors(state, self.cfg))
+        engine.indextts_vocoder_build()
+
+    def run(self, feed):
+        conds = [_as_numpy(feed[f"save_bigvgan_conds_{i}"]).astype(np.float32) for i in range(len(self.cfg.upsample_rates))]
+        cond_layer = _as_numpy(feed["bigvgan_cond_layer_speaker_embedding"]).astype(np.float32)
+        hidden = _as_numpy(feed["save_hidden_state"]).astype(np.float32)
+        if hidden.ndim != 2 or hidden.shape[1] != self.cfg.gpt_dim or hidden.shape[0] < 3:
+            raise ValueError(f"save_hidden_state must be (S >= 3, {self.cfg.gpt_dim}), got {hidden.shape}")
+        return [self.engine.indextts_vocoder_run(hidden, conds, cond_layer, precision=self.precision, hop=self.cfg.hop)]
+
+
 _f5_ready = {}
 
 
@@ -216,12 +243,12 @@ class _F5DecodeGraph(_Graph):
 
 
 _GRAPHS = {"bigvgan": _BigVGANGraph, "f5_preprocess": _F5PreprocessGraph, "f5_transformer": _F5TransformerGraph,
-           "f5_decode": _F5DecodeGraph}
+           "f5_decode": _F5DecodeGraph, "indextts_f": _IndexTTSVocoderGraph}
 
 
 def _kind_of(path: str) -> str:
     base = os.path.basename(str(path)).lower()
-    for key in ("f5_preprocess", "f5_transformer", "f5_decode", "bigvgan"):
+    for key in ("f5_preprocess", "f5_transformer", "f5_decode", "indextts_f", "bigvgan"):
         if key in base:
             return key
     raise ValueError(f"cannot tell which hot-path graph '{path}' is (expected BigVGAN / F5_Preprocess / "

@@ -10,7 +10,7 @@ unlike ``torch.randn``.
 """
 import numpy as np
 
-from .config import BIGVGAN, F5, BigVGANConfig, F5Config
+from .config import BIGVGAN, F5, INDEXTTS_VOCODER, BigVGANConfig, F5Config, IndexTTSVocoderConfig
 
 
 def _n(rng, shape, std):
@@ -48,6 +48,27 @@ def bigvgan_state(seed: int = 1234, cfg: BigVGANConfig = BIGVGAN) -> dict:
     sd["activation_post.act.beta"] = _n(rng, (cl,), 0.4)
     sd["conv_post.weight"] = _n(rng, (1, cl, 7), 0.03 / np.sqrt(cl * 7))
     return sd
+
+
+def ivgan_state(seed: int = 777, cfg: IndexTTSVocoderConfig = INDEXTTS_VOCODER) -> dict:
+    """Synthetic weights of the IndexTTS_F vocoder: the BigVGAN generator (reference names of
+    IndexTTS/modeling_modified/models.py:130-250, weight norm removed) with a conv_post bias, plus gpt.final_norm."""
+    sd = bigvgan_state(seed, cfg)
+    rng = np.random.default_rng(seed + 1)
+    sd["conv_post.bias"] = _n(rng, (1,), 0.01)
+    sd["final_norm.weight"] = (1.0 + _n(rng, (cfg.gpt_dim,), 0.1)).astype(np.float32)
+    sd["final_norm.bias"] = _n(rng, (cfg.gpt_dim,), 0.05)
+    return sd
+
+
+def ivgan_inputs(seed: int, rows: int, cfg: IndexTTSVocoderConfig = INDEXTTS_VOCODER):
+    """IndexTTS_F inputs (Export_IndexTTS.py:497-520): save_bigvgan_conds_0..5 (1,C_i,1), the cond_layer speaker vector
+    (1,1536,1) and save_hidden_state (S, gpt_dim) -- the graph drops the last two rows."""
+    rng = np.random.default_rng(seed)
+    conds = [_n(rng, (1, c, 1), 0.1) for c in cfg.stage_channels()]
+    cond_layer = _n(rng, (1, cfg.upsample_initial_channel, 1), 0.1)
+    hidden = (3.0 * rng.standard_normal((rows, cfg.gpt_dim), dtype=np.float32) + 0.5).astype(np.float32)
+    return conds, cond_layer, hidden
 
 
 def bigvgan_mel(seed: int, batch: int, frames: int, cfg: BigVGANConfig = BIGVGAN) -> np.ndarray:

@@ -141,6 +141,17 @@ def vocos_engine_tensors(state: dict, cfg) -> dict:
     return out
 
 
+def ivgan_engine_tensors(state: dict, cfg) -> dict:
+    """IndexTTS_F vocoder state (IndexTTS bigvgan generator names + final_norm.*) -> tensors for
+    ``Engine.load_state('ivgan', ...)``. Tensors that belong to the conditioning branch the exported graph does not run
+    (speaker_encoder.*, cond_layer.*, conds.*; their outputs arrive as graph inputs, Export_IndexTTS.py:497-520) are
+    dropped; the strides are added because a ConvTranspose1d weight does not carry them."""
+    keep = {k: v for k, v in state.items() if not k.startswith(("speaker_encoder.", "cond_layer.", "conds.", "logit_scale"))}
+    out = bigvgan_engine_tensors(keep)
+    out["upsample_rates"] = np.asarray(cfg.upsample_rates, dtype=np.float32)
+    return out
+
+
 def bigvgan_engine_tensors(state: dict) -> dict:
     """Reference BigVGAN state dict -> tensors for ``Engine.load_state('bigvgan', ...)``."""
     out = {}
