@@ -90,13 +90,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
                                                                    // last S MMA has completed (pv_done of the last block)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                 // [2]
-  uint64_t* kv_empty = bars + 3;                // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_free = bars + 6;                  // softmax threads hold S in registers: the S buffer may be overwritten
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;                  // [2]  K and V stages are released separately: a K tile is dead as soon as
+  uint64_t* k_empty = bars + 3;                 // [2]  S_j = Q K_j^T has run, its V tile only after O += P_j V_j, a whole
+  uint64_t* v_full = bars + 5;                  // [2]  softmax later. With one barrier pair K_{j+1} arrived too late and the
+  uint64_t* v_empty = bars + 7;                 // [2]  softmax threads spent 21 % of their samples waiting for S (ncu r01p).
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;                 // softmax threads hold S in registers: the S buffer may be overwritten
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -108,7 +110,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     prefetch_tmap(&map_qk);
     prefetch_tmap(&map_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_free, 256);
     mbar_init(p_full, 256);
@@ -130,11 +135,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       for (int j = 0; j < nblocks; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (uint32_t)(j / KV_STAGES) & 1u;
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-        tma_load_3d(sK + s * K_BYTES, &map_qk, &kv_full[s], a.H * HD + h * HD, j * BKEY, b);
-        tma_load_3d(sV + s * V_BYTES, &map_v, &kv_full[s], j * BKEY, 0, bh);
-        tma_load_3d(sV + s * V_BYTES + V_BYTES / 2, &map_v, &kv_full[s], j * BKEY + 64, 0, bh);
+        mbar_wait(&k_empty[s], ph ^ 1u);
+        mbar_expect_tx(&k_full[s], K_BYTES);
+        tma_load_3d(sK + s * K_BYTES, &map_qk, &k_full[s], a.H * HD + h * HD, j * BKEY, b);
+        mbar_wait(&v_empty[s], ph ^ 1u);
+        mbar_expect_tx(&v_full[s], V_BYTES);
+        tma_load_3d(sV + s * V_BYTES, &map_v, &v_full[s], j * BKEY, 0, bh);
+        tma_load_3d(sV + s * V_BYTES + V_BYTES / 2, &map_v, &v_full[s], j * BKEY + 64, 0, bh);
       }
     }
   } else if (warp == WARP_MMA) {
@@ -145,19 +152,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       const uint64_t dP0 = make_desc_sw128(smem_u32(sP)), dP1 = make_desc_sw128(smem_u32(sP + P_BYTES / 2));
       auto issue_s = [&](int j) {
         const int s = j % KV_STAGES;
-        mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
+        mbar_wait(&k_full[s], (uint32_t)(j / KV_STAGES) & 1u);
         if (j > 0) mbar_wait(s_free, (uint32_t)(j - 1) & 1u);       // S_{j-1} is in the softmax threads' registers
         tc_fence_after();
         const uint64_t dK = make_desc_sw128(smem_u32(sK + s * K_BYTES));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_S, dQ + (uint64_t)(2 * k), dK + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+        umma_commit(&k_empty[s]);                                   // the K tile is free once this MMA has read it
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < nblocks; ++j) {
         if (j + 1 < nblocks) issue_s(j + 1);                        // runs under the exponentials of block j
         const int s = j % KV_STAGES;
+        mbar_wait(&v_full[s], (uint32_t)(j / KV_STAGES) & 1u);
         mbar_wait(p_full, (uint32_t)j & 1u);
         tc_fence_after();
         const uint64_t dV0 = make_desc_sw128(smem_u32(sV + s * V_BYTES));
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
           umma_bf16(tmem_O + 64, dP1 + (uint64_t)(2 * k), dV1 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(pv_done);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&v_empty[s]);
       }
     }
   } else {

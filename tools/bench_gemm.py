@@ -32,6 +32,13 @@ SHAPES = [
     ("res.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 1),
     ("res.s4 k7", 8, 65536, 48, 48, 7, 1, 1, 1),
     ("res.s5 k7", 8, 131072, 24, 24, 7, 1, 1, 1),
+    # the batched DiT (8 utterances per GPU: M = 2*8*1126)
+    ("bat.qkv", 1, 18016, 3072, 1024, 1, 1, 1, 2),
+    ("bat.out", 1, 18016, 1024, 1024, 1, 1, 1, 1),
+    ("bat.ff1", 1, 18016, 2048, 1024, 1, 1, 1, 2),
+    ("bat.ff2", 1, 18016, 1024, 2048, 1, 1, 1, 1),
+    ("bat.out epi0", 1, 18016, 1024, 1024, 1, 1, 1, 0),
+    ("bat.out epi3", 1, 18016, 1024, 1024, 1, 1, 1, 3),
     # epilogue dissection on one thin and one wide stage: 0 fp32 out | 3 fp32 out + residual | 4 bf16 out + residual
     ("epi0.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 0),
     ("epi3.s3 k7", 8, 32768, 96, 96, 7, 1, 1, 3),
