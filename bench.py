@@ -26,6 +26,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel from the committed
+    `ncu --set full` capture (profiles/r01/traffic.json says which launch of which capture); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(key)
+    return None if e is None else e["bytes_per_launch"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -281,9 +291,10 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
     conv, aa = _sum("bigvgan.resconv"), _sum("bigvgan.aa_snake.")
     if conv["ms"] > 0:
         ach = work["flops_resconv"] / (conv["ms"] / 1e3) / 1e12
-        kern = "rowgemm_tc_kernel (108 resblock convs)" if prec == capi.BF16 else "rowgemm_f32_kernel (SIMT parity engine)"
+        kern = "rowgemm_tc3_kernel (108 resblock convs)" if prec == capi.BF16 else "rowgemm_f32_kernel (SIMT parity engine)"
         res["roofline"] = {"bound": "tensor", "kernel": kern, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                           "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                           "frac": ach / pk["bf16_tflops_sustained"],
+                           "traffic": ncu_traffic("bigvgan.resconv") if prec == capi.BF16 else None,
                            "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                            "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
                            "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
@@ -291,7 +302,8 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
         per_elem = 4.0 if prec == capi.BF16 else 8.0          # bf16 in + bf16 out on the fast path
         gbs = work["aa_elems"] * per_elem / (aa["ms"] / 1e3) / 1e9
         res["roofline_hbm"] = {"bound": "hbm", "kernel": "aa_snake_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                               "frac": gbs / pk["hbm_gbs"], "traffic": None, "avg_launch_ms": aa["ms"] / max(aa["launches"], 1)}
+                               "frac": gbs / pk["hbm_gbs"], "traffic": ncu_traffic("bigvgan.aa_snake") if prec == capi.BF16 else None,
+                               "avg_launch_ms": aa["ms"] / max(aa["launches"], 1)}
     return res
 
 
@@ -383,9 +395,9 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
     if gemm_ms > 0:
         ach = U * work["steps"] * work["flops_gemm_step"] / (gemm_ms / 1e3) / 1e12
-        res["roofline"] = {"bound": "tensor", "kernel": "rowgemm_tc_kernel (DiT qkv/out/ff1/ff2 GEMMs)", "achieved": ach,
+        res["roofline"] = {"bound": "tensor", "kernel": "rowgemm_tc3_kernel (DiT qkv/out/ff1/ff2 GEMMs)", "achieved": ach,
                            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                           "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                           "traffic": ncu_traffic("f5.dit_gemm"), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                            "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms}
     att = prof.get("f5.attention")
     if att and att["ms"] > 0:
