@@ -315,14 +315,15 @@ struct Ctx {
 
 // y = conv(x) with the shifted-row GEMM; x, out are (B, L, C) fp32 (or bf16 for the tc path's A operand)
 void run_conv(Ctx& c, const char* tag, const ConvW& cw, const void* x, int L, int dil, void* out, int out_bf16,
-              const float* res, int accumulate, float scale, int ldx = 0, const float* bias = nullptr) {
+              const float* res, int accumulate, float scale, int ldx = 0, const float* bias = nullptr,
+              __nv_bfloat16* out2 = nullptr) {
   RowGemm p;
   if (ldx == 0) ldx = cw.Cin;
   p.x = x; p.x_bstride = (long)L * ldx; p.ldx = ldx; p.Lin = L;
   p.Cin = cw.Cin; p.N = cw.N; p.taps = cw.taps; p.dil = dil; p.center = (cw.taps - 1) / 2;
   p.M = L; p.B = c.B;
   p.out = out; p.o_bstride = (long)L * cw.N; p.ldo = cw.N; p.out_bf16 = out_bf16;
-  p.bias = bias ? bias : cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale;
+  p.bias = bias ? bias : cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale; p.out2 = c.fast ? out2 : nullptr;
   ProfScope ps(c.e.prof, tag, c.e.stream);
   if (c.fast) {
     rowgemm_tc(p, cw.tc, c.e.stream);
@@ -411,7 +412,8 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
     conv_in = m.mel16.p;
   }
   // conv_pre -> xs (B, T, C0)
-  run_conv(c, "bigvgan.conv_pre", m.pre, conv_in, T, 1, m.xs.p, 0, nullptr, 0, 1.0f, mel_ld, pre_bias);
+  // (the stage output is also written as bf16 by the producing GEMM: the next upsampler's A operand, no cast pass)
+  run_conv(c, "bigvgan.conv_pre", m.pre, conv_in, T, 1, m.xs.p, 0, nullptr, 0, 1.0f, mel_ld, pre_bias, m.xs16.p);
 
   int L = T;
   static const char* kConvTag[8] = {"bigvgan.resconv.s0", "bigvgan.resconv.s1", "bigvgan.resconv.s2", "bigvgan.resconv.s3",
@@ -422,12 +424,7 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
     Stage& st = m.stages[i];
     const char* ctag = kConvTag[i < 8 ? i : 7];
     const char* atag = kActTag[i < 8 ? i : 7];
-    const void* up_in = m.xs.p;
-    if (c.fast) {
-      ProfScope ps(e.prof, "bigvgan.cast", s);
-      cast_f32_to_bf16(m.xs.p, m.xs16.p, (long)B * L * st.Cin, s);
-      up_in = m.xs16.p;
-    }
+    const void* up_in = c.fast ? (const void*)m.xs16.p : (const void*)m.xs.p;
     run_up(c, st, up_in, L, m.xu.p, latent_in ? st.up_bias_c.p : st.up.bias.p);
     L *= st.u;
     for (int j = 0; j < 3; ++j) {
@@ -453,7 +450,8 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
           xcur = xnext;
         } else {
           // xs (+)= conv + x ; the MRF mean (x 1/3, bigvgan.py:399) is folded into the third block's epilogue
-          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f);
+          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f, 0, nullptr,
+                   j == 2 ? m.xs16.p : nullptr);
         }
       }
     }
