@@ -409,13 +409,52 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     return res
 
 
+def bench_indextts_vocoder(args, H, eng, rank, prec, steps, warmup):
+    """Vocoder half of BASELINE.json configs[4] (IndexTTS_F, S latent rows -> 1024*(S-2)+30 samples) through the host-buffer
+    C ABI call a reference script would make: H2D of the latent and conditioning vectors, D2H of the PCM inside the timed
+    region. There is no device-pointer entry point for this graph, so `value` and `e2e` are the same measurement."""
+    torch = H.torch
+    from b200tts import config, synth
+    cfg = config.INDEXTTS_VOCODER
+    S = args.latent_rows
+    conds, cond_layer, hidden = synth.ivgan_inputs(300 + rank, S)
+
+    def step():
+        eng.indextts_vocoder_run(hidden, conds, cond_layer, precision=prec, hop=cfg.hop)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    H.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()                                       # synchronises before returning (host-pointer entry point)
+    dt = time.perf_counter() - t0
+    ms = 1e3 * dt
+    if H.world > 1:
+        t = torch.tensor([ms], device="cuda")
+        H.dist.all_reduce(t, op=H.dist.ReduceOp.MAX)
+        ms = float(t.item())
+    frames = (S - 2) * 4 * H.world * steps              # one latent row = 1024 samples = 4 frames of 256 samples
+    n_out = cfg.out_samples(S - 2)
+    e2e = {"value": frames / (ms / 1e3), "unit": "mel-frames/s", "ms_per_step": ms / steps,
+           "h2d_bytes_per_step": int(hidden[:-2].nbytes + sum(c.nbytes for c in conds) + cond_layer.nbytes),
+           "d2h_bytes_per_step": int(n_out * 2), "rtf": (ms / 1e3 / steps) / (n_out / cfg.sample_rate)}
+    return {"value": e2e["value"], "ms_per_step": ms / steps, "rtf": e2e["rtf"], "e2e": e2e, "gpu_launches": None, "clocks": None,
+            "profile_ms": {},
+            "workload": f"IndexTTS_F vocoder (BigVGAN x1024 with conditioning), latent (S={S}, 1280) -> int16 PCM (1,1,{n_out}), one "
+                        "utterance per step through the host-buffer call (timed on the host clock around synchronising calls) "
+                        "[vocoder half of BASELINE.json configs[4]]"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline"])
+    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder"])
+    ap.add_argument("--latent-rows", type=int, default=142, help="indextts_vocoder workload: rows of save_hidden_state")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=512)
     ap.add_argument("--audio-len", type=int, default=144000)
@@ -453,6 +492,11 @@ def main():
     H = Harness(torch, dist, stream, world)
     need_f5 = args.workload in ("f5", "pipeline") or (args.workload == "bigvgan" and not args.no_extras)
     need_vgan = args.workload in ("bigvgan", "pipeline")
+    if args.workload == "indextts_vocoder":
+        cfgv = config.INDEXTTS_VOCODER
+        state = weights.ivgan_engine_tensors(synth.ivgan_state(777), cfgv) if rank == 0 else None
+        distributed.load_state_broadcast(eng, "ivgan", state, src=0)
+        eng.indextts_vocoder_build()
 
     # weights: rank 0 makes them, NCCL broadcast over NVLink to the others (the only collective of the job)
     if need_vgan:
@@ -479,6 +523,9 @@ def main():
             f5r = bench_f5(args, H, eng, rank, prec, steps=3, warmup=3)
             extra["f5"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **f5r}
         dtype = "bf16" if prec == capi.BF16 else "f32"
+    elif args.workload == "indextts_vocoder":
+        res = bench_indextts_vocoder(args, H, eng, rank, prec, args.steps, args.warmup)
+        dtype = "bf16" if prec == capi.BF16 else "f32"
     elif args.workload == "f5":
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
         dtype = "bf16" if prec == capi.BF16 else "f32"
@@ -497,7 +544,20 @@ def main():
         line.update(extra)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            if args.workload == "bigvgan":
+            if args.workload == "indextts_vocoder":
+                import torch as _t
+                from oracle import indextts_ref
+                _t.set_num_threads(cores)
+                sdv = synth.ivgan_state(777)
+                cds, cl, hid = synth.ivgan_inputs(300, args.latent_rows)
+                indextts_ref.indextts_f_pcm(hid[:6], cds, cl, sdv, config.INDEXTTS_VOCODER)
+                t0 = time.perf_counter()
+                indextts_ref.indextts_f_pcm(hid, cds, cl, sdv, config.INDEXTTS_VOCODER)
+                dtc = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": (args.latent_rows - 2) * 4 / dtc, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+                                        "sample": f"1 x latent ({args.latent_rows},1280), oracle (torch-CPU fp32 restatement of IndexTTS_F)",
+                                        "s_per_utterance": dtc}
+            elif args.workload == "bigvgan":
                 dt = cpu_bigvgan(args.frames, 2, cores)
                 line["cpu_baseline"] = {"value": args.frames / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                         "sample": f"2 x 1 mel (1,100,{args.frames}), oracle (torch-CPU fp32 restatement of the reference "

@@ -216,3 +216,31 @@ def test_f5_session_surface(f5, g):
     wav = C.run(["output_audio"], {"denoised": noise, "ref_signal_len": ref_len})[0]
     assert wav.dtype == np.int16 and wav.shape == g["pcm"].shape
     assert snr_db(g["pcm"], wav) > 55.0
+
+
+def test_f5_iobinding_loop(f5, g):
+    """The reference's bound loop (F5-TTS-ONNX-Inference.py:257-288): outputs aliased onto the inputs, 31 bound runs."""
+    from b200tts import session as ort
+    ort._engines[0] = f5
+    ort._f5_ready[id(f5)] = True
+    B = ort.InferenceSession("F5_Transformer.onnx", precision="fp32")
+    in_names = [i.name for i in B.get_inputs()]
+    out_names = [o.name for o in B.get_outputs()]
+    audio, ids, maxd, noise = _inputs(g)
+    N = int(maxd[0])
+    rq = np.broadcast_to(g["rope_cos_row"], (2, 16, N, 64)).copy()
+    sq = np.broadcast_to(g["rope_sin_row"], (2, 16, N, 64)).copy()
+    feed = [noise.copy(), rq, sq, rq.transpose(0, 1, 3, 2).copy(), sq.transpose(0, 1, 3, 2).copy(),
+            g["cat_mel_text"], g["cat_mel_text_drop"], np.array([0], dtype=np.int32)]
+    inputs = [ort.OrtValue.ortvalue_from_numpy(a, "cuda", 0) for a in feed]
+    outputs = [inputs[0], inputs[-1]]
+    io = B.io_binding()
+    for name, v in zip(in_names, inputs):
+        io.bind_ortvalue_input(name=name, ortvalue=v)
+    for name, v in zip(out_names, outputs):
+        io.bind_ortvalue_output(name=name, ortvalue=v)
+    for _ in range(31):
+        B.run_with_iobinding(io)
+    got = ort.OrtValue.numpy(io.get_outputs()[0])
+    assert int(inputs[-1].numpy()[0]) == 31
+    assert np.abs(got - g["noise_after_31"]).max() <= 1e-3

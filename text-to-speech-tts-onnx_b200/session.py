@@ -76,6 +76,31 @@ class OrtValue:
         return list(self._array.shape)
 
 
+class IOBinding:
+    """The subset of onnxruntime's SessionIOBinding the reference's (dormant) bound loop uses
+    (F5_TTS/F5-TTS-ONNX-Inference.py:257-288): inputs and outputs are OrtValues bound by name, outputs may alias inputs
+    (`noise`, `time_step` are updated in place by every run_with_iobinding call)."""
+
+    def __init__(self, session):
+        self._session = session
+        self._inputs, self._outputs = {}, {}
+
+    def bind_ortvalue_input(self, name, ortvalue):
+        self._inputs[name] = ortvalue
+
+    def bind_ortvalue_output(self, name, ortvalue):
+        self._outputs[name] = ortvalue
+
+    def get_outputs(self):
+        return [self._outputs[o.name] for o in self._session.get_outputs() if o.name in self._outputs]
+
+    def clear_binding_inputs(self):
+        self._inputs.clear()
+
+    def clear_binding_outputs(self):
+        self._outputs.clear()
+
+
 def _as_numpy(v):
     return v.numpy() if isinstance(v, OrtValue) else np.asarray(v)
 
@@ -288,6 +313,25 @@ class InferenceSession:
 
     def run_with_ort_values(self, output_names, input_feed, run_options=None):
         return [OrtValue(o) for o in self.run(output_names, input_feed)]
+
+    def io_binding(self):
+        return IOBinding(self)
+
+    def run_with_iobinding(self, iobinding, run_options=None):
+        """Runs on the bound inputs and writes each bound output IN PLACE into its OrtValue (which may be one of the inputs)."""
+        names = [o.name for o in self._outputs_meta]
+        outs = self.run(names, dict(iobinding._inputs))
+        for name, value in zip(names, outs):
+            bound = iobinding._outputs.get(name)
+            if bound is None:
+                iobinding._outputs[name] = OrtValue(np.asarray(value))
+            else:
+                dst = bound.numpy()
+                src = np.asarray(value)
+                if dst.shape != src.shape or dst.dtype != src.dtype:
+                    bound._array = src.copy()
+                else:
+                    dst[...] = src
 
     def run_all_steps(self, input_feed):
         """F5_Transformer only: all remaining NFE steps in one call, intermediates resident in HBM."""
