@@ -82,6 +82,18 @@ __device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w)
   return pk;
 }
 
+// Explicit shared-space accesses for the epilogue's staging block. Through a generic pointer the compiler emitted LD.E / ST.E,
+// which it may not move across the global stores of the previous row (possible aliasing): the eight staging loads of a block
+// were issued one per row, each exposed (ncu r01u: the thin convolutions and the batched DiT GEMMs are epilogue-bound).
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -146,6 +158,12 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
     if (n0 + cb >= a.N) break;
     uint32_t r[32];
     tmem_ld32(taddr + (uint32_t)cb, r);
+    // this lane's four phase-2 columns: bias / gate fetched under the TMEM load (they are needed first thing in phase 2)
+    const int n = n0 + cb + c4 * 4;
+    const bool n_ok = n < a.N;
+    const float4 bias = (a.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(a.bias + (long)g * a.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gate = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (KIND == EPI_STD && a.gate && n_ok) gate = __ldg(reinterpret_cast<const float4*>(a.gate + (long)g * a.N + n));
     // RoPE block: the (cos, sin) pairs of this lane's 8 phase-2 rows x 4 columns, one 16-byte load each, issued before the
     // TMEM wait (they were 16 dependent L2 round trips inside phase 2: +12 us on the q|k|v GEMM, ncu r01d)
     uint4 cs[8];
@@ -183,9 +201,10 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
     }
 
     // phase 1: row `lane`, 16-byte chunk k goes to chunk slot k ^ (lane & 7) (conflict-free per quarter warp)
+    const uint32_t stg_s = smem_u32(stg);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      *reinterpret_cast<uint4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
+      sts128(stg_s + (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2)) * 4u, r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
     __syncwarp();
 
     // the next block's residual: issued here, once r[] is dead, so it has the whole of phase 2 plus the next block's TMEM
@@ -199,18 +218,19 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
     }
 
     // phase 2
-    const int n = n0 + cb + c4 * 4;
-    const bool n_ok = n < a.N;
-    const float4 bias = (a.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(a.bias + (long)g * a.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 gate = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (KIND == EPI_STD && a.gate && n_ok) gate = __ldg(reinterpret_cast<const float4*>(a.gate + (long)g * a.N + n));
     const bool rope = KIND == EPI_ROPE && n < a.rope_cols;
+    float4 accs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                 // all eight staging rows of this lane in flight at once
+      const int row = i * 4 + sub;
+      accs[i] = lds128(stg_s + (uint32_t)(row * 32 + ((c4 ^ (row & 7)) << 2)) * 4u);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = i * 4 + sub;
       const long flat = epi_flat(a, p, i, n);
       const bool ok = epi_ok(a, p, i, n, flat);
-      const float4 acc = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
+      const float4 acc = accs[i];
       float v0 = acc.x + bias.x, v1 = acc.y + bias.y, v2 = acc.z + bias.z, v3 = acc.w + bias.w;
       if (KIND == EPI_ROPE) {
         if (rope) {                             // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
@@ -257,14 +277,24 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
   }
 }
 
-// The 4 x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost.
-template <int NH>
+// The KS x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost. KS = 4 for a full chunk,
+// 2 / 3 for the ragged last chunk of the thin BigVGAN stages (C = 24, 48, 96), where the generic loop was the critical path.
+template <int NH, int KS>
 __device__ __forceinline__ void issue_tap(uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < KS; ++k)
 #pragma unroll
     for (int h = 0; h < NH; ++h)
       umma_bf16_lohi(d + (uint32_t)h * hstep, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc, k == 0 ? accum : 1u);
+}
+template <int NH>
+__device__ __forceinline__ bool issue_tap_ks(int ksteps, uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accum) {
+  if (ksteps == 4) issue_tap<NH, 4>(d, hstep, a_lo, b_lo, idesc, accum);
+  else if (ksteps == 2) issue_tap<NH, 2>(d, hstep, a_lo, b_lo, idesc, accum);
+  else if (ksteps == 3) issue_tap<NH, 3>(d, hstep, a_lo, b_lo, idesc, accum);
+  else return false;
+  return true;
 }
 
 // A tap's A tile starts (tap*dil) rows = (tap*dil)*128 bytes into the halo tile, i.e. generally NOT on a 1024-byte
@@ -404,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
       for (int c = 0; c < kchunks; ++c) {
         int ksteps = (Cin - c * BK + UMMA_K - 1) / UMMA_K;
         if (ksteps > BK / UMMA_K) ksteps = BK / UMMA_K;
-        const int mode = ksteps == 4 ? nh : 0;                          // 1, 2, 4: fully unrolled issue; else generic
+        const int mode = ksteps == 4 ? nh : 0;                          // full chunk, 1 / 2 / 4 halves: the hot, fully unrolled path
         mbar_wait(&a_full[sa], pa);
         uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
         for (int j = 0; j < taps; ++j, a_lo += tap_lo) {
@@ -418,10 +448,15 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
             // into one accumulator never stalls the tensor pipe (matters when an MMA is short: small BN). The common
             // shapes are fully unrolled and every loop bound lives in a register: ONE thread issues every MMA of the
             // CTA, and a generic double loop here cost 40 % of the GEMM throughput (sweep_e.log).
-            if (mode == 1) issue_tap<1>(d0, hs, a_lo, b_lo, idesc, accum);
-            else if (mode == 2) issue_tap<2>(d0, hs, a_lo, b_lo, idesc, accum);
-            else if (mode == 4) issue_tap<4>(d0, hs, a_lo, b_lo, idesc, accum);
-            else
+            bool done = true;
+            if (mode == 1) issue_tap<1, 4>(d0, hs, a_lo, b_lo, idesc, accum);
+            else if (mode == 2) issue_tap<2, 4>(d0, hs, a_lo, b_lo, idesc, accum);
+            else if (mode == 4) issue_tap<4, 4>(d0, hs, a_lo, b_lo, idesc, accum);
+            else if (nh == 1) done = issue_tap_ks<1>(ksteps, d0, hs, a_lo, b_lo, idesc, accum);      // ragged last chunk
+            else if (nh == 2) done = issue_tap_ks<2>(ksteps, d0, hs, a_lo, b_lo, idesc, accum);
+            else if (nh == 4) done = issue_tap_ks<4>(ksteps, d0, hs, a_lo, b_lo, idesc, accum);
+            else done = false;
+            if (!done)
               for (int k = 0; k < ksteps; ++k)
                 for (int h = 0; h < nh; ++h)
                   umma_bf16_lohi(d0 + (uint32_t)h * hs, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc,
