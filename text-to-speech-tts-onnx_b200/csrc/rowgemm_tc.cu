@@ -823,6 +823,13 @@ int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// Experiment knobs (tools/sweep_gemm.sh, tools/test_2sm.sh), read once per process.
+struct TcEnv { int bm, bn, na, bres, two_sm; };
+const TcEnv& tc_env() {
+  static const TcEnv e{env_int("B200TTS_BM", 0), env_int("B200TTS_BN", 0), env_int("B200TTS_NA", 0), env_int("B200TTS_BRES", 1),
+                       env_int("B200TTS_2SM", -1)};
+  return e;
+}
 int half_stride_of(int bn) { return bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 TileShape pick_tile(int M, int N, long units, int sms, bool rope) {
@@ -854,7 +861,7 @@ TileShape pick_tile(int M, int N, long units, int sms, bool rope) {
     }
   }
   // experiment overrides (tools/sweep_gemm.sh)
-  const int ebm = env_int("B200TTS_BM", 0), ebn = env_int("B200TTS_BN", 0);
+  const int ebm = tc_env().bm, ebn = tc_env().bn;
   if (ebm && ebn && (ebm == 128 || ebm == 256 || ebm == 512) && ebn >= 16 && ebn <= 256 && ebn % 16 == 0 && (!rope || ebn % 64 == 0) &&
       (ebm / 128) * half_stride_of(ebn) <= 512)
     best = TileShape{ebm / 128, ebn};
@@ -903,7 +910,7 @@ void launch_2sm(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_
 
 // CTA-pair launch: 256 x BN pair tiles, BN in {256, 192, 128} dividing N. Returns false when the problem is not eligible.
 bool try_launch_2sm(const RowGemm& p, const TcWeight& w, cudaStream_t stream, bool rope) {
-  const int mode = env_int("B200TTS_2SM", -1);            // -1 auto, 0 off, 1 force when eligible
+  const int mode = tc_env().two_sm;                       // B200TTS_2SM: -1 auto, 0 off, 1 force when eligible
   if (mode == 0) return false;
   int bn = 0;
   for (int c : {256, 192, 128}) if (p.N % c == 0) { bn = c; break; }
@@ -1020,7 +1027,7 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   int nA, nB;
   sc.bres = 0;
   const long w_bytes = (long)kchunks * p.taps * b_stage;
-  if (p.taps > 1 && p.groups == 1 && sc.n_tiles == 1 && w_bytes + 2L * a_stage <= budget && env_int("B200TTS_BRES", 1) != 0) {
+  if (p.taps > 1 && p.groups == 1 && sc.n_tiles == 1 && w_bytes + 2L * a_stage <= budget && tc_env().bres != 0) {
     sc.bres = 1;
     nB = kchunks * p.taps;
     nA = (int)((budget - w_bytes) / a_stage);
