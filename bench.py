@@ -482,8 +482,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libb200tts has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") to fd 1 when the communicator is created; stdout must carry the ONE JSON
+        # line only, so fd 1 points at stderr until the first collectives (the weight broadcast) are done.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.zeros(1, device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
 
     prec = capi.BF16 if args.precision == "bf16" else capi.F32
     eng = capi.Engine(local_rank)
@@ -515,6 +524,12 @@ def main():
             distributed.load_state_broadcast(eng, k, parts[k], src=0)
         eng.f5_build()
 
+    if saved_stdout is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     extra = {}
     if args.workload == "bigvgan":
