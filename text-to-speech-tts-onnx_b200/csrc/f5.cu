@@ -91,7 +91,7 @@ struct F5Model {
   DevBuf<float> noise, cond, cond_drop, cproj, x, h, pred, rope_c, rope_s;
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
-  DevBuf<__nv_bfloat16> h16, c16, n16, qk16, vT16, att16, ff16;        // tensor-core engine
+  DevBuf<__nv_bfloat16> h16, c16, n16, qk16, vT16, att16, ff16, x16;   // tensor-core engine
   DevBuf<__half2> rope_cs16;                                           // [N][64] (cos, sin): exact, the tables are fp16-rounded (q5)
   // preprocess / decode scratch
   DevBuf<float> audio_f, spec, mag, mel, t_a, t_b, t_c, t_wide, grn_scratch;
@@ -508,6 +508,7 @@ void reserve_step(F5Model& m, bool fast) {
     m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.att16.reserve(R * m.D);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
+    m.x16.reserve((size_t)m.U * m.N * round_up(m.n_mels, 8));
   } else {
     m.c32.reserve(R * m.D); m.n32.reserve(R * m.D); m.att32.reserve(R * m.D); m.qkv32.reserve(R * 3 * m.D);
     m.ff32.reserve(R * m.FF);
@@ -558,15 +559,29 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   }
   for (int step = first; step < first + count; ++step) {
     // ---- input embedding: h[b] = Wx x + (Wc c_b + bias) ; x = conv_pos(h) + h ----
-    for (int sq = 0; sq < S; ++sq) {             // sequence sq = (utterance sq/2, CFG row sq%2): both rows share x
-      Epi ep; ep.res = m.cproj.p + (size_t)sq * N * D;
-      linear(e, "f5.embed_x", m.wx, false, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
-    }
     if (fast) {
-      { ProfScope ps(e.prof, "f5.cast", s); cast_f32_to_bf16(m.h.p, m.h16.p, (long)R * D, s); }
+      // tensor-core form: x of all U utterances as one batched A operand (bf16, rows padded to 8), one launch per CFG row
+      // (both rows share x); the epilogue adds the step-invariant half and also writes the bf16 copy conv_pos reads
+      const int ldx = (int)round_up(m.n_mels, 8);
+      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, (long)m.U * N, m.n_mels, ldx, s); }
+      lin_prepare_tc(e, m.wx);
+      for (int b = 0; b < 2; ++b) {
+        RowGemm p;
+        p.x = m.x16.p; p.x_bstride = (long)N * ldx; p.ldx = ldx; p.Lin = N;
+        p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = N; p.B = m.U;
+        p.out = m.h.p + (size_t)b * N * D; p.o_bstride = (long)2 * N * D; p.ldo = D;
+        p.res = m.cproj.p + (size_t)b * N * D;
+        p.out2 = m.h16.p + (size_t)b * N * D;
+        ProfScope ps(e.prof, "f5.embed_x", s);
+        rowgemm_tc(p, m.wx.tc, s);
+      }
       gconv(e, m.cp1, true, m.h16.p, N, m.c16.p, 1, ACT_MISH, nullptr);
       gconv(e, m.cp2, true, m.c16.p, N, m.x.p, 0, ACT_MISH, m.h.p);
     } else {
+      for (int sq = 0; sq < S; ++sq) {           // sequence sq = (utterance sq/2, CFG row sq%2): both rows share x
+        Epi ep; ep.res = m.cproj.p + (size_t)sq * N * D;
+        linear(e, "f5.embed_x", m.wx, false, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
+      }
       gconv(e, m.cp1, false, m.h.p, N, m.c32.p, 0, ACT_MISH, nullptr);
       gconv(e, m.cp2, false, m.c32.p, N, m.x.p, 0, ACT_MISH, m.h.p);
     }
