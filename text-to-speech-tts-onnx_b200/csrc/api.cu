@@ -308,11 +308,11 @@ static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const i
   run_graphed(E, {30, (long long)(uintptr_t)audio_dev, (long long)L, (long long)(uintptr_t)ids_dev, n_text, (long long)N,
                   (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
               [&] {
-                f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N);
+                f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N, 0, 1, precision == PREC_BF16);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 f5_prepare_cond(E);
                 f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
-                f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr);
+                f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr, precision == PREC_BF16);
                 if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
               },
               [&] { f5_restore_shape(E, (int)N, (int)(L / 256 + 1)); });
@@ -330,12 +330,12 @@ static void synth_batch_device(Engine& E, int U, const int16_t* audio_dev, int64
                   (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
               [&] {
                 for (int u = 0; u < U; ++u)
-                  f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U);
+                  f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U, precision == PREC_BF16);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 f5_prepare_cond(E);
                 f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
                 for (int u = 0; u < U; ++u)
-                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr);
+                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr, precision == PREC_BF16);
                 if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
               },
               [&] { f5_restore_shape(E, (int)N, F, U); });

@@ -78,6 +78,10 @@ struct F5Model {
   // vocos + istft
   int VC = 0, VI = 0;
   DevBuf<float> v_embed_w, v_embed_b;       // [7][n_mels][VC]
+  const float* v_embed_ref = nullptr;       // reference layout (VC, n_mels, 7): source of the tensor-core copy
+  TcWeight v_embed_tc, istft_tc, head_tc;   // lazy, tensor-core engine
+  const float* istft_ref = nullptr;         // (2*bins, nfft)
+  DevBuf<__nv_bfloat16> s16a, s16b;         // bf16 staging of the front / back end GEMM operands (tensor-core engine)
   DevBuf<float> v_nw, v_nb, v_fw, v_fb;
   std::vector<VocosBlock> vblocks;
   Lin head;                  // K = VC, N = 2*bins
@@ -141,6 +145,18 @@ struct Epi {
   const float* bias = nullptr; const float* gate = nullptr; const float* res = nullptr;
   int act = ACT_NONE; int out_bf16 = 0;
 };
+
+// fp32 [rows][C] (row stride ld) -> bf16 [rows][round_up(C, 8)] in `dst`: the A operand of a tensor-core GEMM whose producer
+// is an fp32 kernel (norms, GRN, ISTFT input) -- the front / back end of the bf16 engine
+const __nv_bfloat16* stage_bf16(Engine& e, DevBuf<__nv_bfloat16>& dst, const float* x, int ld, int rows, int C, int* ld16) {
+  B2_CHECK(ld == C, "stage_bf16: compact rows expected");
+  *ld16 = (int)round_up(C, 8);
+  dst.reserve((size_t)rows * *ld16);
+  ProfScope ps(e.prof, "f5.cast", e.stream);
+  if (*ld16 == C) cast_f32_to_bf16(x, dst.p, (long)rows * C, e.stream);
+  else cast_pad_f32_to_bf16(x, dst.p, rows, C, *ld16, e.stream);
+  return dst.p;
+}
 
 // rows x K (ldx) @ W^T -> rows x N (ldo). use_tc: bf16 A operand + tcgen05, else fp32 SIMT.
 void linear(Engine& e, const char* tag, Lin& L, bool use_tc, const void* x, int ldx, int rows, void* out, int ldo, const Epi& ep) {
@@ -296,6 +312,7 @@ F5Model* f5_build(Engine& e) {
     B2_CHECK(W.shape[1] == m.n_mels && W.shape[2] == 7, "vocos embed shape");
     m.v_embed_w.alloc((size_t)7 * m.n_mels * m.VC);
     conv_weight_permute(W.data.p, m.v_embed_w.p, m.VC, m.n_mels, 7, 1, 1, s);
+    m.v_embed_ref = W.data.p;
     copy_vec(e, V + "backbone.embed.bias", m.v_embed_b, m.VC);
     copy_vec(e, V + "backbone.norm.weight", m.v_nw, m.VC);
     copy_vec(e, V + "backbone.norm.bias", m.v_nb, m.VC);
@@ -325,6 +342,7 @@ F5Model* f5_build(Engine& e) {
     m.istft.wT.alloc((size_t)kp * m.nfft);
     B2_CUDA(cudaMemsetAsync(m.istft.wT.p, 0, (size_t)kp * m.nfft * sizeof(float), s));
     B2_CUDA(cudaMemcpyAsync(m.istft.wT.p, IB.data.p, (size_t)2 * m.bins * m.nfft * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    m.istft_ref = IB.data.p;
     const Tensor& ws = e.weight(C + "window_sum_inv");
     m.wsi = ws.data.p; m.wsi_len = ws.numel();
   }
@@ -400,7 +418,7 @@ void f5_prepare_cond(Engine& e) {
 // =============================================================================================
 // graph A
 // =============================================================================================
-void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u, int U) {
+void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u, int U, bool fast) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   const int F = (int)(L / m.hop) + 1;
@@ -457,10 +475,19 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
       dwconv7(m.t_a.p, tb.dw.p, tb.dwb.p, m.t_b.p, 1, N, TD, s);
       layernorm_affine(m.t_b.p, tb.lnw.p, tb.lnb.p, m.t_c.p, N, TD, 1e-6f, s);
       Epi e1; e1.bias = tb.pw1.bias.p; e1.act = ACT_GELU_ERF;
-      linear(e, "f5.text_embed.gemm", tb.pw1, false, m.t_c.p, TD, N, m.t_wide.p, TW, e1);
-      grn_inplace(m.t_wide.p, tb.gamma.p, tb.beta.p, m.grn_scratch.p, N, TW, s);
       Epi e2; e2.bias = tb.pw2.bias.p; e2.res = m.t_a.p;
-      linear(e, "f5.text_embed.gemm", tb.pw2, false, m.t_wide.p, TW, N, m.t_b.p, TD, e2);
+      if (fast) {                      // bf16 engine: the two pointwise GEMMs on tensor cores (GRN needs the fp32 hidden)
+        int l16 = 0;
+        const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.t_c.p, TD, N, TD, &l16);
+        linear(e, "f5.text_embed.gemm", tb.pw1, true, a1, l16, N, m.t_wide.p, TW, e1);
+        grn_inplace(m.t_wide.p, tb.gamma.p, tb.beta.p, m.grn_scratch.p, N, TW, s);
+        const __nv_bfloat16* a2 = stage_bf16(e, m.s16b, m.t_wide.p, TW, N, TW, &l16);
+        linear(e, "f5.text_embed.gemm", tb.pw2, true, a2, l16, N, m.t_b.p, TD, e2);
+      } else {
+        linear(e, "f5.text_embed.gemm", tb.pw1, false, m.t_c.p, TD, N, m.t_wide.p, TW, e1);
+        grn_inplace(m.t_wide.p, tb.gamma.p, tb.beta.p, m.grn_scratch.p, N, TW, s);
+        linear(e, "f5.text_embed.gemm", tb.pw2, false, m.t_wide.p, TW, N, m.t_b.p, TD, e2);
+      }
       mask_rows(m.t_b.p, m.ids.p, N, TD, s);
       std::swap(m.t_a, m.t_b);
     }
@@ -645,7 +672,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
 // =============================================================================================
 // graph C
 // =============================================================================================
-long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave) {
+long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, bool fast) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   if (d_mel == nullptr) { d_mel = m.noise.p; }
@@ -661,8 +688,22 @@ long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm
     RowGemm p;                                  // embed: Conv1d(n_mels -> VC, k 7, pad 3)
     p.x = x0; p.ldx = m.n_mels; p.Lin = G; p.Cin = m.n_mels; p.N = VC; p.taps = 7; p.center = 3; p.M = G; p.B = 1;
     p.w = m.v_embed_w.p; p.ldw = VC; p.out = m.d_a.p; p.ldo = VC; p.bias = m.v_embed_b.p;
-    ProfScope ps(e.prof, "f5.vocos_gemm", s);
-    rowgemm_f32(p, s);
+    if (fast) {
+      if (!m.v_embed_tc.ready) {
+        DevBuf<float> tmp((size_t)7 * VC * m.n_mels);
+        conv_weight_permute(m.v_embed_ref, tmp.p, VC, m.n_mels, 7, 1, 0, s);
+        tc_weight_from_f32(m.v_embed_tc, tmp.p, 1, 7, VC, m.n_mels, s);
+        B2_CUDA(cudaStreamSynchronize(s));
+      }
+      int l16 = 0;
+      p.x = stage_bf16(e, m.s16a, x0, m.n_mels, G, m.n_mels, &l16);
+      p.ldx = l16;
+      ProfScope ps(e.prof, "f5.vocos_gemm", s);
+      rowgemm_tc(p, m.v_embed_tc, s);
+    } else {
+      ProfScope ps(e.prof, "f5.vocos_gemm", s);
+      rowgemm_f32(p, s);
+    }
   }
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); l2_norm_affine(m.d_a.p, m.v_nw.p, m.v_nb.p, m.d_b.p, G, VC, s); }
   float* cur = m.d_b.p; float* other = m.d_a.p;
@@ -673,18 +714,60 @@ long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm
       l2_norm_affine(m.d_c.p, vb.nw.p, vb.nb.p, m.d_c.p, G, VC, s);
     }
     Epi e1; e1.bias = vb.pw1.bias.p; e1.act = ACT_GELU_ERF;
-    linear(e, "f5.vocos_gemm", vb.pw1, false, m.d_c.p, VC, G, m.d_wide.p, VI, e1);
     Epi e2; e2.bias = vb.pw2.bias.p; e2.res = cur;
-    linear(e, "f5.vocos_gemm", vb.pw2, false, m.d_wide.p, VI, G, other, VC, e2);
+    if (fast) {                        // pw1 writes its GELU output as bf16: pw2's A operand, no staging pass
+      int l16 = 0;
+      const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16);
+      m.s16b.reserve((size_t)G * VI);
+      e1.out_bf16 = 1;
+      linear(e, "f5.vocos_gemm", vb.pw1, true, a1, l16, G, m.s16b.p, VI, e1);
+      linear(e, "f5.vocos_gemm", vb.pw2, true, m.s16b.p, VI, G, other, VC, e2);
+    } else {
+      linear(e, "f5.vocos_gemm", vb.pw1, false, m.d_c.p, VC, G, m.d_wide.p, VI, e1);
+      linear(e, "f5.vocos_gemm", vb.pw2, false, m.d_wide.p, VI, G, other, VC, e2);
+    }
     std::swap(cur, other);
   }
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); l2_norm_affine(cur, m.v_fw.p, m.v_fb.p, m.d_c.p, G, VC, s); }
   Epi eh; eh.bias = m.head.bias.p;
-  linear(e, "f5.vocos_gemm", m.head, false, m.d_c.p, VC, G, m.d_head.p, m.head.Np, eh);
+  if (fast) {
+    int l16 = 0;
+    const __nv_bfloat16* ah = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16);
+    if (!m.head_tc.ready) {                     // N = nfft + 2 is not a multiple of 4: zero weight rows up to Np (bias is padded too)
+      DevBuf<float> tmp((size_t)m.head.Np * m.head.K);
+      B2_CUDA(cudaMemsetAsync(tmp.p, 0, (size_t)m.head.Np * m.head.K * sizeof(float), s));
+      B2_CUDA(cudaMemcpyAsync(tmp.p, m.head.w_ref, (size_t)m.head.N * m.head.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      tc_weight_from_f32(m.head_tc, tmp.p, 1, 1, m.head.Np, m.head.K, s);
+      B2_CUDA(cudaStreamSynchronize(s));
+    }
+    RowGemm p;
+    p.x = ah; p.ldx = l16; p.Lin = G; p.Cin = m.head.K; p.N = m.head.Np; p.taps = 1; p.M = G; p.B = 1;
+    p.out = m.d_head.p; p.ldo = m.head.Np; p.bias = eh.bias;
+    ProfScope ps(e.prof, "f5.vocos_gemm", s);
+    rowgemm_tc(p, m.head_tc, s);
+  } else {
+    linear(e, "f5.vocos_gemm", m.head, false, m.d_c.p, VC, G, m.d_head.p, m.head.Np, eh);
+  }
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); istft_input(m.d_head.p, m.d_in.p, G, m.bins, m.head.Np, s); }
   B2_CHECK(m.head.Np == m.istft.K, "head / istft padding mismatch");
   Epi ei;
-  linear(e, "f5.istft_gemm", m.istft, false, m.d_in.p, m.istft.K, G, m.d_frames.p, m.nfft, ei);
+  if (fast) {
+    if (!m.istft_tc.ready) {                    // W^T = basis^T: [nfft][2*bins (+ pad)]
+      DevBuf<float> tmp((size_t)m.nfft * m.istft.K);
+      transpose_pad(m.istft_ref, tmp.p, 2 * m.bins, m.nfft, m.istft.K, s);
+      tc_weight_from_f32(m.istft_tc, tmp.p, 1, 1, m.nfft, m.istft.K, s);
+      B2_CUDA(cudaStreamSynchronize(s));
+    }
+    int l16 = 0;
+    RowGemm p;
+    p.x = stage_bf16(e, m.s16a, m.d_in.p, m.istft.K, G, m.istft.K, &l16);
+    p.ldx = l16; p.Lin = G; p.Cin = m.istft.K; p.N = m.nfft; p.taps = 1; p.M = G; p.B = 1;
+    p.out = m.d_frames.p; p.ldo = m.nfft;
+    ProfScope ps(e.prof, "f5.istft_gemm", s);
+    rowgemm_tc(p, m.istft_tc, s);
+  } else {
+    linear(e, "f5.istft_gemm", m.istft, false, m.d_in.p, m.istft.K, G, m.d_frames.p, m.nfft, ei);
+  }
   B2_CHECK((long)m.nfft + (long)m.hop * (G - 1) <= m.wsi_len, "window_sum_inv table too short");
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); istft_overlap_add(m.d_frames.p, m.wsi, G, m.nfft, m.hop, d_pcm, d_wave, s); }
   return (long)m.hop * (G - 1);

@@ -15,7 +15,9 @@ void f5_free(F5Model* m);
 // Fills the state's cond / cond_drop [N][612], ref_signal_len, rope rows. `noise` is NOT drawn here: the caller
 // supplies it through f5_set_noise (the reference draws it with ORT's RandomNormalLike, irreproducible elsewhere).
 // u / U: slot of this utterance in a batch of U utterances that share N (length-bucketed batching; default: one utterance).
-void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u = 0, int U = 1);
+// fast: the text-embedding GEMMs run on tensor cores (bf16 operands); the per-graph session entry points keep fp32.
+void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u = 0, int U = 1,
+                   bool fast = false);
 int f5_ref_len(const Engine& e);
 int f5_seq_len(const Engine& e);
 int f5_cond_dim(const Engine& e);   // n_mels + text_dim (612)
@@ -40,6 +42,7 @@ void f5_prepare_cond(Engine& e);
 void f5_steps(Engine& e, int first, int count, int precision);
 // Graph C (Export_F5.py:197-203): decode noise[ref_len:] -> pcm int16 [256 * (N - ref_len - 1)] (device);
 // d_mel (N x 100 fp32 device) defaults to the state's noise when null.
-long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave);
+// fast: Vocos / ISTFT GEMMs on tensor cores (bf16 operands, fp32 accumulate and residual stream).
+long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, bool fast = false);
 
 }  // namespace b200tts
