@@ -177,6 +177,8 @@ template <typename InT, typename OutT, bool PRECISE, bool POST>
 __global__ void __launch_bounds__(NT) aa_snake_kernel(const InT* __restrict__ x, OutT* __restrict__ y,
                                                       const float* __restrict__ alpha, const float* __restrict__ inv_beta,
                                                       int C, int L, long x_bstride, long y_bstride, int seg, int nseg) {
+  pdl_trigger();
+  pdl_wait();
   const int CP = C >> 1;
   const long gidx = (long)blockIdx.x * NT + threadIdx.x;
   const int sidx = (int)(gidx / CP);
@@ -208,8 +210,8 @@ void launch(const void* x, void* y, const float* alpha, const float* inv_beta, i
   const int nseg = ceil_div(Lout, seg);
   const long threads = (long)nseg * (C / 2);
   dim3 grid(ceil_div(threads, NT), B);
-  aa_snake_kernel<InT, OutT, PRECISE, POST><<<grid, NT, 0, stream>>>(
-      (const InT*)x, (OutT*)y, alpha, inv_beta, C, L, (long)L * C, (long)Lout * C, seg, nseg);
+  launch_pdl(aa_snake_kernel<InT, OutT, PRECISE, POST>, grid, dim3(NT), 0, stream,
+             (const InT*)x, (OutT*)y, alpha, inv_beta, C, L, (long)L * C, (long)Lout * C, seg, nseg);
   B2_LAUNCH_CHECK();
   count_launch();
 }

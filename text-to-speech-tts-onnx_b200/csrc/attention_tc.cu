@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();                                          // after the TMEM allocation (common.cuh)
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // O_a: +128..191, O_b: +192..255
 
@@ -343,7 +345,7 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
   AttnArgs a{N, H, out, H * HD};
   B2_CHECK(S <= 65535, "attention_tc: too many sequences");
   dim3 grid(ceil_div(N, BQ), H, S);
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map_qk, map_v, a);
+  launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
   B2_LAUNCH_CHECK();
   count_launch();
 }

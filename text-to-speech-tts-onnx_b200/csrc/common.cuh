@@ -38,6 +38,33 @@ inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Programmatic dependent launch. The hot path is thousands of short kernels in one stream (16 us each on average for one
+// F5 utterance), so the launch / drain / fill gap between two of them is a visible share of the step. Every hot kernel
+//   1. signals pdl_trigger() once its own on-chip resources are claimed (for tensor-memory users: AFTER tcgen05.alloc, so
+//      that an early-arriving dependent CTA can never take the columns this CTA still waits for), which lets the next
+//      kernel's CTAs be scheduled and run their prologue (barrier init, TMEM alloc, descriptor prefetch) as SMs drain, and
+//   2. executes pdl_wait() before its first access to global memory: it returns when the preceding kernel has completed
+//      and its writes are visible (a no-op for a kernel launched without the attribute).
+// Both are no-ops semantically for ordering: the data dependence of a stream is unchanged.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();     // B200TTS_PDL=0 turns the launch attribute off (rowgemm_f32.cu)
+
+// Launch `kernel` so that it may start while its predecessor in the stream drains (its pdl_wait() orders the data).
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  B2_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+#endif
+
 // Bumped by every device (re)allocation / free of a DevBuf: captured CUDA graphs bake buffer addresses into their nodes,
 // so a cached graph is only replayed while the epoch it was captured under still holds (engine.cuh: GraphCache).
 extern unsigned long long g_alloc_epoch;

@@ -24,6 +24,8 @@ template <int MODE, typename OutT, int NV>
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                       const float* __restrict__ b, OutT* __restrict__ out, int R, int D,
                                                       float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -71,10 +73,10 @@ void launch_rownorm(const float* x, const float* a, const float* b, OutT* out, i
   const dim3 grid(ceil_div(R, 8));
   B2_CHECK(D % 128 == 0, "rownorm: row width must be a multiple of 128");
   switch (D / 128) {
-    case 4: rownorm_kernel<MODE, OutT, 4><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;     // text embedding (512)
-    case 8: rownorm_kernel<MODE, OutT, 8><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;     // DiT (1024)
-    case 10: rownorm_kernel<MODE, OutT, 10><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;   // IndexTTS GPT latent (1280)
-    case 16: rownorm_kernel<MODE, OutT, 16><<<grid, 256, 0, s>>>(x, a, b, out, R, D, eps); break;
+    case 4: launch_pdl(rownorm_kernel<MODE, OutT, 4>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;     // text embedding (512)
+    case 8: launch_pdl(rownorm_kernel<MODE, OutT, 8>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;     // DiT (1024)
+    case 10: launch_pdl(rownorm_kernel<MODE, OutT, 10>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;   // IndexTTS GPT latent (1280)
+    case 16: launch_pdl(rownorm_kernel<MODE, OutT, 16>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;
     default: fail("rownorm: row width must be 512, 1024, 1280 or 2048");
   }
 }
@@ -195,6 +197,8 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ld_src, floa
   dst[(long)n * ld_dst + col0 + c] = src ? src[(long)n * ld_src + c] : 0.f;
 }
 __global__ void euler_kernel(float* __restrict__ noise, const float* __restrict__ pred, long n, float cfg, float dt) {
+  pdl_trigger();
+  pdl_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long u = blockIdx.y;                       // utterance of the batch: pred is [U][2][n], noise [U][n]
@@ -345,7 +349,7 @@ void copy_cols(const float* src, int ld_src, float* dst, int ld_dst, int col0, i
   LAUNCHED();
 }
 void euler_cfg_update(float* noise, const float* pred, long n, int U, float cfg, float dt, cudaStream_t s) {
-  euler_kernel<<<dim3(ceil_div(n, 256), U), 256, 0, s>>>(noise, pred, n, cfg, dt);
+  launch_pdl(euler_kernel, dim3(ceil_div(n, 256), U), dim3(256), 0, s, noise, pred, n, cfg, dt);
   LAUNCHED();
 }
 void istft_input(const float* head, float* out, int G, int bins, int ld, cudaStream_t s) {

@@ -338,6 +338,8 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();                                          // after the TMEM allocation (common.cuh)
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
   const int per_bg = sc.m_tiles * sc.n_tiles;
   const int halo_lo = a.center * a.dil;
@@ -564,6 +566,8 @@ rowgemm_tc2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_before();
   cluster_sync_all();                                     // both allocations are done before the leader's MMAs write the peer's TMEM
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
   const int per_bg = sc.m_tiles * sc.n_tiles;             // pair tiles (256 rows x BN) per (batch, group)
   const int halo_lo = a.center * a.dil;
@@ -747,6 +751,8 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
 namespace {
 
 __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
+  pdl_trigger();
+  pdl_wait();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
@@ -762,6 +768,8 @@ __global__ void uncast_kernel(const __nv_bfloat16* __restrict__ in, float* __res
 }
 
 __global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int C, int ldo) {
+  pdl_trigger();
+  pdl_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ldo) return;
   const long r = i / ldo;
@@ -774,7 +782,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __r
 void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s) {
   if (n <= 0) return;
   B2_CHECK(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, "cast alignment");
-  cast_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(in, out, n);
+  launch_pdl(cast_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, s, in, out, n);
   B2_LAUNCH_CHECK(); count_launch();
 }
 
@@ -786,7 +794,7 @@ void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t 
 
 void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s) {
   if (rows <= 0) return;
-  cast_pad_kernel<<<ceil_div(rows * ldo, 256), 256, 0, s>>>(in, out, rows, C, ldo);
+  launch_pdl(cast_pad_kernel, dim3(ceil_div(rows * ldo, 256)), dim3(256), 0, s, in, out, rows, C, ldo);
   B2_LAUNCH_CHECK(); count_launch();
 }
 
@@ -889,7 +897,7 @@ void launch_one(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(rowgemm_tc3_kernel<KIND, ACT, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   });
-  rowgemm_tc3_kernel<KIND, ACT, BRES><<<grid, NTHREADS3, smem, stream>>>(map_a, map_b, a, sc);
+  launch_pdl(rowgemm_tc3_kernel<KIND, ACT, BRES>, dim3(grid), dim3(NTHREADS3), (size_t)smem, stream, map_a, map_b, a, sc);
 }
 template <int KIND, int ACT>
 void launch_kernel(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& a,
@@ -905,7 +913,7 @@ void launch_2sm(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2sm_kernel<KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   });
-  rowgemm_tc2sm_kernel<KIND, ACT><<<grid, NTHREADS3, smem, stream>>>(map_a, map_b, a, sc);
+  launch_pdl(rowgemm_tc2sm_kernel<KIND, ACT>, dim3(grid), dim3(NTHREADS3), (size_t)smem, stream, map_a, map_b, a, sc);
 }
 
 // CTA-pair launch: 256 x BN pair tiles, BN in {256, 192, 128} dividing N. Returns false when the problem is not eligible.
