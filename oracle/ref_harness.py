@@ -185,6 +185,75 @@ def build_indextts_f(sd: dict, cfg):
     return IndexTTS_F()
 
 
+def build_indextts_gpt(sd: dict, cfg):
+    """The reference's IndexTTS_B / _C / _D / _E wrapper classes, compiled from Export_IndexTTS.py where it lies (the script
+    loads checkpoints at import time, so the class definitions are extracted and exec'd; nothing is copied), driving a Hugging
+    Face GPT2Model -- the class index-tts (un-vendored) builds its inference_model from -- filled with a synthetic state dict.
+    -> (B, C, D, E) modules. B and D take a Python int for a tensor shape (they were written for the tracer), so they are
+    returned as callables that run the module under torch.jit.trace."""
+    import ast
+    from transformers import GPT2Config, GPT2Model
+    path = os.path.join(REF, "IndexTTS", "Export_IndexTTS.py")
+    tree = ast.parse(open(path, encoding="utf-8").read())
+    wanted = {"IndexTTS_B", "IndexTTS_C", "IndexTTS_D", "IndexTTS_E"}
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(sd[k])).float()
+    D = cfg.dim
+    gcfg = GPT2Config(vocab_size=8, n_positions=8, n_embd=D, n_layer=cfg.layers, n_head=cfg.heads,
+                      activation_function="gelu_new", layer_norm_epsilon=cfg.ln_eps, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    tr = GPT2Model(gcfg)
+    own = {k: t(k) for k in sd if k.startswith(("h.", "ln_f."))}
+    missing, unexpected = tr.load_state_dict(own, strict=False)
+    assert not unexpected and all(m.startswith(("wte.", "wpe.")) or m.endswith((".attn.bias", ".attn.masked_bias")) for m in missing), \
+        (missing, unexpected)
+
+    def emb(k):
+        e = torch.nn.Embedding(sd[k].shape[0], D)
+        e.weight.data = t(k)
+        return e
+
+    class _Pos(torch.nn.Module):
+        def __init__(self, k):
+            super().__init__()
+            self.emb = emb(k)
+
+    class _Inf(torch.nn.Module):              # GPT2InferenceModel's attribute names as Export_IndexTTS.py uses them
+        def __init__(self):
+            super().__init__()
+            self.transformer = tr
+            self.embeddings = emb("mel_embedding.weight")
+            self.text_pos_embedding = _Pos("mel_pos_embedding.emb.weight")       # the MEL position table (index-tts naming)
+            fn = torch.nn.LayerNorm(D, eps=cfg.ln_eps)
+            fn.weight.data, fn.bias.data = t("final_norm.weight"), t("final_norm.bias")
+            head = torch.nn.Linear(D, cfg.mel_codes)
+            head.weight.data, head.bias.data = t("mel_head.weight"), t("mel_head.bias")
+            self.lm_head = torch.nn.Sequential(fn, head)
+
+    class _GPT(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.text_embedding = emb("text_embedding.weight")
+            self.text_pos_embedding = _Pos("text_pos_embedding.emb.weight")
+            self.inference_model = _Inf()
+
+    class _Index:
+        pass
+
+    idx = _Index()
+    idx.gpt = _GPT().eval()
+    with torch.inference_mode():
+        B = ns["IndexTTS_B"](idx).eval()
+        C = ns["IndexTTS_C"](idx).eval()
+        Dm = ns["IndexTTS_D"]().eval()
+        E = ns["IndexTTS_E"](idx, cfg.layers, cfg.max_generate).eval()
+    traced = lambda mod: (lambda *a: torch.jit.trace(mod, a, check_trace=False)(*a))
+    return traced(B), C, traced(Dm), E
+
+
 # ----------------------------------------------------------------------------------------------
 # F5-TTS: DiT, STFT_Process, Vocos and the three export wrappers
 # ----------------------------------------------------------------------------------------------

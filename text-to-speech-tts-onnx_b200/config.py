@@ -80,3 +80,40 @@ class IndexTTSVocoderConfig(BigVGANConfig):
 BIGVGAN = BigVGANConfig()
 F5 = F5Config()
 INDEXTTS_VOCODER = IndexTTSVocoderConfig()
+
+
+@dataclass(frozen=True)
+class IndexTTSGPTConfig:
+    """The GPT-2 acoustic model of IndexTTS as graphs B-E run it (reference: IndexTTS/Export_IndexTTS.py:203-289, host loop
+    IndexTTS/Inference_IndexTTS_ONNX.py:719-781). In-repo pins: start/stop text ids 0/1 (:208-209), start mel id 8192
+    (Inference:673), stop mel id 8193 (:36), MAX_GENERATE_LENGTH 800 (:37), REPEAT_PENALITY 0.7 (:38), PENALITY_RANGE 10
+    (:39), q/k pre-scale head_dim^-0.25 (:250-255). model_dim 1280 / 24 layers / 20 heads / 12000 text tokens / 8194 mel
+    codes / 32 conditioning latents come from the un-vendored index-tts config.yaml; the position-table sizes are the
+    smallest that cover MAX_GENERATE_LENGTH."""
+    dim: int = 1280
+    layers: int = 24
+    heads: int = 20
+    head_dim: int = 64
+    text_vocab: int = 12000
+    mel_codes: int = 8194
+    start_text: int = 0
+    stop_text: int = 1
+    start_mel: int = 8192
+    stop_mel: int = 8193
+    text_pos: int = 604
+    mel_pos: int = 803
+    cond_rows: int = 32
+    ln_eps: float = 1e-5
+    max_generate: int = 800
+    repeat_penalty: float = 0.7
+    penalty_range: int = 10
+
+    @property
+    def ff(self) -> int:
+        return 4 * self.dim
+
+
+INDEXTTS_GPT = IndexTTSGPTConfig()
+# reduced copy for the CPU-side golden vectors and quick parity tests (same arithmetic, 3 layers of 8 heads)
+INDEXTTS_GPT_SMALL = IndexTTSGPTConfig(dim=512, layers=3, heads=8, text_vocab=300, mel_codes=130, start_mel=128, stop_mel=129,
+                                       text_pos=64, mel_pos=100, cond_rows=8, max_generate=96)

@@ -71,6 +71,51 @@ def ivgan_inputs(seed: int, rows: int, cfg: IndexTTSVocoderConfig = INDEXTTS_VOC
     return conds, cond_layer, hidden
 
 
+def igpt_state(seed: int = 555, cfg=None) -> dict:
+    """Synthetic weights of the IndexTTS GPT-2 acoustic model under the names graphs B-E read them by (reference:
+    IndexTTS/Export_IndexTTS.py:203-289; transformer blocks are Hugging Face GPT2Block: Conv1D weights are (in, out))."""
+    from .config import INDEXTTS_GPT
+    cfg = cfg or INDEXTTS_GPT
+    rng = np.random.default_rng(seed)
+    D, FF = cfg.dim, cfg.ff
+    sd = {
+        "text_embedding.weight": _n(rng, (cfg.text_vocab, D), 0.7),
+        "text_pos_embedding.emb.weight": _n(rng, (cfg.text_pos, D), 0.3),
+        "mel_embedding.weight": _n(rng, (cfg.mel_codes, D), 0.7),
+        "mel_pos_embedding.emb.weight": _n(rng, (cfg.mel_pos, D), 0.3),
+    }
+    for i in range(cfg.layers):
+        p = f"h.{i}."
+        sd[p + "ln_1.weight"] = (1.0 + _n(rng, (D,), 0.1)).astype(np.float32)
+        sd[p + "ln_1.bias"] = _n(rng, (D,), 0.05)
+        sd[p + "attn.c_attn.weight"] = _n(rng, (D, 3 * D), 1.6 / np.sqrt(D))
+        sd[p + "attn.c_attn.bias"] = _n(rng, (3 * D,), 0.05)
+        sd[p + "attn.c_proj.weight"] = _n(rng, (D, D), 0.5 / np.sqrt(D))
+        sd[p + "attn.c_proj.bias"] = _n(rng, (D,), 0.02)
+        sd[p + "ln_2.weight"] = (1.0 + _n(rng, (D,), 0.1)).astype(np.float32)
+        sd[p + "ln_2.bias"] = _n(rng, (D,), 0.05)
+        sd[p + "mlp.c_fc.weight"] = _n(rng, (D, FF), 1.0 / np.sqrt(D))
+        sd[p + "mlp.c_fc.bias"] = _n(rng, (FF,), 0.05)
+        sd[p + "mlp.c_proj.weight"] = _n(rng, (FF, D), 0.5 / np.sqrt(FF))
+        sd[p + "mlp.c_proj.bias"] = _n(rng, (D,), 0.02)
+    for nm in ("ln_f", "final_norm"):
+        sd[nm + ".weight"] = (1.0 + _n(rng, (D,), 0.1)).astype(np.float32)
+        sd[nm + ".bias"] = _n(rng, (D,), 0.05)
+    sd["mel_head.weight"] = _n(rng, (cfg.mel_codes, D), 2.0 / np.sqrt(D))
+    sd["mel_head.bias"] = _n(rng, (cfg.mel_codes,), 0.1)
+    return sd
+
+
+def igpt_inputs(seed: int, n_text: int, cfg=None):
+    """-> conds_latent (1, cond_rows, D) f32 (graph A's output, Export_IndexTTS.py:200), text_ids (1, n_text) i32."""
+    from .config import INDEXTTS_GPT
+    cfg = cfg or INDEXTTS_GPT
+    rng = np.random.default_rng(seed)
+    conds = _n(rng, (1, cfg.cond_rows, cfg.dim), 0.8)
+    ids = rng.integers(2, cfg.text_vocab, size=(1, n_text)).astype(np.int32)
+    return conds, ids
+
+
 def bigvgan_mel(seed: int, batch: int, frames: int, cfg: BigVGANConfig = BIGVGAN) -> np.ndarray:
     """Log-mel shaped input (B, n_mels, T): 2*randn-4 clipped to [ln 1e-5, 3]."""
     rng = np.random.default_rng(seed)
