@@ -68,6 +68,40 @@ int b200tts_indextts_vocoder_run(b200tts_engine* e, const float* hidden_host, in
                                  const float* cond_layer_host, int precision, int16_t* pcm_host, float* wave_host,
                                  int64_t* n_out);
 
+/* ---- IndexTTS GPT-2 acoustic model: graphs B-E (IndexTTS/Export_IndexTTS.py:203-289) and the greedy loop around them
+ * (IndexTTS/Inference_IndexTTS_ONNX.py:726-781). The KV cache stays on the device between calls.
+ * Tensors "igpt.<name>" must be loaded before the build: text_embedding.weight, text_pos_embedding.emb.weight,
+ * mel_embedding.weight, mel_pos_embedding.emb.weight, h.<i>.{ln_1,ln_2}.{weight,bias}, h.<i>.attn.{c_attn,c_proj}.{weight,bias},
+ * h.<i>.mlp.{c_fc,c_proj}.{weight,bias} (Hugging Face Conv1D layout (in, out), UNscaled: the build applies the export's
+ * head_dim^-0.25 q/k scaling, :250-255), ln_f.*, final_norm.*, mel_head.{weight,bias}, and "igpt.meta" = 8 floats
+ * [start_text, stop_text, start_mel, stop_mel, MAX_GENERATE_LENGTH, PENALITY_RANGE, REPEAT_PENALITY, layer-norm eps]. */
+int b200tts_indextts_gpt_build(b200tts_engine* e);
+/* -> model_dim, layers, heads, mel code count, KV capacity in rows (any pointer may be NULL) */
+int b200tts_indextts_gpt_info(b200tts_engine* e, int* dim, int* layers, int* heads, int* mel_codes, int* max_rows);
+/* graph B (IndexTTS_B, :203-214): text_ids (n_text) -> text_hidden_state (n_text + 2, dim): start / stop ids are added inside */
+int b200tts_indextts_gpt_text_embed(b200tts_engine* e, const int32_t* text_ids_host, int n_text, float* out_host);
+/* graph C (IndexTTS_C, :217-225): mel id, gen_len -> gpt_hidden_state (dim); the caller advances gen_len */
+int b200tts_indextts_gpt_mel_embed(b200tts_engine* e, int32_t mel_id, int64_t gen_len, float* out_host);
+/* graph E (IndexTTS_E.forward, :264-289), one call: hidden_state (ids_len, dim) appended after history_len cached rows
+ * (history_len must be the resident length, or 0 to start a sentence); attention_mask = the int8 flag (1 = causal among the
+ * new rows); repeat_penality (mel_codes). -> last_hidden_state (dim), max_logit_id, kv_seq_len = history_len + ids_len. */
+int b200tts_indextts_gpt_step(b200tts_engine* e, const float* hidden_host, int ids_len, int64_t history_len, int attention_mask,
+                              const float* repeat_penality_host, int precision, float* last_hidden_host, int32_t* max_logit_id,
+                              int64_t* kv_seq_len);
+/* out_key_<layer> (heads, 64, S) and out_value_<layer> (heads, S, 64) of the resident cache, S = resident rows */
+int b200tts_indextts_gpt_kv_read(b200tts_engine* e, int layer, float* key_host, float* value_host, int64_t* rows);
+/* One sentence with the whole loop on the device (graphs B, C, D, then E until the stop id or the limit
+ * min(max_new, MAX_GENERATE_LENGTH - prompt rows); max_new <= 0: no extra limit): conds_latent (cond_rows, dim), text ids
+ * -> ids_out (n), hidden_out (n, dim) = last_hidden_state of every call (what the reference concatenates for graph F).
+ * repeat_penality_inout (mel_codes, may be NULL = all ones): the reference never resets it between sentences. */
+int b200tts_indextts_gpt_generate(b200tts_engine* e, const float* conds_latent_host, int cond_rows, const int32_t* text_ids_host,
+                                  int n_text, int max_new, int precision, float* repeat_penality_inout_host, int32_t* ids_out_host,
+                                  float* hidden_out_host, int* n_out);
+/* same with every buffer on the device (ids_out / hidden_out sized for the limit) */
+int b200tts_indextts_gpt_generate_device(b200tts_engine* e, const float* conds_latent_dev, int cond_rows, const int32_t* text_ids_dev,
+                                         int n_text, int max_new, int precision, float* repeat_penality_inout_dev,
+                                         int32_t* ids_out_dev, float* hidden_out_dev, int* n_out);
+
 /* ---- F5-TTS sessions (F5_TTS/Export_F5.py:98-203, host loop F5-TTS-ONNX-Inference.py:247-311) ----------------
  * Tensors "dit.*" (EMA DiT state dict, Q/K pre-scaled), "vocos.*" (folded) and "f5.*" (export-time constants:
  * time_expand, delta_t, rope_cos/sin, text_pos, stft_basis, fbank, istft_basis, window_sum_inv) must be loaded. */

@@ -41,6 +41,14 @@ SIGNATURES = {
     "b200tts_bigvgan_run_device": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp]),
     "b200tts_indextts_vocoder_build": (_int, [_vp]),
     "b200tts_indextts_vocoder_run": (_int, [_vp, _vp, _int, _vp, _vp, _int, _vp, _vp, _vp]),
+    "b200tts_indextts_gpt_build": (_int, [_vp]),
+    "b200tts_indextts_gpt_info": (_int, [_vp, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32]),
+    "b200tts_indextts_gpt_text_embed": (_int, [_vp, _vp, _int, _vp]),
+    "b200tts_indextts_gpt_mel_embed": (_int, [_vp, ctypes.c_int32, ctypes.c_int64, _vp]),
+    "b200tts_indextts_gpt_step": (_int, [_vp, _vp, _int, ctypes.c_int64, _int, _vp, _int, _vp, _c_i32, _c_i64]),
+    "b200tts_indextts_gpt_kv_read": (_int, [_vp, _int, _vp, _vp, _c_i64]),
+    "b200tts_indextts_gpt_generate": (_int, [_vp, _vp, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _c_i32]),
+    "b200tts_indextts_gpt_generate_device": (_int, [_vp, _vp, _int, _vp, _int, _int, _int, _vp, _vp, _vp, _c_i32]),
     "b200tts_f5_build": (_int, [_vp]),
     "b200tts_f5_preprocess": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _vp, _c_i64]),
     "b200tts_f5_transformer": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _c_i32, _int, _int]),
@@ -184,6 +192,83 @@ class Engine:
                                                           _ptr(wave), ctypes.byref(got)), "indextts_vocoder_run")
         assert got.value == n_out, (got.value, n_out)
         return (pcm, wave) if return_wave else pcm
+
+    # -- IndexTTS GPT-2 acoustic model (graphs B-E) -----------------------------------------------
+    def indextts_gpt_build(self):
+        self._check(self.lib.b200tts_indextts_gpt_build(self.handle), "indextts_gpt_build")
+
+    def indextts_gpt_info(self) -> dict:
+        v = [ctypes.c_int32(0) for _ in range(5)]
+        self._check(self.lib.b200tts_indextts_gpt_info(self.handle, *[ctypes.byref(x) for x in v]), "indextts_gpt_info")
+        return dict(zip(("dim", "layers", "heads", "mel_codes", "max_rows"), (x.value for x in v)))
+
+    def indextts_gpt_text_embed(self, text_ids):
+        """graph B: text_ids (1, n) int32 -> text_hidden_state (1, n + 2, dim)."""
+        ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
+        D = self.indextts_gpt_info()["dim"]
+        out = np.empty((1, ids.size + 2, D), dtype=np.float32)
+        self._check(self.lib.b200tts_indextts_gpt_text_embed(self.handle, _ptr(ids), int(ids.size), _ptr(out)), "indextts_gpt_text_embed")
+        return out
+
+    def indextts_gpt_mel_embed(self, mel_id: int, gen_len: int):
+        """graph C: -> (gpt_hidden_state (1, 1, dim), gen_len + 1)."""
+        D = self.indextts_gpt_info()["dim"]
+        out = np.empty((1, 1, D), dtype=np.float32)
+        self._check(self.lib.b200tts_indextts_gpt_mel_embed(self.handle, int(mel_id), int(gen_len), _ptr(out)), "indextts_gpt_mel_embed")
+        return out, int(gen_len) + 1
+
+    def indextts_gpt_step(self, hidden, history_len: int, attention_mask: int, repeat_penality, precision=F32):
+        """graph E on the resident KV cache -> (last_hidden_state (1, dim), max_logit_id (1, 1) int32, kv_seq_len)."""
+        hidden = _f32(hidden)
+        D = hidden.shape[-1]
+        rows = hidden.size // D
+        pen = _f32(np.asarray(repeat_penality).reshape(-1))
+        last = np.empty((1, D), dtype=np.float32)
+        mid = ctypes.c_int32(0)
+        kv = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_indextts_gpt_step(self.handle, _ptr(hidden), int(rows), int(history_len), int(attention_mask),
+                                                       _ptr(pen), int(precision), _ptr(last), ctypes.byref(mid), ctypes.byref(kv)),
+                    "indextts_gpt_step")
+        return last, np.array([[mid.value]], dtype=np.int32), int(kv.value)
+
+    def indextts_gpt_kv_read(self, layer: int):
+        """-> (out_key_<layer> (H, 64, S), out_value_<layer> (H, S, 64)) of the resident cache."""
+        info = self.indextts_gpt_info()
+        rows = ctypes.c_int64(0)
+        self._check(self.lib.b200tts_indextts_gpt_kv_read(self.handle, int(layer), None, None, ctypes.byref(rows)), "indextts_gpt_kv_read")
+        S, H = int(rows.value), info["heads"]
+        key = np.zeros((H, 64, S), dtype=np.float32)
+        val = np.zeros((H, S, 64), dtype=np.float32)
+        if S:
+            self._check(self.lib.b200tts_indextts_gpt_kv_read(self.handle, int(layer), _ptr(key), _ptr(val), ctypes.byref(rows)),
+                        "indextts_gpt_kv_read")
+        return key, val
+
+    def indextts_gpt_generate(self, conds_latent, text_ids, max_new: int = 0, precision=BF16, penalty=None):
+        """One sentence, loop on the device -> (ids (n,) int32, hidden (n, dim) f32[, penalty (1, mel_codes) when one was passed])."""
+        info = self.indextts_gpt_info()
+        D = info["dim"]
+        conds = _f32(np.asarray(conds_latent).reshape(-1, D))
+        ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
+        cap = info["max_rows"] + 1
+        out_ids = np.zeros((cap,), dtype=np.int32)
+        out_hid = np.zeros((cap, D), dtype=np.float32)
+        pen = None if penalty is None else np.ascontiguousarray(np.asarray(penalty, dtype=np.float32).reshape(1, -1)).copy()
+        n = ctypes.c_int32(0)
+        self._check(self.lib.b200tts_indextts_gpt_generate(self.handle, _ptr(conds), int(conds.shape[0]), _ptr(ids), int(ids.size),
+                                                           int(max_new), int(precision), _ptr(pen), _ptr(out_ids), _ptr(out_hid),
+                                                           ctypes.byref(n)), "indextts_gpt_generate")
+        res = (out_ids[:n.value].copy(), out_hid[:n.value].copy())
+        return res + (pen,) if pen is not None else res
+
+    def indextts_gpt_generate_device(self, conds_ptr, cond_rows, ids_ptr, n_text, ids_out_ptr, hidden_out_ptr, max_new=0, precision=BF16,
+                                     penalty_ptr=0) -> int:
+        n = ctypes.c_int32(0)
+        self._check(self.lib.b200tts_indextts_gpt_generate_device(self.handle, _vp(conds_ptr), int(cond_rows), _vp(ids_ptr), int(n_text),
+                                                                  int(max_new), int(precision), _vp(penalty_ptr) if penalty_ptr else None,
+                                                                  _vp(ids_out_ptr), _vp(hidden_out_ptr), ctypes.byref(n)),
+                    "indextts_gpt_generate_device")
+        return int(n.value)
 
     # -- F5-TTS ----------------------------------------------------------------------------------
     def f5_build(self):

@@ -13,6 +13,7 @@
 #include "bigvgan.cuh"
 #include "engine.cuh"
 #include "f5.cuh"
+#include "gpt2.cuh"
 #include "layout.cuh"
 #include "rowgemm.cuh"
 #include "rowgemm_tc.cuh"
@@ -28,6 +29,7 @@ Engine::~Engine() {
   if (bigvgan) bigvgan_free(bigvgan);
   if (ivgan) bigvgan_free(ivgan);
   if (f5) f5_free(f5);
+  if (igpt) gpt_free(igpt);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 }  // namespace b200tts
@@ -218,6 +220,146 @@ int b200tts_indextts_vocoder_run(b200tts_engine* e, const float* hidden_host, in
     if (wave_host) B2_CUDA(cudaMemcpyAsync(wave_host, d_wave, n_samples * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *n_out = n_samples;
+  });
+}
+
+int b200tts_indextts_gpt_build(b200tts_engine* e) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    if (E.igpt) { gpt_free(E.igpt); E.igpt = nullptr; }
+    E.graphs.clear();
+    E.igpt = gpt_build(E);
+  });
+}
+
+int b200tts_indextts_gpt_info(b200tts_engine* e, int* dim, int* layers, int* heads, int* mel_codes, int* max_rows) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    if (dim) *dim = gpt_dim(*E.igpt);
+    if (layers) *layers = gpt_layers(*E.igpt);
+    if (heads) *heads = gpt_heads(*E.igpt);
+    if (mel_codes) *mel_codes = gpt_mel_codes(*E.igpt);
+    if (max_rows) *max_rows = gpt_max_rows(*E.igpt);
+  });
+}
+
+int b200tts_indextts_gpt_text_embed(b200tts_engine* e, const int32_t* text_ids_host, int n_text, float* out_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    B2_CHECK(out_host && n_text >= 0 && (text_ids_host || n_text == 0), "gpt_text_embed: null buffer");
+    const int D = gpt_dim(*E.igpt);
+    cudaStream_t s = E.stream;
+    E.io_i32.reserve((size_t)n_text + 1);
+    E.io_f32a.reserve((size_t)(n_text + 2) * D);
+    if (n_text) B2_CUDA(cudaMemcpyAsync(E.io_i32.p, text_ids_host, (size_t)n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    gpt_text_embed(E, E.io_i32.p, n_text, E.io_f32a.p);
+    B2_CUDA(cudaMemcpyAsync(out_host, E.io_f32a.p, (size_t)(n_text + 2) * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_indextts_gpt_mel_embed(b200tts_engine* e, int32_t mel_id, int64_t gen_len, float* out_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    B2_CHECK(out_host != nullptr, "gpt_mel_embed: null buffer");
+    const int D = gpt_dim(*E.igpt);
+    cudaStream_t s = E.stream;
+    E.io_i32.reserve(1);
+    E.io_f32a.reserve((size_t)D);
+    B2_CUDA(cudaMemcpyAsync(E.io_i32.p, &mel_id, sizeof(int), cudaMemcpyHostToDevice, s));
+    gpt_mel_embed(E, E.io_i32.p, (int)gen_len, E.io_f32a.p);
+    B2_CUDA(cudaMemcpyAsync(out_host, E.io_f32a.p, (size_t)D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_indextts_gpt_step(b200tts_engine* e, const float* hidden_host, int ids_len, int64_t history_len, int attention_mask,
+                              const float* repeat_penality_host, int precision, float* last_hidden_host, int32_t* max_logit_id,
+                              int64_t* kv_seq_len) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    B2_CHECK(hidden_host && repeat_penality_host && last_hidden_host && max_logit_id && kv_seq_len, "gpt_step: null buffer");
+    B2_CHECK(ids_len >= 1 && history_len >= 0 && history_len < (1 << 20), "gpt_step: bad sizes");
+    const int D = gpt_dim(*E.igpt), Vm = gpt_mel_codes(*E.igpt);
+    cudaStream_t s = E.stream;
+    // staging: [hidden rows | penalty | last hidden]
+    E.io_f32a.reserve((size_t)ids_len * D + Vm + D);
+    E.io_i32.reserve(1);
+    float* d_h = E.io_f32a.p; float* d_pen = d_h + (size_t)ids_len * D; float* d_last = d_pen + Vm;
+    B2_CUDA(cudaMemcpyAsync(d_h, hidden_host, (size_t)ids_len * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_pen, repeat_penality_host, (size_t)Vm * sizeof(float), cudaMemcpyHostToDevice, s));
+    gpt_step(E, d_h, ids_len, (int)history_len, attention_mask, d_pen, precision, d_last, E.io_i32.p);
+    B2_CUDA(cudaMemcpyAsync(last_hidden_host, d_last, (size_t)D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(max_logit_id, E.io_i32.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *kv_seq_len = history_len + ids_len;
+  });
+}
+
+int b200tts_indextts_gpt_kv_read(b200tts_engine* e, int layer, float* key_host, float* value_host, int64_t* rows) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    const int S = gpt_resident_rows(*E.igpt), H = gpt_heads(*E.igpt);
+    if (rows) *rows = S;
+    if (S == 0 || (!key_host && !value_host)) return;
+    B2_CHECK(key_host && value_host, "gpt_kv_read: pass both buffers");
+    const size_t n = (size_t)H * S * 64;
+    cudaStream_t s = E.stream;
+    E.io_f32b.reserve(2 * n);
+    gpt_kv_export(E, layer, E.io_f32b.p, E.io_f32b.p + n);
+    B2_CUDA(cudaMemcpyAsync(key_host, E.io_f32b.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(value_host, E.io_f32b.p + n, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_indextts_gpt_generate_device(b200tts_engine* e, const float* conds_latent_dev, int cond_rows, const int32_t* text_ids_dev,
+                                         int n_text, int max_new, int precision, float* repeat_penality_inout_dev,
+                                         int32_t* ids_out_dev, float* hidden_out_dev, int* n_out) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    B2_CHECK((conds_latent_dev || cond_rows == 0) && (text_ids_dev || n_text == 0) && ids_out_dev && hidden_out_dev && n_out,
+             "gpt_generate: null buffer");
+    *n_out = gpt_generate(E, conds_latent_dev, cond_rows, text_ids_dev, n_text, max_new, precision, repeat_penality_inout_dev,
+                          ids_out_dev, hidden_out_dev);
+    B2_CUDA(cudaStreamSynchronize(E.stream));
+  });
+}
+
+int b200tts_indextts_gpt_generate(b200tts_engine* e, const float* conds_latent_host, int cond_rows, const int32_t* text_ids_host,
+                                  int n_text, int max_new, int precision, float* repeat_penality_inout_host, int32_t* ids_out_host,
+                                  float* hidden_out_host, int* n_out) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(E.igpt != nullptr, "IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+    B2_CHECK((conds_latent_host || cond_rows == 0) && (text_ids_host || n_text == 0) && ids_out_host && hidden_out_host && n_out,
+             "gpt_generate: null buffer");
+    B2_CHECK(cond_rows >= 0 && n_text >= 0, "gpt_generate: bad sizes");
+    const int D = gpt_dim(*E.igpt), Vm = gpt_mel_codes(*E.igpt), cap = gpt_max_rows(*E.igpt);
+    cudaStream_t s = E.stream;
+    // staging: fp32 [conds | penalty | hidden_out (cap + 1 rows)], int32 [text ids | ids_out (cap + 1)]
+    E.io_f32a.reserve((size_t)cond_rows * D + Vm + (size_t)(cap + 1) * D);
+    E.io_i32.reserve((size_t)n_text + cap + 2);
+    float* d_c = E.io_f32a.p; float* d_pen = d_c + (size_t)cond_rows * D; float* d_hid = d_pen + Vm;
+    int* d_txt = E.io_i32.p; int* d_ids = d_txt + n_text + 1;
+    if (cond_rows) B2_CUDA(cudaMemcpyAsync(d_c, conds_latent_host, (size_t)cond_rows * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (n_text) B2_CUDA(cudaMemcpyAsync(d_txt, text_ids_host, (size_t)n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (repeat_penality_inout_host)
+      B2_CUDA(cudaMemcpyAsync(d_pen, repeat_penality_inout_host, (size_t)Vm * sizeof(float), cudaMemcpyHostToDevice, s));
+    const int n = gpt_generate(E, d_c, cond_rows, d_txt, n_text, max_new, precision, repeat_penality_inout_host ? d_pen : nullptr,
+                               d_ids, d_hid);
+    B2_CUDA(cudaMemcpyAsync(ids_out_host, d_ids, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaMemcpyAsync(hidden_out_host, d_hid, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (repeat_penality_inout_host)
+      B2_CUDA(cudaMemcpyAsync(repeat_penality_inout_host, d_pen, (size_t)Vm * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *n_out = n;
   });
 }
 

@@ -82,6 +82,7 @@ struct GraphCache {
 
 struct BigVGANModel;
 struct F5Model;
+struct GptModel;
 
 struct Engine {
   int device = 0;
@@ -92,10 +93,12 @@ struct Engine {
   GraphCache graphs;
   DevBuf<float> io_f32a, io_f32b;          // persistent staging of the host-pointer entry points (stable addresses for graphs)
   DevBuf<int16_t> io_i16;
+  DevBuf<int> io_i32;
   std::string prof_report;                 // last JSON report (owned here so the C ABI can hand out a pointer)
   BigVGANModel* bigvgan = nullptr;         // owned; freed by bigvgan_free / f5_free in ~Engine (api.cu)
   BigVGANModel* ivgan = nullptr;           // the IndexTTS_F vocoder (same generator family, see bigvgan.cuh)
   F5Model* f5 = nullptr;
+  GptModel* igpt = nullptr;                // IndexTTS GPT-2 acoustic model (gpt2.cuh)
 
   const Tensor& weight(const std::string& name) const {
     auto it = weights.find(name);

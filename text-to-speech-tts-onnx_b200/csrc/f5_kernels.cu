@@ -302,6 +302,10 @@ void layernorm_affine(const float* x, const float* w, const float* b, float* out
   launch_rownorm<1, float>(x, w, b, out, R, D, eps, s);
   LAUNCHED();
 }
+void layernorm_affine_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* out, int R, int D, float eps, cudaStream_t s) {
+  launch_rownorm<1, __nv_bfloat16>(x, w, b, out, R, D, eps, s);
+  LAUNCHED();
+}
 void l2_norm_affine(const float* x, const float* w, const float* b, float* out, int R, int C, cudaStream_t s) {
   l2norm_kernel<<<ceil_div(R, 8), 256, 0, s>>>(x, w, b, out, R, C);
   LAUNCHED();

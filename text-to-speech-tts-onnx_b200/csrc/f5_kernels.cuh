@@ -1,6 +1,7 @@
 // Element-wise / reduction kernels of the F5-TTS graphs (everything that is not a GEMM or attention).
 // All tensors are row-major (rows = time, columns = channels), fp32 unless noted.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -11,6 +12,7 @@ namespace b200tts {
 void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s);
 // nn.LayerNorm(D, eps) with affine (text ConvNeXtV2 block, modules.py:248)
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s);
+void layernorm_affine_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* out, int R, int D, float eps, cudaStream_t s);
 // Vocos "LayerNorm": w * x / ||x||_2 + b per row, w already x sqrt(C) (vocos/models.py:80,83; modules.py:46)
 void l2_norm_affine(const float* x, const float* w, const float* b, float* out, int R, int C, cudaStream_t s);
 // depthwise Conv1d k=7 pad 3 on (B, L, C): w [7][C], bias [C]

@@ -1,0 +1,778 @@
+// IndexTTS GPT-2 acoustic model on the device (reference: IndexTTS/Export_IndexTTS.py:203-289, graphs B-E; host loop
+// IndexTTS/Inference_IndexTTS_ONNX.py:726-781).
+//
+// Two regimes share one KV cache:
+//   * prefill (the first call of a sentence: conditioning latents + text rows + start token, ~100-250 rows): the row-GEMMs
+//     of the DiT path (rowgemm_f32 / tcgen05 rowgemm_tc) with LayerNorm, attention and cache-scatter kernels around them;
+//   * decode (one row per call, up to MAX_GENERATE_LENGTH calls): every projection is a matrix-VECTOR product whose cost is
+//     the weight bytes it streams (24 layers x 12 D^2 + mel_head = 0.47 G parameters per token) -> HBM-bound. One warp per
+//     output row, 16-byte loads, the LayerNorm that precedes a projection fused into its prologue (each CTA renormalises the
+//     D-vector it is about to multiply), bias / gelu_new / residual / penalty in the epilogue. The loop state (cache length,
+//     position, produced ids, penalty vector and its release window, stop flag) lives in device memory so that a decode step
+//     is the SAME kernel sequence every time: it is captured once into a CUDA graph and replayed; the host looks at the stop
+//     flag every few steps only.
+// Layouts: hidden rows (rows, D) fp32; K and V caches [layer][head][row][64] fp32 (the reference keeps K transposed as
+// (H, 64, S), gpt_kv_export produces that view); projection weights [N][K] (K contiguous) fp32 or bf16.
+#include "gpt2.cuh"
+
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+#include "f5_kernels.cuh"
+#include "layout.cuh"
+#include "rowgemm.cuh"
+#include "rowgemm_tc.cuh"
+
+namespace b200tts {
+
+namespace {
+
+constexpr int HD = 64;
+// device loop state
+enum : int { ST_KV = 0, ST_GEN = 1, ST_N = 2, ST_STOP = 3, ST_RESET = 4, ST_LIMIT = 5, ST_WORDS = 8 };
+
+struct LoopConst {
+  int start_mel, stop_mel, range;
+  float repeat_penalty;
+};
+
+}  // namespace
+
+struct GptLayer {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *o_b, *fc_b, *p_b;
+  const float *o_kn, *fc_kn, *p_kn;          // Hugging Face Conv1D weights are (in, out) = [K][N]: the fp32 GEMM layout as is
+  DevBuf<float> qkv_b;                       // q and k thirds scaled by 64^-0.25 (Export_IndexTTS.py:250-255)
+  DevBuf<float> qkv_kn;                      // [D][3D], scaled, for the fp32 prefill GEMM
+  DevBuf<float> qkv_nk, o_nk, fc_nk, p_nk;   // [N][K] fp32: decode GEMV of the fp32 engine (built on first use)
+  TcWeight qkv_tc, o_tc, fc_tc, p_tc;        // [N][K] bf16: prefill GEMM and decode GEMV of the bf16 engine
+};
+
+struct GptModel {
+  int D = 0, L = 0, H = 0, FF = 0, Vm = 0, Vt = 0, Pt = 0, Pm = 0, S_max = 0;
+  float eps = 1e-5f;
+  LoopConst lc{};
+  int start_text = 0, stop_text = 1;
+  const float *text_emb, *text_pos, *mel_emb, *mel_pos, *lnf_w, *lnf_b, *fn_w, *fn_b, *head_b;
+  const float* head_nk;                      // mel_head is an nn.Linear: (out, in) = [N][K] already
+  TcWeight head_tc;
+  std::vector<GptLayer> layers;
+  bool f32_ready = false, bf16_ready = false;
+  // cache + loop state
+  DevBuf<float> kc, vc;                      // [L][H][S_max][64]
+  DevBuf<int> state, ids;                    // ST_WORDS ; produced ids [S_max + 1]
+  DevBuf<float> penalty, hid_save;           // [Vm] ; [S_max + 1][D]
+  int resident = 0;                          // host mirror of ST_KV for the per-call (session) entry points
+  // workspaces
+  DevBuf<float> hp, nb32, qkv32, att32, ff32, hcur, logits;
+  DevBuf<__nv_bfloat16> nb16, att16, ff16;
+  DevBuf<int> idbuf;
+  int* h_state = nullptr;                    // pinned
+};
+
+namespace {
+
+GptModel& model(Engine& e) {
+  if (!e.igpt) fail("IndexTTS GPT weights are not built (call b200tts_indextts_gpt_build)");
+  return *e.igpt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum over 256 threads (red: 8 floats of shared memory)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum_f(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ float gelu_new_f(float v) {      // Hugging Face NewGELUActivation (GPT2MLP.act)
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * v * (1.0f + tanhf(k0 * (v + k1 * v * v * v)));
+}
+
+template <typename WT> struct WVec;
+template <> struct WVec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&w)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  }
+};
+template <> struct WVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&w)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w[2 * i] = __uint_as_float(u[i] << 16);
+      w[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+};
+
+struct GemvArgs {
+  const void* W; long ldw;                    // [N][ldw]
+  const float* bias;                          // [N] or null
+  const float* x; int K, N;
+  const float *ln_w, *ln_b, *ln2_w, *ln2_b;   // PRE >= 1: LayerNorm(x); PRE == 2: a second LayerNorm on top (ln_f, final_norm)
+  float eps;
+  const float* res;                           // [N] or null: y += res
+  const float* mul;                           // [N] or null: y *= mul   (repeat penalty)
+  float* y;
+  float* save; const int* state;              // PRE == 2: block 0 stores the FIRST LayerNorm's output at save[state[ST_N]][K]
+  int act;                                    // 0 none, 1 gelu_new
+};
+
+// y[n] = epilogue(W[n][:] . pre(x) + bias[n]); one warp per output row, 8 rows per CTA.
+template <typename WT, int PRE>
+__global__ void __launch_bounds__(256) gemv_kernel(const GemvArgs a) {
+  extern __shared__ float xs[];               // K floats
+  __shared__ float red[8];
+  pdl_trigger();
+  pdl_wait();
+  const int K = a.K, tid = threadIdx.x;
+  for (int k = tid; k < K; k += 256) xs[k] = a.x[k];
+  if constexpr (PRE >= 1) {
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < PRE; ++pass) {
+      const float* lw = pass == 0 ? a.ln_w : a.ln2_w;
+      const float* lb = pass == 0 ? a.ln_b : a.ln2_b;
+      float s = 0.f;
+      for (int k = tid; k < K; k += 256) s += xs[k];
+      const float mean = block_sum(s, red) / (float)K;
+      float q = 0.f;
+      for (int k = tid; k < K; k += 256) { const float d = xs[k] - mean; q += d * d; }
+      const float rstd = 1.0f / sqrtf(block_sum(q, red) / (float)K + a.eps);
+      for (int k = tid; k < K; k += 256) xs[k] = (xs[k] - mean) * rstd * lw[k] + lb[k];
+      __syncthreads();
+      if (PRE == 2 && pass == 0 && blockIdx.x == 0 && a.save != nullptr) {
+        float* dst = a.save + (long)a.state[ST_N] * K;
+        for (int k = tid; k < K; k += 256) dst[k] = xs[k];
+      }
+    }
+  } else {
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= a.N) return;
+  constexpr int V = WVec<WT>::N;
+  const WT* wr = reinterpret_cast<const WT*>(a.W) + (long)n * a.ldw;
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 5
+  for (int k0 = lane * V; k0 < K; k0 += 32 * V) {
+    float w[V];
+    WVec<WT>::load(wr + k0, w);
+    const float4* xv = reinterpret_cast<const float4*>(xs + k0);
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) {
+      const float4 x4 = xv[i];
+      acc0 = fmaf(w[4 * i], x4.x, acc0);
+      acc1 = fmaf(w[4 * i + 1], x4.y, acc1);
+      acc0 = fmaf(w[4 * i + 2], x4.z, acc0);
+      acc1 = fmaf(w[4 * i + 3], x4.w, acc1);
+    }
+  }
+  float v = warp_sum_f(acc0 + acc1);
+  if (lane == 0) {
+    if (a.bias) v += a.bias[n];
+    if (a.act == 1) v = gelu_new_f(v);
+    if (a.res) v += a.res[n];
+    if (a.mul) v *= a.mul[n];
+    a.y[n] = v;
+  }
+}
+
+// Attention of `rows` new query rows against the cache. grid (H, rows), 128 threads.
+// qkv [rows][3D] fp32 (q | k | v thirds, head-major inside a third). The cache already holds the keys / values of the new rows
+// when rows > 1 (kv_scatter_kernel); for rows == 1 this CTA appends its own head's row first. Key range of row r: causal ->
+// [0, hist + r], else [0, hist + rows). The reference adds -128 to masked scores instead of removing them
+// (Export_IndexTTS.py:245,268); exp(-128 - max) underflows to exactly 0 in fp32, so skipping them is the same arithmetic.
+template <typename OutT>
+__global__ void __launch_bounds__(128) gpt_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                                       const int* __restrict__ state, int S_max, int D, int H, int causal,
+                                                       OutT* __restrict__ out) {
+  extern __shared__ float sm[];               // scores [S_max] | q [64] | part [2][64] | red [8]
+  pdl_trigger();
+  pdl_wait();
+  float* sc = sm;
+  float* qs = sm + S_max;
+  float* part = qs + HD;
+  float* red = part + 2 * HD;
+  const int h = blockIdx.x, r = blockIdx.y, rows = gridDim.y, tid = threadIdx.x;
+  const int hist = state[ST_KV];
+  const float* qrow = qkv + (long)r * 3 * D + h * HD;
+  float* kh = kc + (long)h * S_max * HD;
+  float* vh = vc + (long)h * S_max * HD;
+  if (tid < HD) qs[tid] = qrow[tid];
+  if (rows == 1) {                             // decode: append this head's new key / value row
+    if (tid < HD) kh[(long)hist * HD + tid] = qrow[D + tid];
+    else vh[(long)hist * HD + tid - HD] = qrow[2 * D + tid - HD];
+  }
+  __syncthreads();
+  const int nk = causal ? hist + r + 1 : hist + rows;
+  // scores: one key per thread
+  float q[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) q[d] = qs[d];
+  float mx = -3.0e38f;
+  for (int j = tid; j < nk; j += 128) {
+    const float4* kr = reinterpret_cast<const float4*>(kh + (long)j * HD);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 k4 = kr[i];
+      s0 = fmaf(q[4 * i], k4.x, s0); s1 = fmaf(q[4 * i + 1], k4.y, s1);
+      s0 = fmaf(q[4 * i + 2], k4.z, s0); s1 = fmaf(q[4 * i + 3], k4.w, s1);
+    }
+    const float s = s0 + s1;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float sum = 0.f;
+  for (int j = tid; j < nk; j += 128) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  sum = warp_sum_f(sum);
+  if ((tid & 31) == 0) red[4 + (tid >> 5)] = sum;
+  __syncthreads();
+  const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
+  // out[d] = sum_j p_j v[j][d]: two halves of the keys, 64 threads each
+  const int d = tid & (HD - 1), half = tid >> 6;
+  float o0 = 0.f, o1 = 0.f;
+  int j = half;
+  for (; j + 2 < nk; j += 4) {
+    o0 = fmaf(sc[j], vh[(long)j * HD + d], o0);
+    o1 = fmaf(sc[j + 2], vh[(long)(j + 2) * HD + d], o1);
+  }
+  for (; j < nk; j += 2) o0 = fmaf(sc[j], vh[(long)j * HD + d], o0);
+  part[half * HD + d] = o0 + o1;
+  __syncthreads();
+  if (tid < HD) {
+    const float v = (part[tid] + part[HD + tid]) * inv;
+    if constexpr (sizeof(OutT) == 4) out[(long)r * D + h * HD + tid] = v;
+    else out[(long)r * D + h * HD + tid] = __float2bfloat16(v);
+  }
+}
+
+// new rows of k / v (qkv thirds 2 and 3) -> cache rows [hist, hist + rows) of one layer
+__global__ void kv_scatter_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                  const int* __restrict__ state, int rows, int S_max, int D) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * D) return;
+  const int r = (int)(i / D), c = (int)(i - (long)r * D);
+  const int h = c / HD, d = c - h * HD;
+  const int hist = state[ST_KV];
+  const long dst = ((long)h * S_max + hist + r) * HD + d;
+  kc[dst] = qkv[(long)r * 3 * D + D + c];
+  vc[dst] = qkv[(long)r * 3 * D + 2 * D + c];
+}
+
+// argmax (first maximum, as torch.argmax) + the host loop's bookkeeping (Inference_IndexTTS_ONNX.py:757-781):
+// record the id, advance the cache length by `rows`, stop on the stop id, else update the penalty window and write the next
+// call's hidden row  mel_embedding[id] + mel_pos_embedding[gen_len]  (graph C).
+__global__ void __launch_bounds__(1024) gpt_pick_kernel(const float* __restrict__ logits, int Vm, int* __restrict__ state,
+                                                        int* __restrict__ ids, float* __restrict__ penalty,
+                                                        const float* __restrict__ mel_emb, const float* __restrict__ mel_pos,
+                                                        float* __restrict__ hcur, int D, int rows, LoopConst lc, int bookkeeping,
+                                                        int* __restrict__ id_out) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  __shared__ int s_tok, s_go, s_gen;
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  float best = -3.0e38f; int idx = 0x7fffffff;
+  for (int n = tid; n < Vm; n += 1024) {
+    const float v = logits[n];
+    if (v > best) { best = v; idx = n; }       // ascending n per thread: keeps the first maximum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if ((tid & 31) == 0) { bv[tid >> 5] = best; bi[tid >> 5] = idx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 32; ++w)
+      if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+    s_tok = idx; s_go = 0; s_gen = 0;
+    if (id_out) *id_out = idx;
+    if (bookkeeping && !state[ST_STOP]) {
+      const int n = state[ST_N];
+      ids[n] = idx;
+      state[ST_N] = n + 1;
+      state[ST_KV] += rows;
+      if (idx == lc.stop_mel) {
+        state[ST_STOP] = 1;
+      } else {
+        penalty[idx] = lc.repeat_penalty;
+        const int rs = state[ST_RESET];
+        if (n + 1 > lc.range && ids[rs] != idx) { penalty[ids[rs]] = 1.0f; state[ST_RESET] = rs + 1; }
+        s_gen = state[ST_GEN];
+        state[ST_GEN] = s_gen + 1;
+        s_go = 1;
+        if (n + 1 >= state[ST_LIMIT]) state[ST_STOP] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_go) {
+    const float* e = mel_emb + (long)s_tok * D;
+    const float* p = mel_pos + (long)s_gen * D;
+    for (int k = tid; k < D; k += 1024) hcur[k] = e[k] + p[k];
+  }
+}
+
+// rows of  table[id] + pos[pos0 + r]  (graphs B and C; ids on the device). wrap != 0: ids are [start, ids..., stop]
+__global__ void gpt_embed_kernel(const int* __restrict__ ids, int n_ids, const float* __restrict__ table, const float* __restrict__ pos,
+                                 int pos0, float* __restrict__ out, int rows, int D, int wrap, int start_id, int stop_id, int vocab) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)rows * D) return;
+  const int r = (int)(i / D), c = (int)(i - (long)r * D);
+  int id;
+  if (wrap) id = r == 0 ? start_id : (r == rows - 1 ? stop_id : ids[r - 1]);
+  else id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  out[i] = table[(long)id * D + c] + pos[(long)(pos0 + r) * D + c];
+}
+
+__global__ void fill_kernel(float* x, long n, float v) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+__global__ void scale_kernel(float* x, long n, float s) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+// in [R][C] -> out [C][R]
+__global__ void transpose32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < C) ? in[(long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(long)c * R + r] = t[threadIdx.x][i];
+  }
+}
+// cache [H][S_max][64] -> key (H, 64, S), value (H, S, 64)
+__global__ void kv_export_kernel(const float* __restrict__ kc, const float* __restrict__ vc, float* __restrict__ key,
+                                 float* __restrict__ value, int H, int S, int S_max) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)H * S * HD) return;
+  const int h = (int)(i / ((long)S * HD));
+  const int rem = (int)(i - (long)h * S * HD);
+  const int s = rem / HD, d = rem - s * HD;
+  const long src = ((long)h * S_max + s) * HD + d;
+  value[i] = vc[src];
+  key[((long)h * HD + d) * S + s] = kc[src];
+}
+
+#define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
+
+void transpose_to(const float* in, float* out, int R, int C, cudaStream_t s) {
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+  transpose32_kernel<<<grid, block, 0, s>>>(in, out, R, C);
+  B2_LAUNCH_CHECK();
+}
+
+const float* W(Engine& e, const std::string& name, long expect) {
+  const Tensor& t = e.weight("igpt." + name);
+  B2_CHECK(t.numel() == expect, "igpt." + name + ": unexpected size");
+  return t.data.p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight layouts
+// ---------------------------------------------------------------------------------------------------------------------
+void prepare(Engine& e, GptModel& m, int precision) {
+  const bool fast = precision == PREC_BF16;
+  if (fast ? m.bf16_ready : m.f32_ready) return;
+  cudaStream_t s = e.stream;
+  const int D = m.D, FF = m.FF;
+  DevBuf<float> tmp;
+  if (fast) tmp.alloc((size_t)FF * D);
+  for (int i = 0; i < m.L; ++i) {
+    GptLayer& Ly = m.layers[i];
+    struct Job { const float* kn; int K, N; DevBuf<float>* nk; TcWeight* tc; };
+    const Job jobs[4] = {{Ly.qkv_kn.p, D, 3 * D, &Ly.qkv_nk, &Ly.qkv_tc}, {Ly.o_kn, D, D, &Ly.o_nk, &Ly.o_tc},
+                         {Ly.fc_kn, D, FF, &Ly.fc_nk, &Ly.fc_tc}, {Ly.p_kn, FF, D, &Ly.p_nk, &Ly.p_tc}};
+    for (const Job& j : jobs) {
+      if (fast) {
+        transpose_to(j.kn, tmp.p, j.K, j.N, s);                       // [K][N] -> [N][K]
+        tc_weight_from_f32(*j.tc, tmp.p, 1, 1, j.N, j.K, s);
+      } else {
+        j.nk->alloc((size_t)j.N * j.K);
+        transpose_to(j.kn, j.nk->p, j.K, j.N, s);
+      }
+    }
+  }
+  if (fast) tc_weight_from_f32(m.head_tc, m.head_nk, 1, 1, m.Vm, D, s);
+  B2_CUDA(cudaStreamSynchronize(s));
+  (fast ? m.bf16_ready : m.f32_ready) = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// one call of graph E on the resident cache
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename WT, int PRE>
+void gemv(Engine& e, const char* tag, GemvArgs a) {
+  B2_CHECK(a.K % 8 == 0 && a.ldw % 8 == 0 && a.K * sizeof(float) <= 48 * 1024, "gemv: K must be a multiple of 8 and fit shared memory");
+  ProfScope ps(e.prof, tag, e.stream);
+  launch_pdl(gemv_kernel<WT, PRE>, dim3(ceil_div(a.N, 8)), dim3(256), (size_t)a.K * sizeof(float), e.stream, a);
+  LAUNCHED();
+}
+
+template <typename OutT>
+void attention(Engine& e, GptModel& m, int layer, const float* qkv, int rows, int causal, OutT* out) {
+  cudaStream_t s = e.stream;
+  float* kc = m.kc.p + (size_t)layer * m.H * m.S_max * HD;
+  float* vc = m.vc.p + (size_t)layer * m.H * m.S_max * HD;
+  if (rows > 1) {
+    ProfScope ps(e.prof, "igpt.kv_scatter", s);
+    kv_scatter_kernel<<<ceil_div((long)rows * m.D, 256), 256, 0, s>>>(qkv, kc, vc, m.state.p, rows, m.S_max, m.D);
+    LAUNCHED();
+  }
+  const size_t smem = (size_t)(m.S_max + HD + 2 * HD + 8) * sizeof(float);
+  ProfScope ps(e.prof, "igpt.attention", s);
+  launch_pdl(gpt_attn_kernel<OutT>, dim3(m.H, rows), dim3(128), smem, s, qkv, kc, vc, (const int*)m.state.p, m.S_max, m.D, m.H, causal, out);
+  LAUNCHED();
+}
+
+void reserve(GptModel& m, int rows, bool fast) {
+  const size_t R = (size_t)rows;
+  m.qkv32.reserve(R * 3 * m.D);
+  m.hp.reserve(R * m.D);
+  if (fast) { m.nb16.reserve(R * m.D); m.att16.reserve(R * m.D); m.ff16.reserve(R * m.FF); }
+  m.nb32.reserve(R * m.D); m.att32.reserve(R * m.D); m.ff32.reserve(R * m.FF);
+}
+
+// Head: ln_f -> (saved) -> final_norm -> mel_head -> * penalty -> argmax (+ loop bookkeeping)
+template <typename WT>
+void head_and_pick(Engine& e, GptModel& m, const float* x_last, const float* penalty, int rows, int bookkeeping, float* save,
+                   int* id_out) {
+  GemvArgs a{};
+  if constexpr (sizeof(WT) == 4) { a.W = m.head_nk; a.ldw = m.D; } else { a.W = m.head_tc.w.p; a.ldw = m.head_tc.ldc; }
+  a.bias = m.head_b; a.x = x_last; a.K = m.D; a.N = m.Vm;
+  a.ln_w = m.lnf_w; a.ln_b = m.lnf_b; a.ln2_w = m.fn_w; a.ln2_b = m.fn_b; a.eps = m.eps;
+  a.mul = penalty; a.y = m.logits.p; a.save = save; a.state = m.state.p;
+  gemv<WT, 2>(e, "igpt.head", a);
+  ProfScope ps(e.prof, "igpt.pick", e.stream);
+  launch_pdl(gpt_pick_kernel, dim3(1), dim3(1024), 0, e.stream, (const float*)m.logits.p, m.Vm, m.state.p, m.ids.p, m.penalty.p,
+             m.mel_emb, m.mel_pos, m.hcur.p, m.D, rows, m.lc, bookkeeping, id_out);
+  LAUNCHED();
+}
+
+// decode: one row (m.hcur) through the 24 layers with matrix-vector kernels
+template <typename WT>
+void decode_layers(Engine& e, GptModel& m) {
+  const int D = m.D, FF = m.FF;
+  for (int i = 0; i < m.L; ++i) {
+    GptLayer& Ly = m.layers[i];
+    auto wp = [&](DevBuf<float>& nk, TcWeight& tc, GemvArgs& a, int K) {
+      if constexpr (sizeof(WT) == 4) { a.W = nk.p; a.ldw = K; } else { a.W = tc.w.p; a.ldw = tc.ldc; }
+    };
+    GemvArgs q{};
+    wp(Ly.qkv_nk, Ly.qkv_tc, q, D);
+    q.bias = Ly.qkv_b.p; q.x = m.hcur.p; q.K = D; q.N = 3 * D; q.ln_w = Ly.ln1_w; q.ln_b = Ly.ln1_b; q.eps = m.eps; q.y = m.qkv32.p;
+    gemv<WT, 1>(e, "igpt.qkv_gemv", q);
+    attention<float>(e, m, i, m.qkv32.p, 1, 0, m.att32.p);
+    GemvArgs o{};
+    wp(Ly.o_nk, Ly.o_tc, o, D);
+    o.bias = Ly.o_b; o.x = m.att32.p; o.K = D; o.N = D; o.res = m.hcur.p; o.y = m.hcur.p;
+    gemv<WT, 0>(e, "igpt.out_gemv", o);
+    GemvArgs f{};
+    wp(Ly.fc_nk, Ly.fc_tc, f, D);
+    f.bias = Ly.fc_b; f.x = m.hcur.p; f.K = D; f.N = FF; f.ln_w = Ly.ln2_w; f.ln_b = Ly.ln2_b; f.eps = m.eps; f.act = 1; f.y = m.ff32.p;
+    gemv<WT, 1>(e, "igpt.fc_gemv", f);
+    GemvArgs p{};
+    wp(Ly.p_nk, Ly.p_tc, p, FF);
+    p.bias = Ly.p_b; p.x = m.ff32.p; p.K = FF; p.N = D; p.res = m.hcur.p; p.y = m.hcur.p;
+    gemv<WT, 0>(e, "igpt.proj_gemv", p);
+  }
+}
+
+// prefill: `rows` rows (m.hp) through the layers with row-GEMMs
+void prefill_layers(Engine& e, GptModel& m, int rows, int causal, bool fast) {
+  cudaStream_t s = e.stream;
+  const int D = m.D, FF = m.FF;
+  auto gemm = [&](const char* tag, const void* x, int K, int N, const float* kn, const TcWeight& tc, const float* bias, int act,
+                  const float* res, void* out, int out_bf16) {
+    RowGemm p;
+    p.x = x; p.ldx = K; p.Lin = rows; p.Cin = K; p.N = N; p.taps = 1; p.M = rows; p.B = 1;
+    p.out = out; p.ldo = N; p.out_bf16 = out_bf16; p.bias = bias; p.act = act; p.res = res;
+    ProfScope ps(e.prof, tag, s);
+    if (fast) rowgemm_tc(p, tc, s);
+    else { p.w = kn; p.ldw = N; rowgemm_f32(p, s); }
+  };
+  for (int i = 0; i < m.L; ++i) {
+    GptLayer& Ly = m.layers[i];
+    {
+      ProfScope ps(e.prof, "igpt.layernorm", s);
+      if (fast) layernorm_affine_bf16(m.hp.p, Ly.ln1_w, Ly.ln1_b, m.nb16.p, rows, D, m.eps, s);
+      else layernorm_affine(m.hp.p, Ly.ln1_w, Ly.ln1_b, m.nb32.p, rows, D, m.eps, s);
+    }
+    gemm("igpt.qkv_gemm", fast ? (const void*)m.nb16.p : (const void*)m.nb32.p, D, 3 * D, Ly.qkv_kn.p, Ly.qkv_tc, Ly.qkv_b.p, ACT_NONE,
+         nullptr, m.qkv32.p, 0);
+    if (fast) attention<__nv_bfloat16>(e, m, i, m.qkv32.p, rows, causal, m.att16.p);
+    else attention<float>(e, m, i, m.qkv32.p, rows, causal, m.att32.p);
+    gemm("igpt.out_gemm", fast ? (const void*)m.att16.p : (const void*)m.att32.p, D, D, Ly.o_kn, Ly.o_tc, Ly.o_b, ACT_NONE, m.hp.p,
+         m.hp.p, 0);
+    {
+      ProfScope ps(e.prof, "igpt.layernorm", s);
+      if (fast) layernorm_affine_bf16(m.hp.p, Ly.ln2_w, Ly.ln2_b, m.nb16.p, rows, D, m.eps, s);
+      else layernorm_affine(m.hp.p, Ly.ln2_w, Ly.ln2_b, m.nb32.p, rows, D, m.eps, s);
+    }
+    gemm("igpt.fc_gemm", fast ? (const void*)m.nb16.p : (const void*)m.nb32.p, D, FF, Ly.fc_kn, Ly.fc_tc, Ly.fc_b, ACT_GELU_TANH, nullptr,
+         fast ? (void*)m.ff16.p : (void*)m.ff32.p, fast ? 1 : 0);
+    gemm("igpt.proj_gemm", fast ? (const void*)m.ff16.p : (const void*)m.ff32.p, FF, D, Ly.p_kn, Ly.p_tc, Ly.p_b, ACT_NONE, m.hp.p, m.hp.p,
+         0);
+  }
+}
+
+// One E call on the device state. x: rows > 1 -> m.hp holds the rows; rows == 1 -> m.hcur holds the row.
+void e_call(Engine& e, GptModel& m, int rows, int causal, bool fast, const float* penalty, int bookkeeping, float* save, int* id_out) {
+  if (rows == 1) {
+    if (fast) { decode_layers<__nv_bfloat16>(e, m); head_and_pick<__nv_bfloat16>(e, m, m.hcur.p, penalty, 1, bookkeeping, save, id_out); }
+    else { decode_layers<float>(e, m); head_and_pick<float>(e, m, m.hcur.p, penalty, 1, bookkeeping, save, id_out); }
+  } else {
+    prefill_layers(e, m, rows, causal, fast);
+    const float* last = m.hp.p + (size_t)(rows - 1) * m.D;
+    if (fast) head_and_pick<__nv_bfloat16>(e, m, last, penalty, rows, bookkeeping, save, id_out);
+    else head_and_pick<float>(e, m, last, penalty, rows, bookkeeping, save, id_out);
+  }
+}
+
+void set_state(Engine& e, GptModel& m, int kv, int gen, int n, int stop, int reset, int limit) {
+  int* h = m.h_state;
+  for (int i = 0; i < ST_WORDS; ++i) h[i] = 0;
+  h[ST_KV] = kv; h[ST_GEN] = gen; h[ST_N] = n; h[ST_STOP] = stop; h[ST_RESET] = reset; h[ST_LIMIT] = limit;
+  B2_CUDA(cudaMemcpyAsync(m.state.p, h, ST_WORDS * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  B2_CUDA(cudaStreamSynchronize(e.stream));       // h_state is reused
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// build
+// =====================================================================================================================
+GptModel* gpt_build(Engine& e) {
+  std::unique_ptr<GptModel> mp(new GptModel());
+  GptModel& m = *mp;
+  cudaStream_t s = e.stream;
+  const Tensor& te = e.weight("igpt.text_embedding.weight");
+  const Tensor& me = e.weight("igpt.mel_embedding.weight");
+  B2_CHECK(te.shape.size() == 2 && me.shape.size() == 2 && te.shape[1] == me.shape[1], "igpt embeddings: shape");
+  m.D = (int)te.shape[1]; m.Vt = (int)te.shape[0]; m.Vm = (int)me.shape[0];
+  B2_CHECK(m.D % 128 == 0 && m.D % HD == 0, "igpt: model_dim must be a multiple of 128");
+  m.H = m.D / HD; m.FF = 4 * m.D;
+  m.Pt = (int)e.weight("igpt.text_pos_embedding.emb.weight").shape[0];
+  m.Pm = (int)e.weight("igpt.mel_pos_embedding.emb.weight").shape[0];
+  const Tensor& mt = e.weight("igpt.meta");       // [start_text, stop_text, start_mel, stop_mel, max_generate, penalty_range, repeat_penalty, ln_eps]
+  B2_CHECK(mt.numel() == 8, "igpt.meta must hold 8 values");
+  float meta[8];
+  B2_CUDA(cudaMemcpy(meta, mt.data.p, sizeof(meta), cudaMemcpyDeviceToHost));
+  m.start_text = (int)meta[0]; m.stop_text = (int)meta[1];
+  m.lc.start_mel = (int)meta[2]; m.lc.stop_mel = (int)meta[3];
+  m.S_max = (int)meta[4]; m.lc.range = (int)meta[5]; m.lc.repeat_penalty = meta[6]; m.eps = meta[7];
+  B2_CHECK(m.S_max >= 8 && m.S_max <= 8192, "igpt: max_generate out of range");
+  B2_CHECK(m.lc.start_mel < m.Vm && m.lc.stop_mel < m.Vm, "igpt: start / stop mel ids outside the code book");
+  while (e.has_weight("igpt.h." + std::to_string(m.L) + ".ln_1.weight")) ++m.L;
+  B2_CHECK(m.L > 0, "igpt: no transformer layers loaded");
+  const int D = m.D, FF = m.FF;
+  m.text_emb = te.data.p; m.mel_emb = me.data.p;
+  m.text_pos = W(e, "text_pos_embedding.emb.weight", (long)m.Pt * D);
+  m.mel_pos = W(e, "mel_pos_embedding.emb.weight", (long)m.Pm * D);
+  m.lnf_w = W(e, "ln_f.weight", D); m.lnf_b = W(e, "ln_f.bias", D);
+  m.fn_w = W(e, "final_norm.weight", D); m.fn_b = W(e, "final_norm.bias", D);
+  m.head_nk = W(e, "mel_head.weight", (long)m.Vm * D); m.head_b = W(e, "mel_head.bias", m.Vm);
+  m.layers.resize(m.L);
+  const float scale = powf((float)HD, -0.25f);
+  for (int i = 0; i < m.L; ++i) {
+    GptLayer& Ly = m.layers[i];
+    const std::string p = "h." + std::to_string(i) + ".";
+    Ly.ln1_w = W(e, p + "ln_1.weight", D); Ly.ln1_b = W(e, p + "ln_1.bias", D);
+    Ly.ln2_w = W(e, p + "ln_2.weight", D); Ly.ln2_b = W(e, p + "ln_2.bias", D);
+    Ly.o_kn = W(e, p + "attn.c_proj.weight", (long)D * D); Ly.o_b = W(e, p + "attn.c_proj.bias", D);
+    Ly.fc_kn = W(e, p + "mlp.c_fc.weight", (long)D * FF); Ly.fc_b = W(e, p + "mlp.c_fc.bias", FF);
+    Ly.p_kn = W(e, p + "mlp.c_proj.weight", (long)FF * D); Ly.p_b = W(e, p + "mlp.c_proj.bias", D);
+    // q and k columns (and biases) x 64^-0.25 each (Export_IndexTTS.py:250-255): the scores come out divided by 8
+    const float* qw = W(e, p + "attn.c_attn.weight", (long)D * 3 * D);
+    const float* qb = W(e, p + "attn.c_attn.bias", 3 * D);
+    Ly.qkv_b.alloc((size_t)3 * D);
+    B2_CUDA(cudaMemcpyAsync(Ly.qkv_b.p, qb, (size_t)3 * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    scale_kernel<<<ceil_div(2 * D, 256), 256, 0, s>>>(Ly.qkv_b.p, 2 * D, scale);
+    // [D][3D] with the first 2D COLUMNS scaled: transpose -> scale the first 2D rows -> transpose back
+    DevBuf<float> t((size_t)3 * D * D);
+    transpose_to(qw, t.p, D, 3 * D, s);
+    scale_kernel<<<ceil_div((long)2 * D * D, 256), 256, 0, s>>>(t.p, (long)2 * D * D, scale);
+    Ly.qkv_kn.alloc((size_t)3 * D * D);
+    transpose_to(t.p, Ly.qkv_kn.p, 3 * D, D, s);
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaStreamSynchronize(s));
+  }
+  const size_t kv = (size_t)m.L * m.H * m.S_max * HD;
+  m.kc.alloc(kv); m.vc.alloc(kv);
+  B2_CUDA(cudaMemsetAsync(m.kc.p, 0, kv * sizeof(float), s));
+  B2_CUDA(cudaMemsetAsync(m.vc.p, 0, kv * sizeof(float), s));
+  m.state.alloc(ST_WORDS); m.ids.alloc((size_t)m.S_max + 1);
+  m.penalty.alloc((size_t)m.Vm); m.hid_save.alloc((size_t)(m.S_max + 1) * D);
+  m.hcur.alloc((size_t)D); m.logits.alloc((size_t)m.Vm); m.idbuf.alloc(4);
+  B2_CUDA(cudaMemsetAsync(m.ids.p, 0, ((size_t)m.S_max + 1) * sizeof(int), s));
+  B2_CUDA(cudaMemsetAsync(m.state.p, 0, ST_WORDS * sizeof(int), s));
+  B2_CUDA(cudaMallocHost((void**)&m.h_state, ST_WORDS * sizeof(int)));
+  const size_t attn_smem = (size_t)(m.S_max + 3 * HD + 8) * sizeof(float);
+  B2_CHECK(attn_smem <= 200 * 1024, "igpt: cache capacity too large for the attention kernel's score buffer");
+  B2_CUDA(cudaFuncSetAttribute(gpt_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  B2_CUDA(cudaFuncSetAttribute(gpt_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  B2_CUDA(cudaStreamSynchronize(s));
+  return mp.release();
+}
+
+void gpt_free(GptModel* m) {
+  if (!m) return;
+  if (m->h_state) cudaFreeHost(m->h_state);
+  delete m;
+}
+int gpt_dim(const GptModel& m) { return m.D; }
+int gpt_layers(const GptModel& m) { return m.L; }
+int gpt_heads(const GptModel& m) { return m.H; }
+int gpt_mel_codes(const GptModel& m) { return m.Vm; }
+int gpt_max_rows(const GptModel& m) { return m.S_max; }
+int gpt_resident_rows(const GptModel& m) { return m.resident; }
+
+// =====================================================================================================================
+// graphs B, C
+// =====================================================================================================================
+void gpt_text_embed(Engine& e, const int* d_text_ids, int n_text, float* d_out) {
+  GptModel& m = model(e);
+  const int rows = n_text + 2;
+  B2_CHECK(n_text >= 0 && rows <= m.Pt, "text_embed: more text ids than text_pos_embedding rows");
+  gpt_embed_kernel<<<ceil_div((long)rows * m.D, 256), 256, 0, e.stream>>>(d_text_ids, n_text, m.text_emb, m.text_pos, 0, d_out, rows, m.D, 1,
+                                                                          m.start_text, m.stop_text, m.Vt);
+  LAUNCHED();
+}
+
+void gpt_mel_embed(Engine& e, const int* d_id, int gen_len, float* d_out) {
+  GptModel& m = model(e);
+  B2_CHECK(gen_len >= 0 && gen_len < m.Pm, "mel_embed: gen_len outside mel_pos_embedding");
+  gpt_embed_kernel<<<ceil_div((long)m.D, 256), 256, 0, e.stream>>>(d_id, 1, m.mel_emb, m.mel_pos, gen_len, d_out, 1, m.D, 0, 0, 0, m.Vm);
+  LAUNCHED();
+}
+
+// =====================================================================================================================
+// graph E, per call (session surface)
+// =====================================================================================================================
+void gpt_step(Engine& e, const float* d_hidden, int rows, int history, int mask_flag, const float* d_penalty, int precision,
+              float* d_last_hidden, int* d_max_id) {
+  GptModel& m = model(e);
+  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "gpt_step: unknown precision");
+  B2_CHECK(rows >= 1, "gpt_step: no rows");
+  B2_CHECK(history == 0 || history == m.resident, "gpt_step: history_len does not match the resident KV cache");
+  B2_CHECK(history + rows <= m.S_max, "gpt_step: KV cache capacity (MAX_GENERATE_LENGTH) exceeded");
+  const bool fast = precision == PREC_BF16;
+  prepare(e, m, precision);
+  reserve(m, rows, fast);
+  cudaStream_t s = e.stream;
+  set_state(e, m, history, 0, 0, 0, 0, 1 << 30);
+  float* dst = rows == 1 ? m.hcur.p : m.hp.p;
+  B2_CUDA(cudaMemcpyAsync(dst, d_hidden, (size_t)rows * m.D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // save slot 0 of hid_save receives ln_f(last row); bookkeeping off: the caller owns ids / penalty / positions
+  e_call(e, m, rows, mask_flag != 0 ? 1 : 0, fast, d_penalty, 0, m.hid_save.p, d_max_id);
+  B2_CUDA(cudaMemcpyAsync(d_last_hidden, m.hid_save.p, (size_t)m.D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  m.resident = history + rows;
+}
+
+void gpt_kv_export(Engine& e, int layer, float* d_key, float* d_value) {
+  GptModel& m = model(e);
+  B2_CHECK(layer >= 0 && layer < m.L, "kv_export: layer out of range");
+  const int S = m.resident;
+  if (S == 0) return;
+  const size_t off = (size_t)layer * m.H * m.S_max * HD;
+  kv_export_kernel<<<ceil_div((long)m.H * S * HD, 256), 256, 0, e.stream>>>(m.kc.p + off, m.vc.p + off, d_key, d_value, m.H, S, m.S_max);
+  LAUNCHED();
+}
+
+// =====================================================================================================================
+// one sentence, loop on the device
+// =====================================================================================================================
+int gpt_generate(Engine& e, const float* d_conds, int cond_rows, const int* d_text_ids, int n_text, int max_new, int precision,
+                 float* d_penalty, int* d_ids_out, float* d_hidden_out) {
+  GptModel& m = model(e);
+  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "gpt_generate: unknown precision");
+  const bool fast = precision == PREC_BF16;
+  cudaStream_t s = e.stream;
+  const int D = m.D;
+  const int rows = cond_rows + n_text + 2 + 1;             // graph D: conds | [start, text, stop] | first mel row
+  B2_CHECK(cond_rows >= 0 && n_text >= 0 && rows >= 2, "gpt_generate: bad sizes");
+  int limit = m.S_max - rows;                              // Inference_IndexTTS_ONNX.py:745
+  if (max_new > 0 && max_new < limit) limit = max_new;
+  B2_CHECK(limit >= 1, "gpt_generate: the prompt leaves no room to generate (MAX_GENERATE_LENGTH)");
+  B2_CHECK(limit + 1 <= m.Pm, "gpt_generate: mel_pos_embedding has fewer rows than the generation limit");
+  prepare(e, m, precision);
+  reserve(m, rows, fast);
+  if (d_penalty) {
+    B2_CUDA(cudaMemcpyAsync(m.penalty.p, d_penalty, (size_t)m.Vm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {                                                 // a fresh penalty vector (Inference_IndexTTS_ONNX.py:688)
+    fill_kernel<<<ceil_div(m.Vm, 256), 256, 0, s>>>(m.penalty.p, m.Vm, 1.0f);
+    LAUNCHED();
+  }
+  // graphs B, C (start mel id at position 0), D
+  if (cond_rows) B2_CUDA(cudaMemcpyAsync(m.hp.p, d_conds, (size_t)cond_rows * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  gpt_text_embed(e, d_text_ids, n_text, m.hp.p + (size_t)cond_rows * D);
+  {
+    const int start = m.lc.start_mel;
+    B2_CUDA(cudaMemcpyAsync(m.idbuf.p, &start, sizeof(int), cudaMemcpyHostToDevice, s));
+    gpt_mel_embed(e, m.idbuf.p, 0, m.hp.p + (size_t)(rows - 1) * D);
+  }
+  set_state(e, m, /*kv*/ 0, /*gen*/ 1, /*n*/ 0, /*stop*/ 0, /*reset*/ 0, limit);
+  m.resident = 0;
+  // prefill: causal flag 1 (Inference:690), then single rows with flag 0 (:763-765)
+  e_call(e, m, rows, 1, fast, m.penalty.p, 1, m.hid_save.p, nullptr);
+  const int chunk = 16;
+  int produced = 0, stopped = 0;
+  const std::vector<long long> key = {30, precision, (long long)(uintptr_t)m.hcur.p, (long long)(uintptr_t)m.kc.p};
+  while (!stopped) {
+    B2_CUDA(cudaMemcpyAsync(m.h_state, m.state.p, ST_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    produced = m.h_state[ST_N];
+    stopped = m.h_state[ST_STOP];
+    if (stopped) break;
+    int todo = limit - produced;
+    if (todo > chunk) todo = chunk;
+    for (int i = 0; i < todo; ++i)                          // steps after a stop inside the chunk leave the state untouched
+      run_graphed(e, key, [&] { e_call(e, m, 1, 0, fast, m.penalty.p, 1, m.hid_save.p, nullptr); }, [] {});
+  }
+  m.resident = m.h_state[ST_KV];
+  B2_CUDA(cudaMemcpyAsync(d_ids_out, m.ids.p, (size_t)produced * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  B2_CUDA(cudaMemcpyAsync(d_hidden_out, m.hid_save.p, (size_t)produced * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (d_penalty) B2_CUDA(cudaMemcpyAsync(d_penalty, m.penalty.p, (size_t)m.Vm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return produced;
+}
+
+}  // namespace b200tts

@@ -152,6 +152,21 @@ def ivgan_engine_tensors(state: dict, cfg) -> dict:
     return out
 
 
+def igpt_engine_tensors(state: dict, cfg) -> dict:
+    """IndexTTS GPT state (gpt.* names as graphs B-E read them: text_embedding, text_pos_embedding.emb, mel_embedding,
+    mel_pos_embedding.emb, h.<i>.* of the Hugging Face GPT2Model inside inference_model, ln_f, final_norm, mel_head) -> tensors for
+    ``Engine.load_state('igpt', ...)``. Weights stay in the checkpoint's layout and UNscaled; the engine applies the export's q/k
+    pre-scale (Export_IndexTTS.py:250-255). ``meta`` carries the loop constants of Inference_IndexTTS_ONNX.py:36-39."""
+    out = {}
+    for k, v in state.items():
+        if k.endswith((".attn.bias", ".attn.masked_bias")):       # GPT2Attention's causal-mask buffers: unused by graph E
+            continue
+        out[k] = np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+    out["meta"] = np.asarray([cfg.start_text, cfg.stop_text, cfg.start_mel, cfg.stop_mel, cfg.max_generate, cfg.penalty_range,
+                              cfg.repeat_penalty, cfg.ln_eps], dtype=np.float32)
+    return out
+
+
 def bigvgan_engine_tensors(state: dict) -> dict:
     """Reference BigVGAN state dict -> tensors for ``Engine.load_state('bigvgan', ...)``."""
     out = {}
