@@ -185,6 +185,29 @@ def run_reference(args, rank, world):
                 "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                  "sample": f"{steps} x 1 mel (1,100,{T}), torch-CPU fp32 eager restatement of the reference "
                                            "modules (stand-in for ORT CPUExecutionProvider, not installable offline)"}}
+    elif args.workload == "indextts_gpt":
+        import torch as _t
+        from b200tts import synth
+        from oracle import indextts_gpt_ref
+        _t.set_num_threads(cores)
+        cfg = config.INDEXTTS_GPT
+        sd = synth.igpt_state(555)
+        cds, tid = synth.igpt_inputs(900, args.gpt_text, cfg)
+        t0 = time.perf_counter()
+        indextts_gpt_ref.generate(cds, tid, sd, cfg, max_new=1)
+        t_pre = time.perf_counter() - t0
+        n_cpu = 1 + 8 * steps
+        t0 = time.perf_counter()
+        indextts_gpt_ref.generate(cds, tid, sd, cfg, max_new=n_cpu)
+        per_tok = max(time.perf_counter() - t0 - t_pre, 1e-9) / (n_cpu - 1)
+        total = t_pre + (args.new_tokens - 1) * per_tok
+        v = args.new_tokens / total
+        line = {"metric": "mel_tokens_per_s", "value": v, "unit": "tokens/s", "ms_per_step": 1e3 * total, "dtype": "f32",
+                "config": {"workload": f"IndexTTS GPT-2 acoustic model, one sentence: prefill of {cfg.cond_rows + args.gpt_text + 3} rows + "
+                                       f"{args.new_tokens - 1} decode calls [acoustic half of BASELINE.json configs[4]]", "parallelism": "cpu"},
+                "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                 "sample": f"prefill + {n_cpu - 1} decode calls (extrapolated to {args.new_tokens}); torch-CPU fp32 eager "
+                                           "restatement of graphs B-E", "prefill_s": t_pre, "s_per_decode_call": per_tok}}
     else:
         cfg = config.F5
         r = cpu_f5(args.audio_len, args.n_text, steps, cores)
@@ -447,13 +470,91 @@ def bench_indextts_vocoder(args, H, eng, rank, prec, steps, warmup):
                         "[vocoder half of BASELINE.json configs[4]]"}
 
 
+def bench_indextts_gpt(args, H, eng, rank, prec, steps, warmup, sampler=None):
+    """Acoustic half of BASELINE.json configs[4]: one sentence of IndexTTS GPT-2 greedy decode per step -- graphs B, C, D,
+    a prefill of (32 conditioning latents + text + 3) rows and `--new-tokens` single-row decode calls with the KV cache,
+    penalty window and loop state on the device. Metric: generated mel tokens per second."""
+    torch = H.torch
+    from b200tts import capi, config, synth
+    cfg = config.INDEXTTS_GPT
+    n_new = args.new_tokens
+    conds, text_ids = synth.igpt_inputs(900 + rank, args.gpt_text, cfg)
+    D, cap = cfg.dim, cfg.max_generate + 1
+    rows = cfg.cond_rows + args.gpt_text + 3
+    conds_h = torch.from_numpy(conds.reshape(-1, D)).pin_memory()
+    ids_h = torch.from_numpy(text_ids.reshape(-1)).pin_memory()
+    conds_d, ids_d = conds_h.cuda(), ids_h.cuda()
+    out_ids = torch.zeros((cap,), dtype=torch.int32, device="cuda")
+    out_hid = torch.zeros((cap, D), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    produced = []
+
+    def core():
+        produced.append(eng.indextts_gpt_generate_device(conds_d.data_ptr(), cfg.cond_rows, ids_d.data_ptr(), args.gpt_text,
+                                                         out_ids.data_ptr(), out_hid.data_ptr(), max_new=n_new, precision=prec))
+
+    def step_e2e():
+        eng.indextts_gpt_generate(conds, text_ids, max_new=n_new, precision=prec)       # host buffers in and out, synchronises
+
+    with torch.cuda.stream(H.stream):
+        for _ in range(warmup):
+            core()
+        step_e2e()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    produced.clear()
+    ms = H.timed(core, steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    tokens = sum(produced)
+    ms_e2e = H.timed(step_e2e, steps)
+    # per-kernel split of ONE sentence (eager, CUDA events around every launch)
+    eng.profile_begin()
+    with torch.cuda.stream(H.stream):
+        core()
+    prof = eng.profile_end()
+    pk = peaks()
+    wbytes = 2 if prec == capi.BF16 else 4
+    per_tok_w = (cfg.layers * 12 * D * D + cfg.mel_codes * D) * wbytes                      # every projection weight once
+    avg_kv = rows + n_new / 2
+    per_tok_kv = cfg.layers * 2 * avg_kv * D * 4                                            # fp32 cache rows read by attention
+    gemv_tags = ("igpt.qkv_gemv", "igpt.out_gemv", "igpt.fc_gemv", "igpt.proj_gemv", "igpt.head")
+    gemv_ms = sum(prof[t]["ms"] for t in gemv_tags if t in prof)
+    gemv_n = sum(prof[t]["launches"] for t in gemv_tags if t in prof)
+    total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
+    n_tok = produced[-1]
+    res = {
+        "value": tokens * H.world / (ms / 1e3), "ms_per_step": ms / steps,
+        "e2e": {"value": tokens * H.world / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(conds.nbytes + text_ids.nbytes), "d2h_bytes_per_step": int(n_tok * (D * 4 + 4))},
+        "gpu_launches": int(launches), "clocks": clocks, "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        "ms_per_token": ms / max(tokens, 1),
+        "workload": (f"IndexTTS GPT-2 acoustic model ({cfg.layers} layers, dim {D}, {cfg.heads} heads, {cfg.mel_codes} mel codes), one sentence "
+                     f"per step: prefill of {rows} rows ({cfg.cond_rows} latents + {args.gpt_text} text ids + 3) then {n_new - 1} single-row "
+                     f"greedy decode calls, repeat-penalty window on the device [acoustic half of BASELINE.json configs[4]]"),
+    }
+    if gemv_ms > 0:
+        # decode GEMVs of the profiled sentence: (n_tok - 1) decode calls stream every weight once; the prefill's head call too
+        ach = ((n_tok - 1) * per_tok_w + cfg.mel_codes * D * wbytes) / (gemv_ms / 1e3) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": "gemv_kernel (decode projections: LayerNorm + matrix-vector + epilogue)", "achieved": ach,
+                           "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("igpt.gemv"),
+                           "peak_source": pk["source"], "avg_launch_ms": gemv_ms / max(gemv_n, 1), "share_of_step": gemv_ms / total_ms,
+                           "bytes_per_token": int(per_tok_w), "kv_bytes_per_token_avg": int(per_tok_kv)}
+    res["hbm_floor_ms_per_token"] = (per_tok_w + per_tok_kv) / (pk["hbm_gbs"] * 1e9) * 1e3
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder"])
+    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder", "indextts_gpt"])
+    ap.add_argument("--new-tokens", type=int, default=256, help="indextts_gpt workload: E calls per sentence (prefill + decode)")
+    ap.add_argument("--gpt-text", type=int, default=60, help="indextts_gpt workload: text ids per sentence")
     ap.add_argument("--latent-rows", type=int, default=142, help="indextts_vocoder workload: rows of save_hidden_state")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=512)
@@ -507,6 +608,11 @@ def main():
         distributed.load_state_broadcast(eng, "ivgan", state, src=0)
         eng.indextts_vocoder_build()
 
+    if args.workload == "indextts_gpt":
+        state = weights.igpt_engine_tensors(synth.igpt_state(555), config.INDEXTTS_GPT) if rank == 0 else None
+        distributed.load_state_broadcast(eng, "igpt", state, src=0)
+        eng.indextts_gpt_build()
+
     # weights: rank 0 makes them, NCCL broadcast over NVLink to the others (the only collective of the job)
     if need_vgan:
         state = weights.bigvgan_engine_tensors(synth.bigvgan_state(1234)) if rank == 0 else None
@@ -541,6 +647,9 @@ def main():
     elif args.workload == "indextts_vocoder":
         res = bench_indextts_vocoder(args, H, eng, rank, prec, args.steps, args.warmup)
         dtype = "bf16" if prec == capi.BF16 else "f32"
+    elif args.workload == "indextts_gpt":
+        res = bench_indextts_gpt(args, H, eng, rank, prec, args.steps, args.warmup, sampler)
+        dtype = "bf16 weights, fp32 activations / cache / accumulation" if prec == capi.BF16 else "f32"
     elif args.workload == "f5":
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
         dtype = "bf16" if prec == capi.BF16 else "f32"
@@ -555,6 +664,8 @@ def main():
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": workload, "parallelism": f"dp{world} (utterance sharding, weights NCCL-broadcast at load)",
                            "l2": "per-step working set (activations + weights, > 0.5 GB) exceeds the 126 MB L2; no explicit flush"}}
+        if args.workload == "indextts_gpt":
+            line["metric"], line["unit"] = "mel_tokens_per_s", "tokens/s"
         line.update(res)
         line.update(extra)
         if not args.no_cpu_baseline:
@@ -572,6 +683,25 @@ def main():
                 line["cpu_baseline"] = {"value": (args.latent_rows - 2) * 4 / dtc, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                         "sample": f"1 x latent ({args.latent_rows},1280), oracle (torch-CPU fp32 restatement of IndexTTS_F)",
                                         "s_per_utterance": dtc}
+            elif args.workload == "indextts_gpt":
+                import torch as _t
+                from oracle import indextts_gpt_ref
+                _t.set_num_threads(cores)
+                cfgg = config.INDEXTTS_GPT
+                sdg = synth.igpt_state(555)
+                cds, tid = synth.igpt_inputs(900, args.gpt_text, cfgg)
+                t0 = time.perf_counter()
+                indextts_gpt_ref.generate(cds, tid, sdg, cfgg, max_new=1)
+                t_pre = time.perf_counter() - t0
+                n_cpu = 9
+                t0 = time.perf_counter()
+                indextts_gpt_ref.generate(cds, tid, sdg, cfgg, max_new=n_cpu)
+                dtc = time.perf_counter() - t0
+                per_tok = max(dtc - t_pre, 1e-9) / (n_cpu - 1)
+                line["cpu_baseline"] = {"value": args.new_tokens / (t_pre + (args.new_tokens - 1) * per_tok), "unit": "tokens/s", "cores": cores,
+                                        "kind": "port", "sample": f"prefill + {n_cpu - 1} decode calls of one sentence (extrapolated to "
+                                        f"{args.new_tokens}); oracle (torch-CPU fp32 restatement of graphs B-E)",
+                                        "prefill_s": t_pre, "s_per_decode_call": per_tok}
             elif args.workload == "bigvgan":
                 dt = cpu_bigvgan(args.frames, 2, cores)
                 line["cpu_baseline"] = {"value": args.frames / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",

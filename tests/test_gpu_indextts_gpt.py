@@ -136,6 +136,21 @@ def test_generate_is_deterministic_and_restartable(small, g):
     np.testing.assert_array_equal(a[1], b[1])
 
 
+def test_persistent_kernel_matches_per_kernel_path(small, g, monkeypatch):
+    """bf16 engine: the cooperative persistent decode kernel (default) and the graph of per-phase kernels run the same
+    arithmetic (only the attention reduction tree differs)."""
+    eng, sd, conds, text_ids = small
+    a = eng.indextts_gpt_generate(conds, text_ids, max_new=40, precision=capi.BF16)
+    monkeypatch.setenv("B200TTS_GPT_PERSIST", "0")
+    b = eng.indextts_gpt_generate(conds, text_ids, max_new=40, precision=capi.BF16)
+    monkeypatch.delenv("B200TTS_GPT_PERSIST")
+    n = 0
+    while n < min(len(a[0]), len(b[0])) and a[0][n] == b[0][n]:
+        n += 1
+    assert n >= 30, (n, a[0], b[0])
+    assert np.abs(a[1][:n] - b[1][:n]).max() <= 1e-3
+
+
 @pytest.fixture(scope="module")
 def full(engine):
     sd = synth.igpt_state(556, FULL)

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int HD = 64;
 // device loop state
-enum : int { ST_KV = 0, ST_GEN = 1, ST_N = 2, ST_STOP = 3, ST_RESET = 4, ST_LIMIT = 5, ST_WORDS = 8 };
+enum : int { ST_KV = 0, ST_GEN = 1, ST_N = 2, ST_STOP = 3, ST_RESET = 4, ST_LIMIT = 5, ST_ERR = 6, ST_WORDS = 8 };
 
 struct LoopConst {
   int start_mel, stop_mel, range;
@@ -69,6 +69,8 @@ struct GptModel {
   DevBuf<__nv_bfloat16> nb16, att16, ff16;
   DevBuf<int> idbuf;
   int* h_state = nullptr;                    // pinned
+  DevBuf<unsigned char> players;             // device array of PLayer (persistent decode kernel)
+  DevBuf<unsigned int> gbar;                 // its grid-barrier counter
 };
 
 namespace {
@@ -107,15 +109,13 @@ __device__ __forceinline__ float gelu_new_f(float v) {      // Hugging Face NewG
 template <typename WT> struct WVec;
 template <> struct WVec<float> {
   static constexpr int N = 4;
-  __device__ static __forceinline__ void load(const float* p, float (&w)[4]) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&w)[4]) {
+    w[0] = __uint_as_float(v.x); w[1] = __uint_as_float(v.y); w[2] = __uint_as_float(v.z); w[3] = __uint_as_float(v.w);
   }
 };
 template <> struct WVec<__nv_bfloat16> {
   static constexpr int N = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&w)[8]) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  __device__ static __forceinline__ void unpack(const uint4& v, float (&w)[8]) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -138,57 +138,80 @@ struct GemvArgs {
   int act;                                    // 0 none, 1 gelu_new
 };
 
+// LayerNorm of src[K] into dst[K] (both shared): every warp derives the row statistics itself (two passes over shared memory,
+// no block barrier) and normalises its eighth of the row. The caller synchronises before dst is read.
+__device__ __forceinline__ void ln_rows_shared(const float* src, float* dst, int K, const float* lw, const float* lb, float eps,
+                                               int warp, int lane) {
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += src[k];
+  const float mean = warp_sum_f(s) / (float)K;
+  float q = 0.f;
+  for (int k = lane; k < K; k += 32) { const float d = src[k] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum_f(q) / (float)K + eps);
+  const int per = (K + 7) / 8, k1 = min(K, (warp + 1) * per);
+  for (int k = warp * per + lane; k < k1; k += 32) dst[k] = (src[k] - mean) * rstd * lw[k] + lb[k];
+}
+
 // y[n] = epilogue(W[n][:] . pre(x) + bias[n]); one warp per output row, 8 rows per CTA.
-template <typename WT, int PRE>
+// The first NCH 16-byte chunks of the row per lane are fetched BEFORE the grid dependency is awaited: the weights do not depend
+// on the preceding kernel, so under programmatic dependent launch this kernel's HBM stream runs while its predecessor is still
+// computing, and the part that is serialised behind the predecessor is x (a few KB from L2), the LayerNorm and the FMAs.
+template <typename WT, int PRE, int NCH>
 __global__ void __launch_bounds__(256) gemv_kernel(const GemvArgs a) {
-  extern __shared__ float xs[];               // K floats
-  __shared__ float red[8];
-  pdl_trigger();
-  pdl_wait();
-  const int K = a.K, tid = threadIdx.x;
-  for (int k = tid; k < K; k += 256) xs[k] = a.x[k];
-  if constexpr (PRE >= 1) {
-    __syncthreads();
-#pragma unroll 1
-    for (int pass = 0; pass < PRE; ++pass) {
-      const float* lw = pass == 0 ? a.ln_w : a.ln2_w;
-      const float* lb = pass == 0 ? a.ln_b : a.ln2_b;
-      float s = 0.f;
-      for (int k = tid; k < K; k += 256) s += xs[k];
-      const float mean = block_sum(s, red) / (float)K;
-      float q = 0.f;
-      for (int k = tid; k < K; k += 256) { const float d = xs[k] - mean; q += d * d; }
-      const float rstd = 1.0f / sqrtf(block_sum(q, red) / (float)K + a.eps);
-      for (int k = tid; k < K; k += 256) xs[k] = (xs[k] - mean) * rstd * lw[k] + lb[k];
-      __syncthreads();
-      if (PRE == 2 && pass == 0 && blockIdx.x == 0 && a.save != nullptr) {
-        float* dst = a.save + (long)a.state[ST_N] * K;
-        for (int k = tid; k < K; k += 256) dst[k] = xs[k];
-      }
-    }
-  } else {
-    __syncthreads();
-  }
-  const int warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= a.N) return;
+  extern __shared__ float xs[];               // K floats (PRE == 0) or 2 K floats (raw | normalised)
   constexpr int V = WVec<WT>::N;
-  const WT* wr = reinterpret_cast<const WT*>(a.W) + (long)n * a.ldw;
+  const int K = a.K, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * 8 + warp;
+  const bool live = n < a.N;
+  const WT* wr = reinterpret_cast<const WT*>(a.W) + (long)(live ? n : 0) * a.ldw;
+  pdl_trigger();
+  uint4 wq[NCH > 0 ? NCH : 1];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int k0 = (c * 32 + lane) * V;
+    wq[c] = k0 < K ? __ldg(reinterpret_cast<const uint4*>(wr + k0)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  pdl_wait();
+  for (int k = tid; k < K; k += 256) xs[k] = a.x[k];
+  __syncthreads();
+  const float* xv = xs;
+  if constexpr (PRE >= 1) {
+    float* xn = xs + K;
+    ln_rows_shared(xs, xn, K, a.ln_w, a.ln_b, a.eps, warp, lane);
+    __syncthreads();
+    xv = xn;
+    if constexpr (PRE == 2) {
+      if (blockIdx.x == 0 && a.save != nullptr) {
+        float* dst = a.save + (long)a.state[ST_N] * K;
+        for (int k = tid; k < K; k += 256) dst[k] = xn[k];
+      }
+      ln_rows_shared(xn, xs, K, a.ln2_w, a.ln2_b, a.eps, warp, lane);
+      __syncthreads();
+      xv = xs;
+    }
+  }
+  if (!live) return;
   float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 5
-  for (int k0 = lane * V; k0 < K; k0 += 32 * V) {
+  auto fma_chunk = [&](const uint4& q, int k0) {
     float w[V];
-    WVec<WT>::load(wr + k0, w);
-    const float4* xv = reinterpret_cast<const float4*>(xs + k0);
+    WVec<WT>::unpack(q, w);
+    const float4* x4p = reinterpret_cast<const float4*>(xv + k0);
 #pragma unroll
     for (int i = 0; i < V / 4; ++i) {
-      const float4 x4 = xv[i];
+      const float4 x4 = x4p[i];
       acc0 = fmaf(w[4 * i], x4.x, acc0);
       acc1 = fmaf(w[4 * i + 1], x4.y, acc1);
       acc0 = fmaf(w[4 * i + 2], x4.z, acc0);
       acc1 = fmaf(w[4 * i + 3], x4.w, acc1);
     }
+  };
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int k0 = (c * 32 + lane) * V;
+    if (k0 < K) fma_chunk(wq[c], k0);
   }
+#pragma unroll 4
+  for (int k0 = (NCH * 32 + lane) * V; k0 < K; k0 += 32 * V) fma_chunk(__ldg(reinterpret_cast<const uint4*>(wr + k0)), k0);
   float v = warp_sum_f(acc0 + acc1);
   if (lane == 0) {
     if (a.bias) v += a.bias[n];
@@ -199,76 +222,87 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvArgs a) {
   }
 }
 
-// Attention of `rows` new query rows against the cache. grid (H, rows), 128 threads.
+// Attention of `rows` new query rows against the cache. grid (H, rows), 256 threads.
 // qkv [rows][3D] fp32 (q | k | v thirds, head-major inside a third). The cache already holds the keys / values of the new rows
 // when rows > 1 (kv_scatter_kernel); for rows == 1 this CTA appends its own head's row first. Key range of row r: causal ->
 // [0, hist + r], else [0, hist + rows). The reference adds -128 to masked scores instead of removing them
 // (Export_IndexTTS.py:245,268); exp(-128 - max) underflows to exactly 0 in fp32, so skipping them is the same arithmetic.
+// Scores: one key per thread (a 256-byte cache row each). P.V: 16 key groups x 16 float4 columns, partial sums through shared memory.
+constexpr int ATT_NT = 256;
 template <typename OutT>
-__global__ void __launch_bounds__(128) gpt_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
-                                                       const int* __restrict__ state, int S_max, int D, int H, int causal,
-                                                       OutT* __restrict__ out) {
-  extern __shared__ float sm[];               // scores [S_max] | q [64] | part [2][64] | red [8]
+__global__ void __launch_bounds__(ATT_NT) gpt_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                                          const int* __restrict__ state, int S_max, int D, int H, int causal,
+                                                          OutT* __restrict__ out) {
+  extern __shared__ float sm[];               // scores [S_max] | q [64] | part [16][64] | red [16]
   pdl_trigger();
   pdl_wait();
   float* sc = sm;
   float* qs = sm + S_max;
   float* part = qs + HD;
-  float* red = part + 2 * HD;
+  float* red = part + 16 * HD;
   const int h = blockIdx.x, r = blockIdx.y, rows = gridDim.y, tid = threadIdx.x;
   const int hist = state[ST_KV];
   const float* qrow = qkv + (long)r * 3 * D + h * HD;
   float* kh = kc + (long)h * S_max * HD;
   float* vh = vc + (long)h * S_max * HD;
   if (tid < HD) qs[tid] = qrow[tid];
-  if (rows == 1) {                             // decode: append this head's new key / value row
+  if (rows == 1 && tid < 2 * HD) {            // decode: append this head's new key / value row
     if (tid < HD) kh[(long)hist * HD + tid] = qrow[D + tid];
     else vh[(long)hist * HD + tid - HD] = qrow[2 * D + tid - HD];
   }
   __syncthreads();
   const int nk = causal ? hist + r + 1 : hist + rows;
-  // scores: one key per thread
-  float q[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) q[d] = qs[d];
   float mx = -3.0e38f;
-  for (int j = tid; j < nk; j += 128) {
-    const float4* kr = reinterpret_cast<const float4*>(kh + (long)j * HD);
-    float s0 = 0.f, s1 = 0.f;
+  if (tid < nk) {
+    float q[HD];
 #pragma unroll
-    for (int i = 0; i < HD / 4; ++i) {
-      const float4 k4 = kr[i];
-      s0 = fmaf(q[4 * i], k4.x, s0); s1 = fmaf(q[4 * i + 1], k4.y, s1);
-      s0 = fmaf(q[4 * i + 2], k4.z, s0); s1 = fmaf(q[4 * i + 3], k4.w, s1);
+    for (int d = 0; d < HD; ++d) q[d] = qs[d];
+    for (int j = tid; j < nk; j += ATT_NT) {
+      const float4* kr = reinterpret_cast<const float4*>(kh + (long)j * HD);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        const float4 k4 = kr[i];
+        s0 = fmaf(q[4 * i], k4.x, s0); s1 = fmaf(q[4 * i + 1], k4.y, s1);
+        s0 = fmaf(q[4 * i + 2], k4.z, s0); s1 = fmaf(q[4 * i + 3], k4.w, s1);
+      }
+      const float s = s0 + s1;
+      sc[j] = s;
+      mx = fmaxf(mx, s);
     }
-    const float s = s0 + s1;
-    sc[j] = s;
-    mx = fmaxf(mx, s);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) red[tid >> 5] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < ATT_NT / 32; ++i) mx = fmaxf(mx, red[i]);
   float sum = 0.f;
-  for (int j = tid; j < nk; j += 128) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  for (int j = tid; j < nk; j += ATT_NT) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
   sum = warp_sum_f(sum);
-  if ((tid & 31) == 0) red[4 + (tid >> 5)] = sum;
+  if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
   __syncthreads();
-  const float inv = 1.0f / (red[4] + red[5] + red[6] + red[7]);
-  // out[d] = sum_j p_j v[j][d]: two halves of the keys, 64 threads each
-  const int d = tid & (HD - 1), half = tid >> 6;
-  float o0 = 0.f, o1 = 0.f;
-  int j = half;
-  for (; j + 2 < nk; j += 4) {
-    o0 = fmaf(sc[j], vh[(long)j * HD + d], o0);
-    o1 = fmaf(sc[j + 2], vh[(long)(j + 2) * HD + d], o1);
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < ATT_NT / 32; ++i) tot += red[8 + i];
+  const float inv = 1.0f / tot;
+  // out[d] = sum_j p_j v[j][d]
+  const int g = tid >> 4, dq = tid & 15;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int j = g; j < nk; j += 16) {
+    const float p = sc[j];
+    const float4 v4 = *reinterpret_cast<const float4*>(vh + (long)j * HD + dq * 4);
+    o.x = fmaf(p, v4.x, o.x); o.y = fmaf(p, v4.y, o.y); o.z = fmaf(p, v4.z, o.z); o.w = fmaf(p, v4.w, o.w);
   }
-  for (; j < nk; j += 2) o0 = fmaf(sc[j], vh[(long)j * HD + d], o0);
-  part[half * HD + d] = o0 + o1;
+  *reinterpret_cast<float4*>(part + g * HD + dq * 4) = o;
   __syncthreads();
   if (tid < HD) {
-    const float v = (part[tid] + part[HD + tid]) * inv;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v += part[i * HD + tid];
+    v *= inv;
     if constexpr (sizeof(OutT) == 4) out[(long)r * D + h * HD + tid] = v;
     else out[(long)r * D + h * HD + tid] = __float2bfloat16(v);
   }
@@ -393,6 +427,282 @@ __global__ void kv_export_kernel(const float* __restrict__ kc, const float* __re
   key[((long)h * HD + d) * S + s] = kc[src];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent decode: ONE cooperative kernel runs whole decode calls (24 layers + head + pick, several tokens per launch).
+// A decode call is a chain of 122 dependent matrix-vector phases of 3-13 MB each; as separate kernels (even graph-replayed with
+// programmatic dependent launch) every link costs 7-10 us of launch, fill and drain against ~2 us of HBM time. Here the 148
+// CTAs stay resident, a grid barrier (one atomic per CTA) separates the phases, and every warp issues the loads of the weight
+// rows it owns in the NEXT phase before it arrives at the barrier, so the HBM stream never stops while the dependent part
+// (activation vector from L2, LayerNorm, FMAs, warp reduction) runs.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PLayer {
+  const __nv_bfloat16 *wqkv, *wo, *wfc, *wp;           // [N][K] bf16
+  const float *bqkv, *bo, *bfc, *bp, *ln1w, *ln1b, *ln2w, *ln2b;
+};
+struct PArgs {
+  const PLayer* layers;
+  int L, D, FF, H, Vm, S_max;
+  float eps;
+  const __nv_bfloat16* whead;
+  const float *bhead, *lnfw, *lnfb, *fnw, *fnb, *mel_emb, *mel_pos;
+  float *h, *qkv, *att, *ff, *logits, *kc, *vc;
+  int *state, *ids;
+  float *penalty, *hid_save;
+  unsigned int* bar;
+  int n_tokens;
+  LoopConst lc;
+};
+constexpr int P_NT = 512, P_NW = P_NT / 32, P_SLOTS = 20;
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of the (co-resident) grid; `target` = arrivals expected so far. A CTA that waits longer than ~2 s raises ST_ERR.
+__device__ __forceinline__ void grid_bar(unsigned int* bar, unsigned int target, int* state) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(bar) < target) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(&state[ST_ERR], 1); break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int CH, int MAXR>
+__device__ __forceinline__ void p_prefetch(uint4 (&wq)[P_SLOTS], const __nv_bfloat16* __restrict__ W, int N, int gw, int TW, int lane) {
+  constexpr int K = CH * 256;
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i) {
+    const int n = gw + i * TW;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (i * CH + c < P_SLOTS)
+        wq[i * CH + c] = n < N ? __ldg(reinterpret_cast<const uint4*>(W + (long)n * K + (c * 32 + lane) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int CH, int MAXR, typename Epi>
+__device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const __nv_bfloat16* __restrict__ W, int N, const float* xv, int gw,
+                                       int TW, int lane, Epi&& epi) {
+  constexpr int K = CH * 256;
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i) {
+    const int n = gw + i * TW;
+    if (n < N) {
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int k0 = (c * 32 + lane) * 8;
+        uint4 q;
+        if (i * CH + c < P_SLOTS) q = wq[i * CH + c];
+        else q = __ldg(reinterpret_cast<const uint4*>(W + (long)n * K + k0));
+        float w[8];
+        WVec<__nv_bfloat16>::unpack(q, w);
+        const float4 xa = *reinterpret_cast<const float4*>(xv + k0), xb = *reinterpret_cast<const float4*>(xv + k0 + 4);
+        acc0 = fmaf(w[0], xa.x, acc0); acc1 = fmaf(w[1], xa.y, acc1); acc0 = fmaf(w[2], xa.z, acc0); acc1 = fmaf(w[3], xa.w, acc1);
+        acc0 = fmaf(w[4], xb.x, acc0); acc1 = fmaf(w[5], xb.y, acc1); acc0 = fmaf(w[6], xb.z, acc0); acc1 = fmaf(w[7], xb.w, acc1);
+      }
+      const float v = warp_sum_f(acc0 + acc1);
+      if (lane == 0) epi(n, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void p_load_x(float* xs, const float* g, int K) {
+  for (int k = threadIdx.x; k < K; k += P_NT) xs[k] = __ldcg(g + k);
+  __syncthreads();
+}
+// LayerNorm src -> dst (shared), statistics per warp, one sixteenth of the row per warp; ends with a block barrier
+__device__ __forceinline__ void p_ln(const float* src, float* dst, int K, const float* lw, const float* lb, float eps, int warp, int lane) {
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += src[k];
+  const float mean = warp_sum_f(s) / (float)K;
+  float q = 0.f;
+  for (int k = lane; k < K; k += 32) { const float d = src[k] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum_f(q) / (float)K + eps);
+  const int per = (K + P_NW - 1) / P_NW, k1 = min(K, (warp + 1) * per);
+  for (int k = warp * per + lane; k < k1; k += 32) dst[k] = (src[k] - mean) * rstd * __ldg(lw + k) + __ldg(lb + k);
+  __syncthreads();
+}
+
+// one head of the single new row against the cache (same arithmetic as gpt_attn_kernel with rows == 1), 512 threads
+__device__ __forceinline__ void p_attention(const PArgs& a, int layer, int h, float* sc, float* part, float* red, float* qs) {
+  const int tid = threadIdx.x, D = a.D, S_max = a.S_max;
+  const int hist = __ldcg(a.state + ST_KV);
+  const float* qrow = a.qkv + h * HD;
+  float* kh = a.kc + ((long)layer * a.H + h) * S_max * HD;
+  float* vh = a.vc + ((long)layer * a.H + h) * S_max * HD;
+  if (tid < HD) { qs[tid] = __ldcg(qrow + tid); kh[(long)hist * HD + tid] = __ldcg(qrow + D + tid); }
+  else if (tid < 2 * HD) vh[(long)hist * HD + tid - HD] = __ldcg(qrow + 2 * D + tid - HD);
+  __syncthreads();
+  const int nk = hist + 1;
+  float mx = -3.0e38f;
+  for (int j = tid; j < nk; j += P_NT) {
+    const float4* kr = reinterpret_cast<const float4*>(kh + (long)j * HD);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 k4 = __ldcg(kr + i);
+      const float4 q4 = *reinterpret_cast<const float4*>(qs + 4 * i);
+      s0 = fmaf(q4.x, k4.x, s0); s1 = fmaf(q4.y, k4.y, s1); s0 = fmaf(q4.z, k4.z, s0); s1 = fmaf(q4.w, k4.w, s1);
+    }
+    const float s = s0 + s1;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < P_NW; ++i) mx = fmaxf(mx, red[i]);
+  float sum = 0.f;
+  for (int j = tid; j < nk; j += P_NT) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  sum = warp_sum_f(sum);
+  if ((tid & 31) == 0) red[P_NW + (tid >> 5)] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < P_NW; ++i) tot += red[P_NW + i];
+  const float inv = 1.0f / tot;
+  const int g = tid >> 4, dq = tid & 15;                   // 32 key groups x 16 float4 columns
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int j = g; j < nk; j += 32) {
+    const float p = sc[j];
+    const float4 v4 = __ldcg(reinterpret_cast<const float4*>(vh + (long)j * HD + dq * 4));
+    o.x = fmaf(p, v4.x, o.x); o.y = fmaf(p, v4.y, o.y); o.z = fmaf(p, v4.z, o.z); o.w = fmaf(p, v4.w, o.w);
+  }
+  *reinterpret_cast<float4*>(part + g * HD + dq * 4) = o;
+  __syncthreads();
+  if (tid < HD) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v += part[i * HD + tid];
+    a.att[h * HD + tid] = v * inv;
+  }
+}
+
+// argmax + loop bookkeeping of gpt_pick_kernel, by one CTA of 512 threads
+__device__ __forceinline__ void p_pick(const PArgs& a, float* redv, int* redi) {
+  __shared__ int s_tok, s_go, s_gen;
+  const int tid = threadIdx.x;
+  float best = -3.0e38f; int idx = 0x7fffffff;
+  for (int n = tid; n < a.Vm; n += P_NT) {
+    const float v = __ldcg(a.logits + n);
+    if (v > best) { best = v; idx = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if ((tid & 31) == 0) { redv[tid >> 5] = best; redi[tid >> 5] = idx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < P_NW; ++w)
+      if (redv[w] > best || (redv[w] == best && redi[w] < idx)) { best = redv[w]; idx = redi[w]; }
+    int* state = a.state;
+    s_tok = idx; s_go = 0; s_gen = 0;
+    if (!state[ST_STOP]) {
+      const int n = state[ST_N];
+      a.ids[n] = idx;
+      state[ST_N] = n + 1;
+      state[ST_KV] += 1;
+      if (idx == a.lc.stop_mel) {
+        state[ST_STOP] = 1;
+      } else {
+        a.penalty[idx] = a.lc.repeat_penalty;
+        const int rs = state[ST_RESET];
+        if (n + 1 > a.lc.range && a.ids[rs] != idx) { a.penalty[a.ids[rs]] = 1.0f; state[ST_RESET] = rs + 1; }
+        s_gen = state[ST_GEN];
+        state[ST_GEN] = s_gen + 1;
+        s_go = 1;
+        if (n + 1 >= state[ST_LIMIT]) state[ST_STOP] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_go) {
+    const float* e = a.mel_emb + (long)s_tok * a.D;
+    const float* p = a.mel_pos + (long)s_gen * a.D;
+    for (int k = tid; k < a.D; k += P_NT) a.h[k] = __ldg(e + k) + __ldg(p + k);
+  }
+}
+
+// CH_D = D / 256, CH_F = FF / 256; R_* = rows of that phase a warp may own (host checks ceil(N / warps) <= R_*)
+template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
+__global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
+  extern __shared__ float psm[];
+  const int D = a.D, FF = a.FF;
+  float* xs = psm;                       // FF
+  float* xn = xs + FF;                   // D
+  float* sc = xn + D;                    // S_max
+  float* part = sc + a.S_max;            // 32 * 64
+  float* red = part + 32 * HD;           // 2 * P_NW
+  float* qs = red + 2 * P_NW;            // 64
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gw = blockIdx.x * P_NW + warp, TW = gridDim.x * P_NW;
+  unsigned int nb = 0;
+  const unsigned int G = gridDim.x;
+  uint4 wq[P_SLOTS];
+  p_prefetch<CH_D, R_QKV>(wq, a.layers[0].wqkv, 3 * D, gw, TW, lane);
+  for (int t = 0; t < a.n_tokens; ++t) {
+    if (__ldcg(a.state + ST_STOP) || __ldcg(a.state + ST_ERR)) break;      // uniform: state only changes before a grid barrier
+    for (int l = 0; l < a.L; ++l) {
+      const PLayer& Ly = a.layers[l];
+      // qkv = W_qkv . LN1(h) + b
+      p_load_x(xs, a.h, D);
+      p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
+      p_gemv<CH_D, R_QKV>(wq, Ly.wqkv, 3 * D, xn, gw, TW, lane, [&](int n, float v) { a.qkv[n] = v + __ldg(Ly.bqkv + n); });
+      grid_bar(a.bar, ++nb * G, a.state);
+      // attention (one CTA per head); everyone fetches its rows of W_o meanwhile
+      if ((int)blockIdx.x < a.H) p_attention(a, l, blockIdx.x, sc, part, red, qs);
+      p_prefetch<CH_D, 1>(wq, Ly.wo, D, gw, TW, lane);
+      grid_bar(a.bar, ++nb * G, a.state);
+      // h += W_o . att + b
+      p_load_x(xs, a.att, D);
+      p_gemv<CH_D, 1>(wq, Ly.wo, D, xs, gw, TW, lane, [&](int n, float v) { a.h[n] = v + __ldg(Ly.bo + n) + __ldcg(a.h + n); });
+      p_prefetch<CH_D, R_FC>(wq, Ly.wfc, FF, gw, TW, lane);
+      grid_bar(a.bar, ++nb * G, a.state);
+      // ff = gelu_new(W_fc . LN2(h) + b)
+      p_load_x(xs, a.h, D);
+      p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
+      p_gemv<CH_D, R_FC>(wq, Ly.wfc, FF, xn, gw, TW, lane, [&](int n, float v) { a.ff[n] = gelu_new_f(v + __ldg(Ly.bfc + n)); });
+      p_prefetch<CH_F, 1>(wq, Ly.wp, D, gw, TW, lane);
+      grid_bar(a.bar, ++nb * G, a.state);
+      // h += W_p . ff + b
+      p_load_x(xs, a.ff, FF);
+      p_gemv<CH_F, 1>(wq, Ly.wp, D, xs, gw, TW, lane, [&](int n, float v) { a.h[n] = v + __ldg(Ly.bp + n) + __ldcg(a.h + n); });
+      if (l + 1 < a.L) p_prefetch<CH_D, R_QKV>(wq, a.layers[l + 1].wqkv, 3 * D, gw, TW, lane);
+      else p_prefetch<CH_D, R_HEAD>(wq, a.whead, a.Vm, gw, TW, lane);
+      grid_bar(a.bar, ++nb * G, a.state);
+    }
+    // head: ln_f (saved) -> final_norm -> mel_head * penalty
+    p_load_x(xs, a.h, D);
+    p_ln(xs, xn, D, a.lnfw, a.lnfb, a.eps, warp, lane);
+    if (blockIdx.x == 0) {
+      float* dst = a.hid_save + (long)__ldcg(a.state + ST_N) * D;
+      for (int k = tid; k < D; k += P_NT) dst[k] = xn[k];
+    }
+    p_ln(xn, xs, D, a.fnw, a.fnb, a.eps, warp, lane);
+    p_gemv<CH_D, R_HEAD>(wq, a.whead, a.Vm, xs, gw, TW, lane,
+                         [&](int n, float v) { a.logits[n] = (v + __ldg(a.bhead + n)) * __ldcg(a.penalty + n); });
+    p_prefetch<CH_D, R_QKV>(wq, a.layers[0].wqkv, 3 * D, gw, TW, lane);
+    grid_bar(a.bar, ++nb * G, a.state);
+    if (blockIdx.x == 0) p_pick(a, red, reinterpret_cast<int*>(red + P_NW));
+    grid_bar(a.bar, ++nb * G, a.state);
+  }
+}
+
 #define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
 
 void transpose_to(const float* in, float* out, int R, int C, cudaStream_t s) {
@@ -432,7 +742,19 @@ void prepare(Engine& e, GptModel& m, int precision) {
       }
     }
   }
-  if (fast) tc_weight_from_f32(m.head_tc, m.head_nk, 1, 1, m.Vm, D, s);
+  if (fast) {
+    tc_weight_from_f32(m.head_tc, m.head_nk, 1, 1, m.Vm, D, s);
+    std::vector<PLayer> pl(m.L);
+    for (int i = 0; i < m.L; ++i) {
+      GptLayer& Ly = m.layers[i];
+      pl[i] = PLayer{Ly.qkv_tc.w.p, Ly.o_tc.w.p, Ly.fc_tc.w.p, Ly.p_tc.w.p, Ly.qkv_b.p, Ly.o_b, Ly.fc_b, Ly.p_b,
+                     Ly.ln1_w, Ly.ln1_b, Ly.ln2_w, Ly.ln2_b};
+    }
+    m.players.alloc(pl.size() * sizeof(PLayer));
+    B2_CUDA(cudaMemcpyAsync(m.players.p, pl.data(), pl.size() * sizeof(PLayer), cudaMemcpyHostToDevice, s));
+    m.gbar.alloc(1);
+    B2_CUDA(cudaStreamSynchronize(s));            // pl is a stack object
+  }
   B2_CUDA(cudaStreamSynchronize(s));
   (fast ? m.bf16_ready : m.f32_ready) = true;
 }
@@ -442,9 +764,15 @@ void prepare(Engine& e, GptModel& m, int precision) {
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename WT, int PRE>
 void gemv(Engine& e, const char* tag, GemvArgs a) {
-  B2_CHECK(a.K % 8 == 0 && a.ldw % 8 == 0 && a.K * sizeof(float) <= 48 * 1024, "gemv: K must be a multiple of 8 and fit shared memory");
+  const size_t smem = (size_t)a.K * sizeof(float) * (PRE >= 1 ? 2 : 1);
+  B2_CHECK(a.K % 8 == 0 && a.ldw % 8 == 0 && smem <= 48 * 1024, "gemv: K must be a multiple of 8 and fit shared memory");
+  const int chunks = ceil_div((long)a.K, 32 * WVec<WT>::N);      // 16-byte chunks of a weight row per lane
   ProfScope ps(e.prof, tag, e.stream);
-  launch_pdl(gemv_kernel<WT, PRE>, dim3(ceil_div(a.N, 8)), dim3(256), (size_t)a.K * sizeof(float), e.stream, a);
+  const dim3 grid(ceil_div(a.N, 8)), block(256);
+  if (chunks >= 20) launch_pdl(gemv_kernel<WT, PRE, 20>, grid, block, smem, e.stream, a);
+  else if (chunks >= 10) launch_pdl(gemv_kernel<WT, PRE, 10>, grid, block, smem, e.stream, a);
+  else if (chunks >= 5) launch_pdl(gemv_kernel<WT, PRE, 5>, grid, block, smem, e.stream, a);
+  else launch_pdl(gemv_kernel<WT, PRE, 2>, grid, block, smem, e.stream, a);
   LAUNCHED();
 }
 
@@ -458,9 +786,9 @@ void attention(Engine& e, GptModel& m, int layer, const float* qkv, int rows, in
     kv_scatter_kernel<<<ceil_div((long)rows * m.D, 256), 256, 0, s>>>(qkv, kc, vc, m.state.p, rows, m.S_max, m.D);
     LAUNCHED();
   }
-  const size_t smem = (size_t)(m.S_max + HD + 2 * HD + 8) * sizeof(float);
+  const size_t smem = (size_t)(m.S_max + HD + 16 * HD + 16) * sizeof(float);
   ProfScope ps(e.prof, "igpt.attention", s);
-  launch_pdl(gpt_attn_kernel<OutT>, dim3(m.H, rows), dim3(128), smem, s, qkv, kc, vc, (const int*)m.state.p, m.S_max, m.D, m.H, causal, out);
+  launch_pdl(gpt_attn_kernel<OutT>, dim3(m.H, rows), dim3(ATT_NT), smem, s, qkv, kc, vc, (const int*)m.state.p, m.S_max, m.D, m.H, causal, out);
   LAUNCHED();
 }
 
@@ -555,6 +883,53 @@ void prefill_layers(Engine& e, GptModel& m, int rows, int causal, bool fast) {
   }
 }
 
+// Persistent decode (bf16 engine). Returns false when this model shape has no instantiation (the caller falls back to the
+// per-kernel graph path).
+template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
+void launch_persistent(Engine& e, GptModel& m, int n_tokens) {
+  cudaStream_t s = e.stream;
+  int dev = 0, sms = 0, coop = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  B2_CHECK(coop != 0, "persistent decode needs cooperative launch support");
+  const int TW = sms * P_NW;
+  B2_CHECK(ceil_div(3 * m.D, TW) <= R_QKV && ceil_div(m.FF, TW) <= R_FC && ceil_div(m.Vm, TW) <= R_HEAD && m.D <= TW,
+           "persistent decode: too few SMs for the row ownership this instantiation assumes");
+  auto kern = gpt_decode_kernel<CH_D, CH_F, R_QKV, R_FC, R_HEAD>;
+  const size_t smem = (size_t)(m.FF + m.D + m.S_max + 32 * HD + 2 * P_NW + HD) * sizeof(float);
+  static bool once = false;
+  if (!once) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P_NT, smem));
+    B2_CHECK(per_sm >= 1, "persistent decode kernel does not fit an SM");
+    once = true;
+  }
+  PArgs pa{};
+  pa.layers = reinterpret_cast<const PLayer*>(m.players.p);
+  pa.L = m.L; pa.D = m.D; pa.FF = m.FF; pa.H = m.H; pa.Vm = m.Vm; pa.S_max = m.S_max; pa.eps = m.eps;
+  pa.whead = m.head_tc.w.p; pa.bhead = m.head_b; pa.lnfw = m.lnf_w; pa.lnfb = m.lnf_b; pa.fnw = m.fn_w; pa.fnb = m.fn_b;
+  pa.mel_emb = m.mel_emb; pa.mel_pos = m.mel_pos;
+  pa.h = m.hcur.p; pa.qkv = m.qkv32.p; pa.att = m.att32.p; pa.ff = m.ff32.p; pa.logits = m.logits.p; pa.kc = m.kc.p; pa.vc = m.vc.p;
+  pa.state = m.state.p; pa.ids = m.ids.p; pa.penalty = m.penalty.p; pa.hid_save = m.hid_save.p; pa.bar = m.gbar.p;
+  pa.n_tokens = n_tokens; pa.lc = m.lc;
+  B2_CUDA(cudaMemsetAsync(m.gbar.p, 0, sizeof(unsigned int), s));
+  void* args[] = {&pa};
+  ProfScope ps(e.prof, "igpt.decode_persistent", s);
+  B2_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(sms), dim3(P_NT), args, smem, s));
+  LAUNCHED();
+}
+
+bool decode_persistent(Engine& e, GptModel& m, int n_tokens) {
+  const char* v = getenv("B200TTS_GPT_PERSIST");
+  if (v != nullptr && atoi(v) == 0) return false;
+  if (m.head_tc.ldc != m.D) return false;
+  if (m.D == 1280 && m.FF == 5120) { launch_persistent<5, 20, 2, 3, 4>(e, m, n_tokens); return true; }
+  if (m.D == 512 && m.FF == 2048 && m.Vm <= 2048) { launch_persistent<2, 8, 1, 1, 1>(e, m, n_tokens); return true; }
+  return false;
+}
+
 // One E call on the device state. x: rows > 1 -> m.hp holds the rows; rows == 1 -> m.hcur holds the row.
 void e_call(Engine& e, GptModel& m, int rows, int causal, bool fast, const float* penalty, int bookkeeping, float* save, int* id_out) {
   if (rows == 1) {
@@ -646,7 +1021,7 @@ GptModel* gpt_build(Engine& e) {
   B2_CUDA(cudaMemsetAsync(m.ids.p, 0, ((size_t)m.S_max + 1) * sizeof(int), s));
   B2_CUDA(cudaMemsetAsync(m.state.p, 0, ST_WORDS * sizeof(int), s));
   B2_CUDA(cudaMallocHost((void**)&m.h_state, ST_WORDS * sizeof(int)));
-  const size_t attn_smem = (size_t)(m.S_max + 3 * HD + 8) * sizeof(float);
+  const size_t attn_smem = (size_t)(m.S_max + 17 * HD + 16) * sizeof(float);
   B2_CHECK(attn_smem <= 200 * 1024, "igpt: cache capacity too large for the attention kernel's score buffer");
   B2_CUDA(cudaFuncSetAttribute(gpt_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   B2_CUDA(cudaFuncSetAttribute(gpt_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
@@ -754,17 +1129,19 @@ int gpt_generate(Engine& e, const float* d_conds, int cond_rows, const int* d_te
   m.resident = 0;
   // prefill: causal flag 1 (Inference:690), then single rows with flag 0 (:763-765)
   e_call(e, m, rows, 1, fast, m.penalty.p, 1, m.hid_save.p, nullptr);
-  const int chunk = 16;
+  const int chunk = 32;
   int produced = 0, stopped = 0;
   const std::vector<long long> key = {30, precision, (long long)(uintptr_t)m.hcur.p, (long long)(uintptr_t)m.kc.p};
   while (!stopped) {
     B2_CUDA(cudaMemcpyAsync(m.h_state, m.state.p, ST_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    B2_CHECK(m.h_state[ST_ERR] == 0, "gpt_generate: the persistent decode kernel timed out at a grid barrier");
     produced = m.h_state[ST_N];
     stopped = m.h_state[ST_STOP];
     if (stopped) break;
     int todo = limit - produced;
     if (todo > chunk) todo = chunk;
+    if (fast && decode_persistent(e, m, todo)) continue;   // one cooperative kernel for the whole chunk
     for (int i = 0; i < todo; ++i)                          // steps after a stop inside the chunk leave the state untouched
       run_graphed(e, key, [&] { e_call(e, m, 1, 0, fast, m.penalty.p, 1, m.hid_save.p, nullptr); }, [] {});
   }

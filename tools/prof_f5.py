@@ -11,7 +11,7 @@ import b200tts  # noqa: F401,E402
 from b200tts import capi, config, synth, weights  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--what", default="f5", choices=["f5", "bigvgan"])
+ap.add_argument("--what", default="f5", choices=["f5", "bigvgan", "igpt"])
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--frames", type=int, default=512)
@@ -29,6 +29,14 @@ if args.what == "f5":
     for _ in range(args.reps + 1):      # first call builds the bf16 weight layouts; profile the later ones
         pcm = eng.f5_synthesize(audio, ids, int(maxd[0]), noise, precision=capi.BF16, n_steps=args.steps)
     print("f5 ok", pcm.shape, eng.launch_count())
+elif args.what == "igpt":
+    cfg = config.INDEXTTS_GPT
+    eng.load_state("igpt", weights.igpt_engine_tensors(synth.igpt_state(555), cfg))
+    eng.indextts_gpt_build()
+    conds, ids = synth.igpt_inputs(900, 60, cfg)
+    for _ in range(args.reps + 1):      # first call builds the bf16 weight layouts
+        out = eng.indextts_gpt_generate(conds, ids, max_new=args.steps, precision=capi.BF16)
+    print("igpt ok", out[0][:8], eng.launch_count())
 else:
     eng.load_state("bigvgan", weights.bigvgan_engine_tensors(synth.bigvgan_state(1234)))
     eng.bigvgan_build()
