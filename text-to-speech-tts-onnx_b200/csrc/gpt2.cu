@@ -17,6 +17,7 @@
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -70,7 +71,7 @@ struct GptModel {
   DevBuf<int> idbuf;
   int* h_state = nullptr;                    // pinned
   DevBuf<unsigned char> players;             // device array of PLayer (persistent decode kernel)
-  DevBuf<unsigned int> gbar;                 // its grid-barrier counter
+  DevBuf<unsigned long long> tagged;         // its {value, epoch} vectors: h | qkv | att | ff | logits
 };
 
 namespace {
@@ -429,12 +430,20 @@ __global__ void kv_export_kernel(const float* __restrict__ kc, const float* __re
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Persistent decode: ONE cooperative kernel runs whole decode calls (24 layers + head + pick, several tokens per launch).
-// A decode call is a chain of 122 dependent matrix-vector phases of 3-13 MB each; as separate kernels (even graph-replayed with
-// programmatic dependent launch) every link costs 7-10 us of launch, fill and drain against ~2 us of HBM time. Here the 148
-// CTAs stay resident, a grid barrier (one atomic per CTA) separates the phases, and every warp issues the loads of the weight
-// rows it owns in the NEXT phase before it arrives at the barrier, so the HBM stream never stops while the dependent part
-// (activation vector from L2, LayerNorm, FMAs, warp reduction) runs.
+// A decode call is a chain of 122 dependent matrix-vector phases of 3-13 MB each. As separate kernels (graph-replayed, with
+// programmatic dependent launch) every link costs ~7 us against ~2 us of HBM time; a first persistent version with a grid
+// barrier per phase was no faster (ncu: 51 % of the warp samples parked at the barrier, profiles/r01). So there is no barrier:
+//   * every activation vector that crosses CTAs (h, qkv, att, ff, logits) is stored as 64-bit words {value, epoch}; a consumer
+//     polls the words it needs until they carry the epoch of the phase it is in, so "wait for the producers" and "fetch the
+//     vector" are the same L2 round trip, and no fence / atomic / flag sits between two phases;
+//   * a CTA takes part in a phase only if it owns output rows there, hence every reader of a vector is also a producer of
+//     the next one; since each output depends on the WHOLE input vector, a buffer can only be overwritten (one layer later)
+//     after all of its readers are done -- write-after-read safety follows from the data flow itself;
+//   * every warp issues the loads of the weight rows (and bias) it owns in its NEXT phase before it starts polling, so the
+//     HBM stream keeps running while the dependent part (poll, LayerNorm in shared memory, FMAs, warp reduction) executes.
+// The stop decision travels the same way: the pick phase tags the next token's h with a STOP epoch.
 // ---------------------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
 struct PLayer {
   const __nv_bfloat16 *wqkv, *wo, *wfc, *wp;           // [N][K] bf16
   const float *bqkv, *bo, *bfc, *bp, *ln1w, *ln1b, *ln2w, *ln2b;
@@ -445,37 +454,63 @@ struct PArgs {
   float eps;
   const __nv_bfloat16* whead;
   const float *bhead, *lnfw, *lnfb, *fnw, *fnb, *mel_emb, *mel_pos;
-  float *h, *qkv, *att, *ff, *logits, *kc, *vc;
+  u64 *th, *tqkv, *tatt, *tff, *tlogits;               // tagged vectors
+  float *hcur, *kc, *vc;
   int *state, *ids;
   float *penalty, *hid_save;
-  unsigned int* bar;
-  int n_tokens;
+  int n_tokens, n0;                                    // tokens to attempt in this launch; tokens produced before it
   LoopConst lc;
 };
-constexpr int P_NT = 512, P_NW = P_NT / 32, P_SLOTS = 20;
+constexpr int P_NT = 512, P_NW = P_NT / 32, P_SLOTS = 20, P_MAXR = 4;
+constexpr unsigned EP_STOP = 0xffffffffu;
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// all CTAs of the (co-resident) grid; `target` = arrivals expected so far. A CTA that waits longer than ~2 s raises ST_ERR.
-__device__ __forceinline__ void grid_bar(unsigned int* bar, unsigned int target, int* state) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const long long t0 = clock64();
-    while (ld_acquire_u32(bar) < target) {
-      if (clock64() - t0 > 4000000000LL) { atomicExch(&state[ST_ERR], 1); break; }
+__device__ __forceinline__ void st_tagged(u64* p, float v, unsigned ep) {
+  const u64 w = ((u64)ep << 32) | (u64)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {       // weights: read once, keep them out of L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// slow path of a poll: the word did not carry `want` yet. abort: 1 = STOP epoch seen, 2 = timed out (~2 s)
+__device__ __noinline__ u64 poll_slow(const u64* p, unsigned want, int* abort) {
+  const long long t0 = clock64();
+  u64 v = ld_relaxed_u64(p);
+  while ((unsigned)(v >> 32) != want) {
+    if ((unsigned)(v >> 32) == EP_STOP) { *abort = 1; break; }
+    if (clock64() - t0 > 4000000000LL) { *abort = 2; break; }
+    __nanosleep(40);
+    v = ld_relaxed_u64(p);
+  }
+  return v;
+}
+// K tagged words -> floats in shared memory; all loads of a thread are issued before the first one is checked
+template <int CE>
+__device__ __forceinline__ void p_poll_x(float* xs, const u64* g, int K, unsigned want, int* abort) {
+  u64 v[CE];
+  __syncthreads();                                       // xs may still be read by the previous phase of slower warps
+#pragma unroll
+  for (int i = 0; i < CE; ++i) { const int k = threadIdx.x + i * P_NT; v[i] = k < K ? ld_relaxed_u64(g + k) : 0ull; }
+#pragma unroll
+  for (int i = 0; i < CE; ++i) {
+    const int k = threadIdx.x + i * P_NT;
+    if (k < K) {
+      if ((unsigned)(v[i] >> 32) != want) v[i] = poll_slow(g + k, want, abort);
+      xs[k] = __uint_as_float((unsigned)v[i]);
     }
-    __threadfence();
   }
   __syncthreads();
 }
 
 template <int CH, int MAXR>
-__device__ __forceinline__ void p_prefetch(uint4 (&wq)[P_SLOTS], const __nv_bfloat16* __restrict__ W, int N, int gw, int TW, int lane) {
+__device__ __forceinline__ void p_prefetch(uint4 (&wq)[P_SLOTS], float (&bq)[P_MAXR], const __nv_bfloat16* __restrict__ W,
+                                           const float* __restrict__ bias, int N, int gw, int TW, int lane) {
   constexpr int K = CH * 256;
 #pragma unroll
   for (int i = 0; i < MAXR; ++i) {
@@ -483,13 +518,14 @@ __device__ __forceinline__ void p_prefetch(uint4 (&wq)[P_SLOTS], const __nv_bflo
 #pragma unroll
     for (int c = 0; c < CH; ++c)
       if (i * CH + c < P_SLOTS)
-        wq[i * CH + c] = n < N ? __ldg(reinterpret_cast<const uint4*>(W + (long)n * K + (c * 32 + lane) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        wq[i * CH + c] = n < N ? ldg_stream(W + (long)n * K + (c * 32 + lane) * 8) : make_uint4(0u, 0u, 0u, 0u);
+    bq[i] = n < N ? __ldg(bias + n) : 0.f;
   }
 }
 
 template <int CH, int MAXR, typename Epi>
-__device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const __nv_bfloat16* __restrict__ W, int N, const float* xv, int gw,
-                                       int TW, int lane, Epi&& epi) {
+__device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const float (&bq)[P_MAXR], const __nv_bfloat16* __restrict__ W, int N,
+                                       const float* xv, int gw, int TW, int lane, Epi&& epi) {
   constexpr int K = CH * 256;
 #pragma unroll
   for (int i = 0; i < MAXR; ++i) {
@@ -501,7 +537,7 @@ __device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const __nv_bf
         const int k0 = (c * 32 + lane) * 8;
         uint4 q;
         if (i * CH + c < P_SLOTS) q = wq[i * CH + c];
-        else q = __ldg(reinterpret_cast<const uint4*>(W + (long)n * K + k0));
+        else q = ldg_stream(W + (long)n * K + k0);
         float w[8];
         WVec<__nv_bfloat16>::unpack(q, w);
         const float4 xa = *reinterpret_cast<const float4*>(xv + k0), xb = *reinterpret_cast<const float4*>(xv + k0 + 4);
@@ -509,16 +545,12 @@ __device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const __nv_bf
         acc0 = fmaf(w[4], xb.x, acc0); acc1 = fmaf(w[5], xb.y, acc1); acc0 = fmaf(w[6], xb.z, acc0); acc1 = fmaf(w[7], xb.w, acc1);
       }
       const float v = warp_sum_f(acc0 + acc1);
-      if (lane == 0) epi(n, v);
+      if (lane == 0) epi(n, v + bq[i]);
     }
   }
 }
 
-__device__ __forceinline__ void p_load_x(float* xs, const float* g, int K) {
-  for (int k = threadIdx.x; k < K; k += P_NT) xs[k] = __ldcg(g + k);
-  __syncthreads();
-}
-// LayerNorm src -> dst (shared), statistics per warp, one sixteenth of the row per warp; ends with a block barrier
+// LayerNorm src -> dst (shared): statistics per warp, one sixteenth of the row normalised per warp; ends with a block barrier
 __device__ __forceinline__ void p_ln(const float* src, float* dst, int K, const float* lw, const float* lb, float eps, int warp, int lane) {
   float s = 0.f;
   for (int k = lane; k < K; k += 32) s += src[k];
@@ -532,14 +564,21 @@ __device__ __forceinline__ void p_ln(const float* src, float* dst, int K, const 
 }
 
 // one head of the single new row against the cache (same arithmetic as gpt_attn_kernel with rows == 1), 512 threads
-__device__ __forceinline__ void p_attention(const PArgs& a, int layer, int h, float* sc, float* part, float* red, float* qs) {
+__device__ __forceinline__ void p_attention(const PArgs& a, int layer, int h, int hist, unsigned ep, float* sc, float* part, float* red,
+                                            float* qs, int* abort) {
   const int tid = threadIdx.x, D = a.D, S_max = a.S_max;
-  const int hist = __ldcg(a.state + ST_KV);
-  const float* qrow = a.qkv + h * HD;
   float* kh = a.kc + ((long)layer * a.H + h) * S_max * HD;
   float* vh = a.vc + ((long)layer * a.H + h) * S_max * HD;
-  if (tid < HD) { qs[tid] = __ldcg(qrow + tid); kh[(long)hist * HD + tid] = __ldcg(qrow + D + tid); }
-  else if (tid < 2 * HD) vh[(long)hist * HD + tid - HD] = __ldcg(qrow + 2 * D + tid - HD);
+  if (tid < 3 * HD) {                                    // q | k | v of this head, 64 words each
+    const int part_id = tid >> 6, d = tid & (HD - 1);
+    const u64* src = a.tqkv + part_id * D + h * HD + d;
+    u64 v = ld_relaxed_u64(src);
+    if ((unsigned)(v >> 32) != ep) v = poll_slow(src, ep, abort);
+    const float f = __uint_as_float((unsigned)v);
+    if (part_id == 0) qs[d] = f;
+    else if (part_id == 1) kh[(long)hist * HD + d] = f;
+    else vh[(long)hist * HD + d] = f;
+  }
   __syncthreads();
   const int nk = hist + 1;
   float mx = -3.0e38f;
@@ -586,18 +625,29 @@ __device__ __forceinline__ void p_attention(const PArgs& a, int layer, int h, fl
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v += part[i * HD + tid];
-    a.att[h * HD + tid] = v * inv;
+    st_tagged(a.tatt + h * HD + tid, v * inv, ep);
   }
+  __syncthreads();                                       // sc / part / red are reused by the next layer
 }
 
-// argmax + loop bookkeeping of gpt_pick_kernel, by one CTA of 512 threads
-__device__ __forceinline__ void p_pick(const PArgs& a, float* redv, int* redi) {
+// argmax over the tagged logits + the loop bookkeeping of gpt_pick_kernel, by CTA 0; publishes the next token's h
+__device__ __forceinline__ void p_pick(const PArgs& a, unsigned ep_logits, unsigned ep_h_next, float* redv, int* redi, int* abort) {
   __shared__ int s_tok, s_go, s_gen;
   const int tid = threadIdx.x;
   float best = -3.0e38f; int idx = 0x7fffffff;
-  for (int n = tid; n < a.Vm; n += P_NT) {
-    const float v = __ldcg(a.logits + n);
-    if (v > best) { best = v; idx = n; }
+  for (int n0 = 0; n0 < a.Vm; n0 += 8 * P_NT) {
+    u64 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int n = n0 + i * P_NT + tid; v[i] = n < a.Vm ? ld_relaxed_u64(a.tlogits + n) : 0ull; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i * P_NT + tid;
+      if (n < a.Vm) {
+        if ((unsigned)(v[i] >> 32) != ep_logits) v[i] = poll_slow(a.tlogits + n, ep_logits, abort);
+        const float f = __uint_as_float((unsigned)v[i]);
+        if (f > best) { best = f; idx = n; }
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -612,7 +662,7 @@ __device__ __forceinline__ void p_pick(const PArgs& a, float* redv, int* redi) {
       if (redv[w] > best || (redv[w] == best && redi[w] < idx)) { best = redv[w]; idx = redi[w]; }
     int* state = a.state;
     s_tok = idx; s_go = 0; s_gen = 0;
-    if (!state[ST_STOP]) {
+    if (!*abort) {
       const int n = state[ST_N];
       a.ids[n] = idx;
       state[ST_N] = n + 1;
@@ -629,12 +679,17 @@ __device__ __forceinline__ void p_pick(const PArgs& a, float* redv, int* redi) {
         if (n + 1 >= state[ST_LIMIT]) state[ST_STOP] = 1;
       }
     }
+    __threadfence();                                     // ids / penalty / state before the tagged h that announces them
   }
   __syncthreads();
-  if (s_go) {
-    const float* e = a.mel_emb + (long)s_tok * a.D;
-    const float* p = a.mel_pos + (long)s_gen * a.D;
-    for (int k = tid; k < a.D; k += P_NT) a.h[k] = __ldg(e + k) + __ldg(p + k);
+  __threadfence();
+  const bool stop = a.state[ST_STOP] != 0 || *abort;
+  const float* e = a.mel_emb + (long)s_tok * a.D;
+  const float* p = a.mel_pos + (long)s_gen * a.D;
+  for (int k = tid; k < a.D; k += P_NT) {
+    const float hv = s_go ? __ldg(e + k) + __ldg(p + k) : 0.f;
+    if (s_go) a.hcur[k] = hv;                            // plain copy for the host / the next launch
+    st_tagged(a.th + k, hv, stop ? EP_STOP : ep_h_next);
   }
 }
 
@@ -642,7 +697,9 @@ __device__ __forceinline__ void p_pick(const PArgs& a, float* redv, int* redi) {
 template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
 __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
   extern __shared__ float psm[];
-  const int D = a.D, FF = a.FF;
+  __shared__ int s_abort;
+  const int D = a.D, FF = a.FF, L = a.L;
+  constexpr int CE_D = (CH_D * 256 + P_NT - 1) / P_NT, CE_F = (CH_F * 256 + P_NT - 1) / P_NT;
   float* xs = psm;                       // FF
   float* xn = xs + FF;                   // D
   float* sc = xn + D;                    // S_max
@@ -651,56 +708,87 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
   float* qs = red + 2 * P_NW;            // 64
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gw = blockIdx.x * P_NW + warp, TW = gridDim.x * P_NW;
-  unsigned int nb = 0;
-  const unsigned int G = gridDim.x;
+  const int gw0 = blockIdx.x * P_NW;     // a CTA takes part in a phase iff it owns a row there (rows are dealt warp by warp)
+  const bool in_qkv = gw0 < 3 * D, in_d = gw0 < D, in_fc = gw0 < FF, in_head = gw0 < a.Vm, in_att = (int)blockIdx.x < a.H;
+  if (tid == 0) s_abort = 0;
+  __syncthreads();
   uint4 wq[P_SLOTS];
-  p_prefetch<CH_D, R_QKV>(wq, a.layers[0].wqkv, 3 * D, gw, TW, lane);
+  float bq[P_MAXR];
+  float hreg = 0.f;
+  const int hist0 = a.state[ST_KV];      // set by the host before the launch; +1 per token
+  if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
   for (int t = 0; t < a.n_tokens; ++t) {
-    if (__ldcg(a.state + ST_STOP) || __ldcg(a.state + ST_ERR)) break;      // uniform: state only changes before a grid barrier
-    for (int l = 0; l < a.L; ++l) {
+    const unsigned eh0 = 1u + (unsigned)t * (2u * L + 1u);
+    for (int l = 0; l < L; ++l) {
       const PLayer& Ly = a.layers[l];
-      // qkv = W_qkv . LN1(h) + b
-      p_load_x(xs, a.h, D);
-      p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
-      p_gemv<CH_D, R_QKV>(wq, Ly.wqkv, 3 * D, xn, gw, TW, lane, [&](int n, float v) { a.qkv[n] = v + __ldg(Ly.bqkv + n); });
-      grid_bar(a.bar, ++nb * G, a.state);
-      // attention (one CTA per head); everyone fetches its rows of W_o meanwhile
-      if ((int)blockIdx.x < a.H) p_attention(a, l, blockIdx.x, sc, part, red, qs);
-      p_prefetch<CH_D, 1>(wq, Ly.wo, D, gw, TW, lane);
-      grid_bar(a.bar, ++nb * G, a.state);
-      // h += W_o . att + b
-      p_load_x(xs, a.att, D);
-      p_gemv<CH_D, 1>(wq, Ly.wo, D, xs, gw, TW, lane, [&](int n, float v) { a.h[n] = v + __ldg(Ly.bo + n) + __ldcg(a.h + n); });
-      p_prefetch<CH_D, R_FC>(wq, Ly.wfc, FF, gw, TW, lane);
-      grid_bar(a.bar, ++nb * G, a.state);
-      // ff = gelu_new(W_fc . LN2(h) + b)
-      p_load_x(xs, a.h, D);
-      p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
-      p_gemv<CH_D, R_FC>(wq, Ly.wfc, FF, xn, gw, TW, lane, [&](int n, float v) { a.ff[n] = gelu_new_f(v + __ldg(Ly.bfc + n)); });
-      p_prefetch<CH_F, 1>(wq, Ly.wp, D, gw, TW, lane);
-      grid_bar(a.bar, ++nb * G, a.state);
-      // h += W_p . ff + b
-      p_load_x(xs, a.ff, FF);
-      p_gemv<CH_F, 1>(wq, Ly.wp, D, xs, gw, TW, lane, [&](int n, float v) { a.h[n] = v + __ldg(Ly.bp + n) + __ldcg(a.h + n); });
-      if (l + 1 < a.L) p_prefetch<CH_D, R_QKV>(wq, a.layers[l + 1].wqkv, 3 * D, gw, TW, lane);
-      else p_prefetch<CH_D, R_HEAD>(wq, a.whead, a.Vm, gw, TW, lane);
-      grid_bar(a.bar, ++nb * G, a.state);
+      const unsigned ev = 1u + (unsigned)(t * L + l);       // epoch of qkv / att / ff
+      const unsigned eh = eh0 + 2u * l;                     // epoch of h entering the layer
+      if (in_qkv) {
+        // qkv = W_qkv . LN1(h) + b
+        p_poll_x<CE_D>(xs, a.th, D, eh, &s_abort);
+        if (s_abort) goto done;
+        if (lane == 0 && gw < D) hreg = xs[gw];            // residual operand of the rows this warp owns
+        p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
+        p_gemv<CH_D, R_QKV>(wq, bq, Ly.wqkv, 3 * D, xn, gw, TW, lane, [&](int n, float v) { st_tagged(a.tqkv + n, v, ev); });
+      }
+      if (in_att) p_attention(a, l, blockIdx.x, hist0 + t, ev, sc, part, red, qs, &s_abort);
+      if (in_d) {
+        // h += W_o . att + b
+        p_prefetch<CH_D, 1>(wq, bq, Ly.wo, Ly.bo, D, gw, TW, lane);
+        p_poll_x<CE_D>(xs, a.tatt, D, ev, &s_abort);
+        if (s_abort) goto done;
+        p_gemv<CH_D, 1>(wq, bq, Ly.wo, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 1u); });
+      }
+      if (in_fc) {
+        // ff = gelu_new(W_fc . LN2(h) + b)
+        p_prefetch<CH_D, R_FC>(wq, bq, Ly.wfc, Ly.bfc, FF, gw, TW, lane);
+        p_poll_x<CE_D>(xs, a.th, D, eh + 1u, &s_abort);
+        if (s_abort) goto done;
+        if (lane == 0 && gw < D) hreg = xs[gw];
+        p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
+        p_gemv<CH_D, R_FC>(wq, bq, Ly.wfc, FF, xn, gw, TW, lane, [&](int n, float v) { st_tagged(a.tff + n, gelu_new_f(v), ev); });
+      }
+      if (in_d) {
+        // h += W_p . ff + b
+        p_prefetch<CH_F, 1>(wq, bq, Ly.wp, Ly.bp, D, gw, TW, lane);
+        p_poll_x<CE_F>(xs, a.tff, FF, ev, &s_abort);
+        if (s_abort) goto done;
+        p_gemv<CH_F, 1>(wq, bq, Ly.wp, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 2u); });
+      }
+      if (l + 1 < L) {
+        if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gw, TW, lane);
+      } else if (in_head) {
+        p_prefetch<CH_D, R_HEAD>(wq, bq, a.whead, a.bhead, a.Vm, gw, TW, lane);
+      }
     }
-    // head: ln_f (saved) -> final_norm -> mel_head * penalty
-    p_load_x(xs, a.h, D);
-    p_ln(xs, xn, D, a.lnfw, a.lnfb, a.eps, warp, lane);
-    if (blockIdx.x == 0) {
-      float* dst = a.hid_save + (long)__ldcg(a.state + ST_N) * D;
-      for (int k = tid; k < D; k += P_NT) dst[k] = xn[k];
+    if (in_head) {
+      // head: ln_f (saved) -> final_norm -> mel_head * penalty
+      p_poll_x<CE_D>(xs, a.th, D, eh0 + 2u * L, &s_abort);
+      if (s_abort) goto done;
+      __threadfence();                                     // the penalty vector written by the previous pick
+      p_ln(xs, xn, D, a.lnfw, a.lnfb, a.eps, warp, lane);
+      if (blockIdx.x == 0) {
+        float* dst = a.hid_save + (long)(a.n0 + t) * D;
+        for (int k = tid; k < D; k += P_NT) dst[k] = xn[k];
+      }
+      p_ln(xn, xs, D, a.fnw, a.fnb, a.eps, warp, lane);
+      p_gemv<CH_D, R_HEAD>(wq, bq, a.whead, a.Vm, xs, gw, TW, lane,
+                           [&](int n, float v) { st_tagged(a.tlogits + n, v * __ldcg(a.penalty + n), 1u + (unsigned)t); });
     }
-    p_ln(xn, xs, D, a.fnw, a.fnb, a.eps, warp, lane);
-    p_gemv<CH_D, R_HEAD>(wq, a.whead, a.Vm, xs, gw, TW, lane,
-                         [&](int n, float v) { a.logits[n] = (v + __ldg(a.bhead + n)) * __ldcg(a.penalty + n); });
-    p_prefetch<CH_D, R_QKV>(wq, a.layers[0].wqkv, 3 * D, gw, TW, lane);
-    grid_bar(a.bar, ++nb * G, a.state);
-    if (blockIdx.x == 0) p_pick(a, red, reinterpret_cast<int*>(red + P_NW));
-    grid_bar(a.bar, ++nb * G, a.state);
+    if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
+    if (blockIdx.x == 0) p_pick(a, 1u + (unsigned)t, eh0 + 2u * L + 1u, red, reinterpret_cast<int*>(red + P_NW), &s_abort);
   }
+done:
+  if (tid == 0 && s_abort == 2) atomicExch(a.state + ST_ERR, 1);
+}
+
+// tags of a new launch: h <- hcur with epoch 1, every other word epoch 0
+__global__ void gpt_tag_init_kernel(u64* th, u64* tqkv, u64* tatt, u64* tff, u64* tlogits, const float* hcur, int D, int FF, int Vm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D) { th[i] = ((u64)1u << 32) | (u64)__float_as_uint(hcur[i]); tatt[i] = 0ull; }
+  if (i < 3 * D) tqkv[i] = 0ull;
+  if (i < FF) tff[i] = 0ull;
+  if (i < Vm) tlogits[i] = 0ull;
 }
 
 #define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
@@ -752,7 +840,6 @@ void prepare(Engine& e, GptModel& m, int precision) {
     }
     m.players.alloc(pl.size() * sizeof(PLayer));
     B2_CUDA(cudaMemcpyAsync(m.players.p, pl.data(), pl.size() * sizeof(PLayer), cudaMemcpyHostToDevice, s));
-    m.gbar.alloc(1);
     B2_CUDA(cudaStreamSynchronize(s));            // pl is a stack object
   }
   B2_CUDA(cudaStreamSynchronize(s));
@@ -886,7 +973,7 @@ void prefill_layers(Engine& e, GptModel& m, int rows, int causal, bool fast) {
 // Persistent decode (bf16 engine). Returns false when this model shape has no instantiation (the caller falls back to the
 // per-kernel graph path).
 template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
-void launch_persistent(Engine& e, GptModel& m, int n_tokens) {
+void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   cudaStream_t s = e.stream;
   int dev = 0, sms = 0, coop = 0;
   B2_CUDA(cudaGetDevice(&dev));
@@ -911,22 +998,29 @@ void launch_persistent(Engine& e, GptModel& m, int n_tokens) {
   pa.L = m.L; pa.D = m.D; pa.FF = m.FF; pa.H = m.H; pa.Vm = m.Vm; pa.S_max = m.S_max; pa.eps = m.eps;
   pa.whead = m.head_tc.w.p; pa.bhead = m.head_b; pa.lnfw = m.lnf_w; pa.lnfb = m.lnf_b; pa.fnw = m.fn_w; pa.fnb = m.fn_b;
   pa.mel_emb = m.mel_emb; pa.mel_pos = m.mel_pos;
-  pa.h = m.hcur.p; pa.qkv = m.qkv32.p; pa.att = m.att32.p; pa.ff = m.ff32.p; pa.logits = m.logits.p; pa.kc = m.kc.p; pa.vc = m.vc.p;
-  pa.state = m.state.p; pa.ids = m.ids.p; pa.penalty = m.penalty.p; pa.hid_save = m.hid_save.p; pa.bar = m.gbar.p;
-  pa.n_tokens = n_tokens; pa.lc = m.lc;
-  B2_CUDA(cudaMemsetAsync(m.gbar.p, 0, sizeof(unsigned int), s));
+  const size_t nt = (size_t)m.D * 5 + m.FF + m.Vm;
+  m.tagged.reserve(nt);
+  pa.th = m.tagged.p; pa.tqkv = pa.th + m.D; pa.tatt = pa.tqkv + 3 * m.D; pa.tff = pa.tatt + m.D; pa.tlogits = pa.tff + m.FF;
+  pa.hcur = m.hcur.p; pa.kc = m.kc.p; pa.vc = m.vc.p;
+  pa.state = m.state.p; pa.ids = m.ids.p; pa.penalty = m.penalty.p; pa.hid_save = m.hid_save.p;
+  pa.n_tokens = n_tokens; pa.n0 = n0; pa.lc = m.lc;
+  {
+    const int big = std::max(std::max(3 * m.D, m.FF), m.Vm);
+    gpt_tag_init_kernel<<<ceil_div(big, 256), 256, 0, s>>>(pa.th, pa.tqkv, pa.tatt, pa.tff, pa.tlogits, m.hcur.p, m.D, m.FF, m.Vm);
+    LAUNCHED();
+  }
   void* args[] = {&pa};
   ProfScope ps(e.prof, "igpt.decode_persistent", s);
   B2_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(sms), dim3(P_NT), args, smem, s));
   LAUNCHED();
 }
 
-bool decode_persistent(Engine& e, GptModel& m, int n_tokens) {
+bool decode_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   const char* v = getenv("B200TTS_GPT_PERSIST");
   if (v != nullptr && atoi(v) == 0) return false;
   if (m.head_tc.ldc != m.D) return false;
-  if (m.D == 1280 && m.FF == 5120) { launch_persistent<5, 20, 2, 3, 4>(e, m, n_tokens); return true; }
-  if (m.D == 512 && m.FF == 2048 && m.Vm <= 2048) { launch_persistent<2, 8, 1, 1, 1>(e, m, n_tokens); return true; }
+  if (m.D == 1280 && m.FF == 5120) { launch_persistent<5, 20, 2, 3, 4>(e, m, n_tokens, n0); return true; }
+  if (m.D == 512 && m.FF == 2048 && m.Vm <= 2048) { launch_persistent<2, 8, 1, 1, 1>(e, m, n_tokens, n0); return true; }
   return false;
 }
 
@@ -1141,7 +1235,7 @@ int gpt_generate(Engine& e, const float* d_conds, int cond_rows, const int* d_te
     if (stopped) break;
     int todo = limit - produced;
     if (todo > chunk) todo = chunk;
-    if (fast && decode_persistent(e, m, todo)) continue;   // one cooperative kernel for the whole chunk
+    if (fast && decode_persistent(e, m, todo, produced)) continue;   // one cooperative kernel for the whole chunk
     for (int i = 0; i < todo; ++i)                          // steps after a stop inside the chunk leave the state untouched
       run_graphed(e, key, [&] { e_call(e, m, 1, 0, fast, m.penalty.p, 1, m.hid_save.p, nullptr); }, [] {});
   }
