@@ -88,6 +88,54 @@ def test_f32_per_call_session_path_matches_device_loop(small, g):
     assert np.abs(val - g["value0"][:, :S, :].astype(np.float32)).max() <= 1e-2
 
 
+def test_onnxruntime_style_sessions_drive_the_reference_loop(small, g):
+    """The five sessions of Inference_IndexTTS_ONNX.py (B, C, D, E; F is covered in test_gpu_indextts.py) behind the
+    InferenceSession / OrtValue surface, driven by that script's loop with its own variable plumbing."""
+    from b200tts import session as ort
+    eng, sd, conds, text_ids = small
+    ort.register_checkpoint("indextts_gpt", sd)
+    ort.register_checkpoint("indextts_gpt_config", SMALL)
+    ort._igpt_ready.clear()
+    kw = dict(precision="fp32")
+    sB, sC, sD, sE = (ort.InferenceSession(f"/models/IndexTTS_{k}.onnx", **kw) for k in "BCDE")
+    in_E = [i.name for i in sE.get_inputs()]
+    out_E = [o.name for o in sE.get_outputs()]
+    L = SMALL.layers
+    assert in_E[:2] == ["in_key_0", "in_key_1"] and in_E[2 * L:] == ["history_len", "repeat_penality", "ids_len", "hidden_state", "attention_mask"]
+    assert out_E[2 * L:] == ["kv_seq_len", "last_hidden_state", "max_logit_id"]
+    OV = ort.OrtValue
+    text_h = sB.run_with_ort_values(["text_hidden_state"], {"text_ids": OV.ortvalue_from_numpy(text_ids)})[0]
+    gpt_h, gen_len = sC.run_with_ort_values(None, {"gpt_ids": OV.ortvalue_from_numpy(np.array([[SMALL.start_mel]], np.int32)),
+                                                   "kv_seq_len": OV.ortvalue_from_numpy(np.array([0], np.int64))})
+    gpt_h, concat_len = sD.run_with_ort_values(None, {"embed_x": OV.ortvalue_from_numpy(conds), "embed_y": text_h, "embed_z": gpt_h})
+    feed = {n: OV.ortvalue_from_numpy(np.zeros((SMALL.heads, 64, 0), np.float32)) for n in in_E[:L]}
+    feed.update({n: OV.ortvalue_from_numpy(np.zeros((SMALL.heads, 0, 64), np.float32)) for n in in_E[L:2 * L]})
+    pen = np.ones((1, SMALL.mel_codes), np.float32)
+    feed.update({"history_len": OV.ortvalue_from_numpy(np.array([0], np.int64)), "repeat_penality": OV.ortvalue_from_numpy(pen),
+                 "ids_len": concat_len, "attention_mask": OV.ortvalue_from_numpy(np.array([1], np.int8))})
+    ids, reset = [], 0
+    for n in range(1, 13):
+        feed["hidden_state"] = gpt_h
+        outs = sE.run_with_ort_values(out_E, feed)
+        mid = OV.numpy(outs[-1])
+        ids.append(int(mid[0, 0]))
+        if n < 2:
+            feed["attention_mask"] = OV.ortvalue_from_numpy(np.array([0], np.int8))
+            feed["ids_len"] = OV.ortvalue_from_numpy(np.array([1], np.int64))
+        for i in range(2 * L + 1):
+            feed[in_E[i]] = outs[i]
+        pen = OV.numpy(feed["repeat_penality"])
+        pen[:, ids[-1]] = SMALL.repeat_penalty
+        if n > SMALL.penalty_range and ids[reset] != ids[-1]:
+            pen[:, ids[reset]] = 1.0
+            reset += 1
+        feed["repeat_penality"] = OV.ortvalue_from_numpy(pen)
+        gpt_h, gen_len = sC.run_with_ort_values(None, {"gpt_ids": outs[-1], "kv_seq_len": gen_len})
+    np.testing.assert_array_equal(np.asarray(ids, np.int32), g["ids"][:12])
+    k0 = OV.numpy(outs[0])
+    assert k0.shape == (SMALL.heads, 64, int(OV.numpy(outs[2 * L])[0]))
+
+
 def test_history_mismatch_is_an_error(small):
     eng, sd, conds, text_ids = small
     pen = np.ones((1, SMALL.mel_codes), np.float32)

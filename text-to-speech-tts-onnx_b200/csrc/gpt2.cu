@@ -25,6 +25,7 @@
 #include "layout.cuh"
 #include "rowgemm.cuh"
 #include "rowgemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace b200tts {
 
@@ -459,9 +460,10 @@ struct PArgs {
   int *state, *ids;
   float *penalty, *hid_save;
   int n_tokens, n0;                                    // tokens to attempt in this launch; tokens produced before it
+  int buf_bytes;                                       // one half of the shared-memory weight double buffer
   LoopConst lc;
 };
-constexpr int P_NT = 512, P_NW = P_NT / 32, P_SLOTS = 20, P_MAXR = 4;
+constexpr int P_NT = 512, P_NW = P_NT / 32;
 constexpr unsigned EP_STOP = 0xffffffffu;
 
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
@@ -508,45 +510,44 @@ __device__ __forceinline__ void p_poll_x(float* xs, const u64* g, int K, unsigne
   __syncthreads();
 }
 
-template <int CH, int MAXR>
-__device__ __forceinline__ void p_prefetch(uint4 (&wq)[P_SLOTS], float (&bq)[P_MAXR], const __nv_bfloat16* __restrict__ W,
-                                           const float* __restrict__ bias, int N, int gw, int TW, int lane) {
-  constexpr int K = CH * 256;
-#pragma unroll
-  for (int i = 0; i < MAXR; ++i) {
-    const int n = gw + i * TW;
-#pragma unroll
-    for (int c = 0; c < CH; ++c)
-      if (i * CH + c < P_SLOTS)
-        wq[i * CH + c] = n < N ? ldg_stream(W + (long)n * K + (c * 32 + lane) * 8) : make_uint4(0u, 0u, 0u, 0u);
-    bq[i] = n < N ? __ldg(bias + n) : 0.f;
-  }
+// Weight rows [r0, r1) of a projection (row = ch * 512 bytes of bf16) -> shared memory, as one bulk copy per row issued by the
+// warp that will consume it; completion is counted in bytes on `bar`. The caller has synchronised the CTA after the last
+// reader of `buf`.
+struct PJob {
+  const __nv_bfloat16* W; const float* bias; int r0, r1, ch;
+};
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(smem_dst)), "l"((uint64_t)gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void p_issue(const PJob& j, unsigned char* buf, uint64_t* bar, int warp, int lane) {
+  const uint32_t rb = (uint32_t)j.ch * 512u;
+  __syncthreads();
+  if (threadIdx.x == 0) tc::mbar_expect_tx(bar, (uint32_t)(j.r1 - j.r0) * rb);
+  __syncthreads();
+  if (lane == 0)
+    for (int r = j.r0 + warp; r < j.r1; r += P_NW)
+      bulk_g2s(buf + (size_t)(r - j.r0) * rb, j.W + (size_t)r * (size_t)(j.ch * 256), rb, bar);
 }
 
-template <int CH, int MAXR, typename Epi>
-__device__ __forceinline__ void p_gemv(const uint4 (&wq)[P_SLOTS], const float (&bq)[P_MAXR], const __nv_bfloat16* __restrict__ W, int N,
-                                       const float* xv, int gw, int TW, int lane, Epi&& epi) {
-  constexpr int K = CH * 256;
+template <int CH, typename Epi>
+__device__ __forceinline__ void p_gemv(const PJob& j, const unsigned char* buf, const float* xv, int warp, int lane, Epi&& epi) {
+  for (int r = j.r0 + warp; r < j.r1; r += P_NW) {
+    const uint4* wr = reinterpret_cast<const uint4*>(buf + (size_t)(r - j.r0) * (CH * 512));
+    const float b = __ldg(j.bias + r);
+    float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXR; ++i) {
-    const int n = gw + i * TW;
-    if (n < N) {
-      float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int k0 = (c * 32 + lane) * 8;
-        uint4 q;
-        if (i * CH + c < P_SLOTS) q = wq[i * CH + c];
-        else q = ldg_stream(W + (long)n * K + k0);
-        float w[8];
-        WVec<__nv_bfloat16>::unpack(q, w);
-        const float4 xa = *reinterpret_cast<const float4*>(xv + k0), xb = *reinterpret_cast<const float4*>(xv + k0 + 4);
-        acc0 = fmaf(w[0], xa.x, acc0); acc1 = fmaf(w[1], xa.y, acc1); acc0 = fmaf(w[2], xa.z, acc0); acc1 = fmaf(w[3], xa.w, acc1);
-        acc0 = fmaf(w[4], xb.x, acc0); acc1 = fmaf(w[5], xb.y, acc1); acc0 = fmaf(w[6], xb.z, acc0); acc1 = fmaf(w[7], xb.w, acc1);
-      }
-      const float v = warp_sum_f(acc0 + acc1);
-      if (lane == 0) epi(n, v + bq[i]);
+    for (int c = 0; c < CH; ++c) {
+      const int k0 = (c * 32 + lane) * 8;
+      const uint4 q = wr[c * 32 + lane];
+      float w[8];
+      WVec<__nv_bfloat16>::unpack(q, w);
+      const float4 xa = *reinterpret_cast<const float4*>(xv + k0), xb = *reinterpret_cast<const float4*>(xv + k0 + 4);
+      acc0 = fmaf(w[0], xa.x, acc0); acc1 = fmaf(w[1], xa.y, acc1); acc0 = fmaf(w[2], xa.z, acc0); acc1 = fmaf(w[3], xa.w, acc1);
+      acc0 = fmaf(w[4], xb.x, acc0); acc1 = fmaf(w[5], xb.y, acc1); acc0 = fmaf(w[6], xb.z, acc0); acc1 = fmaf(w[7], xb.w, acc1);
     }
+    const float v = warp_sum_f(acc0 + acc1);
+    if (lane == 0) epi(r, v + b);
   }
 }
 
@@ -693,92 +694,137 @@ __device__ __forceinline__ void p_pick(const PArgs& a, unsigned ep_logits, unsig
   }
 }
 
-// CH_D = D / 256, CH_F = FF / 256; R_* = rows of that phase a warp may own (host checks ceil(N / warps) <= R_*)
-template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
+// CH_D = D / 256, CH_F = FF / 256 (16-byte chunks per lane of a weight row).
+// Every projection's rows are dealt to the CTAs in equal contiguous ranges; a CTA's share of the NEXT projection streams into
+// the free half of a double buffer in shared memory (bulk copies, mbarrier completion) while the current phase polls, normalises
+// and multiplies -- the copies run on the TMA path, so the small polling loads are not queued behind them.
+template <int CH_D, int CH_F>
 __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
-  extern __shared__ float psm[];
+  extern __shared__ __align__(128) unsigned char psm_raw[];
   __shared__ int s_abort;
+  __shared__ __align__(8) uint64_t bars[2];
   const int D = a.D, FF = a.FF, L = a.L;
   constexpr int CE_D = (CH_D * 256 + P_NT - 1) / P_NT, CE_F = (CH_F * 256 + P_NT - 1) / P_NT;
-  float* xs = psm;                       // FF
+  unsigned char* bufs[2] = {psm_raw, psm_raw + a.buf_bytes};
+  float* xs = reinterpret_cast<float*>(psm_raw + 2 * (size_t)a.buf_bytes);   // FF
   float* xn = xs + FF;                   // D
   float* sc = xn + D;                    // S_max
   float* part = sc + a.S_max;            // 32 * 64
   float* red = part + 32 * HD;           // 2 * P_NW
   float* qs = red + 2 * P_NW;            // 64
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gw = blockIdx.x * P_NW + warp, TW = gridDim.x * P_NW;
-  const int gw0 = blockIdx.x * P_NW;     // a CTA takes part in a phase iff it owns a row there (rows are dealt warp by warp)
-  const bool in_qkv = gw0 < 3 * D, in_d = gw0 < D, in_fc = gw0 < FF, in_head = gw0 < a.Vm, in_att = (int)blockIdx.x < a.H;
-  if (tid == 0) s_abort = 0;
+  const int c = blockIdx.x, G = gridDim.x;
+  const bool in_att = c < a.H;
+  if (tid == 0) {
+    s_abort = 0;
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_barrier_init();
+  }
   __syncthreads();
-  uint4 wq[P_SLOTS];
-  float bq[P_MAXR];
-  float hreg = 0.f;
-  const int hist0 = a.state[ST_KV];      // set by the host before the launch; +1 per token
-  if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
+  auto share = [&](int N, int& r0, int& r1) { r0 = (int)((long)N * c / G); r1 = (int)((long)N * (c + 1) / G); };
+  auto job_qkv = [&](int l) { PJob j{a.layers[l].wqkv, a.layers[l].bqkv, 0, 0, CH_D}; share(3 * D, j.r0, j.r1); return j; };
+  auto job_o = [&](int l) { PJob j{a.layers[l].wo, a.layers[l].bo, 0, 0, CH_D}; share(D, j.r0, j.r1); return j; };
+  auto job_fc = [&](int l) { PJob j{a.layers[l].wfc, a.layers[l].bfc, 0, 0, CH_D}; share(FF, j.r0, j.r1); return j; };
+  auto job_p = [&](int l) { PJob j{a.layers[l].wp, a.layers[l].bp, 0, 0, CH_F}; share(D, j.r0, j.r1); return j; };
+  const int head_cap = a.buf_bytes / (CH_D * 512);           // head rows that fit one buffer; the rest is a second pass
+  auto job_head = [&](int part_id) {
+    PJob j{a.whead, a.bhead, 0, 0, CH_D};
+    int r0, r1;
+    share(a.Vm, r0, r1);
+    const int mid = min(r1, r0 + head_cap);
+    j.r0 = part_id == 0 ? r0 : mid;
+    j.r1 = part_id == 0 ? mid : r1;
+    return j;
+  };
+  int cur = 0;
+  uint32_t par[2] = {0u, 0u};
+  bool pend[2] = {false, false};
+  float hreg[2] = {0.f, 0.f};                                // residual operand of the (<= 2 per warp) h rows this warp owns
+  const int hist0 = a.state[ST_KV];                          // set by the host before the launch; +1 per token
+  auto issue = [&](const PJob& j) { p_issue(j, bufs[cur ^ 1], &bars[cur ^ 1], warp, lane); pend[cur ^ 1] = true; };
+  auto ready = [&]() { tc::mbar_wait(&bars[cur], par[cur]); par[cur] ^= 1u; pend[cur] = false; };
+  PJob jq = job_qkv(0);
+  cur = 1; issue(jq); cur = 0;                               // the first projection's weights -> buffer 0
   for (int t = 0; t < a.n_tokens; ++t) {
     const unsigned eh0 = 1u + (unsigned)t * (2u * L + 1u);
     for (int l = 0; l < L; ++l) {
       const PLayer& Ly = a.layers[l];
       const unsigned ev = 1u + (unsigned)(t * L + l);       // epoch of qkv / att / ff
       const unsigned eh = eh0 + 2u * l;                     // epoch of h entering the layer
-      if (in_qkv) {
-        // qkv = W_qkv . LN1(h) + b
-        p_poll_x<CE_D>(xs, a.th, D, eh, &s_abort);
-        if (s_abort) goto done;
-        if (lane == 0 && gw < D) hreg = xs[gw];            // residual operand of the rows this warp owns
-        p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
-        p_gemv<CH_D, R_QKV>(wq, bq, Ly.wqkv, 3 * D, xn, gw, TW, lane, [&](int n, float v) { st_tagged(a.tqkv + n, v, ev); });
+      const PJob jo = job_o(l), jf = job_fc(l), jp = job_p(l);
+      // ---- qkv = W_qkv . LN1(h) + b
+      issue(jo);
+      p_poll_x<CE_D>(xs, a.th, D, eh, &s_abort);
+      if (s_abort) goto done;
+      if (lane == 0) { int i = 0; for (int r = jo.r0 + warp; r < jo.r1 && i < 2; r += P_NW, ++i) hreg[i] = xs[r]; }
+      p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
+      ready();
+      p_gemv<CH_D>(jq, bufs[cur], xn, warp, lane, [&](int n, float v) { st_tagged(a.tqkv + n, v, ev); });
+      cur ^= 1;
+      // ---- attention: one CTA per head
+      if (in_att) p_attention(a, l, c, hist0 + t, ev, sc, part, red, qs, &s_abort);
+      // ---- h += W_o . att + b
+      issue(jf);
+      p_poll_x<CE_D>(xs, a.tatt, D, ev, &s_abort);
+      if (s_abort) goto done;
+      ready();
+      {
+        int i = 0;
+        p_gemv<CH_D>(jo, bufs[cur], xs, warp, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg[i < 2 ? i : 1], eh + 1u); ++i; });
       }
-      if (in_att) p_attention(a, l, blockIdx.x, hist0 + t, ev, sc, part, red, qs, &s_abort);
-      if (in_d) {
-        // h += W_o . att + b
-        p_prefetch<CH_D, 1>(wq, bq, Ly.wo, Ly.bo, D, gw, TW, lane);
-        p_poll_x<CE_D>(xs, a.tatt, D, ev, &s_abort);
-        if (s_abort) goto done;
-        p_gemv<CH_D, 1>(wq, bq, Ly.wo, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 1u); });
+      cur ^= 1;
+      // ---- ff = gelu_new(W_fc . LN2(h) + b)
+      issue(jp);
+      p_poll_x<CE_D>(xs, a.th, D, eh + 1u, &s_abort);
+      if (s_abort) goto done;
+      if (lane == 0) { int i = 0; for (int r = jp.r0 + warp; r < jp.r1 && i < 2; r += P_NW, ++i) hreg[i] = xs[r]; }
+      p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
+      ready();
+      p_gemv<CH_D>(jf, bufs[cur], xn, warp, lane, [&](int n, float v) { st_tagged(a.tff + n, gelu_new_f(v), ev); });
+      cur ^= 1;
+      // ---- h += W_p . ff + b
+      jq = l + 1 < L ? job_qkv(l + 1) : job_head(0);
+      issue(jq);
+      p_poll_x<CE_F>(xs, a.tff, FF, ev, &s_abort);
+      if (s_abort) goto done;
+      ready();
+      {
+        int i = 0;
+        p_gemv<CH_F>(jp, bufs[cur], xs, warp, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg[i < 2 ? i : 1], eh + 2u); ++i; });
       }
-      if (in_fc) {
-        // ff = gelu_new(W_fc . LN2(h) + b)
-        p_prefetch<CH_D, R_FC>(wq, bq, Ly.wfc, Ly.bfc, FF, gw, TW, lane);
-        p_poll_x<CE_D>(xs, a.th, D, eh + 1u, &s_abort);
-        if (s_abort) goto done;
-        if (lane == 0 && gw < D) hreg = xs[gw];
-        p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
-        p_gemv<CH_D, R_FC>(wq, bq, Ly.wfc, FF, xn, gw, TW, lane, [&](int n, float v) { st_tagged(a.tff + n, gelu_new_f(v), ev); });
-      }
-      if (in_d) {
-        // h += W_p . ff + b
-        p_prefetch<CH_F, 1>(wq, bq, Ly.wp, Ly.bp, D, gw, TW, lane);
-        p_poll_x<CE_F>(xs, a.tff, FF, ev, &s_abort);
-        if (s_abort) goto done;
-        p_gemv<CH_F, 1>(wq, bq, Ly.wp, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 2u); });
-      }
-      if (l + 1 < L) {
-        if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gw, TW, lane);
-      } else if (in_head) {
-        p_prefetch<CH_D, R_HEAD>(wq, bq, a.whead, a.bhead, a.Vm, gw, TW, lane);
-      }
+      cur ^= 1;
     }
-    if (in_head) {
-      // head: ln_f (saved) -> final_norm -> mel_head * penalty
+    {
+      // ---- head: ln_f (saved) -> final_norm -> mel_head * penalty, in two passes over this CTA's rows
+      const PJob jh0 = jq, jh1 = job_head(1);
+      issue(jh1);
       p_poll_x<CE_D>(xs, a.th, D, eh0 + 2u * L, &s_abort);
       if (s_abort) goto done;
       __threadfence();                                     // the penalty vector written by the previous pick
       p_ln(xs, xn, D, a.lnfw, a.lnfb, a.eps, warp, lane);
-      if (blockIdx.x == 0) {
+      if (c == 0) {
         float* dst = a.hid_save + (long)(a.n0 + t) * D;
         for (int k = tid; k < D; k += P_NT) dst[k] = xn[k];
       }
       p_ln(xn, xs, D, a.fnw, a.fnb, a.eps, warp, lane);
-      p_gemv<CH_D, R_HEAD>(wq, bq, a.whead, a.Vm, xs, gw, TW, lane,
-                           [&](int n, float v) { st_tagged(a.tlogits + n, v * __ldcg(a.penalty + n), 1u + (unsigned)t); });
+      auto epi = [&](int n, float v) { st_tagged(a.tlogits + n, v * __ldcg(a.penalty + n), 1u + (unsigned)t); };
+      ready();
+      p_gemv<CH_D>(jh0, bufs[cur], xs, warp, lane, epi);
+      cur ^= 1;
+      const bool more = t + 1 < a.n_tokens;
+      if (more) { jq = job_qkv(0); issue(jq); }
+      ready();
+      p_gemv<CH_D>(jh1, bufs[cur], xs, warp, lane, epi);
+      cur ^= 1;
+      if (!more) cur ^= 1;                                 // nothing was issued into the other buffer
     }
-    if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
-    if (blockIdx.x == 0) p_pick(a, 1u + (unsigned)t, eh0 + 2u * L + 1u, red, reinterpret_cast<int*>(red + P_NW), &s_abort);
+    if (c == 0) p_pick(a, 1u + (unsigned)t, eh0 + 2u * L + 1u, red, reinterpret_cast<int*>(red + P_NW), &s_abort);
   }
 done:
+  // no bulk copy may still be in flight towards this CTA's shared memory when it exits
+  if (pend[0]) tc::mbar_wait(&bars[0], par[0]);
+  if (pend[1]) tc::mbar_wait(&bars[1], par[1]);
   if (tid == 0 && s_abort == 2) atomicExch(a.state + ST_ERR, 1);
 }
 
@@ -972,7 +1018,7 @@ void prefill_layers(Engine& e, GptModel& m, int rows, int causal, bool fast) {
 
 // Persistent decode (bf16 engine). Returns false when this model shape has no instantiation (the caller falls back to the
 // per-kernel graph path).
-template <int CH_D, int CH_F, int R_QKV, int R_FC, int R_HEAD>
+template <int CH_D, int CH_F>
 void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   cudaStream_t s = e.stream;
   int dev = 0, sms = 0, coop = 0;
@@ -980,11 +1026,15 @@ void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   B2_CHECK(coop != 0, "persistent decode needs cooperative launch support");
-  const int TW = sms * P_NW;
-  B2_CHECK(ceil_div(3 * m.D, TW) <= R_QKV && ceil_div(m.FF, TW) <= R_FC && ceil_div(m.Vm, TW) <= R_HEAD && m.D <= TW,
-           "persistent decode: too few SMs for the row ownership this instantiation assumes");
-  auto kern = gpt_decode_kernel<CH_D, CH_F, R_QKV, R_FC, R_HEAD>;
-  const size_t smem = (size_t)(m.FF + m.D + m.S_max + 32 * HD + 2 * P_NW + HD) * sizeof(float);
+  auto per_cta = [&](int N) { return ceil_div(N, sms); };              // most rows of an N-row projection one CTA owns
+  const int rb_d = CH_D * 512, rb_f = CH_F * 512;
+  int buf_bytes = std::max(std::max(per_cta(3 * m.D) * rb_d, per_cta(m.FF) * rb_d), per_cta(m.D) * rb_f);
+  buf_bytes = std::max(buf_bytes, ceil_div(per_cta(m.Vm), 2) * rb_d);     // the head takes two passes
+  buf_bytes = (int)round_up(buf_bytes, 1024);
+  B2_CHECK(per_cta(m.D) <= 2 * P_NW, "persistent decode: too few SMs (a warp may own at most two residual rows)");
+  auto kern = gpt_decode_kernel<CH_D, CH_F>;
+  const size_t smem = 2 * (size_t)buf_bytes + (size_t)(m.FF + m.D + m.S_max + 32 * HD + 2 * P_NW + HD) * sizeof(float);
+  B2_CHECK(smem <= 227 * 1024, "persistent decode: shared-memory budget exceeded");
   static bool once = false;
   if (!once) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1003,7 +1053,7 @@ void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   pa.th = m.tagged.p; pa.tqkv = pa.th + m.D; pa.tatt = pa.tqkv + 3 * m.D; pa.tff = pa.tatt + m.D; pa.tlogits = pa.tff + m.FF;
   pa.hcur = m.hcur.p; pa.kc = m.kc.p; pa.vc = m.vc.p;
   pa.state = m.state.p; pa.ids = m.ids.p; pa.penalty = m.penalty.p; pa.hid_save = m.hid_save.p;
-  pa.n_tokens = n_tokens; pa.n0 = n0; pa.lc = m.lc;
+  pa.n_tokens = n_tokens; pa.n0 = n0; pa.lc = m.lc; pa.buf_bytes = buf_bytes;
   {
     const int big = std::max(std::max(3 * m.D, m.FF), m.Vm);
     gpt_tag_init_kernel<<<ceil_div(big, 256), 256, 0, s>>>(pa.th, pa.tqkv, pa.tatt, pa.tff, pa.tlogits, m.hcur.p, m.D, m.FF, m.Vm);
@@ -1019,8 +1069,8 @@ bool decode_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   const char* v = getenv("B200TTS_GPT_PERSIST");
   if (v != nullptr && atoi(v) == 0) return false;
   if (m.head_tc.ldc != m.D) return false;
-  if (m.D == 1280 && m.FF == 5120) { launch_persistent<5, 20, 2, 3, 4>(e, m, n_tokens, n0); return true; }
-  if (m.D == 512 && m.FF == 2048 && m.Vm <= 2048) { launch_persistent<2, 8, 1, 1, 1>(e, m, n_tokens, n0); return true; }
+  if (m.D == 1280 && m.FF == 5120) { launch_persistent<5, 20>(e, m, n_tokens, n0); return true; }
+  if (m.D == 512 && m.FF == 2048 && m.Vm <= 2048) { launch_persistent<2, 8>(e, m, n_tokens, n0); return true; }
   return false;
 }
 

@@ -161,6 +161,115 @@ class _IndexTTSVocoderGraph(_Graph):
         return [self.engine.indextts_vocoder_run(hidden, conds, cond_layer, precision=self.precision, hop=self.cfg.hop)]
 
 
+_igpt_ready = {}
+
+
+def load_indextts_gpt(engine, state=None, cfg=None):
+    """Loads + builds the IndexTTS GPT-2 acoustic model once per engine (graphs B, C, E share it)."""
+    from .config import INDEXTTS_GPT
+    cfg = cfg or _checkpoints.get("indextts_gpt_config") or INDEXTTS_GPT
+    key = id(engine)
+    if state is None and key in _igpt_ready:
+        return _igpt_ready[key]
+    state = state if state is not None else _checkpoints.get("indextts_gpt")
+    if state is None:
+        raise RuntimeError("no IndexTTS GPT checkpoint registered: call session.register_checkpoint('indextts_gpt', state)")
+    engine.load_state("igpt", weights.igpt_engine_tensors(state, cfg))
+    engine.indextts_gpt_build()
+    _igpt_ready[key] = cfg
+    return cfg
+
+
+class _IndexTTSTextGraph(_Graph):
+    """IndexTTS_B: IndexTTS/Export_IndexTTS.py:203-214,357-373; called at IndexTTS/Inference_IndexTTS_ONNX.py:723."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine = engine
+        self.cfg = load_indextts_gpt(engine, state)
+        self.inputs = (NodeArg("text_ids", "tensor(int32)", [1, "text_ids_len"]),)
+        self.outputs = (NodeArg("text_hidden_state", "tensor(float)", [1, "text_ids_len", self.cfg.dim]),)
+
+    def run(self, feed):
+        return [self.engine.indextts_gpt_text_embed(_as_numpy(feed["text_ids"]).astype(np.int32))]
+
+
+class _IndexTTSMelEmbedGraph(_Graph):
+    """IndexTTS_C: Export_IndexTTS.py:217-225,377-390; called at Inference_IndexTTS_ONNX.py:729,775."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine = engine
+        self.cfg = load_indextts_gpt(engine, state)
+        self.inputs = (NodeArg("gpt_ids", "tensor(int32)", [1, 1]), NodeArg("kv_seq_len", "tensor(int64)", [1]))
+        self.outputs = (NodeArg("gpt_hidden_state", "tensor(float)", [1, 1, self.cfg.dim]), NodeArg("next_kv_seq_len", "tensor(int64)", [1]))
+
+    def run(self, feed):
+        mel_id = int(_as_numpy(feed["gpt_ids"]).reshape(-1)[0])
+        gen_len = int(_as_numpy(feed["kv_seq_len"]).reshape(-1)[0])
+        h, nxt = self.engine.indextts_gpt_mel_embed(mel_id, gen_len)
+        return [h, np.array([nxt], dtype=np.int64)]
+
+
+class _IndexTTSConcatGraph(_Graph):
+    """IndexTTS_D: Export_IndexTTS.py:228-235,394-414 -- a pure row concatenation (no arithmetic): host memory only."""
+
+    def __init__(self, engine, precision, state=None):
+        self.inputs = tuple(NodeArg(n, "tensor(float)", [1, f"{n}_len", "hidden"]) for n in ("embed_x", "embed_y", "embed_z"))
+        self.outputs = (NodeArg("concat_hidden_state", "tensor(float)", [1, "concat_len", "hidden"]), NodeArg("concat_len", "tensor(int64)", [1]))
+
+    def run(self, feed):
+        h = np.concatenate([_as_numpy(feed[n]).astype(np.float32) for n in ("embed_x", "embed_y", "embed_z")], axis=1)
+        return [h, np.array([h.shape[1]], dtype=np.int64)]
+
+
+class ResidentKV(OrtValue):
+    """out_key_<i> / out_value_<i> of IndexTTS_E: the cache stays in HBM; the reference loop only feeds these values back
+    (Inference_IndexTTS_ONNX.py:766-767), so they are handles. ``numpy()`` materialises the reference layout on demand."""
+
+    def __init__(self, engine, layer, which, rows, heads):
+        self._engine, self._layer, self._which, self._rows, self._heads = engine, layer, which, rows, heads
+
+    @property
+    def _array(self):                     # OrtValue.numpy(v) -- the reference calls it unbound -- reads this attribute
+        key, val = self._engine.indextts_gpt_kv_read(self._layer)
+        return key if self._which == "key" else val
+
+    def shape(self):
+        return [self._heads, 64, self._rows] if self._which == "key" else [self._heads, self._rows, 64]
+
+
+class _IndexTTSDecodeGraph(_Graph):
+    """IndexTTS_E: Export_IndexTTS.py:238-289,416-482; called in the loop of Inference_IndexTTS_ONNX.py:753-781. The in_key / in_value
+    feeds are not read (the cache is resident); history_len says whether the call continues it or starts a sentence."""
+
+    def __init__(self, engine, precision, state=None):
+        self.engine, self.precision = engine, precision
+        self.cfg = cfg = load_indextts_gpt(engine, state)
+        L, H = cfg.layers, cfg.heads
+        self.inputs = tuple(NodeArg(f"in_key_{i}", "tensor(float)", [H, 64, "history_len"]) for i in range(L)) + tuple(
+            NodeArg(f"in_value_{i}", "tensor(float)", [H, "history_len", 64]) for i in range(L)) + (
+            NodeArg("history_len", "tensor(int64)", [1]), NodeArg("repeat_penality", "tensor(float)", [1, cfg.mel_codes]),
+            NodeArg("ids_len", "tensor(int64)", [1]), NodeArg("hidden_state", "tensor(float)", [1, "ids_len", cfg.dim]),
+            NodeArg("attention_mask", "tensor(int8)", [1]))
+        self.outputs = tuple(NodeArg(f"out_key_{i}", "tensor(float)", [H, 64, "kv_seq_len"]) for i in range(L)) + tuple(
+            NodeArg(f"out_value_{i}", "tensor(float)", [H, "kv_seq_len", 64]) for i in range(L)) + (
+            NodeArg("kv_seq_len", "tensor(int64)", [1]), NodeArg("last_hidden_state", "tensor(float)", [1, cfg.dim]),
+            NodeArg("max_logit_id", "tensor(int32)", [1, 1]))
+
+    def run(self, feed):
+        cfg = self.cfg
+        hidden = _as_numpy(feed["hidden_state"]).astype(np.float32)
+        ids_len = int(_as_numpy(feed["ids_len"]).reshape(-1)[0])
+        if hidden.ndim != 3 or hidden.shape[1] != ids_len or hidden.shape[2] != cfg.dim:
+            raise ValueError(f"hidden_state must be (1, ids_len={ids_len}, {cfg.dim}), got {hidden.shape}")
+        hist = int(_as_numpy(feed["history_len"]).reshape(-1)[0])
+        flag = int(_as_numpy(feed["attention_mask"]).reshape(-1)[0])
+        pen = _as_numpy(feed["repeat_penality"]).astype(np.float32)
+        last, mid, kv = self.engine.indextts_gpt_step(hidden, hist, flag, pen, precision=self.precision)
+        keys = [ResidentKV(self.engine, i, "key", kv, cfg.heads) for i in range(cfg.layers)]
+        vals = [ResidentKV(self.engine, i, "value", kv, cfg.heads) for i in range(cfg.layers)]
+        return keys + vals + [np.array([kv], dtype=np.int64), last, mid]
+
+
 _f5_ready = {}
 
 
@@ -268,12 +377,14 @@ class _F5DecodeGraph(_Graph):
 
 
 _GRAPHS = {"bigvgan": _BigVGANGraph, "f5_preprocess": _F5PreprocessGraph, "f5_transformer": _F5TransformerGraph,
-           "f5_decode": _F5DecodeGraph, "indextts_f": _IndexTTSVocoderGraph}
+           "f5_decode": _F5DecodeGraph, "indextts_f": _IndexTTSVocoderGraph, "indextts_b": _IndexTTSTextGraph,
+           "indextts_c": _IndexTTSMelEmbedGraph, "indextts_d": _IndexTTSConcatGraph, "indextts_e": _IndexTTSDecodeGraph}
 
 
 def _kind_of(path: str) -> str:
     base = os.path.basename(str(path)).lower()
-    for key in ("f5_preprocess", "f5_transformer", "f5_decode", "indextts_f", "bigvgan"):
+    for key in ("f5_preprocess", "f5_transformer", "f5_decode", "indextts_f", "indextts_b", "indextts_c", "indextts_d", "indextts_e",
+                "bigvgan"):
         if key in base:
             return key
     raise ValueError(f"cannot tell which hot-path graph '{path}' is (expected BigVGAN / F5_Preprocess / "
@@ -312,7 +423,7 @@ class InferenceSession:
         return self._select(output_names, self._graph.run(input_feed))
 
     def run_with_ort_values(self, output_names, input_feed, run_options=None):
-        return [OrtValue(o) for o in self.run(output_names, input_feed)]
+        return [o if isinstance(o, OrtValue) else OrtValue(o) for o in self.run(output_names, input_feed)]
 
     def io_binding(self):
         return IOBinding(self)
