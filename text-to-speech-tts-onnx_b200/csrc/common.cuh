@@ -51,6 +51,15 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();     // B200TTS_PDL=0 turns the launch attribute off (rowgemm_f32.cu)
+// The attribute is only set inside a PdlScope(true): it pays where kernels are short (one-utterance DiT step: 77.2 -> 75.2 ms,
+// the GPT decode chain) and costs ~0.8 % where they are long (BigVGAN 14.79 -> 15.04 ms, 8-utterance pipeline 444.7 -> 447.8 ms,
+// same-box A/B), because an early-resident dependent CTA holds shared memory / TMEM that the tail of its predecessor could use.
+extern int g_pdl_scope;
+struct PdlScope {
+  int prev;
+  explicit PdlScope(bool on) : prev(g_pdl_scope) { g_pdl_scope = on ? 1 : 0; }
+  ~PdlScope() { g_pdl_scope = prev; }
+};
 
 // Launch `kernel` so that it may start while its predecessor in the stream drains (its pdl_wait() orders the data).
 template <typename... KArgs, typename... Args>
@@ -60,7 +69,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && g_pdl_scope) ? 1 : 0;
   B2_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 #endif

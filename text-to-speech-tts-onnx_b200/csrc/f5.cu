@@ -576,6 +576,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   const int N = m.N, D = m.D, S = 2 * m.U, R = S * N;
   B2_CHECK(fast || m.U == 1, "the fp32 parity engine runs one utterance at a time");
   reserve_step(m, fast);
+  PdlScope pdl(m.U == 1);                  // short kernels only (common.cuh)
   if (!fast) {   // padding rows / columns (t in [N, Npad)) of the fp32 attention operands must read as zero
     B2_CUDA(cudaMemsetAsync(m.kT32.p, 0, (size_t)2 * m.H * m.hd * m.Npad * sizeof(float), s));
     B2_CUDA(cudaMemsetAsync(m.v32.p, 0, (size_t)2 * m.H * m.Npad * m.hd * sizeof(float), s));

@@ -6,6 +6,7 @@ namespace b200tts {
 
 unsigned long long g_launch_count = 0;
 unsigned long long g_alloc_epoch = 0;
+int g_pdl_scope = 0;
 bool pdl_enabled() {
   static const bool on = [] { const char* v = getenv("B200TTS_PDL"); return v == nullptr || atoi(v) != 0; }();
   return on;
