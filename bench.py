@@ -535,8 +535,17 @@ def bench_indextts_gpt(args, H, eng, rank, prec, steps, warmup, sampler=None):
                      f"per step: prefill of {rows} rows ({cfg.cond_rows} latents + {args.gpt_text} text ids + 3) then {n_new - 1} single-row "
                      f"greedy decode calls, repeat-penalty window on the device [acoustic half of BASELINE.json configs[4]]"),
     }
-    if gemv_ms > 0:
-        # decode GEMVs of the profiled sentence: (n_tok - 1) decode calls stream every weight once; the prefill's head call too
+    pers = prof.get("igpt.decode_persistent")
+    if pers and pers["ms"] > 0:
+        # the persistent decode kernel: every decode call streams every projection weight once and reads the cache rows of its head
+        ach = (n_tok - 1) * (per_tok_w + per_tok_kv) / (pers["ms"] / 1e3) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": "gpt_decode_kernel (persistent: 24 layers + head + pick per token, up to 32 tokens per launch)",
+                           "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("igpt.decode"),
+                           "peak_source": pk["source"], "avg_launch_ms": pers["ms"] / max(pers["launches"], 1),
+                           "share_of_step": pers["ms"] / total_ms, "bytes_per_token": int(per_tok_w), "kv_bytes_per_token_avg": int(per_tok_kv),
+                           "ms_per_token_in_kernel": pers["ms"] / max(n_tok - 1, 1)}
+    elif gemv_ms > 0:
+        # per-kernel decode path (B200TTS_GPT_PERSIST=0): (n_tok - 1) decode calls stream every weight once; the prefill's head call too
         ach = ((n_tok - 1) * per_tok_w + cfg.mel_codes * D * wbytes) / (gemv_ms / 1e3) / 1e9
         res["roofline"] = {"bound": "hbm", "kernel": "gemv_kernel (decode projections: LayerNorm + matrix-vector + epilogue)", "achieved": ach,
                            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("igpt.gemv"),
