@@ -92,18 +92,6 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// block-wide sum over 256 threads (red: 8 floats of shared memory)
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum_f(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t += red[i];
-  return t;
-}
-
 __device__ __forceinline__ float gelu_new_f(float v) {      // Hugging Face NewGELUActivation (GPT2MLP.act)
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * v * (1.0f + tanhf(k0 * (v + k1 * v * v * v)));
@@ -461,6 +449,8 @@ struct PArgs {
   int *state, *ids;
   float *penalty, *hid_save;
   int n_tokens, n0;                                    // tokens to attempt in this launch; tokens produced before it
+  int poll_first;                                      // experiment (B200TTS_GPT_POLLFIRST=1): fetch a phase's weight rows AFTER its input
+                                                       // was polled -- measured slower, 1158 vs 1375 tokens/s on one box; default 0
   unsigned long long* trace;                           // optional (B200TTS_GPT_TRACE): globaltimer stamps of token 1, [cta][layer][16]
   LoopConst lc;
 };
@@ -751,7 +741,8 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
   float bq[P_MAXR];
   float hreg = 0.f;
   const int hist0 = a.state[ST_KV];      // set by the host before the launch; +1 per token
-  if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
+  const bool pf = a.poll_first != 0;
+  if (in_qkv && !pf) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
 #define STAMP(i) do { if (a.trace && t == 1 && tid == 0) a.trace[((size_t)blockIdx.x * L + l) * 16 + (i)] = gtimer(); } while (0)
   for (int t = 0; t < a.n_tokens; ++t) {
     const unsigned eh0 = 1u + (unsigned)t * (2u * L + 1u);
@@ -764,6 +755,7 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
         STAMP(0);
         p_poll_x<CE_D>(xs, a.th, D, eh, &s_abort);
         if (s_abort) goto done;
+        if (pf) p_prefetch<CH_D, R_QKV>(wq, bq, Ly.wqkv, Ly.bqkv, 3 * D, gw, TW, lane);
         STAMP(1);
         if (lane == 0 && gw < D) hreg = xs[gw];            // residual operand of the rows this warp owns
         p_ln(xs, xn, D, Ly.ln1w, Ly.ln1b, a.eps, warp, lane);
@@ -774,19 +766,21 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
       if (in_att) { p_attention(a, l, blockIdx.x, hist0 + t, ev, sc, part, red, qs, &s_abort); STAMP(4); }
       if (in_d) {
         // h += W_o . att + b
-        p_prefetch<CH_D, 1>(wq, bq, Ly.wo, Ly.bo, D, gw, TW, lane);
+        if (!pf) p_prefetch<CH_D, 1>(wq, bq, Ly.wo, Ly.bo, D, gw, TW, lane);
         STAMP(5);
         p_poll_x<CE_D>(xs, a.tatt, D, ev, &s_abort);
         if (s_abort) goto done;
+        if (pf) p_prefetch<CH_D, 1>(wq, bq, Ly.wo, Ly.bo, D, gw, TW, lane);
         STAMP(6);
         p_gemv<CH_D, 1>(wq, bq, Ly.wo, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 1u); });
       }
       if (in_fc) {
         // ff = gelu_new(W_fc . LN2(h) + b)
-        p_prefetch<CH_D, R_FC>(wq, bq, Ly.wfc, Ly.bfc, FF, gw, TW, lane);
+        if (!pf) p_prefetch<CH_D, R_FC>(wq, bq, Ly.wfc, Ly.bfc, FF, gw, TW, lane);
         STAMP(7);
         p_poll_x<CE_D>(xs, a.th, D, eh + 1u, &s_abort);
         if (s_abort) goto done;
+        if (pf) p_prefetch<CH_D, R_FC>(wq, bq, Ly.wfc, Ly.bfc, FF, gw, TW, lane);
         STAMP(8);
         if (lane == 0 && gw < D) hreg = xs[gw];
         p_ln(xs, xn, D, Ly.ln2w, Ly.ln2b, a.eps, warp, lane);
@@ -795,24 +789,26 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
       }
       if (in_d) {
         // h += W_p . ff + b
-        p_prefetch<CH_F, 1>(wq, bq, Ly.wp, Ly.bp, D, gw, TW, lane);
+        if (!pf) p_prefetch<CH_F, 1>(wq, bq, Ly.wp, Ly.bp, D, gw, TW, lane);
         STAMP(10);
         p_poll_x<CE_F>(xs, a.tff, FF, ev, &s_abort);
         if (s_abort) goto done;
+        if (pf) p_prefetch<CH_F, 1>(wq, bq, Ly.wp, Ly.bp, D, gw, TW, lane);
         STAMP(11);
         p_gemv<CH_F, 1>(wq, bq, Ly.wp, D, xs, gw, TW, lane, [&](int n, float v) { st_tagged(a.th + n, v + hreg, eh + 2u); });
       }
       STAMP(12);
       if (l + 1 < L) {
-        if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gw, TW, lane);
+        if (in_qkv && !pf) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gw, TW, lane);
       } else if (in_head) {
-        p_prefetch<CH_D, R_HEAD>(wq, bq, a.whead, a.bhead, a.Vm, gw, TW, lane);
+        if (!pf) p_prefetch<CH_D, R_HEAD>(wq, bq, a.whead, a.bhead, a.Vm, gw, TW, lane);
       }
     }
     if (in_head) {
       // head: ln_f (saved) -> final_norm -> mel_head * penalty
       p_poll_x<CE_D>(xs, a.th, D, eh0 + 2u * L, &s_abort);
       if (s_abort) goto done;
+      if (pf) p_prefetch<CH_D, R_HEAD>(wq, bq, a.whead, a.bhead, a.Vm, gw, TW, lane);
       __threadfence();                                     // the penalty vector written by the previous pick
       p_ln(xs, xn, D, a.lnfw, a.lnfb, a.eps, warp, lane);
       if (blockIdx.x == 0) {
@@ -823,7 +819,7 @@ __global__ void __launch_bounds__(P_NT, 1) gpt_decode_kernel(const PArgs a) {
       p_gemv<CH_D, R_HEAD>(wq, bq, a.whead, a.Vm, xs, gw, TW, lane,
                            [&](int n, float v) { st_tagged(a.tlogits + n, v * __ldcg(a.penalty + n), 1u + (unsigned)t); });
     }
-    if (in_qkv) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
+    if (in_qkv && !pf) p_prefetch<CH_D, R_QKV>(wq, bq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gw, TW, lane);
     if (blockIdx.x == 0) p_pick(a, 1u + (unsigned)t, eh0 + 2u * L + 1u, red, reinterpret_cast<int*>(red + P_NW), &s_abort);
   }
 done:
@@ -1052,6 +1048,7 @@ void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
   pa.hcur = m.hcur.p; pa.kc = m.kc.p; pa.vc = m.vc.p;
   pa.state = m.state.p; pa.ids = m.ids.p; pa.penalty = m.penalty.p; pa.hid_save = m.hid_save.p;
   pa.n_tokens = n_tokens; pa.n0 = n0; pa.lc = m.lc;
+  { const char* v = getenv("B200TTS_GPT_POLLFIRST"); pa.poll_first = v != nullptr && atoi(v) != 0; }
   const char* trace_path = getenv("B200TTS_GPT_TRACE");
   const size_t trace_n = (size_t)sms * m.L * 16;
   if (trace_path && n0 == 1) {                              // the first decode launch of a sentence
