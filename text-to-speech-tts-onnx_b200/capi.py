@@ -152,6 +152,11 @@ class Engine:
         for k, v in state.items():
             self.load_tensor(f"{prefix}.{k}", v)
 
+    def load_blob(self, path: str):
+        """Upload every part of an engine blob written by checkpoint.save_blob / tools/convert_checkpoint.py."""
+        from . import checkpoint
+        return checkpoint.load_blob_into(self, path)
+
     def bigvgan_build(self):
         self._check(self.lib.b200tts_bigvgan_build(self.handle), "bigvgan_build")
 
