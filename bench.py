@@ -543,7 +543,8 @@ def bench_indextts_gpt(args, H, eng, rank, prec, steps, warmup, sampler=None):
                            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic("igpt.decode"),
                            "peak_source": pk["source"], "avg_launch_ms": pers["ms"] / max(pers["launches"], 1),
                            "share_of_step": pers["ms"] / total_ms, "bytes_per_token": int(per_tok_w), "kv_bytes_per_token_avg": int(per_tok_kv),
-                           "ms_per_token_in_kernel": pers["ms"] / max(n_tok - 1, 1)}
+                           "ms_per_token_in_kernel": pers["ms"] / max(n_tok - 1, 1),
+                           "traffic_note": "ncu capture of a 7-token launch (profiles/r01/traffic.json): 1.0 GB read per token"}
     elif gemv_ms > 0:
         # per-kernel decode path (B200TTS_GPT_PERSIST=0): (n_tok - 1) decode calls stream every weight once; the prefill's head call too
         ach = ((n_tok - 1) * per_tok_w + cfg.mel_codes * D * wbytes) / (gemv_ms / 1e3) / 1e9
