@@ -185,7 +185,7 @@ def run_reference(args, rank, world):
                 "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                  "sample": f"{steps} x 1 mel (1,100,{T}), torch-CPU fp32 eager restatement of the reference "
                                            "modules (stand-in for ORT CPUExecutionProvider, not installable offline)"}}
-    elif args.workload == "indextts_gpt":
+    elif args.workload in ("indextts_gpt", "indextts"):     # the acoustic half dominates the CPU time of a sentence
         import torch as _t
         from b200tts import synth
         from oracle import indextts_gpt_ref
@@ -556,13 +556,63 @@ def bench_indextts_gpt(args, H, eng, rank, prec, steps, warmup, sampler=None):
     return res
 
 
+def bench_indextts(args, H, eng, rank, prec, steps, warmup, sampler=None):
+    """BASELINE.json configs[4] end to end for one sentence per step, through the host-buffer calls a reference script would make
+    (Inference_IndexTTS_ONNX.py:719-791 minus the conditioning graph A, whose outputs are inputs here): GPT-2 greedy decode of
+    `--new-tokens` mel tokens (graphs B, C, D, E) -> IndexTTS_F vocoder on the hidden states -> int16 PCM. Every call takes host
+    pointers and synchronises, so `value` and `e2e` are the same measurement (timed on the host clock)."""
+    torch = H.torch
+    from b200tts import config, synth
+    gcfg, vcfg = config.INDEXTTS_GPT, config.INDEXTTS_VOCODER
+    conds, text_ids = synth.igpt_inputs(900 + rank, args.gpt_text, gcfg)
+    vconds, cond_layer, _ = synth.ivgan_inputs(300 + rank, 3)
+    n_new = args.new_tokens
+    out = {}
+
+    def step():
+        ids, hidden = eng.indextts_gpt_generate(conds, text_ids, max_new=n_new, precision=prec)
+        out["n"] = len(ids)
+        out["pcm"] = eng.indextts_vocoder_run(hidden, vconds, cond_layer, precision=prec, hop=vcfg.hop)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    H.barrier()
+    l0 = eng.launch_count()
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - l0
+    ms = 1e3 * dt
+    if H.world > 1:
+        t = torch.tensor([ms], device="cuda")
+        H.dist.all_reduce(t, op=H.dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_tok = out["n"]
+    n_samp = int(out["pcm"].shape[-1])
+    frames = (n_tok - 2) * 4 * H.world * steps              # one latent row = 1024 samples = 4 frames of 256 samples
+    audio_s = n_samp / vcfg.sample_rate
+    e2e = {"value": frames / (ms / 1e3), "unit": "mel-frames/s", "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / audio_s,
+           "h2d_bytes_per_step": int(conds.nbytes + text_ids.nbytes + n_tok * gcfg.dim * 4 + sum(c.nbytes for c in vconds) + cond_layer.nbytes),
+           "d2h_bytes_per_step": int(n_tok * (gcfg.dim * 4 + 4) + n_samp * 2)}
+    return {"value": e2e["value"], "ms_per_step": ms / steps, "rtf": e2e["rtf"], "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "profile_ms": {}, "tokens_per_s": n_tok * H.world * steps / (ms / 1e3),
+            "workload": f"IndexTTS sentence end to end without the conditioning graph: GPT-2 decode of {n_tok} mel tokens (prompt "
+                        f"{gcfg.cond_rows + args.gpt_text + 3} rows) + IndexTTS_F vocoder -> {n_samp} samples ({audio_s:.2f} s) "
+                        "[BASELINE.json configs[4]]; host-buffer calls, host clock"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder", "indextts_gpt"])
+    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder", "indextts_gpt", "indextts"])
     ap.add_argument("--new-tokens", type=int, default=256, help="indextts_gpt workload: E calls per sentence (prefill + decode)")
     ap.add_argument("--gpt-text", type=int, default=60, help="indextts_gpt workload: text ids per sentence")
     ap.add_argument("--latent-rows", type=int, default=142, help="indextts_vocoder workload: rows of save_hidden_state")
@@ -612,13 +662,13 @@ def main():
     H = Harness(torch, dist, stream, world)
     need_f5 = args.workload in ("f5", "pipeline") or (args.workload == "bigvgan" and not args.no_extras)
     need_vgan = args.workload in ("bigvgan", "pipeline")
-    if args.workload == "indextts_vocoder":
+    if args.workload in ("indextts_vocoder", "indextts"):
         cfgv = config.INDEXTTS_VOCODER
         state = weights.ivgan_engine_tensors(synth.ivgan_state(777), cfgv) if rank == 0 else None
         distributed.load_state_broadcast(eng, "ivgan", state, src=0)
         eng.indextts_vocoder_build()
 
-    if args.workload == "indextts_gpt":
+    if args.workload in ("indextts_gpt", "indextts"):
         state = weights.igpt_engine_tensors(synth.igpt_state(555), config.INDEXTTS_GPT) if rank == 0 else None
         distributed.load_state_broadcast(eng, "igpt", state, src=0)
         eng.indextts_gpt_build()
@@ -657,6 +707,9 @@ def main():
     elif args.workload == "indextts_vocoder":
         res = bench_indextts_vocoder(args, H, eng, rank, prec, args.steps, args.warmup)
         dtype = "bf16" if prec == capi.BF16 else "f32"
+    elif args.workload == "indextts":
+        res = bench_indextts(args, H, eng, rank, prec, args.steps, args.warmup, sampler)
+        dtype = "bf16" if prec == capi.BF16 else "f32"
     elif args.workload == "indextts_gpt":
         res = bench_indextts_gpt(args, H, eng, rank, prec, args.steps, args.warmup, sampler)
         dtype = "bf16 weights, fp32 activations / cache / accumulation" if prec == capi.BF16 else "f32"
@@ -693,6 +746,8 @@ def main():
                 line["cpu_baseline"] = {"value": (args.latent_rows - 2) * 4 / dtc, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                         "sample": f"1 x latent ({args.latent_rows},1280), oracle (torch-CPU fp32 restatement of IndexTTS_F)",
                                         "s_per_utterance": dtc}
+            elif args.workload == "indextts":
+                pass                                           # see --workload indextts_gpt / indextts_vocoder for the two CPU legs
             elif args.workload == "indextts_gpt":
                 import torch as _t
                 from oracle import indextts_gpt_ref
