@@ -176,6 +176,29 @@ def test_limit_and_stop_token(small, g):
     eng.indextts_gpt_build()
 
 
+@pytest.mark.parametrize("precision", [capi.F32, capi.BF16])
+def test_stop_token_in_the_middle_of_a_decode_chunk(small, precision):
+    """The stop id wins at the 4th call (the 3rd decode call of the first persistent launch / graph chunk): the loop must end
+    there on every CTA, keep the stop call's hidden row and leave the penalty vector as the reference loop would. The stop logit is
+    steered with the penalty vector itself (x -3 on the stop id: outside the reference's 0..1 range, but the graph only multiplies)."""
+    eng, sd, conds, text_ids = small
+    pen = np.ones((1, SMALL.mel_codes), np.float32)
+    pen[0, SMALL.stop_mel] = -3.0
+    want_ids, want_hid, want_pen = R.generate(conds, text_ids, sd, SMALL, max_new=20, penalty=pen)
+    assert want_ids.tolist()[-1] == SMALL.stop_mel and len(want_ids) == 4          # oracle: top-2 margins 0.15 / 0.5 / 3.1 / 2.0
+    ids, hidden, pen_out = eng.indextts_gpt_generate(conds, text_ids, max_new=20, precision=precision, penalty=pen)
+    np.testing.assert_array_equal(ids, want_ids)
+    assert hidden.shape == want_hid.shape
+    if precision == capi.F32:
+        assert np.abs(hidden - want_hid).max() <= 2e-3
+    else:
+        assert all(_cos(hidden[i], want_hid[i]) >= 0.995 for i in range(len(ids)))
+    np.testing.assert_array_equal(pen_out, want_pen)
+    # and the engine is reusable afterwards
+    ids2, _ = eng.indextts_gpt_generate(conds, text_ids, max_new=6, precision=precision)
+    assert len(ids2) == 6
+
+
 def test_generate_is_deterministic_and_restartable(small, g):
     eng, sd, conds, text_ids = small
     a = eng.indextts_gpt_generate(conds, text_ids, max_new=24, precision=capi.BF16)
