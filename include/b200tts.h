@@ -25,7 +25,10 @@ extern "C" {
 
 typedef struct b200tts_engine b200tts_engine;
 
-enum { B200TTS_F32 = 0, B200TTS_BF16 = 1 };   /* arithmetic of the dense contractions */
+/* arithmetic of the dense contractions: fp32 on CUDA cores (the parity engine), or bf16 / IEEE fp16 operands on the tcgen05
+ * tensor cores with fp32 accumulation. BASELINE.json's configurations name fp16 (the reference's own recipe:
+ * F5_TTS/Export_F5.py:139-141,321-333); the IndexTTS GPT-2 entry points take F32 or BF16 only. */
+enum { B200TTS_F32 = 0, B200TTS_BF16 = 1, B200TTS_F16 = 2 };
 
 /* ---- lifetime / errors ------------------------------------------------------------------------------ */
 /* Replaces InferenceSession construction (F5-TTS-ONNX-Inference.py:173-214): one engine per GPU. */
@@ -161,6 +164,9 @@ int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int 
  * path: q, k, v (2, H, N, 64) fp32 host (already roped / pre-scaled) -> out (2, N, H*64) fp32 host. */
 int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
                       float* out_host);
+/* the same with the operand type chosen: precision = B200TTS_BF16 or B200TTS_F16 */
+int b200tts_attention_prec(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
+                           int precision, float* out_host);
 
 /* Micro-benchmark of the tensor-core shifted-row GEMM alone (tools/bench_gemm.py; not on any product path): B batches of
  * M rows x Cin channels (bf16, synthetic) against taps x N x Cin weights, epilogue = bias (+ fp32 residual/gate when

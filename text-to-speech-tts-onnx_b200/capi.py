@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200TTS_LIB") or os.path.join(HERE, "libb200tts.so")   # override: A/B runs of two builds
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2          # include/b200tts.h: B200TTS_F32 / _BF16 / _F16
 
 
 class Libb200ttsMissing(RuntimeError):
@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
     "b200tts_attention": (_int, [_vp, _vp, _vp, _vp, _int, _int, _vp]),
+    "b200tts_attention_prec": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "b200tts_bench_rowgemm": (_int, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _c_f]),
     "b200tts_profile_begin": (_int, [_vp]),
     "b200tts_profile_end": (ctypes.c_char_p, [_vp]),
@@ -362,13 +363,14 @@ class Engine:
                                                    int(precise), int(post), _ptr(y)), "aa_activation")
         return y
 
-    def attention(self, q, k, v):
-        """q, k, v (2, H, N, 64) fp32 -> softmax(q k^T) v as (2, N, H*64), tcgen05 path (bf16 operands)."""
+    def attention(self, q, k, v, precision=BF16):
+        """q, k, v (2, H, N, 64) fp32 -> softmax(q k^T) v as (2, N, H*64), tcgen05 path (bf16 or fp16 operands)."""
         q, k, v = _f32(q), _f32(k), _f32(v)
         two, H, N, hd = q.shape
         assert two == 2 and hd == 64 and k.shape == q.shape and v.shape == q.shape
         out = np.empty((2, N, H * 64), dtype=np.float32)
-        self._check(self.lib.b200tts_attention(self.handle, _ptr(q), _ptr(k), _ptr(v), H, N, _ptr(out)), "attention")
+        self._check(self.lib.b200tts_attention_prec(self.handle, _ptr(q), _ptr(k), _ptr(v), H, N, int(precision), _ptr(out)),
+                    "attention")
         return out
 
     def conv1d(self, x, w, bias=None, dilation=1, groups=1, precision=F32):

@@ -16,6 +16,8 @@
 // version (ncu, profiles/r01).
 #include "aa_act.cuh"
 
+#include <cuda_fp16.h>
+
 namespace b200tts {
 
 __constant__ float c_aa_f[12];
@@ -36,11 +38,20 @@ constexpr int NT = 128;
 template <typename T> struct Raw;
 template <> struct Raw<float> { float2 v; };
 template <> struct Raw<__nv_bfloat16> { uint32_t v; };
+template <> struct Raw<__half> { uint32_t v; };
 __device__ __forceinline__ Raw<float> ldraw(const float* p, bool ok) {
   Raw<float> r; r.v = ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f); return r;
 }
 __device__ __forceinline__ Raw<__nv_bfloat16> ldraw(const __nv_bfloat16* p, bool ok) {
   Raw<__nv_bfloat16> r; r.v = ok ? __ldg(reinterpret_cast<const unsigned int*>(p)) : 0u; return r;
+}
+__device__ __forceinline__ Raw<__half> ldraw(const __half* p, bool ok) {
+  Raw<__half> r; r.v = ok ? __ldg(reinterpret_cast<const unsigned int*>(p)) : 0u; return r;
+}
+__device__ __forceinline__ float2 unpack(const Raw<__half>& r) { return __half22float2(*reinterpret_cast<const __half2*>(&r.v)); }
+__device__ __forceinline__ void st2(__half* p, float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack(const Raw<float>& r) { return r.v; }
 __device__ __forceinline__ float2 unpack(const Raw<__nv_bfloat16>& r) {
@@ -231,9 +242,13 @@ void aa_snake(const void* x, int in_bf16, void* y, int out_bf16, const float* al
   if (precise) {
     B2_CHECK(!in_bf16 && !out_bf16, "aa_snake precise variant is fp32 only");
     launch<float, float, true, false>(x, y, alpha, inv_beta, B, C, L, stream);
-  } else if (!in_bf16 && out_bf16) {
+  } else if (!in_bf16 && out_bf16 == 2) {                        // type codes: 0 = fp32, 1 = bf16, 2 = fp16
+    launch<float, __half, false, false>(x, y, alpha, inv_beta, B, C, L, stream);
+  } else if (in_bf16 == 2 && out_bf16 == 2) {
+    launch<__half, __half, false, false>(x, y, alpha, inv_beta, B, C, L, stream);
+  } else if (!in_bf16 && out_bf16 == 1) {
     launch<float, __nv_bfloat16, false, false>(x, y, alpha, inv_beta, B, C, L, stream);
-  } else if (in_bf16 && out_bf16) {
+  } else if (in_bf16 == 1 && out_bf16 == 1) {
     launch<__nv_bfloat16, __nv_bfloat16, false, false>(x, y, alpha, inv_beta, B, C, L, stream);
   } else if (!in_bf16 && !out_bf16) {
     launch<float, float, false, false>(x, y, alpha, inv_beta, B, C, L, stream);

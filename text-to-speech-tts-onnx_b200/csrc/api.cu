@@ -450,11 +450,11 @@ static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const i
   run_graphed(E, {30, (long long)(uintptr_t)audio_dev, (long long)L, (long long)(uintptr_t)ids_dev, n_text, (long long)N,
                   (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
               [&] {
-                f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N, 0, 1, precision == PREC_BF16);
+                f5_preprocess(E, audio_dev, L, ids_dev, n_text, (int)N, 0, 1, precision);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 f5_prepare_cond(E);
                 f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
-                f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr, precision == PREC_BF16);
+                f5_decode(E, nullptr, (int)N, f5_ref_len(E), pcm_dev, nullptr, precision);
                 if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)N * f5_n_mels(E) * sizeof(float), cudaMemcpyDeviceToDevice, s));
               },
               [&] { f5_restore_shape(E, (int)N, (int)(L / 256 + 1)); });
@@ -472,12 +472,12 @@ static void synth_batch_device(Engine& E, int U, const int16_t* audio_dev, int64
                   (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
               [&] {
                 for (int u = 0; u < U; ++u)
-                  f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U, precision == PREC_BF16);
+                  f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U, precision);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 f5_prepare_cond(E);
                 f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
                 for (int u = 0; u < U; ++u)
-                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr, precision == PREC_BF16);
+                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr, precision);
                 if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
               },
               [&] { f5_restore_shape(E, (int)N, F, U); });
@@ -490,7 +490,7 @@ int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* 
     Engine& E = eng(e);
     B2_CHECK(audio_dev && text_ids_dev && noise_dev && pcm_dev, "f5_synthesize_batch_device: null buffer");
     B2_CHECK(U >= 1 && L > 0 && n_text > 0 && max_duration > L / 256 + 2, "f5_synthesize_batch_device: bad sizes");
-    B2_CHECK(precision == PREC_BF16 || U == 1, "f5_synthesize_batch_device: the fp32 parity engine takes one utterance at a time");
+    B2_CHECK(precision != PREC_F32 || U == 1, "f5_synthesize_batch_device: the fp32 parity engine takes one utterance at a time");
     synth_batch_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, pcm_dev, mel_dev);
   });
 }
@@ -603,12 +603,13 @@ int b200tts_conv1d(b200tts_engine* e, const float* x_host, int B, int Cin, int L
       rowgemm_f32(p, s);
     } else {
       B2_CUDA(cudaMemcpyAsync(w.p, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      const int f16 = precision == PREC_F16 ? 1 : 0;
       TcWeight tw;
-      tc_weight_from_f32(tw, w.p, groups, k, ng, cg, s);
+      tc_weight_from_f32(tw, w.p, groups, k, ng, cg, s, f16);
       const int ld = (int)round_up(Cin, 8);
       DevBuf<__nv_bfloat16> x16((size_t)B * L * ld);
-      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s);
-      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld;
+      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s, f16);
+      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld; p.f16 = f16;
       rowgemm_tc(p, tw, s);
       B2_CUDA(cudaStreamSynchronize(s));   // tw / x16 are freed at scope exit
     }
@@ -656,12 +657,13 @@ int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int 
       rowgemm_f32(p, s);
     } else {
       B2_CUDA(cudaMemcpyAsync(w.p, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      const int f16 = precision == PREC_F16 ? 1 : 0;
       TcWeight tw;
-      tc_weight_from_f32(tw, w.p, 1, 2, (int)N, Cin, s);
+      tc_weight_from_f32(tw, w.p, 1, 2, (int)N, Cin, s, f16);
       const int ld = (int)round_up(Cin, 8);
       DevBuf<__nv_bfloat16> x16((size_t)B * L * ld);
-      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s);
-      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld;
+      cast_pad_f32_to_bf16(xt.p, x16.p, (long)B * L, Cin, ld, s, f16);
+      p.x = x16.p; p.ldx = ld; p.x_bstride = (long)L * ld; p.f16 = f16;
       rowgemm_tc(p, tw, s);
       B2_CUDA(cudaStreamSynchronize(s));
     }
@@ -673,9 +675,16 @@ int b200tts_conv_transpose1d(b200tts_engine* e, const float* x_host, int B, int 
 
 int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
                       float* out_host) {
+  return b200tts_attention_prec(e, q_host, k_host, v_host, H, N, B200TTS_BF16, out_host);
+}
+
+int b200tts_attention_prec(b200tts_engine* e, const float* q_host, const float* k_host, const float* v_host, int H, int N,
+                           int precision, float* out_host) {
   return guarded([&] {
     Engine& E = eng(e);
     B2_CHECK(q_host && k_host && v_host && out_host, "attention: null buffer");
+    B2_CHECK(precision == PREC_BF16 || precision == PREC_F16, "attention: the tcgen05 kernel takes bf16 or fp16 operands");
+    const int f16 = precision == PREC_F16 ? 1 : 0;
     B2_CHECK(H > 0 && N > 0, "attention: empty problem");
     cudaStream_t s = E.stream;
     const int D = H * 64, Np = (int)round_up(N, 8);
@@ -694,10 +703,10 @@ int b200tts_attention(b200tts_engine* e, const float* q_host, const float* k_hos
     DevBuf<__nv_bfloat16> qk16(qk.size()), vt16(vt.size()), o16((size_t)2 * N * D);
     B2_CUDA(cudaMemcpyAsync(d_qk.p, qk.data(), qk.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaMemcpyAsync(d_vt.p, vt.data(), vt.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-    cast_f32_to_bf16(d_qk.p, qk16.p, (long)qk.size(), s);
-    cast_f32_to_bf16(d_vt.p, vt16.p, (long)vt.size(), s);
-    attention_tc(qk16.p, vt16.p, Np, o16.p, 2, N, H, s);
-    cast_bf16_to_f32(o16.p, d_o32.p, (long)2 * N * D, s);
+    cast_f32_to_bf16(d_qk.p, qk16.p, (long)qk.size(), s, f16);
+    cast_f32_to_bf16(d_vt.p, vt16.p, (long)vt.size(), s, f16);
+    attention_tc(qk16.p, vt16.p, Np, o16.p, 2, N, H, s, f16);
+    cast_bf16_to_f32(o16.p, d_o32.p, (long)2 * N * D, s, f16);
     B2_CUDA(cudaMemcpyAsync(out_host, d_o32.p, d_o32.n * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
   });

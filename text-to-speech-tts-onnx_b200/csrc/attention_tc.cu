@@ -46,7 +46,14 @@ struct AttnArgs {
   int N, H;
   __nv_bfloat16* out;
   int ldo;
+  int f16;            // q, k, v, P and out are IEEE fp16 instead of bf16
 };
+
+__device__ __forceinline__ uint32_t pk16(float x, float y, int half) {
+  if (half) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 p = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -148,8 +155,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     }
   } else if (warp == WARP_MMA) {
     if (lane == 0) {
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKEY >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t fmt = a.f16 ? 0u : ((1u << 7) | (1u << 10));        // kind::f16 operand format: 1 = bf16, 0 = fp16
+      const uint32_t idesc_s = (1u << 4) | fmt | ((uint32_t)(BKEY >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | fmt | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint64_t dQ = make_desc_sw128(smem_u32(sQ));
       const uint64_t dP0 = make_desc_sw128(smem_u32(sP)), dP1 = make_desc_sw128(smem_u32(sP + P_BYTES / 2));
       auto issue_s = [&](int j) {
@@ -255,8 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
             up2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), e0, e1);
             const float p0 = ex2(e0), p1 = ex2(e1);
             sum2 = add2(sum2, pk2(p0, p1));
-            __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-            pkd[u] = *reinterpret_cast<uint32_t*>(&pp);
+            pkd[u] = pk16(p0, p1, a.f16);
           }
           const int chunk = (c * 4 + qq) ^ sw;
           *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
@@ -306,15 +313,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         const float4 x0 = *reinterpret_cast<const float4*>(srcx + ((k ^ sw) << 2));
         const float4 x1 = *reinterpret_cast<const float4*>(srcx + (((k + 1) ^ sw) << 2));
         uint32_t w[4];
-        __nv_bfloat162 pp;
-        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 0]) * scale + x0.x, __uint_as_float(mine[k * 4 + 1]) * scale + x0.y);
-        w[0] = *reinterpret_cast<uint32_t*>(&pp);
-        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 2]) * scale + x0.z, __uint_as_float(mine[k * 4 + 3]) * scale + x0.w);
-        w[1] = *reinterpret_cast<uint32_t*>(&pp);
-        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 4]) * scale + x1.x, __uint_as_float(mine[k * 4 + 5]) * scale + x1.y);
-        w[2] = *reinterpret_cast<uint32_t*>(&pp);
-        pp = __floats2bfloat162_rn(__uint_as_float(mine[k * 4 + 6]) * scale + x1.z, __uint_as_float(mine[k * 4 + 7]) * scale + x1.w);
-        w[3] = *reinterpret_cast<uint32_t*>(&pp);
+        w[0] = pk16(__uint_as_float(mine[k * 4 + 0]) * scale + x0.x, __uint_as_float(mine[k * 4 + 1]) * scale + x0.y, a.f16);
+        w[1] = pk16(__uint_as_float(mine[k * 4 + 2]) * scale + x0.z, __uint_as_float(mine[k * 4 + 3]) * scale + x0.w, a.f16);
+        w[2] = pk16(__uint_as_float(mine[k * 4 + 4]) * scale + x1.x, __uint_as_float(mine[k * 4 + 5]) * scale + x1.y, a.f16);
+        w[3] = pk16(__uint_as_float(mine[k * 4 + 6]) * scale + x1.z, __uint_as_float(mine[k * 4 + 7]) * scale + x1.w, a.f16);
         *reinterpret_cast<uint4*>(dst + k * 4) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
 
 }  // namespace
 
-void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream) {
+void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream, int f16) {
   B2_CHECK(S > 0 && N > 0 && H > 0, "attention_tc: empty problem");
   B2_CHECK(ldv % 8 == 0 && ldv >= N, "attention_tc: V^T row stride must be a multiple of 8 and >= N");
   CUtensorMap map_qk, map_v;
@@ -342,7 +344,7 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
-  AttnArgs a{N, H, out, H * HD};
+  AttnArgs a{N, H, out, H * HD, f16};
   B2_CHECK(S <= 65535, "attention_tc: too many sequences");
   dim3 grid(ceil_div(N, BQ), H, S);
   launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);

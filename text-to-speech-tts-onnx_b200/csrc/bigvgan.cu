@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) post_conv_kernel(const float* __restrict_
 struct ConvW {
   DevBuf<float> w;      // fp32 [taps][Cin][N]
   DevBuf<float> bias;   // [N]
-  TcWeight tc;          // bf16 [taps][N][Cin] + tensor map (fast path), built lazily
+  TcWeight tc[2];       // 16-bit [taps][N][Cin] (fast path), built lazily per operand type: [0] bf16, [1] fp16
   int Cin = 0, N = 0, taps = 0;
 };
 
@@ -281,26 +281,26 @@ __global__ void jcn_to_jnc_kernel(const float* __restrict__ in, float* __restric
   }
 }
 
-void prep_tc(Engine& e, ConvW& cw, DevBuf<float>& tmp) {
-  if (cw.tc.ready) return;
+void prep_tc(Engine& e, ConvW& cw, DevBuf<float>& tmp, int f16) {
+  if (cw.tc[f16].ready) return;
   const long total = (long)cw.taps * cw.Cin * cw.N;
   tmp.reserve(total);
   jcn_to_jnc_kernel<<<ceil_div(total, 256), 256, 0, e.stream>>>(cw.w.p, tmp.p, cw.taps, cw.Cin, cw.N);
   B2_LAUNCH_CHECK();
-  tc_weight_from_f32(cw.tc, tmp.p, 1, cw.taps, cw.N, cw.Cin, e.stream);
+  tc_weight_from_f32(cw.tc[f16], tmp.p, 1, cw.taps, cw.N, cw.Cin, e.stream, f16);
 }
 
 }  // namespace
 
-void bigvgan_tc_prepare(Engine& e, BigVGANModel& m) {
-  if (m.pre.tc.ready) return;
+void bigvgan_tc_prepare(Engine& e, BigVGANModel& m, int f16) {
+  if (m.pre.tc[f16].ready) return;
   DevBuf<float> tmp;
   for (auto& st : m.stages) {
-    prep_tc(e, st.up, tmp);
+    prep_tc(e, st.up, tmp, f16);
     for (int j = 0; j < 3; ++j)
-      for (int mm = 0; mm < 3; ++mm) { prep_tc(e, st.c1[j][mm], tmp); prep_tc(e, st.c2[j][mm], tmp); }
+      for (int mm = 0; mm < 3; ++mm) { prep_tc(e, st.c1[j][mm], tmp, f16); prep_tc(e, st.c2[j][mm], tmp, f16); }
   }
-  prep_tc(e, m.pre, tmp);
+  prep_tc(e, m.pre, tmp, f16);
   B2_CUDA(cudaStreamSynchronize(e.stream));
 }
 
@@ -311,6 +311,8 @@ struct Ctx {
   BigVGANModel& m;
   int B;
   bool fast;
+  int f16;      // fast path operand type: 0 = bf16, 1 = fp16
+  int t16;      // its type code as an output (rowgemm.cuh out_bf16 / aa_snake): 1 = bf16, 2 = fp16
 };
 
 // y = conv(x) with the shifted-row GEMM; x, out are (B, L, C) fp32 (or bf16 for the tc path's A operand)
@@ -324,9 +326,10 @@ void run_conv(Ctx& c, const char* tag, const ConvW& cw, const void* x, int L, in
   p.M = L; p.B = c.B;
   p.out = out; p.o_bstride = (long)L * cw.N; p.ldo = cw.N; p.out_bf16 = out_bf16;
   p.bias = bias ? bias : cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale; p.out2 = c.fast ? out2 : nullptr;
+  p.f16 = c.f16;
   ProfScope ps(c.e.prof, tag, c.e.stream);
   if (c.fast) {
-    rowgemm_tc(p, cw.tc, c.e.stream);
+    rowgemm_tc(p, cw.tc[c.f16], c.e.stream);
   } else {
     p.w = cw.w.p; p.ldw = cw.N;
     rowgemm_f32(p, c.e.stream);
@@ -346,9 +349,10 @@ void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out, const f
     p.center = 0; p.M = Lin;
   }
   p.bias = bias;
+  p.f16 = c.f16;
   ProfScope ps(c.e.prof, "bigvgan.ups", c.e.stream);
   if (c.fast) {
-    rowgemm_tc(p, st.up.tc, c.e.stream);
+    rowgemm_tc(p, st.up.tc[c.f16], c.e.stream);
   } else {
     p.w = st.up.w.p; p.ldw = (int)N;
     rowgemm_f32(p, c.e.stream);
@@ -360,11 +364,11 @@ void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out, const f
 void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T, int precision, int16_t* d_pcm, float* d_wave,
                      const float* const* d_conds) {
   B2_CHECK(B > 0 && T > 0, "bigvgan: empty input");
-  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "bigvgan: unknown precision");
+  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16 || precision == PREC_F16, "bigvgan: unknown precision");
   const bool latent_in = m.fn_w.p != nullptr;           // IndexTTS_F: d_in = GPT latent rows (T, gpt_dim), already channels-last
   B2_CHECK(!latent_in || B == 1, "the IndexTTS vocoder takes one latent sequence per call");
   B2_CHECK(latent_in == (d_conds != nullptr), "conditioning vectors go with the IndexTTS vocoder only");
-  Ctx c{e, m, B, precision == PREC_BF16};
+  Ctx c{e, m, B, precision != PREC_F32, precision == PREC_F16 ? 1 : 0, precision == PREC_F16 ? 2 : 1};
   cudaStream_t s = e.stream;
 
   // workspace: every stage tensor has C*L <= C0*hop/… ; the largest is max_i(C_i * L_i), the post tensor adds 30 rows
@@ -379,7 +383,7 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
   m.xu.reserve(ws); m.xs.reserve(ws); m.xa.reserve(ws); m.xb.reserve(ws); m.abuf.reserve(ws);
   if (c.fast) {
     m.abuf16.reserve(ws); m.cbuf16.reserve(ws); m.mel16.reserve((size_t)B * T * round_up(m.n_mels, 8)); m.xs16.reserve(ws);
-    bigvgan_tc_prepare(e, m);  // bf16 weight layouts (first fast call only)
+    bigvgan_tc_prepare(e, m, c.f16);  // 16-bit weight layouts (first fast call of each operand type only)
   } else {
     m.cbuf.reserve(ws);
   }
@@ -408,7 +412,7 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
   if (c.fast) {
     ProfScope ps(e.prof, "bigvgan.cast", s);
     mel_ld = (int)round_up(m.n_mels, 8);      // bf16 rows must be 16-byte multiples for TMA
-    cast_pad_f32_to_bf16(m.mel_cl.p, m.mel16.p, (long)B * T, m.n_mels, mel_ld, s);
+    cast_pad_f32_to_bf16(m.mel_cl.p, m.mel16.p, (long)B * T, m.n_mels, mel_ld, s, c.f16);
     conv_in = m.mel16.p;
   }
   // conv_pre -> xs (B, T, C0)
@@ -433,14 +437,14 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
         const bool last = (mm == 2);
         {
           ProfScope ps(e.prof, atag, s);
-          if (c.fast) aa_snake(xcur, 0, m.abuf16.p, 1, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, false, false, s);
+          if (c.fast) aa_snake(xcur, 0, m.abuf16.p, c.t16, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, false, false, s);
           else aa_snake(xcur, 0, m.abuf.p, 0, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, true, false, s);
         }
-        if (c.fast) run_conv(c, ctag, st.c1[j][mm], m.abuf16.p, L, st.dil[j][mm], m.cbuf16.p, 1, nullptr, 0, 1.0f);
+        if (c.fast) run_conv(c, ctag, st.c1[j][mm], m.abuf16.p, L, st.dil[j][mm], m.cbuf16.p, c.t16, nullptr, 0, 1.0f);
         else run_conv(c, ctag, st.c1[j][mm], m.abuf.p, L, st.dil[j][mm], m.cbuf.p, 0, nullptr, 0, 1.0f);
         {
           ProfScope ps(e.prof, atag, s);
-          if (c.fast) aa_snake(m.cbuf16.p, 1, m.abuf16.p, 1, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, false, false, s);
+          if (c.fast) aa_snake(m.cbuf16.p, c.t16, m.abuf16.p, c.t16, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, false, false, s);
           else aa_snake(m.cbuf.p, 0, m.abuf.p, 0, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, true, false, s);
         }
         const void* a2 = c.fast ? (const void*)m.abuf16.p : (const void*)m.abuf.p;

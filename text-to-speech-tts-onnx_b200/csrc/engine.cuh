@@ -109,7 +109,9 @@ struct Engine {
   ~Engine();
 };
 
-enum Precision : int { PREC_F32 = 0, PREC_BF16 = 1 };
+// arithmetic of the dense contractions; for the 16-bit engines the value doubles as the type code of 16-bit tensors
+// (rowgemm.cuh out_bf16, aa_snake, ln_modulate): 1 = bf16, 2 = IEEE fp16
+enum Precision : int { PREC_F32 = 0, PREC_BF16 = 1, PREC_F16 = 2 };
 
 // Run `body` (a sequence of enqueues on e.stream, no host synchronisation inside) through the graph cache.
 // `on_replay` restores whatever host-side state `body` would have set (it does not run when the graph is replayed).

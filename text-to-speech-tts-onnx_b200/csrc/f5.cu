@@ -14,8 +14,10 @@
 #include "f5.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "attention_tc.cuh"
+#include "dit_chain.cuh"
 #include "f5_kernels.cuh"
 #include "layout.cuh"
 #include "rowgemm.cuh"
@@ -31,7 +33,7 @@ struct Lin {                 // y = x W^T + b ; reference weight [N][K]
   DevBuf<float> w_own;       // when the reference-layout weight is assembled here (qkv concat, Wx/Wc split)
   DevBuf<float> wT;          // [K][Np] (lazy, fp32 engine)
   DevBuf<float> bias;        // [Np] (zero padded) or empty
-  TcWeight tc;               // lazy, tensor-core engine
+  TcWeight tc[2];            // lazy, tensor-core engine: [0] bf16, [1] fp16 operands
 };
 
 struct GConv {               // grouped Conv1d (conv position embedding)
@@ -39,7 +41,7 @@ struct GConv {               // grouped Conv1d (conv position embedding)
   const float* w_ref = nullptr;   // (C, C/groups, k)
   DevBuf<float> w32;         // [g][j][c][n]
   DevBuf<float> bias;
-  TcWeight tc;               // [g][j][n][c]
+  TcWeight tc[2];            // [g][j][n][c]: [0] bf16, [1] fp16
 };
 
 struct TextBlock {
@@ -79,7 +81,7 @@ struct F5Model {
   int VC = 0, VI = 0;
   DevBuf<float> v_embed_w, v_embed_b;       // [7][n_mels][VC]
   const float* v_embed_ref = nullptr;       // reference layout (VC, n_mels, 7): source of the tensor-core copy
-  TcWeight v_embed_tc, istft_tc, head_tc;   // lazy, tensor-core engine
+  TcWeight v_embed_tc[2], istft_tc[2], head_tc[2];   // lazy, tensor-core engine ([0] bf16, [1] fp16)
   const float* istft_ref = nullptr;         // (2*bins, nfft)
   DevBuf<__nv_bfloat16> s16a, s16b;         // bf16 staging of the front / back end GEMM operands (tensor-core engine)
   DevBuf<float> v_nw, v_nb, v_fw, v_fb;
@@ -95,7 +97,9 @@ struct F5Model {
   DevBuf<float> noise, cond, cond_drop, cproj, x, h, pred, rope_c, rope_s;
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
-  DevBuf<__nv_bfloat16> h16, c16, n16, qk16, vT16, att16, ff16, x16;   // tensor-core engine
+  DevBuf<__nv_bfloat16> h16, c16, n16, n16b, qk16, vT16, att16, ff16, x16;   // tensor-core engine (bf16 or fp16 bits)
+  DevBuf<float> chain_stats;                                           // dit_chain.cuh: team scratch
+  DevBuf<unsigned> chain_flags;                                        // [depth][row blocks][8], zeroed once per Euler step
   DevBuf<__half2> rope_cs16;                                           // [N][64] (cos, sin): exact, the tables are fp16-rounded (q5)
   // preprocess / decode scratch
   DevBuf<float> audio_f, spec, mag, mel, t_a, t_b, t_c, t_wide, grn_scratch;
@@ -128,9 +132,9 @@ void lin_prepare_f32(Engine& e, Lin& L) {
   L.wT.alloc((size_t)L.K * L.Np);
   transpose_pad(L.w_ref, L.wT.p, L.N, L.K, L.Np, e.stream);
 }
-void lin_prepare_tc(Engine& e, Lin& L) {
-  if (L.tc.ready) return;
-  tc_weight_from_f32(L.tc, L.w_ref, 1, 1, L.N, L.K, e.stream);
+void lin_prepare_tc(Engine& e, Lin& L, int f16) {
+  if (L.tc[f16].ready) return;
+  tc_weight_from_f32(L.tc[f16], L.w_ref, 1, 1, L.N, L.K, e.stream, f16);
 }
 
 void dw_from(Engine& e, const std::string& wname, const std::string& bname, DevBuf<float>& w, DevBuf<float>& b, int C) {
@@ -148,18 +152,18 @@ struct Epi {
 
 // fp32 [rows][C] (row stride ld) -> bf16 [rows][round_up(C, 8)] in `dst`: the A operand of a tensor-core GEMM whose producer
 // is an fp32 kernel (norms, GRN, ISTFT input) -- the front / back end of the bf16 engine
-const __nv_bfloat16* stage_bf16(Engine& e, DevBuf<__nv_bfloat16>& dst, const float* x, int ld, int rows, int C, int* ld16) {
+const __nv_bfloat16* stage_bf16(Engine& e, DevBuf<__nv_bfloat16>& dst, const float* x, int ld, int rows, int C, int* ld16, int f16) {
   B2_CHECK(ld == C, "stage_bf16: compact rows expected");
   *ld16 = (int)round_up(C, 8);
   dst.reserve((size_t)rows * *ld16);
   ProfScope ps(e.prof, "f5.cast", e.stream);
-  if (*ld16 == C) cast_f32_to_bf16(x, dst.p, (long)rows * C, e.stream);
-  else cast_pad_f32_to_bf16(x, dst.p, rows, C, *ld16, e.stream);
+  if (*ld16 == C) cast_f32_to_bf16(x, dst.p, (long)rows * C, e.stream, f16);
+  else cast_pad_f32_to_bf16(x, dst.p, rows, C, *ld16, e.stream, f16);
   return dst.p;
 }
 
-// rows x K (ldx) @ W^T -> rows x N (ldo). use_tc: bf16 A operand + tcgen05, else fp32 SIMT.
-void linear(Engine& e, const char* tag, Lin& L, bool use_tc, const void* x, int ldx, int rows, void* out, int ldo, const Epi& ep) {
+// rows x K (ldx) @ W^T -> rows x N (ldo). use_tc: 0 = fp32 SIMT; 1 / 2 = bf16 / fp16 A operand + tcgen05 (engine.cuh Precision).
+void linear(Engine& e, const char* tag, Lin& L, int use_tc, const void* x, int ldx, int rows, void* out, int ldo, const Epi& ep) {
   RowGemm p;
   p.x = x; p.x_bstride = 0; p.ldx = ldx; p.Lin = rows;
   p.Cin = L.K; p.N = use_tc ? L.N : L.Np; p.taps = 1; p.M = rows; p.B = 1;
@@ -167,8 +171,10 @@ void linear(Engine& e, const char* tag, Lin& L, bool use_tc, const void* x, int 
   p.bias = ep.bias; p.gate = ep.gate; p.res = ep.res; p.act = ep.act;
   ProfScope ps(e.prof, tag, e.stream);
   if (use_tc) {
-    lin_prepare_tc(e, L);
-    rowgemm_tc(p, L.tc, e.stream);
+    const int f16 = use_tc == PREC_F16 ? 1 : 0;
+    p.f16 = f16;
+    lin_prepare_tc(e, L, f16);
+    rowgemm_tc(p, L.tc[f16], e.stream);
   } else {
     lin_prepare_f32(e, L);
     B2_CHECK(L.Np <= ldo || L.Np == L.N, "linear: padded N exceeds the output row stride");
@@ -244,7 +250,7 @@ F5Model* f5_build(Engine& e) {
     B2_CHECK(L.N == out_dim && L.K == m.D, name + ": AdaLN linear shape");
     table.alloc((size_t)m.nfe * out_dim);
     Epi ep; ep.bias = L.bias.p;
-    linear(e, "f5.build", L, false, st.p, m.D, m.nfe, table.p, out_dim, ep);
+    linear(e, "f5.build", L, 0, st.p, m.D, m.nfe, table.p, out_dim, ep);
     B2_CUDA(cudaStreamSynchronize(s));       // L (and its transposed copy) is freed at scope exit
   };
   for (int i = 0; i < m.depth; ++i) {
@@ -410,15 +416,15 @@ void f5_prepare_cond(Engine& e) {
   Epi ep; ep.bias = m.wc.bias.p;
   for (int u = 0; u < m.U; ++u) {             // sequence 2u = cond, 2u+1 = cond_drop of utterance u
     const size_t co = (size_t)u * m.N * m.cond_dim, po = (size_t)2 * u * m.N * m.D;
-    linear(e, "f5.cond_proj", m.wc, false, m.cond.p + co, m.cond_dim, m.N, m.cproj.p + po, m.D, ep);
-    linear(e, "f5.cond_proj", m.wc, false, m.cond_drop.p + co, m.cond_dim, m.N, m.cproj.p + po + (size_t)m.N * m.D, m.D, ep);
+    linear(e, "f5.cond_proj", m.wc, 0, m.cond.p + co, m.cond_dim, m.N, m.cproj.p + po, m.D, ep);
+    linear(e, "f5.cond_proj", m.wc, 0, m.cond_drop.p + co, m.cond_dim, m.N, m.cproj.p + po + (size_t)m.N * m.D, m.D, ep);
   }
 }
 
 // =============================================================================================
 // graph A
 // =============================================================================================
-void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u, int U, bool fast) {
+void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u, int U, int fast) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   const int F = (int)(L / m.hop) + 1;
@@ -441,7 +447,7 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
   {
     // frames are overlapping rows of the padded signal: row stride = hop (STFT_Process.py:153-157 as one GEMM)
     Epi ep;
-    linear(e, "f5.stft", m.stft, false, m.audio_f.p, m.hop, F, m.spec.p, m.stft.Np, ep);
+    linear(e, "f5.stft", m.stft, 0, m.audio_f.p, m.hop, F, m.spec.p, m.stft.Np, ep);
   }
   const int ldm = m.fbank.K;
   m.mag.reserve((size_t)F * ldm);
@@ -452,7 +458,7 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
   }
   {
     Epi ep;
-    linear(e, "f5.fbank", m.fbank, false, m.mag.p, ldm, F, m.mel.p, m.n_mels, ep);
+    linear(e, "f5.fbank", m.fbank, 0, m.mag.p, ldm, F, m.mel.p, m.n_mels, ep);
   }
   {
     ProfScope ps(e.prof, "f5.pre_elementwise", s);
@@ -478,15 +484,16 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
       Epi e2; e2.bias = tb.pw2.bias.p; e2.res = m.t_a.p;
       if (fast) {                      // bf16 engine: the two pointwise GEMMs on tensor cores (GRN needs the fp32 hidden)
         int l16 = 0;
-        const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.t_c.p, TD, N, TD, &l16);
-        linear(e, "f5.text_embed.gemm", tb.pw1, true, a1, l16, N, m.t_wide.p, TW, e1);
+        const int f16 = fast == PREC_F16 ? 1 : 0;
+        const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.t_c.p, TD, N, TD, &l16, f16);
+        linear(e, "f5.text_embed.gemm", tb.pw1, fast, a1, l16, N, m.t_wide.p, TW, e1);
         grn_inplace(m.t_wide.p, tb.gamma.p, tb.beta.p, m.grn_scratch.p, N, TW, s);
-        const __nv_bfloat16* a2 = stage_bf16(e, m.s16b, m.t_wide.p, TW, N, TW, &l16);
-        linear(e, "f5.text_embed.gemm", tb.pw2, true, a2, l16, N, m.t_b.p, TD, e2);
+        const __nv_bfloat16* a2 = stage_bf16(e, m.s16b, m.t_wide.p, TW, N, TW, &l16, f16);
+        linear(e, "f5.text_embed.gemm", tb.pw2, fast, a2, l16, N, m.t_b.p, TD, e2);
       } else {
-        linear(e, "f5.text_embed.gemm", tb.pw1, false, m.t_c.p, TD, N, m.t_wide.p, TW, e1);
+        linear(e, "f5.text_embed.gemm", tb.pw1, 0, m.t_c.p, TD, N, m.t_wide.p, TW, e1);
         grn_inplace(m.t_wide.p, tb.gamma.p, tb.beta.p, m.grn_scratch.p, N, TW, s);
-        linear(e, "f5.text_embed.gemm", tb.pw2, false, m.t_wide.p, TW, N, m.t_b.p, TD, e2);
+        linear(e, "f5.text_embed.gemm", tb.pw2, 0, m.t_wide.p, TW, N, m.t_b.p, TD, e2);
       }
       mask_rows(m.t_b.p, m.ids.p, N, TD, s);
       std::swap(m.t_a, m.t_b);
@@ -500,7 +507,7 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
 // =============================================================================================
 namespace {
 
-void gconv(Engine& e, GConv& g, bool fast, const void* x, int N, void* out, int out_bf16, int act, const float* res) {
+void gconv(Engine& e, GConv& g, int fast, const void* x, int N, void* out, int out_bf16, int act, const float* res) {
   F5Model& m = *e.f5;
   const int cg = g.C / g.groups;
   RowGemm p;
@@ -512,13 +519,15 @@ void gconv(Engine& e, GConv& g, bool fast, const void* x, int N, void* out, int 
   (void)m;
   ProfScope ps(e.prof, "f5.conv_pos", e.stream);
   if (fast) {
-    if (!g.tc.ready) {
+    const int f16 = fast == PREC_F16 ? 1 : 0;
+    p.f16 = f16;
+    if (!g.tc[f16].ready) {
       DevBuf<float> tmp((size_t)g.C * cg * g.k);
       conv_weight_permute(g.w_ref, tmp.p, g.C, cg, g.k, g.groups, 0, e.stream);
-      tc_weight_from_f32(g.tc, tmp.p, g.groups, g.k, cg, cg, e.stream);
+      tc_weight_from_f32(g.tc[f16], tmp.p, g.groups, g.k, cg, cg, e.stream, f16);
       B2_CUDA(cudaStreamSynchronize(e.stream));
     }
-    rowgemm_tc(p, g.tc, e.stream);
+    rowgemm_tc(p, g.tc[f16], e.stream);
   } else {
     if (!g.w32.p) {
       g.w32.alloc((size_t)g.C * cg * g.k);
@@ -532,7 +541,9 @@ void gconv(Engine& e, GConv& g, bool fast, const void* x, int N, void* out, int 
 void reserve_step(F5Model& m, bool fast) {
   const size_t R = (size_t)2 * m.U * m.N;
   if (fast) {
-    m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.att16.reserve(R * m.D);
+    m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.n16b.reserve(R * m.D); m.att16.reserve(R * m.D);
+    m.chain_stats.reserve(dit_chain_stats_floats((int)R));
+    m.chain_flags.reserve(dit_chain_flag_words((int)R) * (size_t)m.depth);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
     m.x16.reserve((size_t)m.U * m.N * round_up(m.n_mels, 8));
@@ -566,16 +577,25 @@ void attention_f32(Engine& e, F5Model& m, int b) {
 
 }  // namespace
 
+// B200TTS_CHAIN=0 keeps every DiT block as seven launches (LN, q|k|v, attention, out, LN, ff1, ff2): the A/B switch for the
+// fused row-block chain (dit_chain.cu).
+static bool chain_enabled() {
+  static const bool on = [] { const char* v = getenv("B200TTS_CHAIN"); return !(v != nullptr && v[0] == '0'); }();
+  return on;
+}
+
 void f5_steps(Engine& e, int first, int count, int precision) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   B2_CHECK(m.N > 0, "f5_steps: no utterance state (run preprocess / begin first)");
   B2_CHECK(first >= 0 && count >= 0 && first + count <= m.nfe - 1, "f5_steps: time_step out of range");
-  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16, "f5_steps: unknown precision");
-  const bool fast = precision == PREC_BF16;
+  B2_CHECK(precision == PREC_F32 || precision == PREC_BF16 || precision == PREC_F16, "f5_steps: unknown precision");
+  const int fast = precision == PREC_F32 ? 0 : precision;      // 0 = fp32 SIMT parity engine, 1 / 2 = bf16 / fp16 tensor-core engine
+  const int f16 = precision == PREC_F16 ? 1 : 0;
   const int N = m.N, D = m.D, S = 2 * m.U, R = S * N;
   B2_CHECK(fast || m.U == 1, "the fp32 parity engine runs one utterance at a time");
-  reserve_step(m, fast);
+  reserve_step(m, fast != 0);
+  const bool chain = fast && chain_enabled() && dit_chain_supported(D, m.FF, m.H);
   PdlScope pdl(m.U == 1);                  // short kernels only (common.cuh)
   if (!fast) {   // padding rows / columns (t in [N, Npad)) of the fp32 attention operands must read as zero
     B2_CUDA(cudaMemsetAsync(m.kT32.p, 0, (size_t)2 * m.H * m.hd * m.Npad * sizeof(float), s));
@@ -584,35 +604,81 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   if (fast) {
     ProfScope ps(e.prof, "f5.cast", s);
     rope_pack_half(m.cur_cos, m.cur_sin, m.rope_cs16.p, (long)N * m.hd, s);
+    for (auto& L : m.layers) { lin_prepare_tc(e, L.qkv, f16); lin_prepare_tc(e, L.out, f16); lin_prepare_tc(e, L.ff1, f16); lin_prepare_tc(e, L.ff2, f16); }
   }
+  // q | k | v of block l from the LN-modulated rows in `a16`: one GEMM, RoPE + V^T in the epilogue (modules.py:459-466)
+  auto qkv_fast = [&](DiTLayer& L, const __nv_bfloat16* a16) {
+    RowGemm p;
+    p.x = a16; p.ldx = D; p.Lin = R; p.Cin = D; p.N = 3 * D; p.taps = 1; p.M = R; p.B = 1;
+    p.out = m.qk16.p; p.ldo = 2 * D; p.out_bf16 = fast; p.o_limit = (long)R * 2 * D + 3 * D;
+    p.bias = L.qkv.bias.p; p.f16 = f16;
+    p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N;
+    p.vt_out = m.vT16.p; p.vt_col0 = 2 * D; p.vt_ld = m.Npad; p.vt_heads = m.H;
+    ProfScope ps(e.prof, "f5.qkv_gemm", s);
+    rowgemm_tc(p, L.qkv.tc[f16], s);
+  };
+  const size_t flag_words = dit_chain_flag_words(R);
   for (int step = first; step < first + count; ++step) {
     // ---- input embedding: h[b] = Wx x + (Wc c_b + bias) ; x = conv_pos(h) + h ----
     if (fast) {
-      // tensor-core form: x of all U utterances as one batched A operand (bf16, rows padded to 8), one launch per CFG row
-      // (both rows share x); the epilogue adds the step-invariant half and also writes the bf16 copy conv_pos reads
+      // tensor-core form: x of all U utterances as one batched A operand (16-bit, rows padded to 8), one launch per CFG row
+      // (both rows share x); the epilogue adds the step-invariant half and also writes the 16-bit copy conv_pos reads
       const int ldx = (int)round_up(m.n_mels, 8);
-      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, (long)m.U * N, m.n_mels, ldx, s); }
-      lin_prepare_tc(e, m.wx);
+      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, (long)m.U * N, m.n_mels, ldx, s, f16); }
+      lin_prepare_tc(e, m.wx, f16);
       for (int b = 0; b < 2; ++b) {
         RowGemm p;
         p.x = m.x16.p; p.x_bstride = (long)N * ldx; p.ldx = ldx; p.Lin = N;
         p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = N; p.B = m.U;
         p.out = m.h.p + (size_t)b * N * D; p.o_bstride = (long)2 * N * D; p.ldo = D;
         p.res = m.cproj.p + (size_t)b * N * D;
-        p.out2 = m.h16.p + (size_t)b * N * D;
+        p.out2 = m.h16.p + (size_t)b * N * D; p.f16 = f16;
         ProfScope ps(e.prof, "f5.embed_x", s);
-        rowgemm_tc(p, m.wx.tc, s);
+        rowgemm_tc(p, m.wx.tc[f16], s);
       }
-      gconv(e, m.cp1, true, m.h16.p, N, m.c16.p, 1, ACT_MISH, nullptr);
-      gconv(e, m.cp2, true, m.c16.p, N, m.x.p, 0, ACT_MISH, m.h.p);
+      gconv(e, m.cp1, fast, m.h16.p, N, m.c16.p, fast, ACT_MISH, nullptr);
+      gconv(e, m.cp2, fast, m.c16.p, N, m.x.p, 0, ACT_MISH, m.h.p);
     } else {
       for (int sq = 0; sq < S; ++sq) {           // sequence sq = (utterance sq/2, CFG row sq%2): both rows share x
         Epi ep; ep.res = m.cproj.p + (size_t)sq * N * D;
-        linear(e, "f5.embed_x", m.wx, false, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
+        linear(e, "f5.embed_x", m.wx, 0, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
       }
-      gconv(e, m.cp1, false, m.h.p, N, m.c32.p, 0, ACT_MISH, nullptr);
-      gconv(e, m.cp2, false, m.c32.p, N, m.x.p, 0, ACT_MISH, m.h.p);
+      gconv(e, m.cp1, 0, m.h.p, N, m.c32.p, 0, ACT_MISH, nullptr);
+      gconv(e, m.cp2, 0, m.c32.p, N, m.x.p, 0, ACT_MISH, m.h.p);
     }
+    const float* mf = m.mod_final.p + (size_t)step * 2 * D;       // chunk order: scale, shift (modules.py:323)
+    if (chain) {
+      // ---- 22 DiT blocks, fused: block 0's LN + q|k|v as two launches, then per block attention + ONE chain kernel that runs
+      //      out-proj, LN, ff1, ff2, LN and the NEXT block's q|k|v (dit_chain.cu) ----
+      B2_CUDA(cudaMemsetAsync(m.chain_flags.p, 0, flag_words * m.depth * sizeof(unsigned), s));
+      {
+        const float* mod0 = m.layers[0].mod.p + (size_t)step * 6 * D;
+        { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, mod0 + D, mod0, m.n16b.p, fast, R, D, s); }
+        qkv_fast(m.layers[0], m.n16b.p);
+      }
+      for (int l = 0; l < m.depth; ++l) {
+        DiTLayer& L = m.layers[l];
+        const float* mod = L.mod.p + (size_t)step * 6 * D;
+        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16); }
+        const bool last = l + 1 == m.depth;
+        const float* nxt = last ? nullptr : m.layers[l + 1].mod.p + (size_t)step * 6 * D;
+        DitChain c;
+        c.R = R; c.D = D; c.FF = m.FF; c.f16 = f16; c.has_qkv = last ? 0 : 1;
+        c.att16 = m.att16.p; c.x = m.x.p; c.n16 = m.n16.p; c.ff16 = m.ff16.p; c.n16b = m.n16b.p;
+        c.w_out = &L.out.tc[f16]; c.w_ff1 = &L.ff1.tc[f16]; c.w_ff2 = &L.ff2.tc[f16];
+        c.b_out = L.out.bias.p; c.gate_msa = mod + 2 * D; c.shift_mlp = mod + 3 * D; c.scale_mlp = mod + 4 * D;
+        c.b_ff1 = L.ff1.bias.p; c.b_ff2 = L.ff2.bias.p; c.gate_mlp = mod + 5 * D;
+        if (last) { c.scale_nxt = mf; c.shift_nxt = mf + D; }
+        else {
+          c.shift_nxt = nxt; c.scale_nxt = nxt + D;
+          c.w_qkv = &m.layers[l + 1].qkv.tc[f16]; c.b_qkv = m.layers[l + 1].qkv.bias.p;
+          c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
+        }
+        c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
+        ProfScope ps(e.prof, "f5.chain", s);
+        dit_chain(c, s);
+      }
+    } else {
     // ---- 22 DiT blocks ----
     for (int l = 0; l < m.depth; ++l) {
       DiTLayer& L = m.layers[l];
@@ -622,18 +688,11 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       void* nbuf = fast ? (void*)m.n16.p : (void*)m.n32.p;
       { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, scale_msa, shift_msa, nbuf, fast, R, D, s); }
       if (fast) {
-        lin_prepare_tc(e, L.qkv);
-        RowGemm p;
-        p.x = m.n16.p; p.ldx = D; p.Lin = R; p.Cin = D; p.N = 3 * D; p.taps = 1; p.M = R; p.B = 1;
-        p.out = m.qk16.p; p.ldo = 2 * D; p.out_bf16 = 1; p.o_limit = (long)R * 2 * D + 3 * D;
-        p.bias = L.qkv.bias.p;
-        p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N;
-        p.vt_out = m.vT16.p; p.vt_col0 = 2 * D; p.vt_ld = m.Npad; p.vt_heads = m.H;
-        { ProfScope ps(e.prof, "f5.qkv_gemm", s); rowgemm_tc(p, L.qkv.tc, s); }
-        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s); }
+        qkv_fast(L, m.n16.p);
+        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16); }
       } else {
         Epi ep; ep.bias = L.qkv.bias.p;
-        linear(e, "f5.qkv_gemm", L.qkv, false, m.n32.p, D, R, m.qkv32.p, 3 * D, ep);
+        linear(e, "f5.qkv_gemm", L.qkv, 0, m.n32.p, D, R, m.qkv32.p, 3 * D, ep);
         {
           ProfScope ps(e.prof, "f5.rope_split", s);
           rope_split_f32(m.qkv32.p, m.cur_cos, m.cur_sin, m.kT32.p, m.v32.p, N, m.H, m.hd, m.Npad, s);
@@ -655,10 +714,10 @@ void f5_steps(Engine& e, int first, int count, int precision) {
         linear(e, "f5.ff2_gemm", L.ff2, fast, fast ? (const void*)m.ff16.p : (const void*)m.ff32.p, m.FF, R, m.x.p, D, ep);
       }
     }
+    }
     // ---- final modulation, projection, CFG + Euler ----
-    const float* mf = m.mod_final.p + (size_t)step * 2 * D;       // chunk order: scale, shift (modules.py:323)
-    void* nbuf = fast ? (void*)m.n16.p : (void*)m.n32.p;
-    { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, mf, mf + D, nbuf, fast, R, D, s); }
+    void* nbuf = fast ? (chain ? (void*)m.n16b.p : (void*)m.n16.p) : (void*)m.n32.p;
+    if (!chain) { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, mf, mf + D, nbuf, fast, R, D, s); }
     {
       Epi ep; ep.bias = m.proj.bias.p;
       linear(e, "f5.proj_out", m.proj, fast, nbuf, D, R, m.pred.p, m.n_mels, ep);
@@ -673,13 +732,14 @@ void f5_steps(Engine& e, int first, int count, int precision) {
 // =============================================================================================
 // graph C
 // =============================================================================================
-long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, bool fast) {
+long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, int fast) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
   if (d_mel == nullptr) { d_mel = m.noise.p; }
   B2_CHECK(ref_len >= 0 && ref_len < N, "decode: ref_signal_len must be in [0, max_duration)");
   const int G = N - ref_len;
   B2_CHECK(G <= m.max_frames, "decode: more frames than the ISTFT window-sum table covers");
+  const int f16 = fast == PREC_F16 ? 1 : 0;
   const float* x0 = d_mel + (size_t)ref_len * m.n_mels;        // slice [:, ref_len:] -- rows are frames
   const int VC = m.VC, VI = m.VI;
   m.d_a.reserve((size_t)G * VC); m.d_b.reserve((size_t)G * VC); m.d_c.reserve((size_t)G * VC);
@@ -690,17 +750,17 @@ long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm
     p.x = x0; p.ldx = m.n_mels; p.Lin = G; p.Cin = m.n_mels; p.N = VC; p.taps = 7; p.center = 3; p.M = G; p.B = 1;
     p.w = m.v_embed_w.p; p.ldw = VC; p.out = m.d_a.p; p.ldo = VC; p.bias = m.v_embed_b.p;
     if (fast) {
-      if (!m.v_embed_tc.ready) {
+      if (!m.v_embed_tc[f16].ready) {
         DevBuf<float> tmp((size_t)7 * VC * m.n_mels);
         conv_weight_permute(m.v_embed_ref, tmp.p, VC, m.n_mels, 7, 1, 0, s);
-        tc_weight_from_f32(m.v_embed_tc, tmp.p, 1, 7, VC, m.n_mels, s);
+        tc_weight_from_f32(m.v_embed_tc[f16], tmp.p, 1, 7, VC, m.n_mels, s, f16);
         B2_CUDA(cudaStreamSynchronize(s));
       }
       int l16 = 0;
-      p.x = stage_bf16(e, m.s16a, x0, m.n_mels, G, m.n_mels, &l16);
-      p.ldx = l16;
+      p.x = stage_bf16(e, m.s16a, x0, m.n_mels, G, m.n_mels, &l16, f16);
+      p.ldx = l16; p.f16 = f16;
       ProfScope ps(e.prof, "f5.vocos_gemm", s);
-      rowgemm_tc(p, m.v_embed_tc, s);
+      rowgemm_tc(p, m.v_embed_tc[f16], s);
     } else {
       ProfScope ps(e.prof, "f5.vocos_gemm", s);
       rowgemm_f32(p, s);
@@ -718,14 +778,14 @@ long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm
     Epi e2; e2.bias = vb.pw2.bias.p; e2.res = cur;
     if (fast) {                        // pw1 writes its GELU output as bf16: pw2's A operand, no staging pass
       int l16 = 0;
-      const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16);
+      const __nv_bfloat16* a1 = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16, f16);
       m.s16b.reserve((size_t)G * VI);
-      e1.out_bf16 = 1;
-      linear(e, "f5.vocos_gemm", vb.pw1, true, a1, l16, G, m.s16b.p, VI, e1);
-      linear(e, "f5.vocos_gemm", vb.pw2, true, m.s16b.p, VI, G, other, VC, e2);
+      e1.out_bf16 = fast;
+      linear(e, "f5.vocos_gemm", vb.pw1, fast, a1, l16, G, m.s16b.p, VI, e1);
+      linear(e, "f5.vocos_gemm", vb.pw2, fast, m.s16b.p, VI, G, other, VC, e2);
     } else {
-      linear(e, "f5.vocos_gemm", vb.pw1, false, m.d_c.p, VC, G, m.d_wide.p, VI, e1);
-      linear(e, "f5.vocos_gemm", vb.pw2, false, m.d_wide.p, VI, G, other, VC, e2);
+      linear(e, "f5.vocos_gemm", vb.pw1, 0, m.d_c.p, VC, G, m.d_wide.p, VI, e1);
+      linear(e, "f5.vocos_gemm", vb.pw2, 0, m.d_wide.p, VI, G, other, VC, e2);
     }
     std::swap(cur, other);
   }
@@ -733,41 +793,41 @@ long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm
   Epi eh; eh.bias = m.head.bias.p;
   if (fast) {
     int l16 = 0;
-    const __nv_bfloat16* ah = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16);
-    if (!m.head_tc.ready) {                     // N = nfft + 2 is not a multiple of 4: zero weight rows up to Np (bias is padded too)
+    const __nv_bfloat16* ah = stage_bf16(e, m.s16a, m.d_c.p, VC, G, VC, &l16, f16);
+    if (!m.head_tc[f16].ready) {                     // N = nfft + 2 is not a multiple of 4: zero weight rows up to Np (bias is padded too)
       DevBuf<float> tmp((size_t)m.head.Np * m.head.K);
       B2_CUDA(cudaMemsetAsync(tmp.p, 0, (size_t)m.head.Np * m.head.K * sizeof(float), s));
       B2_CUDA(cudaMemcpyAsync(tmp.p, m.head.w_ref, (size_t)m.head.N * m.head.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      tc_weight_from_f32(m.head_tc, tmp.p, 1, 1, m.head.Np, m.head.K, s);
+      tc_weight_from_f32(m.head_tc[f16], tmp.p, 1, 1, m.head.Np, m.head.K, s, f16);
       B2_CUDA(cudaStreamSynchronize(s));
     }
     RowGemm p;
     p.x = ah; p.ldx = l16; p.Lin = G; p.Cin = m.head.K; p.N = m.head.Np; p.taps = 1; p.M = G; p.B = 1;
-    p.out = m.d_head.p; p.ldo = m.head.Np; p.bias = eh.bias;
+    p.out = m.d_head.p; p.ldo = m.head.Np; p.bias = eh.bias; p.f16 = f16;
     ProfScope ps(e.prof, "f5.vocos_gemm", s);
-    rowgemm_tc(p, m.head_tc, s);
+    rowgemm_tc(p, m.head_tc[f16], s);
   } else {
-    linear(e, "f5.vocos_gemm", m.head, false, m.d_c.p, VC, G, m.d_head.p, m.head.Np, eh);
+    linear(e, "f5.vocos_gemm", m.head, 0, m.d_c.p, VC, G, m.d_head.p, m.head.Np, eh);
   }
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); istft_input(m.d_head.p, m.d_in.p, G, m.bins, m.head.Np, s); }
   B2_CHECK(m.head.Np == m.istft.K, "head / istft padding mismatch");
   Epi ei;
   if (fast) {
-    if (!m.istft_tc.ready) {                    // W^T = basis^T: [nfft][2*bins (+ pad)]
+    if (!m.istft_tc[f16].ready) {                    // W^T = basis^T: [nfft][2*bins (+ pad)]
       DevBuf<float> tmp((size_t)m.nfft * m.istft.K);
       transpose_pad(m.istft_ref, tmp.p, 2 * m.bins, m.nfft, m.istft.K, s);
-      tc_weight_from_f32(m.istft_tc, tmp.p, 1, 1, m.nfft, m.istft.K, s);
+      tc_weight_from_f32(m.istft_tc[f16], tmp.p, 1, 1, m.nfft, m.istft.K, s, f16);
       B2_CUDA(cudaStreamSynchronize(s));
     }
     int l16 = 0;
     RowGemm p;
-    p.x = stage_bf16(e, m.s16a, m.d_in.p, m.istft.K, G, m.istft.K, &l16);
+    p.x = stage_bf16(e, m.s16a, m.d_in.p, m.istft.K, G, m.istft.K, &l16, f16);
     p.ldx = l16; p.Lin = G; p.Cin = m.istft.K; p.N = m.nfft; p.taps = 1; p.M = G; p.B = 1;
-    p.out = m.d_frames.p; p.ldo = m.nfft;
+    p.out = m.d_frames.p; p.ldo = m.nfft; p.f16 = f16;
     ProfScope ps(e.prof, "f5.istft_gemm", s);
-    rowgemm_tc(p, m.istft_tc, s);
+    rowgemm_tc(p, m.istft_tc[f16], s);
   } else {
-    linear(e, "f5.istft_gemm", m.istft, false, m.d_in.p, m.istft.K, G, m.d_frames.p, m.nfft, ei);
+    linear(e, "f5.istft_gemm", m.istft, 0, m.d_in.p, m.istft.K, G, m.d_frames.p, m.nfft, ei);
   }
   B2_CHECK((long)m.nfft + (long)m.hop * (G - 1) <= m.wsi_len, "window_sum_inv table too short");
   { ProfScope ps(e.prof, "f5.vocos_elementwise", s); istft_overlap_add(m.d_frames.p, m.wsi, G, m.nfft, m.hop, d_pcm, d_wave, s); }

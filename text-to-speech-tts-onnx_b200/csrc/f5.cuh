@@ -17,7 +17,7 @@ void f5_free(F5Model* m);
 // u / U: slot of this utterance in a batch of U utterances that share N (length-bucketed batching; default: one utterance).
 // fast: the text-embedding GEMMs run on tensor cores (bf16 operands); the per-graph session entry points keep fp32.
 void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_ids, int n_text, int N, int u = 0, int U = 1,
-                   bool fast = false);
+                   int fast = 0 /* engine.cuh Precision: 0 fp32 SIMT front end, 1 / 2 bf16 / fp16 tensor-core GEMMs */);
 int f5_ref_len(const Engine& e);
 int f5_seq_len(const Engine& e);
 int f5_cond_dim(const Engine& e);   // n_mels + text_dim (612)
@@ -43,6 +43,6 @@ void f5_steps(Engine& e, int first, int count, int precision);
 // Graph C (Export_F5.py:197-203): decode noise[ref_len:] -> pcm int16 [256 * (N - ref_len - 1)] (device);
 // d_mel (N x 100 fp32 device) defaults to the state's noise when null.
 // fast: Vocos / ISTFT GEMMs on tensor cores (bf16 operands, fp32 accumulate and residual stream).
-long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, bool fast = false);
+long f5_decode(Engine& e, const float* d_mel, int N, int ref_len, int16_t* d_pcm, float* d_wave, int fast = 0);
 
 }  // namespace b200tts

@@ -1,5 +1,7 @@
 #include "f5_kernels.cuh"
 
+#include <type_traits>
+
 #include <cuda_fp16.h>
 
 namespace b200tts {
@@ -58,6 +60,12 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
     for (int k = 0; k < 4; ++k) o[k] = MODE == 0 ? o[k] * (1.0f + av[k]) + bv[k] : o[k] * av[k] + bv[k];
     if constexpr (sizeof(OutT) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long)row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
+    } else if constexpr (std::is_same<OutT, __half>::value) {
+      __half2 p0 = __floats2half2_rn(o[0], o[1]), p1 = __floats2half2_rn(o[2], o[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (long)row * D + c) = pk;
     } else {
       __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
       uint2 pk;
@@ -294,7 +302,8 @@ inline dim3 g1(long n, int bs = 256) { return dim3(ceil_div(n, bs)); }
 #define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
 
 void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s) {
-  if (out_bf16) launch_rownorm<0, __nv_bfloat16>(x, scale, shift, (__nv_bfloat16*)out, R, D, 1e-6f, s);
+  if (out_bf16 == 2) launch_rownorm<0, __half>(x, scale, shift, (__half*)out, R, D, 1e-6f, s);
+  else if (out_bf16) launch_rownorm<0, __nv_bfloat16>(x, scale, shift, (__nv_bfloat16*)out, R, D, 1e-6f, s);
   else launch_rownorm<0, float>(x, scale, shift, (float*)out, R, D, 1e-6f, s);
   LAUNCHED();
 }

@@ -8,7 +8,7 @@
 namespace b200tts {
 
 // out = LayerNorm(x; no affine, eps 1e-6) * (1 + scale) + shift   (F5 modules.py:301-305,321-325,609)
-// x [R][D] fp32; scale, shift [D]; out fp32 or bf16 with row stride D.
+// x [R][D] fp32; scale, shift [D]; out fp32 (out_bf16 = 0), bf16 (1) or fp16 (2) with row stride D.
 void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s);
 // nn.LayerNorm(D, eps) with affine (text ConvNeXtV2 block, modules.py:248)
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s);

@@ -37,7 +37,8 @@ struct RowGemm {
   int ldo = 0;
   long o_shift = 0;
   long o_limit = 0;       // 0 -> M*ldo
-  int out_bf16 = 0;
+  int out_bf16 = 0;       // type code of `out`: 0 = fp32, 1 = bf16, 2 = fp16
+  int f16 = 0;            // tensor-core path: operand (A, W, out2, vt_out) 16-bit type: 0 = bf16, 1 = fp16
   __nv_bfloat16* out2 = nullptr;   // tensor-core path only: optional second, bf16, copy of the output (same indexing)
   // epilogue: v = acc + bias[n]; v = act(v); v *= gate[n]; v += res[idx]; if (accumulate) v += out[idx]; v *= scale
   const float* bias = nullptr;    // [groups*N]

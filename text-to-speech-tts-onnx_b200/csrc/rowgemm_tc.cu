@@ -32,270 +32,11 @@
 #include <mutex>
 #include <string>
 
-#include "tc_ptx.cuh"
+#include "rowgemm_tc_dev.cuh"
 
 namespace b200tts {
 
 namespace {
-
-constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
-constexpr int NTHREADS3 = 352;         // warps 0..7 epilogue, warp 8 A producer, warp 9 MMA issuer, warp 10 B producer
-constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_TMA_B = 10;   // the SMSP arbiter favours the HIGHEST warp id: the two single-thread roles that
-                                            // feed the tensor pipe must not lose issue slots to the epilogue warps they share
-                                            // an SMSP with (A/B on one box: +13..25 % on every shape)
-constexpr int A_BOX_ROWS = 64;
-constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
-constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;      // one 32x32 fp32 block per epilogue warp
-constexpr int EPI_BYTES = 8 * EPI_STAGE_BYTES;
-
-using namespace tc;
-
-enum EpiKind : int { EPI_STD = 0, EPI_ROPE = 1 };
-
-struct TcArgs {
-  int Cin, N, taps, dil, center, groups, M;
-  int BN, kchunks;              // kchunks = ceil(Cin / 64)
-  void* out; long o_bstride; int ldo; long o_shift; long o_limit; int out_bf16;
-  const float* bias; const float* gate; const float* res; int accumulate; float scale;
-  const __half2* rope_cs; int rope_cols, rope_rows;
-  __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
-  __nv_bfloat16* out2;          // optional bf16 copy of the output (same indexing)
-};
-
-struct Tc3Sched {
-  int bm;                               // output rows per tile = 128 * halves
-  int halves;                           // 128-row accumulators per tile (1, 2 or 4): independent MMA chains
-  int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
-  int a_rows;                           // rows per A stage (multiple of 64) = round_up(bm + (taps-1)*dil, 64)
-  int a_box;                            // rows per A TMA box: the largest of 256 / 128 / 64 that divides a_rows
-  int nA, nB;                           // ring depths (bres: nB = kchunks*taps resident B tiles)
-  int bres;                             // 1: the whole weight tensor stays in shared memory for the life of the CTA
-  int half_stride, nacc;                // TMEM columns per 128-row accumulator; accumulator stages (1 or 2)
-};
-
-__device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(x, y), p1 = __floats2bfloat162_rn(z, w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&p0);
-  pk.y = *reinterpret_cast<uint32_t*>(&p1);
-  return pk;
-}
-
-// Explicit shared-space accesses for the epilogue's staging block. Through a generic pointer the compiler emitted LD.E / ST.E,
-// which it may not move across the global stores of the previous row (possible aliasing): the eight staging loads of a block
-// were issued one per row, each exposed (ncu r01u: the thin convolutions and the batched DiT GEMMs are epilogue-bound).
-__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Activations of the bf16 engine (operands are already rounded to 8 mantissa bits, so the 2^-11 MUFU error is noise).
-template <int ACT>
-__device__ __forceinline__ float act_fast(float v) {
-  if (ACT == ACT_GELU_TANH) {
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    const float u = k0 * (v + k1 * v * v * v);
-    return 0.5f * v * (1.0f + tanh_fast(u));
-  } else if (ACT == ACT_MISH) {            // x * tanh(softplus(x)), softplus threshold 20 (F5 modules.py:172)
-    const float sp = v > 20.0f ? v : __logf(1.0f + __expf(v));
-    return v * tanh_fast(sp);
-  } else if (ACT == ACT_GELU_ERF) {
-    return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
-  }
-  return v;
-}
-
-// One epilogue warp, one accumulator (128 TMEM lanes x BN columns): this warp owns lanes [32q, 32q+32) = tile rows
-// row0 .. row0+31 and walks the 32-column blocks cb = cb_first, cb_first + cb_step, ... < BN.
-//   phase 1  tcgen05.ld 32 columns of the lane's row -> 8 x STS.128 into the warp's swizzled 4 KB staging block
-//   phase 2  lane = (sub = lane/8, c4 = lane%8): rows i*4 + sub (i < 8), columns c4*4 .. c4*4+3 : LDS.128, math, global I/O
-struct EpiPos {
-  int sub, c4, t_row0, n0;
-  long obase, gshift;
-};
-
-__device__ __forceinline__ long epi_flat(const TcArgs& a, const EpiPos& p, int i, int n) {
-  return (long)(p.t_row0 + i * 4 + p.sub) * a.ldo + p.gshift + n;
-}
-__device__ __forceinline__ bool epi_ok(const TcArgs& a, const EpiPos& p, int i, int n, long flat) {
-  return (p.t_row0 + i * 4 + p.sub) < a.M && n < a.N && flat >= 0 && flat < a.o_limit;
-}
-// residual operand of block cb, in the phase-2 layout (issued one block ahead: the first before the accumulator is ready,
-// the next ones at the end of the previous block's phase 2)
-__device__ __forceinline__ void epi_load_res(const TcArgs& a, const EpiPos& p, int cb, float4 (&res)[8]) {
-  const int n = p.n0 + cb + p.c4 * 4;
-  const bool in = cb < a.BN;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long flat = epi_flat(a, p, i, n);
-    res[i] = (in && epi_ok(a, p, i, n, flat)) ? *reinterpret_cast<const float4*>(a.res + p.obase + flat) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-template <int KIND, int ACT>
-__device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_t taddr, uint32_t taddr_hstep, int n_mine, float* stg,
-                                              int lane, int g, int cb_first, int cb_step, float4 (&res)[8]) {
-  // n_mine 128-row halves belong to this warp (rows +256 and TMEM columns +taddr_hstep apart); their 32-column blocks form
-  // ONE sequence for the residual look-ahead, so the first block of the second half is prefetched like any other.
-  const int sub = p.sub, c4 = p.c4, n0 = p.n0;
-  const bool has_res = KIND == EPI_STD && a.res != nullptr;
-#pragma unroll 1
-  for (int hh = 0; hh < n_mine; ++hh, p.t_row0 += 256, taddr += taddr_hstep) {
-  if (p.t_row0 >= a.M) break;                                // warp-uniform: no valid rows in this 32-row block
-#pragma unroll 1
-  for (int cb = cb_first; cb < a.BN; cb += cb_step) {
-    if (n0 + cb >= a.N) break;
-    uint32_t r[32];
-    tmem_ld32(taddr + (uint32_t)cb, r);
-    // this lane's four phase-2 columns: bias / gate fetched under the TMEM load (they are needed first thing in phase 2)
-    const int n = n0 + cb + c4 * 4;
-    const bool n_ok = n < a.N;
-    const float4 bias = (a.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(a.bias + (long)g * a.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 gate = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (KIND == EPI_STD && a.gate && n_ok) gate = __ldg(reinterpret_cast<const float4*>(a.gate + (long)g * a.N + n));
-    // RoPE block: the (cos, sin) pairs of this lane's 8 phase-2 rows x 4 columns, one 16-byte load each, issued before the
-    // TMEM wait (they were 16 dependent L2 round trips inside phase 2: +12 us on the q|k|v GEMM, ncu r01d)
-    uint4 cs[8];
-    if (KIND == EPI_ROPE && n0 + cb < a.rope_cols) {
-      const int d = (n0 + cb + c4 * 4) & 63;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int t = p.t_row0 + i * 4 + sub;
-        cs[i] = t < a.M ? __ldg(reinterpret_cast<const uint4*>(a.rope_cs + (long)(t % a.rope_rows) * 64 + d)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    tmem_ld_wait();
-
-    if (KIND == EPI_ROPE && a.vt_out != nullptr && n0 + cb >= a.vt_col0) {
-      // V columns: written transposed, vt[(batch*heads + h)*64 + d][t]; in the row-per-lane layout consecutive lanes are
-      // consecutive t, so each store instruction writes one 64-byte run.
-      const int t = p.t_row0 + lane;
-      if (t < a.M) {
-        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int n = n0 + cb + k * 4;
-          if (n < a.N) {
-            const float4 bi = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const int cv = n - a.vt_col0;
-            __nv_bfloat16* o = a.vt_out + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
-            o[0] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 0]) + bi.x);
-            o[(long)a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 1]) + bi.y);
-            o[2L * a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 2]) + bi.z);
-            o[3L * a.vt_ld] = __float2bfloat16_rn(__uint_as_float(r[k * 4 + 3]) + bi.w);
-          }
-        }
-      }
-      continue;
-    }
-
-    // phase 1: row `lane`, 16-byte chunk k goes to chunk slot k ^ (lane & 7) (conflict-free per quarter warp)
-    const uint32_t stg_s = smem_u32(stg);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      sts128(stg_s + (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2)) * 4u, r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
-    __syncwarp();
-
-    // the next block's residual: issued here, once r[] is dead, so it has the whole of phase 2 plus the next block's TMEM
-    // load and transpose to arrive (issued after phase 2 it was exposed: the thin BigVGAN conv2 ran at half speed)
-    float4 res_n[8];
-    if (has_res) {
-      const bool last_cb = cb + cb_step >= a.BN || n0 + cb + cb_step >= a.N;
-      EpiPos pn = p;
-      if (last_cb) pn.t_row0 += 256;                         // (rows beyond M / a half that is not ours load zeros)
-      epi_load_res(a, pn, (last_cb && hh + 1 < n_mine) ? cb_first : cb + cb_step, res_n);
-    }
-
-    // phase 2
-    const bool rope = KIND == EPI_ROPE && n < a.rope_cols;
-    float4 accs[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {                 // all eight staging rows of this lane in flight at once
-      const int row = i * 4 + sub;
-      accs[i] = lds128(stg_s + (uint32_t)(row * 32 + ((c4 ^ (row & 7)) << 2)) * 4u);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = i * 4 + sub;
-      const long flat = epi_flat(a, p, i, n);
-      const bool ok = epi_ok(a, p, i, n, flat);
-      const float4 acc = accs[i];
-      float v0 = acc.x + bias.x, v1 = acc.y + bias.y, v2 = acc.z + bias.z, v3 = acc.w + bias.w;
-      if (KIND == EPI_ROPE) {
-        if (rope) {                             // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
-          const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].x));
-          const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].y));
-          const float2 cs2 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].z));
-          const float2 cs3 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].w));
-          const float x0 = v0, x1 = v1, x2 = v2, x3 = v3;
-          v0 = x0 * cs0.x - x1 * cs0.y; v1 = x1 * cs1.x + x0 * cs1.y;
-          v2 = x2 * cs2.x - x3 * cs2.y; v3 = x3 * cs3.x + x2 * cs3.y;
-        }
-      } else {
-        if (ACT != ACT_NONE) { v0 = act_fast<ACT>(v0); v1 = act_fast<ACT>(v1); v2 = act_fast<ACT>(v2); v3 = act_fast<ACT>(v3); }
-        v0 *= gate.x; v1 *= gate.y; v2 *= gate.z; v3 *= gate.w;
-        if (has_res) { v0 += res[i].x; v1 += res[i].y; v2 += res[i].z; v3 += res[i].w; }
-      }
-      if (ok) {
-        if (a.out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + p.obase + flat;
-          if (KIND == EPI_STD && a.accumulate) {
-            const uint2 pv = *reinterpret_cast<const uint2*>(o);
-            v0 += __uint_as_float(pv.x << 16); v1 += __uint_as_float(pv.x & 0xFFFF0000u);
-            v2 += __uint_as_float(pv.y << 16); v3 += __uint_as_float(pv.y & 0xFFFF0000u);
-          }
-          *reinterpret_cast<uint2*>(o) = pack_bf16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
-        } else {
-          float* o = reinterpret_cast<float*>(a.out) + p.obase + flat;
-          if (KIND == EPI_STD && a.accumulate) {
-            const float4 pv = *reinterpret_cast<const float4*>(o);
-            v0 += pv.x; v1 += pv.y; v2 += pv.z; v3 += pv.w;
-          }
-          *reinterpret_cast<float4*>(o) = make_float4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
-        }
-        if (KIND == EPI_STD && a.out2 != nullptr)      // second copy of the result in bf16 (the next GEMM's A operand)
-          *reinterpret_cast<uint2*>(a.out2 + p.obase + flat) = pack_bf16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
-      }
-    }
-    if (has_res) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = res_n[i];
-    }
-    __syncwarp();                                // the staging block is rewritten by the next iteration's phase 1
-  }
-  }
-}
-
-// The KS x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost. KS = 4 for a full chunk,
-// 2 / 3 for the ragged last chunk of the thin BigVGAN stages (C = 24, 48, 96), where the generic loop was the critical path.
-template <int NH, int KS>
-__device__ __forceinline__ void issue_tap(uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
-#pragma unroll
-  for (int k = 0; k < KS; ++k)
-#pragma unroll
-    for (int h = 0; h < NH; ++h)
-      umma_bf16_lohi(d + (uint32_t)h * hstep, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc, k == 0 ? accum : 1u);
-}
-template <int NH>
-__device__ __forceinline__ bool issue_tap_ks(int ksteps, uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                             uint32_t accum) {
-  if (ksteps == 4) issue_tap<NH, 4>(d, hstep, a_lo, b_lo, idesc, accum);
-  else if (ksteps == 2) issue_tap<NH, 2>(d, hstep, a_lo, b_lo, idesc, accum);
-  else if (ksteps == 3) issue_tap<NH, 3>(d, hstep, a_lo, b_lo, idesc, accum);
-  else return false;
-  return true;
-}
 
 // A tap's A tile starts (tap*dil) rows = (tap*dil)*128 bytes into the halo tile, i.e. generally NOT on a 1024-byte
 // swizzle-atom boundary. Measured on B200 (tools/debug_conv.py): the tensor core applies the 128B-swizzle XOR to the
@@ -415,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) rowgemm_tc3_kernel(const __grid_
     }
   } else if (warp == WARP_MMA) {
     // ===== MMA issuer: the whole warp walks the (warp-uniform) loops, one elected lane issues =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = idesc_f16kind(128, a.BN, a.f16);
     const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a)), b_lo0 = desc_lo_sw128(smem_u32(smem_b));
     const uint32_t a_stage_lo = (uint32_t)a_stage_bytes >> 4, b_stage_lo = (uint32_t)b_stage_bytes >> 4;
     const uint32_t tap_lo = (uint32_t)a.dil * 8u;                   // dil rows x 128 B, in 16-byte units
@@ -626,7 +367,7 @@ rowgemm_tc2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   } else if (warp == WARP_MMA) {
     if (leader) {
       // ===== MMA issuer (leader CTA only): M = 256 across the pair =====
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc = idesc_f16kind(256, a.BN, a.f16);
       const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a)), b_lo0 = desc_lo_sw128(smem_u32(smem_b));
       const uint32_t a_stage_lo = (uint32_t)a_stage_bytes >> 4, b_stage_lo = (uint32_t)b_stage_bytes >> 4;
       const uint32_t tap_lo = (uint32_t)a.dil * 8u;
@@ -750,60 +491,60 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
 
 namespace {
 
-__global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
+__global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n, int f16) {
   pdl_trigger();
   pdl_wait();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(in + i));
-    *reinterpret_cast<uint2*>(out + i) = pack_bf16x4(v.x, v.y, v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = pack16x4(v.x, v.y, v.z, v.w, f16);
   } else {
-    for (long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+    for (long k = i; k < n; ++k) reinterpret_cast<uint16_t*>(out)[k] = pack16(in[k], f16);
   }
 }
 
-__global__ void uncast_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long n) {
+__global__ void uncast_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long n, int f16) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i < n) out[i] = f16 ? __half2float(reinterpret_cast<const __half*>(in)[i]) : __bfloat162float(in[i]);
 }
 
-__global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int C, int ldo) {
+__global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int C, int ldo, int f16) {
   pdl_trigger();
   pdl_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ldo) return;
   const long r = i / ldo;
   const int c = (int)(i - r * ldo);
-  out[i] = c < C ? __float2bfloat16_rn(in[r * C + c]) : __float2bfloat16_rn(0.f);
+  reinterpret_cast<uint16_t*>(out)[i] = pack16(c < C ? in[r * C + c] : 0.f, f16);
 }
 
 }  // namespace
 
-void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s) {
+void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s, int f16) {
   if (n <= 0) return;
   B2_CHECK(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, "cast alignment");
-  launch_pdl(cast_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, s, in, out, n);
+  launch_pdl(cast_kernel, dim3(ceil_div(ceil_div(n, 4), 256)), dim3(256), 0, s, in, out, n, f16);
   B2_LAUNCH_CHECK(); count_launch();
 }
 
-void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s) {
+void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s, int f16) {
   if (n <= 0) return;
-  uncast_kernel<<<ceil_div(n, 256), 256, 0, s>>>(in, out, n);
+  uncast_kernel<<<ceil_div(n, 256), 256, 0, s>>>(in, out, n, f16);
   B2_LAUNCH_CHECK(); count_launch();
 }
 
-void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s) {
+void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s, int f16) {
   if (rows <= 0) return;
-  launch_pdl(cast_pad_kernel, dim3(ceil_div(rows * ldo, 256)), dim3(256), 0, s, in, out, rows, C, ldo);
+  launch_pdl(cast_pad_kernel, dim3(ceil_div(rows * ldo, 256)), dim3(256), 0, s, in, out, rows, C, ldo, f16);
   B2_LAUNCH_CHECK(); count_launch();
 }
 
-void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps, int N, int Cin, cudaStream_t s) {
-  tw.Cin = Cin; tw.N = N; tw.taps = taps; tw.groups = groups;
+void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps, int N, int Cin, cudaStream_t s, int f16) {
+  tw.Cin = Cin; tw.N = N; tw.taps = taps; tw.groups = groups; tw.f16 = f16;
   tw.ldc = (int)round_up(Cin, 8);
   const long rows = (long)groups * taps * N;
   tw.w.alloc((size_t)rows * tw.ldc);
-  cast_pad_f32_to_bf16(w_gjnc, tw.w.p, rows, Cin, tw.ldc, s);
+  cast_pad_f32_to_bf16(w_gjnc, tw.w.p, rows, Cin, tw.ldc, s, f16);
   tw.ready = true;
 }
 
@@ -887,6 +628,7 @@ TcArgs make_args(const RowGemm& p, int BN) {
   a.rope_cs = p.rope_cs; a.rope_cols = p.rope_cols; a.rope_rows = p.rope_rows > 0 ? p.rope_rows : 1;
   a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
   a.out2 = p.out2;
+  a.f16 = p.f16;
   return a;
 }
 
@@ -991,6 +733,7 @@ bool try_launch_2sm(const RowGemm& p, const TcWeight& w, cudaStream_t stream, bo
 void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream) {
   B2_CHECK(w.ready, "rowgemm_tc: tensor-core weights not prepared");
   B2_CHECK(p.Cin == w.Cin && p.N == w.N && p.taps == w.taps && p.groups == w.groups, "rowgemm_tc: weight/problem mismatch");
+  B2_CHECK((p.f16 != 0) == (w.f16 != 0), "rowgemm_tc: operand dtype differs from the prepared weight's (bf16 vs fp16)");
   B2_CHECK(p.N % 4 == 0 && p.ldo % 4 == 0 && p.o_shift % 4 == 0, "rowgemm_tc: output alignment");
   B2_CHECK(p.ldx % 8 == 0 && p.x_bstride % 8 == 0, "rowgemm_tc: A rows must be 16-byte aligned");
   B2_CHECK(p.groups == 1 || p.Cin % BK == 0, "rowgemm_tc: grouped problems need Cin % 64 == 0");

@@ -13,11 +13,12 @@ namespace b200tts {
 struct TcWeight {
   DevBuf<__nv_bfloat16> w;
   int Cin = 0, ldc = 0, N = 0, taps = 0, groups = 1;
+  int f16 = 0;            // 16-bit type of the stored weights: 0 = bf16, 1 = fp16
   bool ready = false;
 };
 
 // Build from an fp32 device tensor already laid out as [groups*taps][N][Cin] (c contiguous).
-void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps, int N, int Cin, cudaStream_t s);
+void tc_weight_from_f32(TcWeight& tw, const float* w_gjnc, int groups, int taps, int N, int Cin, cudaStream_t s, int f16 = 0);
 
 // A operand: bf16, rows of p.ldx elements (ldx % 8 == 0). Output fp32 or bf16 (p.out_bf16).
 void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream);
@@ -26,9 +27,10 @@ void rowgemm_tc(const RowGemm& p, const TcWeight& w, cudaStream_t stream);
 void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2,
                    uint32_t box1);
 
-void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s);
-void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s);
+// f16 != 0: the 16-bit side is IEEE fp16 instead of bf16 (same storage type)
+void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s, int f16 = 0);
+void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s, int f16 = 0);
 // (rows, C) fp32 -> (rows, ldo) bf16 with zero-filled padding columns
-void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s);
+void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s, int f16 = 0);
 
 }  // namespace b200tts

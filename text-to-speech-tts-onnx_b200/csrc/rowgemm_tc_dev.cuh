@@ -1,0 +1,309 @@
+// Device-side pieces shared by the tcgen05 kernels (rowgemm_tc.cu, dit_chain.cu): tile constants, the argument block of
+// one GEMM's epilogue, the smem-transposed coalesced epilogue, and the fully unrolled MMA issue helpers. Include inside
+// namespace b200tts, within an anonymous namespace of the including translation unit.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200tts {
+namespace {
+
+constexpr int BK = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS3 = 352;         // warps 0..7 epilogue, warp 8 A producer, warp 9 MMA issuer, warp 10 B producer
+constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_TMA_B = 10;   // the SMSP arbiter favours the HIGHEST warp id: the two single-thread roles that
+                                            // feed the tensor pipe must not lose issue slots to the epilogue warps they share
+                                            // an SMSP with (A/B on one box: +13..25 % on every shape)
+constexpr int A_BOX_ROWS = 64;
+constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;      // one 32x32 fp32 block per epilogue warp
+constexpr int EPI_BYTES = 8 * EPI_STAGE_BYTES;
+
+using namespace tc;
+
+enum EpiKind : int { EPI_STD = 0, EPI_ROPE = 1 };
+
+// tcgen05 instruction descriptor of kind::f16: fp32 accumulator, K-major A and B of the 16-bit type (format code 1 = bf16,
+// 0 = fp16), N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t idesc_f16kind(int M, int N, int f16) {
+  const uint32_t fmt = f16 ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+  int Cin, N, taps, dil, center, groups, M;
+  int BN, kchunks;              // kchunks = ceil(Cin / 64)
+  void* out; long o_bstride; int ldo; long o_shift; long o_limit; int out_bf16;
+  const float* bias; const float* gate; const float* res; int accumulate; float scale;
+  const __half2* rope_cs; int rope_cols, rope_rows;
+  __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
+  __nv_bfloat16* out2;          // optional 16-bit copy of the output (same indexing, operand dtype)
+  int f16;                      // 16-bit type of the A / B operands, out2 and vt_out: 0 = bf16, 1 = fp16 (IEEE half);
+                                // out_bf16 is the type code of `out`: 0 = fp32, 1 = bf16, 2 = fp16
+};
+
+struct Tc3Sched {
+  int bm;                               // output rows per tile = 128 * halves
+  int halves;                           // 128-row accumulators per tile (1, 2 or 4): independent MMA chains
+  int m_tiles, n_tiles, num_tiles;      // per (batch, group): m_tiles x n_tiles ; num_tiles = all
+  int a_rows;                           // rows per A stage (multiple of 64) = round_up(bm + (taps-1)*dil, 64)
+  int a_box;                            // rows per A TMA box: the largest of 256 / 128 / 64 that divides a_rows
+  int nA, nB;                           // ring depths (bres: nB = kchunks*taps resident B tiles)
+  int bres;                             // 1: the whole weight tensor stays in shared memory for the life of the CTA
+  int half_stride, nacc;                // TMEM columns per 128-row accumulator; accumulator stages (1 or 2)
+};
+
+__device__ __forceinline__ uint2 pack_bf16x4(float x, float y, float z, float w) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(x, y), p1 = __floats2bfloat162_rn(z, w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  return pk;
+}
+
+// 16-bit packing by type code (warp-uniform branch): half != 0 -> IEEE fp16, else bf16
+__device__ __forceinline__ uint32_t pack16x2(float x, float y, int half) {
+  if (half) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 p = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ uint2 pack16x4(float x, float y, float z, float w, int half) {
+  return make_uint2(pack16x2(x, y, half), pack16x2(z, w, half));
+}
+__device__ __forceinline__ uint16_t pack16(float x, int half) {
+  if (half) return __half_as_ushort(__float2half_rn(x));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t v, int half) {
+  if (half) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+
+// Explicit shared-space accesses for the epilogue's staging block. Through a generic pointer the compiler emitted LD.E / ST.E,
+// which it may not move across the global stores of the previous row (possible aliasing): the eight staging loads of a block
+// were issued one per row, each exposed (ncu r01u: the thin convolutions and the batched DiT GEMMs are epilogue-bound).
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Activations of the bf16 engine (operands are already rounded to 8 mantissa bits, so the 2^-11 MUFU error is noise).
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+  if (ACT == ACT_GELU_TANH) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float u = k0 * (v + k1 * v * v * v);
+    return 0.5f * v * (1.0f + tanh_fast(u));
+  } else if (ACT == ACT_MISH) {            // x * tanh(softplus(x)), softplus threshold 20 (F5 modules.py:172)
+    const float sp = v > 20.0f ? v : __logf(1.0f + __expf(v));
+    return v * tanh_fast(sp);
+  } else if (ACT == ACT_GELU_ERF) {
+    return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
+  }
+  return v;
+}
+
+// One epilogue warp, one accumulator (128 TMEM lanes x BN columns): this warp owns lanes [32q, 32q+32) = tile rows
+// row0 .. row0+31 and walks the 32-column blocks cb = cb_first, cb_first + cb_step, ... < BN.
+//   phase 1  tcgen05.ld 32 columns of the lane's row -> 8 x STS.128 into the warp's swizzled 4 KB staging block
+//   phase 2  lane = (sub = lane/8, c4 = lane%8): rows i*4 + sub (i < 8), columns c4*4 .. c4*4+3 : LDS.128, math, global I/O
+struct EpiPos {
+  int sub, c4, t_row0, n0;
+  long obase, gshift;
+};
+
+__device__ __forceinline__ long epi_flat(const TcArgs& a, const EpiPos& p, int i, int n) {
+  return (long)(p.t_row0 + i * 4 + p.sub) * a.ldo + p.gshift + n;
+}
+__device__ __forceinline__ bool epi_ok(const TcArgs& a, const EpiPos& p, int i, int n, long flat) {
+  return (p.t_row0 + i * 4 + p.sub) < a.M && n < a.N && flat >= 0 && flat < a.o_limit;
+}
+// residual operand of block cb, in the phase-2 layout (issued one block ahead: the first before the accumulator is ready,
+// the next ones at the end of the previous block's phase 2)
+__device__ __forceinline__ void epi_load_res(const TcArgs& a, const EpiPos& p, int cb, float4 (&res)[8]) {
+  const int n = p.n0 + cb + p.c4 * 4;
+  const bool in = cb < a.BN;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long flat = epi_flat(a, p, i, n);
+    res[i] = (in && epi_ok(a, p, i, n, flat)) ? *reinterpret_cast<const float4*>(a.res + p.obase + flat) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// STATS: psum[i] / psq[i] accumulate the sum and the sum of squares of the values this lane writes for its phase-2 row i
+// (row i*4 + sub of the warp's 32): the LayerNorm statistics of the fused DiT chain (dit_chain.cu).
+template <int KIND, int ACT, bool STATS = false>
+__device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_t taddr, uint32_t taddr_hstep, int n_mine, float* stg,
+                                              int lane, int g, int cb_first, int cb_step, float4 (&res)[8],
+                                              float* psum = nullptr, float* psq = nullptr) {
+  // n_mine 128-row halves belong to this warp (rows +256 and TMEM columns +taddr_hstep apart); their 32-column blocks form
+  // ONE sequence for the residual look-ahead, so the first block of the second half is prefetched like any other.
+  const int sub = p.sub, c4 = p.c4, n0 = p.n0;
+  const bool has_res = KIND == EPI_STD && a.res != nullptr;
+#pragma unroll 1
+  for (int hh = 0; hh < n_mine; ++hh, p.t_row0 += 256, taddr += taddr_hstep) {
+  if (p.t_row0 >= a.M) break;                                // warp-uniform: no valid rows in this 32-row block
+#pragma unroll 1
+  for (int cb = cb_first; cb < a.BN; cb += cb_step) {
+    if (n0 + cb >= a.N) break;
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)cb, r);
+    // this lane's four phase-2 columns: bias / gate fetched under the TMEM load (they are needed first thing in phase 2)
+    const int n = n0 + cb + c4 * 4;
+    const bool n_ok = n < a.N;
+    const float4 bias = (a.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(a.bias + (long)g * a.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gate = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (KIND == EPI_STD && a.gate && n_ok) gate = __ldg(reinterpret_cast<const float4*>(a.gate + (long)g * a.N + n));
+    // RoPE block: the (cos, sin) pairs of this lane's 8 phase-2 rows x 4 columns, one 16-byte load each, issued before the
+    // TMEM wait (they were 16 dependent L2 round trips inside phase 2: +12 us on the q|k|v GEMM, ncu r01d)
+    uint4 cs[8];
+    if (KIND == EPI_ROPE && n0 + cb < a.rope_cols) {
+      const int d = (n0 + cb + c4 * 4) & 63;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = p.t_row0 + i * 4 + sub;
+        cs[i] = t < a.M ? __ldg(reinterpret_cast<const uint4*>(a.rope_cs + (long)(t % a.rope_rows) * 64 + d)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    tmem_ld_wait();
+
+    if (KIND == EPI_ROPE && a.vt_out != nullptr && n0 + cb >= a.vt_col0) {
+      // V columns: written transposed, vt[(batch*heads + h)*64 + d][t]; in the row-per-lane layout consecutive lanes are
+      // consecutive t, so each store instruction writes one 64-byte run.
+      const int t = p.t_row0 + lane;
+      if (t < a.M) {
+        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int n = n0 + cb + k * 4;
+          if (n < a.N) {
+            const float4 bi = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cv = n - a.vt_col0;
+            __nv_bfloat16* o = a.vt_out + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
+            uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+            o16[0] = pack16(__uint_as_float(r[k * 4 + 0]) + bi.x, a.f16);
+            o16[(long)a.vt_ld] = pack16(__uint_as_float(r[k * 4 + 1]) + bi.y, a.f16);
+            o16[2L * a.vt_ld] = pack16(__uint_as_float(r[k * 4 + 2]) + bi.z, a.f16);
+            o16[3L * a.vt_ld] = pack16(__uint_as_float(r[k * 4 + 3]) + bi.w, a.f16);
+          }
+        }
+      }
+      continue;
+    }
+
+    // phase 1: row `lane`, 16-byte chunk k goes to chunk slot k ^ (lane & 7) (conflict-free per quarter warp)
+    const uint32_t stg_s = smem_u32(stg);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      sts128(stg_s + (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2)) * 4u, r[k * 4], r[k * 4 + 1], r[k * 4 + 2], r[k * 4 + 3]);
+    __syncwarp();
+
+    // the next block's residual: issued here, once r[] is dead, so it has the whole of phase 2 plus the next block's TMEM
+    // load and transpose to arrive (issued after phase 2 it was exposed: the thin BigVGAN conv2 ran at half speed)
+    float4 res_n[8];
+    if (has_res) {
+      const bool last_cb = cb + cb_step >= a.BN || n0 + cb + cb_step >= a.N;
+      EpiPos pn = p;
+      if (last_cb) pn.t_row0 += 256;                         // (rows beyond M / a half that is not ours load zeros)
+      epi_load_res(a, pn, (last_cb && hh + 1 < n_mine) ? cb_first : cb + cb_step, res_n);
+    }
+
+    // phase 2
+    const bool rope = KIND == EPI_ROPE && n < a.rope_cols;
+    float4 accs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                 // all eight staging rows of this lane in flight at once
+      const int row = i * 4 + sub;
+      accs[i] = lds128(stg_s + (uint32_t)(row * 32 + ((c4 ^ (row & 7)) << 2)) * 4u);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + sub;
+      const long flat = epi_flat(a, p, i, n);
+      const bool ok = epi_ok(a, p, i, n, flat);
+      const float4 acc = accs[i];
+      float v0 = acc.x + bias.x, v1 = acc.y + bias.y, v2 = acc.z + bias.z, v3 = acc.w + bias.w;
+      if (KIND == EPI_ROPE) {
+        if (rope) {                             // (x0, x1) -> x*cos + (-x1, x0)*sin, tables repeat per 64-wide head
+          const float2 cs0 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].x));
+          const float2 cs1 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].y));
+          const float2 cs2 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].z));
+          const float2 cs3 = __half22float2(*reinterpret_cast<const __half2*>(&cs[i].w));
+          const float x0 = v0, x1 = v1, x2 = v2, x3 = v3;
+          v0 = x0 * cs0.x - x1 * cs0.y; v1 = x1 * cs1.x + x0 * cs1.y;
+          v2 = x2 * cs2.x - x3 * cs2.y; v3 = x3 * cs3.x + x2 * cs3.y;
+        }
+      } else {
+        if (ACT != ACT_NONE) { v0 = act_fast<ACT>(v0); v1 = act_fast<ACT>(v1); v2 = act_fast<ACT>(v2); v3 = act_fast<ACT>(v3); }
+        v0 *= gate.x; v1 *= gate.y; v2 *= gate.z; v3 *= gate.w;
+        if (has_res) { v0 += res[i].x; v1 += res[i].y; v2 += res[i].z; v3 += res[i].w; }
+      }
+      if (STATS && ok) {
+        const float w0 = v0 * a.scale, w1 = v1 * a.scale, w2 = v2 * a.scale, w3 = v3 * a.scale;
+        psum[i] += (w0 + w1) + (w2 + w3);
+        psq[i] += (w0 * w0 + w1 * w1) + (w2 * w2 + w3 * w3);
+      }
+      if (ok) {
+        if (a.out_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + p.obase + flat;
+          if (KIND == EPI_STD && a.accumulate) {
+            const uint2 pv = *reinterpret_cast<const uint2*>(o);
+            const float2 p01 = unpack16x2(pv.x, a.out_bf16 == 2), p23 = unpack16x2(pv.y, a.out_bf16 == 2);
+            v0 += p01.x; v1 += p01.y; v2 += p23.x; v3 += p23.y;
+          }
+          *reinterpret_cast<uint2*>(o) = pack16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale, a.out_bf16 == 2);
+        } else {
+          float* o = reinterpret_cast<float*>(a.out) + p.obase + flat;
+          if (KIND == EPI_STD && a.accumulate) {
+            const float4 pv = *reinterpret_cast<const float4*>(o);
+            v0 += pv.x; v1 += pv.y; v2 += pv.z; v3 += pv.w;
+          }
+          *reinterpret_cast<float4*>(o) = make_float4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale);
+        }
+        if (KIND == EPI_STD && a.out2 != nullptr)      // second copy of the result in bf16 (the next GEMM's A operand)
+          *reinterpret_cast<uint2*>(a.out2 + p.obase + flat) = pack16x4(v0 * a.scale, v1 * a.scale, v2 * a.scale, v3 * a.scale, a.f16);
+      }
+    }
+    if (has_res) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = res_n[i];
+    }
+    __syncwarp();                                // the staging block is rewritten by the next iteration's phase 1
+  }
+  }
+}
+
+// The KS x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost. KS = 4 for a full chunk,
+// 2 / 3 for the ragged last chunk of the thin BigVGAN stages (C = 24, 48, 96), where the generic loop was the critical path.
+template <int NH, int KS>
+__device__ __forceinline__ void issue_tap(uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      umma_bf16_lohi(d + (uint32_t)h * hstep, a_lo + (uint32_t)h * 1024u + 2u * k, b_lo + 2u * k, idesc, k == 0 ? accum : 1u);
+}
+template <int NH>
+__device__ __forceinline__ bool issue_tap_ks(int ksteps, uint32_t d, uint32_t hstep, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accum) {
+  if (ksteps == 4) issue_tap<NH, 4>(d, hstep, a_lo, b_lo, idesc, accum);
+  else if (ksteps == 2) issue_tap<NH, 2>(d, hstep, a_lo, b_lo, idesc, accum);
+  else if (ksteps == 3) issue_tap<NH, 3>(d, hstep, a_lo, b_lo, idesc, accum);
+  else return false;
+  return true;
+}
+
+}  // namespace
+}  // namespace b200tts
