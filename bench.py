@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- the driver's measurement contract for the B200 TTS hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bigvgan|f5|pipeline]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pipeline|f5|bigvgan|...]
 
 One "step" = one pass of the hot path over one batch of synthetic input.
-  bigvgan  (default) BASELINE.json configs[1]: BigVGAN-v2 24khz_100band_256x, mels (8,100,512) -> int16 PCM.
-  f5       configs[2]: F5-TTS NFE=32 (31 Euler steps), 6 s reference / 150 text ids, N = 1126, preprocess (STFT/mel/text
-           embed) + DiT loop + Vocos/ISTFT decode, one utterance per step.
-  pipeline configs[3] per-GPU share: U utterances of config-3 shape, each F5 (mel) then BigVGAN on the generated frames.
-The default run times `bigvgan` as the headline line and attaches a short `f5` measurement under the key "f5".
-Each rank runs the same per-GPU batch (utterances shard with no data-path collective: weak scaling); NCCL is used once,
-to broadcast the weights from rank 0 at load. Prints ONE JSON line on rank 0.
+  pipeline (default) BASELINE.json's metric configuration ("F5-TTS NFE=32 + BigVGAN 24 kHz"; configs[3] per-GPU share): U = 8
+           utterances of config-3 shape per GPU -- graph A, the batched 31-step DiT loop, BigVGAN on the generated frames --
+           through b200tts_f5_bigvgan_pipeline. `value`: inputs resident in HBM (device-pointer entry); `e2e`: the host-buffer
+           C call (pinned host inputs, H2D / D2H inside the timed region).
+  f5       configs[2]: one utterance per step (latency): preprocess + DiT loop + Vocos/ISTFT decode.
+  bigvgan  configs[1]: BigVGAN-v2 24khz_100band_256x, mels (8,100,512) -> int16 PCM.
+The default run attaches short `f5` and `bigvgan` measurements under those keys. Each rank runs the same per-GPU batch
+(utterances shard with no data-path collective: weak scaling); NCCL is used once, to broadcast the weights from rank 0 at
+load. Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -112,7 +114,10 @@ def f5_work(cfg, N, ref_len):
     per_tok = cfg.depth * (per_tok_layer_gemm + per_tok_layer_attn) + per_tok_embed
     steps = cfg.nfe - 1
     G = N - ref_len
+    # the fused row-block chain (dit_chain.cu) runs out-proj + ff1 + ff2 of every block and q|k|v of blocks 1..depth-1
+    per_tok_chain = cfg.depth * 2.0 * (D * D + 2 * D * FF) + (cfg.depth - 1) * 2.0 * 3 * D * D
     return {"frames": G, "flops_step": 2 * N * per_tok, "flops_gemm_step": 2 * N * cfg.depth * per_tok_layer_gemm,
+            "flops_chain_step": 2 * N * per_tok_chain,
             "flops_attn_step": 2 * N * cfg.depth * per_tok_layer_attn, "flops_total": steps * 2 * N * per_tok,
             "steps": steps, "audio_s": cfg.hop * (G - 1) / cfg.sample_rate}
 
@@ -212,19 +217,24 @@ def run_reference(args, rank, world):
         cfg = config.F5
         r = cpu_f5(args.audio_len, args.n_text, steps, cores)
         G = r["N"] - r["ref_len"]
-        total = r["pre_s"] + (cfg.nfe - 1) * r["step_s"] + r["decode_s"]
+        total = r["pre_s"] + (cfg.nfe - 1) * r["step_s"]
         if args.workload == "pipeline":
-            tv = cpu_bigvgan(G, 1, cores)
-            total += tv
+            r["bigvgan_s"] = cpu_bigvgan(G, 1, cores)
+            total += r["bigvgan_s"]
+        else:
+            total += r["decode_s"]
         v = G / total
         line = {"metric": "mel_frames_per_s", "value": v, "unit": "mel-frames/s", "ms_per_step": 1e3 * total, "dtype": "f32",
                 "config": {"workload": f"F5-TTS NFE={cfg.nfe} N={r['N']} (ref {r['ref_len']} frames)"
-                                       + (" + BigVGAN" if args.workload == "pipeline" else " + Vocos/ISTFT")
-                                       + " [BASELINE.json configs[2]]; one utterance", "parallelism": "cpu"},
+                                       + (" + BigVGAN on the generated frames [BASELINE.json configs[3] per-GPU share; one of its utterances per reference step]"
+                                          if args.workload == "pipeline" else " + Vocos/ISTFT [BASELINE.json configs[2]]; one utterance"),
+                           "parallelism": "cpu"},
                 "rtf": total / (cfg.hop * (G - 1) / cfg.sample_rate),
                 "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-                                 "sample": f"graph A once, {steps} of {cfg.nfe - 1} DiT steps (x{cfg.nfe - 1} extrapolated), graph C once; "
-                                           "torch-CPU fp32 eager restatement of the reference modules", "parts_s": r}}
+                                 "sample": f"graph A once, {steps} of {cfg.nfe - 1} DiT steps (x{cfg.nfe - 1} extrapolated), "
+                                           + ("BigVGAN on the generated frames once" if args.workload == "pipeline" else "graph C once")
+                                           + "; torch-CPU fp32 eager restatement of the reference modules (stand-in for ORT "
+                                             "CPUExecutionProvider, not installable offline)", "parts_s": r}}
     line.update({"impl": "reference", "n_gpus": world, "steps": steps, "warmup": 1, "higher_is_better": True, "scaling": "weak",
                  "vs_baseline": None, "data": "synthetic",
                  "e2e": {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -276,10 +286,10 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
     def step_device():
         eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
 
-    def step_e2e():
-        mel_dev.copy_(mel_host, non_blocking=True)
-        eng.bigvgan_run_device(mel_dev.data_ptr(), B, T, pcm_dev.data_ptr(), precision=prec)
-        pcm_host.copy_(pcm_dev, non_blocking=True)
+    mel_np, pcm_np = mel_host.numpy(), pcm_host.numpy()
+
+    def step_e2e():          # the reference-facing call: host (pinned) mel in, host (pinned) PCM out, copies inside b200tts_bigvgan_run
+        eng.bigvgan_run(mel_np, precision=prec, out=pcm_np)
 
     with torch.cuda.stream(H.stream):
         for _ in range(warmup):
@@ -331,7 +341,8 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
 
 
 def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, sampler=None):
-    """U utterances per step, each: A + 31 x B + C (Vocos) [+ BigVGAN on the generated mel frames when with_vocoder]."""
+    """U utterances per step. with_vocoder: the metric's pipeline (A, batched 31-step DiT loop, BigVGAN on the generated
+    frames) in one call; else A + 31 x B + C (Vocos / ISTFT) per utterance."""
     torch = H.torch
     from b200tts import capi, config, synth
     cfg, vcfg = config.F5, config.BIGVGAN
@@ -341,42 +352,37 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     ref_len = L // cfg.hop + 1
     G = N - ref_len
     ns = cfg.hop * (G - 1)
+    nv = vcfg.out_samples(G)
     work = f5_work(cfg, N, ref_len)
     # contiguous per-utterance blocks: audio [U][L] i16, text ids [U][n_text] i32, Euler-start noise [U][N*100] f32
     audio_h = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).pin_memory()
     ids_h = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).pin_memory()
     noise_h = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).pin_memory()
     audio_d, ids_d, noise_d = audio_h.cuda(), ids_h.cuda(), noise_h.cuda()
-    pcm_d = torch.empty((U, ns), dtype=torch.int16, device="cuda")
-    pcm_h = torch.empty((U, ns), dtype=torch.int16).pin_memory()
-    mel_d = torch.empty((U, N, cfg.n_mels), dtype=torch.float32, device="cuda")
-    if with_vocoder:
-        vmel_d = torch.empty((U, vcfg.num_mels, G), dtype=torch.float32, device="cuda")
-        vpcm_d = torch.empty((U, 1, vcfg.out_samples(G)), dtype=torch.int16, device="cuda")
-        vpcm_h = torch.empty((U, 1, vcfg.out_samples(G)), dtype=torch.int16).pin_memory()
+    pcm_d = torch.empty((U, nv if with_vocoder else ns), dtype=torch.int16, device="cuda")
+    audio_np, ids_np, noise_np = audio_h.numpy(), ids_h.numpy(), noise_h.numpy().reshape(U, N, cfg.n_mels)
+    wav_np = torch.empty((U, nv), dtype=torch.int16).pin_memory().numpy()
     torch.cuda.synchronize()
 
-    def core():
-        # one batched DiT loop over the U utterances of this GPU (they share N: length-bucketed batching)
-        eng.f5_synthesize_batch_device(U, audio_d.data_ptr(), L, ids_d.data_ptr(), args.n_text, N, noise_d.data_ptr(),
-                                       pcm_d.data_ptr(), precision=prec, mel_ptr=mel_d.data_ptr() if with_vocoder else 0)
+    def core():              # inputs resident in HBM, device-pointer entry point, no synchronisation
         if with_vocoder:
-            vmel_d.copy_(mel_d[:, ref_len:, :].transpose(1, 2))          # (U, 100, G): BigVGAN's mel_features layout
-            eng.bigvgan_run_device(vmel_d.data_ptr(), U, G, vpcm_d.data_ptr(), precision=prec)
-
-    def step_e2e():
-        audio_d.copy_(audio_h, non_blocking=True)
-        ids_d.copy_(ids_h, non_blocking=True)
-        noise_d.copy_(noise_h, non_blocking=True)
-        core()
-        if with_vocoder:
-            vpcm_h.copy_(vpcm_d, non_blocking=True)
+            eng.f5_bigvgan_pipeline_device(U, audio_d.data_ptr(), L, ids_d.data_ptr(), args.n_text, N, noise_d.data_ptr(),
+                                           pcm_d.data_ptr(), precision=prec)
         else:
-            pcm_h.copy_(pcm_d, non_blocking=True)
+            eng.f5_synthesize_batch_device(U, audio_d.data_ptr(), L, ids_d.data_ptr(), args.n_text, N, noise_d.data_ptr(),
+                                           pcm_d.data_ptr(), precision=prec)
+
+    def step_e2e():          # the reference-facing host-buffer C call: H2D of audio / ids / noise and D2H of the PCM inside it
+        if with_vocoder:
+            eng.f5_bigvgan_pipeline(audio_np, ids_np, N, noise_np, precision=prec, out=wav_np)
+        else:
+            for u in range(U):
+                eng.f5_synthesize(audio_np[u], ids_np[u], N, noise_np[u], precision=prec)
 
     with torch.cuda.stream(H.stream):
         for _ in range(warmup):
             core()
+        step_e2e()
         step_e2e()
     torch.cuda.synchronize()
     if sampler:
@@ -398,30 +404,40 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     prof = eng.profile_end()
     pk = peaks()
     frames = U * G * H.world * steps
-    audio_s = U * (vcfg.out_samples(G) / vcfg.sample_rate if with_vocoder else work["audio_s"])
+    audio_s = U * (nv / vcfg.sample_rate if with_vocoder else work["audio_s"])
     h2d = U * (L * 2 + args.n_text * 4 + N * cfg.n_mels * 4)
-    d2h = U * (vcfg.out_samples(G) * 2 if with_vocoder else ns * 2)
+    d2h = U * (nv * 2 if with_vocoder else ns * 2)
     res = {
         "value": frames / (ms / 1e3), "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / audio_s,
         "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / steps, "rtf": (ms_e2e / 1e3 / steps) / audio_s},
+                "ms_per_step": ms_e2e / steps, "rtf": (ms_e2e / 1e3 / steps) / audio_s,
+                "api": "b200tts_f5_bigvgan_pipeline (host buffers)" if with_vocoder else "b200tts_f5_synthesize (host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "host_enqueue_ms_per_step": host_enqueue_ms,
         "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
         "workload": (f"F5-TTS NFE={cfg.nfe} ({cfg.nfe - 1} Euler steps, CFG pair), {L / cfg.sample_rate:.0f} s ref / {args.n_text} text ids, "
-                     f"N={N}, G={G} generated frames, {U} utterance(s) per GPU per step, preprocess + DiT + "
-                     + ("Vocos/ISTFT decode and BigVGAN on the generated mel [BASELINE.json configs[3] per-GPU share]" if with_vocoder
+                     f"N={N}, G={G} generated frames, {U} utterance(s) per GPU per step: preprocess + DiT loop + "
+                     + ("BigVGAN-v2 24 kHz on the generated mel [BASELINE.json metric configuration: configs[3] per-GPU share]" if with_vocoder
                         else "Vocos/ISTFT decode [BASELINE.json configs[2]]")),
     }
-    gemm_tags = ("f5.qkv_gemm", "f5.out_gemm", "f5.ff1_gemm", "f5.ff2_gemm")
-    gemm_ms = sum(prof[t]["ms"] for t in gemm_tags if t in prof)
-    gemm_n = sum(prof[t]["launches"] for t in gemm_tags if t in prof)
     total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
-    if gemm_ms > 0:
-        ach = U * work["steps"] * work["flops_gemm_step"] / (gemm_ms / 1e3) / 1e12
-        res["roofline"] = {"bound": "tensor", "kernel": "rowgemm_tc3_kernel (DiT qkv/out/ff1/ff2 GEMMs)", "achieved": ach,
-                           "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                           "traffic": ncu_traffic("f5.dit_gemm"), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                           "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms}
+    kname = {capi.BF16: "bf16", capi.F16: "fp16"}.get(prec, "f32")
+    chain = prof.get("f5.chain")
+    if chain and chain["ms"] > 0:
+        ach = U * work["steps"] * work["flops_chain_step"] / (chain["ms"] / 1e3) / 1e12
+        res["roofline"] = {"bound": "tensor", "kernel": f"dit_chain_kernel ({kname}: out-proj + LN + ff1 + ff2 + LN + next q|k|v per launch)",
+                           "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                           "traffic": ncu_traffic("f5.chain"), "peak_source": pk["source"] + " (sustained cuBLAS bf16; fp16 has the same tensor rate)",
+                           "avg_launch_ms": chain["ms"] / max(chain["launches"], 1), "share_of_step": chain["ms"] / total_ms}
+    else:
+        gemm_tags = ("f5.qkv_gemm", "f5.out_gemm", "f5.ff1_gemm", "f5.ff2_gemm")
+        gemm_ms = sum(prof[t]["ms"] for t in gemm_tags if t in prof)
+        gemm_n = sum(prof[t]["launches"] for t in gemm_tags if t in prof)
+        if gemm_ms > 0:
+            ach = U * work["steps"] * work["flops_gemm_step"] / (gemm_ms / 1e3) / 1e12
+            res["roofline"] = {"bound": "tensor", "kernel": f"rowgemm_tc kernels ({kname}: DiT qkv/out/ff1/ff2 GEMMs)", "achieved": ach,
+                               "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                               "traffic": ncu_traffic("f5.dit_gemm"), "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                               "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms}
     att = prof.get("f5.attention")
     if att and att["ms"] > 0:
         ach = U * work["steps"] * work["flops_attn_step"] / (att["ms"] / 1e3) / 1e12
@@ -429,6 +445,7 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
                                      "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                                      "avg_launch_ms": att["ms"] / max(att["launches"], 1), "share_of_step": att["ms"] / total_ms}
     res["dit_tflops_overall"] = U * work["flops_total"] / (ms / steps / 1e3) / 1e12
+    res["dit_frac_of_tensor_peak"] = res["dit_tflops_overall"] / pk["bf16_tflops_sustained"]
     return res
 
 
@@ -612,7 +629,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bigvgan", choices=["bigvgan", "f5", "pipeline", "indextts_vocoder", "indextts_gpt", "indextts"])
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "f5", "bigvgan", "indextts_vocoder", "indextts_gpt", "indextts"])
     ap.add_argument("--new-tokens", type=int, default=256, help="indextts_gpt workload: E calls per sentence (prefill + decode)")
     ap.add_argument("--gpt-text", type=int, default=60, help="indextts_gpt workload: text ids per sentence")
     ap.add_argument("--latent-rows", type=int, default=142, help="indextts_vocoder workload: rows of save_hidden_state")
@@ -621,9 +638,11 @@ def main():
     ap.add_argument("--audio-len", type=int, default=144000)
     ap.add_argument("--n-text", type=int, default=150)
     ap.add_argument("--utterances", type=int, default=8, help="pipeline workload: utterances per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="operand type of the tensor-core engine (BASELINE.json's configurations name fp16); fp32 = the SIMT parity engine")
+    ap.add_argument("--no-chain", action="store_true", help="DiT blocks as separate launches instead of the fused row-block chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the attached F5 measurement of the default run")
+    ap.add_argument("--no-extras", action="store_true", help="skip the attached f5 / bigvgan measurements of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -655,12 +674,17 @@ def main():
         dist.all_reduce(t)
         torch.cuda.synchronize()
 
-    prec = capi.BF16 if args.precision == "bf16" else capi.F32
+    prec = {"fp16": capi.F16, "bf16": capi.BF16, "fp32": capi.F32}[args.precision]
+    if args.workload in ("indextts_gpt", "indextts", "indextts_vocoder") and prec == capi.F16:
+        prec = capi.BF16                                       # the IndexTTS entry points take bf16 weights
+    dtype = {capi.F16: "fp16", capi.BF16: "bf16", capi.F32: "f32"}[prec]
     eng = capi.Engine(local_rank)
+    if args.no_chain:
+        eng.set_option("dit_chain", 0)
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
     H = Harness(torch, dist, stream, world)
-    need_f5 = args.workload in ("f5", "pipeline") or (args.workload == "bigvgan" and not args.no_extras)
+    need_f5 = args.workload in ("f5", "pipeline")
     need_vgan = args.workload in ("bigvgan", "pipeline")
     if args.workload in ("indextts_vocoder", "indextts"):
         cfgv = config.INDEXTTS_VOCODER
@@ -700,25 +724,23 @@ def main():
     extra = {}
     if args.workload == "bigvgan":
         res = bench_bigvgan(args, H, eng, rank, args.batch, args.frames, prec, args.steps, args.warmup, sampler)
-        if need_f5:
-            f5r = bench_f5(args, H, eng, rank, prec, steps=3, warmup=3)
-            extra["f5"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **f5r}
-        dtype = "bf16" if prec == capi.BF16 else "f32"
     elif args.workload == "indextts_vocoder":
         res = bench_indextts_vocoder(args, H, eng, rank, prec, args.steps, args.warmup)
-        dtype = "bf16" if prec == capi.BF16 else "f32"
     elif args.workload == "indextts":
         res = bench_indextts(args, H, eng, rank, prec, args.steps, args.warmup, sampler)
-        dtype = "bf16" if prec == capi.BF16 else "f32"
     elif args.workload == "indextts_gpt":
         res = bench_indextts_gpt(args, H, eng, rank, prec, args.steps, args.warmup, sampler)
         dtype = "bf16 weights, fp32 activations / cache / accumulation" if prec == capi.BF16 else "f32"
     elif args.workload == "f5":
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
-        dtype = "bf16" if prec == capi.BF16 else "f32"
     else:
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, with_vocoder=True, U=args.utterances, sampler=sampler)
-        dtype = "bf16" if prec == capi.BF16 else "f32"
+        if not args.no_extras:
+            # the two other single-GPU configurations, short: configs[2] (one utterance, latency) and configs[1] (vocoder alone)
+            f5r = bench_f5(args, H, eng, rank, prec, steps=5, warmup=3)
+            extra["f5"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **f5r}
+            vgr = bench_bigvgan(args, H, eng, rank, args.batch, args.frames, prec, steps=10, warmup=3)
+            extra["bigvgan"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **vgr}
 
     if rank == 0:
         workload = res.pop("workload")
@@ -731,7 +753,7 @@ def main():
             line["metric"], line["unit"] = "mel_tokens_per_s", "tokens/s"
         line.update(res)
         line.update(extra)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:              # rank 0 at N = 1 only: the other ranks would idle behind it
             cores = os.cpu_count() or 1
             if args.workload == "indextts_vocoder":
                 import torch as _t
@@ -775,10 +797,17 @@ def main():
             else:
                 r = cpu_f5(args.audio_len, args.n_text, 2, cores)
                 G = r["N"] - r["ref_len"]
-                tot = r["pre_s"] + (config.F5.nfe - 1) * r["step_s"] + r["decode_s"]
+                tot = r["pre_s"] + (config.F5.nfe - 1) * r["step_s"]
+                if args.workload == "pipeline":
+                    r["bigvgan_s"] = cpu_bigvgan(G, 1, cores)
+                    tot += r["bigvgan_s"]
+                else:
+                    tot += r["decode_s"]
                 line["cpu_baseline"] = {"value": G / tot, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-                                        "sample": f"graph A, 2 of {config.F5.nfe - 1} DiT steps (extrapolated), graph C of ONE utterance; oracle "
-                                                  "(torch-CPU fp32 restatement of the reference modules)", "parts_s": r}
+                                        "sample": f"ONE utterance of the batch: graph A, 2 of {config.F5.nfe - 1} DiT steps (extrapolated), "
+                                                  + ("BigVGAN on its generated frames" if args.workload == "pipeline" else "graph C")
+                                                  + "; oracle (torch-CPU fp32 restatement of the reference modules; ORT is not installable offline)",
+                                        "parts_s": r}
         print(json.dumps(line), flush=True)
 
     if world > 1:

@@ -38,6 +38,11 @@ const char* b200tts_last_error(void);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the engine's own stream. */
 int b200tts_set_stream(b200tts_engine* e, void* cuda_stream);
 int b200tts_synchronize(b200tts_engine* e);
+/* Engine switches (the role of the reference's provider / session options, F5-TTS-ONNX-Inference.py:41-85,152-169):
+ *   "dit_chain"   1 (default): every F5 DiT block runs as attention + ONE fused row-block kernel; 0: seven launches per block
+ *   "cuda_graphs" 1 (default): repeated calls of one shape replay a captured CUDA graph; 0: enqueue kernel by kernel
+ * Results do not depend on cuda_graphs; dit_chain changes the LayerNorm variance formula's rounding only. */
+int b200tts_set_option(b200tts_engine* e, const char* name, int value);
 /* Number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
 unsigned long long b200tts_launch_count(void);
 
@@ -143,6 +148,22 @@ int b200tts_f5_synthesize_device(b200tts_engine* e, const int16_t* audio_dev, in
 int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* audio_dev, int64_t L,
                                        const int32_t* text_ids_dev, int n_text, int64_t max_duration, const float* noise_dev,
                                        int precision, int n_steps, int16_t* pcm_dev, float* mel_dev);
+
+/* The metric's pipeline (BASELINE.json: "F5-TTS NFE=32 + BigVGAN 24 kHz"; configs[3]) for U utterances that share
+ * (L, n_text, max_duration), in ONE call: graph A per utterance, one batched DiT loop of n_steps Euler steps (< 0: NFE-1), then
+ * the GENERATED frames mel[:, ref_len:] (G = max_duration - (L/256+1) of them) through the BigVGAN session
+ * (BigVGAN/Export_BigVGAN.py:44-49) without leaving the device. Both b200tts_f5_build and b200tts_bigvgan_build must have run.
+ *   audio [U][L] i16, text_ids [U][n_text] i32, noise [U][N][100] f32
+ *   -> wav [U][256*G + 30] i16 (BigVGAN), wav_vocos (optional, may be NULL) [U][256*(G-1)] i16 = the reference's own F5_Decode
+ *      (Vocos + ISTFT) of the same mel, mel (optional) [U][N][100] f32.
+ * The reference never chains these two graphs; parity is per graph: mel vs F5_Transformer, wav vs BigVGAN
+ * fed that mel. The _device variant takes device pointers and enqueues on the engine stream without synchronising. */
+int b200tts_f5_bigvgan_pipeline(b200tts_engine* e, int U, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host,
+                                int n_text, int64_t max_duration, const float* noise_host, int precision, int n_steps,
+                                int16_t* wav_host, int16_t* wav_vocos_host, float* mel_host);
+int b200tts_f5_bigvgan_pipeline_device(b200tts_engine* e, int U, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
+                                       int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
+                                       int16_t* wav_dev, int16_t* wav_vocos_dev, float* mel_dev);
 
 /* ---- single-op entry points (parity tests of the kernels through the boundary) -------------------------
  * Anti-aliased SnakeBeta (BigVGAN/modeling_modified/act.py:25-29): x (B, C, L) fp32 host in the reference

@@ -134,6 +134,30 @@ def test_bigvgan_bf16_vs_oracle(bigvgan_engine):
     assert np.abs(wave[..., :15]).max() <= np.abs(owave.numpy()[..., :15]).max() * 1.5 + 50
 
 
+def test_bigvgan_fp16_vs_oracle(bigvgan_engine):
+    """fp16 conv operands / activations (the type BASELINE.json configs[1] names): PCM SNR >= 48 dB at this small size."""
+    sd = synth.bigvgan_state(1234)
+    mel = synth.bigvgan_mel(22, 2, 48)
+    pcm, wave = bigvgan_engine.bigvgan_run(mel, precision=capi.F16, return_wave=True)
+    _, owave = R.bigvgan_pcm(mel, sd, CFG, return_float=True)
+    s = snr_db(owave.numpy(), wave)
+    assert s > 48.0, s
+    assert np.isfinite(wave).all()
+
+
+@pytest.mark.parametrize("case", [(768, 768, 7, 3, 1, 2, 300), (24, 24, 11, 5, 1, 1, 4099), (1024, 1024, 31, 1, 16, 2, 130)])
+def test_conv1d_tcgen05_fp16(engine, case):
+    Cin, Cout, k, dil, groups, B, L = case
+    rng = np.random.default_rng(Cin + k)
+    x = rng.standard_normal((B, Cin, L)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin // groups, k)) / np.sqrt(Cin // groups * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    got = engine.conv1d(x, w, b, dilation=dil, groups=groups, precision=capi.F16)
+    xh, wh = torch.from_numpy(x).half().float(), torch.from_numpy(w).half().float()
+    want = torch.nn.functional.conv1d(xh, wh, torch.from_numpy(b), dilation=dil, padding=(k * dil - dil) // 2, groups=groups).numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-4 * np.sqrt(Cin // groups * k))
+
+
 def test_bigvgan_batch_items_independent(bigvgan_engine):
     mel = synth.bigvgan_mel(23, 3, 16)
     all_ = bigvgan_engine.bigvgan_run(mel, precision=capi.F32)

@@ -1,5 +1,15 @@
-"""GPU, BASELINE.json's FULL sizes: the oracle needs minutes there, so parity rests on size-independent properties of the path
-(the small-size tests next to this file pin the arithmetic against the reference's vectors):
+"""GPU, BASELINE.json's FULL sizes.
+
+Against the reference itself: tests/golden/fullsize_ref.npz holds what the reference's own modules produce at configs[0..2]
+sizes (oracle/make_golden_fullsize.py: BigVGAN (1,100,512); F5 N = 1126, all 31 steps, graph C). At these sizes the engine
+picks other tiles than the small tests do (multi-wave schedules, the CTA-pair GEMM, the fused DiT chain with 9 teams).
+
+Stated tolerances at these sizes (measured on B200, profiles/r02/parity_fullsize.md):
+  fp32 engine          BigVGAN PCM <= 2 LSB;  F5 mel max-abs <= 1e-3 after 31 steps, PCM <= 3 LSB
+  fp16 engine (bench)  BigVGAN PCM SNR >= 50 dB (57.1 measured);  F5 mel cosine >= 0.99999, PCM SNR >= 55 dB (61.9 measured)
+  bf16 engine          BigVGAN PCM SNR >= 36 dB (39.0 measured);  F5 mel cosine >= 0.9999,  PCM SNR >= 40 dB (44.0 measured)
+
+Plus size-independent properties of the path:
 
   * batch decomposition: a batch equals its items run alone (the reference graphs are batch-1) -- bit-exact,
   * tiling invariance: the first frames of a long mel do not depend on what follows beyond the receptive field,
@@ -13,11 +23,44 @@ import numpy as np
 import pytest
 import torch
 
+import os
+
 import b200tts  # noqa: F401
 from b200tts import capi, config, synth, weights
+from conftest import GOLDEN, snr_db
 
 pytestmark = pytest.mark.gpu
 VCFG, FCFG = config.BIGVGAN, config.F5
+
+
+@pytest.fixture(scope="module")
+def gf():
+    return dict(np.load(os.path.join(GOLDEN, "fullsize_ref.npz")))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+def test_bigvgan_config1_vs_reference_golden(bigvgan_engine, gf):
+    """configs[0]/[1] size, mel (1,100,512): fp32 engine vs the reference's int16 within 2 LSB; the 16-bit engines by PCM SNR,
+    alone and as an item of a batch of 8 (configs[1]: CTA-pair convolutions, 3-wave schedules)."""
+    mel = synth.bigvgan_mel(int(gf["vgan_mel_seed"]), 1, int(gf["vgan_T"]))
+    want = gf["vgan_pcm"].astype(np.int32)
+    got = bigvgan_engine.bigvgan_run(mel, precision=capi.F32).astype(np.int32)
+    assert got.shape == want.shape == (1, 1, 131102)
+    d = np.abs(got - want)
+    assert d.max() <= 2 and (d <= 1).mean() > 0.999
+    mel8 = synth.bigvgan_mel(100, 8, 512)
+    mel8[3] = mel[0]
+    for prec, floor in ((capi.F16, 50.0), (capi.BF16, 36.0)):
+        one = bigvgan_engine.bigvgan_run(mel, precision=prec)
+        assert snr_db(want, one) >= floor, (prec, snr_db(want, one))
+        batch = bigvgan_engine.bigvgan_run(mel8, precision=prec)
+        np.testing.assert_array_equal(batch[3], one[0])
+
+
 
 
 def test_bigvgan_config2_batch_equals_items(bigvgan_engine):
@@ -57,6 +100,55 @@ def f5_engine(engine):
     engine.load_state("f5", weights.f5_export_constants(dsd, FCFG))
     engine.f5_build()
     return engine
+
+
+def test_f5_config3_vs_reference_golden(f5_engine, gf):
+    """configs[2]: 6 s reference, 150 text ids, N = 1126, 31 Euler steps, Vocos / ISTFT decode -- against the reference's own
+    graphs A, B (x31), C. fp32 engine to the fp32 tolerance; fp16 (the benchmarked type) and bf16 engines, fused chain on and off."""
+    audio, ids, maxd, noise = synth.f5_inputs(int(gf["input_seed"]), int(gf["audio_len"]), int(gf["n_text"]))
+    N = int(maxd[0])
+    ref_len = int(gf["f5_ref_signal_len"])
+    assert N == 1126 and ref_len == 563
+    pcm, mel = f5_engine.f5_synthesize(audio, ids, N, noise, precision=capi.F32, return_mel=True)
+    assert np.abs(mel - gf["f5_mel"]).max() <= 1e-3
+    d = np.abs(pcm.astype(np.int32) - gf["f5_pcm"].astype(np.int32))
+    assert d.max() <= 3 and (d <= 1).mean() > 0.99
+    _, mel1 = f5_engine.f5_synthesize(audio, ids, N, noise, precision=capi.F32, n_steps=1, return_mel=True)
+    assert np.abs(mel1 - gf["f5_mel_after_1"]).max() <= 1e-4
+    try:
+        for prec, cos_floor, snr_floor in ((capi.F16, 0.99999, 55.0), (capi.BF16, 0.9999, 40.0)):
+            for chain in (1, 0):
+                f5_engine.set_option("dit_chain", chain)
+                pcm, mel = f5_engine.f5_synthesize(audio, ids, N, noise, precision=prec, return_mel=True)
+                assert np.isfinite(mel).all()
+                assert cosine(mel, gf["f5_mel"]) >= cos_floor, (prec, chain, cosine(mel, gf["f5_mel"]))
+                assert cosine(mel[:, ref_len:], gf["f5_mel"][:, ref_len:]) >= cos_floor
+                assert snr_db(gf["f5_pcm"], pcm) >= snr_floor, (prec, chain, snr_db(gf["f5_pcm"], pcm))
+    finally:
+        f5_engine.set_option("dit_chain", 1)
+
+
+def test_f5_bigvgan_pipeline_vs_reference_golden(f5_engine, bigvgan_engine, gf):
+    """The metric's pipeline through ONE host-buffer C call (b200tts_f5_bigvgan_pipeline): the mel equals the F5 golden, the Vocos
+    wav the F5_Decode golden, and the BigVGAN wav equals the BigVGAN session fed that mel (parity is per graph: the reference never
+    chains the two). U = 2 copies of the golden utterance: the batched DiT loop sees M = 4504 rows."""
+    audio, ids, maxd, noise = synth.f5_inputs(int(gf["input_seed"]), int(gf["audio_len"]), int(gf["n_text"]))
+    N, ref_len = int(maxd[0]), int(gf["f5_ref_signal_len"])
+    U = 2
+    au = np.repeat(audio.reshape(1, -1), U, 0)
+    tx = np.repeat(ids.reshape(1, -1), U, 0)
+    nz = np.repeat(noise.reshape(1, N, 100), U, 0)
+    wav, voc, mel = f5_engine.f5_bigvgan_pipeline(au, tx, N, nz, precision=capi.F16, with_vocos=True, return_mel=True)
+    G = N - ref_len
+    assert wav.shape == (U, 256 * G + 30) and voc.shape == (U, 256 * (G - 1)) and mel.shape == (U, N, 100)
+    for u in range(U):
+        assert cosine(mel[u], gf["f5_mel"][0]) >= 0.99999
+        assert snr_db(gf["f5_pcm"].reshape(-1), voc[u]) >= 55.0
+        direct = bigvgan_engine.bigvgan_run(np.ascontiguousarray(mel[u:u + 1, ref_len:, :].transpose(0, 2, 1)), precision=capi.F16)
+        np.testing.assert_array_equal(direct.reshape(-1), wav[u])
+    np.testing.assert_array_equal(wav[0], wav[1])
+    wav1 = f5_engine.f5_bigvgan_pipeline(au[:1], tx[:1], N, nz[:1], precision=capi.F16)
+    assert snr_db(wav[0], wav1[0]) >= 60.0          # batch of two vs one: other GEMM tile schedules, same rows
 
 
 def test_f5_config3_batch_equals_single(f5_engine):

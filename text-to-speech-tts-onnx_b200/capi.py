@@ -33,6 +33,7 @@ SIGNATURES = {
     "b200tts_last_error": (ctypes.c_char_p, []),
     "b200tts_set_stream": (_int, [_vp, _vp]),
     "b200tts_synchronize": (_int, [_vp]),
+    "b200tts_set_option": (_int, [_vp, ctypes.c_char_p, _int]),
     "b200tts_launch_count": (ctypes.c_ulonglong, []),
     "b200tts_load_tensor": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
     "b200tts_load_tensor_device": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "b200tts_f5_synthesize": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _c_i64, _vp]),
     "b200tts_f5_synthesize_device": (_int, [_vp, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
     "b200tts_f5_synthesize_batch_device": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
+    "b200tts_f5_bigvgan_pipeline": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp, _vp]),
+    "b200tts_f5_bigvgan_pipeline_device": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp, _vp]),
     "b200tts_aa_activation": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp]),
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
@@ -126,6 +129,9 @@ class Engine:
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.b200tts_set_stream(self.handle, _vp(cuda_stream_ptr or 0)), "set_stream")
 
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.b200tts_set_option(self.handle, name.encode(), int(value)), "set_option")
+
     def synchronize(self):
         self._check(self.lib.b200tts_synchronize(self.handle), "synchronize")
 
@@ -162,12 +168,14 @@ class Engine:
         self._check(self.lib.b200tts_bigvgan_build(self.handle), "bigvgan_build")
 
     # -- BigVGAN ---------------------------------------------------------------------------------
-    def bigvgan_run(self, mel, precision=F32, return_wave=False, hop=256):
+    def bigvgan_run(self, mel, precision=F32, return_wave=False, hop=256, out=None):
+        """out: optional caller-owned int16 array (B, 1, hop*T+30), e.g. pinned, to receive the PCM."""
         mel = _f32(mel)
         assert mel.ndim == 3, "mel_features must be (B, n_mels, T)"
         B, _, T = mel.shape
         n_out = hop * T + 30
-        pcm = np.empty((B, 1, n_out), dtype=np.int16)
+        pcm = np.empty((B, 1, n_out), dtype=np.int16) if out is None else out
+        assert pcm.dtype == np.int16 and pcm.size == B * n_out and pcm.flags["C_CONTIGUOUS"]
         wave = np.empty((B, 1, n_out), dtype=np.float32) if return_wave else None
         self._check(self.lib.b200tts_bigvgan_run(self.handle, _ptr(mel), B, T, int(precision), _ptr(pcm), _ptr(wave)),
                     "bigvgan_run")
@@ -344,6 +352,38 @@ class Engine:
         self._check(self.lib.b200tts_f5_synthesize_batch_device(self.handle, int(U), _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
                                                                 int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
                                                                 _vp(pcm_ptr), _vp(mel_ptr or 0)), "f5_synthesize_batch_device")
+
+    def f5_bigvgan_pipeline(self, audio, text_ids, max_duration: int, noise, precision=BF16, n_steps: int = -1, with_vocos=False,
+                            return_mel=False, hop: int = 256, out=None):
+        """U utterances sharing (L, n_text, max_duration): audio (U, L) i16, text_ids (U, n_text) i32, noise (U, N, 100) f32
+        -> BigVGAN wav (U, 256*G+30) i16 [, Vocos wav (U, 256*(G-1))] [, mel (U, N, 100)] through ONE host-buffer C call."""
+        audio = np.ascontiguousarray(audio, dtype=np.int16)
+        audio = audio.reshape(-1, audio.shape[-1])
+        U, L = audio.shape
+        ids = np.ascontiguousarray(text_ids, dtype=np.int32).reshape(U, -1)
+        N = int(max_duration)
+        noise = _f32(noise).reshape(U, N, 100)
+        G = N - (L // hop + 1)
+        wav = np.empty((U, hop * G + 30), dtype=np.int16) if out is None else out      # out: caller-owned (e.g. pinned) PCM buffer
+        assert wav.dtype == np.int16 and wav.size == U * (hop * G + 30) and wav.flags["C_CONTIGUOUS"]
+        voc = np.empty((U, hop * (G - 1)), dtype=np.int16) if with_vocos else None
+        mel = np.empty((U, N, 100), dtype=np.float32) if return_mel else None
+        self._check(self.lib.b200tts_f5_bigvgan_pipeline(self.handle, U, _ptr(audio), L, _ptr(ids), ids.shape[1], N, _ptr(noise),
+                                                         int(precision), int(n_steps), _ptr(wav), _ptr(voc), _ptr(mel)),
+                    "f5_bigvgan_pipeline")
+        res = [wav]
+        if with_vocos:
+            res.append(voc)
+        if return_mel:
+            res.append(mel)
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def f5_bigvgan_pipeline_device(self, U, audio_ptr, L, ids_ptr, n_text, max_duration, noise_ptr, wav_ptr, precision=BF16,
+                                   n_steps: int = -1, wav_vocos_ptr: int = 0, mel_ptr: int = 0):
+        self._check(self.lib.b200tts_f5_bigvgan_pipeline_device(self.handle, int(U), _vp(audio_ptr), int(L), _vp(ids_ptr), int(n_text),
+                                                                int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
+                                                                _vp(wav_ptr), _vp(wav_vocos_ptr or 0), _vp(mel_ptr or 0)),
+                    "f5_bigvgan_pipeline_device")
 
     def bench_rowgemm(self, B, M, N, Cin, taps=1, dil=1, groups=1, epilogue=0, iters=20) -> float:
         """Average ms per launch of the tensor-core shifted-row GEMM on synthetic operands (tools/bench_gemm.py)."""

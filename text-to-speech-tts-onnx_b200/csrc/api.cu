@@ -96,6 +96,8 @@ int b200tts_create(int device, b200tts_engine** out) {
     e->impl.own_stream = true;
     const char* g = getenv("B200TTS_GRAPHS");           // B200TTS_GRAPHS=0: always enqueue kernel by kernel
     e->impl.graphs.enabled = !(g != nullptr && g[0] == '0');
+    const char* ch = getenv("B200TTS_CHAIN");           // B200TTS_CHAIN=0: DiT blocks as separate launches (A/B of dit_chain.cu)
+    e->impl.dit_chain = !(ch != nullptr && ch[0] == '0');
     *out = e.release();
   });
 }
@@ -118,6 +120,19 @@ int b200tts_set_stream(b200tts_engine* e, void* cuda_stream) {
       B2_CUDA(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
       E.own_stream = true;
     }
+  });
+}
+
+int b200tts_set_option(b200tts_engine* e, const char* name, int value) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(name != nullptr, "set_option: null name");
+    B2_CUDA(cudaStreamSynchronize(E.stream));
+    const std::string n(name);
+    if (n == "dit_chain") E.dit_chain = value != 0;
+    else if (n == "cuda_graphs") E.graphs.enabled = value != 0;
+    else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs)");
+    E.graphs.clear();                                    // captured graphs bake the code path in
   });
 }
 
@@ -463,21 +478,27 @@ static void synth_device(Engine& E, const int16_t* audio_dev, int64_t L, const i
 // U utterances that share (L, n_text, max_duration): graph A per utterance, ONE batched DiT loop over all 2U sequences
 // (the GEMMs see M = 2*U*N rows instead of 2*N), graph C per utterance.
 static void synth_batch_device(Engine& E, int U, const int16_t* audio_dev, int64_t L, const int32_t* ids_dev, int n_text, int64_t N,
-                               const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev) {
+                               const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev,
+                               int16_t* vgan_pcm_dev = nullptr) {
   cudaStream_t s = E.stream;
   const int nm = f5_n_mels(E);
   const int F = (int)(L / 256 + 1);
   const long ns = 256L * (N - F - 1);
   run_graphed(E, {31, U, (long long)(uintptr_t)audio_dev, (long long)L, (long long)(uintptr_t)ids_dev, n_text, (long long)N,
-                  (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev},
+                  (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev,
+                  (long long)(uintptr_t)vgan_pcm_dev},
               [&] {
                 for (int u = 0; u < U; ++u)
                   f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U, precision);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 f5_prepare_cond(E);
                 f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
-                for (int u = 0; u < U; ++u)
-                  f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr, precision);
+                if (pcm_dev)
+                  for (int u = 0; u < U; ++u)
+                    f5_decode(E, f5_noise(E, u), (int)N, F, pcm_dev + (size_t)u * ns, nullptr, precision);
+                if (vgan_pcm_dev)        // the generated frames, channels-last as they lie, straight into BigVGAN (bigvgan.cuh)
+                  bigvgan_forward(E, *E.bigvgan, f5_noise(E) + (size_t)F * nm, U, (int)(N - F), precision, vgan_pcm_dev, nullptr, nullptr,
+                                  (long)N * nm);
                 if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
               },
               [&] { f5_restore_shape(E, (int)N, F, U); });
@@ -492,6 +513,56 @@ int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* 
     B2_CHECK(U >= 1 && L > 0 && n_text > 0 && max_duration > L / 256 + 2, "f5_synthesize_batch_device: bad sizes");
     B2_CHECK(precision != PREC_F32 || U == 1, "f5_synthesize_batch_device: the fp32 parity engine takes one utterance at a time");
     synth_batch_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, pcm_dev, mel_dev);
+  });
+}
+
+static void pipeline_check(Engine& E, int U, int64_t L, int n_text, int64_t N, int precision) {
+  B2_CHECK(E.f5 != nullptr, "F5 weights are not built (call b200tts_f5_build)");
+  B2_CHECK(E.bigvgan != nullptr, "BigVGAN weights are not built (call b200tts_bigvgan_build)");
+  B2_CHECK(U >= 1 && L > 0 && n_text > 0 && N > L / 256 + 2 && N < (1 << 30), "f5_bigvgan_pipeline: bad sizes");
+  B2_CHECK(precision != PREC_F32 || U == 1, "f5_bigvgan_pipeline: the fp32 parity engine takes one utterance at a time");
+  B2_CHECK(bigvgan_num_mels(*E.bigvgan) == f5_n_mels(E), "f5_bigvgan_pipeline: the vocoder's mel width differs from the DiT's");
+}
+
+int b200tts_f5_bigvgan_pipeline_device(b200tts_engine* e, int U, const int16_t* audio_dev, int64_t L, const int32_t* text_ids_dev,
+                                       int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
+                                       int16_t* wav_dev, int16_t* wav_vocos_dev, float* mel_dev) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_dev && text_ids_dev && noise_dev && wav_dev, "f5_bigvgan_pipeline_device: null buffer");
+    pipeline_check(E, U, L, n_text, max_duration, precision);
+    synth_batch_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, wav_vocos_dev, mel_dev, wav_dev);
+  });
+}
+
+int b200tts_f5_bigvgan_pipeline(b200tts_engine* e, int U, const int16_t* audio_host, int64_t L, const int32_t* text_ids_host, int n_text,
+                                int64_t max_duration, const float* noise_host, int precision, int n_steps, int16_t* wav_host,
+                                int16_t* wav_vocos_host, float* mel_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_host && text_ids_host && noise_host && wav_host, "f5_bigvgan_pipeline: null buffer");
+    pipeline_check(E, U, L, n_text, max_duration, precision);
+    cudaStream_t s = E.stream;
+    const int64_t N = max_duration, F = L / 256 + 1, G = N - F;
+    const int nm = f5_n_mels(E);
+    const long nv = bigvgan_out_samples(*E.bigvgan, (int)G), ns = 256L * (G - 1);
+    // persistent staging (stable addresses -> graph replay): i16 [audio | wav | wav_vocos], f32 [noise], f32 [mel | ids]
+    const size_t Lp = (size_t)round_up((long)U * L, 8), nvp = (size_t)round_up((long)U * nv, 8), nsp = (size_t)round_up((long)U * ns, 8);
+    const size_t nmel = (size_t)U * N * nm;
+    E.io_i16.reserve(Lp + nvp + nsp);
+    E.io_f32a.reserve(nmel);
+    E.io_f32b.reserve(nmel + (size_t)round_up((long)U * n_text, 4));
+    int16_t* d_audio = E.io_i16.p; int16_t* d_wav = d_audio + Lp; int16_t* d_voc = wav_vocos_host ? d_wav + nvp : nullptr;
+    float* d_noise = E.io_f32a.p; float* d_mel = mel_host ? E.io_f32b.p : nullptr;
+    int* d_ids = reinterpret_cast<int*>(E.io_f32b.p + nmel);
+    B2_CUDA(cudaMemcpyAsync(d_audio, audio_host, (size_t)U * L * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids, text_ids_host, (size_t)U * n_text * sizeof(int), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_noise, noise_host, nmel * sizeof(float), cudaMemcpyHostToDevice, s));
+    synth_batch_device(E, U, d_audio, L, d_ids, n_text, N, d_noise, precision, n_steps, d_voc, d_mel, d_wav);
+    B2_CUDA(cudaMemcpyAsync(wav_host, d_wav, (size_t)U * nv * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (wav_vocos_host) B2_CUDA(cudaMemcpyAsync(wav_vocos_host, d_voc, (size_t)U * ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel, nmel * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
   });
 }
 

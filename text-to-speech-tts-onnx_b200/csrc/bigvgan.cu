@@ -362,12 +362,13 @@ void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out, const f
 }  // namespace
 
 void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T, int precision, int16_t* d_pcm, float* d_wave,
-                     const float* const* d_conds) {
+                     const float* const* d_conds, long cl_bstride) {
   B2_CHECK(B > 0 && T > 0, "bigvgan: empty input");
   B2_CHECK(precision == PREC_F32 || precision == PREC_BF16 || precision == PREC_F16, "bigvgan: unknown precision");
   const bool latent_in = m.fn_w.p != nullptr;           // IndexTTS_F: d_in = GPT latent rows (T, gpt_dim), already channels-last
   B2_CHECK(!latent_in || B == 1, "the IndexTTS vocoder takes one latent sequence per call");
   B2_CHECK(latent_in == (d_conds != nullptr), "conditioning vectors go with the IndexTTS vocoder only");
+  B2_CHECK(!latent_in || cl_bstride == 0, "the channels-last mel input belongs to the mel vocoder");
   Ctx c{e, m, B, precision != PREC_F32, precision == PREC_F16 ? 1 : 0, precision == PREC_F16 ? 2 : 1};
   cudaStream_t s = e.stream;
 
@@ -402,6 +403,11 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
       B2_LAUNCH_CHECK(); count_launch();
     }
     pre_bias = m.pre_bias_c.p;
+  } else if (cl_bstride > 0) {
+    B2_CHECK(cl_bstride >= (long)T * m.n_mels, "bigvgan: channels-last batch stride shorter than one mel");
+    ProfScope ps(e.prof, "bigvgan.mel_transpose", s);
+    B2_CUDA(cudaMemcpy2DAsync(m.mel_cl.p, (size_t)T * m.n_mels * sizeof(float), d_in, (size_t)cl_bstride * sizeof(float),
+                              (size_t)T * m.n_mels * sizeof(float), (size_t)B, cudaMemcpyDeviceToDevice, s));
   } else {
     ProfScope ps(e.prof, "bigvgan.mel_transpose", s);
     batched_transpose(d_in, m.mel_cl.p, B, m.n_mels, T, s);

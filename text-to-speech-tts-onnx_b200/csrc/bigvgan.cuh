@@ -18,8 +18,11 @@ BigVGANModel* bigvgan_build(Engine& e, const std::string& prefix);
 // IndexTTS (d_conds = nstages + 1 device vectors: cond_0..cond_{n-1} of C_i floats, then the cond_layer vector of C0):
 //   d_in = latent rows (T, gpt_dim) fp32 device = hidden[:-2], B = 1.
 // d_pcm: (B, hop*T+30) int16 device; d_wave (optional): same shape fp32, the pre-cast value tanh(.)*32767 clamped.
+// cl_bstride > 0 (mel vocoder only): d_in is ALREADY channels-last, (B, T, n_mels) rows with cl_bstride floats between batches --
+// how the F5 DiT leaves its mel (f5.cu: noise [U][N][n_mels], generated frames = rows ref_len..N-1), so the F5 -> BigVGAN
+// pipeline hands the frames over without the (B, n_mels, T) round trip.
 void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T, int precision, int16_t* d_pcm, float* d_wave,
-                     const float* const* d_conds = nullptr);
+                     const float* const* d_conds = nullptr, long cl_bstride = 0);
 
 void bigvgan_free(BigVGANModel* m);
 int bigvgan_num_mels(const BigVGANModel& m);        // conv_pre input width (n_mels, or gpt_dim for IndexTTS)
@@ -27,7 +30,7 @@ int bigvgan_num_stages(const BigVGANModel& m);
 int bigvgan_stage_channels(const BigVGANModel& m, int i);   // i = -1: conv_pre output channels
 long bigvgan_out_samples(const BigVGANModel& m, int T);   // hop*T + 30
 
-// bf16 weight layouts for the tensor-core path (idempotent).
-void bigvgan_tc_prepare(Engine& e, BigVGANModel& m);
+// 16-bit weight layouts for the tensor-core path (idempotent per operand type: f16 = 0 bf16, 1 fp16).
+void bigvgan_tc_prepare(Engine& e, BigVGANModel& m, int f16 = 0);
 
 }  // namespace b200tts

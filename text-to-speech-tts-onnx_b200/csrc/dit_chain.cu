@@ -56,6 +56,7 @@ struct ChainArgs {
   int vt_ld, vt_heads;
   float* stats;
   unsigned* flags;
+  unsigned long long* trace;      // optional [CTA][64] globaltimer stamps (B200TTS_CHAIN_TRACE, tools/chain_trace.py)
 };
 
 // ---- team hand-offs: monotonic counters in global memory (zero at kernel start), one per (row block, event) -----------------
@@ -76,6 +77,13 @@ __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target)
   while (ld_acquire_gpu(p) < target) {
     __nanosleep(40);
     if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void stamp(const ChainArgs& c, int slot) {
+  if (c.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    c.trace[(size_t)blockIdx.x * 64 + slot] = t;
   }
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -131,31 +139,52 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
     wait_counter(flag_stat, 2u * CH_TEAM);
   }
   epi_bar();
-  // pass 2: warp w normalises rows [16w, 16w + 16) of the slab; lane l owns columns col0 + 4l .. 4l + 3
+  if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
+  // pass 2: warp w normalises rows [16w, 16w + 16) of the slab; lane l owns columns col0 + 4l .. 4l + 3. All loads of the
+  // 16 rows are issued before the first use (one L2 round trip for the statistics, one for x, not one per row).
   const int col = slice * (c.D / CH_TEAM) + lane * 4;
   const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
   const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
   const float inv_d = 1.0f / (float)c.D;
-#pragma unroll 4
-  for (int j = 0; j < 16; ++j) {
-    const int row = warp * 16 + j;
-    const long grow = (long)rb * CH_ROWS + rank * 128 + row;
-    if (grow >= c.R) break;                                   // warp-uniform
-    float2 pr = make_float2(0.f, 0.f);
-    if (lane < CH_TEAM) pr = __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)row * CH_TEAM + lane) * 2));
+  const long grow0 = (long)rb * CH_ROWS + rank * 128 + warp * 16;
+  float2 pr[4];
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      pr.x += __shfl_xor_sync(0xffffffffu, pr.x, o);
-      pr.y += __shfl_xor_sync(0xffffffffu, pr.y, o);
+  for (int k = 0; k < 4; ++k)       // lane = (row k*4 + lane/8, slot lane%8)
+    pr[k] = __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_TEAM + (lane & 7)) * 2));
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float4 xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long g = grow0 + half * 8 + j;
+      xv[j] = g < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + g * c.D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float sum = __shfl_sync(0xffffffffu, pr.x, 0), sq = __shfl_sync(0xffffffffu, pr.y, 0);
-    const float mean = sum * inv_d;
-    const float var = fmaxf(sq * inv_d - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + 1e-6f);
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(c.x + grow * c.D + col));
-    const float y0 = (v.x - mean) * rstd * (1.0f + sc.x) + sh.x, y1 = (v.y - mean) * rstd * (1.0f + sc.y) + sh.y;
-    const float y2 = (v.z - mean) * rstd * (1.0f + sc.z) + sh.z, y3 = (v.w - mean) * rstd * (1.0f + sc.w) + sh.w;
-    *reinterpret_cast<uint2*>(dst + grow * c.D + col) = pack16x4(y0, y1, y2, y3, c.f16);
+    if (half == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          pr[k].x += __shfl_xor_sync(0xffffffffu, pr[k].x, o);
+          pr[k].y += __shfl_xor_sync(0xffffffffu, pr[k].y, o);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int jj = half * 8 + j;
+      const float px = (jj >> 2) == 0 ? pr[0].x : (jj >> 2) == 1 ? pr[1].x : (jj >> 2) == 2 ? pr[2].x : pr[3].x;
+      const float py = (jj >> 2) == 0 ? pr[0].y : (jj >> 2) == 1 ? pr[1].y : (jj >> 2) == 2 ? pr[2].y : pr[3].y;
+      const float sum = __shfl_sync(0xffffffffu, px, (jj & 3) * 8), sq = __shfl_sync(0xffffffffu, py, (jj & 3) * 8);
+      const long g = grow0 + jj;
+      if (g >= c.R) continue;                                   // warp-uniform
+      const float mean = sum * inv_d;
+      const float var = fmaxf(sq * inv_d - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + 1e-6f);
+      const float4 v = xv[j];
+      const float y0 = (v.x - mean) * rstd * (1.0f + sc.x) + sh.x, y1 = (v.y - mean) * rstd * (1.0f + sc.y) + sh.y;
+      const float y2 = (v.z - mean) * rstd * (1.0f + sc.z) + sh.z, y3 = (v.w - mean) * rstd * (1.0f + sc.w) + sh.w;
+      *reinterpret_cast<uint2*>(dst + g * c.D + col) = pack16x4(y0, y1, y2, y3, c.f16);
+    }
   }
   team_signal(flag_ready, tid);
 }
@@ -214,10 +243,12 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         for (int j = 0; j < njobs; ++j) {
           const JobShape js = job_shape(j, c.D, c.FF);
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
+          stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
             wait_counter(flags + (j == 1 ? F_N16 : j == 2 ? F_FF16 : F_N16B), 2u * CH_TEAM);
             fence_proxy_async_global();
           }
+          stamp(c, 8 + 8 * j + 1);
           for (int ck = 0; ck < js.K / BK; ++ck) {
             mbar_wait(&a_empty[sa], pa ^ 1);
             if (leader) mbar_expect_tx(&a_full[sa], 2u * CH_A_BYTES);
@@ -268,6 +299,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             mbar_wait(&a_full[sa], pa);
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
+            if (ck == 0 && lane == 0) stamp(c, 8 + 8 * j + 2);
             const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
             const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
             const uint32_t accum = ck > 0 ? 1u : 0u;
@@ -290,7 +322,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
               }
               umma2_commit_mc(&b_empty[sb]);
               umma2_commit_mc(&a_empty[sa]);
-              if (ck == chunks - 1) umma2_commit_mc(&acc_full[j]);
+              if (ck == chunks - 1) { umma2_commit_mc(&acc_full[j]); stamp(c, 8 + 8 * j + 3); }
             }
             __syncwarp();
             if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
@@ -301,9 +333,11 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     }
   } else {
     // ===== epilogue (both CTAs, warps 0..7): this CTA's 128 rows; q = TMEM lane quarter, e = even / odd 32-column blocks =====
-    pdl_wait();
     const int q = warp & 3, e = warp >> 2;
     const int tid = warp * 32 + lane;
+    if (tid == 0) stamp(c, 0);
+    pdl_wait();
+    if (tid == 0) stamp(c, 1);
     float* stg = smem_epi + warp * (EPI_STAGE_BYTES / 4);
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     TcArgs a;
@@ -332,11 +366,14 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         if (p.t_row0 < a.M) epi_load_res(a, p, e * 32, res);
         mbar_wait(&acc_full[0], ph);
         tc_fence_after();
+        if (tid == 0) stamp(c, 8 + 8 * 0 + 4);
         epilogue_warp<EPI_STD, ACT_NONE, true>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res, psum, psq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[0]);
+        if (tid == 0) stamp(c, 8 + 8 * 0 + 5);
         ln_phase(c, rb, (int)rank, slice, 0, psum, psq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
+        if (tid == 0) stamp(c, 8 + 8 * 0 + 7);
       }
       // ---- job 1: ff16 = GELU_tanh(n16 @ Wff1^T + b_ff1) ----
       {
@@ -347,11 +384,14 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         p.n0 = slice * js.n_pair;
         mbar_wait(&acc_full[1], ph);
         tc_fence_after();
+        if (tid == 0) stamp(c, 8 + 8 * 1 + 4);
         epilogue_warp<EPI_STD, ACT_GELU_TANH, false>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[1]);
+        if (tid == 0) stamp(c, 8 + 8 * 1 + 5);
         team_signal(flags + F_FF16, tid);
+        if (tid == 0) stamp(c, 8 + 8 * 1 + 7);
       }
       // ---- job 2: x += gate_mlp * (ff16 @ Wff2^T + b_ff2) ; LN-modulate (next block's attention / final) -> n16b ----
       {
@@ -365,11 +405,14 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         if (p.t_row0 < a.M) epi_load_res(a, p, e * 32, res);
         mbar_wait(&acc_full[2], ph);
         tc_fence_after();
+        if (tid == 0) stamp(c, 8 + 8 * 2 + 4);
         epilogue_warp<EPI_STD, ACT_NONE, true>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res, psum, psq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[2]);
+        if (tid == 0) stamp(c, 8 + 8 * 2 + 5);
         ln_phase(c, rb, (int)rank, slice, 1, psum, psq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
+        if (tid == 0) stamp(c, 8 + 8 * 2 + 7);
       }
       // ---- job 3: q | k | v of the next block: bias + RoPE -> qk16, V transposed -> vt_out ----
       if (c.has_qkv) {
@@ -382,10 +425,12 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         p.n0 = slice * js.n_pair;
         mbar_wait(&acc_full[3], ph);
         tc_fence_after();
+        if (tid == 0) stamp(c, 8 + 8 * 3 + 4);
         epilogue_warp<EPI_ROPE, ACT_NONE, false>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[3]);
+        if (tid == 0) stamp(c, 8 + 8 * 3 + 5);
         a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0;
       }
     }
@@ -442,7 +487,7 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
   c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
-  c.stats = d.stats; c.flags = d.flags;
+  c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
   CUtensorMap mA[4], mB[4];
   const void* a_ptr[4] = {d.att16, d.n16, d.ff16, d.n16b};
   const int a_k[4] = {d.D, d.D, d.FF, d.D};

@@ -34,6 +34,7 @@ struct DitChain {
   // team synchronisation scratch (sizes below); `flags` must be zero when the kernel starts
   float* stats = nullptr;
   unsigned* flags = nullptr;
+  unsigned long long* trace = nullptr;   // optional [CTAs][64] %globaltimer stamps of the hand-offs (debug: B200TTS_CHAIN_TRACE=<file>)
 };
 
 bool dit_chain_supported(int D, int FF, int H);      // shapes the kernel is specialised for + enough co-resident CTA pairs

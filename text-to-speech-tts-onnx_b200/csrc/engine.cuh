@@ -99,6 +99,7 @@ struct Engine {
   BigVGANModel* ivgan = nullptr;           // the IndexTTS_F vocoder (same generator family, see bigvgan.cuh)
   F5Model* f5 = nullptr;
   GptModel* igpt = nullptr;                // IndexTTS GPT-2 acoustic model (gpt2.cuh)
+  bool dit_chain = true;                   // F5 DiT blocks through the fused row-block chain kernel (dit_chain.cu); b200tts_set_option
 
   const Tensor& weight(const std::string& name) const {
     auto it = weights.find(name);

@@ -14,7 +14,9 @@
 #include "f5.cuh"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "attention_tc.cuh"
 #include "dit_chain.cuh"
@@ -100,6 +102,7 @@ struct F5Model {
   DevBuf<__nv_bfloat16> h16, c16, n16, n16b, qk16, vT16, att16, ff16, x16;   // tensor-core engine (bf16 or fp16 bits)
   DevBuf<float> chain_stats;                                           // dit_chain.cuh: team scratch
   DevBuf<unsigned> chain_flags;                                        // [depth][row blocks][8], zeroed once per Euler step
+  DevBuf<unsigned long long> chain_trace;                              // debug only (B200TTS_CHAIN_TRACE)
   DevBuf<__half2> rope_cs16;                                           // [N][64] (cos, sin): exact, the tables are fp16-rounded (q5)
   // preprocess / decode scratch
   DevBuf<float> audio_f, spec, mag, mel, t_a, t_b, t_c, t_wide, grn_scratch;
@@ -577,13 +580,6 @@ void attention_f32(Engine& e, F5Model& m, int b) {
 
 }  // namespace
 
-// B200TTS_CHAIN=0 keeps every DiT block as seven launches (LN, q|k|v, attention, out, LN, ff1, ff2): the A/B switch for the
-// fused row-block chain (dit_chain.cu).
-static bool chain_enabled() {
-  static const bool on = [] { const char* v = getenv("B200TTS_CHAIN"); return !(v != nullptr && v[0] == '0'); }();
-  return on;
-}
-
 void f5_steps(Engine& e, int first, int count, int precision) {
   F5Model& m = model(e);
   cudaStream_t s = e.stream;
@@ -595,7 +591,9 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   const int N = m.N, D = m.D, S = 2 * m.U, R = S * N;
   B2_CHECK(fast || m.U == 1, "the fp32 parity engine runs one utterance at a time");
   reserve_step(m, fast != 0);
-  const bool chain = fast && chain_enabled() && dit_chain_supported(D, m.FF, m.H);
+  // e.dit_chain = false (B200TTS_CHAIN=0 / b200tts_set_option) keeps every DiT block as seven launches (LN, q|k|v, attention, out,
+  // LN, ff1, ff2): the A/B switch for the fused row-block chain (dit_chain.cu)
+  const bool chain = fast && e.dit_chain && dit_chain_supported(D, m.FF, m.H);
   PdlScope pdl(m.U == 1);                  // short kernels only (common.cuh)
   if (!fast) {   // padding rows / columns (t in [N, Npad)) of the fp32 attention operands must read as zero
     B2_CUDA(cudaMemsetAsync(m.kT32.p, 0, (size_t)2 * m.H * m.hd * m.Npad * sizeof(float), s));
@@ -618,6 +616,9 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     rowgemm_tc(p, L.qkv.tc[f16], s);
   };
   const size_t flag_words = dit_chain_flag_words(R);
+  // debug: B200TTS_CHAIN_TRACE=<file> (with B200TTS_GRAPHS=0) dumps the %globaltimer stamps of the LAST chain launch, [CTA][64] u64
+  const char* trace_path = chain ? getenv("B200TTS_CHAIN_TRACE") : nullptr;
+  if (trace_path) { m.chain_trace.reserve((size_t)512 * 64); B2_CUDA(cudaMemsetAsync(m.chain_trace.p, 0, (size_t)512 * 64 * 8, s)); }
   for (int step = first; step < first + count; ++step) {
     // ---- input embedding: h[b] = Wx x + (Wc c_b + bias) ; x = conv_pos(h) + h ----
     if (fast) {
@@ -675,6 +676,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
           c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
         }
         c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
+        c.trace = trace_path ? m.chain_trace.p : nullptr;
         ProfScope ps(e.prof, "f5.chain", s);
         dit_chain(c, s);
       }
@@ -725,6 +727,16 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     {
       ProfScope ps(e.prof, "f5.euler", s);
       euler_cfg_update(m.noise.p, m.pred.p, (long)N * m.n_mels, m.U, m.cfg_strength, m.delta_t[step], s);
+    }
+  }
+  if (trace_path) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      std::vector<unsigned long long> h((size_t)512 * 64);
+      B2_CUDA(cudaMemcpyAsync(h.data(), m.chain_trace.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
+      B2_CUDA(cudaStreamSynchronize(s));
+      if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
   }
 }
