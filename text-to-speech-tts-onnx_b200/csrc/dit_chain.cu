@@ -32,16 +32,18 @@ namespace b200tts {
 
 namespace {
 
-constexpr int CH_A_STAGES = 5, CH_B_STAGES = 4;
+constexpr int CH_A_STAGES = 4, CH_B_STAGES = 3;
 constexpr int CH_A_BYTES = 128 * 128;            // 128 rows x 64 channels x 2 B
 constexpr int CH_B_BYTES = 192 * 128;            // up to 192 weight rows per CTA and chunk (q|k|v: two 96-row boxes)
 constexpr int CH_STAT_BYTES = 2 * 128 * 2 * 4;   // [column half e][row][sum, sum of squares]
+constexpr int CH_EPI_BYTES = 8 * 8192;           // per epilogue warp: residual tile + result tile (4 KB each, rowgemm_tc_dev.cuh: EpiTile)
+constexpr int CH_VEC_BYTES = 2 * 384 * 4;        // bias / gate of the CTA's column slice
 constexpr int CH_TEAM = 8;                       // CTA pairs per row block
 constexpr int CH_ROWS = 256;                     // rows per block (one M = 256 pair tile)
 constexpr int CH_NFLAGS = 8;
 enum { F_STAT1 = 0, F_N16 = 1, F_FF16 = 2, F_STAT2 = 3, F_N16B = 4 };
-constexpr int CH_BAR_BYTES = (2 * CH_A_STAGES + 2 * CH_B_STAGES + 8) * 8 + 16;
-constexpr int CH_SMEM = CH_A_STAGES * CH_A_BYTES + CH_B_STAGES * CH_B_BYTES + EPI_BYTES + CH_STAT_BYTES + CH_BAR_BYTES + 1024;
+constexpr int CH_BAR_BYTES = (2 * CH_A_STAGES + 2 * CH_B_STAGES + 8 + 8) * 8 + 16;
+constexpr int CH_SMEM = CH_A_STAGES * CH_A_BYTES + CH_B_STAGES * CH_B_BYTES + CH_EPI_BYTES + CH_VEC_BYTES + CH_STAT_BYTES + CH_BAR_BYTES + 1024;
 static_assert(CH_SMEM <= 227 * 1024, "dit_chain: shared memory budget");
 
 struct ChainArgs {
@@ -60,13 +62,17 @@ struct ChainArgs {
 };
 
 // ---- team hand-offs: monotonic counters in global memory (zero at kernel start), one per (row block, event) -----------------
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+// Polling is RELAXED (an acquire load costs a CCTL.IVALL -- a full L1 invalidation of the SM -- per poll: ncu r02a counted
+// 92 865 of them in one launch, thrashing the L1 lines the epilogue warps of the same SM live on); one acquire fence follows
+// the poll that succeeds.
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_gpu(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // generic-proxy global writes (epilogue stores) <-> async-proxy reads (TMA loads of the same bytes by another CTA)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -74,10 +80,11 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // construction (dit_chain(): grid <= resident pairs); the watchdog turns a protocol bug into a trap instead of a hung GPU.
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
   const long long t0 = clock64();
-  while (ld_acquire_gpu(p) < target) {
-    __nanosleep(40);
+  while (ld_relaxed_gpu(p) < target) {
+    __nanosleep(64);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+  fence_acq_rel_gpu();
 }
 __device__ __forceinline__ void stamp(const ChainArgs& c, int slot) {
   if (c.trace != nullptr) {
@@ -88,12 +95,16 @@ __device__ __forceinline__ void stamp(const ChainArgs& c, int slot) {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// the eight epilogue warps of a CTA have finished writing a slab: make it visible to the team and count this CTA in
+// The eight epilogue warps of a CTA have finished writing a slab: make it visible to the team and count this CTA in. The CTA
+// barrier orders every warp's stores before thread 0's fence, and a gpu-scope fence is cumulative over what its thread has
+// observed (the grid-barrier idiom: bar.sync; thread 0: fence + atomic) -- one MEMBAR per CTA instead of 256.
 __device__ __forceinline__ void team_signal(unsigned* flag, int tid) {
-  fence_proxy_async_global();
-  __threadfence();
   epi_bar();
-  if (tid == 0) red_release_gpu(flag, 1u);
+  if (tid == 0) {
+    fence_proxy_async_global();
+    fence_acq_rel_gpu();
+    red_relaxed_gpu(flag, 1u);
+  }
 }
 
 struct JobShape { int K, n_pair, nsub, sub_n, tmem_col, b_rows; };
@@ -107,35 +118,24 @@ __device__ __forceinline__ JobShape job_shape(int j, int D, int FF) {
 }
 
 // LayerNorm statistics + modulation of this CTA's [128 rows] x [128 columns at col0] slab of x (all 256 epilogue threads).
-//   psum / psq : per-lane partial sums from epilogue_warp<.., STATS> (phase-2 rows i*4 + sub of the warp's 32 rows)
-__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind, float (&psum)[8], float (&psq)[8],
+//   rsum / rsq : this lane's row sums over the warp's column blocks (epilogue_rows_tma<.., STATS>)
+__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind, float rsum, float rsq,
                                          const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
                                          unsigned* flag_ready, float* st, int warp, int lane) {
   const int tid = warp * 32 + lane;
-  const int q = warp & 3, e = warp >> 2, sub = lane >> 3, c4 = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      psum[i] += __shfl_xor_sync(0xffffffffu, psum[i], o);
-      psq[i] += __shfl_xor_sync(0xffffffffu, psq[i], o);
-    }
-    if (c4 == 0) {
-      const int row = q * 32 + i * 4 + sub;
-      st[(e * 128 + row) * 2 + 0] = psum[i];
-      st[(e * 128 + row) * 2 + 1] = psq[i];
-    }
-  }
+  const int q = warp & 3, e = warp >> 2;
+  st[(e * 128 + q * 32 + lane) * 2 + 0] = rsum;                 // the row-layout epilogue leaves a row's sums in one lane
+  st[(e * 128 + q * 32 + lane) * 2 + 1] = rsq;
   epi_bar();
   float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_TEAM * 2);
   if (tid < 128) {
     const float s = st[tid * 2] + st[(128 + tid) * 2], sq = st[tid * 2 + 1] + st[(128 + tid) * 2 + 1];
     *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_TEAM + slice) * 2) = make_float2(s, sq);
   }
-  __threadfence();
   epi_bar();
   if (tid == 0) {
-    red_release_gpu(flag_stat, 1u);
+    fence_acq_rel_gpu();
+    red_relaxed_gpu(flag_stat, 1u);
     wait_counter(flag_stat, 2u * CH_TEAM);
   }
   epi_bar();
@@ -193,13 +193,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS3, 1)
 dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                  const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
-                 const __grid_constant__ CUtensorMap mB2, const __grid_constant__ CUtensorMap mB3, const ChainArgs c) {
+                 const __grid_constant__ CUtensorMap mB2, const __grid_constant__ CUtensorMap mB3,
+                 const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mFFo,
+                 const __grid_constant__ CUtensorMap mQKo, const ChainArgs c) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + CH_A_STAGES * CH_A_BYTES;
-  float* smem_epi = reinterpret_cast<float*>(smem_b + CH_B_STAGES * CH_B_BYTES);
-  float* smem_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem_epi) + EPI_BYTES);
+  uint8_t* smem_epi = smem_b + CH_B_STAGES * CH_B_BYTES;              // 1024-aligned: stage sizes are multiples of 1 KB
+  float* smem_vec = reinterpret_cast<float*>(smem_epi + CH_EPI_BYTES);
+  float* smem_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem_vec) + CH_VEC_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_stat) + CH_STAT_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + CH_A_STAGES;
@@ -207,7 +210,8 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   uint64_t* b_empty = b_full + CH_B_STAGES;
   uint64_t* acc_full = b_empty + CH_B_STAGES;            // [4] one per job
   uint64_t* acc_empty = acc_full + 4;                    // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  uint64_t* res_bar = acc_empty + 4;                     // [8] one per epilogue warp (residual tiles)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -219,9 +223,11 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   if (warp == WARP_TMA && lane == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mA1); prefetch_tmap(&mA2); prefetch_tmap(&mA3);
     prefetch_tmap(&mB0); prefetch_tmap(&mB1); prefetch_tmap(&mB2); prefetch_tmap(&mB3);
+    prefetch_tmap(&mX); prefetch_tmap(&mFFo); prefetch_tmap(&mQKo);
     for (int s = 0; s < CH_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < CH_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int j = 0; j < 4; ++j) { mbar_init(&acc_full[j], 1); mbar_init(&acc_empty[j], 16); }
+    for (int w = 0; w < 8; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                     // the peer's barriers exist before anything signals them
@@ -332,63 +338,74 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue (both CTAs, warps 0..7): this CTA's 128 rows; q = TMEM lane quarter, e = even / odd 32-column blocks =====
+    // ===== epilogue (both CTAs, warps 0..7): this CTA's 128 rows; q = TMEM lane quarter, e = even / odd 32-column blocks.
+    // Row-layout epilogue with TMA tiles (rowgemm_tc_dev.cuh: epilogue_rows_tma) =====
     const int q = warp & 3, e = warp >> 2;
     const int tid = warp * 32 + lane;
     if (tid == 0) stamp(c, 0);
     pdl_wait();
     if (tid == 0) stamp(c, 1);
-    float* stg = smem_epi + warp * (EPI_STAGE_BYTES / 4);
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    EpiTile et;
+    et.res_tile = smem_epi + warp * 8192; et.out_tile = et.res_tile + 4096; et.res_bar = &res_bar[warp]; et.res_phase = 0u;
+    float* s_bias = smem_vec;
+    float* s_gate = smem_vec + 384;
+    // bias / gate of the CTA's column slice -> shared memory (broadcast reads in the epilogue)
+    auto stage_vec = [&](const float* bias, const float* gate, int n0, int n) {
+      epi_bar();                                               // the previous job's readers are done
+      for (int i = tid; i < n; i += 256) {
+        s_bias[i] = __ldg(bias + n0 + i);
+        if (gate) s_gate[i] = __ldg(gate + n0 + i);
+      }
+      epi_bar();
+    };
     TcArgs a;
     a.taps = 1; a.dil = 1; a.center = 0; a.groups = 1; a.M = c.R;
     a.o_bstride = 0; a.o_shift = 0; a.accumulate = 0; a.scale = 1.0f; a.out2 = nullptr; a.f16 = c.f16;
     a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0; a.vt_ld = 0; a.vt_heads = 0;
+    a.out = nullptr; a.ldo = 0; a.o_limit = 0; a.out_bf16 = 0; a.bias = nullptr; a.gate = nullptr; a.res = nullptr;
     int it = 0;
     for (int rb = team; rb < c.nrb; rb += c.teams, ++it) {
       unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
       const uint32_t ph = (uint32_t)it & 1u;
-      EpiPos p;
-      p.sub = lane >> 3; p.c4 = lane & 7;
-      p.t_row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
-      p.obase = 0; p.gshift = 0;
-      float4 res[8];
-      float psum[8], psq[8];
+      const int row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
+      float rsum, rsq;
       // ---- job 0: x += gate_msa * (att @ Wout^T + b_out) ; LN-modulate (mlp) -> n16 ----
       {
         const JobShape js = job_shape(0, c.D, c.FF);
+        const int n0 = slice * js.n_pair;
         a.Cin = js.K; a.N = c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        a.out = c.x; a.ldo = c.D; a.o_limit = (long)c.R * c.D; a.out_bf16 = 0;
-        a.bias = c.b_out; a.gate = c.gate_msa; a.res = c.x;
-        p.n0 = slice * js.n_pair;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { psum[i] = 0.f; psq[i] = 0.f; }
-        if (p.t_row0 < a.M) epi_load_res(a, p, e * 32, res);
+        stage_vec(c.b_out, c.gate_msa, n0, js.n_pair);
+        epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
+        rsum = 0.f; rsq = 0.f;
         mbar_wait(&acc_full[0], ph);
         tc_fence_after();
         if (tid == 0) stamp(c, 8 + 8 * 0 + 4);
-        epilogue_warp<EPI_STD, ACT_NONE, true>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res, psum, psq);
+        epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
+                                                      s_bias, s_gate, rsum, rsq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[0]);
+        epi_tma_drain(lane);
         if (tid == 0) stamp(c, 8 + 8 * 0 + 5);
-        ln_phase(c, rb, (int)rank, slice, 0, psum, psq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
+        ln_phase(c, rb, (int)rank, slice, 0, rsum, rsq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
         if (tid == 0) stamp(c, 8 + 8 * 0 + 7);
       }
       // ---- job 1: ff16 = GELU_tanh(n16 @ Wff1^T + b_ff1) ----
       {
         const JobShape js = job_shape(1, c.D, c.FF);
+        const int n0 = slice * js.n_pair;
         a.Cin = js.K; a.N = c.FF; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        a.out = c.ff16; a.ldo = c.FF; a.o_limit = (long)c.R * c.FF; a.out_bf16 = c.f16 ? 2 : 1;
-        a.bias = c.b_ff1; a.gate = nullptr; a.res = nullptr;
-        p.n0 = slice * js.n_pair;
+        stage_vec(c.b_ff1, nullptr, n0, js.n_pair);
         mbar_wait(&acc_full[1], ph);
         tc_fence_after();
         if (tid == 0) stamp(c, 8 + 8 * 1 + 4);
-        epilogue_warp<EPI_STD, ACT_GELU_TANH, false>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res);
+        epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64,
+                                                          lane, s_bias, nullptr, rsum, rsq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[1]);
+        epi_tma_drain(lane);
         if (tid == 0) stamp(c, 8 + 8 * 1 + 5);
         team_signal(flags + F_FF16, tid);
         if (tid == 0) stamp(c, 8 + 8 * 1 + 7);
@@ -396,40 +413,41 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       // ---- job 2: x += gate_mlp * (ff16 @ Wff2^T + b_ff2) ; LN-modulate (next block's attention / final) -> n16b ----
       {
         const JobShape js = job_shape(2, c.D, c.FF);
+        const int n0 = slice * js.n_pair;
         a.Cin = js.K; a.N = c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        a.out = c.x; a.ldo = c.D; a.o_limit = (long)c.R * c.D; a.out_bf16 = 0;
-        a.bias = c.b_ff2; a.gate = c.gate_mlp; a.res = c.x;
-        p.n0 = slice * js.n_pair;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { psum[i] = 0.f; psq[i] = 0.f; }
-        if (p.t_row0 < a.M) epi_load_res(a, p, e * 32, res);
+        stage_vec(c.b_ff2, c.gate_mlp, n0, js.n_pair);
+        epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
+        rsum = 0.f; rsq = 0.f;
         mbar_wait(&acc_full[2], ph);
         tc_fence_after();
         if (tid == 0) stamp(c, 8 + 8 * 2 + 4);
-        epilogue_warp<EPI_STD, ACT_NONE, true>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res, psum, psq);
+        epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
+                                                      s_bias, s_gate, rsum, rsq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[2]);
+        epi_tma_drain(lane);
         if (tid == 0) stamp(c, 8 + 8 * 2 + 5);
-        ln_phase(c, rb, (int)rank, slice, 1, psum, psq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
+        ln_phase(c, rb, (int)rank, slice, 1, rsum, rsq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
         if (tid == 0) stamp(c, 8 + 8 * 2 + 7);
       }
-      // ---- job 3: q | k | v of the next block: bias + RoPE -> qk16, V transposed -> vt_out ----
+      // ---- job 3: q | k | v of the next block: bias + RoPE -> qk16 (TMA tiles), V transposed -> vt_out ----
       if (c.has_qkv) {
         const JobShape js = job_shape(3, c.D, c.FF);
+        const int n0 = slice * js.n_pair;
         a.Cin = js.K; a.N = 3 * c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        a.out = c.qk16; a.ldo = 2 * c.D; a.o_limit = (long)c.R * 2 * c.D + 3 * c.D; a.out_bf16 = c.f16 ? 2 : 1;
-        a.bias = c.b_qkv; a.gate = nullptr; a.res = nullptr;
         a.rope_cs = c.rope_cs; a.rope_cols = 2 * c.D; a.rope_rows = c.rope_rows;
         a.vt_out = c.vt_out; a.vt_col0 = 2 * c.D; a.vt_ld = c.vt_ld; a.vt_heads = c.vt_heads;
-        p.n0 = slice * js.n_pair;
+        stage_vec(c.b_qkv, nullptr, n0, js.n_pair);
         mbar_wait(&acc_full[3], ph);
         tc_fence_after();
         if (tid == 0) stamp(c, 8 + 8 * 3 + 4);
-        epilogue_warp<EPI_ROPE, ACT_NONE, false>(a, p, tmem_base + (uint32_t)js.tmem_col + lane_sel, 0u, 1, stg, lane, 0, e * 32, 64, res);
+        epilogue_rows_tma<TK_ROPE16, ACT_NONE, false>(a, &mQKo, nullptr, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
+                                                      s_bias, nullptr, rsum, rsq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[3]);
+        epi_tma_drain(lane);
         if (tid == 0) stamp(c, 8 + 8 * 3 + 5);
         a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0;
       }
@@ -498,8 +516,14 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
                              d.has_qkv ? (uint32_t)(3 * d.D / (4 * CH_TEAM)) : (uint32_t)(d.D / (2 * CH_TEAM))};
   for (int j = 0; j < 4; ++j)
     tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc, b_box[j]);
+  // epilogue tiles: x (fp32, residual in / result out), ff16 and q|k (16 bit, result out), 32 rows x 32 columns each
+  CUtensorMap mX, mFFo, mQKo;
+  tc_encode_map2d(&mX, d.x, 4, (uint64_t)d.D, (uint64_t)d.R, (uint64_t)d.D, 32, 32);
+  tc_encode_map2d(&mFFo, d.ff16, 2, (uint64_t)d.FF, (uint64_t)d.R, (uint64_t)d.FF, 32, 32);
+  if (d.has_qkv) tc_encode_map2d(&mQKo, d.qk16, 2, (uint64_t)2 * d.D, (uint64_t)d.R, (uint64_t)2 * d.D, 32, 32);
+  else mQKo = mFFo;
   launch_pdl(dit_chain_kernel, dim3((unsigned)(c.teams * CH_TEAM * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
-             mB[0], mB[1], mB[2], mB[3], c);
+             mB[0], mB[1], mB[2], mB[3], mX, mFFo, mQKo, c);
   B2_LAUNCH_CHECK();
   count_launch();
 }

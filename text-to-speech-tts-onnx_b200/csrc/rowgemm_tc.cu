@@ -489,6 +489,23 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
   if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
 
+void tc_encode_map2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t box0,
+                     uint32_t box1) {
+  B2_CHECK(elem_bytes == 2 || elem_bytes == 4, "tc_encode_map2d: element size");
+  B2_CHECK(((uintptr_t)base & 15) == 0 && (ld1 * elem_bytes) % 16 == 0, "TMA base / stride must be 16-byte aligned");
+  const uint32_t inner = box0 * (uint32_t)elem_bytes;
+  B2_CHECK(inner == 128 || inner == 64, "tc_encode_map2d: box rows must be 128 or 64 bytes");
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld1 * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled (2-D) failed with CUresult " + std::to_string((int)r));
+}
+
 namespace {
 
 __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n, int f16) {

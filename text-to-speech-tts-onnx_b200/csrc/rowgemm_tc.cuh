@@ -28,6 +28,12 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
                    uint32_t box1);
 
 // f16 != 0: the 16-bit side is IEEE fp16 instead of bf16 (same storage type)
+// 2-D TMA map for epilogue tiles: dims {d0 (contiguous), d1} of `elem_bytes`-wide elements (2 or 4), row stride ld1 elements,
+// box {box0, box1} with box0 * elem_bytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B); rows / columns beyond the dims are
+// zero-filled on load and clipped on store
+void tc_encode_map2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t box0,
+                     uint32_t box1);
+
 void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s, int f16 = 0);
 void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s, int f16 = 0);
 // (rows, C) fp32 -> (rows, ldo) bf16 with zero-filled padding columns

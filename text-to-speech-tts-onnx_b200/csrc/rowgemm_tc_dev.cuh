@@ -285,6 +285,156 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
   }
 }
 
+// =============================================================================================
+// Row-layout epilogue with TMA tiles (dit_chain.cu). The transposing epilogue above spends ~600 instructions per 32x32
+// block on address arithmetic, bounds tests, the shared-memory transpose and 16 + 8 global accesses per lane -- 2.3 us per
+// block when the tile's epilogue is exposed (one tile per CTA: chain timeline, profiles/r02). Here a lane keeps the
+// accumulator's native layout (lane = row, 32 consecutive columns in registers): bias / gate come from a shared-memory copy
+// (broadcast reads), the fp32 residual tile is fetched by the TMA unit into a 128B-swizzled tile (8 conflict-free LDS.128
+// per lane), the result goes into a swizzled staging tile (8 or 4 STS.128) and ONE thread hands it to the TMA unit, which does
+// the coalescing and the row clipping. LayerNorm statistics are thread-local sums (a lane owns a row): no shuffles.
+// =============================================================================================
+struct EpiTile {
+  uint8_t* res_tile;      // 4 KB, 1024-byte aligned: residual tile [32 rows][32 fp32], SWIZZLE_128B
+  uint8_t* out_tile;      // 4 KB, 1024-byte aligned: result tile, fp32 [32][128 B] SWIZZLE_128B or 16-bit [32][64 B] SWIZZLE_64B
+  uint64_t* res_bar;      // mbarrier (count 1) the residual tiles complete on
+  uint32_t res_phase;     // parity of the next residual tile to wait for
+};
+enum TileKind : int { TK_RES_F32 = 0, TK_ACT16 = 1, TK_ROPE16 = 2 };
+
+// lane 0: fetch the residual tile of the 32-column block at global column n, rows row0 .. row0 + 31
+__device__ __forceinline__ void epi_tma_fetch_res(const CUtensorMap* map_res, EpiTile& et, int n, int row0, int lane) {
+  if (lane == 0) {
+    mbar_expect_tx(et.res_bar, 32u * 128u);
+    tma_load_2d(et.res_tile, map_res, et.res_bar, n, row0);
+  }
+}
+// the warp's stores have been performed (global memory holds the tiles); orders them before generic-proxy reads that follow a
+// barrier (LN pass 2) and before the team counters
+__device__ __forceinline__ void epi_tma_drain(int lane) {
+  if (lane == 0) {
+    bulk_wait0();
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
+  __syncwarp();
+}
+
+// One warp, rows row0 .. row0 + 31 (TMEM lanes of `taddr`), blocks cb = cb_first, cb_first + cb_step, ... < a.BN of the CTA's
+// column slice starting at global column n0. s_bias / s_gate: shared-memory copies of bias[n0 ..), gate[n0 ..) (s_gate may be
+// null). TK_RES_F32: out = res + gate * (acc + bias) as fp32 (the residual tile of the FIRST block must already be in flight:
+// epi_tma_fetch_res); TK_ACT16: out = act(acc + bias) as 16 bit; TK_ROPE16: q | k columns roped as 16 bit, V columns through
+// the transposed scalar path of epilogue_warp.
+template <int TK, int ACT, bool STATS>
+__device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
+                                                  uint32_t taddr, int row0, int n0, int cb_first, int cb_step, int lane,
+                                                  const float* s_bias, const float* s_gate, float& rsum, float& rsq) {
+  const uint32_t out_s = smem_u32(et.out_tile), res_s = smem_u32(et.res_tile);
+  const uint32_t bias_s = smem_u32(s_bias), gate_s = s_gate ? smem_u32(s_gate) : 0u;
+  const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
+  const uint32_t row64 = (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+  const int t = row0 + lane;
+#pragma unroll 1
+  for (int cb = cb_first; cb < a.BN; cb += cb_step) {
+    const int n = n0 + cb;
+    if (n >= a.N) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + (uint32_t)cb, v);
+    uint4 cs[8];
+    const bool rope = TK == TK_ROPE16 && n < a.rope_cols;
+    if (rope) {           // this row's (cos, sin) pairs of the block's 32 columns: one 128-byte line, fetched under the TMEM load
+      const __half2* cp = a.rope_cs + (long)((t < a.M ? t : 0) % a.rope_rows) * 64 + (n & 63);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = __ldg(reinterpret_cast<const uint4*>(cp) + k);
+    }
+    if (TK == TK_RES_F32) { mbar_wait(et.res_bar, et.res_phase); et.res_phase ^= 1u; }
+    tmem_ld_wait();
+
+    if (TK == TK_ROPE16 && a.vt_out != nullptr && n >= a.vt_col0) {
+      // V columns: written transposed, vt[(sequence*heads + h)*64 + d][t]; consecutive lanes are consecutive t
+      if (t < a.M) {
+        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
+          const int cv = n + k * 4 - a.vt_col0;
+          uint16_t* o16 = reinterpret_cast<uint16_t*>(a.vt_out) + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
+          o16[0] = pack16(__uint_as_float(v[k * 4 + 0]) + bi.x, a.f16);
+          o16[(long)a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 1]) + bi.y, a.f16);
+          o16[2L * a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 2]) + bi.z, a.f16);
+          o16[3L * a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 3]) + bi.w, a.f16);
+        }
+      }
+      continue;
+    }
+
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
+      f[k * 4 + 0] = __uint_as_float(v[k * 4 + 0]) + bi.x; f[k * 4 + 1] = __uint_as_float(v[k * 4 + 1]) + bi.y;
+      f[k * 4 + 2] = __uint_as_float(v[k * 4 + 2]) + bi.z; f[k * 4 + 3] = __uint_as_float(v[k * 4 + 3]) + bi.w;
+    }
+    if (TK == TK_ACT16 && ACT != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = act_fast<ACT>(f[i]);
+    }
+    if (TK == TK_RES_F32) {
+      if (s_gate) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 g = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
+          f[k * 4 + 0] *= g.x; f[k * 4 + 1] *= g.y; f[k * 4 + 2] *= g.z; f[k * 4 + 3] *= g.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 rr = lds128(res_s + row128 + (((uint32_t)k ^ sw128) << 4));
+        f[k * 4 + 0] += rr.x; f[k * 4 + 1] += rr.y; f[k * 4 + 2] += rr.z; f[k * 4 + 3] += rr.w;
+      }
+      __syncwarp();                                            // every lane has read the residual tile: fetch the next one
+      if (cb + cb_step < a.BN && n + cb_step < a.N) epi_tma_fetch_res(map_res, et, n + cb_step, row0, lane);
+    }
+    if (rope) {           // (x0, x1) -> x * cos + (-x1, x0) * sin, interleaved pairs (F5 modules.py:421-430)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t w[4] = {cs[k].x, cs[k].y, cs[k].z, cs[k].w};
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const float2 c0 = __half22float2(*reinterpret_cast<const __half2*>(&w[2 * h2]));
+          const float2 c1 = __half22float2(*reinterpret_cast<const __half2*>(&w[2 * h2 + 1]));
+          const float x0 = f[k * 4 + 2 * h2], x1 = f[k * 4 + 2 * h2 + 1];
+          f[k * 4 + 2 * h2] = x0 * c0.x - x1 * c0.y;
+          f[k * 4 + 2 * h2 + 1] = x1 * c1.x + x0 * c1.y;
+        }
+      }
+    }
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { rsum += f[i]; rsq = fmaf(f[i], f[i], rsq); }
+    }
+    if (lane == 0) bulk_wait_read0();                          // the previous block's store has read the staging tile
+    __syncwarp();
+    if (TK == TK_RES_F32) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sts128(out_s + row128 + (((uint32_t)k ^ sw128) << 4), __float_as_uint(f[k * 4]), __float_as_uint(f[k * 4 + 1]),
+               __float_as_uint(f[k * 4 + 2]), __float_as_uint(f[k * 4 + 3]));
+    } else {
+      const int half = a.f16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sts128(out_s + row64 + (((uint32_t)k ^ sw64) << 4), pack16x2(f[k * 8], f[k * 8 + 1], half), pack16x2(f[k * 8 + 2], f[k * 8 + 3], half),
+               pack16x2(f[k * 8 + 4], f[k * 8 + 5], half), pack16x2(f[k * 8 + 6], f[k * 8 + 7], half));
+    }
+    fence_proxy_async();                                       // generic-proxy writes of the staging tile -> async proxy
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map_out, et.out_tile, n, row0);
+      bulk_commit();
+    }
+  }
+}
+
 // The KS x NH MMAs of one (64-channel chunk, tap): K steps outermost, 128-row halves innermost. KS = 4 for a full chunk,
 // 2 / 3 for the ragged last chunk of the thin BigVGAN stages (C = 24, 48, 96), where the generic loop was the critical path.
 template <int NH, int KS>

@@ -146,6 +146,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// ---- 2-D TMA tiles for the epilogues: residual tiles in, result tiles out (the TMA unit does the coalescing) -----------------
+// load a box into this CTA's shared memory; completion (bytes) on this CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// store a box from shared memory (rows / columns outside the tensor are clipped); joins the thread's current bulk group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (the staging tile may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have COMPLETED (their global writes are performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- CTA pair (cta_group::2): two SMs of one TPC run ONE M=256 MMA; each holds 128 rows of A / D and half of B ----------
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
 __device__ __forceinline__ uint32_t cluster_ctarank() {
