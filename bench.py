@@ -324,18 +324,18 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
     conv, aa = _sum("bigvgan.resconv"), _sum("bigvgan.aa_snake.")
     if conv["ms"] > 0:
         ach = work["flops_resconv"] / (conv["ms"] / 1e3) / 1e12
-        kern = "rowgemm_tc3_kernel (108 resblock convs)" if prec == capi.BF16 else "rowgemm_f32_kernel (SIMT parity engine)"
+        kern = "rowgemm_f32_kernel (SIMT parity engine)" if prec == capi.F32 else "rowgemm_tc3 / tc2sm kernels (108 resblock convs)"
         res["roofline"] = {"bound": "tensor", "kernel": kern, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / pk["bf16_tflops_sustained"],
-                           "traffic": ncu_traffic("bigvgan.resconv") if prec == capi.BF16 else None,
+                           "traffic": ncu_traffic("bigvgan.resconv") if prec != capi.F32 else None,
                            "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                            "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
                            "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
     if aa["ms"] > 0:
-        per_elem = 4.0 if prec == capi.BF16 else 8.0          # bf16 in + bf16 out on the fast path
+        per_elem = 4.0 if prec != capi.F32 else 8.0          # 16 bit in + 16 bit out on the fast path
         gbs = work["aa_elems"] * per_elem / (aa["ms"] / 1e3) / 1e9
         res["roofline_hbm"] = {"bound": "hbm", "kernel": "aa_snake_kernel", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                               "frac": gbs / pk["hbm_gbs"], "traffic": ncu_traffic("bigvgan.aa_snake") if prec == capi.BF16 else None,
+                               "frac": gbs / pk["hbm_gbs"], "traffic": ncu_traffic("bigvgan.aa_snake") if prec != capi.F32 else None,
                                "avg_launch_ms": aa["ms"] / max(aa["launches"], 1)}
     return res
 

@@ -146,6 +146,9 @@ def test_f5_bigvgan_pipeline_vs_reference_golden(f5_engine, bigvgan_engine, gf):
         assert snr_db(gf["f5_pcm"].reshape(-1), voc[u]) >= 55.0
         direct = bigvgan_engine.bigvgan_run(np.ascontiguousarray(mel[u:u + 1, ref_len:, :].transpose(0, 2, 1)), precision=capi.F16)
         np.testing.assert_array_equal(direct.reshape(-1), wav[u])
+    # two copies of one utterance in a batch sit at different offsets of the 256-row blocks / tiles: a row's result must not
+    # depend on where it sits (the fused LayerNorm spells out its rounding steps for exactly this reason, dit_chain.cu)
+    np.testing.assert_array_equal(mel[0], mel[1])
     np.testing.assert_array_equal(wav[0], wav[1])
     wav1 = f5_engine.f5_bigvgan_pipeline(au[:1], tx[:1], N, nz[:1], precision=capi.F16)
     assert snr_db(wav[0], wav1[0]) >= 60.0          # batch of two vs one: other GEMM tile schedules, same rows

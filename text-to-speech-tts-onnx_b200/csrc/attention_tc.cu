@@ -20,7 +20,10 @@
 // Shared memory 112 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA phases.
 #include "attention_tc.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "rowgemm_tc.cuh"
 #include "tc_ptx.cuh"
@@ -47,7 +50,17 @@ struct AttnArgs {
   __nv_bfloat16* out;
   int ldo;
   int f16;            // q, k, v, P and out are IEEE fp16 instead of bf16
+  unsigned long long* trace;   // debug: [CTA][64] %globaltimer stamps (B200TTS_ATTN_TRACE=<file>, tools/attn_trace.py)
 };
+
+__device__ __forceinline__ void astamp(const AttnArgs& a, int slot) {
+  if (a.trace != nullptr && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    a.trace[cta * 64 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ uint32_t pk16(float x, float y, int half) {
   if (half) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
@@ -134,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   pdl_trigger();                                          // after the TMEM allocation (common.cuh)
   pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) astamp(a, 0);
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // O_a: +128..191, O_b: +192..255
 
   if (warp == WARP_TMA) {
@@ -169,9 +183,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_S, dQ + (uint64_t)(2 * k), dK + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
-        umma_commit(&k_empty[s]);                                   // the K tile is free once this MMA has read it
+        umma_commit(&k_empty[s]);
+        astamp(a, 4 + 4 * j + 0);                                   // the K tile is free once this MMA has read it
       };
       mbar_wait(q_full, 0);
+      astamp(a, 1);
       issue_s(0);
       for (int j = 0; j < nblocks; ++j) {
         if (j + 1 < nblocks) issue_s(j + 1);                        // runs under the exponentials of block j
@@ -188,6 +204,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         }
         umma_commit(pv_done);
         umma_commit(&v_empty[s]);
+        astamp(a, 4 + 4 * j + 1);
       }
     }
   } else {
@@ -205,6 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       const int kvalid = a.N - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
+      if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 2);
       uint32_t v[2][32];
       tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64), v[0]);
       tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64 + 32), v[1]);
@@ -275,10 +293,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       tc_fence_before();                 // order our TMEM accesses before the MMA warp's next writes
       fence_proxy_async();               // make the generic-proxy smem writes of P visible to the tensor core
       mbar_arrive(p_full);
+      if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 3);
     }
     // ---- merge the two key halves of each row, normalise, store ----
     mbar_wait(pv_done, (uint32_t)(nblocks - 1) & 1u);
     tc_fence_after();
+    if (threadIdx.x == 0) astamp(a, 2);
     stat[(g * 2 + 0) * BQ + r] = m_ref;
     stat[(g * 2 + 1) * BQ + r] = l_run;
     softmax_bar();
@@ -322,6 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     }
   }
 
+  if (threadIdx.x == 0) astamp(a, 3);
   tc_fence_before();
   __syncthreads();
   if (warp == WARP_MMA) {
@@ -344,12 +365,30 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
-  AttnArgs a{N, H, out, H * HD, f16};
+  AttnArgs a{N, H, out, H * HD, f16, nullptr};
+  static DevBuf<unsigned long long> trace_buf;
+  const char* trace_path = getenv("B200TTS_ATTN_TRACE");
+  const size_t ncta = (size_t)ceil_div(N, BQ) * H * S;
+  if (trace_path) {
+    trace_buf.reserve(ncta * 64);
+    B2_CUDA(cudaMemsetAsync(trace_buf.p, 0, ncta * 64 * 8, stream));
+    a.trace = trace_buf.p;
+  }
   B2_CHECK(S <= 65535, "attention_tc: too many sequences");
   dim3 grid(ceil_div(N, BQ), H, S);
   launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
   B2_LAUNCH_CHECK();
   count_launch();
+  if (trace_path) {                                        // debug only: dump the stamps of this launch
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      std::vector<unsigned long long> h(ncta * 64);
+      B2_CUDA(cudaMemcpyAsync(h.data(), trace_buf.p, h.size() * 8, cudaMemcpyDeviceToHost, stream));
+      B2_CUDA(cudaStreamSynchronize(stream));
+      if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
+  }
 }
 
 }  // namespace b200tts

@@ -1,29 +1,31 @@
 // One DiT block's row-local chain as ONE persistent tcgen05 kernel (sm_100a).
 //
-// Why. For one utterance (R = 2 x 1126 rows) every dense layer of the DiT is a 5..14 GFLOP GEMM: as separate launches each
-// one is a 15-25 us kernel of which 2-6 us are tensor work -- the rest is launch / fill / drain, and the LayerNorm-modulate
-// between them is a kernel of its own (profiles/r01: GEMMs at 0.27 of the tensor peak, 1 395 rownorm launches per utterance).
-// But everything between two attention calls is local to a block of rows:
+// Why. Everything between two attention calls is local to a block of rows:
 //     att rows -> out-proj (+gate, +residual) -> LN-modulate -> ff1 (GELU) -> ff2 (+gate, +residual) -> LN-modulate -> q|k|v
-// (modules.py:599-613; only attention itself mixes rows). So a TEAM of 8 CTA pairs owns a 256-row block and walks that
-// chain without leaving the SMs: pair s of the team computes output columns [n/8 * s, n/8 * (s+1)) of every GEMM with
-// tcgen05.mma.cta_group::2 (M = 256: each CTA holds 128 rows of A / D and half of the pair's weight slice), the activations
-// between GEMMs go through L2 (written by the epilogue warps, fetched back by TMA), and the hand-offs inside a team are
-// release / acquire counters in global memory -- no grid-wide barrier, no kernel boundary. 9 teams x 8 pairs = 144 CTAs for
-// one utterance; for a batch the teams stride over the row blocks.
+// (modules.py:599-613; only attention itself mixes rows). As separate launches each of these is a kernel whose launch, fill,
+// drain and fp32-residual epilogue are exposed, with a LayerNorm kernel between them (profiles/r01: GEMMs at 0.27 of the tensor
+// peak for one utterance, 1 395 rownorm launches). Here a TEAM of T CTA pairs owns a 256-row block and walks that chain without
+// leaving the SMs: pair s of the team computes output columns [n/T * s, n/T * (s+1)) of every GEMM with
+// tcgen05.mma.cta_group::2 (M = 256: each CTA holds 128 rows of A / D and half of the pair's weight slice), in sub-tiles of
+// <= 256 columns whose accumulators alternate between the two halves of TMEM (the epilogue of one sub-tile runs under the main
+// loop of the next). The activations between GEMMs go through L2 (written by the epilogue warps, fetched back by TMA), and the
+// hand-offs inside a team are release / acquire counters in global memory -- no grid-wide barrier, no kernel boundary.
+//   T = 8 for one utterance (9 row blocks x 8 pairs = 144 CTAs: every GEMM is one sub-tile per pair),
+//   T = 1 for a batch of 8 (71 row blocks, one pair each: 4 / 8 / 4 / 12 sub-tiles per GEMM, hand-offs stay inside the pair).
 //
 // Per CTA: 11 warps as in rowgemm_tc.cu (0-7 epilogue, 8 A producer, 9 MMA issuer (leader CTA only), 10 B producer).
-//   job 0  out  : A = att16  K = D    pair columns 128  TMEM [0, 128)      epilogue: x += gate_msa * (acc + b)   + LN statistics
-//   job 1  ff1  : A = n16    K = D    pair columns 256  TMEM [128, 384)    epilogue: GELU_tanh(acc + b) -> ff16
-//   job 2  ff2  : A = ff16   K = FF   pair columns 128  TMEM [384, 512)    epilogue: x += gate_mlp * (acc + b)   + LN statistics
-//   job 3  qkv  : A = n16b   K = D    pair columns 384  TMEM [128, 512)    epilogue: bias + interleaved RoPE, V transposed
-// LayerNorm (no affine, eps 1e-6, modules.py:296) of a row needs all 1024 columns = all 8 pairs: each CTA reduces (sum, sum
-// of squares) of its 128 columns in the epilogue it already runs, publishes them (8 partial pairs per row), waits for its
-// team, then normalises + modulates its own 128 x 128 slab of x (re-read from L2) into the 16-bit A operand of the next GEMM.
-// The weight stream never waits for anything (the B producer runs ahead across job boundaries and does not even wait for
-// the previous kernel: weights are constants), so each hand-off costs the epilogue + one L2 round trip, not a pipeline refill.
+//   job 0  out  : A = att16  K = D    epilogue: x += gate_msa * (acc + b)   + LN statistics
+//   job 1  ff1  : A = n16    K = D    epilogue: GELU_tanh(acc + b) -> ff16
+//   job 2  ff2  : A = ff16   K = FF   epilogue: x += gate_mlp * (acc + b)   + LN statistics
+//   job 3  qkv  : A = n16b   K = D    epilogue: bias + interleaved RoPE, V transposed   (the NEXT block's projections)
+// LayerNorm (no affine, eps 1e-6, modules.py:296) of a row needs all 1024 columns = all T pairs: each CTA reduces (sum, sum of
+// squares) of its columns in the epilogue it already runs (thread-local: a lane owns a row), publishes them (T partial pairs
+// per row), waits for its team, then normalises + modulates its own [128 rows] x [D / T columns] slab of x (re-read from L2)
+// into the 16-bit A operand of the next GEMM. The weight stream never waits for anything (the B producer runs ahead across job
+// boundaries and does not even wait for the previous kernel: weights are constants).
 #include "dit_chain.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "rowgemm_tc_dev.cuh"
@@ -32,22 +34,22 @@ namespace b200tts {
 
 namespace {
 
-constexpr int CH_A_STAGES = 4, CH_B_STAGES = 3;
+constexpr int CH_A_STAGES = 4, CH_B_STAGES = 4;
 constexpr int CH_A_BYTES = 128 * 128;            // 128 rows x 64 channels x 2 B
-constexpr int CH_B_BYTES = 192 * 128;            // up to 192 weight rows per CTA and chunk (q|k|v: two 96-row boxes)
+constexpr int CH_B_BYTES = 128 * 128;            // up to 128 weight rows per CTA and chunk (half of a 256-column sub-tile)
 constexpr int CH_STAT_BYTES = 2 * 128 * 2 * 4;   // [column half e][row][sum, sum of squares]
 constexpr int CH_EPI_BYTES = 8 * 8192;           // per epilogue warp: residual tile + result tile (4 KB each, rowgemm_tc_dev.cuh: EpiTile)
-constexpr int CH_VEC_BYTES = 2 * 384 * 4;        // bias / gate of the CTA's column slice
-constexpr int CH_TEAM = 8;                       // CTA pairs per row block
+constexpr int CH_VEC_BYTES = 2 * 256 * 4;        // bias / gate of the current sub-tile
+constexpr int CH_MAX_TEAM = 8;                   // statistics slots per row
 constexpr int CH_ROWS = 256;                     // rows per block (one M = 256 pair tile)
 constexpr int CH_NFLAGS = 8;
 enum { F_STAT1 = 0, F_N16 = 1, F_FF16 = 2, F_STAT2 = 3, F_N16B = 4 };
-constexpr int CH_BAR_BYTES = (2 * CH_A_STAGES + 2 * CH_B_STAGES + 8 + 8) * 8 + 16;
+constexpr int CH_BAR_BYTES = (2 * CH_A_STAGES + 2 * CH_B_STAGES + 4 + 8) * 8 + 16;
 constexpr int CH_SMEM = CH_A_STAGES * CH_A_BYTES + CH_B_STAGES * CH_B_BYTES + CH_EPI_BYTES + CH_VEC_BYTES + CH_STAT_BYTES + CH_BAR_BYTES + 1024;
 static_assert(CH_SMEM <= 227 * 1024, "dit_chain: shared memory budget");
 
 struct ChainArgs {
-  int R, nrb, teams, has_qkv, f16, D, FF;
+  int R, nrb, teams, team, has_qkv, f16, D, FF;      // team = CTA pairs per row block (1, 2, 4 or 8)
   float* x;
   __nv_bfloat16 *n16, *ff16, *n16b;
   const float *b_out, *gate_msa, *shift_mlp, *scale_mlp, *b_ff1, *b_ff2, *gate_mlp, *shift_nxt, *scale_nxt, *b_qkv;
@@ -63,8 +65,7 @@ struct ChainArgs {
 
 // ---- team hand-offs: monotonic counters in global memory (zero at kernel start), one per (row block, event) -----------------
 // Polling is RELAXED (an acquire load costs a CCTL.IVALL -- a full L1 invalidation of the SM -- per poll: ncu r02a counted
-// 92 865 of them in one launch, thrashing the L1 lines the epilogue warps of the same SM live on); one acquire fence follows
-// the poll that succeeds.
+// 92 865 of them in one launch); one acquire fence follows the poll that succeeds.
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -95,9 +96,9 @@ __device__ __forceinline__ void stamp(const ChainArgs& c, int slot) {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// The eight epilogue warps of a CTA have finished writing a slab: make it visible to the team and count this CTA in. The CTA
-// barrier orders every warp's stores before thread 0's fence, and a gpu-scope fence is cumulative over what its thread has
-// observed (the grid-barrier idiom: bar.sync; thread 0: fence + atomic) -- one MEMBAR per CTA instead of 256.
+// The eight epilogue warps of a CTA have finished writing a slab (their TMA stores are drained): make it visible to the team
+// and count this CTA in. The CTA barrier orders every warp's stores before thread 0's fence, and a gpu-scope fence is
+// cumulative over what its thread has observed (the grid-barrier idiom) -- one MEMBAR per CTA instead of 256.
 __device__ __forceinline__ void team_signal(unsigned* flag, int tid) {
   epi_bar();
   if (tid == 0) {
@@ -107,18 +108,25 @@ __device__ __forceinline__ void team_signal(unsigned* flag, int tid) {
   }
 }
 
-struct JobShape { int K, n_pair, nsub, sub_n, tmem_col, b_rows; };
-__device__ __forceinline__ JobShape job_shape(int j, int D, int FF) {
-  switch (j) {
-    case 0: return JobShape{D, D / CH_TEAM, 1, D / CH_TEAM, 0, D / (2 * CH_TEAM)};
-    case 1: return JobShape{D, FF / CH_TEAM, 1, FF / CH_TEAM, 128, FF / (2 * CH_TEAM)};
-    case 2: return JobShape{FF, D / CH_TEAM, 1, D / CH_TEAM, 384, D / (2 * CH_TEAM)};
-    default: return JobShape{D, 3 * D / CH_TEAM, 2, 3 * D / (2 * CH_TEAM), 128, 3 * D / (4 * CH_TEAM)};
-  }
+// Job j of the chain for a team of `team` pairs: the pair's n_pair output columns are walked in nsubt sub-tiles of w columns
+// (one M = 256, N = w accumulator each; b_rows = w / 2 weight rows per CTA and 64-channel chunk).
+struct JobShape { int K, N, n_pair, w, nsubt, b_rows; };
+__device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int team) {
+  JobShape s;
+  s.K = j == 2 ? FF : D;
+  s.N = j == 0 ? D : j == 1 ? FF : j == 2 ? D : 3 * D;
+  s.n_pair = s.N / team;
+  s.w = s.n_pair <= 256 ? s.n_pair : (s.n_pair % 256 == 0 ? 256 : 192);
+  s.nsubt = s.n_pair / s.w;
+  s.b_rows = s.w / 2;
+  return s;
 }
 
-// LayerNorm statistics + modulation of this CTA's [128 rows] x [128 columns at col0] slab of x (all 256 epilogue threads).
+// LayerNorm statistics + modulation of this CTA's [128 rows] x [D / team columns] slab of x (all 256 epilogue threads).
 //   rsum / rsq : this lane's row sums over the warp's column blocks (epilogue_rows_tma<.., STATS>)
+// Order matters for latency (loaded L2 round trips cost ~1 us here: the weight stream keeps the SM's memory queues deep):
+// the slab is this CTA's own output, so its first 128 columns are fetched BEFORE waiting for the team's statistics, and each
+// later pass issues all 16 row loads of a lane before its first use.
 __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind, float rsum, float rsq,
                                          const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
                                          unsigned* flag_ready, float* st, int warp, int lane) {
@@ -127,65 +135,74 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
   st[(e * 128 + q * 32 + lane) * 2 + 0] = rsum;                 // the row-layout epilogue leaves a row's sums in one lane
   st[(e * 128 + q * 32 + lane) * 2 + 1] = rsq;
   epi_bar();
-  float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_TEAM * 2);
+  float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
   if (tid < 128) {
     const float s = st[tid * 2] + st[(128 + tid) * 2], sq = st[tid * 2 + 1] + st[(128 + tid) * 2 + 1];
-    *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_TEAM + slice) * 2) = make_float2(s, sq);
+    *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_MAX_TEAM + slice) * 2) = make_float2(s, sq);
   }
   epi_bar();
-  if (tid == 0) {
+  if (tid == 0) {                                              // publish first: the team waits for the slowest member
     fence_acq_rel_gpu();
     red_relaxed_gpu(flag_stat, 1u);
-    wait_counter(flag_stat, 2u * CH_TEAM);
   }
+  epi_tma_drain(lane);                                         // this warp's x tiles are in global memory (under the exchange)
   epi_bar();
-  if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
-  // pass 2: warp w normalises rows [16w, 16w + 16) of the slab; lane l owns columns col0 + 4l .. 4l + 3. All loads of the
-  // 16 rows are issued before the first use (one L2 round trip for the statistics, one for x, not one per row).
-  const int col = slice * (c.D / CH_TEAM) + lane * 4;
-  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
-  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
+  // warp w normalises rows [16w, 16w + 16) of the slab, 128 columns per pass (lane l: columns 4l .. 4l + 3)
+  const int n_slab = c.D / c.team;
   const float inv_d = 1.0f / (float)c.D;
   const long grow0 = (long)rb * CH_ROWS + rank * 128 + warp * 16;
+  const int col0 = slice * n_slab + lane * 4;
+  float4 xv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    xv[j] = grow0 + j < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + (grow0 + j) * c.D + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) wait_counter(flag_stat, 2u * (unsigned)c.team);
+  epi_bar();
+  if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
   float2 pr[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k)       // lane = (row k*4 + lane/8, slot lane%8)
-    pr[k] = __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_TEAM + (lane & 7)) * 2));
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    float4 xv[8];
+    pr[k] = (lane & 7) < c.team
+                ? __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_MAX_TEAM + (lane & 7)) * 2))
+                : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long g = grow0 + half * 8 + j;
-      xv[j] = g < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + g * c.D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      pr[k].x += __shfl_xor_sync(0xffffffffu, pr[k].x, o);
+      pr[k].y += __shfl_xor_sync(0xffffffffu, pr[k].y, o);
     }
-    if (half == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          pr[k].x += __shfl_xor_sync(0xffffffffu, pr[k].x, o);
-          pr[k].y += __shfl_xor_sync(0xffffffffu, pr[k].y, o);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int jj = half * 8 + j;
-      const float px = (jj >> 2) == 0 ? pr[0].x : (jj >> 2) == 1 ? pr[1].x : (jj >> 2) == 2 ? pr[2].x : pr[3].x;
-      const float py = (jj >> 2) == 0 ? pr[0].y : (jj >> 2) == 1 ? pr[1].y : (jj >> 2) == 2 ? pr[2].y : pr[3].y;
-      const float sum = __shfl_sync(0xffffffffu, px, (jj & 3) * 8), sq = __shfl_sync(0xffffffffu, py, (jj & 3) * 8);
-      const long g = grow0 + jj;
-      if (g >= c.R) continue;                                   // warp-uniform
-      const float mean = sum * inv_d;
-      const float var = fmaxf(sq * inv_d - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-6f);
-      const float4 v = xv[j];
-      const float y0 = (v.x - mean) * rstd * (1.0f + sc.x) + sh.x, y1 = (v.y - mean) * rstd * (1.0f + sc.y) + sh.y;
-      const float y2 = (v.z - mean) * rstd * (1.0f + sc.z) + sh.z, y3 = (v.w - mean) * rstd * (1.0f + sc.w) + sh.w;
-      *reinterpret_cast<uint2*>(dst + g * c.D + col) = pack16x4(y0, y1, y2, y3, c.f16);
-    }
+    const float mean = __fmul_rn(pr[k].x, inv_d);
+    pr[k].x = mean;                                            // -> (mean, rstd) of row k*4 + lane/8
+    pr[k].y = rsqrtf(__fadd_rn(fmaxf(__fsub_rn(__fmul_rn(pr[k].y, inv_d), __fmul_rn(mean, mean)), 0.f), 1e-6f));
   }
+#pragma unroll 1
+  for (int cg = 0; cg < n_slab; cg += 128) {
+    const int col = col0 + cg;
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
+    const float4 sc1 = make_float4(1.0f + sc.x, 1.0f + sc.y, 1.0f + sc.z, 1.0f + sc.w);
+    uint2 yo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 ms = j < 4 ? pr[0] : j < 8 ? pr[1] : j < 12 ? pr[2] : pr[3];
+      const float mean = __shfl_sync(0xffffffffu, ms.x, (j & 3) * 8), rstd = __shfl_sync(0xffffffffu, ms.y, (j & 3) * 8);
+      const float4 v = xv[j];
+      // explicit rounding steps: every row gets the same arithmetic whatever slot of the unrolled loop it falls in
+      yo[j] = pack16x4(__fmaf_rn(__fmul_rn(__fsub_rn(v.x, mean), rstd), sc1.x, sh.x), __fmaf_rn(__fmul_rn(__fsub_rn(v.y, mean), rstd), sc1.y, sh.y),
+                       __fmaf_rn(__fmul_rn(__fsub_rn(v.z, mean), rstd), sc1.z, sh.z), __fmaf_rn(__fmul_rn(__fsub_rn(v.w, mean), rstd), sc1.w, sh.w),
+                       c.f16);
+    }
+    if (cg + 128 < n_slab) {                                   // the next pass's loads go out before this pass's stores
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        xv[j] = grow0 + j < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + (grow0 + j) * c.D + col + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (grow0 + j < c.R) *reinterpret_cast<uint2*>(dst + (grow0 + j) * c.D + col) = yo[j];
+  }
+  if (tid == 0) stamp(c, 40 + kind);
   team_signal(flag_ready, tid);
 }
 
@@ -208,17 +225,18 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   uint64_t* a_empty = a_full + CH_A_STAGES;
   uint64_t* b_full = a_empty + CH_A_STAGES;
   uint64_t* b_empty = b_full + CH_B_STAGES;
-  uint64_t* acc_full = b_empty + CH_B_STAGES;            // [4] one per job
-  uint64_t* acc_empty = acc_full + 4;                    // [4]
-  uint64_t* res_bar = acc_empty + 4;                     // [8] one per epilogue warp (residual tiles)
+  uint64_t* acc_full = b_empty + CH_B_STAGES;            // [2] one per TMEM half
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint64_t* res_bar = acc_empty + 2;                     // [8] one per epilogue warp (residual tiles)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const int team = pair / CH_TEAM, slice = pair - team * CH_TEAM;
+  const int team = pair / c.team, slice = pair - team * c.team;
   const int njobs = c.has_qkv ? 4 : 3;
+  const unsigned team_ctas = 2u * (unsigned)c.team;
 
   if (warp == WARP_TMA && lane == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mA1); prefetch_tmap(&mA2); prefetch_tmap(&mA3);
@@ -226,7 +244,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     prefetch_tmap(&mX); prefetch_tmap(&mFFo); prefetch_tmap(&mQKo);
     for (int s = 0; s < CH_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < CH_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int j = 0; j < 4; ++j) { mbar_init(&acc_full[j], 1); mbar_init(&acc_empty[j], 16); }
+    for (int j = 0; j < 2; ++j) { mbar_init(&acc_full[j], 1); mbar_init(&acc_empty[j], 16); }
     for (int w = 0; w < 8; ++w) mbar_init(&res_bar[w], 1);
     fence_barrier_init();
   }
@@ -240,99 +258,91 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
-      // ===== A producer (both CTAs): this CTA's 128 rows of each job's A operand; waits for the team hand-off first =====
+      // ===== A producer (both CTAs): this CTA's 128 rows of each job's A operand, once per sub-tile; waits for the team's
+      // hand-off before the first sub-tile of a job =====
       pdl_wait();
       int sa = 0; uint32_t pa = 0;
       for (int rb = team; rb < c.nrb; rb += c.teams) {
         const int row0 = rb * CH_ROWS + (int)rank * 128;
         const unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF);
+          const JobShape js = job_shape(j, c.D, c.FF, c.team);
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
           stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
-            wait_counter(flags + (j == 1 ? F_N16 : j == 2 ? F_FF16 : F_N16B), 2u * CH_TEAM);
+            wait_counter(flags + (j == 1 ? F_N16 : j == 2 ? F_FF16 : F_N16B), team_ctas);
             fence_proxy_async_global();
           }
           stamp(c, 8 + 8 * j + 1);
-          for (int ck = 0; ck < js.K / BK; ++ck) {
-            mbar_wait(&a_empty[sa], pa ^ 1);
-            if (leader) mbar_expect_tx(&a_full[sa], 2u * CH_A_BYTES);
-            tma_load_3d_2sm(smem_a + sa * CH_A_BYTES, map, &a_full[sa], ck * BK, row0, 0);
-            if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
-          }
+          for (int st = 0; st < js.nsubt; ++st)
+            for (int ck = 0; ck < js.K / BK; ++ck) {
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              if (leader) mbar_expect_tx(&a_full[sa], 2u * CH_A_BYTES);
+              tma_load_3d_2sm(smem_a + sa * CH_A_BYTES, map, &a_full[sa], ck * BK, row0, 0);
+              if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
+            }
         }
       }
     }
   } else if (warp == WARP_TMA_B) {
     if (lane == 0) {
-      // ===== B producer (both CTAs): this CTA's half of the pair's weight slice. No pdl_wait: weights are constants =====
+      // ===== B producer (both CTAs): this CTA's half of each sub-tile's weight rows. No pdl_wait: weights are constants =====
       int sb = 0; uint32_t pb = 0;
       for (int rb = team; rb < c.nrb; rb += c.teams) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF);
+          const JobShape js = job_shape(j, c.D, c.FF, c.team);
           const CUtensorMap* map = j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3;
-          const int n_row0 = slice * js.n_pair + (int)rank * js.b_rows;
-          const uint32_t tx = 2u * (uint32_t)(js.nsub * js.b_rows * 128);
-          for (int ck = 0; ck < js.K / BK; ++ck) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            if (leader) mbar_expect_tx(&b_full[sb], tx);
-            for (int s = 0; s < js.nsub; ++s)
-              tma_load_3d_2sm(smem_b + sb * CH_B_BYTES + s * (CH_B_BYTES / 2), map, &b_full[sb], ck * BK, n_row0 + s * js.sub_n, 0);
-            if (++sb == CH_B_STAGES) { sb = 0; pb ^= 1; }
+          const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
+          for (int st = 0; st < js.nsubt; ++st) {
+            const int n_row0 = slice * js.n_pair + st * js.w + (int)rank * js.b_rows;
+            for (int ck = 0; ck < js.K / BK; ++ck) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              if (leader) mbar_expect_tx(&b_full[sb], tx);
+              tma_load_3d_2sm(smem_b + sb * CH_B_BYTES, map, &b_full[sb], ck * BK, n_row0, 0);
+              if (++sb == CH_B_STAGES) { sb = 0; pb ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp == WARP_MMA) {
     if (leader) {
-      // ===== MMA issuer (leader CTA only): M = 256 across the pair =====
+      // ===== MMA issuer (leader CTA only): M = 256 across the pair; sub-tile t accumulates in TMEM half t & 1 =====
       const uint32_t a_lo0 = desc_lo_sw128(smem_u32(smem_a)), b_lo0 = desc_lo_sw128(smem_u32(smem_b));
-      const uint32_t a_stage_lo = (uint32_t)CH_A_BYTES >> 4, b_stage_lo = (uint32_t)CH_B_BYTES >> 4, b_sub_lo = (uint32_t)(CH_B_BYTES / 2) >> 4;
+      const uint32_t a_stage_lo = (uint32_t)CH_A_BYTES >> 4, b_stage_lo = (uint32_t)CH_B_BYTES >> 4;
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      int it = 0;
-      for (int rb = team; rb < c.nrb; rb += c.teams, ++it) {
+      uint32_t t = 0;
+      for (int rb = team; rb < c.nrb; rb += c.teams) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF);
-          const uint32_t idesc = idesc_f16kind(256, js.sub_n, c.f16);
-          mbar_wait(&acc_empty[j], ((uint32_t)it & 1u) ^ 1u);
-          // the q|k|v accumulator [128, 512) overlaps ff1's and ff2's: the previous row block's q|k|v epilogue must have drained
-          if (j == 1 && it > 0 && c.has_qkv) mbar_wait(&acc_empty[3], (uint32_t)(it - 1) & 1u);
-          tc_fence_after();
-          const uint32_t d0 = tmem_base + (uint32_t)js.tmem_col;
+          const JobShape js = job_shape(j, c.D, c.FF, c.team);
+          const uint32_t idesc = idesc_f16kind(256, js.w, c.f16);
           const int chunks = js.K / BK;
-          for (int ck = 0; ck < chunks; ++ck) {
-            mbar_wait(&a_full[sa], pa);
-            mbar_wait(&b_full[sb], pb);
+          for (int st = 0; st < js.nsubt; ++st, ++t) {
+            const uint32_t buf = t & 1u;
+            mbar_wait(&acc_empty[buf], ((t >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            if (ck == 0 && lane == 0) stamp(c, 8 + 8 * j + 2);
-            const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
-            const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
-            const uint32_t accum = ck > 0 ? 1u : 0u;
-            if (elect_one()) {
-              if (js.nsub == 1) {
+            const uint32_t d0 = tmem_base + buf * 256u;
+            for (int ck = 0; ck < chunks; ++ck) {
+              mbar_wait(&a_full[sa], pa);
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              if (ck == 0 && st == 0 && lane == 0) stamp(c, 8 + 8 * j + 2);
+              const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage_lo;
+              const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
+              const uint32_t accum = ck > 0 ? 1u : 0u;
+              if (elect_one()) {
                 umma2_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
                 umma2_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
                 umma2_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
                 umma2_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
-              } else {                                      // two column halves share the A tile
-                const uint32_t d1 = d0 + (uint32_t)js.sub_n, b_hi = b_lo + b_sub_lo;
-                umma2_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
-                umma2_bf16_lohi(d1, a_lo + 0, b_hi + 0, idesc, accum);
-                umma2_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
-                umma2_bf16_lohi(d1, a_lo + 2, b_hi + 2, idesc, 1u);
-                umma2_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
-                umma2_bf16_lohi(d1, a_lo + 4, b_hi + 4, idesc, 1u);
-                umma2_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
-                umma2_bf16_lohi(d1, a_lo + 6, b_hi + 6, idesc, 1u);
+                umma2_commit_mc(&b_empty[sb]);
+                umma2_commit_mc(&a_empty[sa]);
+                if (ck == chunks - 1) { umma2_commit_mc(&acc_full[buf]); if (st == js.nsubt - 1) stamp(c, 8 + 8 * j + 3); }
               }
-              umma2_commit_mc(&b_empty[sb]);
-              umma2_commit_mc(&a_empty[sa]);
-              if (ck == chunks - 1) { umma2_commit_mc(&acc_full[j]); stamp(c, 8 + 8 * j + 3); }
+              __syncwarp();
+              if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
+              if (++sb == CH_B_STAGES) { sb = 0; pb ^= 1; }
             }
-            __syncwarp();
-            if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
-            if (++sb == CH_B_STAGES) { sb = 0; pb ^= 1; }
           }
         }
       }
@@ -349,13 +359,13 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     EpiTile et;
     et.res_tile = smem_epi + warp * 8192; et.out_tile = et.res_tile + 4096; et.res_bar = &res_bar[warp]; et.res_phase = 0u;
     float* s_bias = smem_vec;
-    float* s_gate = smem_vec + 384;
-    // bias / gate of the CTA's column slice -> shared memory (broadcast reads in the epilogue)
+    float* s_gate = smem_vec + 256;
+    // bias / gate of the sub-tile's columns -> shared memory (broadcast reads in the epilogue)
     auto stage_vec = [&](const float* bias, const float* gate, int n0, int n) {
-      epi_bar();                                               // the previous job's readers are done
-      for (int i = tid; i < n; i += 256) {
-        s_bias[i] = __ldg(bias + n0 + i);
-        if (gate) s_gate[i] = __ldg(gate + n0 + i);
+      epi_bar();                                               // the previous sub-tile's readers are done
+      if (tid < n) {
+        s_bias[tid] = __ldg(bias + n0 + tid);
+        if (gate) s_gate[tid] = __ldg(gate + n0 + tid);
       }
       epi_bar();
     };
@@ -364,92 +374,51 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     a.o_bstride = 0; a.o_shift = 0; a.accumulate = 0; a.scale = 1.0f; a.out2 = nullptr; a.f16 = c.f16;
     a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0; a.vt_ld = 0; a.vt_heads = 0;
     a.out = nullptr; a.ldo = 0; a.o_limit = 0; a.out_bf16 = 0; a.bias = nullptr; a.gate = nullptr; a.res = nullptr;
-    int it = 0;
-    for (int rb = team; rb < c.nrb; rb += c.teams, ++it) {
+    uint32_t t = 0;
+    for (int rb = team; rb < c.nrb; rb += c.teams) {
       unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
-      const uint32_t ph = (uint32_t)it & 1u;
       const int row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
-      float rsum, rsq;
-      // ---- job 0: x += gate_msa * (att @ Wout^T + b_out) ; LN-modulate (mlp) -> n16 ----
-      {
-        const JobShape js = job_shape(0, c.D, c.FF);
-        const int n0 = slice * js.n_pair;
-        a.Cin = js.K; a.N = c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        stage_vec(c.b_out, c.gate_msa, n0, js.n_pair);
-        epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
-        rsum = 0.f; rsq = 0.f;
-        mbar_wait(&acc_full[0], ph);
-        tc_fence_after();
-        if (tid == 0) stamp(c, 8 + 8 * 0 + 4);
-        epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
-                                                      s_bias, s_gate, rsum, rsq);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&acc_empty[0]);
-        epi_tma_drain(lane);
-        if (tid == 0) stamp(c, 8 + 8 * 0 + 5);
-        ln_phase(c, rb, (int)rank, slice, 0, rsum, rsq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
-        if (tid == 0) stamp(c, 8 + 8 * 0 + 7);
-      }
-      // ---- job 1: ff16 = GELU_tanh(n16 @ Wff1^T + b_ff1) ----
-      {
-        const JobShape js = job_shape(1, c.D, c.FF);
-        const int n0 = slice * js.n_pair;
-        a.Cin = js.K; a.N = c.FF; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        stage_vec(c.b_ff1, nullptr, n0, js.n_pair);
-        mbar_wait(&acc_full[1], ph);
-        tc_fence_after();
-        if (tid == 0) stamp(c, 8 + 8 * 1 + 4);
-        epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64,
-                                                          lane, s_bias, nullptr, rsum, rsq);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&acc_empty[1]);
-        epi_tma_drain(lane);
-        if (tid == 0) stamp(c, 8 + 8 * 1 + 5);
-        team_signal(flags + F_FF16, tid);
-        if (tid == 0) stamp(c, 8 + 8 * 1 + 7);
-      }
-      // ---- job 2: x += gate_mlp * (ff16 @ Wff2^T + b_ff2) ; LN-modulate (next block's attention / final) -> n16b ----
-      {
-        const JobShape js = job_shape(2, c.D, c.FF);
-        const int n0 = slice * js.n_pair;
-        a.Cin = js.K; a.N = c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        stage_vec(c.b_ff2, c.gate_mlp, n0, js.n_pair);
-        epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
-        rsum = 0.f; rsq = 0.f;
-        mbar_wait(&acc_full[2], ph);
-        tc_fence_after();
-        if (tid == 0) stamp(c, 8 + 8 * 2 + 4);
-        epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
-                                                      s_bias, s_gate, rsum, rsq);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&acc_empty[2]);
-        epi_tma_drain(lane);
-        if (tid == 0) stamp(c, 8 + 8 * 2 + 5);
-        ln_phase(c, rb, (int)rank, slice, 1, rsum, rsq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
-        if (tid == 0) stamp(c, 8 + 8 * 2 + 7);
-      }
-      // ---- job 3: q | k | v of the next block: bias + RoPE -> qk16 (TMA tiles), V transposed -> vt_out ----
-      if (c.has_qkv) {
-        const JobShape js = job_shape(3, c.D, c.FF);
-        const int n0 = slice * js.n_pair;
-        a.Cin = js.K; a.N = 3 * c.D; a.BN = js.n_pair; a.kchunks = js.K / BK;
-        a.rope_cs = c.rope_cs; a.rope_cols = 2 * c.D; a.rope_rows = c.rope_rows;
-        a.vt_out = c.vt_out; a.vt_col0 = 2 * c.D; a.vt_ld = c.vt_ld; a.vt_heads = c.vt_heads;
-        stage_vec(c.b_qkv, nullptr, n0, js.n_pair);
-        mbar_wait(&acc_full[3], ph);
-        tc_fence_after();
-        if (tid == 0) stamp(c, 8 + 8 * 3 + 4);
-        epilogue_rows_tma<TK_ROPE16, ACT_NONE, false>(a, &mQKo, nullptr, et, tmem_base + (uint32_t)js.tmem_col + lane_sel, row0, n0, e * 32, 64, lane,
-                                                      s_bias, nullptr, rsum, rsq);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&acc_empty[3]);
-        epi_tma_drain(lane);
-        if (tid == 0) stamp(c, 8 + 8 * 3 + 5);
-        a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0;
+      for (int j = 0; j < njobs; ++j) {
+        const JobShape js = job_shape(j, c.D, c.FF, c.team);
+        a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.K / BK;
+        const float* bias = j == 0 ? c.b_out : j == 1 ? c.b_ff1 : j == 2 ? c.b_ff2 : c.b_qkv;
+        const float* gate = j == 0 ? c.gate_msa : j == 2 ? c.gate_mlp : nullptr;
+        if (j == 3) {
+          a.rope_cs = c.rope_cs; a.rope_cols = 2 * c.D; a.rope_rows = c.rope_rows;
+          a.vt_out = c.vt_out; a.vt_col0 = 2 * c.D; a.vt_ld = c.vt_ld; a.vt_heads = c.vt_heads;
+        } else {
+          a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0;
+        }
+        float rsum = 0.f, rsq = 0.f;
+        for (int st = 0; st < js.nsubt; ++st, ++t) {
+          const uint32_t buf = t & 1u;
+          const int n0 = slice * js.n_pair + st * js.w;
+          const uint32_t taddr = tmem_base + buf * 256u + lane_sel;
+          stage_vec(bias, gate, n0, js.w);
+          if (j == 0 || j == 2) epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
+          mbar_wait(&acc_full[buf], (t >> 1) & 1u);
+          tc_fence_after();
+          if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
+          if (j == 0 || j == 2)
+            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq);
+          else if (j == 1)
+            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
+          else
+            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+        }
+        if (tid == 0) stamp(c, 8 + 8 * j + 5);
+        if (j == 0) {
+          ln_phase(c, rb, (int)rank, slice, 0, rsum, rsq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
+        } else if (j == 2) {
+          ln_phase(c, rb, (int)rank, slice, 1, rsum, rsq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
+        } else {
+          epi_tma_drain(lane);
+          if (j == 1) team_signal(flags + F_FF16, tid);
+        }
+        if (tid == 0) stamp(c, 8 + 8 * j + 7);
       }
     }
   }
@@ -476,15 +445,31 @@ int resident_pairs() {
   return pairs;
 }
 
+// pairs per row block: the split that finishes nrb row blocks soonest on `pairs` resident pairs (a pair's share of a block's
+// work is 1 / team, and blocks beyond pairs / team wait for a second round)
+int pick_team(int nrb, int pairs) {
+  const char* ev = getenv("B200TTS_CHAIN_TEAM");             // experiment override
+  if (ev != nullptr) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8) return v; }
+  int best = 1;
+  double best_cost = 1e300;
+  for (int tm : {1, 2, 4, 8}) {                              // ties go to the smaller team: fewer hand-offs, more overlap
+    const int teams = pairs / tm;
+    if (teams < 1) continue;
+    const double cost = (double)ceil_div(nrb, teams) / tm;
+    if (cost < best_cost - 1e-12) { best_cost = cost; best = tm; }
+  }
+  return best;
+}
+
 }  // namespace
 
-size_t dit_chain_stats_floats(int R) { return (size_t)ceil_div(R, CH_ROWS) * 2 * CH_ROWS * CH_TEAM * 2; }
+size_t dit_chain_stats_floats(int R) { return (size_t)ceil_div(R, CH_ROWS) * 2 * CH_ROWS * CH_MAX_TEAM * 2; }
 size_t dit_chain_flag_words(int R) { return (size_t)ceil_div(R, CH_ROWS) * CH_NFLAGS; }
 
 bool dit_chain_supported(int D, int FF, int H) {
-  // the job table (column slices of 128 / 256 / 128 / 2 x 192 per pair, 512 TMEM columns) is laid out for the F5 DiT
+  // the job table (sub-tiles of 128 / 192 / 256 columns, two 256-column TMEM halves) is laid out for the F5 DiT
   if (D != 1024 || FF != 2048 || H * 64 != D) return false;
-  return resident_pairs() >= CH_TEAM;
+  return resident_pairs() >= CH_MAX_TEAM;
 }
 
 void dit_chain(const DitChain& d, cudaStream_t stream) {
@@ -499,7 +484,8 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
            d.w_ff2->Cin == d.FF && (!d.has_qkv || (d.w_qkv->N == 3 * d.D && d.w_qkv->Cin == d.D)), "dit_chain: weight shapes");
   ChainArgs c;
   c.R = d.R; c.nrb = ceil_div(d.R, CH_ROWS); c.has_qkv = d.has_qkv; c.f16 = d.f16; c.D = d.D; c.FF = d.FF;
-  const int max_teams = resident_pairs() / CH_TEAM;
+  c.team = pick_team(c.nrb, resident_pairs());
+  const int max_teams = resident_pairs() / c.team;
   c.teams = c.nrb < max_teams ? c.nrb : max_teams;
   c.x = d.x; c.n16 = d.n16; c.ff16 = d.ff16; c.n16b = d.n16b;
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;
@@ -512,17 +498,18 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   for (int j = 0; j < 4; ++j)
     tc_encode_map(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
   const TcWeight* ws[4] = {d.w_out, d.w_ff1, d.w_ff2, wq};
-  const uint32_t b_box[4] = {(uint32_t)(d.D / (2 * CH_TEAM)), (uint32_t)(d.FF / (2 * CH_TEAM)), (uint32_t)(d.D / (2 * CH_TEAM)),
-                             d.has_qkv ? (uint32_t)(3 * d.D / (4 * CH_TEAM)) : (uint32_t)(d.D / (2 * CH_TEAM))};
-  for (int j = 0; j < 4; ++j)
-    tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc, b_box[j]);
+  for (int j = 0; j < 4; ++j) {
+    const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, c.team);
+    tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
+                  (uint32_t)js.b_rows);
+  }
   // epilogue tiles: x (fp32, residual in / result out), ff16 and q|k (16 bit, result out), 32 rows x 32 columns each
   CUtensorMap mX, mFFo, mQKo;
   tc_encode_map2d(&mX, d.x, 4, (uint64_t)d.D, (uint64_t)d.R, (uint64_t)d.D, 32, 32);
   tc_encode_map2d(&mFFo, d.ff16, 2, (uint64_t)d.FF, (uint64_t)d.R, (uint64_t)d.FF, 32, 32);
   if (d.has_qkv) tc_encode_map2d(&mQKo, d.qk16, 2, (uint64_t)2 * d.D, (uint64_t)d.R, (uint64_t)2 * d.D, 32, 32);
   else mQKo = mFFo;
-  launch_pdl(dit_chain_kernel, dim3((unsigned)(c.teams * CH_TEAM * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
+  launch_pdl(dit_chain_kernel, dim3((unsigned)(c.teams * c.team * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
              mB[0], mB[1], mB[2], mB[3], mX, mFFo, mQKo, c);
   B2_LAUNCH_CHECK();
   count_launch();

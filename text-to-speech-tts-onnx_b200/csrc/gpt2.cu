@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(1024) gpt_pick_kernel(const float* __restrict_
   pdl_trigger();
   pdl_wait();
   const int tid = threadIdx.x;
-  float best = -3.0e38f; int idx = 0x7fffffff;
+  float best = -3.0e38f; int idx = 0;      // idx stays a valid row even if no logit beats the sentinel (NaN / -inf rows)
   for (int n = tid; n < Vm; n += 1024) {
     const float v = logits[n];
     if (v > best) { best = v; idx = n; }       // ascending n per thread: keeps the first maximum
@@ -662,7 +664,7 @@ __device__ __forceinline__ void p_attention(const PArgs& a, int layer, int h, in
 __device__ __forceinline__ void p_pick(const PArgs& a, unsigned ep_logits, unsigned ep_h_next, float* redv, int* redi, int* abort) {
   __shared__ int s_tok, s_go, s_gen;
   const int tid = threadIdx.x;
-  float best = -3.0e38f; int idx = 0x7fffffff;
+  float best = -3.0e38f; int idx = 0;      // idx stays a valid row even if no logit beats the sentinel (NaN / -inf rows)
   for (int n0 = 0; n0 < a.Vm; n0 += 8 * P_NT) {
     u64 v[8];
 #pragma unroll
@@ -1032,13 +1034,20 @@ void launch_persistent(Engine& e, GptModel& m, int n_tokens, int n0) {
            "persistent decode: too few SMs for the row ownership this instantiation assumes");
   auto kern = gpt_decode_kernel<CH_D, CH_F, R_QKV, R_FC, R_HEAD>;
   const size_t smem = (size_t)(m.FF + m.D + m.S_max + 32 * HD + 2 * P_NW + HD) * sizeof(float);
-  static bool once = false;
-  if (!once) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P_NT, smem));
-    B2_CHECK(per_sm >= 1, "persistent decode kernel does not fit an SM");
-    once = true;
+  // the opt-in shared-memory size is a per-device function attribute and depends on the model (S_max): raise it whenever this
+  // (device, size) needs more than what was set before (a second model / a second GPU in one process)
+  static std::mutex attr_mu;
+  static std::map<int, size_t> attr_smem;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    size_t& cur = attr_smem[dev];
+    if (smem > cur) {
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P_NT, smem));
+      B2_CHECK(per_sm >= 1, "persistent decode kernel does not fit an SM");
+      cur = smem;
+    }
   }
   PArgs pa{};
   pa.layers = reinterpret_cast<const PLayer*>(m.players.p);
@@ -1226,6 +1235,13 @@ void gpt_step(Engine& e, const float* d_hidden, int rows, int history, int mask_
   B2_CHECK(rows >= 1, "gpt_step: no rows");
   B2_CHECK(history == 0 || history == m.resident, "gpt_step: history_len does not match the resident KV cache");
   B2_CHECK(history + rows <= m.S_max, "gpt_step: KV cache capacity (MAX_GENERATE_LENGTH) exceeded");
+  // The graph's mask is additive and sliced [:ids_len, :kv_seq_len] (Export_IndexTTS.py:245,272): with history > 0 AND several
+  // new rows it would let row r see cache columns <= r only. The reference loop never does that (prefill has history 0, decode
+  // has one row); this engine's causal path appends after the history, so the combination is refused rather than answered
+  // differently.
+  B2_CHECK(!(history > 0 && rows > 1 && mask_flag != 0),
+           "gpt_step: a masked multi-row call on top of a resident history is not supported (the reference graph slices its "
+           "mask from column 0; prefill with history_len = 0 or feed one row per call)");
   const bool fast = precision == PREC_BF16;
   prepare(e, m, precision);
   reserve(m, rows, fast);
@@ -1264,7 +1280,10 @@ int gpt_generate(Engine& e, const float* d_conds, int cond_rows, const int* d_te
   int limit = m.S_max - rows;                              // Inference_IndexTTS_ONNX.py:745
   if (max_new > 0 && max_new < limit) limit = max_new;
   B2_CHECK(limit >= 1, "gpt_generate: the prompt leaves no room to generate (MAX_GENERATE_LENGTH)");
-  B2_CHECK(limit + 1 <= m.Pm, "gpt_generate: mel_pos_embedding has fewer rows than the generation limit");
+  // positions run to `limit`: a checkpoint whose mel_pos_embedding is shorter than MAX_GENERATE_LENGTH (IndexTTS-1.0: 608 rows)
+  // bounds the generation instead of failing calls that would never get that far
+  if (limit + 1 > m.Pm) limit = m.Pm - 1;
+  B2_CHECK(limit >= 1, "gpt_generate: mel_pos_embedding is empty");
   prepare(e, m, precision);
   reserve(m, rows, fast);
   if (d_penalty) {

@@ -179,6 +179,35 @@ def sec_bigvgan():
         eng.set_stream(0)
 
 
+def sec_twins():
+    """Two copies of one utterance in a batch: are their mels bit-identical? (rows at different tile offsets)"""
+    import torch
+    eng = f5_engine()
+    L, n_text = int(os.environ.get("TWIN_L", "144000")), 150
+    a, t, maxd, nz = synth.f5_inputs(1, L, n_text)
+    N = int(os.environ.get("TWIN_N", int(maxd[0])))
+    nz = np.random.default_rng(5).standard_normal((1, N, 100), dtype=np.float32)
+    U = 2
+    ns = 256 * (N - (L // 256 + 1) - 1)
+    audio = torch.from_numpy(np.repeat(a.reshape(1, -1), U, 0)).cuda()
+    ids = torch.from_numpy(np.repeat(t.reshape(1, -1), U, 0)).cuda()
+    noise = torch.from_numpy(np.repeat(nz.reshape(1, -1), U, 0)).cuda()
+    pcm = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
+    mel = torch.zeros((U, N, 100), dtype=torch.float32, device="cuda")
+    for prec in ("f16",):
+        for chain in (0, 1):
+            eng.set_option("dit_chain", chain)
+            for steps in (1,):
+                eng.f5_synthesize_batch_device(U, audio.data_ptr(), L, ids.data_ptr(), n_text, N, noise.data_ptr(), pcm.data_ptr(),
+                                               precision=PREC[prec], n_steps=steps, mel_ptr=mel.data_ptr())
+                eng.synchronize()
+                m = mel.cpu().numpy()
+                d = np.abs(m[0] - m[1])
+                rows = np.nonzero(d.max(axis=1))[0]
+                out(section="twins", N=N, team=os.environ.get("B200TTS_CHAIN_TEAM", "auto"), prec=prec, chain=chain, steps=steps, mel_maxabs_between_twins=float(d.max()), n_rows_differ=int(rows.size),
+                    first_rows=rows[:8].tolist(), pcm_equal=bool((pcm[0] == pcm[1]).all().item()))
+
+
 if __name__ == "__main__":
     for name in sys.argv[1:]:
         t0 = time.time()
