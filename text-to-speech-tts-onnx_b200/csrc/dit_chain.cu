@@ -50,6 +50,7 @@ static_assert(CH_SMEM <= 227 * 1024, "dit_chain: shared memory budget");
 
 struct ChainArgs {
   int R, nrb, teams, team, has_qkv, f16, D, FF;      // team = CTA pairs per row block (1, 2, 4 or 8)
+  int l2hint;                                        // experiment: x tiles stored with the L2 evict_last policy
   float* x;
   __nv_bfloat16 *n16, *ff16, *n16b;
   const float *b_out, *gate_msa, *shift_mlp, *scale_mlp, *b_ff1, *b_ff2, *gate_mlp, *shift_nxt, *scale_nxt, *b_qkv;
@@ -124,9 +125,9 @@ __device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int
 
 // LayerNorm statistics + modulation of this CTA's [128 rows] x [D / team columns] slab of x (all 256 epilogue threads).
 //   rsum / rsq : this lane's row sums over the warp's column blocks (epilogue_rows_tma<.., STATS>)
-// Order matters for latency (loaded L2 round trips cost ~1 us here: the weight stream keeps the SM's memory queues deep):
-// the slab is this CTA's own output, so its first 128 columns are fetched BEFORE waiting for the team's statistics, and each
-// later pass issues all 16 row loads of a lane before its first use.
+// Measured alternatives that were SLOWER on B200 (profiles/r02/chain_timeline.md): fetching the slab before the statistics
+// arrive with 16 row loads per lane in flight (+3.6 ms per utterance), and walking whole rows instead of 128-column groups
+// (+6 ms): more loads in flight per thread only lengthen the loaded L2 latency here.
 __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind, float rsum, float rsq,
                                          const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
                                          unsigned* flag_ready, float* st, int warp, int lane) {
@@ -141,66 +142,63 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
     *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_MAX_TEAM + slice) * 2) = make_float2(s, sq);
   }
   epi_bar();
-  if (tid == 0) {                                              // publish first: the team waits for the slowest member
+  if (tid == 0) {
     fence_acq_rel_gpu();
     red_relaxed_gpu(flag_stat, 1u);
+    wait_counter(flag_stat, 2u * (unsigned)c.team);
   }
-  epi_tma_drain(lane);                                         // this warp's x tiles are in global memory (under the exchange)
+  epi_tma_drain(lane);                                         // x tiles of this warp are in global memory (under the exchange)
   epi_bar();
-  // warp w normalises rows [16w, 16w + 16) of the slab, 128 columns per pass (lane l: columns 4l .. 4l + 3)
+  if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
+  // pass 2: warp w normalises rows [16w, 16w + 16) of the slab, 128 columns at a time (lane l: columns 4l .. 4l + 3)
   const int n_slab = c.D / c.team;
   const float inv_d = 1.0f / (float)c.D;
   const long grow0 = (long)rb * CH_ROWS + rank * 128 + warp * 16;
-  const int col0 = slice * n_slab + lane * 4;
-  float4 xv[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    xv[j] = grow0 + j < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + (grow0 + j) * c.D + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid == 0) wait_counter(flag_stat, 2u * (unsigned)c.team);
-  epi_bar();
-  if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
   float2 pr[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)       // lane = (row k*4 + lane/8, slot lane%8)
+  for (int k = 0; k < 4; ++k) {     // lane = (row k*4 + lane/8, slot lane%8)
     pr[k] = (lane & 7) < c.team
                 ? __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_MAX_TEAM + (lane & 7)) * 2))
                 : make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       pr[k].x += __shfl_xor_sync(0xffffffffu, pr[k].x, o);
       pr[k].y += __shfl_xor_sync(0xffffffffu, pr[k].y, o);
     }
+    // explicit rounding steps here and below: a row's arithmetic must not depend on the slot of the unrolled loop it falls in
+    // (the compiler contracted them differently per slot: two copies of one utterance in a batch differed in the last bit)
     const float mean = __fmul_rn(pr[k].x, inv_d);
     pr[k].x = mean;                                            // -> (mean, rstd) of row k*4 + lane/8
     pr[k].y = rsqrtf(__fadd_rn(fmaxf(__fsub_rn(__fmul_rn(pr[k].y, inv_d), __fmul_rn(mean, mean)), 0.f), 1e-6f));
   }
 #pragma unroll 1
   for (int cg = 0; cg < n_slab; cg += 128) {
-    const int col = col0 + cg;
+    const int col = slice * n_slab + cg + lane * 4;
     const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + col));
     const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + col));
-    const float4 sc1 = make_float4(1.0f + sc.x, 1.0f + sc.y, 1.0f + sc.z, 1.0f + sc.w);
-    uint2 yo[16];
+    const float4 sc1 = make_float4(__fadd_rn(1.0f, sc.x), __fadd_rn(1.0f, sc.y), __fadd_rn(1.0f, sc.z), __fadd_rn(1.0f, sc.w));
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float4 xv[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 ms = j < 4 ? pr[0] : j < 8 ? pr[1] : j < 12 ? pr[2] : pr[3];
-      const float mean = __shfl_sync(0xffffffffu, ms.x, (j & 3) * 8), rstd = __shfl_sync(0xffffffffu, ms.y, (j & 3) * 8);
-      const float4 v = xv[j];
-      // explicit rounding steps: every row gets the same arithmetic whatever slot of the unrolled loop it falls in
-      yo[j] = pack16x4(__fmaf_rn(__fmul_rn(__fsub_rn(v.x, mean), rstd), sc1.x, sh.x), __fmaf_rn(__fmul_rn(__fsub_rn(v.y, mean), rstd), sc1.y, sh.y),
-                       __fmaf_rn(__fmul_rn(__fsub_rn(v.z, mean), rstd), sc1.z, sh.z), __fmaf_rn(__fmul_rn(__fsub_rn(v.w, mean), rstd), sc1.w, sh.w),
-                       c.f16);
+      for (int j = 0; j < 8; ++j) {
+        const long g = grow0 + half * 8 + j;
+        xv[j] = g < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + g * c.D + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jj = half * 8 + j;
+        const float2 ms = half == 0 ? (j < 4 ? pr[0] : pr[1]) : (j < 4 ? pr[2] : pr[3]);
+        const float mean = __shfl_sync(0xffffffffu, ms.x, (jj & 3) * 8), rstd = __shfl_sync(0xffffffffu, ms.y, (jj & 3) * 8);
+        const long g = grow0 + jj;
+        if (g >= c.R) continue;                                 // warp-uniform
+        const float4 v = xv[j];
+        *reinterpret_cast<uint2*>(dst + g * c.D + col) =
+            pack16x4(__fmaf_rn(__fmul_rn(__fsub_rn(v.x, mean), rstd), sc1.x, sh.x), __fmaf_rn(__fmul_rn(__fsub_rn(v.y, mean), rstd), sc1.y, sh.y),
+                     __fmaf_rn(__fmul_rn(__fsub_rn(v.z, mean), rstd), sc1.z, sh.z), __fmaf_rn(__fmul_rn(__fsub_rn(v.w, mean), rstd), sc1.w, sh.w),
+                     c.f16);
+      }
     }
-    if (cg + 128 < n_slab) {                                   // the next pass's loads go out before this pass's stores
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        xv[j] = grow0 + j < c.R ? __ldcg(reinterpret_cast<const float4*>(c.x + (grow0 + j) * c.D + col + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (grow0 + j < c.R) *reinterpret_cast<uint2*>(dst + (grow0 + j) * c.D + col) = yo[j];
   }
   if (tid == 0) stamp(c, 40 + kind);
   team_signal(flag_ready, tid);
@@ -375,6 +373,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0; a.vt_ld = 0; a.vt_heads = 0;
     a.out = nullptr; a.ldo = 0; a.o_limit = 0; a.out_bf16 = 0; a.bias = nullptr; a.gate = nullptr; a.res = nullptr;
     uint32_t t = 0;
+    const uint64_t x_policy = c.l2hint ? l2_policy_evict_last() : 0ull;
     for (int rb = team; rb < c.nrb; rb += c.teams) {
       unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
       const int row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
@@ -400,7 +399,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           tc_fence_after();
           if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
           if (j == 0 || j == 2)
-            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq);
+            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy);
           else if (j == 1)
             epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
           else
@@ -492,6 +491,7 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
   c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
   c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
+  { const char* v = getenv("B200TTS_CHAIN_L2HINT"); c.l2hint = v != nullptr && atoi(v) != 0; }
   CUtensorMap mA[4], mB[4];
   const void* a_ptr[4] = {d.att16, d.n16, d.ff16, d.n16b};
   const int a_k[4] = {d.D, d.D, d.FF, d.D};

@@ -327,7 +327,8 @@ __device__ __forceinline__ void epi_tma_drain(int lane) {
 template <int TK, int ACT, bool STATS>
 __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
                                                   uint32_t taddr, int row0, int n0, int cb_first, int cb_step, int lane,
-                                                  const float* s_bias, const float* s_gate, float& rsum, float& rsq) {
+                                                  const float* s_bias, const float* s_gate, float& rsum, float& rsq,
+                                                  uint64_t store_policy = 0ull /* L2 cache hint of the result tiles, 0 = none */) {
   const uint32_t out_s = smem_u32(et.out_tile), res_s = smem_u32(et.res_tile);
   const uint32_t bias_s = smem_u32(s_bias), gate_s = s_gate ? smem_u32(s_gate) : 0u;
   const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
@@ -429,7 +430,8 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
     fence_proxy_async();                                       // generic-proxy writes of the staging tile -> async proxy
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(map_out, et.out_tile, n, row0);
+      if (store_policy) tma_store_2d_hint(map_out, et.out_tile, n, row0, store_policy);
+      else tma_store_2d(map_out, et.out_tile, n, row0);
       bulk_commit();
     }
   }
