@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
         r = cpu_f5(args.audio_len, args.n_text, steps, cores)
         G = r["N"] - r["ref_len"]
         total = r["pre_s"] + (cfg.nfe - 1) * r["step_s"]
-        if args.workload == "pipeline":
+        if args.workload in ("pipeline", "config4"):
             r["bigvgan_s"] = cpu_bigvgan(G, 1, cores)
             total += r["bigvgan_s"]
         else:
@@ -227,12 +227,12 @@ def run_reference(args, rank, world):
         line = {"metric": "mel_frames_per_s", "value": v, "unit": "mel-frames/s", "ms_per_step": 1e3 * total, "dtype": "f32",
                 "config": {"workload": f"F5-TTS NFE={cfg.nfe} N={r['N']} (ref {r['ref_len']} frames)"
                                        + (" + BigVGAN on the generated frames [BASELINE.json configs[3] per-GPU share; one of its utterances per reference step]"
-                                          if args.workload == "pipeline" else " + Vocos/ISTFT [BASELINE.json configs[2]]; one utterance"),
+                                          if args.workload in ("pipeline", "config4") else " + Vocos/ISTFT [BASELINE.json configs[2]]; one utterance"),
                            "parallelism": "cpu"},
                 "rtf": total / (cfg.hop * (G - 1) / cfg.sample_rate),
                 "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                  "sample": f"graph A once, {steps} of {cfg.nfe - 1} DiT steps (x{cfg.nfe - 1} extrapolated), "
-                                           + ("BigVGAN on the generated frames once" if args.workload == "pipeline" else "graph C once")
+                                           + ("BigVGAN on the generated frames once" if args.workload in ("pipeline", "config4") else "graph C once")
                                            + "; torch-CPU fp32 eager restatement of the reference modules (stand-in for ORT "
                                              "CPUExecutionProvider, not installable offline)", "parts_s": r}}
     line.update({"impl": "reference", "n_gpus": world, "steps": steps, "warmup": 1, "higher_is_better": True, "scaling": "weak",
@@ -449,6 +449,114 @@ def bench_f5(args, H, eng, rank, prec, steps, warmup, with_vocoder=False, U=1, s
     return res
 
 
+def config4_set(cfg, n_utt=64, n_text=150):
+    """BASELINE.json configs[3] / SURVEY.md 8d "Config 4": 64 utterances = config 3 with seeds 1000+i and reference lengths
+    uniform in [4 s, 8 s] (N = 2 x reference frames in [752, 1502]). Returns [(seed, L)]."""
+    rng = np.random.default_rng(4)
+    secs = rng.uniform(4.0, 8.0, size=n_utt)
+    return [(1000 + i, int(round(secs[i] * cfg.sample_rate))) for i in range(n_utt)]
+
+
+def bench_config4(args, H, eng, rank, prec, steps, warmup, sampler=None):
+    """STRONG scaling: the 64-utterance set is dealt to the ranks (longest first to the lightest rank, cost N^2 + c N); a rank
+    runs its share as ONE ragged batch through b200tts_f5_bigvgan_pipeline_ragged (graph A per utterance, one DiT loop over all
+    its 2 * sum(N) rows, BigVGAN per utterance). value = generated frames of ALL utterances / max-over-ranks time."""
+    torch = H.torch
+    from b200tts import config, distributed, synth
+    cfg, vcfg = config.F5, config.BIGVGAN
+    utts = config4_set(cfg, args.config4_utterances, args.n_text)
+    Ns_all = [2 * (L // cfg.hop + 1) for _, L in utts]
+    shards = distributed.shard_utterances([float(n) * n + 4096.0 * n for n in Ns_all], H.world)
+    mine = shards[rank]
+    ins = [synth.f5_inputs(utts[i][0], utts[i][1], args.n_text) for i in mine]
+    L = np.asarray([utts[i][1] for i in mine], dtype=np.int64)
+    Ns = np.asarray([Ns_all[i] for i in mine], dtype=np.int64)
+    nt = np.full(len(mine), args.n_text, dtype=np.int32)
+    G_mine = Ns - (L // cfg.hop + 1)
+    G_all = [n - n // 2 for n in Ns_all]
+    nv = int(sum(vcfg.out_samples(int(g)) for g in G_mine))
+    audio_h = torch.from_numpy(np.concatenate([a.reshape(-1) for a, _, _, _ in ins])).pin_memory()
+    ids_h = torch.from_numpy(np.concatenate([t.reshape(-1) for _, t, _, _ in ins])).pin_memory()
+    noise_h = torch.from_numpy(np.concatenate([n.reshape(-1, cfg.n_mels) for _, _, _, n in ins], 0)).pin_memory()
+    wav_h = torch.empty((nv,), dtype=torch.int16).pin_memory()
+    audio_d, ids_d, noise_d = audio_h.cuda(), ids_h.cuda(), noise_h.cuda()
+    wav_d = torch.empty((nv,), dtype=torch.int16, device="cuda")
+    audio_np, ids_np, noise_np, wav_np = audio_h.numpy(), ids_h.numpy(), noise_h.numpy(), wav_h.numpy()
+    U = len(mine)
+    torch.cuda.synchronize()
+
+    def core():
+        eng.f5_bigvgan_pipeline_ragged_device(U, audio_d.data_ptr(), L, ids_d.data_ptr(), nt, Ns, noise_d.data_ptr(), wav_d.data_ptr(), precision=prec)
+
+    def step_e2e():
+        eng.f5_bigvgan_pipeline_ragged_concat(audio_np, L, ids_np, nt, Ns, noise_np, wav_np, precision=prec)
+
+    with torch.cuda.stream(H.stream):
+        for _ in range(warmup):
+            core()
+        step_e2e()
+        step_e2e()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    ms = H.timed(core, steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = H.timed(step_e2e, steps)
+    # per-rank busy time (one more step, timed locally, no barrier inside): the tail imbalance of the deal
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(H.stream):
+        ev0.record(H.stream)
+        core()
+        ev1.record(H.stream)
+    torch.cuda.synchronize()
+    my_ms = ev0.elapsed_time(ev1)
+    busy = [my_ms]
+    if H.world > 1:
+        t = torch.zeros(H.world, device="cuda")
+        t[rank] = my_ms
+        H.dist.all_reduce(t)
+        busy = [float(v) for v in t.tolist()]
+    eng.profile_begin()
+    with torch.cuda.stream(H.stream):
+        core()
+    prof = eng.profile_end()
+    pk = peaks()
+    frames = float(sum(G_all)) * steps
+    audio_s = sum(vcfg.out_samples(int(g)) for g in G_all) / vcfg.sample_rate
+    flops_all = sum(f5_work(cfg, n, n // 2)["flops_total"] for n in Ns_all)
+    h2d = int(audio_h.numel() * 2 + ids_h.numel() * 4 + noise_h.numel() * 4)
+    res = {
+        "value": frames / (ms / 1e3), "ms_per_step": ms / steps, "rtf": (ms / 1e3 / steps) / audio_s,
+        "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nv * 2),
+                "ms_per_step": ms_e2e / steps, "rtf": (ms_e2e / 1e3 / steps) / audio_s, "api": "b200tts_f5_bigvgan_pipeline_ragged (host buffers)",
+                "bytes_are": "this rank's share"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+        "rank_busy_ms": [round(b, 2) for b in busy], "tail_imbalance": (max(busy) / (sum(busy) / len(busy)) - 1.0) if busy else None,
+        "utterances_per_rank": [len(s) for s in shards],
+        "workload": (f"F5-TTS NFE={cfg.nfe} + BigVGAN-v2 24 kHz, batch of {len(utts)} synthetic utterances (seeds 1000+i, references uniform in "
+                     f"[4 s, 8 s] -> N in [{min(Ns_all)}, {max(Ns_all)}], {args.n_text} text ids) dealt longest-first to {H.world} GPU(s); each "
+                     "rank runs its share as ONE ragged batch [BASELINE.json configs[3]]"),
+    }
+    total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
+    kname = {2: "fp16", 1: "bf16"}.get(int(prec), "f32")
+    chain = prof.get("f5.chain")
+    if chain and chain["ms"] > 0:
+        steps_n = cfg.nfe - 1
+        fl = sum(f5_work(cfg, int(n), int(n) // 2)["flops_chain_step"] for n in Ns) * steps_n
+        ach = fl / (chain["ms"] / 1e3) / 1e12
+        res["roofline"] = {"bound": "tensor", "kernel": f"dit_chain_kernel ({kname}: out-proj + LN + ff1 + ff2 + LN + next q|k|v per launch)",
+                           "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                           "traffic": ncu_traffic("f5.chain"), "peak_source": pk["source"] + " (sustained cuBLAS bf16; fp16 has the same tensor rate)",
+                           "avg_launch_ms": chain["ms"] / max(chain["launches"], 1), "share_of_step": chain["ms"] / total_ms, "rank": 0}
+    res["dit_tflops_overall"] = flops_all / (ms / steps / 1e3) / 1e12
+    res["dit_frac_of_tensor_peak"] = res["dit_tflops_overall"] / (pk["bf16_tflops_sustained"] * H.world)
+    return res
+
+
 def bench_indextts_vocoder(args, H, eng, rank, prec, steps, warmup):
     """Vocoder half of BASELINE.json configs[4] (IndexTTS_F, S latent rows -> 1024*(S-2)+30 samples) through the host-buffer
     C ABI call a reference script would make: H2D of the latent and conditioning vectors, D2H of the PCM inside the timed
@@ -629,7 +737,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "f5", "bigvgan", "indextts_vocoder", "indextts_gpt", "indextts"])
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "config4", "f5", "bigvgan", "indextts_vocoder", "indextts_gpt", "indextts"])
+    ap.add_argument("--config4-utterances", type=int, default=64)
     ap.add_argument("--new-tokens", type=int, default=256, help="indextts_gpt workload: E calls per sentence (prefill + decode)")
     ap.add_argument("--gpt-text", type=int, default=60, help="indextts_gpt workload: text ids per sentence")
     ap.add_argument("--latent-rows", type=int, default=142, help="indextts_vocoder workload: rows of save_hidden_state")
@@ -684,8 +793,8 @@ def main():
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
     H = Harness(torch, dist, stream, world)
-    need_f5 = args.workload in ("f5", "pipeline")
-    need_vgan = args.workload in ("bigvgan", "pipeline")
+    need_f5 = args.workload in ("f5", "pipeline", "config4")
+    need_vgan = args.workload in ("bigvgan", "pipeline", "config4")
     if args.workload in ("indextts_vocoder", "indextts"):
         cfgv = config.INDEXTTS_VOCODER
         state = weights.ivgan_engine_tensors(synth.ivgan_state(777), cfgv) if rank == 0 else None
@@ -733,6 +842,8 @@ def main():
         dtype = "bf16 weights, fp32 activations / cache / accumulation" if prec == capi.BF16 else "f32"
     elif args.workload == "f5":
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
+    elif args.workload == "config4":
+        res = bench_config4(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
     else:
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, with_vocoder=True, U=args.utterances, sampler=sampler)
         if not args.no_extras:
@@ -745,7 +856,8 @@ def main():
     if rank == 0:
         workload = res.pop("workload")
         line = {"metric": "mel_frames_per_s", "value": res.pop("value"), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": "strong" if args.workload == "config4" else "weak",
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic",
                 "config": {"workload": workload, "parallelism": f"dp{world} (utterance sharding, weights NCCL-broadcast at load)",
                            "l2": "per-step working set (activations + weights, > 0.5 GB) exceeds the 126 MB L2; no explicit flush"}}
@@ -798,14 +910,14 @@ def main():
                 r = cpu_f5(args.audio_len, args.n_text, 2, cores)
                 G = r["N"] - r["ref_len"]
                 tot = r["pre_s"] + (config.F5.nfe - 1) * r["step_s"]
-                if args.workload == "pipeline":
+                if args.workload in ("pipeline", "config4"):
                     r["bigvgan_s"] = cpu_bigvgan(G, 1, cores)
                     tot += r["bigvgan_s"]
                 else:
                     tot += r["decode_s"]
                 line["cpu_baseline"] = {"value": G / tot, "unit": "mel-frames/s", "cores": cores, "kind": "port",
                                         "sample": f"ONE utterance of the batch: graph A, 2 of {config.F5.nfe - 1} DiT steps (extrapolated), "
-                                                  + ("BigVGAN on its generated frames" if args.workload == "pipeline" else "graph C")
+                                                  + ("BigVGAN on its generated frames" if args.workload in ("pipeline", "config4") else "graph C")
                                                   + "; oracle (torch-CPU fp32 restatement of the reference modules; ORT is not installable offline)",
                                         "parts_s": r}
         print(json.dumps(line), flush=True)

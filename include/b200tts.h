@@ -165,6 +165,21 @@ int b200tts_f5_bigvgan_pipeline_device(b200tts_engine* e, int U, const int16_t* 
                                        int n_text, int64_t max_duration, const float* noise_dev, int precision, int n_steps,
                                        int16_t* wav_dev, int16_t* wav_vocos_dev, float* mel_dev);
 
+/* The same pipeline for a RAGGED batch (configs[3]: 64 utterances whose references last 4-8 s): every utterance has its own
+ * L[u], n_text[u], max_duration[u] (host arrays of U entries) and all buffers are concatenated in utterance order --
+ * audio [sum L], text_ids [sum n_text], noise [sum N][100] -> wav [sum (256*G_u + 30)], wav_vocos (optional) [sum 256*(G_u - 1)],
+ * mel (optional) [sum N][100]. The utterances share ONE DiT loop (row-wise GEMMs over all 2*sum(N) rows; attention, RoPE and
+ * V^T by per-sequence tables), so every utterance's result equals its single run (reference: one utterance per script run,
+ * F5-TTS-ONNX-Inference.py:227-311). */
+int b200tts_f5_bigvgan_pipeline_ragged(b200tts_engine* e, int U, const int16_t* audio_host, const int64_t* L,
+                                       const int32_t* text_ids_host, const int32_t* n_text, const int64_t* max_duration,
+                                       const float* noise_host, int precision, int n_steps, int16_t* wav_host,
+                                       int16_t* wav_vocos_host, float* mel_host);
+int b200tts_f5_bigvgan_pipeline_ragged_device(b200tts_engine* e, int U, const int16_t* audio_dev, const int64_t* L,
+                                              const int32_t* text_ids_dev, const int32_t* n_text, const int64_t* max_duration,
+                                              const float* noise_dev, int precision, int n_steps, int16_t* wav_dev,
+                                              int16_t* wav_vocos_dev, float* mel_dev);
+
 /* ---- single-op entry points (parity tests of the kernels through the boundary) -------------------------
  * Anti-aliased SnakeBeta (BigVGAN/modeling_modified/act.py:25-29): x (B, C, L) fp32 host in the reference
  * layout -> y (B, C, L) (post=0) or (B, C, L+30) (post=1, the bigvgan.py:370,381-382 tables). alpha_log /

@@ -302,3 +302,37 @@ def test_f5_iobinding_loop(f5, g):
     got = ort.OrtValue.numpy(io.get_outputs()[0])
     assert int(inputs[-1].numpy()[0]) == 31
     assert np.abs(got - g["noise_after_31"]).max() <= 1e-3
+
+
+# ---- ragged batches (config 4: utterances of different lengths share one DiT loop) -----------------------------------------
+def test_ragged_batch_equals_single_utterances(f5, g):
+    """Three utterances of different (audio length, text length, max_duration) through b200tts_f5_bigvgan_pipeline_ragged ==
+    each of them alone (the reference runs one utterance per script run, F5-TTS-ONNX-Inference.py:227-311). Rows of a sequence
+    sit at other offsets of the row blocks / attention tiles in the batch; a row's result must not depend on that. One of them
+    is also held against the oracle on the CPU."""
+    from b200tts import weights as W
+    f5.load_state("bigvgan", W.bigvgan_engine_tensors(synth.bigvgan_state(1234)))
+    f5.bigvgan_build()
+    specs = [(9000, 13, 36 + 41), (16384, 20, 130), (12345, 17, 49 + 70)]          # (L, n_text, N): ref frames L//256+1 = 36, 65, 49
+    audios, texts, Ns, noises = [], [], [], []
+    for i, (L, nt, N) in enumerate(specs):
+        a, t, _, _ = synth.f5_inputs(50 + i, audio_len=L, n_text=nt)
+        audios.append(a.reshape(-1)); texts.append(t.reshape(-1)); Ns.append(N)
+        noises.append(np.random.default_rng(90 + i).standard_normal((N, 100), dtype=np.float32))
+    for prec, steps in ((capi.F16, 31), (capi.BF16, 4)):
+        wavs, vocs, mels = f5.f5_bigvgan_pipeline_ragged(audios, texts, Ns, noises, precision=prec, n_steps=steps, with_vocos=True, return_mel=True)
+        for u, (L, nt, N) in enumerate(specs):
+            G = N - (L // 256 + 1)
+            assert wavs[u].shape == (256 * G + 30,) and vocs[u].shape == (256 * (G - 1),) and mels[u].shape == (N, 100)
+            w1, v1, m1 = f5.f5_bigvgan_pipeline(audios[u][None], texts[u][None], N, noises[u][None], precision=prec, n_steps=steps,
+                                               with_vocos=True, return_mel=True)
+            np.testing.assert_allclose(mels[u], m1[0], rtol=0, atol=2e-5)
+            assert snr_db(w1[0], wavs[u]) >= 60.0 and snr_db(v1[0], vocs[u]) >= 60.0
+    # fp16, all 31 steps, utterance 0 against the oracle
+    dsd, vsd = synth.f5_dit_state(int(g["dit_seed"])), synth.vocos_state(int(g["vocos_seed"]))
+    L, nt, N = specs[0]
+    wavs, vocs, mels = f5.f5_bigvgan_pipeline_ragged(audios, texts, Ns, noises, precision=capi.F16, with_vocos=True, return_mel=True)
+    want_pcm, want_mel, _ = R.f5_synthesize(audios[0].reshape(1, 1, -1), texts[0].reshape(1, -1), [N], noises[0][None], dsd, vsd, CFG,
+                                            steps=31, return_mel=True)
+    assert cosine(mels[0], want_mel.numpy()) >= 0.99999
+    assert snr_db(want_pcm.numpy().reshape(-1), vocs[0]) > 45.0

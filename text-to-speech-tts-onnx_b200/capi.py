@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200tts_f5_synthesize_batch_device": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp]),
     "b200tts_f5_bigvgan_pipeline": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp, _vp]),
     "b200tts_f5_bigvgan_pipeline_device": (_int, [_vp, _int, _vp, ctypes.c_int64, _vp, _int, ctypes.c_int64, _vp, _int, _int, _vp, _vp, _vp]),
+    "b200tts_f5_bigvgan_pipeline_ragged": (_int, [_vp, _int, _vp, _c_i64, _vp, _c_i32, _c_i64, _vp, _int, _int, _vp, _vp, _vp]),
+    "b200tts_f5_bigvgan_pipeline_ragged_device": (_int, [_vp, _int, _vp, _c_i64, _vp, _c_i32, _c_i64, _vp, _int, _int, _vp, _vp, _vp]),
     "b200tts_aa_activation": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp]),
     "b200tts_conv1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _int, _int, _vp, _int, _vp]),
     "b200tts_conv_transpose1d": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _int, _vp]),
@@ -384,6 +386,58 @@ class Engine:
                                                                 int(max_duration), _vp(noise_ptr), int(precision), int(n_steps),
                                                                 _vp(wav_ptr), _vp(wav_vocos_ptr or 0), _vp(mel_ptr or 0)),
                     "f5_bigvgan_pipeline_device")
+
+    def f5_bigvgan_pipeline_ragged(self, audios, text_ids, max_durations, noises, precision=BF16, n_steps: int = -1, with_vocos=False,
+                                   return_mel=False, hop: int = 256, out=None):
+        """Ragged batch: lists of per-utterance arrays -- audios[u] (L_u,) i16, text_ids[u] (n_u,) i32, max_durations[u], noises[u]
+        (N_u, 100) f32 -> list of BigVGAN wavs (256*G_u + 30,) [, list of Vocos wavs] [, list of mels], ONE host-buffer C call."""
+        U = len(audios)
+        au = [np.ascontiguousarray(a, dtype=np.int16).reshape(-1) for a in audios]
+        tx = [np.ascontiguousarray(t, dtype=np.int32).reshape(-1) for t in text_ids]
+        Ns = np.asarray([int(n) for n in max_durations], dtype=np.int64)
+        nz = [_f32(z).reshape(int(n), 100) for z, n in zip(noises, Ns)]
+        L = np.asarray([a.size for a in au], dtype=np.int64)
+        nt = np.asarray([t.size for t in tx], dtype=np.int32)
+        G = Ns - (L // hop + 1)
+        nv, ns = hop * G + 30, hop * (G - 1)
+        a_cat, t_cat, z_cat = np.concatenate(au), np.concatenate(tx), np.concatenate(nz, 0)
+        wav = np.empty(int(nv.sum()), dtype=np.int16) if out is None else out
+        voc = np.empty(int(ns.sum()), dtype=np.int16) if with_vocos else None
+        mel = np.empty((int(Ns.sum()), 100), dtype=np.float32) if return_mel else None
+        self.f5_bigvgan_pipeline_ragged_concat(a_cat, L, t_cat, nt, Ns, z_cat, wav, precision=precision, n_steps=n_steps, voc=voc, mel=mel)
+        split = lambda x, sizes: [x[int(o):int(o + n)] for o, n in zip(np.concatenate([[0], np.cumsum(sizes)[:-1]]), sizes)]
+        res = [split(wav, nv)]
+        if with_vocos:
+            res.append(split(voc, ns))
+        if return_mel:
+            res.append(split(mel, Ns))
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def f5_bigvgan_pipeline_ragged_concat(self, audio_cat, L, ids_cat, n_text, max_duration, noise_cat, wav, precision=BF16, n_steps: int = -1,
+                                          voc=None, mel=None):
+        """The C call itself on already concatenated host buffers (bench.py: pinned): audio_cat i16 [sum L], ids_cat i32 [sum n_text],
+        noise_cat f32 [sum N, 100]; L / max_duration int64 [U], n_text int32 [U]; wav i16 [sum (256 G + 30)] (caller-owned)."""
+        L = np.ascontiguousarray(L, dtype=np.int64)
+        n_text = np.ascontiguousarray(n_text, dtype=np.int32)
+        max_duration = np.ascontiguousarray(max_duration, dtype=np.int64)
+        assert audio_cat.dtype == np.int16 and ids_cat.dtype == np.int32 and noise_cat.dtype == np.float32 and wav.dtype == np.int16
+        assert audio_cat.size == int(L.sum()) and ids_cat.size == int(n_text.sum()) and noise_cat.size == int(max_duration.sum()) * 100
+        self._check(self.lib.b200tts_f5_bigvgan_pipeline_ragged(self.handle, int(L.size), _ptr(audio_cat), L.ctypes.data_as(_c_i64), _ptr(ids_cat),
+                                                                n_text.ctypes.data_as(_c_i32), max_duration.ctypes.data_as(_c_i64),
+                                                                _ptr(noise_cat), int(precision), int(n_steps), _ptr(wav), _ptr(voc), _ptr(mel)),
+                    "f5_bigvgan_pipeline_ragged")
+
+    def f5_bigvgan_pipeline_ragged_device(self, U, audio_ptr, L, ids_ptr, n_text, max_duration, noise_ptr, wav_ptr, precision=BF16,
+                                          n_steps: int = -1, wav_vocos_ptr: int = 0, mel_ptr: int = 0):
+        """L, n_text, max_duration: host numpy arrays (int64, int32, int64) of U entries; the data pointers are device pointers."""
+        L = np.ascontiguousarray(L, dtype=np.int64)
+        n_text = np.ascontiguousarray(n_text, dtype=np.int32)
+        max_duration = np.ascontiguousarray(max_duration, dtype=np.int64)
+        self._check(self.lib.b200tts_f5_bigvgan_pipeline_ragged_device(self.handle, int(U), _vp(audio_ptr), L.ctypes.data_as(_c_i64),
+                                                                       _vp(ids_ptr), n_text.ctypes.data_as(_c_i32),
+                                                                       max_duration.ctypes.data_as(_c_i64), _vp(noise_ptr), int(precision),
+                                                                       int(n_steps), _vp(wav_ptr), _vp(wav_vocos_ptr or 0), _vp(mel_ptr or 0)),
+                    "f5_bigvgan_pipeline_ragged_device")
 
     def bench_rowgemm(self, B, M, N, Cin, taps=1, dil=1, groups=1, epilogue=0, iters=20) -> float:
         """Average ms per launch of the tensor-core shifted-row GEMM on synthetic operands (tools/bench_gemm.py)."""

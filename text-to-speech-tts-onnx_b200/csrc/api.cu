@@ -488,6 +488,7 @@ static void synth_batch_device(Engine& E, int U, const int16_t* audio_dev, int64
                   (long long)(uintptr_t)noise_dev, precision, n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev,
                   (long long)(uintptr_t)vgan_pcm_dev},
               [&] {
+                f5_begin(E, (int)N, U);
                 for (int u = 0; u < U; ++u)
                   f5_preprocess(E, audio_dev + (size_t)u * L, L, ids_dev + (size_t)u * n_text, n_text, (int)N, u, U, precision);
                 B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)U * N * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -514,6 +515,49 @@ int b200tts_f5_synthesize_batch_device(b200tts_engine* e, int U, const int16_t* 
     B2_CHECK(precision != PREC_F32 || U == 1, "f5_synthesize_batch_device: the fp32 parity engine takes one utterance at a time");
     synth_batch_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, pcm_dev, mel_dev);
   });
+}
+
+// Ragged batch (BASELINE.json configs[3]: utterances with 4-8 s references share one DiT loop): per-utterance lengths, all
+// buffers concatenated in utterance order. pcm_dev (Vocos) and vgan_pcm_dev (BigVGAN) are optional.
+static void synth_ragged_device(Engine& E, int U, const int16_t* audio_dev, const int64_t* L, const int32_t* ids_dev, const int32_t* n_text,
+                                const int64_t* Ns, const float* noise_dev, int precision, int n_steps, int16_t* pcm_dev, float* mel_dev,
+                                int16_t* vgan_pcm_dev) {
+  cudaStream_t s = E.stream;
+  const int nm = f5_n_mels(E);
+  std::vector<int> Nv(U), Fv(U);
+  std::vector<long long> key = {32, U, (long long)(uintptr_t)audio_dev, (long long)(uintptr_t)ids_dev, (long long)(uintptr_t)noise_dev, precision,
+                                n_steps, (long long)(uintptr_t)pcm_dev, (long long)(uintptr_t)mel_dev, (long long)(uintptr_t)vgan_pcm_dev};
+  long Ntot = 0;
+  for (int u = 0; u < U; ++u) {
+    B2_CHECK(L[u] > 0 && n_text[u] > 0 && Ns[u] > L[u] / 256 + 2 && Ns[u] < (1 << 30), "ragged batch: bad sizes");
+    Nv[u] = (int)Ns[u]; Fv[u] = (int)(L[u] / 256 + 1); Ntot += Nv[u];
+    key.push_back(L[u]); key.push_back(n_text[u]); key.push_back(Ns[u]);
+  }
+  f5_begin_ragged(E, U, Nv.data());              // layout + per-row tables: outside the capture (host -> device uploads)
+  run_graphed(E, key,
+              [&] {
+                f5_begin_ragged(E, U, Nv.data());  // (no upload: the tables match)
+                size_t ao = 0, io = 0;
+                for (int u = 0; u < U; ++u) {
+                  f5_preprocess(E, audio_dev + ao, L[u], ids_dev + io, n_text[u], Nv[u], u, U, precision);
+                  ao += (size_t)L[u]; io += (size_t)n_text[u];
+                }
+                B2_CUDA(cudaMemcpyAsync(f5_noise(E), noise_dev, (size_t)Ntot * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                f5_prepare_cond(E);
+                f5_steps(E, 0, n_steps < 0 ? f5_nfe(E) - 1 : n_steps, precision);
+                size_t po = 0, vo = 0;
+                for (int u = 0; u < U; ++u) {
+                  const int G = Nv[u] - Fv[u];
+                  if (pcm_dev) f5_decode(E, f5_noise(E, u), Nv[u], Fv[u], pcm_dev + po, nullptr, precision);
+                  if (vgan_pcm_dev)       // generated frames of utterance u, channels-last as they lie
+                    bigvgan_forward(E, *E.bigvgan, f5_noise(E, u) + (size_t)Fv[u] * nm, 1, G, precision, vgan_pcm_dev + vo, nullptr, nullptr,
+                                    (long)G * nm);
+                  po += (size_t)256 * (G - 1);
+                  vo += (size_t)bigvgan_out_samples(*E.bigvgan, G);
+                }
+                if (mel_dev) B2_CUDA(cudaMemcpyAsync(mel_dev, f5_noise(E), (size_t)Ntot * nm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+              },
+              [&] { f5_restore_ragged(E, U, Nv.data(), Fv.data()); });
 }
 
 static void pipeline_check(Engine& E, int U, int64_t L, int n_text, int64_t N, int precision) {
@@ -561,6 +605,57 @@ int b200tts_f5_bigvgan_pipeline(b200tts_engine* e, int U, const int16_t* audio_h
     synth_batch_device(E, U, d_audio, L, d_ids, n_text, N, d_noise, precision, n_steps, d_voc, d_mel, d_wav);
     B2_CUDA(cudaMemcpyAsync(wav_host, d_wav, (size_t)U * nv * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
     if (wav_vocos_host) B2_CUDA(cudaMemcpyAsync(wav_vocos_host, d_voc, (size_t)U * ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel, nmel * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int b200tts_f5_bigvgan_pipeline_ragged_device(b200tts_engine* e, int U, const int16_t* audio_dev, const int64_t* L,
+                                              const int32_t* text_ids_dev, const int32_t* n_text, const int64_t* max_duration,
+                                              const float* noise_dev, int precision, int n_steps, int16_t* wav_dev, int16_t* wav_vocos_dev,
+                                              float* mel_dev) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_dev && L && text_ids_dev && n_text && max_duration && noise_dev && wav_dev, "f5_bigvgan_pipeline_ragged_device: null buffer");
+    B2_CHECK(U >= 1 && U <= 4096, "f5_bigvgan_pipeline_ragged_device: batch size");
+    B2_CHECK(E.f5 != nullptr && E.bigvgan != nullptr, "F5 / BigVGAN weights are not built");
+    B2_CHECK(precision != PREC_F32 || U == 1, "the fp32 parity engine takes one utterance at a time");
+    synth_ragged_device(E, U, audio_dev, L, text_ids_dev, n_text, max_duration, noise_dev, precision, n_steps, wav_vocos_dev, mel_dev, wav_dev);
+  });
+}
+
+int b200tts_f5_bigvgan_pipeline_ragged(b200tts_engine* e, int U, const int16_t* audio_host, const int64_t* L, const int32_t* text_ids_host,
+                                       const int32_t* n_text, const int64_t* max_duration, const float* noise_host, int precision, int n_steps,
+                                       int16_t* wav_host, int16_t* wav_vocos_host, float* mel_host) {
+  return guarded([&] {
+    Engine& E = eng(e);
+    B2_CHECK(audio_host && L && text_ids_host && n_text && max_duration && noise_host && wav_host, "f5_bigvgan_pipeline_ragged: null buffer");
+    B2_CHECK(U >= 1 && U <= 4096, "f5_bigvgan_pipeline_ragged: batch size");
+    B2_CHECK(E.f5 != nullptr && E.bigvgan != nullptr, "F5 / BigVGAN weights are not built");
+    B2_CHECK(precision != PREC_F32 || U == 1, "the fp32 parity engine takes one utterance at a time");
+    cudaStream_t s = E.stream;
+    const int nm = f5_n_mels(E);
+    long Ltot = 0, ttot = 0, Ntot = 0, nv = 0, ns = 0;
+    for (int u = 0; u < U; ++u) {
+      B2_CHECK(L[u] > 0 && n_text[u] > 0 && max_duration[u] > L[u] / 256 + 2, "f5_bigvgan_pipeline_ragged: bad sizes");
+      const long G = max_duration[u] - (L[u] / 256 + 1);
+      Ltot += L[u]; ttot += n_text[u]; Ntot += max_duration[u];
+      nv += bigvgan_out_samples(*E.bigvgan, (int)G); ns += 256L * (G - 1);
+    }
+    // persistent staging (stable addresses -> graph replay): i16 [audio | wav | wav_vocos], f32 [noise], f32 [mel | ids]
+    const size_t Lp = (size_t)round_up(Ltot, 8), nvp = (size_t)round_up(nv, 8), nsp = (size_t)round_up(ns, 8), nmel = (size_t)Ntot * nm;
+    E.io_i16.reserve(Lp + nvp + nsp);
+    E.io_f32a.reserve(nmel);
+    E.io_f32b.reserve(nmel + (size_t)round_up(ttot, 4));
+    int16_t* d_audio = E.io_i16.p; int16_t* d_wav = d_audio + Lp; int16_t* d_voc = wav_vocos_host ? d_wav + nvp : nullptr;
+    float* d_noise = E.io_f32a.p; float* d_mel = mel_host ? E.io_f32b.p : nullptr;
+    int* d_ids = reinterpret_cast<int*>(E.io_f32b.p + nmel);
+    B2_CUDA(cudaMemcpyAsync(d_audio, audio_host, (size_t)Ltot * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_ids, text_ids_host, (size_t)ttot * sizeof(int), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(d_noise, noise_host, nmel * sizeof(float), cudaMemcpyHostToDevice, s));
+    synth_ragged_device(E, U, d_audio, L, d_ids, n_text, max_duration, d_noise, precision, n_steps, d_voc, d_mel, d_wav);
+    B2_CUDA(cudaMemcpyAsync(wav_host, d_wav, (size_t)nv * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
+    if (wav_vocos_host) B2_CUDA(cudaMemcpyAsync(wav_vocos_host, d_voc, (size_t)ns * sizeof(int16_t), cudaMemcpyDeviceToHost, s));
     if (mel_host) B2_CUDA(cudaMemcpyAsync(mel_host, d_mel, nmel * sizeof(float), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
   });

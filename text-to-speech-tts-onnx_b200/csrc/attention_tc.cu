@@ -50,6 +50,8 @@ struct AttnArgs {
   __nv_bfloat16* out;
   int ldo;
   int f16;            // q, k, v, P and out are IEEE fp16 instead of bf16
+  const int* seq_off; // ragged batches: first row of every sequence in the concatenated [rows][2*H*64] tensor (null: b * N)
+  const int* seq_len; // ragged batches: tokens of every sequence (null: N)
   unsigned long long* trace;   // debug: [CTA][64] %globaltimer stamps (B200TTS_ATTN_TRACE=<file>, tools/attn_trace.py)
 };
 
@@ -123,7 +125,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int nblocks = (a.N + BKEY - 1) / BKEY;
+  // ragged batch: sequence b has Nb tokens starting at row rb0 of ONE concatenated tensor (TMA batch coordinate 0); rows past
+  // its end belong to the next sequence and are masked like the keys of a ragged last block
+  const int Nb = a.seq_len ? __ldg(a.seq_len + b) : a.N;
+  const int rb0 = a.seq_off ? __ldg(a.seq_off + b) : 0;
+  const int bz = a.seq_off ? 0 : b;
+  if (q0 >= Nb) return;                           // grid.x covers the longest sequence (whole CTA leaves: nothing allocated yet)
+  const int nblocks = (Nb + BKEY - 1) / BKEY;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();       // SWIZZLE_128B tiles need a 1024-byte aligned base
@@ -153,14 +161,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   if (warp == WARP_TMA) {
     if (lane == 0) {
       mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(sQ, &map_qk, q_full, h * HD, q0, b);
+      tma_load_3d(sQ, &map_qk, q_full, h * HD, rb0 + q0, bz);
       const int bh = b * a.H + h;
       for (int j = 0; j < nblocks; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (uint32_t)(j / KV_STAGES) & 1u;
         mbar_wait(&k_empty[s], ph ^ 1u);
         mbar_expect_tx(&k_full[s], K_BYTES);
-        tma_load_3d(sK + s * K_BYTES, &map_qk, &k_full[s], a.H * HD + h * HD, j * BKEY, b);
+        tma_load_3d(sK + s * K_BYTES, &map_qk, &k_full[s], a.H * HD + h * HD, rb0 + j * BKEY, bz);
         mbar_wait(&v_empty[s], ph ^ 1u);
         mbar_expect_tx(&v_full[s], V_BYTES);
         tma_load_3d(sV + s * V_BYTES, &map_v, &v_full[s], j * BKEY, 0, bh);
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     const int sw = r & 7;
 
     for (int j = 0; j < nblocks; ++j) {
-      const int kvalid = a.N - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
+      const int kvalid = Nb - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 2);
@@ -325,9 +333,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     }
     softmax_bar();
     const int q = q0 + r;
-    if (q < a.N) {
+    if (q < Nb) {
       const float* srcx = xch + (g * BQ + r) * 32;
-      __nv_bfloat16* dst = a.out + ((long)b * a.N + q) * a.ldo + h * HD + g * 32;
+      __nv_bfloat16* dst = a.out + ((a.seq_off ? (long)rb0 : (long)b * a.N) + q) * a.ldo + h * HD + g * 32;
 #pragma unroll
       for (int k = 0; k < 8; k += 2) {
         const float4 x0 = *reinterpret_cast<const float4*>(srcx + ((k ^ sw) << 2));
@@ -353,19 +361,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
 
 }  // namespace
 
-void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream, int f16) {
+void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __nv_bfloat16* out, int S, int N, int H, cudaStream_t stream, int f16,
+                  const int* d_seq_off, const int* d_seq_len, long total_rows) {
   B2_CHECK(S > 0 && N > 0 && H > 0, "attention_tc: empty problem");
   B2_CHECK(ldv % 8 == 0 && ldv >= N, "attention_tc: V^T row stride must be a multiple of 8 and >= N");
   CUtensorMap map_qk, map_v;
-  // q|k: [S][N][2*H*64] bf16 -> dims {2*H*64, N, S}, box {64, 128, 1}
-  tc_encode_map(&map_qk, qk, (uint64_t)2 * H * HD, (uint64_t)N, (uint64_t)S, (uint64_t)2 * H * HD, (uint64_t)N * 2 * H * HD, BQ);
-  // V^T: [S*H][64][ldv] bf16 -> dims {N keys, 64 d, S*H}, box {64 keys, 64 d, 1}
-  tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
+  const bool ragged = d_seq_off != nullptr;
+  B2_CHECK(ragged == (d_seq_len != nullptr) && (!ragged || total_rows > 0), "attention_tc: ragged batches need offsets, lengths and the row total");
+  if (ragged) {
+    // one concatenated [total_rows][2*H*64] tensor (rows past the end read as zero); N = the longest sequence
+    tc_encode_map(&map_qk, qk, (uint64_t)2 * H * HD, (uint64_t)total_rows, 1, (uint64_t)2 * H * HD, (uint64_t)total_rows * 2 * H * HD, BQ);
+    // V^T rows are ldv wide for every sequence: the keys beyond a sequence's length hold stale (finite) values and meet P = 0
+    tc_encode_map(&map_v, vT, (uint64_t)ldv, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
+  } else {
+    // q|k: [S][N][2*H*64] -> dims {2*H*64, N, S}, box {64, 128, 1}
+    tc_encode_map(&map_qk, qk, (uint64_t)2 * H * HD, (uint64_t)N, (uint64_t)S, (uint64_t)2 * H * HD, (uint64_t)N * 2 * H * HD, BQ);
+    // V^T: [S*H][64][ldv] -> dims {N keys, 64 d, S*H}, box {64 keys, 64 d, 1}
+    tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
+  }
   static std::once_flag once;
   std::call_once(once, [] {
     B2_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
-  AttnArgs a{N, H, out, H * HD, f16, nullptr};
+  AttnArgs a{N, H, out, H * HD, f16, d_seq_off, d_seq_len, nullptr};
   static DevBuf<unsigned long long> trace_buf;
   const char* trace_path = getenv("B200TTS_ATTN_TRACE");
   const size_t ncta = (size_t)ceil_div(N, BQ) * H * S;

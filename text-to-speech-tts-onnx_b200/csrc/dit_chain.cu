@@ -57,6 +57,7 @@ struct ChainArgs {
   __nv_bfloat16* qk16;
   const __half2* rope_cs;
   int rope_rows;
+  const int2* rowinfo;
   __nv_bfloat16* vt_out;
   int vt_ld, vt_heads;
   float* stats;
@@ -372,6 +373,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     a.o_bstride = 0; a.o_shift = 0; a.accumulate = 0; a.scale = 1.0f; a.out2 = nullptr; a.f16 = c.f16;
     a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0; a.vt_ld = 0; a.vt_heads = 0;
     a.out = nullptr; a.ldo = 0; a.o_limit = 0; a.out_bf16 = 0; a.bias = nullptr; a.gate = nullptr; a.res = nullptr;
+    a.rowinfo = c.rowinfo;
     uint32_t t = 0;
     const uint64_t x_policy = c.l2hint ? l2_policy_evict_last() : 0ull;
     for (int rb = team; rb < c.nrb; rb += c.teams) {
@@ -489,7 +491,7 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.x = d.x; c.n16 = d.n16; c.ff16 = d.ff16; c.n16b = d.n16b;
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
-  c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
+  c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.rowinfo = d.rowinfo; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
   c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
   { const char* v = getenv("B200TTS_CHAIN_L2HINT"); c.l2hint = v != nullptr && atoi(v) != 0; }
   CUtensorMap mA[4], mB[4];

@@ -29,6 +29,7 @@ struct DitChain {
   __nv_bfloat16* qk16 = nullptr;   // [R][2D] roped q | k
   const __half2* rope_cs = nullptr;
   int rope_rows = 1;
+  const int2* rowinfo = nullptr;   // ragged batches: (sequence, position) per row (rowgemm.cuh)
   __nv_bfloat16* vt_out = nullptr;
   int vt_ld = 0, vt_heads = 0;
   // team synchronisation scratch (sizes below); `flags` must be zero when the kernel starts

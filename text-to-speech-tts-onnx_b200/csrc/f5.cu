@@ -94,8 +94,16 @@ struct F5Model {
   long wsi_len = 0;
 
   // ---- per-utterance state + workspaces (grow-only) ----
-  int N = 0, ref_len = 0, Npad = 0;
-  int U = 1;                 // utterances in flight (equal N): rows of every DiT tensor are [u][cfg row][t]
+  int N = 0, ref_len = 0, Npad = 0;   // N = longest max_duration of the batch (every utterance's, when they are equal)
+  int U = 1;                 // utterances in flight: rows of every DiT tensor are [u][cfg row][t], utterances concatenated
+  // ragged batches (length-bucketed micro-batches; utterance u has Nu[u] frames, Fu[u] of them reference):
+  std::vector<int> Nu, Fu;
+  std::vector<long> tok_off; // rows of noise / cond before utterance u (sequence 2u+b starts at row 2*tok_off[u] + b*Nu[u])
+  long Ntot = 0;             // sum of Nu
+  bool ragged = false;       // the Nu differ: RoPE / V^T / attention take per-row (sequence, position) tables
+  DevBuf<int> seq_off, seq_len;      // [2U] first row / length of every sequence
+  DevBuf<int2> rowinfo;              // [2*Ntot] (sequence, position) of every DiT row
+  std::vector<int> tables_for;       // the Nu the device tables were built for (skip the upload when a batch shape repeats)
   DevBuf<float> noise, cond, cond_drop, cproj, x, h, pred, rope_c, rope_s;
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
@@ -373,24 +381,65 @@ int f5_seq_len(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); ret
 int f5_cond_dim(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->cond_dim; }
 int f5_n_mels(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->n_mels; }
 int f5_nfe(const Engine& e) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return e.f5->nfe; }
-float* f5_cond(Engine& e, int u) { F5Model& m = model(e); return m.cond.p + (size_t)u * m.N * m.cond_dim; }
-float* f5_cond_drop(Engine& e, int u) { F5Model& m = model(e); return m.cond_drop.p + (size_t)u * m.N * m.cond_dim; }
-float* f5_noise(Engine& e, int u) { F5Model& m = model(e); return m.noise.p + (size_t)u * m.N * m.n_mels; }
+static long tok_of(const F5Model& m, int u) {
+  B2_CHECK(u >= 0 && u < (int)m.tok_off.size(), "utterance index outside the batch");
+  return m.tok_off[u];
+}
+float* f5_cond(Engine& e, int u) { F5Model& m = model(e); return m.cond.p + (size_t)tok_of(m, u) * m.cond_dim; }
+float* f5_cond_drop(Engine& e, int u) { F5Model& m = model(e); return m.cond_drop.p + (size_t)tok_of(m, u) * m.cond_dim; }
+float* f5_noise(Engine& e, int u) { F5Model& m = model(e); return m.noise.p + (size_t)tok_of(m, u) * m.n_mels; }
+long f5_tok_offset(const Engine& e, int u) { B2_CHECK(e.f5 != nullptr, "F5 not built"); return tok_of(*e.f5, u); }
+
+// host-side shape state of a batch: per-utterance lengths, offsets, totals (no device work)
+static void set_shape(F5Model& m, int U, const int* Ns, const int* Fs) {
+  B2_CHECK(U >= 1 && U <= 4096, "batch of utterances must be in [1, 4096]");
+  m.U = U; m.Nu.assign(Ns, Ns + U); m.Fu.assign(U, 0); m.tok_off.assign(U, 0);
+  m.N = 0; m.Ntot = 0; m.ragged = false;
+  for (int u = 0; u < U; ++u) {
+    B2_CHECK(Ns[u] > 0 && Ns[u] <= m.max_frames, "max_duration must be in [1, MAX_SIGNAL_LENGTH]");
+    if (Fs) m.Fu[u] = Fs[u];
+    m.tok_off[u] = m.Ntot;
+    m.Ntot += Ns[u];
+    if (Ns[u] > m.N) m.N = Ns[u];
+    if (Ns[u] != Ns[0]) m.ragged = true;
+  }
+  m.Npad = (int)round_up(m.N, 8);
+  m.ref_len = m.Fu[0];
+  m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;     // rows [0, N) of the fp16-rounded tables
+}
+
+void f5_begin_ragged(Engine& e, int U, const int* Ns) {
+  F5Model& m = model(e);
+  set_shape(m, U, Ns, nullptr);
+  const size_t T = (size_t)m.Ntot, R = 2 * T;
+  m.noise.reserve(T * m.n_mels);
+  m.cond.reserve(T * m.cond_dim);
+  m.cond_drop.reserve(T * m.cond_dim);
+  m.cproj.reserve(R * m.D);
+  m.x.reserve(R * m.D);
+  m.h.reserve(R * m.D);
+  m.pred.reserve(R * m.n_mels);
+  if (m.ragged && m.tables_for != m.Nu) {   // per-sequence / per-row tables (host -> device: call this OUTSIDE a stream capture)
+    std::vector<int> so(2 * U), sl(2 * U);
+    std::vector<int2> ri(R);
+    for (int u = 0; u < U; ++u)
+      for (int b = 0; b < 2; ++b) {
+        const int sq = 2 * u + b;
+        so[sq] = (int)(2 * m.tok_off[u] + (long)b * m.Nu[u]); sl[sq] = m.Nu[u];
+        for (int t = 0; t < m.Nu[u]; ++t) ri[(size_t)so[sq] + t] = make_int2(sq, t);
+      }
+    m.seq_off.reserve(so.size()); m.seq_len.reserve(sl.size()); m.rowinfo.reserve(ri.size());
+    B2_CUDA(cudaMemcpyAsync(m.seq_off.p, so.data(), so.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+    B2_CUDA(cudaMemcpyAsync(m.seq_len.p, sl.data(), sl.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+    B2_CUDA(cudaMemcpyAsync(m.rowinfo.p, ri.data(), ri.size() * sizeof(int2), cudaMemcpyHostToDevice, e.stream));
+    B2_CUDA(cudaStreamSynchronize(e.stream));      // the host vectors go out of scope
+    m.tables_for = m.Nu;
+  }
+}
 
 void f5_begin(Engine& e, int N, int U) {
-  F5Model& m = model(e);
-  B2_CHECK(N > 0 && N <= m.max_frames, "max_duration must be in [1, MAX_SIGNAL_LENGTH]");
-  B2_CHECK(U >= 1 && U <= 4096, "batch of utterances must be in [1, 4096]");
-  m.N = N; m.Npad = (int)round_up(N, 8); m.U = U;
-  const size_t S = (size_t)2 * U;
-  m.noise.reserve((size_t)U * N * m.n_mels);
-  m.cond.reserve((size_t)U * N * m.cond_dim);
-  m.cond_drop.reserve((size_t)U * N * m.cond_dim);
-  m.cproj.reserve(S * N * m.D);
-  m.x.reserve(S * N * m.D);
-  m.h.reserve(S * N * m.D);
-  m.pred.reserve(S * N * m.n_mels);
-  m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;     // rows [0, N) of the fp16-rounded tables
+  std::vector<int> Ns((size_t)(U > 0 ? U : 1), N);
+  f5_begin_ragged(e, U, Ns.data());
 }
 
 void f5_set_rope(Engine& e, const float* d_cos, const float* d_sin) {
@@ -409,18 +458,19 @@ void f5_rope_buffers(Engine& e, float** d_cos, float** d_sin) {
 }
 
 void f5_restore_shape(Engine& e, int N, int ref_len, int U) {
-  F5Model& m = model(e);
-  m.N = N; m.Npad = (int)round_up(N, 8); m.ref_len = ref_len; m.U = U;
-  m.cur_cos = m.rope_cos; m.cur_sin = m.rope_sin;
+  std::vector<int> Ns((size_t)U, N), Fs((size_t)U, ref_len);
+  set_shape(model(e), U, Ns.data(), Fs.data());
 }
+void f5_restore_ragged(Engine& e, int U, const int* Ns, const int* Fs) { set_shape(model(e), U, Ns, Fs); }
 
 void f5_prepare_cond(Engine& e) {
   F5Model& m = model(e);
   Epi ep; ep.bias = m.wc.bias.p;
   for (int u = 0; u < m.U; ++u) {             // sequence 2u = cond, 2u+1 = cond_drop of utterance u
-    const size_t co = (size_t)u * m.N * m.cond_dim, po = (size_t)2 * u * m.N * m.D;
-    linear(e, "f5.cond_proj", m.wc, 0, m.cond.p + co, m.cond_dim, m.N, m.cproj.p + po, m.D, ep);
-    linear(e, "f5.cond_proj", m.wc, 0, m.cond_drop.p + co, m.cond_dim, m.N, m.cproj.p + po + (size_t)m.N * m.D, m.D, ep);
+    const int Nu = m.Nu[u];
+    const size_t co = (size_t)m.tok_off[u] * m.cond_dim, po = (size_t)2 * m.tok_off[u] * m.D;
+    linear(e, "f5.cond_proj", m.wc, 0, m.cond.p + co, m.cond_dim, Nu, m.cproj.p + po, m.D, ep);
+    linear(e, "f5.cond_proj", m.wc, 0, m.cond_drop.p + co, m.cond_dim, Nu, m.cproj.p + po + (size_t)Nu * m.D, m.D, ep);
   }
 }
 
@@ -435,11 +485,12 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
   B2_CHECK(n_text >= 0 && n_text <= N, "text_ids longer than max_duration");
   B2_CHECK(F <= N, "max_duration shorter than the reference audio");
   B2_CHECK(u >= 0 && u < U, "utterance index outside the batch");
-  if (u == 0) f5_begin(e, N, U);
-  B2_CHECK(m.N == N && m.U == U, "utterances of one batch must share max_duration");
-  m.ref_len = F;
-  float* cond = m.cond.p + (size_t)u * N * m.cond_dim;
-  float* cond_drop = m.cond_drop.p + (size_t)u * N * m.cond_dim;
+  if (U == 1) f5_begin(e, N, 1);              // a batch (U > 1) is laid out by f5_begin / f5_begin_ragged before its first utterance
+  B2_CHECK(m.U == U && (int)m.Nu.size() == U && m.Nu[u] == N, "f5_preprocess: the batch layout (f5_begin_ragged) does not match this utterance");
+  m.Fu[u] = F;
+  if (u == 0) m.ref_len = F;
+  float* cond = m.cond.p + (size_t)m.tok_off[u] * m.cond_dim;
+  float* cond_drop = m.cond_drop.p + (size_t)m.tok_off[u] * m.cond_dim;
   // ---- STFT -> |X| -> mel -> log : cond[:, :n_mels] ----
   {
     ProfScope ps(e.prof, "f5.pre_elementwise", s);
@@ -510,16 +561,14 @@ void f5_preprocess(Engine& e, const int16_t* d_audio, long L, const int* d_text_
 // =============================================================================================
 namespace {
 
-void gconv(Engine& e, GConv& g, int fast, const void* x, int N, void* out, int out_bf16, int act, const float* res) {
-  F5Model& m = *e.f5;
+void gconv(Engine& e, GConv& g, int fast, const void* x, int N, int nseq, void* out, int out_bf16, int act, const float* res) {
   const int cg = g.C / g.groups;
   RowGemm p;
   p.x = x; p.x_bstride = (long)N * g.C; p.ldx = g.C; p.Lin = N;
   p.Cin = cg; p.N = cg; p.taps = g.k; p.dil = 1; p.center = (g.k - 1) / 2; p.groups = g.groups;
-  p.M = N; p.B = 2 * m.U;
+  p.M = N; p.B = nseq;
   p.out = out; p.o_bstride = (long)N * g.C; p.ldo = g.C; p.out_bf16 = out_bf16;
   p.bias = g.bias.p; p.act = act; p.res = res;
-  (void)m;
   ProfScope ps(e.prof, "f5.conv_pos", e.stream);
   if (fast) {
     const int f16 = fast == PREC_F16 ? 1 : 0;
@@ -542,14 +591,14 @@ void gconv(Engine& e, GConv& g, int fast, const void* x, int N, void* out, int o
 }
 
 void reserve_step(F5Model& m, bool fast) {
-  const size_t R = (size_t)2 * m.U * m.N;
+  const size_t R = (size_t)2 * m.Ntot;
   if (fast) {
     m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.n16b.reserve(R * m.D); m.att16.reserve(R * m.D);
     m.chain_stats.reserve(dit_chain_stats_floats((int)R));
     m.chain_flags.reserve(dit_chain_flag_words((int)R) * (size_t)m.depth);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
-    m.x16.reserve((size_t)m.U * m.N * round_up(m.n_mels, 8));
+    m.x16.reserve((size_t)m.Ntot * round_up(m.n_mels, 8));
   } else {
     m.c32.reserve(R * m.D); m.n32.reserve(R * m.D); m.att32.reserve(R * m.D); m.qkv32.reserve(R * 3 * m.D);
     m.ff32.reserve(R * m.FF);
@@ -588,8 +637,10 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   B2_CHECK(precision == PREC_F32 || precision == PREC_BF16 || precision == PREC_F16, "f5_steps: unknown precision");
   const int fast = precision == PREC_F32 ? 0 : precision;      // 0 = fp32 SIMT parity engine, 1 / 2 = bf16 / fp16 tensor-core engine
   const int f16 = precision == PREC_F16 ? 1 : 0;
-  const int N = m.N, D = m.D, S = 2 * m.U, R = S * N;
+  const int N = m.N, D = m.D, S = 2 * m.U, R = (int)(2 * m.Ntot);   // N = the longest utterance
+  const int2* rowinfo = m.ragged ? m.rowinfo.p : nullptr;
   B2_CHECK(fast || m.U == 1, "the fp32 parity engine runs one utterance at a time");
+  B2_CHECK((int)m.Nu.size() == m.U && m.Ntot > 0, "f5_steps: no batch layout (f5_begin / f5_begin_ragged)");
   reserve_step(m, fast != 0);
   // e.dit_chain = false (B200TTS_CHAIN=0 / b200tts_set_option) keeps every DiT block as seven launches (LN, q|k|v, attention, out,
   // LN, ff1, ff2): the A/B switch for the fused row-block chain (dit_chain.cu)
@@ -601,6 +652,8 @@ void f5_steps(Engine& e, int first, int count, int precision) {
   }
   if (fast) {
     ProfScope ps(e.prof, "f5.cast", s);
+    // stale V^T columns beyond a short sequence's length meet probabilities of exactly zero: they must hold finite values
+    if (m.ragged) B2_CUDA(cudaMemsetAsync(m.vT16.p, 0, (size_t)2 * m.U * m.H * m.hd * m.Npad * sizeof(__nv_bfloat16), s));
     rope_pack_half(m.cur_cos, m.cur_sin, m.rope_cs16.p, (long)N * m.hd, s);
     for (auto& L : m.layers) { lin_prepare_tc(e, L.qkv, f16); lin_prepare_tc(e, L.out, f16); lin_prepare_tc(e, L.ff1, f16); lin_prepare_tc(e, L.ff2, f16); }
   }
@@ -610,7 +663,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     p.x = a16; p.ldx = D; p.Lin = R; p.Cin = D; p.N = 3 * D; p.taps = 1; p.M = R; p.B = 1;
     p.out = m.qk16.p; p.ldo = 2 * D; p.out_bf16 = fast; p.o_limit = (long)R * 2 * D + 3 * D;
     p.bias = L.qkv.bias.p; p.f16 = f16;
-    p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N;
+    p.rope_cs = m.rope_cs16.p; p.rope_cols = 2 * D; p.rope_rows = N; p.rowinfo = rowinfo;
     p.vt_out = m.vT16.p; p.vt_col0 = 2 * D; p.vt_ld = m.Npad; p.vt_heads = m.H;
     ProfScope ps(e.prof, "f5.qkv_gemm", s);
     rowgemm_tc(p, L.qkv.tc[f16], s);
@@ -625,27 +678,34 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       // tensor-core form: x of all U utterances as one batched A operand (16-bit, rows padded to 8), one launch per CFG row
       // (both rows share x); the epilogue adds the step-invariant half and also writes the 16-bit copy conv_pos reads
       const int ldx = (int)round_up(m.n_mels, 8);
-      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, (long)m.U * N, m.n_mels, ldx, s, f16); }
+      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, m.Ntot, m.n_mels, ldx, s, f16); }
       lin_prepare_tc(e, m.wx, f16);
-      for (int b = 0; b < 2; ++b) {
-        RowGemm p;
-        p.x = m.x16.p; p.x_bstride = (long)N * ldx; p.ldx = ldx; p.Lin = N;
-        p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = N; p.B = m.U;
-        p.out = m.h.p + (size_t)b * N * D; p.o_bstride = (long)2 * N * D; p.ldo = D;
-        p.res = m.cproj.p + (size_t)b * N * D;
-        p.out2 = m.h16.p + (size_t)b * N * D; p.f16 = f16;
-        ProfScope ps(e.prof, "f5.embed_x", s);
-        rowgemm_tc(p, m.wx.tc[f16], s);
+      // uniform batch: one launch per CFG row over all utterances and one grouped conv over all 2U sequences; ragged batch:
+      // the same per utterance (its two sequences), since a sequence's length is the batch stride of these launches
+      const int groups = m.ragged ? m.U : 1;
+      for (int gi = 0; gi < groups; ++gi) {
+        const int Ng = m.ragged ? m.Nu[gi] : N, Ug = m.ragged ? 1 : m.U;
+        const size_t t0 = m.ragged ? (size_t)m.tok_off[gi] : 0, r0 = 2 * t0;
+        for (int b = 0; b < 2; ++b) {
+          RowGemm p;
+          p.x = m.x16.p + t0 * ldx; p.x_bstride = (long)Ng * ldx; p.ldx = ldx; p.Lin = Ng;
+          p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = Ng; p.B = Ug;
+          p.out = m.h.p + (r0 + (size_t)b * Ng) * D; p.o_bstride = (long)2 * Ng * D; p.ldo = D;
+          p.res = m.cproj.p + (r0 + (size_t)b * Ng) * D;
+          p.out2 = m.h16.p + (r0 + (size_t)b * Ng) * D; p.f16 = f16;
+          ProfScope ps(e.prof, "f5.embed_x", s);
+          rowgemm_tc(p, m.wx.tc[f16], s);
+        }
+        gconv(e, m.cp1, fast, m.h16.p + r0 * D, Ng, 2 * Ug, m.c16.p + r0 * D, fast, ACT_MISH, nullptr);
+        gconv(e, m.cp2, fast, m.c16.p + r0 * D, Ng, 2 * Ug, m.x.p + r0 * D, 0, ACT_MISH, m.h.p + r0 * D);
       }
-      gconv(e, m.cp1, fast, m.h16.p, N, m.c16.p, fast, ACT_MISH, nullptr);
-      gconv(e, m.cp2, fast, m.c16.p, N, m.x.p, 0, ACT_MISH, m.h.p);
     } else {
       for (int sq = 0; sq < S; ++sq) {           // sequence sq = (utterance sq/2, CFG row sq%2): both rows share x
         Epi ep; ep.res = m.cproj.p + (size_t)sq * N * D;
         linear(e, "f5.embed_x", m.wx, 0, m.noise.p + (size_t)(sq / 2) * N * m.n_mels, m.n_mels, N, m.h.p + (size_t)sq * N * D, D, ep);
       }
-      gconv(e, m.cp1, 0, m.h.p, N, m.c32.p, 0, ACT_MISH, nullptr);
-      gconv(e, m.cp2, 0, m.c32.p, N, m.x.p, 0, ACT_MISH, m.h.p);
+      gconv(e, m.cp1, 0, m.h.p, N, S, m.c32.p, 0, ACT_MISH, nullptr);
+      gconv(e, m.cp2, 0, m.c32.p, N, S, m.x.p, 0, ACT_MISH, m.h.p);
     }
     const float* mf = m.mod_final.p + (size_t)step * 2 * D;       // chunk order: scale, shift (modules.py:323)
     if (chain) {
@@ -660,7 +720,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       for (int l = 0; l < m.depth; ++l) {
         DiTLayer& L = m.layers[l];
         const float* mod = L.mod.p + (size_t)step * 6 * D;
-        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16); }
+        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16, m.ragged ? m.seq_off.p : nullptr, m.ragged ? m.seq_len.p : nullptr, R); }
         const bool last = l + 1 == m.depth;
         const float* nxt = last ? nullptr : m.layers[l + 1].mod.p + (size_t)step * 6 * D;
         DitChain c;
@@ -673,7 +733,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
         else {
           c.shift_nxt = nxt; c.scale_nxt = nxt + D;
           c.w_qkv = &m.layers[l + 1].qkv.tc[f16]; c.b_qkv = m.layers[l + 1].qkv.bias.p;
-          c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
+          c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.rowinfo = rowinfo; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
         }
         c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
         c.trace = trace_path ? m.chain_trace.p : nullptr;
@@ -691,7 +751,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, scale_msa, shift_msa, nbuf, fast, R, D, s); }
       if (fast) {
         qkv_fast(L, m.n16.p);
-        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16); }
+        { ProfScope ps(e.prof, "f5.attention", s); attention_tc(m.qk16.p, m.vT16.p, m.Npad, m.att16.p, S, N, m.H, s, f16, m.ragged ? m.seq_off.p : nullptr, m.ragged ? m.seq_len.p : nullptr, R); }
       } else {
         Epi ep; ep.bias = L.qkv.bias.p;
         linear(e, "f5.qkv_gemm", L.qkv, 0, m.n32.p, D, R, m.qkv32.p, 3 * D, ep);
@@ -726,7 +786,13 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     }
     {
       ProfScope ps(e.prof, "f5.euler", s);
-      euler_cfg_update(m.noise.p, m.pred.p, (long)N * m.n_mels, m.U, m.cfg_strength, m.delta_t[step], s);
+      if (!m.ragged) {
+        euler_cfg_update(m.noise.p, m.pred.p, (long)N * m.n_mels, m.U, m.cfg_strength, m.delta_t[step], s);
+      } else {
+        for (int u = 0; u < m.U; ++u)
+          euler_cfg_update(m.noise.p + (size_t)m.tok_off[u] * m.n_mels, m.pred.p + (size_t)2 * m.tok_off[u] * m.n_mels, (long)m.Nu[u] * m.n_mels, 1,
+                           m.cfg_strength, m.delta_t[step], s);
+      }
     }
   }
   if (trace_path) {

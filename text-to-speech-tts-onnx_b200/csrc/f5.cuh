@@ -29,6 +29,11 @@ float* f5_cond_drop(Engine& e, int u = 0);
 float* f5_noise(Engine& e, int u = 0);
 // Set up state for externally supplied graph-B inputs (the per-step session path): allocates for N rows.
 void f5_begin(Engine& e, int N, int U = 1);
+// Ragged batch: utterance u has Ns[u] frames. Lays out the concatenated tensors and uploads the per-sequence /
+// per-row tables (synchronises: call it outside a stream capture); f5_preprocess(.., Ns[u], u, U) then fills utterance u.
+void f5_begin_ragged(Engine& e, int U, const int* Ns);
+void f5_restore_ragged(Engine& e, int U, const int* Ns, const int* Fs);
+long f5_tok_offset(const Engine& e, int u);     // rows of noise / cond before utterance u
 // rope rows [N][64] fp32 device (cos, sin) -- defaults to the model's fp16-rounded tables, may be overridden
 void f5_set_rope(Engine& e, const float* d_cos, const float* d_sin);
 // same, but returns the device buffers ([N][64] each) for the caller to fill (then selects them)

@@ -53,6 +53,7 @@ struct RowGemm {
   //   columns >= vt_col0    : written transposed, vt_out[((row / rope_rows) * heads + h) * 64 + d][t] (row stride vt_ld)
   const __half2* rope_cs = nullptr;
   int rope_cols = 0, rope_rows = 1;
+  const int2* rowinfo = nullptr;   // ragged batches: (sequence, position) per output row instead of row / rope_rows, row % rope_rows
   __nv_bfloat16* vt_out = nullptr;
   int vt_col0 = 0, vt_ld = 0, vt_heads = 0;
 };

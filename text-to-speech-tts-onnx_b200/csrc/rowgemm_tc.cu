@@ -646,6 +646,7 @@ TcArgs make_args(const RowGemm& p, int BN) {
   a.vt_out = p.vt_out; a.vt_col0 = p.vt_col0; a.vt_ld = p.vt_ld; a.vt_heads = p.vt_heads;
   a.out2 = p.out2;
   a.f16 = p.f16;
+  a.rowinfo = p.rowinfo;
   return a;
 }
 

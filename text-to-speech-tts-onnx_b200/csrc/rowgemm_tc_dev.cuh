@@ -40,6 +40,7 @@ struct TcArgs {
   const __half2* rope_cs; int rope_cols, rope_rows;
   __nv_bfloat16* vt_out; int vt_col0, vt_ld, vt_heads;
   __nv_bfloat16* out2;          // optional 16-bit copy of the output (same indexing, operand dtype)
+  const int2* rowinfo;          // ragged batches: (sequence, position) of every output row; null = row / rope_rows, row % rope_rows
   int f16;                      // 16-bit type of the A / B operands, out2 and vt_out: 0 = bf16, 1 = fp16 (IEEE half);
                                 // out_bf16 is the type code of `out`: 0 = fp32, 1 = bf16, 2 = fp16
 };
@@ -174,7 +175,8 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int t = p.t_row0 + i * 4 + sub;
-        cs[i] = t < a.M ? __ldg(reinterpret_cast<const uint4*>(a.rope_cs + (long)(t % a.rope_rows) * 64 + d)) : make_uint4(0u, 0u, 0u, 0u);
+        const int pos = t < a.M ? (a.rowinfo ? __ldg(&a.rowinfo[t]).y : t % a.rope_rows) : 0;
+        cs[i] = t < a.M ? __ldg(reinterpret_cast<const uint4*>(a.rope_cs + (long)pos * 64 + d)) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
     tmem_ld_wait();
@@ -184,7 +186,8 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
       // consecutive t, so each store instruction writes one 64-byte run.
       const int t = p.t_row0 + lane;
       if (t < a.M) {
-        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
+        int tt = t % a.rope_rows, bb = t / a.rope_rows;
+        if (a.rowinfo) { const int2 ri = __ldg(&a.rowinfo[t]); bb = ri.x; tt = ri.y; }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int n = n0 + cb + k * 4;
@@ -334,6 +337,11 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
   const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
   const uint32_t row64 = (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
   const int t = row0 + lane;
+  int tt = 0, bb = 0;                                          // position in / index of this row's sequence (RoPE, V^T)
+  if (TK == TK_ROPE16 && t < a.M) {
+    if (a.rowinfo) { const int2 ri = __ldg(&a.rowinfo[t]); bb = ri.x; tt = ri.y; }
+    else { tt = t % a.rope_rows; bb = t / a.rope_rows; }
+  }
 #pragma unroll 1
   for (int cb = cb_first; cb < a.BN; cb += cb_step) {
     const int n = n0 + cb;
@@ -343,7 +351,7 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
     uint4 cs[8];
     const bool rope = TK == TK_ROPE16 && n < a.rope_cols;
     if (rope) {           // this row's (cos, sin) pairs of the block's 32 columns: one 128-byte line, fetched under the TMEM load
-      const __half2* cp = a.rope_cs + (long)((t < a.M ? t : 0) % a.rope_rows) * 64 + (n & 63);
+      const __half2* cp = a.rope_cs + (long)tt * 64 + (n & 63);
 #pragma unroll
       for (int k = 0; k < 8; ++k) cs[k] = __ldg(reinterpret_cast<const uint4*>(cp) + k);
     }
@@ -353,7 +361,6 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
     if (TK == TK_ROPE16 && a.vt_out != nullptr && n >= a.vt_col0) {
       // V columns: written transposed, vt[(sequence*heads + h)*64 + d][t]; consecutive lanes are consecutive t
       if (t < a.M) {
-        const int tt = t % a.rope_rows, bb = t / a.rope_rows;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
