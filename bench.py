@@ -4,15 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pipeline|f5|bigvgan|...]
 
 One "step" = one pass of the hot path over one batch of synthetic input.
-  pipeline (default) BASELINE.json's metric configuration ("F5-TTS NFE=32 + BigVGAN 24 kHz"; configs[3] per-GPU share): U = 8
-           utterances of config-3 shape per GPU -- graph A, the batched 31-step DiT loop, BigVGAN on the generated frames --
-           through b200tts_f5_bigvgan_pipeline. `value`: inputs resident in HBM (device-pointer entry); `e2e`: the host-buffer
-           C call (pinned host inputs, H2D / D2H inside the timed region).
+  config4  (default) BASELINE.json's metric configuration ("F5-TTS NFE=32 + BigVGAN 24 kHz"), configs[3]: a batch of 64 synthetic
+           utterances (references 4-8 s, N in [752, 1502]) dealt longest-first to the N GPUs; a rank runs its share as ONE ragged
+           batch through b200tts_f5_bigvgan_pipeline_ragged -- graph A per utterance, one 31-step DiT loop over all its rows,
+           BigVGAN on every utterance's generated frames. STRONG scaling: the 64 utterances are the job whatever N is.
+           `value`: inputs resident in HBM (device-pointer entry); `e2e`: the host-buffer C call (pinned host buffers, H2D / D2H
+           inside the timed region).
+  pipeline the same pipeline on U = 8 utterances of config-3 shape (6 s reference) per GPU, weak scaling.
   f5       configs[2]: one utterance per step (latency): preprocess + DiT loop + Vocos/ISTFT decode.
   bigvgan  configs[1]: BigVGAN-v2 24khz_100band_256x, mels (8,100,512) -> int16 PCM.
-The default run attaches short `f5` and `bigvgan` measurements under those keys. Each rank runs the same per-GPU batch
-(utterances shard with no data-path collective: weak scaling); NCCL is used once, to broadcast the weights from rank 0 at
-load. Prints ONE JSON line on rank 0.
+The default run (one GPU) attaches short `pipeline`, `f5` and `bigvgan` measurements under those keys. Utterances shard with no
+data-path collective; NCCL is used once, to broadcast the weights from rank 0 at load. Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -737,7 +739,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "config4", "f5", "bigvgan", "indextts_vocoder", "indextts_gpt", "indextts"])
+    ap.add_argument("--workload", default="config4", choices=["config4", "pipeline", "f5", "bigvgan", "indextts_vocoder", "indextts_gpt", "indextts"])
     ap.add_argument("--config4-utterances", type=int, default=64)
     ap.add_argument("--new-tokens", type=int, default=256, help="indextts_gpt workload: E calls per sentence (prefill + decode)")
     ap.add_argument("--gpt-text", type=int, default=60, help="indextts_gpt workload: text ids per sentence")
@@ -844,14 +846,17 @@ def main():
         res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
     elif args.workload == "config4":
         res = bench_config4(args, H, eng, rank, prec, args.steps, args.warmup, sampler=sampler)
-    else:
-        res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, with_vocoder=True, U=args.utterances, sampler=sampler)
-        if not args.no_extras:
-            # the two other single-GPU configurations, short: configs[2] (one utterance, latency) and configs[1] (vocoder alone)
+        if not args.no_extras and world == 1:
+            # the other single-GPU configurations, short: the uniform pipeline (8 x config-3 utterances per GPU), configs[2] (one
+            # utterance, latency) and configs[1] (vocoder alone)
+            ppr = bench_f5(args, H, eng, rank, prec, steps=3, warmup=3, with_vocoder=True, U=args.utterances)
+            extra["pipeline"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **ppr}
             f5r = bench_f5(args, H, eng, rank, prec, steps=5, warmup=3)
             extra["f5"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **f5r}
             vgr = bench_bigvgan(args, H, eng, rank, args.batch, args.frames, prec, steps=10, warmup=3)
             extra["bigvgan"] = {"metric": "mel_frames_per_s", "unit": "mel-frames/s", **vgr}
+    else:
+        res = bench_f5(args, H, eng, rank, prec, args.steps, args.warmup, with_vocoder=True, U=args.utterances, sampler=sampler)
 
     if rank == 0:
         workload = res.pop("workload")
