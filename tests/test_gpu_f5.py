@@ -168,6 +168,23 @@ def test_transformer_fp16_and_fused_chain_vs_reference(f5, g):
         f5.set_option("dit_chain", 1)
 
 
+def test_fused_chain_one_step(f5, g):
+    """One Euler step at N = 130 through the fused chain (two row blocks, team of 8) == the seven-launch path to fp16 noise.
+    Small on purpose: this is the case tools/sanitize.sh runs under compute-sanitizer racecheck / synccheck."""
+    _, _, _, noise = _inputs(g)
+    out = {}
+    try:
+        for chain in (0, 1):
+            f5.set_option("dit_chain", chain)
+            out[chain], _ = f5.f5_transformer(noise, g["rope_cos_row"], g["rope_sin_row"], g["cat_mel_text"], g["cat_mel_text_drop"], 0,
+                                              n_steps=1, precision=capi.F16)
+    finally:
+        f5.set_option("dit_chain", 1)
+    dt0 = float(g["delta_t"][0])
+    assert cosine((out[1] - noise) / dt0, (out[0] - noise) / dt0) > 0.99999
+    assert cosine((out[1] - noise) / dt0, (g["noise_after_1"] - noise) / dt0) > 0.9999
+
+
 def test_synthesize_fp16_vs_reference(f5, g):
     audio, text_ids, maxd, noise = _inputs(g)
     pcm, mel = f5.f5_synthesize(audio, text_ids, int(maxd[0]), noise, precision=capi.F16, return_mel=True)
@@ -336,3 +353,29 @@ def test_ragged_batch_equals_single_utterances(f5, g):
                                             steps=31, return_mel=True)
     assert cosine(mels[0], want_mel.numpy()) >= 0.99999
     assert snr_db(want_pcm.numpy().reshape(-1), vocs[0]) > 45.0
+
+
+def test_frontend_wav_and_text_in_wav_out(f5, g, tmp_path):
+    """The reference script's call surface (F5-TTS-ONNX-Inference.py:13-39,223-315): a wav file + reference text + text to speak in,
+    a wav file out. The front end's ids / duration / noise drive the same engine call a direct caller would make."""
+    from b200tts import frontend as fe
+    import string
+    symbols = [" "] + list(string.ascii_lowercase) + list(",.'!?")
+    vocab_path = tmp_path / "vocab.txt"
+    vocab_path.write_text("".join(s + "\n" for s in symbols), encoding="utf-8")
+    audio, _, _, _ = synth.f5_inputs(7, audio_len=24000, n_text=4)
+    ref_wav = str(tmp_path / "ref.wav")
+    fe.save_wav(ref_wav, audio.reshape(-1))
+    tts = fe.F5Synthesizer(f5, str(vocab_path), precision=capi.F16, nfe_steps=4)
+    ref_text, gen_text = "hello there, world.", "this is a test."
+    out_wav = str(tmp_path / "generated.wav")
+    pcm = tts.synthesize(ref_wav, ref_text, gen_text, out_path=out_wav)
+    a, ids, maxd, noise = tts.prepare(ref_wav, ref_text, gen_text)
+    frames = 24000 // 256 + 1
+    assert maxd == frames + int(frames / len(ref_text) * len(gen_text))
+    assert ids.shape == (1, len(ref_text + gen_text) + 1)          # 'world.' + 'this' glued: the symbol pass inserts one space
+    np.testing.assert_array_equal(a.reshape(-1), audio.reshape(-1))
+    want = f5.f5_synthesize(a, ids, maxd, noise, precision=capi.F16, n_steps=4).reshape(-1)
+    np.testing.assert_array_equal(pcm, want)
+    assert pcm.size == 256 * (maxd - frames - 1)
+    np.testing.assert_array_equal(fe.load_wav_mono_int16(out_wav), pcm)
