@@ -5,19 +5,22 @@
 //   S_j  = Q K_j^T   tcgen05.mma  M=128 N=128 K=64   (Q, K tiles: TMA boxes of the [2N][2048] q|k tensor, SWIZZLE_128B)
 //   P_j  = exp2(S_j log2e - m)   256 softmax threads: thread (row r, key half g) owns 64 keys of its row in ONE pass
 //          (the 64 scores are pulled from TMEM into registers, which also frees the S buffer so that S_{j+1} is computed
-//          while the exponentials run), packed FFMA2 / FADD2 arithmetic, P (bf16) to shared memory in the K-major
-//          SWIZZLE_128B layout the next MMA wants
-//   O_g += P_jg V_jg tcgen05.mma  M=128 N=64 K=64 per key half, accumulated IN TMEM across blocks.
-// The two key halves of a row are independent split-KV streams: each has its own running maximum, row sum and O
-// accumulator, so the two threads of a row never synchronise inside the loop; they are merged once at the end
-// (O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m))) through shared memory.
+//          while the exponentials run), packed FFMA2 / FADD2 arithmetic, P (16 bit) back into TENSOR MEMORY
+//   O   += P_j V_j   tcgen05.mma  M=128 N=64 K=128 with the A operand in tensor memory, accumulated in TMEM across blocks.
+// Round 2 (profiles/r02/ncu_summary_r02a.md): P used to go through ONE shared-memory tile, so the softmax threads of block j+1
+// had to wait for P_j V_j to finish before they could write (p_full -> MMA issue -> pv_done = 0.5 us of a 1.1-1.5 us block
+// period; XU pipe 49 % busy). Now the probabilities stay in registers until the end of the block and only then wait for
+// P_{j-1} V_{j-1} (long done); the MMA runs under the next block's exponentials and the softmax warps never stall on it.
+// The two threads of a row share ONE running maximum (exchanged through shared memory, a 64-thread named barrier per warp
+// pair), hence one O accumulator: TMEM = S 128 + O 64 + P 64 columns = 256 -> two CTAs per SM.
 // The running maximum is lazy (FlashAttention-4 style): it only moves when a block's maximum exceeds it by more than 8
-// (log2 units), and only then is O_g rescaled in TMEM (tcgen05.ld / multiply / tcgen05.st, warp-voted); P stays below
-// 2^8, which bf16 and the fp32 accumulators hold without loss.
-// The first version (r01b: 30.5 us per call, 16.8 M instructions, issue-bound) walked S twice with 128 threads, kept O
-// in registers and folded PV into it every block (64 FFMA + 2 TMEM loads per row per block).
+// (log2 units), and only then is O rescaled in TMEM (tcgen05.ld / multiply / tcgen05.st, warp-voted); P stays below
+// 2^8, which bf16 / fp16 and the fp32 accumulators hold without loss.
+// A fraction of the exponentials (template POLY of every 4 pairs) runs on the FMA pipes instead of the MUFU unit
+// (Cody-Waite range reduction + degree-3 minimax polynomial, relative error 8.8e-5 < half an ulp of fp16): the kernel is
+// MUFU-bound otherwise (16 ex2 per clock and SM against 8192 tensor FLOPs).
 // 320 threads: warps 0-7 = softmax/epilogue, warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.
-// Shared memory 112 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA phases.
+// Shared memory 82 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's non-MUFU phases.
 #include "attention_tc.cuh"
 
 #include <cstdio>
@@ -40,16 +43,18 @@ constexpr int WARP_TMA = 8, WARP_MMA = 9;       // highest warp ids: the SMSP ar
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
 constexpr int K_BYTES = BKEY * HD * 2;          // 16 KB
 constexpr int V_BYTES = HD * BKEY * 2;          // 16 KB = two [64 d][64 keys] chunks
-constexpr int P_BYTES = BQ * BKEY * 2;          // 32 KB = two [128 rows][64 keys] chunks
+constexpr int XCH_BYTES = 2 * 2 * BQ * 4;       // [block parity][key half][row] floats: the row maximum / row sum exchange
 constexpr int KV_STAGES = 2;
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES + 128;      // x2 CTAs + 2 KB reserved <= 228 KB
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCH_BYTES + 128;      // 82 KB
 constexpr float RESCALE_TAU = 8.0f;             // log2 units
+constexpr int ATTN_POLY_DEFAULT = 1;
+// tensor-memory columns of a CTA
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
 
 struct AttnArgs {
   int N, H;
   __nv_bfloat16* out;
   int ldo;
-  int f16;            // q, k, v, P and out are IEEE fp16 instead of bf16
   const int* seq_off; // ragged batches: first row of every sequence in the concatenated [rows][2*H*64] tensor (null: b * N)
   const int* seq_len; // ragged batches: tokens of every sequence (null: N)
   unsigned long long* trace;   // debug: [CTA][64] %globaltimer stamps (B200TTS_ATTN_TRACE=<file>, tools/attn_trace.py)
@@ -64,8 +69,9 @@ __device__ __forceinline__ void astamp(const AttnArgs& a, int slot) {
   }
 }
 
-__device__ __forceinline__ uint32_t pk16(float x, float y, int half) {
-  if (half) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
+template <bool F16>
+__device__ __forceinline__ uint32_t pk16(float x, float y) {
+  if (F16) { __half2 h = __floats2half2_rn(x, y); return *reinterpret_cast<uint32_t*>(&h); }
   __nv_bfloat162 p = __floats2bfloat162_rn(x, y);
   return *reinterpret_cast<uint32_t*>(&p);
 }
@@ -99,23 +105,67 @@ __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigne
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long add2_rm(unsigned long long a, unsigned long long b) {      // round towards -inf
+  unsigned long long d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^e for a pair of exponents e <= 8 on the FMA pipes: e = n + f with n = floor(e) (the magic-number add in round-down mode
+// leaves n in the low mantissa bits), 2^f by a degree-3 minimax polynomial on [0, 1) (relative error 8.8e-5), n added to
+// the exponent field by integer arithmetic. Exponents below -126 are clamped (the result is then a denormal ~ 1e-38).
+__device__ __forceinline__ void ex2_fma_pair(float e0, float e1, float& p0, float& p1) {
+  const float MAGIC = 12582912.f;               // 1.5 * 2^23
+  e0 = fmaxf(e0, -126.f);
+  e1 = fmaxf(e1, -126.f);
+  const unsigned long long x2 = pk2(e0, e1);
+  const unsigned long long t2 = add2_rm(x2, pk2(MAGIC, MAGIC));
+  const unsigned long long n2 = add2(t2, pk2(-MAGIC, -MAGIC));                   // floor(e), exact
+  const unsigned long long f2 = fma2(n2, pk2(-1.f, -1.f), x2);                   // e - floor(e) in [0, 1)
+  unsigned long long q2 = fma2(f2, pk2(0.077119089663028717f, 0.077119089663028717f), pk2(0.227564394474029541f, 0.227564394474029541f));
+  q2 = fma2(q2, f2, pk2(0.695146143436431885f, 0.695146143436431885f));
+  q2 = fma2(q2, f2, pk2(1.f, 1.f));
+  float t0, t1, q0, q1;
+  up2(t2, t0, t1);
+  up2(q2, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// the two warps (key halves) that share query rows [32 qd, 32 qd + 32)
+__device__ __forceinline__ void pair_bar(int qd) {
+  switch (qd) {                                   // immediate barrier ids: a register id makes ptxas reserve all 16
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = lanes, K = 16 elements = 8 columns of packed 16-bit pairs)
+// is read from tensor memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// POLY: of every 4 score pairs, POLY are exponentiated on the FMA pipes (0, 1 or 2)
+template <bool F16, int POLY>
 __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,
                                                               const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + KV_STAGES * K_BYTES;
-  uint8_t* sP = sV + KV_STAGES * V_BYTES;
-  float* stat = reinterpret_cast<float*>(sQ);                      // [2 halves][m, l][128 rows]: reuses the Q tile once the
-                                                                   // last S MMA has completed (pv_done of the last block)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  float* xch = reinterpret_cast<float*>(sV + KV_STAGES * V_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch) + XCH_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;                  // [2]  K and V stages are released separately: a K tile is dead as soon as
   uint64_t* k_empty = bars + 3;                 // [2]  S_j = Q K_j^T has run, its V tile only after O += P_j V_j, a whole
-  uint64_t* v_full = bars + 5;                  // [2]  softmax later. With one barrier pair K_{j+1} arrived too late and the
-  uint64_t* v_empty = bars + 7;                 // [2]  softmax threads spent 21 % of their samples waiting for S (ncu r01p).
+  uint64_t* v_full = bars + 5;                  // [2]  softmax later
+  uint64_t* v_empty = bars + 7;                 // [2]
   uint64_t* s_full = bars + 9;
   uint64_t* s_free = bars + 10;                 // softmax threads hold S in registers: the S buffer may be overwritten
   uint64_t* p_full = bars + 11;
@@ -148,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == WARP_MMA) tmem_alloc(tmem_ptr, 256);
+  if (warp == WARP_MMA) tmem_alloc(tmem_ptr, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,7 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) astamp(a, 0);
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;     // O_a: +128..191, O_b: +192..255
+  const uint32_t tmem_S = tmem_base + TM_S, tmem_O = tmem_base + TM_O, tmem_P = tmem_base + TM_P;
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -177,11 +227,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     }
   } else if (warp == WARP_MMA) {
     if (lane == 0) {
-      const uint32_t fmt = a.f16 ? 0u : ((1u << 7) | (1u << 10));        // kind::f16 operand format: 1 = bf16, 0 = fp16
+      const uint32_t fmt = F16 ? 0u : ((1u << 7) | (1u << 10));          // kind::f16 operand format: 1 = bf16, 0 = fp16
       const uint32_t idesc_s = (1u << 4) | fmt | ((uint32_t)(BKEY >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | fmt | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint64_t dQ = make_desc_sw128(smem_u32(sQ));
-      const uint64_t dP0 = make_desc_sw128(smem_u32(sP)), dP1 = make_desc_sw128(smem_u32(sP + P_BYTES / 2));
       auto issue_s = [&](int j) {
         const int s = j % KV_STAGES;
         mbar_wait(&k_full[s], (uint32_t)(j / KV_STAGES) & 1u);
@@ -206,10 +255,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         const uint64_t dV0 = make_desc_sw128(smem_u32(sV + s * V_BYTES));
         const uint64_t dV1 = make_desc_sw128(smem_u32(sV + s * V_BYTES + V_BYTES / 2));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                               // the two key halves are independent accumulators
-          umma_bf16(tmem_O, dP0 + (uint64_t)(2 * k), dV0 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_O + 64, dP1 + (uint64_t)(2 * k), dV1 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)                                 // keys [0, 64) of the block: P columns 0..31
+          umma_ts(tmem_O, tmem_P + (uint32_t)(8 * k), dV0 + (uint64_t)(2 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                                 // keys [64, 128): P columns 32..63
+          umma_ts(tmem_O, tmem_P + (uint32_t)(32 + 8 * k), dV1 + (uint64_t)(2 * k), idesc_pv, 1u);
         umma_commit(pv_done);
         umma_commit(&v_empty[s]);
         astamp(a, 4 + 4 * j + 1);
@@ -220,11 +270,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
     const int qd = warp & 3, g = warp >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t tmem_Og = tmem_O + (uint32_t)(g * 64);
+    const uint32_t tmem_Og = tmem_O + lane_addr + (uint32_t)(g * 32);            // this thread's 32 of the 64 output columns
+    const uint32_t tmem_Pg = tmem_P + lane_addr + (uint32_t)(g * 32);            // its 64 probabilities = 32 packed columns
     const float LOG2E = 1.4426950408889634f;
-    float m_ref = -INFINITY, l_run = 0.f;        // m_ref in log2 units
-    uint8_t* prow = sP + g * (P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
-    const int sw = r & 7;
+    float m_ref = -INFINITY, l_run = 0.f;        // m_ref in log2 units, shared by the two threads of a row
 
     for (int j = 0; j < nblocks; ++j) {
       const int kvalid = Nb - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
@@ -249,103 +298,83 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
-      mx *= LOG2E;
+      // the row maximum over both key halves (key half 0 always holds a valid key, so it is finite)
+      float* xb = xch + (j & 1) * (2 * BQ);
+      xb[g * BQ + r] = mx;
+      pair_bar(qd);
+      mx = fmaxf(mx, xb[(g ^ 1) * BQ + r]) * LOG2E;
       // lazy running maximum
       const bool move = mx > m_ref + RESCALE_TAU;
       const float m_new = move ? mx : m_ref;
       const float alpha = move ? ex2(m_ref - m_new) : 1.0f;          // exp2(-inf) = 0 on the first block
       m_ref = m_new;
       l_run *= alpha;
-      if (j > 0) {
-        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);                 // O += P_{j-1} V_{j-1} has landed; P buffer is free again
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, move)) {                         // rescale O_g in TMEM (rare after the first blocks)
-#pragma unroll 1
-          for (int cb = 0; cb < HD; cb += 16) {                      // 16 columns at a time: the 64 scores stay live
-            uint32_t o[16];
-            tmem_ld16(tmem_Og + lane_addr + (uint32_t)cb, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem_Og + lane_addr + (uint32_t)cb, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      // P = exp2(s*log2e - m) -> bf16 -> swizzled smem; fp32 row sum (packed accumulator). No key seen yet (m = -inf) -> P = 0
-      const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-      const unsigned long long sc2 = pk2(LOG2E, LOG2E), nm2 = pk2(-m_use, -m_use);
+      // P = exp2(s*log2e - m) -> 16 bit, kept in registers; fp32 row sum (packed accumulator)
+      const unsigned long long sc2 = pk2(LOG2E, LOG2E), nm2 = pk2(-m_ref, -m_ref);
       unsigned long long sum2 = pk2(0.f, 0.f);
+      uint32_t pkd[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        // 32 keys = four 16-byte chunks of this row's 128-byte (64-key) line: chunk index c*4 + q, swizzled by the row
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          uint32_t pkd[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = qq * 8 + u * 2;
-            float e0, e1;
-            up2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), e0, e1);
-            const float p0 = ex2(e0), p1 = ex2(e1);
-            sum2 = add2(sum2, pk2(p0, p1));
-            pkd[u] = pk16(p0, p1, a.f16);
+        for (int u = 0; u < 16; ++u) {
+          const int i = u * 2;
+          float e0, e1, p0, p1;
+          up2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), e0, e1);
+          if ((u & 3) < POLY) {
+            ex2_fma_pair(e0, e1, p0, p1);
+          } else {
+            p0 = ex2(e0);
+            p1 = ex2(e1);
           }
-          const int chunk = (c * 4 + qq) ^ sw;
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]);
+          sum2 = add2(sum2, pk2(p0, p1));
+          pkd[c * 16 + u] = pk16<F16>(p0, p1);
         }
       }
       float s0, s1;
       up2(sum2, s0, s1);
       l_run += s0 + s1;
-      tc_fence_before();                 // order our TMEM accesses before the MMA warp's next writes
-      fence_proxy_async();               // make the generic-proxy smem writes of P visible to the tensor core
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);                 // O += P_{j-1} V_{j-1} has landed (issued a whole block ago)
+        tc_fence_after();
+      }
+      tmem_st32(tmem_Pg, pkd);
+      if (j > 0 && __any_sync(0xffffffffu, move)) {                  // rescale this thread's half of O (rare after the first blocks)
+#pragma unroll
+        for (int cb = 0; cb < 32; cb += 16) {
+          uint32_t o[16];
+          tmem_ld16(tmem_Og + (uint32_t)cb, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem_Og + (uint32_t)cb, o);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();                 // order our TMEM writes before the MMA that reads P / accumulates into O
       mbar_arrive(p_full);
       if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 3);
     }
-    // ---- merge the two key halves of each row, normalise, store ----
+    // ---- row sum over both key halves, normalise, store ----
+    float* xb = xch + (nblocks & 1) * (2 * BQ);          // the buffer the last block did not use
+    xb[g * BQ + r] = l_run;
+    pair_bar(qd);
+    const float scale = 1.0f / (l_run + xb[(g ^ 1) * BQ + r]);
     mbar_wait(pv_done, (uint32_t)(nblocks - 1) & 1u);
     tc_fence_after();
     if (threadIdx.x == 0) astamp(a, 2);
-    stat[(g * 2 + 0) * BQ + r] = m_ref;
-    stat[(g * 2 + 1) * BQ + r] = l_run;
-    softmax_bar();
-    const float m_o = stat[((g ^ 1) * 2 + 0) * BQ + r], l_o = stat[((g ^ 1) * 2 + 1) * BQ + r];
-    const float m_all = fmaxf(m_ref, m_o);       // finite: key half 0 always holds at least one valid key
-    const float w_me = m_ref == -INFINITY ? 0.f : ex2(m_ref - m_all);
-    const float w_ot = m_o == -INFINITY ? 0.f : ex2(m_o - m_all);
-    const float scale = w_me / (l_run * w_me + l_o * w_ot);
-    // thread (r, g) stores output columns [32g, 32g+32); the other 32 columns of its O_g go to the partner through the
-    // (now idle) P buffer: [2 halves][128 rows][32 floats], 16-byte chunks swizzled by the row
-    float* xch = reinterpret_cast<float*>(sP);
-    uint32_t mine[32];
-    {
-      uint32_t o[32];
-      tmem_ld32(tmem_Og + lane_addr + (uint32_t)((g ^ 1) * 32), o);        // the partner's columns
-      tmem_ld32(tmem_Og + lane_addr + (uint32_t)(g * 32), mine);
-      tmem_ld_wait();
-      float* dstx = xch + ((g ^ 1) * BQ + r) * 32;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<float4*>(dstx + ((k ^ sw) << 2)) =
-            make_float4(__uint_as_float(o[k * 4]) * scale, __uint_as_float(o[k * 4 + 1]) * scale, __uint_as_float(o[k * 4 + 2]) * scale,
-                        __uint_as_float(o[k * 4 + 3]) * scale);
-    }
-    softmax_bar();
+    uint32_t o[32];
+    tmem_ld32(tmem_Og, o);
+    tmem_ld_wait();
     const int q = q0 + r;
     if (q < Nb) {
-      const float* srcx = xch + (g * BQ + r) * 32;
       __nv_bfloat16* dst = a.out + ((a.seq_off ? (long)rb0 : (long)b * a.N) + q) * a.ldo + h * HD + g * 32;
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
-        const float4 x0 = *reinterpret_cast<const float4*>(srcx + ((k ^ sw) << 2));
-        const float4 x1 = *reinterpret_cast<const float4*>(srcx + (((k + 1) ^ sw) << 2));
+      for (int k = 0; k < 4; ++k) {
         uint32_t w[4];
-        w[0] = pk16(__uint_as_float(mine[k * 4 + 0]) * scale + x0.x, __uint_as_float(mine[k * 4 + 1]) * scale + x0.y, a.f16);
-        w[1] = pk16(__uint_as_float(mine[k * 4 + 2]) * scale + x0.z, __uint_as_float(mine[k * 4 + 3]) * scale + x0.w, a.f16);
-        w[2] = pk16(__uint_as_float(mine[k * 4 + 4]) * scale + x1.x, __uint_as_float(mine[k * 4 + 5]) * scale + x1.y, a.f16);
-        w[3] = pk16(__uint_as_float(mine[k * 4 + 6]) * scale + x1.z, __uint_as_float(mine[k * 4 + 7]) * scale + x1.w, a.f16);
-        *reinterpret_cast<uint4*>(dst + k * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = pk16<F16>(__uint_as_float(o[k * 8 + 2 * i]) * scale, __uint_as_float(o[k * 8 + 2 * i + 1]) * scale);
+        *reinterpret_cast<uint4*>(dst + k * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -355,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, TM_COLS);
   }
 }
 
@@ -379,11 +408,22 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
     // V^T: [S*H][64][ldv] -> dims {N keys, 64 d, S*H}, box {64 keys, 64 d, 1}
     tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
   }
+  // exponentials on the FMA pipes: B200TTS_ATTN_POLY = 0, 1 or 2 of every 4 score pairs (read once)
+  static const int poly = [] {
+    const char* e = getenv("B200TTS_ATTN_POLY");
+    const int p = e ? atoi(e) : ATTN_POLY_DEFAULT;
+    return p < 0 ? 0 : (p > 2 ? 2 : p);
+  }();
+  using KernelFn = void (*)(CUtensorMap, CUtensorMap, AttnArgs);
+  static const KernelFn kernels[2][3] = {{attn_tc_kernel<false, 0>, attn_tc_kernel<false, 1>, attn_tc_kernel<false, 2>},
+                                         {attn_tc_kernel<true, 0>, attn_tc_kernel<true, 1>, attn_tc_kernel<true, 2>}};
   static std::once_flag once;
   std::call_once(once, [] {
-    B2_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    for (int t = 0; t < 2; ++t)
+      for (int p = 0; p < 3; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
-  AttnArgs a{N, H, out, H * HD, f16, d_seq_off, d_seq_len, nullptr};
+  const KernelFn kernel = kernels[f16 ? 1 : 0][poly];
+  AttnArgs a{N, H, out, H * HD, d_seq_off, d_seq_len, nullptr};
   static DevBuf<unsigned long long> trace_buf;
   const char* trace_path = getenv("B200TTS_ATTN_TRACE");
   const size_t ncta = (size_t)ceil_div(N, BQ) * H * S;
@@ -394,7 +434,7 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
   }
   B2_CHECK(S <= 65535, "attention_tc: too many sequences");
   dim3 grid(ceil_div(N, BQ), H, S);
-  launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
+  launch_pdl(kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
   B2_LAUNCH_CHECK();
   count_launch();
   if (trace_path) {                                        // debug only: dump the stamps of this launch

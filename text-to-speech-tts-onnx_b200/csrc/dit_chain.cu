@@ -37,7 +37,7 @@ namespace {
 constexpr int CH_A_STAGES = 4, CH_B_STAGES = 4;
 constexpr int CH_A_BYTES = 128 * 128;            // 128 rows x 64 channels x 2 B
 constexpr int CH_B_BYTES = 128 * 128;            // up to 128 weight rows per CTA and chunk (half of a 256-column sub-tile)
-constexpr int CH_STAT_BYTES = 2 * 128 * 2 * 4;   // [column half e][row][sum, sum of squares]
+constexpr int CH_STAT_BYTES = 8 * 2 * 128 * 2 * 4;   // [128-column group of the slice][column parity e][row][sum, sum of squares]
 constexpr int CH_EPI_BYTES = 8 * 8192;           // per epilogue warp: residual tile + result tile (4 KB each, rowgemm_tc_dev.cuh: EpiTile)
 constexpr int CH_VEC_BYTES = 2 * 256 * 4;        // bias / gate of the current sub-tile
 constexpr int CH_MAX_TEAM = 8;                   // statistics slots per row
@@ -129,18 +129,23 @@ __device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int
 // Measured alternatives that were SLOWER on B200 (profiles/r02/chain_timeline.md): fetching the slab before the statistics
 // arrive with 16 row loads per lane in flight (+3.6 ms per utterance), and walking whole rows instead of 128-column groups
 // (+6 ms): more loads in flight per thread only lengthen the loaded L2 latency here.
-__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind, float rsum, float rsq,
+__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind,
                                          const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
                                          unsigned* flag_ready, float* st, int warp, int lane) {
   const int tid = warp * 32 + lane;
-  const int q = warp & 3, e = warp >> 2;
-  st[(e * 128 + q * 32 + lane) * 2 + 0] = rsum;                 // the row-layout epilogue leaves a row's sums in one lane
-  st[(e * 128 + q * 32 + lane) * 2 + 1] = rsq;
+  // the row-layout epilogue left every row's partials in shared memory: st[group][parity][row] (sum, sum of squares), one group
+  // per 128 output columns of this CTA's slice. Global slot = the group's index among the 8 groups of the row (D = 1024): the
+  // same 8 numbers whatever the team size, reduced in the same order by every reader.
   epi_bar();
   float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
+  const int groups = CH_MAX_TEAM / c.team;
   if (tid < 128) {
-    const float s = st[tid * 2] + st[(128 + tid) * 2], sq = st[tid * 2 + 1] + st[(128 + tid) * 2 + 1];
-    *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_MAX_TEAM + slice) * 2) = make_float2(s, sq);
+    for (int gi = 0; gi < groups; ++gi) {
+      const float2 p0 = *reinterpret_cast<const float2*>(st + ((size_t)(gi * 2 + 0) * 128 + tid) * 2);
+      const float2 p1 = *reinterpret_cast<const float2*>(st + ((size_t)(gi * 2 + 1) * 128 + tid) * 2);
+      *reinterpret_cast<float2*>(stats + ((size_t)tid * CH_MAX_TEAM + slice * groups + gi) * 2) =
+          make_float2(__fadd_rn(p0.x, p1.x), __fadd_rn(p0.y, p1.y));
+    }
   }
   epi_bar();
   if (tid == 0) {
@@ -158,9 +163,7 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
   float2 pr[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {     // lane = (row k*4 + lane/8, slot lane%8)
-    pr[k] = (lane & 7) < c.team
-                ? __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_MAX_TEAM + (lane & 7)) * 2))
-                : make_float2(0.f, 0.f);
+    pr[k] = __ldcg(reinterpret_cast<const float2*>(stats + ((size_t)(warp * 16 + k * 4 + (lane >> 3)) * CH_MAX_TEAM + (lane & 7)) * 2));
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       pr[k].x += __shfl_xor_sync(0xffffffffu, pr[k].x, o);
@@ -401,7 +404,8 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           tc_fence_after();
           if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
           if (j == 0 || j == 2)
-            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy);
+            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
+                                                          smem_stat, slice * js.n_pair, q * 32 + lane);
           else if (j == 1)
             epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
           else
@@ -412,9 +416,9 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         }
         if (tid == 0) stamp(c, 8 + 8 * j + 5);
         if (j == 0) {
-          ln_phase(c, rb, (int)rank, slice, 0, rsum, rsq, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
+          ln_phase(c, rb, (int)rank, slice, 0, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
         } else if (j == 2) {
-          ln_phase(c, rb, (int)rank, slice, 1, rsum, rsq, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
+          ln_phase(c, rb, (int)rank, slice, 1, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
         } else {
           epi_tma_drain(lane);
           if (j == 1) team_signal(flags + F_FF16, tid);

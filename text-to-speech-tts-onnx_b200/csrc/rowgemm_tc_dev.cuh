@@ -331,7 +331,9 @@ template <int TK, int ACT, bool STATS>
 __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
                                                   uint32_t taddr, int row0, int n0, int cb_first, int cb_step, int lane,
                                                   const float* s_bias, const float* s_gate, float& rsum, float& rsq,
-                                                  uint64_t store_policy = 0ull /* L2 cache hint of the result tiles, 0 = none */) {
+                                                  uint64_t store_policy = 0ull /* L2 cache hint of the result tiles, 0 = none */,
+                                                  float* stat_slots = nullptr /* STATS: [group][parity][128 rows] float2 in smem */,
+                                                  int stat_col0 = 0 /* first column of the caller's slice */, int stat_row = 0) {
   const uint32_t out_s = smem_u32(et.out_tile), res_s = smem_u32(et.res_tile);
   const uint32_t bias_s = smem_u32(s_bias), gate_s = s_gate ? smem_u32(s_gate) : 0u;
   const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
@@ -417,8 +419,17 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
       }
     }
     if (STATS) {
+      // LayerNorm partials of this row, one (sum, sum of squares) per 128-column group of the OUTPUT and column parity of the
+      // warp: a group is two of this warp's blocks (cb & 64 = 0, then != 0), summed in one chain from zero and parked in shared
+      // memory. The grouping is the same whatever the slice width of the caller, so the statistics of a row do not depend on
+      // how many CTA pairs share its row block (batch == single utterance, bit for bit).
 #pragma unroll
       for (int i = 0; i < 32; ++i) { rsum += f[i]; rsq = fmaf(f[i], f[i], rsq); }
+      if ((cb & 64) != 0 && stat_slots != nullptr) {
+        float2* slot = reinterpret_cast<float2*>(stat_slots) + (size_t)(((n - stat_col0) >> 7) * 2 + ((cb >> 5) & 1)) * 128 + stat_row;
+        *slot = make_float2(rsum, rsq);
+        rsum = 0.f; rsq = 0.f;
+      }
     }
     if (lane == 0) bulk_wait_read0();                          // the previous block's store has read the staging tile
     __syncwarp();

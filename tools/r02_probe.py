@@ -179,6 +179,44 @@ def sec_bigvgan():
         eng.set_stream(0)
 
 
+def sec_attn_time():
+    """fp16, fused chain: time per call and the event-timed share of attention / chain, one and eight config-3 utterances."""
+    import torch
+    eng = f5_engine()
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    L, n_text = 144000, 150
+    for U in (1, 8):
+        ins = [synth.f5_inputs(1000 + i, L, n_text) for i in range(U)]
+        N = int(ins[0][2][0])
+        ns = 256 * (N - (L // 256 + 1) - 1)
+        audio = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).cuda()
+        ids = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).cuda()
+        noise = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).cuda()
+        pcm = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
+
+        def run():
+            eng.f5_synthesize_batch_device(U, audio.data_ptr(), L, ids.data_ptr(), n_text, N, noise.data_ptr(), pcm.data_ptr(), precision=capi.F16)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5 if U == 1 else 2
+            e0.record(stream)
+            for _ in range(reps):
+                run()
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        eng.profile_begin()
+        with torch.cuda.stream(stream):
+            run()
+        prof = eng.profile_end()
+        out(section="attn_time", U=U, poly=os.environ.get("B200TTS_ATTN_POLY", "default"), ms_per_call=ms, ms_per_utt=ms / U,
+            attention_ms=round(prof["f5.attention"]["ms"], 3), chain_ms=round(prof["f5.chain"]["ms"], 3))
+
+
 def sec_twins():
     """Two copies of one utterance in a batch: are their mels bit-identical? (rows at different tile offsets)"""
     import torch
