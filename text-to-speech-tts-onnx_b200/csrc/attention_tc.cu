@@ -19,8 +19,13 @@
 // A fraction of the exponentials (template POLY of every 4 pairs) runs on the FMA pipes instead of the MUFU unit
 // (Cody-Waite range reduction + degree-3 minimax polynomial, relative error 8.8e-5 < half an ulp of fp16): the kernel is
 // MUFU-bound otherwise (16 ex2 per clock and SM against 8192 tensor FLOPs).
-// 320 threads: warps 0-7 = softmax/epilogue, warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.
-// Shared memory 82 KB and 256 TMEM columns per CTA -> two CTAs per SM overlap each other's non-MUFU phases.
+// Threads: 4 G softmax / epilogue warps (G = 2 threads per query row by default, 4 optional), then the TMA producer and the
+// MMA issuer + TMEM owner. Shared memory 84 KB and 256 TMEM columns per CTA -> two CTAs per SM.
+// What bounds it (profiles/r02/attention_r02.md): not one pipe. Removing the exponentials, the MMAs and the loads altogether
+// (debug switches, since deleted) only shortened a launch from 20.2 to 15.9 us: ~380 instructions per warp and key block at an
+// IPC of 0.5 per scheduler (stall reasons: fixed-latency `wait` 24 %, scoreboard 27 %, MIO / math throttle 10 %), i.e. issue-
+// and latency-bound softmax code. 4 threads per row (twice the warps, half the work each) and FMA-pipe exponentials both
+// measured within noise of the default; kept as switches (B200TTS_ATTN_G, B200TTS_ATTN_POLY).
 #include "attention_tc.cuh"
 
 #include <cstdio>
@@ -38,16 +43,18 @@ namespace {
 using namespace tc;
 
 constexpr int BQ = 128, BKEY = 128, HD = 64;
-constexpr int NTHREADS = 320;
-constexpr int WARP_TMA = 8, WARP_MMA = 9;       // highest warp ids: the SMSP arbiter favours them over the softmax warps
+// G softmax threads per query row (2 or 4): thread (row r, key group g) owns 128 / G keys of every block. 4 G softmax warps,
+// then the TMA producer and the MMA issuer (highest warp ids: the SMSP arbiter favours them over the softmax warps)
+constexpr int nthreads(int G) { return (4 * G + 2) * 32; }
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
 constexpr int K_BYTES = BKEY * HD * 2;          // 16 KB
 constexpr int V_BYTES = HD * BKEY * 2;          // 16 KB = two [64 d][64 keys] chunks
-constexpr int XCH_BYTES = 2 * 2 * BQ * 4;       // [block parity][key half][row] floats: the row maximum / row sum exchange
+constexpr int XCH_BYTES = 2 * 4 * BQ * 4;       // [block parity][key group][row] floats: the row maximum / row sum exchange
 constexpr int KV_STAGES = 2;
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCH_BYTES + 128;      // 82 KB
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCH_BYTES + 128;      // 84 KB
 constexpr float RESCALE_TAU = 8.0f;             // log2 units
 constexpr int ATTN_POLY_DEFAULT = 1;
+constexpr int ATTN_G_DEFAULT = 2;
 // tensor-memory columns of a CTA
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
 
@@ -130,15 +137,20 @@ __device__ __forceinline__ void ex2_fma_pair(float e0, float e1, float& p0, floa
   p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
-// the two warps (key halves) that share query rows [32 qd, 32 qd + 32)
-__device__ __forceinline__ void pair_bar(int qd) {
+// the G warps (key groups) that share query rows [32 qd, 32 qd + 32)
+template <int G>
+__device__ __forceinline__ void rows_bar(int qd) {
   switch (qd) {                                   // immediate barrier ids: a register id makes ptxas reserve all 16
-    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(32 * G) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(32 * G) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(32 * G) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(32 * G) : "memory"); break;
   }
 }
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = lanes, K = 16 elements = 8 columns of packed 16-bit pairs)
 // is read from tensor memory
@@ -152,8 +164,8 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 }
 
 // POLY: of every 4 score pairs, POLY are exponentiated on the FMA pipes (0, 1 or 2)
-template <bool F16, int POLY>
-__global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,
+template <bool F16, int POLY, int G>
+__global__ void __launch_bounds__(nthreads(G), 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,
                                                               const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -172,6 +184,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
   uint64_t* pv_done = bars + 12;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
+  constexpr int WARP_TMA = 4 * G, WARP_MMA = 4 * G + 1;
+  constexpr int KT = BKEY / G;                    // keys per softmax thread and block
+  constexpr int OC = HD / G;                      // output columns per softmax thread
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -193,8 +208,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_full, 256);
+    mbar_init(s_free, 4 * G);                   // one arrival per softmax WARP: 256 per-thread arrivals on one barrier word
+    mbar_init(p_full, 4 * G);                   // serialise in the shared-memory atomic unit (~1 us per block, profiles/r02)
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -266,43 +281,53 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ===== softmax + epilogue: row r of the query tile, key half g of every block =====
+    // ===== softmax + epilogue: row r of the query tile, key group g (KT keys) of every block =====
     const int qd = warp & 3, g = warp >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const uint32_t tmem_Og = tmem_O + lane_addr + (uint32_t)(g * 32);            // this thread's 32 of the 64 output columns
-    const uint32_t tmem_Pg = tmem_P + lane_addr + (uint32_t)(g * 32);            // its 64 probabilities = 32 packed columns
+    const uint32_t tmem_Sg = tmem_S + lane_addr + (uint32_t)(g * KT);            // this thread's KT scores
+    const uint32_t tmem_Og = tmem_O + lane_addr + (uint32_t)(g * OC);            // its OC of the 64 output columns
+    const uint32_t tmem_Pg = tmem_P + lane_addr + (uint32_t)(g * KT / 2);        // its KT probabilities = KT / 2 packed columns
     const float LOG2E = 1.4426950408889634f;
-    float m_ref = -INFINITY, l_run = 0.f;        // m_ref in log2 units, shared by the two threads of a row
+    float m_ref = -INFINITY, l_run = 0.f;        // m_ref in log2 units, shared by the G threads of a row
 
     for (int j = 0; j < nblocks; ++j) {
-      const int kvalid = Nb - j * BKEY - g * 64;        // valid keys among this thread's 64 (may be <= 0 in the last block)
+      const int kvalid = Nb - j * BKEY - g * KT;        // valid keys among this thread's KT (may be <= 0 in the last block)
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 2);
-      uint32_t v[2][32];
-      tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64), v[0]);
-      tmem_ld32(tmem_S + lane_addr + (uint32_t)(g * 64 + 32), v[1]);
+      uint32_t v[KT];
+      if (KT == 64) {
+        tmem_ld32(tmem_Sg, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+        tmem_ld32(tmem_Sg + 32u, reinterpret_cast<uint32_t(&)[32]>(v[KT - 32]));
+      } else {
+        tmem_ld32(tmem_Sg, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+      }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(s_free);
-      if (kvalid < 64) {                          // last, ragged block: keys beyond N do not exist
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      if (kvalid < KT) {                          // last, ragged block: keys beyond N do not exist
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kvalid) v[c][i] = 0xff800000u;        // -inf
+        for (int i = 0; i < KT; ++i)
+          if (i >= kvalid) v[i] = 0xff800000u;        // -inf
       }
-      float mx = -INFINITY;
+      float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;        // four chains: the FMNMX3 latency is exposed otherwise
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
-      // the row maximum over both key halves (key half 0 always holds a valid key, so it is finite)
-      float* xb = xch + (j & 1) * (2 * BQ);
+      for (int i = 0; i < KT; i += 8) {
+        mxa = max3(mxa, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        mxb = max3(mxb, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        mxc = max3(mxc, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+        mxd = max3(mxd, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+      }
+      float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+      // the row maximum over all key groups (group 0 always holds a valid key, so it is finite)
+      float* xb = xch + (j & 1) * (4 * BQ);
       xb[g * BQ + r] = mx;
-      pair_bar(qd);
-      mx = fmaxf(mx, xb[(g ^ 1) * BQ + r]) * LOG2E;
+      rows_bar<G>(qd);
+#pragma unroll
+      for (int o = 1; o < G; ++o) mx = fmaxf(mx, xb[((g + o) & (G - 1)) * BQ + r]);
+      mx *= LOG2E;
       // lazy running maximum
       const bool move = mx > m_ref + RESCALE_TAU;
       const float m_new = move ? mx : m_ref;
@@ -312,23 +337,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       // P = exp2(s*log2e - m) -> 16 bit, kept in registers; fp32 row sum (packed accumulator)
       const unsigned long long sc2 = pk2(LOG2E, LOG2E), nm2 = pk2(-m_ref, -m_ref);
       unsigned long long sum2 = pk2(0.f, 0.f);
-      uint32_t pkd[32];
+      uint32_t pkd[KT / 2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int i = u * 2;
-          float e0, e1, p0, p1;
-          up2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sc2, nm2), e0, e1);
-          if ((u & 3) < POLY) {
-            ex2_fma_pair(e0, e1, p0, p1);
-          } else {
-            p0 = ex2(e0);
-            p1 = ex2(e1);
-          }
-          sum2 = add2(sum2, pk2(p0, p1));
-          pkd[c * 16 + u] = pk16<F16>(p0, p1);
+      for (int u = 0; u < KT / 2; ++u) {
+        const int i = u * 2;
+        float e0, e1, p0, p1;
+        up2(fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+        if ((u & 3) < POLY) {
+          ex2_fma_pair(e0, e1, p0, p1);
+        } else {
+          p0 = ex2(e0);
+          p1 = ex2(e1);
         }
+        sum2 = add2(sum2, pk2(p0, p1));
+        pkd[u] = pk16<F16>(p0, p1);
       }
       float s0, s1;
       up2(sum2, s0, s1);
@@ -337,11 +359,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
         mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);                 // O += P_{j-1} V_{j-1} has landed (issued a whole block ago)
         tc_fence_after();
       }
-      tmem_st32(tmem_Pg, pkd);
-      if (j > 0 && __any_sync(0xffffffffu, move)) {                  // rescale this thread's half of O (rare after the first blocks)
+      tmem_st_n(tmem_Pg, pkd);
+      if (j > 0 && __any_sync(0xffffffffu, move)) {                  // rescale this thread's share of O (rare after the first blocks)
+        uint32_t o[16];
 #pragma unroll
-        for (int cb = 0; cb < 32; cb += 16) {
-          uint32_t o[16];
+        for (int cb = 0; cb < OC; cb += 16) {
           tmem_ld16(tmem_Og + (uint32_t)cb, o);
           tmem_ld_wait();
 #pragma unroll
@@ -351,25 +373,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) attn_tc_kernel(const __grid_const
       }
       tmem_st_wait();
       tc_fence_before();                 // order our TMEM writes before the MMA that reads P / accumulates into O
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       if (threadIdx.x == 0) astamp(a, 4 + 4 * j + 3);
     }
-    // ---- row sum over both key halves, normalise, store ----
-    float* xb = xch + (nblocks & 1) * (2 * BQ);          // the buffer the last block did not use
+    // ---- row sum over all key groups, normalise, store ----
+    float* xb = xch + (nblocks & 1) * (4 * BQ);          // the buffer the last block did not use
     xb[g * BQ + r] = l_run;
-    pair_bar(qd);
-    const float scale = 1.0f / (l_run + xb[(g ^ 1) * BQ + r]);
+    rows_bar<G>(qd);
+    float l_all = 0.f;
+#pragma unroll
+    for (int o = 0; o < G; ++o) l_all += xb[o * BQ + r];                 // the same order in every thread of the row
+    const float scale = 1.0f / l_all;
     mbar_wait(pv_done, (uint32_t)(nblocks - 1) & 1u);
     tc_fence_after();
     if (threadIdx.x == 0) astamp(a, 2);
-    uint32_t o[32];
-    tmem_ld32(tmem_Og, o);
+    uint32_t o[OC];
+    tmem_ld_n(tmem_Og, o);
     tmem_ld_wait();
     const int q = q0 + r;
     if (q < Nb) {
-      __nv_bfloat16* dst = a.out + ((a.seq_off ? (long)rb0 : (long)b * a.N) + q) * a.ldo + h * HD + g * 32;
+      __nv_bfloat16* dst = a.out + ((a.seq_off ? (long)rb0 : (long)b * a.N) + q) * a.ldo + h * HD + g * OC;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < OC / 8; ++k) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -414,15 +440,25 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
     const int p = e ? atoi(e) : ATTN_POLY_DEFAULT;
     return p < 0 ? 0 : (p > 2 ? 2 : p);
   }();
+  // softmax threads per query row: B200TTS_ATTN_G = 2 or 4 (read once)
+  static const int gsel = [] {
+    const char* e = getenv("B200TTS_ATTN_G");
+    const int g = e ? atoi(e) : ATTN_G_DEFAULT;
+    return g == 2 ? 0 : 1;
+  }();
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, AttnArgs);
-  static const KernelFn kernels[2][3] = {{attn_tc_kernel<false, 0>, attn_tc_kernel<false, 1>, attn_tc_kernel<false, 2>},
-                                         {attn_tc_kernel<true, 0>, attn_tc_kernel<true, 1>, attn_tc_kernel<true, 2>}};
+  static const KernelFn kernels[2][2][3] = {
+      {{attn_tc_kernel<false, 0, 2>, attn_tc_kernel<false, 1, 2>, attn_tc_kernel<false, 2, 2>},
+       {attn_tc_kernel<true, 0, 2>, attn_tc_kernel<true, 1, 2>, attn_tc_kernel<true, 2, 2>}},
+      {{attn_tc_kernel<false, 0, 4>, attn_tc_kernel<false, 1, 4>, attn_tc_kernel<false, 2, 4>},
+       {attn_tc_kernel<true, 0, 4>, attn_tc_kernel<true, 1, 4>, attn_tc_kernel<true, 2, 4>}}};
   static std::once_flag once;
   std::call_once(once, [] {
-    for (int t = 0; t < 2; ++t)
-      for (int p = 0; p < 3; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    for (int g = 0; g < 2; ++g)
+      for (int t = 0; t < 2; ++t)
+        for (int p = 0; p < 3; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[g][t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
-  const KernelFn kernel = kernels[f16 ? 1 : 0][poly];
+  const KernelFn kernel = kernels[gsel][f16 ? 1 : 0][poly];
   AttnArgs a{N, H, out, H * HD, d_seq_off, d_seq_len, nullptr};
   static DevBuf<unsigned long long> trace_buf;
   const char* trace_path = getenv("B200TTS_ATTN_TRACE");
@@ -434,7 +470,7 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
   }
   B2_CHECK(S <= 65535, "attention_tc: too many sequences");
   dim3 grid(ceil_div(N, BQ), H, S);
-  launch_pdl(kernel, grid, dim3(NTHREADS), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
+  launch_pdl(kernel, grid, dim3(nthreads(gsel == 0 ? 2 : 4)), (size_t)SMEM_BYTES, stream, map_qk, map_v, a);
   B2_LAUNCH_CHECK();
   count_launch();
   if (trace_path) {                                        // debug only: dump the stamps of this launch

@@ -31,6 +31,8 @@ def main():
     for s, n in names.items():
         v_ = t[:, s]; v_ = v_[v_ > 0]
         print(f"{n:28s} min {rel(v_.min()):7.2f} med {rel(np.median(v_)):7.2f} max {rel(v_.max()):7.2f}")
+    if os.environ.get("ATTN_TRACE_BRIEF"):
+        return
     for j in range(9):
         row = []
         for kk, nm in enumerate(["S issued", "PV issued", "s_full seen", "p_full arrived"]):
