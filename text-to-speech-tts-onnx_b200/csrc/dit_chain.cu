@@ -14,15 +14,23 @@
 //   T = 1 for a batch of 8 (71 row blocks, one pair each: 4 / 8 / 4 / 12 sub-tiles per GEMM, hand-offs stay inside the pair).
 //
 // Per CTA: 11 warps as in rowgemm_tc.cu (0-7 epilogue, 8 A producer, 9 MMA issuer (leader CTA only), 10 B producer).
-//   job 0  out  : A = att16  K = D    epilogue: x += gate_msa * (acc + b)   + LN statistics
-//   job 1  ff1  : A = n16    K = D    epilogue: GELU_tanh(acc + b) -> ff16
-//   job 2  ff2  : A = ff16   K = FF   epilogue: x += gate_mlp * (acc + b)   + LN statistics
-//   job 3  qkv  : A = n16b   K = D    epilogue: bias + interleaved RoPE, V transposed   (the NEXT block's projections)
-// LayerNorm (no affine, eps 1e-6, modules.py:296) of a row needs all 1024 columns = all T pairs: each CTA reduces (sum, sum of
-// squares) of its columns in the epilogue it already runs (thread-local: a lane owns a row), publishes them (T partial pairs
-// per row), waits for its team, then normalises + modulates its own [128 rows] x [D / T columns] slab of x (re-read from L2)
-// into the 16-bit A operand of the next GEMM. The weight stream never waits for anything (the B producer runs ahead across job
-// boundaries and does not even wait for the previous kernel: weights are constants).
+//   job 0  out  : A = att16  K = D    epilogue: x += gate_msa * (acc + b); n16 = c x (1 + scale_mlp); LN partials
+//   job 1  ff1  : A = n16    K = D    epilogue: GELU_tanh(rho acc - rmu u + v) -> ff16
+//   job 2  ff2  : A = ff16   K = FF   epilogue: x += gate_mlp * (acc + b); n16b = c x (1 + scale_nxt); LN partials
+//   job 3  qkv  : A = n16b   K = D    epilogue: rho acc - rmu u + v, interleaved RoPE, V transposed   (the NEXT block's projections)
+// LayerNorm (no affine, eps 1e-6, modules.py:296) of a row needs all 1024 columns = all T pairs, i.e. it can only be applied
+// after the whole row has been produced. Until round 2b that was a second pass: publish (sum, sum of squares), wait for the
+// team, re-read the CTA's slab of x from L2, normalise + modulate, write the 16-bit A operand (14 of 57 us per block for one
+// utterance, 2 x 28 us of a 300 us launch for eight: profiles/r02). Now the LayerNorm is FOLDED INTO THE GEMMS around it:
+//     (LN(x)(1 + s) + t) W^T + b  =  rstd * (x (1 + s)) W^T  -  rstd * mean * u  +  v,    u = W (1 + s),  v = W t + b
+// (u, v: per-column vectors of a (block, Euler step), computed once per operand type from the 16-bit weights, f5.cu). The
+// epilogue that produces x writes  c * x * (1 + s)  as the 16-bit A operand in the same pass (plain 64-byte stores per lane)
+// and publishes the row partials; the NEXT GEMM's epilogue computes  (rstd / c) * acc - rstd * mean * u + v. The statistics
+// are needed only there, a whole main loop later, so no CTA ever waits for them. c is the row's 1 / std at the previous
+// LayerNorm (carried in `rowscale`): algebraically irrelevant, it keeps the fp16 operand in the range normalised rows have.
+// Only the last block's final LayerNorm (it feeds proj_out, a separate GEMM) still takes the second pass (ln_phase).
+// The weight stream never waits for anything (the B producer runs ahead across job boundaries and does not even wait for the
+// previous kernel: weights are constants).
 #include "dit_chain.cuh"
 
 #include <cstdlib>
@@ -39,7 +47,7 @@ constexpr int CH_A_BYTES = 128 * 128;            // 128 rows x 64 channels x 2 B
 constexpr int CH_B_BYTES = 128 * 128;            // up to 128 weight rows per CTA and chunk (half of a 256-column sub-tile)
 constexpr int CH_STAT_BYTES = 8 * 2 * 128 * 2 * 4;   // [128-column group of the slice][column parity e][row][sum, sum of squares]
 constexpr int CH_EPI_BYTES = 8 * 8192;           // per epilogue warp: residual tile + result tile (4 KB each, rowgemm_tc_dev.cuh: EpiTile)
-constexpr int CH_VEC_BYTES = 2 * 256 * 4;        // bias / gate of the current sub-tile
+constexpr int CH_VEC_BYTES = 3 * 256 * 4;        // bias / gate (or u) / 1 + scale of the current sub-tile
 constexpr int CH_MAX_TEAM = 8;                   // statistics slots per row
 constexpr int CH_ROWS = 256;                     // rows per block (one M = 256 pair tile)
 constexpr int CH_NFLAGS = 8;
@@ -60,6 +68,9 @@ struct ChainArgs {
   const int2* rowinfo;
   __nv_bfloat16* vt_out;
   int vt_ld, vt_heads;
+  // LayerNorm folded into the GEMMs (see the header): per-column vectors of this (block, Euler step) and the per-row scale
+  const float *u_ff1, *v_ff1, *u_qkv, *v_qkv;
+  float* rowscale;
   float* stats;
   unsigned* flags;
   unsigned long long* trace;      // optional [CTA][64] globaltimer stamps (B200TTS_CHAIN_TRACE, tools/chain_trace.py)
@@ -124,18 +135,11 @@ __device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int
   return s;
 }
 
-// LayerNorm statistics + modulation of this CTA's [128 rows] x [D / team columns] slab of x (all 256 epilogue threads).
-//   rsum / rsq : this lane's row sums over the warp's column blocks (epilogue_rows_tma<.., STATS>)
-// Measured alternatives that were SLOWER on B200 (profiles/r02/chain_timeline.md): fetching the slab before the statistics
-// arrive with 16 row loads per lane in flight (+3.6 ms per utterance), and walking whole rows instead of 128-column groups
-// (+6 ms): more loads in flight per thread only lengthen the loaded L2 latency here.
-__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind,
-                                         const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
-                                         unsigned* flag_ready, float* st, int warp, int lane) {
-  const int tid = warp * 32 + lane;
-  // the row-layout epilogue left every row's partials in shared memory: st[group][parity][row] (sum, sum of squares), one group
-  // per 128 output columns of this CTA's slice. Global slot = the group's index among the 8 groups of the row (D = 1024): the
-  // same 8 numbers whatever the team size, reduced in the same order by every reader.
+// This CTA's LayerNorm partials (left in shared memory by the row-layout epilogue: st[group][parity][row] = (sum, sum of
+// squares), one group per 128 output columns of the CTA's slice) -> the row block's global slots. Global slot = the group's
+// index among the 8 groups of a row (D = 1024): the same 8 numbers whatever the team size, reduced in the same order by every
+// reader. The caller's team_signal() publishes them together with the tiles the same epilogue wrote.
+__device__ __forceinline__ void publish_stats(const ChainArgs& c, int rb, int rank, int slice, int kind, const float* st, int tid) {
   epi_bar();
   float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
   const int groups = CH_MAX_TEAM / c.team;
@@ -147,6 +151,30 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
           make_float2(__fadd_rn(p0.x, p1.x), __fadd_rn(p0.y, p1.y));
     }
   }
+}
+// (mean, 1 / std) of row `r` (0 .. 127 of this CTA) from the 8 published slots; the caller has waited for the team's counter
+__device__ __forceinline__ float2 row_mean_rstd(const ChainArgs& c, int rb, int rank, int kind, int r) {
+  const float4* p = reinterpret_cast<const float4*>(c.stats + (((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128 + r) * CH_MAX_TEAM) * 2);
+  const float4 a0 = __ldcg(p), a1 = __ldcg(p + 1), a2 = __ldcg(p + 2), a3 = __ldcg(p + 3);      // (s0, q0, s1, q1) ...
+  const float s = __fadd_rn(__fadd_rn(__fadd_rn(a0.x, a0.z), __fadd_rn(a1.x, a1.z)), __fadd_rn(__fadd_rn(a2.x, a2.z), __fadd_rn(a3.x, a3.z)));
+  const float q = __fadd_rn(__fadd_rn(__fadd_rn(a0.y, a0.w), __fadd_rn(a1.y, a1.w)), __fadd_rn(__fadd_rn(a2.y, a2.w), __fadd_rn(a3.y, a3.w)));
+  const float inv_d = 1.0f / (float)c.D;
+  const float mean = __fmul_rn(s, inv_d);
+  const float rstd = rsqrtf(__fadd_rn(fmaxf(__fsub_rn(__fmul_rn(q, inv_d), __fmul_rn(mean, mean)), 0.f), 1e-6f));
+  return make_float2(mean, rstd);
+}
+
+// LayerNorm statistics + modulation of this CTA's [128 rows] x [D / team columns] slab of x (all 256 epilogue threads).
+//   rsum / rsq : this lane's row sums over the warp's column blocks (epilogue_rows_tma<.., STATS>)
+// Measured alternatives that were SLOWER on B200 (profiles/r02/chain_timeline.md): fetching the slab before the statistics
+// arrive with 16 row loads per lane in flight (+3.6 ms per utterance), and walking whole rows instead of 128-column groups
+// (+6 ms): more loads in flight per thread only lengthen the loaded L2 latency here.
+__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind,
+                                         const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
+                                         unsigned* flag_ready, float* st, int warp, int lane) {
+  const int tid = warp * 32 + lane;
+  publish_stats(c, rb, rank, slice, kind, st, tid);
+  float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
   epi_bar();
   if (tid == 0) {
     fence_acq_rel_gpu();
@@ -362,12 +390,14 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     et.res_tile = smem_epi + warp * 8192; et.out_tile = et.res_tile + 4096; et.res_bar = &res_bar[warp]; et.res_phase = 0u;
     float* s_bias = smem_vec;
     float* s_gate = smem_vec + 256;
-    // bias / gate of the sub-tile's columns -> shared memory (broadcast reads in the epilogue)
-    auto stage_vec = [&](const float* bias, const float* gate, int n0, int n) {
+    float* s_mul = smem_vec + 512;
+    // bias (or v) / gate (or u) / 1 + scale of the sub-tile's columns -> shared memory (broadcast reads in the epilogue)
+    auto stage_vec = [&](const float* bias, const float* gate, const float* scale, int n0, int n) {
       epi_bar();                                               // the previous sub-tile's readers are done
       if (tid < n) {
         s_bias[tid] = __ldg(bias + n0 + tid);
         if (gate) s_gate[tid] = __ldg(gate + n0 + tid);
+        if (scale) s_mul[tid] = __fadd_rn(1.0f, __ldg(scale + n0 + tid));
       }
       epi_bar();
     };
@@ -382,42 +412,72 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     for (int rb = team; rb < c.nrb; rb += c.teams) {
       unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
       const int row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
+      const int myrow = row0 + lane;                           // the row this lane owns in every epilogue of the row block
+      // LayerNorm folded into the GEMMs: job 0 / 2 write c * x * (1 + scale) next to x, job 1 / 3 undo c and apply mean / rstd.
+      // c = the row's 1 / std at the PREVIOUS LayerNorm (a scale only: any c > 0 gives the same result up to rounding; a stale
+      // estimate keeps the 16-bit operand in the range the normalised rows would have)
+      float c_row = myrow < c.R ? __ldcg(c.rowscale + myrow) : 1.0f;
+      float rho = 1.0f, rmu = 0.0f;
       for (int j = 0; j < njobs; ++j) {
         const JobShape js = job_shape(j, c.D, c.FF, c.team);
         a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.K / BK;
-        const float* bias = j == 0 ? c.b_out : j == 1 ? c.b_ff1 : j == 2 ? c.b_ff2 : c.b_qkv;
-        const float* gate = j == 0 ? c.gate_msa : j == 2 ? c.gate_mlp : nullptr;
+        const bool fold = j == 0 || (j == 2 && c.has_qkv);      // this job's epilogue emits the next GEMM's A operand
+        const float* bias = j == 0 ? c.b_out : j == 1 ? c.v_ff1 : j == 2 ? c.b_ff2 : c.v_qkv;
+        const float* gate = j == 0 ? c.gate_msa : j == 1 ? c.u_ff1 : j == 2 ? c.gate_mlp : c.u_qkv;
+        const float* scale = !fold ? nullptr : j == 0 ? c.scale_mlp : c.scale_nxt;
         if (j == 3) {
           a.rope_cs = c.rope_cs; a.rope_cols = 2 * c.D; a.rope_rows = c.rope_rows;
           a.vt_out = c.vt_out; a.vt_col0 = 2 * c.D; a.vt_ld = c.vt_ld; a.vt_heads = c.vt_heads;
         } else {
           a.rope_cs = nullptr; a.rope_cols = 0; a.rope_rows = 1; a.vt_out = nullptr; a.vt_col0 = 0;
         }
+        if (j == 1 || j == 3) {
+          // the statistics of the LayerNorm in front of this GEMM: published by the whole team before it signalled the A tiles
+          if (tid == 0) wait_counter(flags + (j == 1 ? F_N16 : F_N16B), team_ctas);
+          epi_bar();
+          const float2 ms = row_mean_rstd(c, rb, (int)rank, j == 1 ? 0 : 1, q * 32 + lane);
+          rho = __fdiv_rn(ms.y, c_row);
+          rmu = __fmul_rn(ms.y, ms.x);
+          c_row = ms.y;                                         // the scale of the NEXT emitted operand
+          if (j == 3 && slice == 0 && e == 0 && myrow < c.R) c.rowscale[myrow] = ms.y;     // for the next block's launch
+        }
+        EpiEmit emit;
+        if (fold) {
+          emit.row = myrow < c.R ? reinterpret_cast<uint16_t*>(j == 0 ? c.n16 : c.n16b) + (size_t)myrow * c.D : nullptr;
+          emit.s_mul = s_mul; emit.c = c_row;
+        }
         float rsum = 0.f, rsq = 0.f;
         for (int st = 0; st < js.nsubt; ++st, ++t) {
           const uint32_t buf = t & 1u;
           const int n0 = slice * js.n_pair + st * js.w;
           const uint32_t taddr = tmem_base + buf * 256u + lane_sel;
-          stage_vec(bias, gate, n0, js.w);
+          stage_vec(bias, gate, scale, n0, js.w);
           if (j == 0 || j == 2) epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
           mbar_wait(&acc_full[buf], (t >> 1) & 1u);
           tc_fence_after();
           if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
           if (j == 0 || j == 2)
             epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
-                                                          smem_stat, slice * js.n_pair, q * 32 + lane);
+                                                          smem_stat, slice * js.n_pair, q * 32 + lane, 1.0f, 0.0f, emit);
           else if (j == 1)
-            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
+            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+                                                                    0ull, nullptr, 0, 0, rho, rmu);
           else
-            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, nullptr, rsum, rsq);
+            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+                                                                0ull, nullptr, 0, 0, rho, rmu);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
         }
         if (tid == 0) stamp(c, 8 + 8 * j + 5);
-        if (j == 0) {
-          ln_phase(c, rb, (int)rank, slice, 0, c.scale_mlp, c.shift_mlp, c.n16, flags + F_STAT1, flags + F_N16, smem_stat, warp, lane);
+        if (fold) {
+          // x tiles (TMA stores) and the emitted 16-bit rows (plain stores) of this CTA are complete: publish the LayerNorm
+          // partials and hand everything to the team with ONE counter (the next GEMM's A producer and its epilogue wait on it)
+          publish_stats(c, rb, (int)rank, slice, j == 0 ? 0 : 1, smem_stat, tid);
+          epi_tma_drain(lane);
+          team_signal(flags + (j == 0 ? F_N16 : F_N16B), tid);
         } else if (j == 2) {
+          // last block: the final LayerNorm feeds proj_out (a separate GEMM) -> normalise in a second pass as before
           ln_phase(c, rb, (int)rank, slice, 1, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
         } else {
           epi_tma_drain(lane);
@@ -496,6 +556,8 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
   c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.rowinfo = d.rowinfo; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
+  B2_CHECK(d.u_ff1 && d.v_ff1 && d.rowscale && (!d.has_qkv || (d.u_qkv && d.v_qkv)), "dit_chain: folded-LayerNorm vectors");
+  c.u_ff1 = d.u_ff1; c.v_ff1 = d.v_ff1; c.u_qkv = d.u_qkv; c.v_qkv = d.v_qkv; c.rowscale = d.rowscale;
   c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
   { const char* v = getenv("B200TTS_CHAIN_L2HINT"); c.l2hint = v != nullptr && atoi(v) != 0; }
   CUtensorMap mA[4], mB[4];

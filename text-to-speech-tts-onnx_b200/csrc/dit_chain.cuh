@@ -32,6 +32,12 @@ struct DitChain {
   const int2* rowinfo = nullptr;   // ragged batches: (sequence, position) per row (rowgemm.cuh)
   __nv_bfloat16* vt_out = nullptr;
   int vt_ld = 0, vt_heads = 0;
+  // LayerNorm folded into the GEMMs: per-column vectors of THIS (block, Euler step), computed from the 16-bit weights
+  //   u_ff1 = W_ff1 (1 + scale_mlp), v_ff1 = W_ff1 shift_mlp + b_ff1 [FF];  u_qkv / v_qkv likewise for the next block's q|k|v [3D]
+  // and the per-row scale carried from LayerNorm to LayerNorm: rowscale[r] = 1 / std of row r at the LayerNorm in front of this
+  // block's attention (written by ln_modulate for block 0 and by the previous chain launch afterwards; updated in place)
+  const float *u_ff1 = nullptr, *v_ff1 = nullptr, *u_qkv = nullptr, *v_qkv = nullptr;
+  float* rowscale = nullptr;
   // team synchronisation scratch (sizes below); `flags` must be zero when the kernel starts
   float* stats = nullptr;
   unsigned* flags = nullptr;

@@ -57,6 +57,10 @@ struct VocosBlock {
 struct DiTLayer {
   Lin qkv, out, ff1, ff2;
   DevBuf<float> mod;         // [nfe][6*D]: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+  // LayerNorm folded into the GEMMs of the fused chain (dit_chain.cu), per 16-bit operand type ([0] bf16, [1] fp16):
+  //   fu1 / fv1 [nfe][FF]: W_ff1 (1 + scale_mlp), W_ff1 shift_mlp + b_ff1;  fuq / fvq [nfe][3D]: the same for q|k|v with the msa pair
+  DevBuf<float> fu1[2], fv1[2], fuq[2], fvq[2];
+  bool fold_ready[2] = {false, false};
 };
 
 }  // namespace
@@ -108,7 +112,8 @@ struct F5Model {
   const float *cur_cos = nullptr, *cur_sin = nullptr;
   DevBuf<float> n32, qkv32, att32, ff32, kT32, v32, s32, c32;          // fp32 engine
   DevBuf<__nv_bfloat16> h16, c16, n16, n16b, qk16, vT16, att16, ff16, x16;   // tensor-core engine (bf16 or fp16 bits)
-  DevBuf<float> chain_stats;                                           // dit_chain.cuh: team scratch
+  DevBuf<float> chain_stats;
+  DevBuf<float> rowscale;       // [rows] 1 / std of every row at the latest LayerNorm (dit_chain.cu)                                           // dit_chain.cuh: team scratch
   DevBuf<unsigned> chain_flags;                                        // [depth][row blocks][8], zeroed once per Euler step
   DevBuf<unsigned long long> chain_trace;                              // debug only (B200TTS_CHAIN_TRACE)
   DevBuf<__half2> rope_cs16;                                           // [N][64] (cos, sin): exact, the tables are fp16-rounded (q5)
@@ -595,6 +600,7 @@ void reserve_step(F5Model& m, bool fast) {
   if (fast) {
     m.h16.reserve(R * m.D); m.c16.reserve(R * m.D); m.n16.reserve(R * m.D); m.n16b.reserve(R * m.D); m.att16.reserve(R * m.D);
     m.chain_stats.reserve(dit_chain_stats_floats((int)R));
+    m.rowscale.reserve(R);
     m.chain_flags.reserve(dit_chain_flag_words((int)R) * (size_t)m.depth);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
@@ -656,6 +662,18 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     if (m.ragged) B2_CUDA(cudaMemsetAsync(m.vT16.p, 0, (size_t)2 * m.U * m.H * m.hd * m.Npad * sizeof(__nv_bfloat16), s));
     rope_pack_half(m.cur_cos, m.cur_sin, m.rope_cs16.p, (long)N * m.hd, s);
     for (auto& L : m.layers) { lin_prepare_tc(e, L.qkv, f16); lin_prepare_tc(e, L.out, f16); lin_prepare_tc(e, L.ff1, f16); lin_prepare_tc(e, L.ff2, f16); }
+    if (chain) {
+      for (auto& L : m.layers) {
+        if (L.fold_ready[f16]) continue;
+        L.fu1[f16].alloc((size_t)m.nfe * m.FF); L.fv1[f16].alloc((size_t)m.nfe * m.FF);
+        L.fuq[f16].alloc((size_t)m.nfe * 3 * D); L.fvq[f16].alloc((size_t)m.nfe * 3 * D);
+        fold_vectors(L.ff1.tc[f16].w.p, L.ff1.tc[f16].ldc, D, f16, L.mod.p + 4 * D, L.mod.p + 3 * D, 6 * D, L.ff1.bias.p, L.fu1[f16].p, L.fv1[f16].p,
+                     m.FF, m.nfe, s);
+        fold_vectors(L.qkv.tc[f16].w.p, L.qkv.tc[f16].ldc, D, f16, L.mod.p + D, L.mod.p, 6 * D, L.qkv.bias.p, L.fuq[f16].p, L.fvq[f16].p, 3 * D,
+                     m.nfe, s);
+        L.fold_ready[f16] = true;
+      }
+    }
   }
   // q | k | v of block l from the LN-modulated rows in `a16`: one GEMM, RoPE + V^T in the epilogue (modules.py:459-466)
   auto qkv_fast = [&](DiTLayer& L, const __nv_bfloat16* a16) {
@@ -714,7 +732,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       B2_CUDA(cudaMemsetAsync(m.chain_flags.p, 0, flag_words * m.depth * sizeof(unsigned), s));
       {
         const float* mod0 = m.layers[0].mod.p + (size_t)step * 6 * D;
-        { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, mod0 + D, mod0, m.n16b.p, fast, R, D, s); }
+        { ProfScope ps(e.prof, "f5.ln_modulate", s); ln_modulate(m.x.p, mod0 + D, mod0, m.n16b.p, fast, R, D, s, m.rowscale.p); }
         qkv_fast(m.layers[0], m.n16b.p);
       }
       for (int l = 0; l < m.depth; ++l) {
@@ -735,6 +753,9 @@ void f5_steps(Engine& e, int first, int count, int precision) {
           c.w_qkv = &m.layers[l + 1].qkv.tc[f16]; c.b_qkv = m.layers[l + 1].qkv.bias.p;
           c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.rowinfo = rowinfo; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
         }
+        c.u_ff1 = L.fu1[f16].p + (size_t)step * m.FF; c.v_ff1 = L.fv1[f16].p + (size_t)step * m.FF;
+        if (!last) { c.u_qkv = m.layers[l + 1].fuq[f16].p + (size_t)step * 3 * D; c.v_qkv = m.layers[l + 1].fvq[f16].p + (size_t)step * 3 * D; }
+        c.rowscale = m.rowscale.p;
         c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
         c.trace = trace_path ? m.chain_trace.p : nullptr;
         ProfScope ps(e.prof, "f5.chain", s);

@@ -25,7 +25,7 @@ __device__ __forceinline__ float warp_max(float v) {
 template <int MODE, typename OutT, int NV>
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                       const float* __restrict__ b, OutT* __restrict__ out, int R, int D,
-                                                      float eps) {
+                                                      float eps, float* __restrict__ rstd_out) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
     sq += dx * dx + dy * dy + dz * dz + dw * dw;
   }
   const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+  if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + i * 32) * 4;
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 }
 
 template <int MODE, typename OutT>
-void launch_rownorm(const float* x, const float* a, const float* b, OutT* out, int R, int D, float eps, cudaStream_t s) {
+void launch_rownorm(const float* x, const float* a, const float* b, OutT* out, int R, int D, float eps, cudaStream_t s, float* rstd_out = nullptr) {
   const dim3 grid(ceil_div(R, 8));
   B2_CHECK(D % 128 == 0, "rownorm: row width must be a multiple of 128");
   switch (D / 128) {
-    case 4: launch_pdl(rownorm_kernel<MODE, OutT, 4>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;     // text embedding (512)
-    case 8: launch_pdl(rownorm_kernel<MODE, OutT, 8>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;     // DiT (1024)
-    case 10: launch_pdl(rownorm_kernel<MODE, OutT, 10>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;   // IndexTTS GPT latent (1280)
-    case 16: launch_pdl(rownorm_kernel<MODE, OutT, 16>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps); break;
+    case 4: launch_pdl(rownorm_kernel<MODE, OutT, 4>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps, rstd_out); break;     // text embedding (512)
+    case 8: launch_pdl(rownorm_kernel<MODE, OutT, 8>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps, rstd_out); break;     // DiT (1024)
+    case 10: launch_pdl(rownorm_kernel<MODE, OutT, 10>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps, rstd_out); break;   // IndexTTS GPT latent (1280)
+    case 16: launch_pdl(rownorm_kernel<MODE, OutT, 16>, grid, dim3(256), 0, s, x, a, b, out, R, D, eps, rstd_out); break;
     default: fail("rownorm: row width must be 512, 1024, 1280 or 2048");
   }
 }
@@ -295,16 +296,62 @@ __global__ void rope_pack_kernel(const float* __restrict__ c, const float* __res
   if (i < n) out[i] = __floats2half2_rn(c[i], sn[i]);
 }
 
+// u[t][j] = sum_k W[j][k] (1 + scale[t][k]),  v[t][j] = sum_k W[j][k] shift[t][k] + bias[j]   for the nfe rows of a modulation
+// table, from the 16-bit weights the tensor cores multiply with (dit_chain.cu: LayerNorm folded into the GEMM). One block per j.
+__global__ void __launch_bounds__(128) fold_vectors_kernel(const uint16_t* __restrict__ w, int ldc, int K, int f16,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift, int mod_ld,
+                                                           const float* __restrict__ bias, float* __restrict__ u, float* __restrict__ v,
+                                                           int N, int nfe) {
+  __shared__ float red[2][4];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  float wk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = tid + i * 128;
+    float x = 0.f;
+    if (k < K) {
+      const uint16_t raw = w[(size_t)j * ldc + k];
+      x = f16 ? __half2float(__ushort_as_half(raw)) : __bfloat162float(__ushort_as_bfloat16(raw));
+    }
+    wk[i] = x;
+  }
+  for (int t = 0; t < nfe; ++t) {
+    float su = 0.f, sv = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = tid + i * 128;
+      if (k < K) {
+        su = fmaf(wk[i], 1.0f + scale[(size_t)t * mod_ld + k], su);
+        sv = fmaf(wk[i], shift[(size_t)t * mod_ld + k], sv);
+      }
+    }
+    su = warp_sum(su); sv = warp_sum(sv);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = su; red[1][tid >> 5] = sv; }
+    __syncthreads();
+    if (tid == 0) {
+      u[(size_t)t * N + j] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+      v[(size_t)t * N + j] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]) + bias[j];
+    }
+    __syncthreads();
+  }
+}
+
 inline dim3 g1(long n, int bs = 256) { return dim3(ceil_div(n, bs)); }
 
 }  // namespace
 
 #define LAUNCHED() do { B2_LAUNCH_CHECK(); count_launch(); } while (0)
 
-void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s) {
-  if (out_bf16 == 2) launch_rownorm<0, __half>(x, scale, shift, (__half*)out, R, D, 1e-6f, s);
-  else if (out_bf16) launch_rownorm<0, __nv_bfloat16>(x, scale, shift, (__nv_bfloat16*)out, R, D, 1e-6f, s);
-  else launch_rownorm<0, float>(x, scale, shift, (float*)out, R, D, 1e-6f, s);
+void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s, float* rstd_out) {
+  if (out_bf16 == 2) launch_rownorm<0, __half>(x, scale, shift, (__half*)out, R, D, 1e-6f, s, rstd_out);
+  else if (out_bf16) launch_rownorm<0, __nv_bfloat16>(x, scale, shift, (__nv_bfloat16*)out, R, D, 1e-6f, s, rstd_out);
+  else launch_rownorm<0, float>(x, scale, shift, (float*)out, R, D, 1e-6f, s, rstd_out);
+  LAUNCHED();
+}
+void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, const float* shift, int mod_ld, const float* bias, float* u,
+                  float* v, int N, int nfe, cudaStream_t s) {
+  B2_CHECK(K <= 1024, "fold_vectors: K <= 1024");
+  fold_vectors_kernel<<<N, 128, 0, s>>>(reinterpret_cast<const uint16_t*>(w16), ldc, K, f16, scale, shift, mod_ld, bias, u, v, N, nfe);
   LAUNCHED();
 }
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s) {

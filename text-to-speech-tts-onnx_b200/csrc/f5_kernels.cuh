@@ -9,7 +9,12 @@ namespace b200tts {
 
 // out = LayerNorm(x; no affine, eps 1e-6) * (1 + scale) + shift   (F5 modules.py:301-305,321-325,609)
 // x [R][D] fp32; scale, shift [D]; out fp32 (out_bf16 = 0), bf16 (1) or fp16 (2) with row stride D.
-void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s);
+void ln_modulate(const float* x, const float* scale, const float* shift, void* out, int out_bf16, int R, int D, cudaStream_t s,
+                 float* rstd_out = nullptr /* optional [R]: 1 / std of every row */);
+// u[t][j] = sum_k W16[j][k] (1 + scale[t][k]), v[t][j] = sum_k W16[j][k] shift[t][k] + bias[j], t < nfe (rows of a modulation table
+// with row stride mod_ld); W16 = the [N][ldc] 16-bit tensor-core weight (K <= 1024 columns used)
+void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, const float* shift, int mod_ld, const float* bias, float* u,
+                  float* v, int N, int nfe, cudaStream_t s);
 // nn.LayerNorm(D, eps) with affine (text ConvNeXtV2 block, modules.py:248)
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s);
 void layernorm_affine_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* out, int R, int D, float eps, cudaStream_t s);

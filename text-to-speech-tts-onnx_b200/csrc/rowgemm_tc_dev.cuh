@@ -327,13 +327,24 @@ __device__ __forceinline__ void epi_tma_drain(int lane) {
 // null). TK_RES_F32: out = res + gate * (acc + bias) as fp32 (the residual tile of the FIRST block must already be in flight:
 // epi_tma_fetch_res); TK_ACT16: out = act(acc + bias) as 16 bit; TK_ROPE16: q | k columns roped as 16 bit, V columns through
 // the transposed scalar path of epilogue_warp.
-template <int TK, int ACT, bool STATS>
+// AFFINE (the LayerNorm folded into the GEMM, dit_chain.cu): the A operand held c * x * (1 + scale) instead of the normalised
+// rows, so  LN(x)(1 + scale) + shift) W^T + b  =  rho * acc - rmu * u[col] + v[col]  with rho = rstd / c, rmu = rstd * mean and
+// the per-column vectors u = W (1 + scale), v = W shift + b passed in place of gate / bias (s_gate = u, s_bias = v).
+// EpiEmit (TK_RES_F32 only): besides the fp32 result x, write c * x * mul[col] as 16 bit straight to global memory (a lane
+// owns 64 contiguous bytes of its row) -- the A operand of the NEXT GEMM, produced without a second pass over x.
+struct EpiEmit {
+  uint16_t* row = nullptr;     // this lane's row of the 16-bit tensor (null: row out of range / nothing to emit)
+  const float* s_mul = nullptr;   // shared-memory copy of (1 + scale)[n0 ..)
+  float c = 1.0f;              // the row's scale (a stale 1 / std estimate: keeps fp16 in range)
+};
+template <int TK, int ACT, bool STATS, bool AFFINE = false>
 __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
                                                   uint32_t taddr, int row0, int n0, int cb_first, int cb_step, int lane,
                                                   const float* s_bias, const float* s_gate, float& rsum, float& rsq,
                                                   uint64_t store_policy = 0ull /* L2 cache hint of the result tiles, 0 = none */,
                                                   float* stat_slots = nullptr /* STATS: [group][parity][128 rows] float2 in smem */,
-                                                  int stat_col0 = 0 /* first column of the caller's slice */, int stat_row = 0) {
+                                                  int stat_col0 = 0 /* first column of the caller's slice */, int stat_row = 0,
+                                                  float rho = 1.0f, float rmu = 0.0f, EpiEmit emit = EpiEmit()) {
   const uint32_t out_s = smem_u32(et.out_tile), res_s = smem_u32(et.res_tile);
   const uint32_t bias_s = smem_u32(s_bias), gate_s = s_gate ? smem_u32(s_gate) : 0u;
   const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
@@ -365,13 +376,19 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
       if (t < a.M) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
+          float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
+          float w0 = __uint_as_float(v[k * 4 + 0]), w1 = __uint_as_float(v[k * 4 + 1]), w2 = __uint_as_float(v[k * 4 + 2]), w3 = __uint_as_float(v[k * 4 + 3]);
+          if (AFFINE) {
+            const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
+            bi.x = fmaf(-rmu, u.x, bi.x); bi.y = fmaf(-rmu, u.y, bi.y); bi.z = fmaf(-rmu, u.z, bi.z); bi.w = fmaf(-rmu, u.w, bi.w);
+            w0 *= rho; w1 *= rho; w2 *= rho; w3 *= rho;
+          }
           const int cv = n + k * 4 - a.vt_col0;
           uint16_t* o16 = reinterpret_cast<uint16_t*>(a.vt_out) + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
-          o16[0] = pack16(__uint_as_float(v[k * 4 + 0]) + bi.x, a.f16);
-          o16[(long)a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 1]) + bi.y, a.f16);
-          o16[2L * a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 2]) + bi.z, a.f16);
-          o16[3L * a.vt_ld] = pack16(__uint_as_float(v[k * 4 + 3]) + bi.w, a.f16);
+          o16[0] = pack16(w0 + bi.x, a.f16);
+          o16[(long)a.vt_ld] = pack16(w1 + bi.y, a.f16);
+          o16[2L * a.vt_ld] = pack16(w2 + bi.z, a.f16);
+          o16[3L * a.vt_ld] = pack16(w3 + bi.w, a.f16);
         }
       }
       continue;
@@ -381,8 +398,16 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
-      f[k * 4 + 0] = __uint_as_float(v[k * 4 + 0]) + bi.x; f[k * 4 + 1] = __uint_as_float(v[k * 4 + 1]) + bi.y;
-      f[k * 4 + 2] = __uint_as_float(v[k * 4 + 2]) + bi.z; f[k * 4 + 3] = __uint_as_float(v[k * 4 + 3]) + bi.w;
+      if (AFFINE) {
+        const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
+        f[k * 4 + 0] = fmaf(rho, __uint_as_float(v[k * 4 + 0]), fmaf(-rmu, u.x, bi.x));
+        f[k * 4 + 1] = fmaf(rho, __uint_as_float(v[k * 4 + 1]), fmaf(-rmu, u.y, bi.y));
+        f[k * 4 + 2] = fmaf(rho, __uint_as_float(v[k * 4 + 2]), fmaf(-rmu, u.z, bi.z));
+        f[k * 4 + 3] = fmaf(rho, __uint_as_float(v[k * 4 + 3]), fmaf(-rmu, u.w, bi.w));
+      } else {
+        f[k * 4 + 0] = __uint_as_float(v[k * 4 + 0]) + bi.x; f[k * 4 + 1] = __uint_as_float(v[k * 4 + 1]) + bi.y;
+        f[k * 4 + 2] = __uint_as_float(v[k * 4 + 2]) + bi.z; f[k * 4 + 3] = __uint_as_float(v[k * 4 + 3]) + bi.w;
+      }
     }
     if (TK == TK_ACT16 && ACT != ACT_NONE) {
 #pragma unroll
@@ -429,6 +454,23 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
         float2* slot = reinterpret_cast<float2*>(stat_slots) + (size_t)(((n - stat_col0) >> 7) * 2 + ((cb >> 5) & 1)) * 128 + stat_row;
         *slot = make_float2(rsum, rsq);
         rsum = 0.f; rsq = 0.f;
+      }
+    }
+    if (TK == TK_RES_F32 && emit.row != nullptr) {
+      const uint32_t mul_s = smem_u32(emit.s_mul);
+      const float lim = a.f16 ? 65504.0f : 3.0e38f;            // saturate instead of overflowing to inf (fp16 operands)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 m0 = lds128(mul_s + (uint32_t)(cb + k * 8) * 4u), m1 = lds128(mul_s + (uint32_t)(cb + k * 8 + 4) * 4u);
+        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float y0 = fminf(fmaxf(__fmul_rn(__fmul_rn(emit.c, f[k * 8 + 2 * i]), mm[2 * i]), -lim), lim);
+          const float y1 = fminf(fmaxf(__fmul_rn(__fmul_rn(emit.c, f[k * 8 + 2 * i + 1]), mm[2 * i + 1]), -lim), lim);
+          w[i] = pack16x2(y0, y1, a.f16);
+        }
+        *reinterpret_cast<uint4*>(emit.row + n + k * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     if (lane == 0) bulk_wait_read0();                          // the previous block's store has read the staging tile
