@@ -30,7 +30,22 @@ Engine::~Engine() {
   if (ivgan) bigvgan_free(ivgan);
   if (f5) f5_free(f5);
   if (igpt) gpt_free(igpt);
+  for (int i = 0; i < 2; ++i) {
+    if (aux_stream[i]) cudaStreamDestroy(aux_stream[i]);
+    if (ev_acc[i]) cudaEventDestroy(ev_acc[i]);
+    if (ev_end[i]) cudaEventDestroy(ev_end[i]);
+  }
+  if (ev_fork) cudaEventDestroy(ev_fork);
   if (own_stream && stream) cudaStreamDestroy(stream);
+}
+void Engine::ensure_aux() {
+  if (aux_stream[0]) return;
+  for (int i = 0; i < 2; ++i) {
+    B2_CUDA(cudaStreamCreateWithFlags(&aux_stream[i], cudaStreamNonBlocking));
+    B2_CUDA(cudaEventCreateWithFlags(&ev_acc[i], cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&ev_end[i], cudaEventDisableTiming));
+  }
+  B2_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
 }
 }  // namespace b200tts
 
@@ -131,7 +146,8 @@ int b200tts_set_option(b200tts_engine* e, const char* name, int value) {
     const std::string n(name);
     if (n == "dit_chain") E.dit_chain = value != 0;
     else if (n == "cuda_graphs") E.graphs.enabled = value != 0;
-    else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs)");
+    else if (n == "bigvgan_branches") E.bigvgan_branches = value != 0;
+    else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs, bigvgan_branches)");
     E.graphs.clear();                                    // captured graphs bake the code path in
   });
 }

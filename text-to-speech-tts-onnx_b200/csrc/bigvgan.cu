@@ -138,8 +138,9 @@ struct BigVGANModel {
   DevBuf<float> post_w;             // [7][Clast]
   int Clast = 0;
   // workspaces (grow-only)
-  DevBuf<float> mel_cl, xu, xs, xa, xb, abuf, cbuf;
-  DevBuf<__nv_bfloat16> abuf16, cbuf16, mel16, xs16;
+  DevBuf<float> mel_cl, xu, xs, abuf, cbuf;
+  DevBuf<float> xa[3], xb[3];                      // per resblock branch (the three branches of a stage run concurrently)
+  DevBuf<__nv_bfloat16> abuf16[3], cbuf16[3], mel16, xs16;
 };
 
 namespace {
@@ -313,6 +314,7 @@ struct Ctx {
   bool fast;
   int f16;      // fast path operand type: 0 = bf16, 1 = fp16
   int t16;      // its type code as an output (rowgemm.cuh out_bf16 / aa_snake): 1 = bf16, 2 = fp16
+  cudaStream_t s;   // the stream this (branch of the) forward pass enqueues on
 };
 
 // y = conv(x) with the shifted-row GEMM; x, out are (B, L, C) fp32 (or bf16 for the tc path's A operand)
@@ -327,12 +329,12 @@ void run_conv(Ctx& c, const char* tag, const ConvW& cw, const void* x, int L, in
   p.out = out; p.o_bstride = (long)L * cw.N; p.ldo = cw.N; p.out_bf16 = out_bf16;
   p.bias = bias ? bias : cw.bias.p; p.res = res; p.accumulate = accumulate; p.scale = scale; p.out2 = c.fast ? out2 : nullptr;
   p.f16 = c.f16;
-  ProfScope ps(c.e.prof, tag, c.e.stream);
+  ProfScope ps(c.e.prof, tag, c.s);
   if (c.fast) {
-    rowgemm_tc(p, cw.tc[c.f16], c.e.stream);
+    rowgemm_tc(p, cw.tc[c.f16], c.s);
   } else {
     p.w = cw.w.p; p.ldw = cw.N;
-    rowgemm_f32(p, c.e.stream);
+    rowgemm_f32(p, c.s);
   }
 }
 
@@ -350,12 +352,12 @@ void run_up(Ctx& c, const Stage& st, const void* x, int Lin, float* out, const f
   }
   p.bias = bias;
   p.f16 = c.f16;
-  ProfScope ps(c.e.prof, "bigvgan.ups", c.e.stream);
+  ProfScope ps(c.e.prof, "bigvgan.ups", c.s);
   if (c.fast) {
-    rowgemm_tc(p, st.up.tc[c.f16], c.e.stream);
+    rowgemm_tc(p, st.up.tc[c.f16], c.s);
   } else {
     p.w = st.up.w.p; p.ldw = (int)N;
-    rowgemm_f32(p, c.e.stream);
+    rowgemm_f32(p, c.s);
   }
 }
 
@@ -369,8 +371,11 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
   B2_CHECK(!latent_in || B == 1, "the IndexTTS vocoder takes one latent sequence per call");
   B2_CHECK(latent_in == (d_conds != nullptr), "conditioning vectors go with the IndexTTS vocoder only");
   B2_CHECK(!latent_in || cl_bstride == 0, "the channels-last mel input belongs to the mel vocoder");
-  Ctx c{e, m, B, precision != PREC_F32, precision == PREC_F16 ? 1 : 0, precision == PREC_F16 ? 2 : 1};
   cudaStream_t s = e.stream;
+  Ctx c{e, m, B, precision != PREC_F32, precision == PREC_F16 ? 1 : 0, precision == PREC_F16 ? 2 : 1, s};
+  // concurrent resblock branches: tensor-core engines only (the fp32 parity engine stays strictly serial)
+  const bool par = c.fast && e.bigvgan_branches;
+  if (par) e.ensure_aux();
 
   // workspace: every stage tensor has C*L <= C0*hop/… ; the largest is max_i(C_i * L_i), the post tensor adds 30 rows
   long maxel = (long)m.C0 * T;
@@ -381,9 +386,11 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
   }
   const size_t ws = (size_t)maxel * B;
   m.mel_cl.reserve((size_t)B * T * m.n_mels);
-  m.xu.reserve(ws); m.xs.reserve(ws); m.xa.reserve(ws); m.xb.reserve(ws); m.abuf.reserve(ws);
+  m.xu.reserve(ws); m.xs.reserve(ws); m.abuf.reserve(ws);
+  for (int j = 0; j < (par ? 3 : 1); ++j) { m.xa[j].reserve(ws); m.xb[j].reserve(ws); }
   if (c.fast) {
-    m.abuf16.reserve(ws); m.cbuf16.reserve(ws); m.mel16.reserve((size_t)B * T * round_up(m.n_mels, 8)); m.xs16.reserve(ws);
+    for (int j = 0; j < (par ? 3 : 1); ++j) { m.abuf16[j].reserve(ws); m.cbuf16[j].reserve(ws); }
+    m.mel16.reserve((size_t)B * T * round_up(m.n_mels, 8)); m.xs16.reserve(ws);
     bigvgan_tc_prepare(e, m, c.f16);  // 16-bit weight layouts (first fast call of each operand type only)
   } else {
     m.cbuf.reserve(ws);
@@ -437,32 +444,52 @@ void bigvgan_forward(Engine& e, BigVGANModel& m, const float* d_in, int B, int T
     const void* up_in = c.fast ? (const void*)m.xs16.p : (const void*)m.xs.p;
     run_up(c, st, up_in, L, m.xu.p, latent_in ? st.up_bias_c.p : st.up.bias.p);
     L *= st.u;
+    // fork: the three resblocks read the same stage input xu. Branch j enqueues on its own stream and owns its scratch tensors;
+    // the branches meet again in xs, which they update in the reference's order ((b0 + b1) + b2) / 3: the last convolution of
+    // branch j waits for that of branch j - 1 (an event), so the sum is bit-identical to the serial schedule.
+    if (par) {
+      B2_CUDA(cudaEventRecord(e.ev_fork, s));
+      for (int a = 0; a < 2; ++a) B2_CUDA(cudaStreamWaitEvent(e.aux_stream[a], e.ev_fork, 0));
+    }
     for (int j = 0; j < 3; ++j) {
+      Ctx cj = c;
+      cj.s = par && j > 0 ? e.aux_stream[j - 1] : s;
+      const int bj = par ? j : 0;
+      __nv_bfloat16* a16 = m.abuf16[bj].p;
+      __nv_bfloat16* c16 = m.cbuf16[bj].p;
       const float* xcur = m.xu.p;
       for (int mm = 0; mm < 3; ++mm) {
         const bool last = (mm == 2);
         {
-          ProfScope ps(e.prof, atag, s);
-          if (c.fast) aa_snake(xcur, 0, m.abuf16.p, c.t16, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, false, false, s);
-          else aa_snake(xcur, 0, m.abuf.p, 0, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, true, false, s);
+          ProfScope ps(e.prof, atag, cj.s);
+          if (c.fast) aa_snake(xcur, 0, a16, c.t16, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, false, false, cj.s);
+          else aa_snake(xcur, 0, m.abuf.p, 0, st.act[j][2 * mm].alpha.p, st.act[j][2 * mm].inv_beta.p, B, st.C, L, true, false, cj.s);
         }
-        if (c.fast) run_conv(c, ctag, st.c1[j][mm], m.abuf16.p, L, st.dil[j][mm], m.cbuf16.p, c.t16, nullptr, 0, 1.0f);
-        else run_conv(c, ctag, st.c1[j][mm], m.abuf.p, L, st.dil[j][mm], m.cbuf.p, 0, nullptr, 0, 1.0f);
+        if (c.fast) run_conv(cj, ctag, st.c1[j][mm], a16, L, st.dil[j][mm], c16, c.t16, nullptr, 0, 1.0f);
+        else run_conv(cj, ctag, st.c1[j][mm], m.abuf.p, L, st.dil[j][mm], m.cbuf.p, 0, nullptr, 0, 1.0f);
         {
-          ProfScope ps(e.prof, atag, s);
-          if (c.fast) aa_snake(m.cbuf16.p, c.t16, m.abuf16.p, c.t16, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, false, false, s);
-          else aa_snake(m.cbuf.p, 0, m.abuf.p, 0, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, true, false, s);
+          ProfScope ps(e.prof, atag, cj.s);
+          if (c.fast) aa_snake(c16, c.t16, a16, c.t16, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, false, false, cj.s);
+          else aa_snake(m.cbuf.p, 0, m.abuf.p, 0, st.act[j][2 * mm + 1].alpha.p, st.act[j][2 * mm + 1].inv_beta.p, B, st.C, L, true, false, cj.s);
         }
-        const void* a2 = c.fast ? (const void*)m.abuf16.p : (const void*)m.abuf.p;
+        const void* a2 = c.fast ? (const void*)a16 : (const void*)m.abuf.p;
         if (!last) {
-          float* xnext = (mm == 0) ? m.xa.p : m.xb.p;
-          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, xnext, 0, xcur, 0, 1.0f);   // x = xt + x
+          float* xnext = (mm == 0) ? m.xa[bj].p : m.xb[bj].p;
+          run_conv(cj, ctag, st.c2[j][mm], a2, L, 1, xnext, 0, xcur, 0, 1.0f);   // x = xt + x
           xcur = xnext;
         } else {
           // xs (+)= conv + x ; the MRF mean (x 1/3, bigvgan.py:399) is folded into the third block's epilogue
-          run_conv(c, ctag, st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f, 0, nullptr,
+          if (par && j > 0) B2_CUDA(cudaStreamWaitEvent(cj.s, e.ev_acc[j - 1], 0));
+          run_conv(cj, ctag, st.c2[j][mm], a2, L, 1, m.xs.p, 0, xcur, j > 0 ? 1 : 0, j == 2 ? (float)(1.0 / 3.0) : 1.0f, 0, nullptr,
                    j == 2 ? m.xs16.p : nullptr);
+          if (par && j < 2) B2_CUDA(cudaEventRecord(e.ev_acc[j], cj.s));
         }
+      }
+    }
+    if (par) {      // join: the next stage (and the post-processing) continues on the caller's stream
+      for (int a = 0; a < 2; ++a) {
+        B2_CUDA(cudaEventRecord(e.ev_end[a], e.aux_stream[a]));
+        B2_CUDA(cudaStreamWaitEvent(s, e.ev_end[a], 0));
       }
     }
   }

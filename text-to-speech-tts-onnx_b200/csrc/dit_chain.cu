@@ -135,6 +135,14 @@ __device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int
   return s;
 }
 
+// First output column of sub-tile `st` of pair `slice`. Jobs 0-2: the pair's columns are contiguous (the LayerNorm partials are
+// grouped per slice). Job 3 (q|k|v): sub-tiles are dealt round-robin over the team and walked from the last column down, so that
+// every pair meets its V columns FIRST: their transposing epilogue (2-byte stores, ~2x the time of a q / k tile) then runs under
+// the next sub-tile's main loop, and the exposed last epilogue of the launch is a q / k one (chain timeline, profiles/r02).
+__device__ __forceinline__ int subtile_col0(int j, int st, int slice, int team, const JobShape& js) {
+  return j == 3 ? ((js.nsubt - 1 - st) * team + slice) * js.w : slice * js.n_pair + st * js.w;
+}
+
 // This CTA's LayerNorm partials (left in shared memory by the row-layout epilogue: st[group][parity][row] = (sum, sum of
 // squares), one group per 128 output columns of the CTA's slice) -> the row block's global slots. Global slot = the group's
 // index among the 8 groups of a row (D = 1024): the same 8 numbers whatever the team size, reduced in the same order by every
@@ -324,7 +332,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           const CUtensorMap* map = j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3;
           const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
           for (int st = 0; st < js.nsubt; ++st) {
-            const int n_row0 = slice * js.n_pair + st * js.w + (int)rank * js.b_rows;
+            const int n_row0 = subtile_col0(j, st, slice, c.team, js) + (int)rank * js.b_rows;
             for (int ck = 0; ck < js.K / BK; ++ck) {
               mbar_wait(&b_empty[sb], pb ^ 1);
               if (leader) mbar_expect_tx(&b_full[sb], tx);
@@ -449,7 +457,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         float rsum = 0.f, rsq = 0.f;
         for (int st = 0; st < js.nsubt; ++st, ++t) {
           const uint32_t buf = t & 1u;
-          const int n0 = slice * js.n_pair + st * js.w;
+          const int n0 = subtile_col0(j, st, slice, c.team, js);
           const uint32_t taddr = tmem_base + buf * 256u + lane_sel;
           stage_vec(bias, gate, scale, n0, js.w);
           if (j == 0 || j == 2) epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);

@@ -100,6 +100,13 @@ struct Engine {
   F5Model* f5 = nullptr;
   GptModel* igpt = nullptr;                // IndexTTS GPT-2 acoustic model (gpt2.cuh)
   bool dit_chain = true;                   // F5 DiT blocks through the fused row-block chain kernel (dit_chain.cu); b200tts_set_option
+  // BigVGAN: the three resblocks of a stage (kernel sizes 3 / 7 / 11, bigvgan.py:396-399) are independent until their sum, so
+  // they run as three concurrent branches (this stream + two auxiliary ones, forked / joined with events; inside a captured
+  // graph these become parallel branches). b200tts_set_option("bigvgan_branches", 0) serialises them again.
+  bool bigvgan_branches = true;
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_acc[2] = {nullptr, nullptr}, ev_end[2] = {nullptr, nullptr};
+  void ensure_aux();                       // creates the auxiliary streams / events (outside any capture)
 
   const Tensor& weight(const std::string& name) const {
     auto it = weights.find(name);

@@ -687,7 +687,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
     rowgemm_tc(p, L.qkv.tc[f16], s);
   };
   const size_t flag_words = dit_chain_flag_words(R);
-  // debug: B200TTS_CHAIN_TRACE=<file> (with B200TTS_GRAPHS=0) dumps the %globaltimer stamps of the LAST chain launch, [CTA][64] u64
+  // debug: B200TTS_CHAIN_TRACE=<file> (with B200TTS_GRAPHS=0) dumps the %globaltimer stamps of the last-but-one block's chain launch, [CTA][64] u64
   const char* trace_path = chain ? getenv("B200TTS_CHAIN_TRACE") : nullptr;
   if (trace_path) { m.chain_trace.reserve((size_t)512 * 64); B2_CUDA(cudaMemsetAsync(m.chain_trace.p, 0, (size_t)512 * 64 * 8, s)); }
   for (int step = first; step < first + count; ++step) {
@@ -757,7 +757,7 @@ void f5_steps(Engine& e, int first, int count, int precision) {
         if (!last) { c.u_qkv = m.layers[l + 1].fuq[f16].p + (size_t)step * 3 * D; c.v_qkv = m.layers[l + 1].fvq[f16].p + (size_t)step * 3 * D; }
         c.rowscale = m.rowscale.p;
         c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
-        c.trace = trace_path ? m.chain_trace.p : nullptr;
+        c.trace = trace_path && l == m.depth - 2 ? m.chain_trace.p : nullptr;      // a typical block (the last one has no q|k|v job)
         ProfScope ps(e.prof, "f5.chain", s);
         dit_chain(c, s);
       }

@@ -179,6 +179,37 @@ def sec_bigvgan():
         eng.set_stream(0)
 
 
+def sec_bvg_branches():
+    """BigVGAN with the three resblock branches of a stage serial (0) or concurrent (1): outputs must be bit-identical; time per step
+    for the configs[1] batch (8, 100, 512) and for one config-3 utterance's generated mel (1, 100, 563)."""
+    import torch
+    eng = capi.Engine(0)
+    eng.load_state("bigvgan", weights.bigvgan_engine_tensors(synth.bigvgan_state(1234)))
+    eng.bigvgan_build()
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    res = {}
+    for B, T in ((8, 512), (1, 563)):
+        mel = synth.bigvgan_mel(100, B, T)
+        md = torch.from_numpy(mel).cuda()
+        for br in (0, 1):
+            eng.set_option("bigvgan_branches", br)
+            pd = torch.zeros((B, 1, config.BIGVGAN.out_samples(T)), dtype=torch.int16, device="cuda")
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    eng.bigvgan_run_device(md.data_ptr(), B, T, pd.data_ptr(), precision=capi.F16)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    eng.bigvgan_run_device(md.data_ptr(), B, T, pd.data_ptr(), precision=capi.F16)
+                e1.record(stream)
+                torch.cuda.synchronize()
+            res[(B, T, br)] = pd.cpu().numpy().copy()
+            out(section="bvg_branches", B=B, T=T, branches=br, ms_per_step=e0.elapsed_time(e1) / 10)
+        out(section="bvg_branches", B=B, T=T, bit_identical=bool(np.array_equal(res[(B, T, 0)], res[(B, T, 1)])))
+
+
 def sec_attn_time():
     """fp16, fused chain: time per call and the event-timed share of attention / chain, one and eight config-3 utterances."""
     import torch
