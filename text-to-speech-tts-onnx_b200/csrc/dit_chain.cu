@@ -71,6 +71,8 @@ struct ChainArgs {
   // LayerNorm folded into the GEMMs (see the header): per-column vectors of this (block, Euler step) and the per-row scale
   const float *u_ff1, *v_ff1, *u_qkv, *v_qkv;
   float* rowscale;
+  int fp8;                                           // ff1 and q|k|v run with e4m3 operands (A emitted as e4m3, weights pre-quantised)
+  const float *sw_ff1, *sw_qkv;                      // per-output-channel scales of the e4m3 weights
   float* stats;
   unsigned* flags;
   unsigned long long* trace;      // optional [CTA][64] globaltimer stamps (B200TTS_CHAIN_TRACE, tools/chain_trace.py)
@@ -123,10 +125,14 @@ __device__ __forceinline__ void team_signal(unsigned* flag, int tid) {
 
 // Job j of the chain for a team of `team` pairs: the pair's n_pair output columns are walked in nsubt sub-tiles of w columns
 // (one M = 256, N = w accumulator each; b_rows = w / 2 weight rows per CTA and 64-channel chunk).
-struct JobShape { int K, N, n_pair, w, nsubt, b_rows; };
-__device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int team) {
+constexpr float CH_FP8_GAIN = 8.0f;                  // extra scale of an e4m3 A operand: centres N(0, 1)-like rows in the e4m3 range
+struct JobShape { int K, N, n_pair, w, nsubt, b_rows, chunks, kstep, fp8; };
+__device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int team, int fp8 = 0) {
   JobShape s;
   s.K = j == 2 ? FF : D;
+  s.fp8 = fp8 && (j == 1 || j == 3) ? 1 : 0;
+  s.kstep = s.fp8 ? 128 : BK;                       // operand elements per 128-byte swizzle row = per pipeline chunk
+  s.chunks = s.K / s.kstep;
   s.N = j == 0 ? D : j == 1 ? FF : j == 2 ? D : 3 * D;
   s.n_pair = s.N / team;
   s.w = s.n_pair <= 256 ? s.n_pair : (s.n_pair % 256 == 0 ? 256 : 192);
@@ -304,7 +310,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         const int row0 = rb * CH_ROWS + (int)rank * 128;
         const unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team);
+          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
           stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
@@ -313,10 +319,10 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           }
           stamp(c, 8 + 8 * j + 1);
           for (int st = 0; st < js.nsubt; ++st)
-            for (int ck = 0; ck < js.K / BK; ++ck) {
+            for (int ck = 0; ck < js.chunks; ++ck) {
               mbar_wait(&a_empty[sa], pa ^ 1);
               if (leader) mbar_expect_tx(&a_full[sa], 2u * CH_A_BYTES);
-              tma_load_3d_2sm(smem_a + sa * CH_A_BYTES, map, &a_full[sa], ck * BK, row0, 0);
+              tma_load_3d_2sm(smem_a + sa * CH_A_BYTES, map, &a_full[sa], ck * js.kstep, row0, 0);
               if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
             }
         }
@@ -328,15 +334,15 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       int sb = 0; uint32_t pb = 0;
       for (int rb = team; rb < c.nrb; rb += c.teams) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team);
+          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
           const CUtensorMap* map = j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3;
           const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
           for (int st = 0; st < js.nsubt; ++st) {
             const int n_row0 = subtile_col0(j, st, slice, c.team, js) + (int)rank * js.b_rows;
-            for (int ck = 0; ck < js.K / BK; ++ck) {
+            for (int ck = 0; ck < js.chunks; ++ck) {
               mbar_wait(&b_empty[sb], pb ^ 1);
               if (leader) mbar_expect_tx(&b_full[sb], tx);
-              tma_load_3d_2sm(smem_b + sb * CH_B_BYTES, map, &b_full[sb], ck * BK, n_row0, 0);
+              tma_load_3d_2sm(smem_b + sb * CH_B_BYTES, map, &b_full[sb], ck * js.kstep, n_row0, 0);
               if (++sb == CH_B_STAGES) { sb = 0; pb ^= 1; }
             }
           }
@@ -352,9 +358,9 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       uint32_t t = 0;
       for (int rb = team; rb < c.nrb; rb += c.teams) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team);
-          const uint32_t idesc = idesc_f16kind(256, js.w, c.f16);
-          const int chunks = js.K / BK;
+          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
+          const uint32_t idesc = idesc_f16kind(256, js.w, js.fp8 ? 1 : c.f16);      // e4m3 shares format code 0 with fp16
+          const int chunks = js.chunks;
           for (int st = 0; st < js.nsubt; ++st, ++t) {
             const uint32_t buf = t & 1u;
             mbar_wait(&acc_empty[buf], ((t >> 1) & 1u) ^ 1u);
@@ -369,10 +375,17 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
               const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
               const uint32_t accum = ck > 0 ? 1u : 0u;
               if (elect_one()) {
-                umma2_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
-                umma2_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
-                umma2_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
-                umma2_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
+                if (js.fp8) {
+                  umma2_f8_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
+                  umma2_f8_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
+                  umma2_f8_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
+                  umma2_f8_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
+                } else {
+                  umma2_bf16_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
+                  umma2_bf16_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
+                  umma2_bf16_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
+                  umma2_bf16_lohi(d0, a_lo + 6, b_lo + 6, idesc, 1u);
+                }
                 umma2_commit_mc(&b_empty[sb]);
                 umma2_commit_mc(&a_empty[sa]);
                 if (ck == chunks - 1) { umma2_commit_mc(&acc_full[buf]); if (st == js.nsubt - 1) stamp(c, 8 + 8 * j + 3); }
@@ -400,12 +413,13 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     float* s_gate = smem_vec + 256;
     float* s_mul = smem_vec + 512;
     // bias (or v) / gate (or u) / 1 + scale of the sub-tile's columns -> shared memory (broadcast reads in the epilogue)
-    auto stage_vec = [&](const float* bias, const float* gate, const float* scale, int n0, int n) {
+    auto stage_vec = [&](const float* bias, const float* gate, const float* scale, const float* wscale, int n0, int n) {
       epi_bar();                                               // the previous sub-tile's readers are done
       if (tid < n) {
         s_bias[tid] = __ldg(bias + n0 + tid);
         if (gate) s_gate[tid] = __ldg(gate + n0 + tid);
         if (scale) s_mul[tid] = __fadd_rn(1.0f, __ldg(scale + n0 + tid));
+        if (wscale) s_mul[tid] = __ldg(wscale + n0 + tid);     // (a job has one or the other)
       }
       epi_bar();
     };
@@ -427,8 +441,10 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       float c_row = myrow < c.R ? __ldcg(c.rowscale + myrow) : 1.0f;
       float rho = 1.0f, rmu = 0.0f;
       for (int j = 0; j < njobs; ++j) {
-        const JobShape js = job_shape(j, c.D, c.FF, c.team);
-        a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.K / BK;
+        const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
+        a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.chunks;
+        const float* wscale = !js.fp8 ? nullptr : j == 1 ? c.sw_ff1 : c.sw_qkv;
+        const bool next_fp8 = c.fp8 && (j == 0 || j == 2);      // the operand this job emits feeds an e4m3 GEMM
         const bool fold = j == 0 || (j == 2 && c.has_qkv);      // this job's epilogue emits the next GEMM's A operand
         const float* bias = j == 0 ? c.b_out : j == 1 ? c.v_ff1 : j == 2 ? c.b_ff2 : c.v_qkv;
         const float* gate = j == 0 ? c.gate_msa : j == 1 ? c.u_ff1 : j == 2 ? c.gate_mlp : c.u_qkv;
@@ -444,22 +460,25 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           if (tid == 0) wait_counter(flags + (j == 1 ? F_N16 : F_N16B), team_ctas);
           epi_bar();
           const float2 ms = row_mean_rstd(c, rb, (int)rank, j == 1 ? 0 : 1, q * 32 + lane);
-          rho = __fdiv_rn(ms.y, c_row);
+          rho = __fdiv_rn(ms.y, js.fp8 ? c_row * CH_FP8_GAIN : c_row);
           rmu = __fmul_rn(ms.y, ms.x);
           c_row = ms.y;                                         // the scale of the NEXT emitted operand
           if (j == 3 && slice == 0 && e == 0 && myrow < c.R) c.rowscale[myrow] = ms.y;     // for the next block's launch
         }
         EpiEmit emit;
         if (fold) {
-          emit.row = myrow < c.R ? reinterpret_cast<uint16_t*>(j == 0 ? c.n16 : c.n16b) + (size_t)myrow * c.D : nullptr;
-          emit.s_mul = s_mul; emit.c = c_row;
+          if (next_fp8) emit.row8 = myrow < c.R ? reinterpret_cast<uint8_t*>(j == 0 ? c.n16 : c.n16b) + (size_t)myrow * c.D : nullptr;
+          else emit.row = myrow < c.R ? reinterpret_cast<uint16_t*>(j == 0 ? c.n16 : c.n16b) + (size_t)myrow * c.D : nullptr;
+          emit.s_mul = s_mul; emit.c = next_fp8 ? c_row * CH_FP8_GAIN : c_row;
+        } else if (wscale) {
+          emit.s_mul = s_mul;                                    // AFFINE epilogue: the e4m3 weights' per-column scales
         }
         float rsum = 0.f, rsq = 0.f;
         for (int st = 0; st < js.nsubt; ++st, ++t) {
           const uint32_t buf = t & 1u;
           const int n0 = subtile_col0(j, st, slice, c.team, js);
           const uint32_t taddr = tmem_base + buf * 256u + lane_sel;
-          stage_vec(bias, gate, scale, n0, js.w);
+          stage_vec(bias, gate, scale, wscale, n0, js.w);
           if (j == 0 || j == 2) epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
           mbar_wait(&acc_full[buf], (t >> 1) & 1u);
           tc_fence_after();
@@ -469,10 +488,10 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
                                                           smem_stat, slice * js.n_pair, q * 32 + lane, 1.0f, 0.0f, emit);
           else if (j == 1)
             epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
-                                                                    0ull, nullptr, 0, 0, rho, rmu);
+                                                                    0ull, nullptr, 0, 0, rho, rmu, emit);
           else
             epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
-                                                                0ull, nullptr, 0, 0, rho, rmu);
+                                                                0ull, nullptr, 0, 0, rho, rmu, emit);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
@@ -565,19 +584,31 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
   c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.rowinfo = d.rowinfo; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
   B2_CHECK(d.u_ff1 && d.v_ff1 && d.rowscale && (!d.has_qkv || (d.u_qkv && d.v_qkv)), "dit_chain: folded-LayerNorm vectors");
+  B2_CHECK(!d.fp8 || (d.w8_ff1 && d.sw_ff1 && (!d.has_qkv || (d.w8_qkv && d.sw_qkv))), "dit_chain: e4m3 weights / scales");
+  c.fp8 = d.fp8; c.sw_ff1 = d.sw_ff1; c.sw_qkv = d.sw_qkv;
   c.u_ff1 = d.u_ff1; c.v_ff1 = d.v_ff1; c.u_qkv = d.u_qkv; c.v_qkv = d.v_qkv; c.rowscale = d.rowscale;
   c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
   { const char* v = getenv("B200TTS_CHAIN_L2HINT"); c.l2hint = v != nullptr && atoi(v) != 0; }
   CUtensorMap mA[4], mB[4];
   const void* a_ptr[4] = {d.att16, d.n16, d.ff16, d.n16b};
   const int a_k[4] = {d.D, d.D, d.FF, d.D};
-  for (int j = 0; j < 4; ++j)
-    tc_encode_map(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
+  for (int j = 0; j < 4; ++j) {
+    if (d.fp8 && (j == 1 || j == 3))     // e4m3 rows of D bytes in the (2 D byte) rows' buffer, densely packed
+      tc_encode_map_u8(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
+    else
+      tc_encode_map(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
+  }
   const TcWeight* ws[4] = {d.w_out, d.w_ff1, d.w_ff2, wq};
   for (int j = 0; j < 4; ++j) {
-    const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, c.team);
-    tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
-                  (uint32_t)js.b_rows);
+    const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, c.team, d.fp8);
+    if (d.fp8 && (j == 1 || (j == 3 && d.has_qkv))) {
+      const void* w8 = j == 1 ? d.w8_ff1 : d.w8_qkv;
+      const uint64_t n_rows = j == 1 ? (uint64_t)d.FF : (uint64_t)3 * d.D;
+      tc_encode_map_u8(&mB[j], w8, (uint64_t)d.D, n_rows, 1, (uint64_t)d.D, n_rows * d.D, (uint32_t)js.b_rows);
+    } else {
+      tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
+                    (uint32_t)js.b_rows);
+    }
   }
   // epilogue tiles: x (fp32, residual in / result out), ff16 and q|k (16 bit, result out), 32 rows x 32 columns each
   CUtensorMap mX, mFFo, mQKo;

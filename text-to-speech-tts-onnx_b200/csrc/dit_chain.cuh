@@ -38,6 +38,11 @@ struct DitChain {
   // block's attention (written by ln_modulate for block 0 and by the previous chain launch afterwards; updated in place)
   const float *u_ff1 = nullptr, *v_ff1 = nullptr, *u_qkv = nullptr, *v_qkv = nullptr;
   float* rowscale = nullptr;
+  // optional e4m3 mode of ff1 and q|k|v (tcgen05 kind::f8f6f4): weights [N][D] bytes with per-output-channel scales (u / v above
+  // must then be computed from the DEQUANTISED weights); the A operands are emitted as e4m3 by the epilogues that produce x
+  int fp8 = 0;
+  const void *w8_ff1 = nullptr, *w8_qkv = nullptr;
+  const float *sw_ff1 = nullptr, *sw_qkv = nullptr;
   // team synchronisation scratch (sizes below); `flags` must be zero when the kernel starts
   float* stats = nullptr;
   unsigned* flags = nullptr;

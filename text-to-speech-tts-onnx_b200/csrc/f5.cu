@@ -61,6 +61,11 @@ struct DiTLayer {
   //   fu1 / fv1 [nfe][FF]: W_ff1 (1 + scale_mlp), W_ff1 shift_mlp + b_ff1;  fuq / fvq [nfe][3D]: the same for q|k|v with the msa pair
   DevBuf<float> fu1[2], fv1[2], fuq[2], fvq[2];
   bool fold_ready[2] = {false, false};
+  // optional e4m3 mode of ff1 / q|k|v (engine option dit_fp8): weights quantised per output channel, their scales, and the
+  // folded-LayerNorm vectors recomputed from the dequantised weights
+  DevBuf<uint8_t> w8_ff1, w8_qkv;
+  DevBuf<float> sw_ff1, sw_qkv, fu1_8, fv1_8, fuq_8, fvq_8;
+  bool fp8_ready = false;
 };
 
 }  // namespace
@@ -673,6 +678,19 @@ void f5_steps(Engine& e, int first, int count, int precision) {
                      m.nfe, s);
         L.fold_ready[f16] = true;
       }
+      if (e.dit_fp8) {
+        for (auto& L : m.layers) {
+          if (L.fp8_ready) continue;
+          L.w8_ff1.alloc((size_t)m.FF * D); L.sw_ff1.alloc(m.FF); L.w8_qkv.alloc((size_t)3 * D * D); L.sw_qkv.alloc((size_t)3 * D);
+          quantize_rows_e4m3(L.ff1.w_ref, m.FF, D, L.w8_ff1.p, D, L.sw_ff1.p, s);
+          quantize_rows_e4m3(L.qkv.w_ref, 3 * D, D, L.w8_qkv.p, D, L.sw_qkv.p, s);
+          L.fu1_8.alloc((size_t)m.nfe * m.FF); L.fv1_8.alloc((size_t)m.nfe * m.FF);
+          L.fuq_8.alloc((size_t)m.nfe * 3 * D); L.fvq_8.alloc((size_t)m.nfe * 3 * D);
+          fold_vectors(L.w8_ff1.p, D, D, 2, L.mod.p + 4 * D, L.mod.p + 3 * D, 6 * D, L.ff1.bias.p, L.fu1_8.p, L.fv1_8.p, m.FF, m.nfe, s, L.sw_ff1.p);
+          fold_vectors(L.w8_qkv.p, D, D, 2, L.mod.p + D, L.mod.p, 6 * D, L.qkv.bias.p, L.fuq_8.p, L.fvq_8.p, 3 * D, m.nfe, s, L.sw_qkv.p);
+          L.fp8_ready = true;
+        }
+      }
     }
   }
   // q | k | v of block l from the LN-modulated rows in `a16`: one GEMM, RoPE + V^T in the epilogue (modules.py:459-466)
@@ -753,8 +771,19 @@ void f5_steps(Engine& e, int first, int count, int precision) {
           c.w_qkv = &m.layers[l + 1].qkv.tc[f16]; c.b_qkv = m.layers[l + 1].qkv.bias.p;
           c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.rowinfo = rowinfo; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
         }
-        c.u_ff1 = L.fu1[f16].p + (size_t)step * m.FF; c.v_ff1 = L.fv1[f16].p + (size_t)step * m.FF;
-        if (!last) { c.u_qkv = m.layers[l + 1].fuq[f16].p + (size_t)step * 3 * D; c.v_qkv = m.layers[l + 1].fvq[f16].p + (size_t)step * 3 * D; }
+        if (e.dit_fp8) {
+          c.fp8 = 1;
+          c.w8_ff1 = L.w8_ff1.p; c.sw_ff1 = L.sw_ff1.p;
+          c.u_ff1 = L.fu1_8.p + (size_t)step * m.FF; c.v_ff1 = L.fv1_8.p + (size_t)step * m.FF;
+          if (!last) {
+            DiTLayer& Ln = m.layers[l + 1];
+            c.w8_qkv = Ln.w8_qkv.p; c.sw_qkv = Ln.sw_qkv.p;
+            c.u_qkv = Ln.fuq_8.p + (size_t)step * 3 * D; c.v_qkv = Ln.fvq_8.p + (size_t)step * 3 * D;
+          }
+        } else {
+          c.u_ff1 = L.fu1[f16].p + (size_t)step * m.FF; c.v_ff1 = L.fv1[f16].p + (size_t)step * m.FF;
+          if (!last) { c.u_qkv = m.layers[l + 1].fuq[f16].p + (size_t)step * 3 * D; c.v_qkv = m.layers[l + 1].fvq[f16].p + (size_t)step * 3 * D; }
+        }
         c.rowscale = m.rowscale.p;
         c.stats = m.chain_stats.p; c.flags = m.chain_flags.p + (size_t)l * flag_words;
         c.trace = trace_path && l == m.depth - 2 ? m.chain_trace.p : nullptr;      // a typical block (the last one has no q|k|v job)

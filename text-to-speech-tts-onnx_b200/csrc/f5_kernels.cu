@@ -3,6 +3,7 @@
 #include <type_traits>
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace b200tts {
 
@@ -298,7 +299,26 @@ __global__ void rope_pack_kernel(const float* __restrict__ c, const float* __res
 
 // u[t][j] = sum_k W[j][k] (1 + scale[t][k]),  v[t][j] = sum_k W[j][k] shift[t][k] + bias[j]   for the nfe rows of a modulation
 // table, from the 16-bit weights the tensor cores multiply with (dit_chain.cu: LayerNorm folded into the GEMM). One block per j.
-__global__ void __launch_bounds__(128) fold_vectors_kernel(const uint16_t* __restrict__ w, int ldc, int K, int f16,
+// Per-output-channel e4m3 quantisation of a weight [N][K] (fp32): scale[j] = max|W[j][:]| / 448, q[j][k] = e4m3(W[j][k] / scale[j])
+__global__ void __launch_bounds__(128) quantize_rows_e4m3_kernel(const float* __restrict__ w, int K, uint8_t* __restrict__ q, int ldq,
+                                                                 float* __restrict__ scale) {
+  __shared__ float red[4];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  float am = 0.f;
+  for (int k = tid; k < K; k += 128) am = fmaxf(am, fabsf(w[(size_t)j * K + k]));
+  am = warp_max(am);
+  if ((tid & 31) == 0) red[tid >> 5] = am;
+  __syncthreads();
+  am = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  const float s = am > 0.f ? am / 448.0f : 1.0f;
+  if (tid == 0) scale[j] = s;
+  const float inv = 1.0f / s;
+  for (int k = tid; k < K; k += 128)
+    q[(size_t)j * ldq + k] = (uint8_t)__nv_cvt_float_to_fp8(w[(size_t)j * K + k] * inv, __NV_SATFINITE, __NV_E4M3);
+}
+
+// f16: 0 = bf16, 1 = fp16, 2 = e4m3 bytes with the per-row scale `wscale`
+__global__ void __launch_bounds__(128) fold_vectors_kernel(const void* __restrict__ wv, const float* __restrict__ wscale, int ldc, int K, int f16,
                                                            const float* __restrict__ scale, const float* __restrict__ shift, int mod_ld,
                                                            const float* __restrict__ bias, float* __restrict__ u, float* __restrict__ v,
                                                            int N, int nfe) {
@@ -310,8 +330,13 @@ __global__ void __launch_bounds__(128) fold_vectors_kernel(const uint16_t* __res
     const int k = tid + i * 128;
     float x = 0.f;
     if (k < K) {
-      const uint16_t raw = w[(size_t)j * ldc + k];
-      x = f16 ? __half2float(__ushort_as_half(raw)) : __bfloat162float(__ushort_as_bfloat16(raw));
+      if (f16 == 2) {
+        const __half_raw hr = __nv_cvt_fp8_to_halfraw(reinterpret_cast<const uint8_t*>(wv)[(size_t)j * ldc + k], __NV_E4M3);
+        x = __half2float(__half(hr)) * wscale[j];
+      } else {
+        const uint16_t raw = reinterpret_cast<const uint16_t*>(wv)[(size_t)j * ldc + k];
+        x = f16 ? __half2float(__ushort_as_half(raw)) : __bfloat162float(__ushort_as_bfloat16(raw));
+      }
     }
     wk[i] = x;
   }
@@ -349,9 +374,14 @@ void ln_modulate(const float* x, const float* scale, const float* shift, void* o
   LAUNCHED();
 }
 void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, const float* shift, int mod_ld, const float* bias, float* u,
-                  float* v, int N, int nfe, cudaStream_t s) {
+                  float* v, int N, int nfe, cudaStream_t s, const float* wscale) {
   B2_CHECK(K <= 1024, "fold_vectors: K <= 1024");
-  fold_vectors_kernel<<<N, 128, 0, s>>>(reinterpret_cast<const uint16_t*>(w16), ldc, K, f16, scale, shift, mod_ld, bias, u, v, N, nfe);
+  B2_CHECK(f16 != 2 || wscale != nullptr, "fold_vectors: e4m3 weights need their row scales");
+  fold_vectors_kernel<<<N, 128, 0, s>>>(w16, wscale, ldc, K, f16, scale, shift, mod_ld, bias, u, v, N, nfe);
+  LAUNCHED();
+}
+void quantize_rows_e4m3(const float* w, int N, int K, void* q, int ldq, float* scale, cudaStream_t s) {
+  quantize_rows_e4m3_kernel<<<N, 128, 0, s>>>(w, K, reinterpret_cast<uint8_t*>(q), ldq, scale);
   LAUNCHED();
 }
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s) {

@@ -13,8 +13,11 @@ void ln_modulate(const float* x, const float* scale, const float* shift, void* o
                  float* rstd_out = nullptr /* optional [R]: 1 / std of every row */);
 // u[t][j] = sum_k W16[j][k] (1 + scale[t][k]), v[t][j] = sum_k W16[j][k] shift[t][k] + bias[j], t < nfe (rows of a modulation table
 // with row stride mod_ld); W16 = the [N][ldc] 16-bit tensor-core weight (K <= 1024 columns used)
+// f16 = 2: W16 is an e4m3 byte tensor with per-row scales `wscale` (quantize_rows_e4m3)
 void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, const float* shift, int mod_ld, const float* bias, float* u,
-                  float* v, int N, int nfe, cudaStream_t s);
+                  float* v, int N, int nfe, cudaStream_t s, const float* wscale = nullptr);
+// per-output-channel e4m3 quantisation of an fp32 weight [N][K]: q [N][ldq] bytes, scale [N] (W ~ q * scale)
+void quantize_rows_e4m3(const float* w, int N, int K, void* q, int ldq, float* scale, cudaStream_t s);
 // nn.LayerNorm(D, eps) with affine (text ConvNeXtV2 block, modules.py:248)
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s);
 void layernorm_affine_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* out, int R, int D, float eps, cudaStream_t s);

@@ -489,6 +489,19 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
   if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
 
+// 8-bit operands (e4m3): dims {d0 bytes (contiguous), d1, d2}, byte strides, box {128, box1, 1}, SWIZZLE_128B
+void tc_encode_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t box1) {
+  B2_CHECK(((uintptr_t)base & 15) == 0 && ld1 % 16 == 0 && ld2 % 16 == 0, "TMA base / strides must be multiples of 16 bytes");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {ld1, ld2};
+  cuuint32_t box[3] = {128u, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled (u8) failed with CUresult " + std::to_string((int)r));
+}
+
 void tc_encode_map2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t box0,
                      uint32_t box1) {
   B2_CHECK(elem_bytes == 2 || elem_bytes == 4, "tc_encode_map2d: element size");

@@ -31,6 +31,8 @@ void tc_encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
 // 2-D TMA map for epilogue tiles: dims {d0 (contiguous), d1} of `elem_bytes`-wide elements (2 or 4), row stride ld1 elements,
 // box {box0, box1} with box0 * elem_bytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B); rows / columns beyond the dims are
 // zero-filled on load and clipped on store
+// 8-bit (e4m3) operand map: dims {d0 bytes, d1, d2}, byte strides {ld1, ld2}, box {128, box1, 1}, SWIZZLE_128B, zero OOB fill
+void tc_encode_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t box1);
 void tc_encode_map2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t box0,
                      uint32_t box1);
 

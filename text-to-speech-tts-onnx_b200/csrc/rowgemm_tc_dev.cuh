@@ -2,6 +2,7 @@
 // one GEMM's epilogue, the smem-transposed coalesced epilogue, and the fully unrolled MMA issue helpers. Include inside
 // namespace b200tts, within an anonymous namespace of the including translation unit.
 #pragma once
+#include <cuda_fp8.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -233,7 +234,6 @@ __device__ __forceinline__ void epilogue_warp(const TcArgs& a, EpiPos p, uint32_
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int row = i * 4 + sub;
       const long flat = epi_flat(a, p, i, n);
       const bool ok = epi_ok(a, p, i, n, flat);
       const float4 acc = accs[i];
@@ -334,8 +334,10 @@ __device__ __forceinline__ void epi_tma_drain(int lane) {
 // owns 64 contiguous bytes of its row) -- the A operand of the NEXT GEMM, produced without a second pass over x.
 struct EpiEmit {
   uint16_t* row = nullptr;     // this lane's row of the 16-bit tensor (null: row out of range / nothing to emit)
+  uint8_t* row8 = nullptr;     // ... or of the 8-bit (e4m3) tensor: the next GEMM runs with fp8 operands
   const float* s_mul = nullptr;   // shared-memory copy of (1 + scale)[n0 ..)
-  float c = 1.0f;              // the row's scale (a stale 1 / std estimate: keeps fp16 in range)
+                                  // (AFFINE epilogues reuse the field: per-column multiplier of the accumulator = e4m3 weight scales)
+  float c = 1.0f;              // the row's scale (a stale 1 / std estimate: keeps fp16 / e4m3 in range)
 };
 template <int TK, int ACT, bool STATS, bool AFFINE = false>
 __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
@@ -381,7 +383,12 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
           if (AFFINE) {
             const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
             bi.x = fmaf(-rmu, u.x, bi.x); bi.y = fmaf(-rmu, u.y, bi.y); bi.z = fmaf(-rmu, u.z, bi.z); bi.w = fmaf(-rmu, u.w, bi.w);
-            w0 *= rho; w1 *= rho; w2 *= rho; w3 *= rho;
+            float4 r4 = make_float4(rho, rho, rho, rho);
+            if (emit.s_mul != nullptr) {
+              const float4 sw = lds128(smem_u32(emit.s_mul) + (uint32_t)(cb + k * 4) * 4u);
+              r4.x *= sw.x; r4.y *= sw.y; r4.z *= sw.z; r4.w *= sw.w;
+            }
+            w0 *= r4.x; w1 *= r4.y; w2 *= r4.z; w3 *= r4.w;
           }
           const int cv = n + k * 4 - a.vt_col0;
           uint16_t* o16 = reinterpret_cast<uint16_t*>(a.vt_out) + ((long)(bb * a.vt_heads + (cv >> 6)) * 64 + (cv & 63)) * a.vt_ld + tt;
@@ -400,10 +407,15 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
       const float4 bi = lds128(bias_s + (uint32_t)(cb + k * 4) * 4u);
       if (AFFINE) {
         const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
-        f[k * 4 + 0] = fmaf(rho, __uint_as_float(v[k * 4 + 0]), fmaf(-rmu, u.x, bi.x));
-        f[k * 4 + 1] = fmaf(rho, __uint_as_float(v[k * 4 + 1]), fmaf(-rmu, u.y, bi.y));
-        f[k * 4 + 2] = fmaf(rho, __uint_as_float(v[k * 4 + 2]), fmaf(-rmu, u.z, bi.z));
-        f[k * 4 + 3] = fmaf(rho, __uint_as_float(v[k * 4 + 3]), fmaf(-rmu, u.w, bi.w));
+        float4 r4 = make_float4(rho, rho, rho, rho);
+        if (emit.s_mul != nullptr) {                             // e4m3 weights: their per-output-channel scales
+          const float4 sw = lds128(smem_u32(emit.s_mul) + (uint32_t)(cb + k * 4) * 4u);
+          r4.x *= sw.x; r4.y *= sw.y; r4.z *= sw.z; r4.w *= sw.w;
+        }
+        f[k * 4 + 0] = fmaf(r4.x, __uint_as_float(v[k * 4 + 0]), fmaf(-rmu, u.x, bi.x));
+        f[k * 4 + 1] = fmaf(r4.y, __uint_as_float(v[k * 4 + 1]), fmaf(-rmu, u.y, bi.y));
+        f[k * 4 + 2] = fmaf(r4.z, __uint_as_float(v[k * 4 + 2]), fmaf(-rmu, u.z, bi.z));
+        f[k * 4 + 3] = fmaf(r4.w, __uint_as_float(v[k * 4 + 3]), fmaf(-rmu, u.w, bi.w));
       } else {
         f[k * 4 + 0] = __uint_as_float(v[k * 4 + 0]) + bi.x; f[k * 4 + 1] = __uint_as_float(v[k * 4 + 1]) + bi.y;
         f[k * 4 + 2] = __uint_as_float(v[k * 4 + 2]) + bi.z; f[k * 4 + 3] = __uint_as_float(v[k * 4 + 3]) + bi.w;
@@ -455,6 +467,22 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
         *slot = make_float2(rsum, rsq);
         rsum = 0.f; rsq = 0.f;
       }
+    }
+    if (TK == TK_RES_F32 && emit.row8 != nullptr) {
+      // e4m3 operand of the next GEMM: 32 columns = 32 bytes per lane; cvt saturates at +-448
+      const uint32_t mul_s = smem_u32(emit.s_mul);
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 m0 = lds128(mul_s + (uint32_t)(cb + k * 4) * 4u);
+        const float y0 = __fmul_rn(__fmul_rn(emit.c, f[k * 4 + 0]), m0.x), y1 = __fmul_rn(__fmul_rn(emit.c, f[k * 4 + 1]), m0.y);
+        const float y2 = __fmul_rn(__fmul_rn(emit.c, f[k * 4 + 2]), m0.z), y3 = __fmul_rn(__fmul_rn(emit.c, f[k * 4 + 3]), m0.w);
+        const uint32_t lo = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(y0, y1), __NV_SATFINITE, __NV_E4M3);
+        const uint32_t hi = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(y2, y3), __NV_SATFINITE, __NV_E4M3);
+        w[k] = lo | (hi << 16);
+      }
+      *reinterpret_cast<uint4*>(emit.row8 + n) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(emit.row8 + n + 16) = make_uint4(w[4], w[5], w[6], w[7]);
     }
     if (TK == TK_RES_F32 && emit.row != nullptr) {
       const uint32_t mul_s = smem_u32(emit.s_mul);

@@ -216,6 +216,19 @@ __device__ __forceinline__ void umma2_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
       "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128) : "memory");
 }
+// the same for 8-bit operands (kind::f8f6f4, here e4m3 x e4m3: format code 0 in the descriptor): K = 32 elements = 32 bytes
+// per instruction, so the descriptor arithmetic of a 128-byte swizzle row (4 instructions, +2 each) is unchanged
+__device__ __forceinline__ void umma2_f8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128) : "memory");
+}
 // arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

@@ -210,6 +210,57 @@ def sec_bvg_branches():
         out(section="bvg_branches", B=B, T=T, bit_identical=bool(np.array_equal(res[(B, T, 0)], res[(B, T, 1)])))
 
 
+def sec_f5_fp8():
+    """Optional e4m3 mode of ff1 / q|k|v (engine option dit_fp8): parity against the reference goldens at N = 130 and N = 1126, and
+    time per call for one and eight config-3 utterances, fp8 off / on."""
+    import torch
+    eng = f5_engine()
+    for gname, mel_key, pcm_key, ref_key in (("f5_ref.npz", "noise_after_31", "pcm", "ref_signal_len"), ("fullsize_ref.npz", "f5_mel", "f5_pcm", "f5_ref_signal_len")):
+        g = dict(np.load(os.path.join(GOLD, gname)))
+        audio, text_ids, maxd, noise = synth.f5_inputs(int(g["input_seed"]), int(g["audio_len"]), int(g["n_text"]))
+        N = int(maxd[0])
+        for fp8 in (0, 1):
+            eng.set_option("dit_fp8", fp8)
+            pcm, mel = eng.f5_synthesize(audio, text_ids, N, noise, precision=capi.F16, return_mel=True)
+            r = int(g[ref_key])
+            out(section="f5_fp8", N=N, fp8=fp8, mel_cos=cosine(mel, g[mel_key]), gen_mel_cos=cosine(mel[:, r:], g[mel_key][:, r:]),
+                mel_maxabs=float(np.abs(mel - g[mel_key]).max()), pcm_snr=snr_db(g[pcm_key], pcm), finite=bool(np.isfinite(mel).all()))
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    L, n_text = 144000, 150
+    for U in (1, 8):
+        ins = [synth.f5_inputs(1000 + i, L, n_text) for i in range(U)]
+        N = int(ins[0][2][0])
+        ns = 256 * (N - (L // 256 + 1) - 1)
+        audio = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).cuda()
+        ids = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).cuda()
+        noise = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).cuda()
+        pcm = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
+        for fp8 in (0, 1):
+            eng.set_option("dit_fp8", fp8)
+
+            def run():
+                eng.f5_synthesize_batch_device(U, audio.data_ptr(), L, ids.data_ptr(), n_text, N, noise.data_ptr(), pcm.data_ptr(), precision=capi.F16)
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 5 if U == 1 else 2
+                e0.record(stream)
+                for _ in range(reps):
+                    run()
+                e1.record(stream)
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            eng.profile_begin()
+            with torch.cuda.stream(stream):
+                run()
+            prof = eng.profile_end()
+            out(section="f5_fp8", U=U, fp8=fp8, ms_per_call=ms, ms_per_utt=ms / U, chain_ms=round(prof["f5.chain"]["ms"], 3),
+                attention_ms=round(prof["f5.attention"]["ms"], 3))
+
+
 def sec_attn_time():
     """fp16, fused chain: time per call and the event-timed share of attention / chain, one and eight config-3 utterances."""
     import torch
