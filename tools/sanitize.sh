@@ -16,6 +16,6 @@ run() {   # tool subset env... -- pytest args
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
   ENVV=(B200TTS_2SM=1); run $tool conv2sm tests/test_gpu_bigvgan.py -k "conv1d_tcgen05_bf16 and (case0 or case5 or case9)"
   ENVV=(X=1); run $tool attention tests/test_gpu_f5.py -k "attention_tcgen05 and (130 or 257)"
-  ENVV=(X=1); run $tool chain tests/test_gpu_f5.py -k "fused_chain_one_step"
+  ENVV=(X=1); run $tool chain tests/test_gpu_f5.py -k "fused_chain_one_step"          # fp16 / bf16 operands and the e4m3 option
   ENVV=(X=1); run $tool gptdecode tests/test_gpu_indextts_gpt.py -k "bf16_generate_prefix or stop_token_in_the_middle"
 done
