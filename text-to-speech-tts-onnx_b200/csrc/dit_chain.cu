@@ -33,6 +33,7 @@
 // previous kernel: weights are constants).
 #include "dit_chain.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -57,7 +58,8 @@ constexpr int CH_SMEM = CH_A_STAGES * CH_A_BYTES + CH_B_STAGES * CH_B_BYTES + CH
 static_assert(CH_SMEM <= 227 * 1024, "dit_chain: shared memory budget");
 
 struct ChainArgs {
-  int R, nrb, teams, team, has_qkv, f16, D, FF;      // team = CTA pairs per row block (1, 2, 4 or 8)
+  int R, nrb, teams, team, has_qkv, f16, D, FF;      // phase 0: `teams` teams of `team` CTA pairs (1, 2, 4 or 8) walk row blocks [0, nrb0)
+  int nrb0, rem, team1;                              // phase 1: the `rem` = nrb - nrb0 remaining row blocks, one team of `team1` pairs each
   int l2hint;                                        // experiment: x tiles stored with the L2 evict_last policy
   float* x;
   __nv_bfloat16 *n16, *ff16, *n16b;
@@ -153,10 +155,10 @@ __device__ __forceinline__ int subtile_col0(int j, int st, int slice, int team, 
 // squares), one group per 128 output columns of the CTA's slice) -> the row block's global slots. Global slot = the group's
 // index among the 8 groups of a row (D = 1024): the same 8 numbers whatever the team size, reduced in the same order by every
 // reader. The caller's team_signal() publishes them together with the tiles the same epilogue wrote.
-__device__ __forceinline__ void publish_stats(const ChainArgs& c, int rb, int rank, int slice, int kind, const float* st, int tid) {
+__device__ __forceinline__ void publish_stats(const ChainArgs& c, int tsz, int rb, int rank, int slice, int kind, const float* st, int tid) {
   epi_bar();
   float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
-  const int groups = CH_MAX_TEAM / c.team;
+  const int groups = CH_MAX_TEAM / tsz;
   if (tid < 128) {
     for (int gi = 0; gi < groups; ++gi) {
       const float2 p0 = *reinterpret_cast<const float2*>(st + ((size_t)(gi * 2 + 0) * 128 + tid) * 2);
@@ -183,23 +185,23 @@ __device__ __forceinline__ float2 row_mean_rstd(const ChainArgs& c, int rb, int 
 // Measured alternatives that were SLOWER on B200 (profiles/r02/chain_timeline.md): fetching the slab before the statistics
 // arrive with 16 row loads per lane in flight (+3.6 ms per utterance), and walking whole rows instead of 128-column groups
 // (+6 ms): more loads in flight per thread only lengthen the loaded L2 latency here.
-__device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, int slice, int kind,
+__device__ __forceinline__ void ln_phase(const ChainArgs& c, int tsz, int rb, int rank, int slice, int kind,
                                          const float* scale, const float* shift, __nv_bfloat16* dst, unsigned* flag_stat,
                                          unsigned* flag_ready, float* st, int warp, int lane) {
   const int tid = warp * 32 + lane;
-  publish_stats(c, rb, rank, slice, kind, st, tid);
+  publish_stats(c, tsz, rb, rank, slice, kind, st, tid);
   float* stats = c.stats + ((size_t)(rb * 2 + kind) * CH_ROWS + rank * 128) * (CH_MAX_TEAM * 2);
   epi_bar();
   if (tid == 0) {
     fence_acq_rel_gpu();
     red_relaxed_gpu(flag_stat, 1u);
-    wait_counter(flag_stat, 2u * (unsigned)c.team);
+    wait_counter(flag_stat, 2u * (unsigned)tsz);
   }
   epi_tma_drain(lane);                                         // x tiles of this warp are in global memory (under the exchange)
   epi_bar();
   if (tid == 0) stamp(c, 8 + 8 * (kind * 2) + 6);
   // pass 2: warp w normalises rows [16w, 16w + 16) of the slab, 128 columns at a time (lane l: columns 4l .. 4l + 3)
-  const int n_slab = c.D / c.team;
+  const int n_slab = c.D / tsz;
   const float inv_d = 1.0f / (float)c.D;
   const long grow0 = (long)rb * CH_ROWS + rank * 128 + warp * 16;
   float2 pr[4];
@@ -250,11 +252,33 @@ __device__ __forceinline__ void ln_phase(const ChainArgs& c, int rb, int rank, i
   team_signal(flag_ready, tid);
 }
 
+// The two phases of a launch as seen by CTA pair `pair`: phase 0 = whole rounds of row blocks at team size c.team (every pair
+// busy), phase 1 = the remainder, one team of c.team1 >= c.team pairs per block. A launch whose row blocks are one more than a
+// multiple of the resident pairs used to cost a whole extra round (configs[3]: 593 = 8 x 74 + 1 blocks on one GPU, 297 / 149 / 75
+// per rank on 2 / 4 / 8); now the odd block is shared by 8 pairs and costs a sixth of a round.
+struct Phase { int tsz, slice, rb0, rb1, step; };
+__device__ __forceinline__ bool get_phase(const ChainArgs& c, int pair, int ph, Phase& p) {
+  if (ph == 0) {
+    p.tsz = c.team;
+    const int tm = pair / c.team;
+    p.slice = pair - tm * c.team;
+    p.rb0 = tm; p.rb1 = c.nrb0; p.step = c.teams;
+    return tm < c.teams && tm < c.nrb0;
+  }
+  p.tsz = c.team1;
+  const int tm = pair / c.team1;
+  p.slice = pair - tm * c.team1;
+  p.rb0 = c.nrb0 + tm; p.rb1 = p.rb0 + 1; p.step = 1;
+  return tm < c.rem;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS3, 1)
 dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
                  const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1,
                  const __grid_constant__ CUtensorMap mB2, const __grid_constant__ CUtensorMap mB3,
+                 const __grid_constant__ CUtensorMap mC0, const __grid_constant__ CUtensorMap mC1,      // the weight maps of phase 1
+                 const __grid_constant__ CUtensorMap mC2, const __grid_constant__ CUtensorMap mC3,      // (box rows depend on the team size)
                  const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mFFo,
                  const __grid_constant__ CUtensorMap mQKo, const ChainArgs c) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -278,13 +302,12 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const int team = pair / c.team, slice = pair - team * c.team;
   const int njobs = c.has_qkv ? 4 : 3;
-  const unsigned team_ctas = 2u * (unsigned)c.team;
 
   if (warp == WARP_TMA && lane == 0) {
     prefetch_tmap(&mA0); prefetch_tmap(&mA1); prefetch_tmap(&mA2); prefetch_tmap(&mA3);
     prefetch_tmap(&mB0); prefetch_tmap(&mB1); prefetch_tmap(&mB2); prefetch_tmap(&mB3);
+    if (c.rem > 0) { prefetch_tmap(&mC0); prefetch_tmap(&mC1); prefetch_tmap(&mC2); prefetch_tmap(&mC3); }
     prefetch_tmap(&mX); prefetch_tmap(&mFFo); prefetch_tmap(&mQKo);
     for (int s = 0; s < CH_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < CH_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -306,11 +329,15 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       // hand-off before the first sub-tile of a job =====
       pdl_wait();
       int sa = 0; uint32_t pa = 0;
-      for (int rb = team; rb < c.nrb; rb += c.teams) {
+      for (int ph = 0; ph < 2; ++ph) {
+      Phase P;
+      if (!get_phase(c, pair, ph, P)) continue;
+      const unsigned team_ctas = 2u * (unsigned)P.tsz;
+      for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         const int row0 = rb * CH_ROWS + (int)rank * 128;
         const unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
           stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
@@ -327,18 +354,24 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
             }
         }
       }
+      }
     }
   } else if (warp == WARP_TMA_B) {
     if (lane == 0) {
       // ===== B producer (both CTAs): this CTA's half of each sub-tile's weight rows. No pdl_wait: weights are constants =====
       int sb = 0; uint32_t pb = 0;
-      for (int rb = team; rb < c.nrb; rb += c.teams) {
+      for (int ph = 0; ph < 2; ++ph) {
+      Phase P;
+      if (!get_phase(c, pair, ph, P)) continue;
+      const int slice = P.slice;
+      for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
-          const CUtensorMap* map = j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3;
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
+          const CUtensorMap* map = ph == 0 ? (j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3)
+                                           : (j == 0 ? &mC0 : j == 1 ? &mC1 : j == 2 ? &mC2 : &mC3);
           const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
           for (int st = 0; st < js.nsubt; ++st) {
-            const int n_row0 = subtile_col0(j, st, slice, c.team, js) + (int)rank * js.b_rows;
+            const int n_row0 = subtile_col0(j, st, slice, P.tsz, js) + (int)rank * js.b_rows;
             for (int ck = 0; ck < js.chunks; ++ck) {
               mbar_wait(&b_empty[sb], pb ^ 1);
               if (leader) mbar_expect_tx(&b_full[sb], tx);
@@ -348,6 +381,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           }
         }
       }
+      }
     }
   } else if (warp == WARP_MMA) {
     if (leader) {
@@ -356,9 +390,12 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       const uint32_t a_stage_lo = (uint32_t)CH_A_BYTES >> 4, b_stage_lo = (uint32_t)CH_B_BYTES >> 4;
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       uint32_t t = 0;
-      for (int rb = team; rb < c.nrb; rb += c.teams) {
+      for (int ph = 0; ph < 2; ++ph) {
+      Phase P;
+      if (!get_phase(c, pair, ph, P)) continue;
+      for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
           const uint32_t idesc = idesc_f16kind(256, js.w, js.fp8 ? 1 : c.f16);      // e4m3 shares format code 0 with fp16
           const int chunks = js.chunks;
           for (int st = 0; st < js.nsubt; ++st, ++t) {
@@ -397,6 +434,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           }
         }
       }
+      }
     }
   } else {
     // ===== epilogue (both CTAs, warps 0..7): this CTA's 128 rows; q = TMEM lane quarter, e = even / odd 32-column blocks.
@@ -431,7 +469,12 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
     a.rowinfo = c.rowinfo;
     uint32_t t = 0;
     const uint64_t x_policy = c.l2hint ? l2_policy_evict_last() : 0ull;
-    for (int rb = team; rb < c.nrb; rb += c.teams) {
+    for (int ph = 0; ph < 2; ++ph) {
+    Phase P;
+    if (!get_phase(c, pair, ph, P)) continue;
+    const int slice = P.slice;
+    const unsigned team_ctas = 2u * (unsigned)P.tsz;
+    for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
       unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
       const int row0 = rb * CH_ROWS + (int)rank * 128 + q * 32;
       const int myrow = row0 + lane;                           // the row this lane owns in every epilogue of the row block
@@ -441,7 +484,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       float c_row = myrow < c.R ? __ldcg(c.rowscale + myrow) : 1.0f;
       float rho = 1.0f, rmu = 0.0f;
       for (int j = 0; j < njobs; ++j) {
-        const JobShape js = job_shape(j, c.D, c.FF, c.team, c.fp8);
+        const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
         a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.chunks;
         const float* wscale = !js.fp8 ? nullptr : j == 1 ? c.sw_ff1 : c.sw_qkv;
         const bool next_fp8 = c.fp8 && (j == 0 || j == 2);      // the operand this job emits feeds an e4m3 GEMM
@@ -476,7 +519,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         float rsum = 0.f, rsq = 0.f;
         for (int st = 0; st < js.nsubt; ++st, ++t) {
           const uint32_t buf = t & 1u;
-          const int n0 = subtile_col0(j, st, slice, c.team, js);
+          const int n0 = subtile_col0(j, st, slice, P.tsz, js);
           const uint32_t taddr = tmem_base + buf * 256u + lane_sel;
           stage_vec(bias, gate, scale, wscale, n0, js.w);
           if (j == 0 || j == 2) epi_tma_fetch_res(&mX, et, n0 + e * 32, row0, lane);
@@ -500,18 +543,19 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         if (fold) {
           // x tiles (TMA stores) and the emitted 16-bit rows (plain stores) of this CTA are complete: publish the LayerNorm
           // partials and hand everything to the team with ONE counter (the next GEMM's A producer and its epilogue wait on it)
-          publish_stats(c, rb, (int)rank, slice, j == 0 ? 0 : 1, smem_stat, tid);
+          publish_stats(c, P.tsz, rb, (int)rank, slice, j == 0 ? 0 : 1, smem_stat, tid);
           epi_tma_drain(lane);
           team_signal(flags + (j == 0 ? F_N16 : F_N16B), tid);
         } else if (j == 2) {
           // last block: the final LayerNorm feeds proj_out (a separate GEMM) -> normalise in a second pass as before
-          ln_phase(c, rb, (int)rank, slice, 1, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
+          ln_phase(c, P.tsz, rb, (int)rank, slice, 1, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
         } else {
           epi_tma_drain(lane);
           if (j == 1) team_signal(flags + F_FF16, tid);
         }
         if (tid == 0) stamp(c, 8 + 8 * j + 7);
       }
+    }
     }
   }
 
@@ -576,9 +620,41 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
            d.w_ff2->Cin == d.FF && (!d.has_qkv || (d.w_qkv->N == 3 * d.D && d.w_qkv->Cin == d.D)), "dit_chain: weight shapes");
   ChainArgs c;
   c.R = d.R; c.nrb = ceil_div(d.R, CH_ROWS); c.has_qkv = d.has_qkv; c.f16 = d.f16; c.D = d.D; c.FF = d.FF;
-  c.team = pick_team(c.nrb, resident_pairs());
-  const int max_teams = resident_pairs() / c.team;
-  c.teams = c.nrb < max_teams ? c.nrb : max_teams;
+  // plan: phase 0 = whole rounds of row blocks at team size t0, phase 1 = the remaining blocks with the largest team that still
+  // gives each its own team; the (t0, t1) pair with the lowest modelled time wins (B200TTS_CHAIN_TEAM forces one phase)
+  const int pairs = resident_pairs();
+  c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1;
+  if (getenv("B200TTS_CHAIN_TEAM") != nullptr) {
+    c.team = pick_team(c.nrb, pairs);
+    const int max_teams = pairs / c.team;
+    c.teams = c.nrb < max_teams ? c.nrb : max_teams;
+  } else {
+    // time of one round of row blocks by team size, relative (measured: a round of 74 blocks at T = 1 takes 340 us, a block
+    // shared by 8 pairs 57 us; profiles/r02 chain timelines)
+    static const double round_cost[4] = {1.0, 0.55, 0.30, 0.17};
+    auto lg = [](int t) { return t == 1 ? 0 : t == 2 ? 1 : t == 4 ? 2 : 3; };
+    auto team_for = [&](int blocks, int tmin) {                    // largest team size that gives every block its own team
+      int t = CH_MAX_TEAM;
+      while (t > tmin && blocks > pairs / t) t /= 2;
+      return t;
+    };
+    double best = 1e300;
+    for (int t0 = 1; t0 <= CH_MAX_TEAM; t0 *= 2) {
+      const int teams0 = pairs / t0;
+      const int full = c.nrb / teams0, rem = c.nrb - full * teams0;
+      const int t1 = rem > 0 ? team_for(rem, t0) : t0;
+      if (rem > pairs / t1) continue;                              // (only for t0 = 8: the remainder is another round)
+      const double cost = full * round_cost[lg(t0)] + (rem > 0 ? round_cost[lg(t1)] : 0.0);
+      if (cost < best - 1e-9) {
+        best = cost;
+        if (full == 0) { c.team = t1; c.teams = rem; c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1; }
+        else { c.team = t0; c.teams = teams0; c.nrb0 = full * teams0; c.rem = rem; c.team1 = t1; }
+      }
+    }
+    if (best > 1e299) {                                            // cannot happen (t0 = 1 always qualifies); keep a safe default
+      c.team = 1; c.teams = c.nrb < pairs ? c.nrb : pairs; c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1;
+    }
+  }
   c.x = d.x; c.n16 = d.n16; c.ff16 = d.ff16; c.n16b = d.n16b;
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;
   c.gate_mlp = d.gate_mlp; c.shift_nxt = d.shift_nxt; c.scale_nxt = d.scale_nxt; c.b_qkv = d.b_qkv;
@@ -599,25 +675,29 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
       tc_encode_map(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
   }
   const TcWeight* ws[4] = {d.w_out, d.w_ff1, d.w_ff2, wq};
-  for (int j = 0; j < 4; ++j) {
-    const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, c.team, d.fp8);
-    if (d.fp8 && (j == 1 || (j == 3 && d.has_qkv))) {
-      const void* w8 = j == 1 ? d.w8_ff1 : d.w8_qkv;
-      const uint64_t n_rows = j == 1 ? (uint64_t)d.FF : (uint64_t)3 * d.D;
-      tc_encode_map_u8(&mB[j], w8, (uint64_t)d.D, n_rows, 1, (uint64_t)d.D, n_rows * d.D, (uint32_t)js.b_rows);
-    } else {
-      tc_encode_map(&mB[j], ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
-                    (uint32_t)js.b_rows);
+  CUtensorMap mC[4];
+  for (int ph = 0; ph < 2; ++ph)
+    for (int j = 0; j < 4; ++j) {
+      CUtensorMap* mp = ph == 0 ? &mB[j] : &mC[j];
+      const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, ph == 0 ? c.team : c.team1, d.fp8);
+      if (d.fp8 && (j == 1 || (j == 3 && d.has_qkv))) {
+        const void* w8 = j == 1 ? d.w8_ff1 : d.w8_qkv;
+        const uint64_t n_rows = j == 1 ? (uint64_t)d.FF : (uint64_t)3 * d.D;
+        tc_encode_map_u8(mp, w8, (uint64_t)d.D, n_rows, 1, (uint64_t)d.D, n_rows * d.D, (uint32_t)js.b_rows);
+      } else {
+        tc_encode_map(mp, ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
+                      (uint32_t)js.b_rows);
+      }
     }
-  }
   // epilogue tiles: x (fp32, residual in / result out), ff16 and q|k (16 bit, result out), 32 rows x 32 columns each
   CUtensorMap mX, mFFo, mQKo;
   tc_encode_map2d(&mX, d.x, 4, (uint64_t)d.D, (uint64_t)d.R, (uint64_t)d.D, 32, 32);
   tc_encode_map2d(&mFFo, d.ff16, 2, (uint64_t)d.FF, (uint64_t)d.R, (uint64_t)d.FF, 32, 32);
   if (d.has_qkv) tc_encode_map2d(&mQKo, d.qk16, 2, (uint64_t)2 * d.D, (uint64_t)d.R, (uint64_t)2 * d.D, 32, 32);
   else mQKo = mFFo;
-  launch_pdl(dit_chain_kernel, dim3((unsigned)(c.teams * c.team * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
-             mB[0], mB[1], mB[2], mB[3], mX, mFFo, mQKo, c);
+  const int grid_pairs = std::max(c.teams * c.team, c.rem * c.team1);
+  launch_pdl(dit_chain_kernel, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
+             mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
   B2_LAUNCH_CHECK();
   count_launch();
 }
