@@ -183,3 +183,21 @@ def test_bigvgan_session_surface(bigvgan_engine):
     assert np.abs(wav.astype(np.int32) - want).max() <= 2
     with pytest.raises(ValueError):
         sess.run([out_name], {in_name: np.ones((1, 100, 0), dtype=np.float32)})
+
+
+def test_bigvgan_fp16_session_reports_float16_and_takes_it(bigvgan_engine):
+    """The fp16 graph variant (BASELINE.json configs[1], q6): the session reports a float16 input exactly as the reference's fp16
+    export does, so the reference's own dtype switch (Export_BigVGAN.py:155-165) feeds float16 mels; the PCM stays within the fp16
+    engine's bar of the fp32 reference."""
+    from b200tts import session as onnxruntime
+    onnxruntime._engines[0] = bigvgan_engine
+    onnxruntime.register_checkpoint("bigvgan", synth.bigvgan_state(1234))
+    sess = onnxruntime.InferenceSession("/tmp/BigVGAN.onnx", providers=[], precision="fp16")
+    model_dtype = sess._inputs_meta[0].type
+    assert "float16" in model_dtype
+    mel = synth.bigvgan_mel(11, 1, 24)
+    feed = onnxruntime.OrtValue.ortvalue_from_numpy(mel.astype(np.float16), "cpu", 0)
+    wav = sess.run_with_ort_values(["generated_wav"], {"mel_features": feed})[0].numpy()
+    want = R.bigvgan_pcm(mel.astype(np.float16).astype(np.float32), synth.bigvgan_state(1234), CFG).numpy()
+    assert wav.dtype == np.int16 and wav.shape == want.shape
+    assert snr_db(want, wav) > 45.0

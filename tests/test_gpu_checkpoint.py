@@ -31,3 +31,32 @@ def test_blob_loaded_bigvgan_matches_state_dict(engine, tmp_path):
     engine.bigvgan_build()
     got = engine.bigvgan_run(mel, precision=capi.F32)
     assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1      # g*v/||v|| reproduces the weights to fp32 round-off
+
+
+def test_session_runs_from_a_blob_loaded_engine(tmp_path):
+    """weights uploaded from an engine blob (Engine.load_blob) drive the onnxruntime-shaped sessions directly -- no
+    register_checkpoint, no second conversion / upload."""
+    from b200tts import session as ort
+    sd = synth.bigvgan_state(77)
+    p = str(tmp_path / "vgan.b200tts")
+    checkpoint.save_blob(p, {"bigvgan": weights.bigvgan_engine_tensors(sd)})
+    eng = capi.Engine(0)
+    assert not eng.has_state("bigvgan")
+    assert eng.load_blob(p) == ["bigvgan"] and eng.has_state("bigvgan")
+    saved_engine, saved_ckpt = ort._engines.get(0), ort._checkpoints.pop("bigvgan", None)
+    try:
+        ort._engines[0] = eng
+        sess = ort.InferenceSession("BigVGAN.onnx", precision="fp32")
+        mel = synth.bigvgan_mel(3, 1, 16)
+        got = sess.run(["generated_wav"], {"mel_features": mel})[0]
+        eng.load_state("bigvgan", weights.bigvgan_engine_tensors(sd))
+        eng.bigvgan_build()
+        want = eng.bigvgan_run(mel, precision=capi.F32)
+        np.testing.assert_array_equal(got, want)
+    finally:
+        if saved_engine is not None:
+            ort._engines[0] = saved_engine
+        else:
+            ort._engines.pop(0, None)
+        if saved_ckpt is not None:
+            ort._checkpoints["bigvgan"] = saved_ckpt

@@ -127,6 +127,23 @@ def test_reference_loop_through_the_sessions(sessions):
     S = g["concat_hidden"].shape[1] + 13
     assert OV.numpy(outs[0]).shape == (CFG.heads, 64, S) and outs[L].shape() == [CFG.heads, S, 64]
     assert int(OV.numpy(outs[2 * L])[0]) == S and int(OV.numpy(gen_len)[0]) == 15
+    # KV handles are views of the resident cache: one more call makes the older ones stale -- reading them or feeding
+    # them back raises instead of silently showing / attending over the advanced cache; host arrays are refused for history > 0
+    old = list(outs)
+    feed["hidden_state"] = gpt_h
+    outs = s["E"].run_with_ort_values(out_E, feed)
+    assert outs[0].is_current() and not old[0].is_current()
+    with pytest.raises(RuntimeError, match="stale KV handle"):
+        OV.numpy(old[0])
+    stale = dict(feed)
+    for i in range(2 * L + 1):
+        stale[in_E[i]] = outs[i]
+    stale[in_E[0]] = old[0]
+    with pytest.raises(ValueError, match="stale or foreign KV handle"):
+        s["E"].run_with_ort_values(out_E, stale)
+    stale[in_E[0]] = OV.ortvalue_from_numpy(np.zeros((CFG.heads, 64, S + 1), np.float32))
+    with pytest.raises(ValueError, match="RESIDENT cache"):
+        s["E"].run_with_ort_values(out_E, stale)
 
 
 def test_missing_inputs_and_bad_shapes_raise(sessions):

@@ -160,6 +160,12 @@ class Engine:
     def load_state(self, prefix: str, state: dict):
         for k, v in state.items():
             self.load_tensor(f"{prefix}.{k}", v)
+        self.__dict__.setdefault("loaded_prefixes", set()).add(prefix)      # session.py: a blob-loaded engine needs no re-upload
+
+    def has_state(self, *prefixes) -> bool:
+        """True when every given prefix ("dit", "vocos", "f5", "bigvgan", "igpt", "ivgan") has been uploaded (load_state / load_blob)."""
+        have = self.__dict__.get("loaded_prefixes", set())
+        return all(p in have for p in prefixes)
 
     def load_blob(self, path: str):
         """Upload every part of an engine blob written by checkpoint.save_blob / tools/convert_checkpoint.py."""

@@ -113,17 +113,27 @@ class _Graph:
         raise NotImplementedError
 
 
+def _has_state(engine, *prefixes):
+    """Whether the engine already holds these weight prefixes (capi.Engine.load_state / load_blob); stand-in engines may not know."""
+    f = getattr(engine, "has_state", None)
+    return bool(f and f(*prefixes))
+
+
 class _BigVGANGraph(_Graph):
     """BigVGAN/Export_BigVGAN.py:37-49,65-70."""
 
     def __init__(self, engine, precision, state=None):
         self.engine, self.precision = engine, precision
         self.cfg = BIGVGAN
-        self.inputs = (NodeArg("mel_features", "tensor(float)", [1, self.cfg.num_mels, "mel_features_len"]),)
+        self.inputs = (NodeArg("mel_features", "tensor(float16)" if precision == capi.F16 else "tensor(float)",
+                               [1, self.cfg.num_mels, "mel_features_len"]),)
         self.outputs = (NodeArg("generated_wav", "tensor(int16)", [1, 1, "generated_len"]),)
         state = state if state is not None else _checkpoints.get("bigvgan")
+        if state is None and _has_state(engine, "bigvgan"):
+            engine.bigvgan_build()           # weights came from an engine blob (Engine.load_blob): nothing to convert or upload
+            return
         if state is None:
-            raise RuntimeError("no BigVGAN checkpoint registered: call session.register_checkpoint('bigvgan', state)")
+            raise RuntimeError("no BigVGAN checkpoint registered: call session.register_checkpoint('bigvgan', state) or engine.load_blob(path)")
         engine.load_state("bigvgan", weights.bigvgan_engine_tensors(state))
         engine.bigvgan_build()
 
@@ -172,9 +182,12 @@ def load_indextts_gpt(engine, state=None, cfg=None):
     if state is None and key in _igpt_ready:
         return _igpt_ready[key]
     state = state if state is not None else _checkpoints.get("indextts_gpt")
-    if state is None:
-        raise RuntimeError("no IndexTTS GPT checkpoint registered: call session.register_checkpoint('indextts_gpt', state)")
-    engine.load_state("igpt", weights.igpt_engine_tensors(state, cfg))
+    if state is None and _has_state(engine, "igpt"):
+        pass                                 # uploaded from an engine blob (Engine.load_blob)
+    elif state is None:
+        raise RuntimeError("no IndexTTS GPT checkpoint registered: call session.register_checkpoint('indextts_gpt', state) or engine.load_blob(path)")
+    else:
+        engine.load_state("igpt", weights.igpt_engine_tensors(state, cfg))
     engine.indextts_gpt_build()
     _igpt_ready[key] = cfg
     return cfg
@@ -225,11 +238,19 @@ class ResidentKV(OrtValue):
     """out_key_<i> / out_value_<i> of IndexTTS_E: the cache stays in HBM; the reference loop only feeds these values back
     (Inference_IndexTTS_ONNX.py:766-767), so they are handles. ``numpy()`` materialises the reference layout on demand."""
 
-    def __init__(self, engine, layer, which, rows, heads):
+    def __init__(self, engine, layer, which, rows, heads, owner=None, generation=0):
         self._engine, self._layer, self._which, self._rows, self._heads = engine, layer, which, rows, heads
+        self._owner, self._generation = owner, generation      # the decode graph whose resident cache this handle views
+
+    def is_current(self):
+        """A handle is a VIEW of the resident cache: it is valid until the next IndexTTS_E call changes the cache."""
+        return self._owner is None or self._owner._generation == self._generation
 
     @property
     def _array(self):                     # OrtValue.numpy(v) -- the reference calls it unbound -- reads this attribute
+        if not self.is_current():
+            raise RuntimeError("stale KV handle: the resident cache has advanced since this out_key / out_value was returned "
+                               "(ORT would have kept a copy; read it with numpy() before the next IndexTTS_E call)")
         key, val = self._engine.indextts_gpt_kv_read(self._layer)
         return key if self._which == "key" else val
 
@@ -243,6 +264,7 @@ class _IndexTTSDecodeGraph(_Graph):
 
     def __init__(self, engine, precision, state=None):
         self.engine, self.precision = engine, precision
+        self._generation = 0                 # bumped by every call: handles of older calls are stale views
         self.cfg = cfg = load_indextts_gpt(engine, state)
         L, H = cfg.layers, cfg.heads
         self.inputs = tuple(NodeArg(f"in_key_{i}", "tensor(float)", [H, 64, "history_len"]) for i in range(L)) + tuple(
@@ -264,9 +286,24 @@ class _IndexTTSDecodeGraph(_Graph):
         hist = int(_as_numpy(feed["history_len"]).reshape(-1)[0])
         flag = int(_as_numpy(feed["attention_mask"]).reshape(-1)[0])
         pen = _as_numpy(feed["repeat_penality"]).astype(np.float32)
+        if hist > 0:
+            # the in_key / in_value feeds are not uploaded (the cache is resident), so they must BE the resident cache: handles of
+            # the latest call with history_len rows. ORT would honour any fed tensor; feeding older or edited caches is refused
+            # here instead of silently attending over something else.
+            for i in range(cfg.layers):
+                for name in (f"in_key_{i}", f"in_value_{i}"):
+                    v = feed.get(name)
+                    if v is None:
+                        continue
+                    if not isinstance(v, ResidentKV):
+                        raise ValueError(f"{name}: IndexTTS_E continues the RESIDENT cache; feed the out_key / out_value handles of the "
+                                         f"previous call (got {type(v).__name__})")
+                    if v._owner is not self or not v.is_current() or v._rows != hist:
+                        raise ValueError(f"{name}: stale or foreign KV handle (rows {v._rows}, history_len {hist})")
         last, mid, kv = self.engine.indextts_gpt_step(hidden, hist, flag, pen, precision=self.precision)
-        keys = [ResidentKV(self.engine, i, "key", kv, cfg.heads) for i in range(cfg.layers)]
-        vals = [ResidentKV(self.engine, i, "value", kv, cfg.heads) for i in range(cfg.layers)]
+        self._generation += 1
+        keys = [ResidentKV(self.engine, i, "key", kv, cfg.heads, self, self._generation) for i in range(cfg.layers)]
+        vals = [ResidentKV(self.engine, i, "value", kv, cfg.heads, self, self._generation) for i in range(cfg.layers)]
         return keys + vals + [np.array([kv], dtype=np.int64), last, mid]
 
 
@@ -279,6 +316,10 @@ def load_f5(engine, dit_state=None, vocos_state=None, cfg=F5):
         return
     dit_state = dit_state if dit_state is not None else _checkpoints.get("dit")
     vocos_state = vocos_state if vocos_state is not None else _checkpoints.get("vocos")
+    if dit_state is None and vocos_state is None and _has_state(engine, "dit", "vocos", "f5"):
+        engine.f5_build()                    # uploaded from an engine blob (Engine.load_blob)
+        _f5_ready[id(engine)] = True
+        return
     if dit_state is None or vocos_state is None:
         raise RuntimeError("no F5 checkpoint registered: call session.register_checkpoint('dit', ...) and ('vocos', ...)")
     engine.load_state("dit", weights.dit_engine_tensors(dit_state, cfg))
@@ -396,7 +437,9 @@ class InferenceSession:
                  device_id: int = 0, precision: str = "bf16", weights=None, **_ignored):
         self._kind = _kind_of(path_or_bytes)
         self._providers = ["B200ExecutionProvider"]
-        prec = {"fp32": capi.F32, "f32": capi.F32, "bf16": capi.BF16}[precision]
+        # "fp16" is the arithmetic BASELINE.json's configs name (the reference's fp16 exports): its BigVGAN graph reports a float16
+        # input, so a reference script feeds float16 mels (Export_BigVGAN.py:155-165), which run() widens again
+        prec = {"fp32": capi.F32, "f32": capi.F32, "bf16": capi.BF16, "fp16": capi.F16, "f16": capi.F16}[precision]
         self._graph = _GRAPHS[self._kind](get_engine(device_id), prec, weights)
         self._inputs_meta = list(self._graph.inputs)
         self._outputs_meta = list(self._graph.outputs)

@@ -35,13 +35,15 @@ def main():
         parts["vocos"] = weights.vocos_engine_tensors(checkpoint.vocos_from_checkpoint(_load(a.vocos)), config.F5)
     if a.bigvgan:
         parts["bigvgan"] = weights.bigvgan_engine_tensors(checkpoint.bigvgan_from_checkpoint(_load(a.bigvgan)))
-    if a.indextts_gpt:
-        parts["igpt"] = weights.igpt_engine_tensors(checkpoint.indextts_gpt_from_checkpoint(_load(a.indextts_gpt)), config.INDEXTTS_GPT)
+    if a.indextts_bigvgan and not a.indextts_gpt:
+        # gpt.final_norm is part of the vocoder graph (Export_IndexTTS.py:301): without it the blob's ivgan part cannot be built
+        ap.error("--indextts-bigvgan needs --indextts-gpt (the vocoder graph starts with gpt.final_norm)")
+    gpt_sd = checkpoint.indextts_gpt_from_checkpoint(_load(a.indextts_gpt)) if a.indextts_gpt else None
+    if gpt_sd is not None:
+        parts["igpt"] = weights.igpt_engine_tensors(gpt_sd, config.INDEXTTS_GPT)
     if a.indextts_bigvgan:
         sd = checkpoint.bigvgan_from_checkpoint(_load(a.indextts_bigvgan))
-        if a.indextts_gpt:            # gpt.final_norm feeds the vocoder graph (Export_IndexTTS.py:301)
-            g = checkpoint.indextts_gpt_from_checkpoint(_load(a.indextts_gpt))
-            sd["final_norm.weight"], sd["final_norm.bias"] = g["final_norm.weight"], g["final_norm.bias"]
+        sd["final_norm.weight"], sd["final_norm.bias"] = gpt_sd["final_norm.weight"], gpt_sd["final_norm.bias"]
         parts["ivgan"] = weights.ivgan_engine_tensors(sd, config.INDEXTTS_VOCODER)
     if not parts:
         ap.error("nothing to convert")
