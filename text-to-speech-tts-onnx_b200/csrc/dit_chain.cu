@@ -272,6 +272,7 @@ __device__ __forceinline__ bool get_phase(const ChainArgs& c, int pair, int ph, 
   return tm < c.rem;
 }
 
+template <bool FP8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS3, 1)
 dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
@@ -337,7 +338,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         const int row0 = rb * CH_ROWS + (int)rank * 128;
         const unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
           stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
@@ -366,7 +367,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       const int slice = P.slice;
       for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
           const CUtensorMap* map = ph == 0 ? (j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3)
                                            : (j == 0 ? &mC0 : j == 1 ? &mC1 : j == 2 ? &mC2 : &mC3);
           const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
@@ -395,7 +396,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       if (!get_phase(c, pair, ph, P)) continue;
       for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
           const uint32_t idesc = idesc_f16kind(256, js.w, js.fp8 ? 1 : c.f16);      // e4m3 shares format code 0 with fp16
           const int chunks = js.chunks;
           for (int st = 0; st < js.nsubt; ++st, ++t) {
@@ -412,7 +413,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
               const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_stage_lo;
               const uint32_t accum = ck > 0 ? 1u : 0u;
               if (elect_one()) {
-                if (js.fp8) {
+                if (FP8 && js.fp8) {
                   umma2_f8_lohi(d0, a_lo + 0, b_lo + 0, idesc, accum);
                   umma2_f8_lohi(d0, a_lo + 2, b_lo + 2, idesc, 1u);
                   umma2_f8_lohi(d0, a_lo + 4, b_lo + 4, idesc, 1u);
@@ -484,10 +485,10 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       float c_row = myrow < c.R ? __ldcg(c.rowscale + myrow) : 1.0f;
       float rho = 1.0f, rmu = 0.0f;
       for (int j = 0; j < njobs; ++j) {
-        const JobShape js = job_shape(j, c.D, c.FF, P.tsz, c.fp8);
+        const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
         a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.chunks;
         const float* wscale = !js.fp8 ? nullptr : j == 1 ? c.sw_ff1 : c.sw_qkv;
-        const bool next_fp8 = c.fp8 && (j == 0 || j == 2);      // the operand this job emits feeds an e4m3 GEMM
+        const bool next_fp8 = FP8 && (j == 0 || j == 2);      // the operand this job emits feeds an e4m3 GEMM
         const bool fold = j == 0 || (j == 2 && c.has_qkv);      // this job's epilogue emits the next GEMM's A operand
         const float* bias = j == 0 ? c.b_out : j == 1 ? c.v_ff1 : j == 2 ? c.b_ff2 : c.v_qkv;
         const float* gate = j == 0 ? c.gate_msa : j == 1 ? c.u_ff1 : j == 2 ? c.gate_mlp : c.u_qkv;
@@ -527,13 +528,13 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           tc_fence_after();
           if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
           if (j == 0 || j == 2)
-            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
+            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true, false, FP8>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
                                                           smem_stat, slice * js.n_pair, q * 32 + lane, 1.0f, 0.0f, emit);
           else if (j == 1)
-            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true, FP8>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
                                                                     0ull, nullptr, 0, 0, rho, rmu, emit);
           else
-            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true, FP8>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
                                                                 0ull, nullptr, 0, 0, rho, rmu, emit);
           tc_fence_before();
           __syncwarp();
@@ -543,9 +544,11 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         if (fold) {
           // x tiles (TMA stores) and the emitted 16-bit rows (plain stores) of this CTA are complete: publish the LayerNorm
           // partials and hand everything to the team with ONE counter (the next GEMM's A producer and its epilogue wait on it)
+          // (the x tiles still in flight through the TMA unit are nobody else's business: only this warp reads them back, two
+          // jobs later; they are drained after the signal, off the team's critical path)
           publish_stats(c, P.tsz, rb, (int)rank, slice, j == 0 ? 0 : 1, smem_stat, tid);
-          epi_tma_drain(lane);
           team_signal(flags + (j == 0 ? F_N16 : F_N16B), tid);
+          epi_tma_drain(lane);
         } else if (j == 2) {
           // last block: the final LayerNorm feeds proj_out (a separate GEMM) -> normalise in a second pass as before
           ln_phase(c, P.tsz, rb, (int)rank, slice, 1, c.scale_nxt, c.shift_nxt, c.n16b, flags + F_STAT2, flags + F_N16B, smem_stat, warp, lane);
@@ -572,7 +575,8 @@ int resident_pairs() {
   static int pairs = -1;
   static std::once_flag once;
   std::call_once(once, [] {
-    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     int dev = 0, sms = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -696,8 +700,12 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   if (d.has_qkv) tc_encode_map2d(&mQKo, d.qk16, 2, (uint64_t)2 * d.D, (uint64_t)d.R, (uint64_t)2 * d.D, 32, 32);
   else mQKo = mFFo;
   const int grid_pairs = std::max(c.teams * c.team, c.rem * c.team1);
-  launch_pdl(dit_chain_kernel, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
-             mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
+  if (d.fp8)
+    launch_pdl(dit_chain_kernel<true>, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
+               mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
+  else
+    launch_pdl(dit_chain_kernel<false>, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
+               mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
   B2_LAUNCH_CHECK();
   count_launch();
 }

@@ -339,7 +339,7 @@ struct EpiEmit {
                                   // (AFFINE epilogues reuse the field: per-column multiplier of the accumulator = e4m3 weight scales)
   float c = 1.0f;              // the row's scale (a stale 1 / std estimate: keeps fp16 / e4m3 in range)
 };
-template <int TK, int ACT, bool STATS, bool AFFINE = false>
+template <int TK, int ACT, bool STATS, bool AFFINE = false, bool FP8 = false>
 __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtensorMap* map_out, const CUtensorMap* map_res, EpiTile& et,
                                                   uint32_t taddr, int row0, int n0, int cb_first, int cb_step, int lane,
                                                   const float* s_bias, const float* s_gate, float& rsum, float& rsq,
@@ -384,7 +384,7 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
             const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
             bi.x = fmaf(-rmu, u.x, bi.x); bi.y = fmaf(-rmu, u.y, bi.y); bi.z = fmaf(-rmu, u.z, bi.z); bi.w = fmaf(-rmu, u.w, bi.w);
             float4 r4 = make_float4(rho, rho, rho, rho);
-            if (emit.s_mul != nullptr) {
+            if (FP8 && emit.s_mul != nullptr) {
               const float4 sw = lds128(smem_u32(emit.s_mul) + (uint32_t)(cb + k * 4) * 4u);
               r4.x *= sw.x; r4.y *= sw.y; r4.z *= sw.z; r4.w *= sw.w;
             }
@@ -408,7 +408,7 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
       if (AFFINE) {
         const float4 u = lds128(gate_s + (uint32_t)(cb + k * 4) * 4u);
         float4 r4 = make_float4(rho, rho, rho, rho);
-        if (emit.s_mul != nullptr) {                             // e4m3 weights: their per-output-channel scales
+        if (FP8 && emit.s_mul != nullptr) {                      // e4m3 weights: their per-output-channel scales
           const float4 sw = lds128(smem_u32(emit.s_mul) + (uint32_t)(cb + k * 4) * 4u);
           r4.x *= sw.x; r4.y *= sw.y; r4.z *= sw.z; r4.w *= sw.w;
         }
@@ -468,7 +468,7 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
         rsum = 0.f; rsq = 0.f;
       }
     }
-    if (TK == TK_RES_F32 && emit.row8 != nullptr) {
+    if (FP8 && TK == TK_RES_F32 && emit.row8 != nullptr) {
       // e4m3 operand of the next GEMM: 32 columns = 32 bytes per lane; cvt saturates at +-448
       const uint32_t mul_s = smem_u32(emit.s_mul);
       uint32_t w[8];
