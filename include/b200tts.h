@@ -49,6 +49,9 @@ int b200tts_synchronize(b200tts_engine* e);
 int b200tts_set_option(b200tts_engine* e, const char* name, int value);
 /* Number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
 unsigned long long b200tts_launch_count(void);
+/* Host arithmetic only (no GPU needed; unit-tested on CPU): the row-block schedule the fused DiT chain would use for `row_blocks`
+ * blocks of 256 rows on `resident_pairs` CTA pairs -> plan5 = {team, teams, blocks in phase 0, remaining blocks, team of phase 1}. */
+int b200tts_debug_chain_plan(int row_blocks, int resident_pairs, int* plan5);
 
 /* ---- weights (replace the .onnx initializers written by Export_F5.py / Export_BigVGAN.py) ------------ */
 /* name = "<model>.<reference state_dict name>", model in {bigvgan, dit, vocos}; fp32, row-major, rank <= 4.

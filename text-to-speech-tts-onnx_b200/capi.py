@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200tts_synchronize": (_int, [_vp]),
     "b200tts_set_option": (_int, [_vp, ctypes.c_char_p, _int]),
     "b200tts_launch_count": (ctypes.c_ulonglong, []),
+    "b200tts_debug_chain_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "b200tts_load_tensor": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
     "b200tts_load_tensor_device": (_int, [_vp, ctypes.c_char_p, _vp, _c_i64, _int]),
     "b200tts_bigvgan_build": (_int, [_vp]),

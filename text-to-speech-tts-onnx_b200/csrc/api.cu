@@ -11,6 +11,7 @@
 #include "aa_act.cuh"
 #include "attention_tc.cuh"
 #include "bigvgan.cuh"
+#include "dit_chain.cuh"
 #include "engine.cuh"
 #include "f5.cuh"
 #include "gpt2.cuh"
@@ -93,6 +94,13 @@ extern "C" {
 const char* b200tts_last_error(void) { return g_last_error.c_str(); }
 
 unsigned long long b200tts_launch_count(void) { return g_launch_count; }
+
+int b200tts_debug_chain_plan(int row_blocks, int resident_pairs, int* plan5) {
+  if (plan5 == nullptr || row_blocks <= 0 || resident_pairs <= 0) return 1;
+  const DitChainPlan pl = dit_chain_plan(row_blocks, resident_pairs);
+  plan5[0] = pl.team; plan5[1] = pl.teams; plan5[2] = pl.nrb0; plan5[3] = pl.rem; plan5[4] = pl.team1;
+  return 0;
+}
 
 int b200tts_create(int device, b200tts_engine** out) {
   return guarded([&] {

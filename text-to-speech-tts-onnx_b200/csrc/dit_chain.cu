@@ -603,6 +603,37 @@ int pick_team(int nrb, int pairs) {
 
 }  // namespace
 
+// plan: phase 0 = whole rounds of row blocks at team size t0, phase 1 = the remaining blocks with the largest team that still
+// gives each its own team; the (t0, t1) pair with the lowest modelled time wins. Pure host arithmetic (tests/test_chain_plan_cpu.py).
+DitChainPlan dit_chain_plan(int nrb, int pairs) {
+  DitChainPlan pl;
+  pl.team = 1; pl.teams = nrb < pairs ? nrb : pairs; pl.nrb0 = nrb; pl.rem = 0; pl.team1 = 1; pl.cost = 1e300;
+  if (nrb <= 0 || pairs <= 0) return pl;
+  // time of one round of row blocks by team size, relative (measured: a round of 74 blocks at T = 1 takes 340 us, a block
+  // shared by 8 pairs 57 us; profiles/r02 chain timelines)
+  static const double round_cost[4] = {1.0, 0.55, 0.30, 0.17};
+  auto lg = [](int t) { return t == 1 ? 0 : t == 2 ? 1 : t == 4 ? 2 : 3; };
+  auto team_for = [&](int blocks, int tmin) {                    // largest team size that gives every block its own team
+    int t = CH_MAX_TEAM;
+    while (t > tmin && blocks > pairs / t) t /= 2;
+    return t;
+  };
+  for (int t0 = 1; t0 <= CH_MAX_TEAM; t0 *= 2) {
+    const int teams0 = pairs / t0;
+    if (teams0 < 1) break;
+    const int full = nrb / teams0, rem = nrb - full * teams0;
+    const int t1 = rem > 0 ? team_for(rem, t0) : t0;
+    if (rem > pairs / t1) continue;                              // (only for t0 = 8: the remainder is another round)
+    const double cost = full * round_cost[lg(t0)] + (rem > 0 ? round_cost[lg(t1)] : 0.0);
+    if (cost < pl.cost - 1e-9) {
+      pl.cost = cost;
+      if (full == 0) { pl.team = t1; pl.teams = rem; pl.nrb0 = nrb; pl.rem = 0; pl.team1 = 1; }
+      else { pl.team = t0; pl.teams = teams0; pl.nrb0 = full * teams0; pl.rem = rem; pl.team1 = t1; }
+    }
+  }
+  return pl;
+}
+
 size_t dit_chain_stats_floats(int R) { return (size_t)ceil_div(R, CH_ROWS) * 2 * CH_ROWS * CH_MAX_TEAM * 2; }
 size_t dit_chain_flag_words(int R) { return (size_t)ceil_div(R, CH_ROWS) * CH_NFLAGS; }
 
@@ -624,40 +655,15 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
            d.w_ff2->Cin == d.FF && (!d.has_qkv || (d.w_qkv->N == 3 * d.D && d.w_qkv->Cin == d.D)), "dit_chain: weight shapes");
   ChainArgs c;
   c.R = d.R; c.nrb = ceil_div(d.R, CH_ROWS); c.has_qkv = d.has_qkv; c.f16 = d.f16; c.D = d.D; c.FF = d.FF;
-  // plan: phase 0 = whole rounds of row blocks at team size t0, phase 1 = the remaining blocks with the largest team that still
-  // gives each its own team; the (t0, t1) pair with the lowest modelled time wins (B200TTS_CHAIN_TEAM forces one phase)
   const int pairs = resident_pairs();
-  c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1;
-  if (getenv("B200TTS_CHAIN_TEAM") != nullptr) {
+  if (getenv("B200TTS_CHAIN_TEAM") != nullptr) {                  // experiment override: one phase at the forced team size
+    c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1;
     c.team = pick_team(c.nrb, pairs);
     const int max_teams = pairs / c.team;
     c.teams = c.nrb < max_teams ? c.nrb : max_teams;
   } else {
-    // time of one round of row blocks by team size, relative (measured: a round of 74 blocks at T = 1 takes 340 us, a block
-    // shared by 8 pairs 57 us; profiles/r02 chain timelines)
-    static const double round_cost[4] = {1.0, 0.55, 0.30, 0.17};
-    auto lg = [](int t) { return t == 1 ? 0 : t == 2 ? 1 : t == 4 ? 2 : 3; };
-    auto team_for = [&](int blocks, int tmin) {                    // largest team size that gives every block its own team
-      int t = CH_MAX_TEAM;
-      while (t > tmin && blocks > pairs / t) t /= 2;
-      return t;
-    };
-    double best = 1e300;
-    for (int t0 = 1; t0 <= CH_MAX_TEAM; t0 *= 2) {
-      const int teams0 = pairs / t0;
-      const int full = c.nrb / teams0, rem = c.nrb - full * teams0;
-      const int t1 = rem > 0 ? team_for(rem, t0) : t0;
-      if (rem > pairs / t1) continue;                              // (only for t0 = 8: the remainder is another round)
-      const double cost = full * round_cost[lg(t0)] + (rem > 0 ? round_cost[lg(t1)] : 0.0);
-      if (cost < best - 1e-9) {
-        best = cost;
-        if (full == 0) { c.team = t1; c.teams = rem; c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1; }
-        else { c.team = t0; c.teams = teams0; c.nrb0 = full * teams0; c.rem = rem; c.team1 = t1; }
-      }
-    }
-    if (best > 1e299) {                                            // cannot happen (t0 = 1 always qualifies); keep a safe default
-      c.team = 1; c.teams = c.nrb < pairs ? c.nrb : pairs; c.nrb0 = c.nrb; c.rem = 0; c.team1 = 1;
-    }
+    const DitChainPlan pl = dit_chain_plan(c.nrb, pairs);
+    c.team = pl.team; c.teams = pl.teams; c.nrb0 = pl.nrb0; c.rem = pl.rem; c.team1 = pl.team1;
   }
   c.x = d.x; c.n16 = d.n16; c.ff16 = d.ff16; c.n16b = d.n16b;
   c.b_out = d.b_out; c.gate_msa = d.gate_msa; c.shift_mlp = d.shift_mlp; c.scale_mlp = d.scale_mlp; c.b_ff1 = d.b_ff1; c.b_ff2 = d.b_ff2;

@@ -49,6 +49,10 @@ struct DitChain {
   unsigned long long* trace = nullptr;   // optional [CTAs][64] %globaltimer stamps of the hand-offs (debug: B200TTS_CHAIN_TRACE=<file>)
 };
 
+// The row-block schedule of one launch (dit_chain.cu, "two-phase"): phase 0 = `teams` teams of `team` CTA pairs walk row blocks
+// [0, nrb0) in whole rounds; phase 1 = the `rem` remaining blocks, one team of `team1` pairs each. cost = modelled time in rounds at T = 1.
+struct DitChainPlan { int team, teams, nrb0, rem, team1; double cost; };
+DitChainPlan dit_chain_plan(int nrb, int pairs);
 bool dit_chain_supported(int D, int FF, int H);      // shapes the kernel is specialised for + enough co-resident CTA pairs
 size_t dit_chain_stats_floats(int R);
 size_t dit_chain_flag_words(int R);
