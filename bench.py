@@ -760,8 +760,9 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
                     help="operand type of the tensor-core engine (BASELINE.json's configurations name fp16); fp32 = the SIMT parity engine")
     ap.add_argument("--no-chain", action="store_true", help="DiT blocks as separate launches instead of the fused row-block chain")
-    ap.add_argument("--fp8", action="store_true", help="optional lower-fidelity mode: ff1 and q|k|v of the fused chain with e4m3 operands "
-                                                       "(PCM SNR ~32 dB instead of ~62 dB against the fp32 reference; NOT the default)")
+    ap.add_argument("--fp8", type=int, nargs="?", const=2, default=0, choices=[0, 1, 2],
+                    help="optional lower-fidelity mode of the fused chain (NOT the default): 1 = ff1 and q|k|v with e4m3 operands (PCM SNR "
+                         "~32 dB against the fp32 reference instead of ~62 dB), 2 (bare --fp8) = ff2 as well (~30.5 dB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the attached f5 / bigvgan measurements of the default run")
     args = ap.parse_args()
@@ -803,8 +804,8 @@ def main():
     if args.no_chain:
         eng.set_option("dit_chain", 0)
     if args.fp8:
-        eng.set_option("dit_fp8", 1)
-        dtype += "+e4m3(ff1,qkv)"
+        eng.set_option("dit_fp8", args.fp8)
+        dtype += "+e4m3(ff1,qkv)" if args.fp8 == 1 else "+e4m3(ff1,ff2,qkv)"
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
     H = Harness(torch, dist, stream, world)

@@ -42,8 +42,9 @@ int b200tts_synchronize(b200tts_engine* e);
  *   "dit_chain"   1 (default): every F5 DiT block runs as attention + ONE fused row-block kernel; 0: seven launches per block
  *   "cuda_graphs" 1 (default): repeated calls of one shape replay a captured CUDA graph; 0: enqueue kernel by kernel
  *   "bigvgan_branches" 1 (default): the three resblocks of a BigVGAN stage run as concurrent branches; 0: one after the other
- *   "dit_fp8"     0 (default); 1: ff1 and q|k|v of the fused chain take e4m3 operands (tcgen05 kind::f8f6f4). A lower-fidelity mode
- *                 (PCM SNR ~32 dB against the fp32 reference instead of ~62 dB for fp16), 11 % faster on eight utterances
+ *   "dit_fp8"     0 (default); 1: ff1 and q|k|v of the fused chain take e4m3 operands (tcgen05 kind::f8f6f4); 2: ff2 as well.
+ *                 Lower-fidelity modes (PCM SNR ~32 / ~30.5 dB against the fp32 reference instead of ~62 dB for fp16), 9 / 15 %
+ *                 faster on eight utterances
  * Results do not depend on cuda_graphs or bigvgan_branches (bit-identical); dit_chain changes how the LayerNorm is applied
  * (folded into the GEMM epilogues, same tolerance class). */
 int b200tts_set_option(b200tts_engine* e, const char* name, int value);

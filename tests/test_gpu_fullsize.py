@@ -150,21 +150,23 @@ def test_f5_config3_vs_reference_golden(f5_engine, gf):
 
 
 def test_f5_config3_fp8_option_vs_reference_golden(f5_engine, gf):
-    """Engine option dit_fp8: ff1 and q|k|v of the fused chain with e4m3 operands (tcgen05 kind::f8f6f4, per-row activation scale,
-    per-output-channel weight scale, fp32 accumulation). An optional lower-fidelity mode: measured on B200 mel cosine 0.99993,
+    """Engine option dit_fp8 (1 / 2): ff1 and q|k|v (and ff2) of the fused chain with e4m3 operands (tcgen05 kind::f8f6f4, per-row
+    activation scale -- a static one for the hidden activation --, per-output-channel weight scale, fp32 accumulation). An optional lower-fidelity mode: measured on B200 mel cosine 0.99993,
     generated-mel cosine 0.99981, PCM SNR 32.4 dB at N = 1126 (oracle/fp8_study.py predicts 29.7 dB for e4m3 operands in these
     GEMMs); the bars below are what the mode must keep. Switching it off again restores the fp16 numbers."""
     audio, ids, maxd, noise = synth.f5_inputs(int(gf["input_seed"]), int(gf["audio_len"]), int(gf["n_text"]))
     N = int(maxd[0])
     ref_len = int(gf["f5_ref_signal_len"])
     try:
-        f5_engine.set_option("dit_fp8", 1)
-        pcm, mel = f5_engine.f5_synthesize(audio, ids, N, noise, precision=capi.F16, return_mel=True)
-        assert np.isfinite(mel).all()
-        assert cosine(mel, gf["f5_mel"]) >= 0.9998, cosine(mel, gf["f5_mel"])
-        assert cosine(mel[:, ref_len:], gf["f5_mel"][:, ref_len:]) >= 0.9995
-        assert snr_db(gf["f5_pcm"], pcm) >= 28.0, snr_db(gf["f5_pcm"], pcm)
-        assert snr_db(gf["f5_pcm"], pcm) < 50.0            # the option really changed the arithmetic
+        # level 1: ff1 + q|k|v (32.4 dB measured); level 2: ff2 as well, fed by an e4m3 hidden activation (30.5 dB measured)
+        for level, cos_floor, gen_floor, snr_floor in ((1, 0.9998, 0.9995, 28.0), (2, 0.9997, 0.9993, 26.0)):
+            f5_engine.set_option("dit_fp8", level)
+            pcm, mel = f5_engine.f5_synthesize(audio, ids, N, noise, precision=capi.F16, return_mel=True)
+            assert np.isfinite(mel).all()
+            assert cosine(mel, gf["f5_mel"]) >= cos_floor, (level, cosine(mel, gf["f5_mel"]))
+            assert cosine(mel[:, ref_len:], gf["f5_mel"][:, ref_len:]) >= gen_floor
+            assert snr_db(gf["f5_pcm"], pcm) >= snr_floor, (level, snr_db(gf["f5_pcm"], pcm))
+            assert snr_db(gf["f5_pcm"], pcm) < 50.0            # the option really changed the arithmetic
     finally:
         f5_engine.set_option("dit_fp8", 0)
     pcm, mel = f5_engine.f5_synthesize(audio, ids, N, noise, precision=capi.F16, return_mel=True)

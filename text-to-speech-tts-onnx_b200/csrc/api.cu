@@ -155,7 +155,7 @@ int b200tts_set_option(b200tts_engine* e, const char* name, int value) {
     if (n == "dit_chain") E.dit_chain = value != 0;
     else if (n == "cuda_graphs") E.graphs.enabled = value != 0;
     else if (n == "bigvgan_branches") E.bigvgan_branches = value != 0;
-    else if (n == "dit_fp8") E.dit_fp8 = value != 0;
+    else if (n == "dit_fp8") E.dit_fp8 = value < 0 ? 0 : (value > 2 ? 2 : value);
     else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs, bigvgan_branches, dit_fp8)");
     E.graphs.clear();                                    // captured graphs bake the code path in
   });

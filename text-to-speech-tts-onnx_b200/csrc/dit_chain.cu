@@ -128,11 +128,12 @@ __device__ __forceinline__ void team_signal(unsigned* flag, int tid) {
 // Job j of the chain for a team of `team` pairs: the pair's n_pair output columns are walked in nsubt sub-tiles of w columns
 // (one M = 256, N = w accumulator each; b_rows = w / 2 weight rows per CTA and 64-channel chunk).
 constexpr float CH_FP8_GAIN = 8.0f;                  // extra scale of an e4m3 A operand: centres N(0, 1)-like rows in the e4m3 range
+constexpr float CH_FP8_HGAIN = 16.0f;                // static scale of the e4m3 hidden activation (GELU output; saturates at 28): f5.cu folds 1 / it into gate / bias of ff2
 struct JobShape { int K, N, n_pair, w, nsubt, b_rows, chunks, kstep, fp8; };
 __device__ __host__ __forceinline__ JobShape job_shape(int j, int D, int FF, int team, int fp8 = 0) {
   JobShape s;
   s.K = j == 2 ? FF : D;
-  s.fp8 = fp8 && (j == 1 || j == 3) ? 1 : 0;
+  s.fp8 = (fp8 && (j == 1 || j == 3)) || (fp8 >= 2 && j == 2) ? 1 : 0;      // level 1: ff1, q|k|v; level 2: ff2 as well
   s.kstep = s.fp8 ? 128 : BK;                       // operand elements per 128-byte swizzle row = per pipeline chunk
   s.chunks = s.K / s.kstep;
   s.N = j == 0 ? D : j == 1 ? FF : j == 2 ? D : 3 * D;
@@ -272,7 +273,7 @@ __device__ __forceinline__ bool get_phase(const ChainArgs& c, int pair, int ph, 
   return tm < c.rem;
 }
 
-template <bool FP8>
+template <int FP8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS3, 1)
 dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                  const __grid_constant__ CUtensorMap mA2, const __grid_constant__ CUtensorMap mA3,
@@ -338,7 +339,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         const int row0 = rb * CH_ROWS + (int)rank * 128;
         const unsigned* flags = c.flags + (size_t)rb * CH_NFLAGS;
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, FP8);
           const CUtensorMap* map = j == 0 ? &mA0 : j == 1 ? &mA1 : j == 2 ? &mA2 : &mA3;
           stamp(c, 8 + 8 * j + 0);
           if (j > 0) {
@@ -367,7 +368,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       const int slice = P.slice;
       for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, FP8);
           const CUtensorMap* map = ph == 0 ? (j == 0 ? &mB0 : j == 1 ? &mB1 : j == 2 ? &mB2 : &mB3)
                                            : (j == 0 ? &mC0 : j == 1 ? &mC1 : j == 2 ? &mC2 : &mC3);
           const uint32_t tx = 2u * (uint32_t)(js.b_rows * 128);
@@ -396,7 +397,7 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       if (!get_phase(c, pair, ph, P)) continue;
       for (int rb = P.rb0; rb < P.rb1; rb += P.step) {
         for (int j = 0; j < njobs; ++j) {
-          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
+          const JobShape js = job_shape(j, c.D, c.FF, P.tsz, FP8);
           const uint32_t idesc = idesc_f16kind(256, js.w, js.fp8 ? 1 : c.f16);      // e4m3 shares format code 0 with fp16
           const int chunks = js.chunks;
           for (int st = 0; st < js.nsubt; ++st, ++t) {
@@ -485,9 +486,9 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
       float c_row = myrow < c.R ? __ldcg(c.rowscale + myrow) : 1.0f;
       float rho = 1.0f, rmu = 0.0f;
       for (int j = 0; j < njobs; ++j) {
-        const JobShape js = job_shape(j, c.D, c.FF, P.tsz, (FP8 ? 1 : 0));
+        const JobShape js = job_shape(j, c.D, c.FF, P.tsz, FP8);
         a.Cin = js.K; a.N = js.N; a.BN = js.w; a.kchunks = js.chunks;
-        const float* wscale = !js.fp8 ? nullptr : j == 1 ? c.sw_ff1 : c.sw_qkv;
+        const float* wscale = !js.fp8 || j == 2 ? nullptr : j == 1 ? c.sw_ff1 : c.sw_qkv;      // (ff2: folded into its gate / bias vectors)
         const bool next_fp8 = FP8 && (j == 0 || j == 2);      // the operand this job emits feeds an e4m3 GEMM
         const bool fold = j == 0 || (j == 2 && c.has_qkv);      // this job's epilogue emits the next GEMM's A operand
         const float* bias = j == 0 ? c.b_out : j == 1 ? c.v_ff1 : j == 2 ? c.b_ff2 : c.v_qkv;
@@ -517,6 +518,11 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
         } else if (wscale) {
           emit.s_mul = s_mul;                                    // AFFINE epilogue: the e4m3 weights' per-column scales
         }
+        emit.c = fold ? emit.c : 0.0f;                           // (non-fold jobs: 0 = no e4m3 hidden activation)
+        if (FP8 >= 2 && j == 1) {                                // ff1 writes the hidden activation as e4m3 for an e4m3 ff2
+          emit.c = CH_FP8_HGAIN;
+          emit.row8 = myrow < c.R ? reinterpret_cast<uint8_t*>(c.ff16) + (size_t)myrow * c.FF : nullptr;
+        }
         float rsum = 0.f, rsq = 0.f;
         for (int st = 0; st < js.nsubt; ++st, ++t) {
           const uint32_t buf = t & 1u;
@@ -528,13 +534,13 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
           tc_fence_after();
           if (tid == 0 && st == 0) stamp(c, 8 + 8 * j + 4);
           if (j == 0 || j == 2)
-            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true, false, FP8>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
+            epilogue_rows_tma<TK_RES_F32, ACT_NONE, true, false, (FP8 != 0)>(a, &mX, &mX, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq, x_policy,
                                                           smem_stat, slice * js.n_pair, q * 32 + lane, 1.0f, 0.0f, emit);
           else if (j == 1)
-            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true, FP8>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+            epilogue_rows_tma<TK_ACT16, ACT_GELU_TANH, false, true, (FP8 != 0)>(a, &mFFo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
                                                                     0ull, nullptr, 0, 0, rho, rmu, emit);
           else
-            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true, FP8>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
+            epilogue_rows_tma<TK_ROPE16, ACT_NONE, false, true, (FP8 != 0)>(a, &mQKo, nullptr, et, taddr, row0, n0, e * 32, 64, lane, s_bias, s_gate, rsum, rsq,
                                                                 0ull, nullptr, 0, 0, rho, rmu, emit);
           tc_fence_before();
           __syncwarp();
@@ -575,8 +581,9 @@ int resident_pairs() {
   static int pairs = -1;
   static std::once_flag once;
   std::call_once(once, [] {
-    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     int dev = 0, sms = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -671,6 +678,7 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   c.qk16 = d.qk16; c.rope_cs = d.rope_cs; c.rope_rows = d.rope_rows > 0 ? d.rope_rows : 1; c.rowinfo = d.rowinfo; c.vt_out = d.vt_out; c.vt_ld = d.vt_ld; c.vt_heads = d.vt_heads;
   B2_CHECK(d.u_ff1 && d.v_ff1 && d.rowscale && (!d.has_qkv || (d.u_qkv && d.v_qkv)), "dit_chain: folded-LayerNorm vectors");
   B2_CHECK(!d.fp8 || (d.w8_ff1 && d.sw_ff1 && (!d.has_qkv || (d.w8_qkv && d.sw_qkv))), "dit_chain: e4m3 weights / scales");
+  B2_CHECK(d.fp8 < 2 || d.w8_ff2, "dit_chain: e4m3 ff2 weights");
   c.fp8 = d.fp8; c.sw_ff1 = d.sw_ff1; c.sw_qkv = d.sw_qkv;
   c.u_ff1 = d.u_ff1; c.v_ff1 = d.v_ff1; c.u_qkv = d.u_qkv; c.v_qkv = d.v_qkv; c.rowscale = d.rowscale;
   c.stats = d.stats; c.flags = d.flags; c.trace = d.trace;
@@ -679,7 +687,7 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   const void* a_ptr[4] = {d.att16, d.n16, d.ff16, d.n16b};
   const int a_k[4] = {d.D, d.D, d.FF, d.D};
   for (int j = 0; j < 4; ++j) {
-    if (d.fp8 && (j == 1 || j == 3))     // e4m3 rows of D bytes in the (2 D byte) rows' buffer, densely packed
+    if ((d.fp8 && (j == 1 || j == 3)) || (d.fp8 >= 2 && j == 2))     // e4m3 rows of K bytes in the 16-bit rows' buffer, densely packed
       tc_encode_map_u8(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
     else
       tc_encode_map(&mA[j], a_ptr[j], (uint64_t)a_k[j], (uint64_t)d.R, 1, (uint64_t)a_k[j], (uint64_t)d.R * a_k[j], 128);
@@ -690,10 +698,11 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
     for (int j = 0; j < 4; ++j) {
       CUtensorMap* mp = ph == 0 ? &mB[j] : &mC[j];
       const JobShape js = job_shape(j == 3 && !d.has_qkv ? 0 : j, d.D, d.FF, ph == 0 ? c.team : c.team1, d.fp8);
-      if (d.fp8 && (j == 1 || (j == 3 && d.has_qkv))) {
-        const void* w8 = j == 1 ? d.w8_ff1 : d.w8_qkv;
-        const uint64_t n_rows = j == 1 ? (uint64_t)d.FF : (uint64_t)3 * d.D;
-        tc_encode_map_u8(mp, w8, (uint64_t)d.D, n_rows, 1, (uint64_t)d.D, n_rows * d.D, (uint32_t)js.b_rows);
+      if ((d.fp8 && (j == 1 || (j == 3 && d.has_qkv))) || (d.fp8 >= 2 && j == 2)) {
+        const void* w8 = j == 1 ? d.w8_ff1 : j == 2 ? d.w8_ff2 : d.w8_qkv;
+        const uint64_t n_rows = j == 1 ? (uint64_t)d.FF : j == 2 ? (uint64_t)d.D : (uint64_t)3 * d.D;
+        const uint64_t kk = j == 2 ? (uint64_t)d.FF : (uint64_t)d.D;
+        tc_encode_map_u8(mp, w8, kk, n_rows, 1, kk, n_rows * kk, (uint32_t)js.b_rows);
       } else {
         tc_encode_map(mp, ws[j]->w.p, (uint64_t)ws[j]->Cin, (uint64_t)ws[j]->N, 1, (uint64_t)ws[j]->ldc, (uint64_t)ws[j]->N * ws[j]->ldc,
                       (uint32_t)js.b_rows);
@@ -706,12 +715,9 @@ void dit_chain(const DitChain& d, cudaStream_t stream) {
   if (d.has_qkv) tc_encode_map2d(&mQKo, d.qk16, 2, (uint64_t)2 * d.D, (uint64_t)d.R, (uint64_t)2 * d.D, 32, 32);
   else mQKo = mFFo;
   const int grid_pairs = std::max(c.teams * c.team, c.rem * c.team1);
-  if (d.fp8)
-    launch_pdl(dit_chain_kernel<true>, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
-               mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
-  else
-    launch_pdl(dit_chain_kernel<false>, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
-               mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
+  auto kern = d.fp8 >= 2 ? dit_chain_kernel<2> : d.fp8 == 1 ? dit_chain_kernel<1> : dit_chain_kernel<0>;
+  launch_pdl(kern, dim3((unsigned)(grid_pairs * 2)), dim3(NTHREADS3), (size_t)CH_SMEM, stream, mA[0], mA[1], mA[2], mA[3],
+             mB[0], mB[1], mB[2], mB[3], mC[0], mC[1], mC[2], mC[3], mX, mFFo, mQKo, c);
   B2_LAUNCH_CHECK();
   count_launch();
 }

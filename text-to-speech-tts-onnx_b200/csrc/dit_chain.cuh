@@ -40,8 +40,9 @@ struct DitChain {
   float* rowscale = nullptr;
   // optional e4m3 mode of ff1 and q|k|v (tcgen05 kind::f8f6f4): weights [N][D] bytes with per-output-channel scales (u / v above
   // must then be computed from the DEQUANTISED weights); the A operands are emitted as e4m3 by the epilogues that produce x
-  int fp8 = 0;
-  const void *w8_ff1 = nullptr, *w8_qkv = nullptr;
+  int fp8 = 0;                       // 1: ff1 + q|k|v; 2: ff2 as well (its A operand = the hidden activation written as 16 * GELU(.) in
+                                     // e4m3 by ff1's epilogue; gate_mlp / b_ff2 must then carry the weight scale: gate * sw / 16, b * 16 / sw)
+  const void *w8_ff1 = nullptr, *w8_qkv = nullptr, *w8_ff2 = nullptr;
   const float *sw_ff1 = nullptr, *sw_qkv = nullptr;
   // team synchronisation scratch (sizes below); `flags` must be zero when the kernel starts
   float* stats = nullptr;

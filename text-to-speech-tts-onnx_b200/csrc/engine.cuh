@@ -102,7 +102,7 @@ struct Engine {
   bool dit_chain = true;                   // F5 DiT blocks through the fused row-block chain kernel (dit_chain.cu); b200tts_set_option
   // ff1 and q|k|v of the fused chain with e4m3 operands (tcgen05 kind::f8f6f4, fp32 accumulation): an OPTIONAL lower-fidelity
   // mode (PCM SNR ~30 dB instead of ~60, oracle/fp8_study.py); off by default. b200tts_set_option("dit_fp8", 1)
-  bool dit_fp8 = false;
+  int dit_fp8 = 0;                         // 0 off, 1 ff1 + q|k|v, 2 ff2 as well
   // BigVGAN: the three resblocks of a stage (kernel sizes 3 / 7 / 11, bigvgan.py:396-399) are independent until their sum, so
   // they run as three concurrent branches (this stream + two auxiliary ones, forked / joined with events; inside a captured
   // graph these become parallel branches). b200tts_set_option("bigvgan_branches", 0) serialises them again.

@@ -63,8 +63,8 @@ struct DiTLayer {
   bool fold_ready[2] = {false, false};
   // optional e4m3 mode of ff1 / q|k|v (engine option dit_fp8): weights quantised per output channel, their scales, and the
   // folded-LayerNorm vectors recomputed from the dequantised weights
-  DevBuf<uint8_t> w8_ff1, w8_qkv;
-  DevBuf<float> sw_ff1, sw_qkv, fu1_8, fv1_8, fuq_8, fvq_8;
+  DevBuf<uint8_t> w8_ff1, w8_qkv, w8_ff2;
+  DevBuf<float> sw_ff1, sw_qkv, sw_ff2, fu1_8, fv1_8, fuq_8, fvq_8, gate8, bias8;      // gate8 / bias8: ff2's gate_mlp / bias with the weight scale
   bool fp8_ready = false;
 };
 
@@ -688,6 +688,10 @@ void f5_steps(Engine& e, int first, int count, int precision) {
           L.fuq_8.alloc((size_t)m.nfe * 3 * D); L.fvq_8.alloc((size_t)m.nfe * 3 * D);
           fold_vectors(L.w8_ff1.p, D, D, 2, L.mod.p + 4 * D, L.mod.p + 3 * D, 6 * D, L.ff1.bias.p, L.fu1_8.p, L.fv1_8.p, m.FF, m.nfe, s, L.sw_ff1.p);
           fold_vectors(L.w8_qkv.p, D, D, 2, L.mod.p + D, L.mod.p, 6 * D, L.qkv.bias.p, L.fuq_8.p, L.fvq_8.p, 3 * D, m.nfe, s, L.sw_qkv.p);
+          // level 2 (ff2): weights [D][FF], the hidden activation is written as 16 * GELU(.) in e4m3 (dit_chain.cu: CH_FP8_HGAIN)
+          L.w8_ff2.alloc((size_t)D * m.FF); L.sw_ff2.alloc(D); L.gate8.alloc((size_t)m.nfe * D); L.bias8.alloc(D);
+          quantize_rows_e4m3(L.ff2.w_ref, D, m.FF, L.w8_ff2.p, m.FF, L.sw_ff2.p, s);
+          fold_gate_bias(L.mod.p + 5 * D, 6 * D, L.ff2.bias.p, L.sw_ff2.p, 16.0f, L.gate8.p, L.bias8.p, D, m.nfe, s);
           L.fp8_ready = true;
         }
       }
@@ -772,7 +776,8 @@ void f5_steps(Engine& e, int first, int count, int precision) {
           c.qk16 = m.qk16.p; c.rope_cs = m.rope_cs16.p; c.rope_rows = N; c.rowinfo = rowinfo; c.vt_out = m.vT16.p; c.vt_ld = m.Npad; c.vt_heads = m.H;
         }
         if (e.dit_fp8) {
-          c.fp8 = 1;
+          c.fp8 = e.dit_fp8 >= 2 ? 2 : 1;
+          if (c.fp8 == 2) { c.w8_ff2 = L.w8_ff2.p; c.gate_mlp = L.gate8.p + (size_t)step * D; c.b_ff2 = L.bias8.p; }
           c.w8_ff1 = L.w8_ff1.p; c.sw_ff1 = L.sw_ff1.p;
           c.u_ff1 = L.fu1_8.p + (size_t)step * m.FF; c.v_ff1 = L.fv1_8.p + (size_t)step * m.FF;
           if (!last) {

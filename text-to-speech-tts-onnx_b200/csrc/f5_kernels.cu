@@ -380,6 +380,21 @@ void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, 
   fold_vectors_kernel<<<N, 128, 0, s>>>(w16, wscale, ldc, K, f16, scale, shift, mod_ld, bias, u, v, N, nfe);
   LAUNCHED();
 }
+// e4m3 ff2 (dit_chain.cu, fp8 level 2): acc = sum_k e4m3(h_k * hgain) * e4m3(W_jk / sw_j), so gate * (acc * sw_j / hgain + b_j)
+// = gate8 * (acc + bias8) with gate8[t][j] = gate[t][j] * sw_j / hgain and bias8[j] = b_j * hgain / sw_j
+__global__ void fold_gate_bias_kernel(const float* __restrict__ gate, int mod_ld, const float* __restrict__ bias, const float* __restrict__ sw,
+                                      float hgain, float* __restrict__ gate8, float* __restrict__ bias8, int N, int nfe) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const float s = sw[j] / hgain;
+  bias8[j] = bias[j] / s;
+  for (int t = 0; t < nfe; ++t) gate8[(size_t)t * N + j] = gate[(size_t)t * mod_ld + j] * s;
+}
+void fold_gate_bias(const float* gate, int mod_ld, const float* bias, const float* sw, float hgain, float* gate8, float* bias8, int N, int nfe,
+                    cudaStream_t s) {
+  fold_gate_bias_kernel<<<ceil_div(N, 128), 128, 0, s>>>(gate, mod_ld, bias, sw, hgain, gate8, bias8, N, nfe);
+  LAUNCHED();
+}
 void quantize_rows_e4m3(const float* w, int N, int K, void* q, int ldq, float* scale, cudaStream_t s) {
   quantize_rows_e4m3_kernel<<<N, 128, 0, s>>>(w, K, reinterpret_cast<uint8_t*>(q), ldq, scale);
   LAUNCHED();

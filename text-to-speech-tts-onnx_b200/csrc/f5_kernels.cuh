@@ -18,6 +18,9 @@ void fold_vectors(const void* w16, int ldc, int K, int f16, const float* scale, 
                   float* v, int N, int nfe, cudaStream_t s, const float* wscale = nullptr);
 // per-output-channel e4m3 quantisation of an fp32 weight [N][K]: q [N][ldq] bytes, scale [N] (W ~ q * scale)
 void quantize_rows_e4m3(const float* w, int N, int K, void* q, int ldq, float* scale, cudaStream_t s);
+// gate8[t][j] = gate[t][j] * sw[j] / hgain (t < nfe, gate rows mod_ld apart), bias8[j] = bias[j] * hgain / sw[j]
+void fold_gate_bias(const float* gate, int mod_ld, const float* bias, const float* sw, float hgain, float* gate8, float* bias8, int N, int nfe,
+                    cudaStream_t s);
 // nn.LayerNorm(D, eps) with affine (text ConvNeXtV2 block, modules.py:248)
 void layernorm_affine(const float* x, const float* w, const float* b, float* out, int R, int D, float eps, cudaStream_t s);
 void layernorm_affine_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* out, int R, int D, float eps, cudaStream_t s);

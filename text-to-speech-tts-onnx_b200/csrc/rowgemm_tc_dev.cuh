@@ -501,6 +501,22 @@ __device__ __forceinline__ void epilogue_rows_tma(const TcArgs& a, const CUtenso
         *reinterpret_cast<uint4*>(emit.row + n + k * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
+    if (FP8 && TK == TK_ACT16 && emit.c != 0.0f) {
+      // e4m3 hidden activation (the A operand of an e4m3 ff2): emit.c * act(.), 32 bytes per lane straight to global memory
+      // (emit.row8 = this lane's row, null beyond the last row); no 16-bit tile is written
+      if (emit.row8 != nullptr) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t lo = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(emit.c * f[k * 4 + 0], emit.c * f[k * 4 + 1]), __NV_SATFINITE, __NV_E4M3);
+          const uint32_t hi = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(emit.c * f[k * 4 + 2], emit.c * f[k * 4 + 3]), __NV_SATFINITE, __NV_E4M3);
+          w[k] = lo | (hi << 16);
+        }
+        *reinterpret_cast<uint4*>(emit.row8 + n) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(emit.row8 + n + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      continue;
+    }
     if (lane == 0) bulk_wait_read0();                          // the previous block's store has read the staging tile
     __syncwarp();
     if (TK == TK_RES_F32) {

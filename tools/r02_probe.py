@@ -219,7 +219,7 @@ def sec_f5_fp8():
         g = dict(np.load(os.path.join(GOLD, gname)))
         audio, text_ids, maxd, noise = synth.f5_inputs(int(g["input_seed"]), int(g["audio_len"]), int(g["n_text"]))
         N = int(maxd[0])
-        for fp8 in (0, 1):
+        for fp8 in (0, 1, 2):
             eng.set_option("dit_fp8", fp8)
             pcm, mel = eng.f5_synthesize(audio, text_ids, N, noise, precision=capi.F16, return_mel=True)
             r = int(g[ref_key])
@@ -236,7 +236,7 @@ def sec_f5_fp8():
         ids = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).cuda()
         noise = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).cuda()
         pcm = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
-        for fp8 in (0, 1):
+        for fp8 in (0, 1, 2):
             eng.set_option("dit_fp8", fp8)
 
             def run():
