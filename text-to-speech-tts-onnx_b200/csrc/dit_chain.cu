@@ -12,6 +12,9 @@
 // hand-offs inside a team are release / acquire counters in global memory -- no grid-wide barrier, no kernel boundary.
 //   T = 8 for one utterance (9 row blocks x 8 pairs = 144 CTAs: every GEMM is one sub-tile per pair),
 //   T = 1 for a batch of 8 (71 row blocks, one pair each: 4 / 8 / 4 / 12 sub-tiles per GEMM, hand-offs stay inside the pair).
+// A launch runs in two phases (dit_chain_plan): whole rounds of row blocks at one team size, then the remaining blocks with a
+// larger team each, so that a block count just above a multiple of the resident pairs does not cost a whole extra round.
+// Optional e4m3 operands (template FP8 = 1: ff1 and q|k|v, 2: ff2 as well) on tcgen05 kind::f8f6f4; see DESIGN.md 3a item 8.
 //
 // Per CTA: 11 warps as in rowgemm_tc.cu (0-7 epilogue, 8 A producer, 9 MMA issuer (leader CTA only), 10 B producer).
 //   job 0  out  : A = att16  K = D    epilogue: x += gate_msa * (acc + b); n16 = c x (1 + scale_mlp); LN partials
