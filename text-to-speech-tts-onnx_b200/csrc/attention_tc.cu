@@ -24,8 +24,9 @@
 // What bounds it (profiles/r02/attention_r02.md): not one pipe. Removing the exponentials, the MMAs and the loads altogether
 // (debug switches, since deleted) only shortened a launch from 20.2 to 15.9 us: ~380 instructions per warp and key block at an
 // IPC of 0.5 per scheduler (stall reasons: fixed-latency `wait` 24 %, scoreboard 27 %, MIO / math throttle 10 %), i.e. issue-
-// and latency-bound softmax code. 4 threads per row (twice the warps, half the work each) and FMA-pipe exponentials both
-// measured within noise of the default; kept as switches (B200TTS_ATTN_G, B200TTS_ATTN_POLY).
+// and latency-bound softmax code. 4 threads per row (twice the warps, half the work each) measured within noise of 2; half of the
+// exponentials on the FMA pipes (POLY = 2, the default) is worth 5 % of the kernel in the batched benchmark. Both are switches
+// (B200TTS_ATTN_G, B200TTS_ATTN_POLY).
 #include "attention_tc.cuh"
 
 #include <cstdio>
@@ -53,7 +54,7 @@ constexpr int XCH_BYTES = 2 * 4 * BQ * 4;       // [block parity][key group][row
 constexpr int KV_STAGES = 2;
 constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCH_BYTES + 128;      // 84 KB
 constexpr float RESCALE_TAU = 8.0f;             // log2 units
-constexpr int ATTN_POLY_DEFAULT = 1;
+constexpr int ATTN_POLY_DEFAULT = 2;      // configs[3]: 3569 ms per step against 3617 (POLY 1) / 3609 (POLY 0), profiles/r02/probe_zl
 constexpr int ATTN_G_DEFAULT = 2;
 // tensor-memory columns of a CTA
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
