@@ -164,7 +164,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// POLY: of every 4 score pairs, POLY are exponentiated on the FMA pipes (0, 1 or 2)
+// POLY: of every 4 score pairs, POLY are exponentiated on the FMA pipes (0 .. 3)
 template <bool F16, int POLY, int G>
 __global__ void __launch_bounds__(nthreads(G), 2) attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk,
                                                               const __grid_constant__ CUtensorMap map_v, const AttnArgs a) {
@@ -435,11 +435,11 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
     // V^T: [S*H][64][ldv] -> dims {N keys, 64 d, S*H}, box {64 keys, 64 d, 1}
     tc_encode_map(&map_v, vT, (uint64_t)N, (uint64_t)HD, (uint64_t)S * H, (uint64_t)ldv, (uint64_t)HD * ldv, HD);
   }
-  // exponentials on the FMA pipes: B200TTS_ATTN_POLY = 0, 1 or 2 of every 4 score pairs (read once)
+  // exponentials on the FMA pipes: B200TTS_ATTN_POLY = 0 .. 3 of every 4 score pairs (read once)
   static const int poly = [] {
     const char* e = getenv("B200TTS_ATTN_POLY");
     const int p = e ? atoi(e) : ATTN_POLY_DEFAULT;
-    return p < 0 ? 0 : (p > 2 ? 2 : p);
+    return p < 0 ? 0 : (p > 3 ? 3 : p);
   }();
   // softmax threads per query row: B200TTS_ATTN_G = 2 or 4 (read once)
   static const int gsel = [] {
@@ -448,16 +448,16 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
     return g == 2 ? 0 : 1;
   }();
   using KernelFn = void (*)(CUtensorMap, CUtensorMap, AttnArgs);
-  static const KernelFn kernels[2][2][3] = {
-      {{attn_tc_kernel<false, 0, 2>, attn_tc_kernel<false, 1, 2>, attn_tc_kernel<false, 2, 2>},
-       {attn_tc_kernel<true, 0, 2>, attn_tc_kernel<true, 1, 2>, attn_tc_kernel<true, 2, 2>}},
-      {{attn_tc_kernel<false, 0, 4>, attn_tc_kernel<false, 1, 4>, attn_tc_kernel<false, 2, 4>},
-       {attn_tc_kernel<true, 0, 4>, attn_tc_kernel<true, 1, 4>, attn_tc_kernel<true, 2, 4>}}};
+  static const KernelFn kernels[2][2][4] = {
+      {{attn_tc_kernel<false, 0, 2>, attn_tc_kernel<false, 1, 2>, attn_tc_kernel<false, 2, 2>, attn_tc_kernel<false, 3, 2>},
+       {attn_tc_kernel<true, 0, 2>, attn_tc_kernel<true, 1, 2>, attn_tc_kernel<true, 2, 2>, attn_tc_kernel<true, 3, 2>}},
+      {{attn_tc_kernel<false, 0, 4>, attn_tc_kernel<false, 1, 4>, attn_tc_kernel<false, 2, 4>, attn_tc_kernel<false, 3, 4>},
+       {attn_tc_kernel<true, 0, 4>, attn_tc_kernel<true, 1, 4>, attn_tc_kernel<true, 2, 4>, attn_tc_kernel<true, 3, 4>}}};
   static std::once_flag once;
   std::call_once(once, [] {
     for (int g = 0; g < 2; ++g)
       for (int t = 0; t < 2; ++t)
-        for (int p = 0; p < 3; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[g][t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        for (int p = 0; p < 4; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[g][t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   });
   const KernelFn kernel = kernels[gsel][f16 ? 1 : 0][poly];
   AttnArgs a{N, H, out, H * HD, d_seq_off, d_seq_len, nullptr};
