@@ -19,6 +19,8 @@ Plus size-independent properties of the path:
     CTA-pair kernel and multi-wave schedules, none of which may change a row's result),
   * every output is finite and uses the int16 range sensibly.
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -230,6 +232,42 @@ def test_f5_config3_batch_equals_single(f5_engine):
     # the reference region (first 563 frames) is driven by the same conditioning as the generated one: both move off the noise
     moved = (mel_b - noise.view(U, N, FCFG.n_mels)).abs().mean(dim=(1, 2))
     assert bool((moved > 1e-3).all())
+
+
+def test_f5_two_phase_chain_schedule_equals_single(f5_engine):
+    """Nine uniform config-3 utterances = 80 row blocks: the fused chain walks 74 of them in phase 0 (one CTA pair each) and the last
+    6 in phase 1 (a team of 8 pairs each, other weight maps) -- the schedule configs[3] runs with (593 = 8 x 74 + 1 blocks). The first
+    utterance (phase 0) and the last one (its rows lie in the phase-1 blocks) must equal their single runs (team of 8, one phase)."""
+    U, L, n_text, steps = 9, 144000, 150, 2
+    plan = (ctypes.c_int * 5)()
+    assert capi.load_library().b200tts_debug_chain_plan((2 * U * 1126 + 255) // 256, 74, plan) == 0
+    assert list(plan) == [1, 74, 74, 6, 8]
+    ins = [synth.f5_inputs(170 + i, L, n_text) for i in range(U)]
+    N = int(ins[0][2][0])
+    ns = 256 * (N - (L // 256 + 1) - 1)
+    audio = torch.from_numpy(np.stack([a.reshape(-1) for a, _, _, _ in ins])).cuda()
+    ids = torch.from_numpy(np.stack([t.reshape(-1) for _, t, _, _ in ins])).cuda()
+    noise = torch.from_numpy(np.stack([n.reshape(-1) for _, _, _, n in ins])).cuda()
+    pcm_b = torch.zeros((U, ns), dtype=torch.int16, device="cuda")
+    mel_b = torch.zeros((U, N, FCFG.n_mels), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for level in (0, 2):                                     # fp16 operands, and the e4m3 option (its phase-1 weight maps differ too)
+        try:
+            f5_engine.set_option("dit_fp8", level)
+            f5_engine.f5_synthesize_batch_device(U, audio.data_ptr(), L, ids.data_ptr(), n_text, N, noise.data_ptr(), pcm_b.data_ptr(),
+                                                 precision=capi.F16, n_steps=steps, mel_ptr=mel_b.data_ptr())
+            f5_engine.synchronize()
+            assert bool(torch.isfinite(mel_b).all())
+            for u in (0, U - 1):
+                pcm_1 = torch.zeros((ns,), dtype=torch.int16, device="cuda")
+                mel_1 = torch.zeros((N, FCFG.n_mels), dtype=torch.float32, device="cuda")
+                torch.cuda.synchronize()
+                f5_engine.f5_synthesize_device(audio[u].data_ptr(), L, ids[u].data_ptr(), n_text, N, noise[u].data_ptr(), pcm_1.data_ptr(),
+                                               precision=capi.F16, n_steps=steps, mel_ptr=mel_1.data_ptr())
+                f5_engine.synchronize()
+                np.testing.assert_allclose(mel_b[u].cpu().numpy(), mel_1.cpu().numpy(), rtol=0, atol=1e-5)
+        finally:
+            f5_engine.set_option("dit_fp8", 0)
 
 
 def test_f5_config3_full_run_is_deterministic(f5_engine):
