@@ -453,12 +453,11 @@ void attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, int ldv, __n
        {attn_tc_kernel<true, 0, 2>, attn_tc_kernel<true, 1, 2>, attn_tc_kernel<true, 2, 2>, attn_tc_kernel<true, 3, 2>}},
       {{attn_tc_kernel<false, 0, 4>, attn_tc_kernel<false, 1, 4>, attn_tc_kernel<false, 2, 4>, attn_tc_kernel<false, 3, 4>},
        {attn_tc_kernel<true, 0, 4>, attn_tc_kernel<true, 1, 4>, attn_tc_kernel<true, 2, 4>, attn_tc_kernel<true, 3, 4>}}};
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  if (once.first())
     for (int g = 0; g < 2; ++g)
       for (int t = 0; t < 2; ++t)
         for (int p = 0; p < 4; ++p) B2_CUDA(cudaFuncSetAttribute(kernels[g][t][p], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  });
   const KernelFn kernel = kernels[gsel][f16 ? 1 : 0][poly];
   AttnArgs a{N, H, out, H * HD, d_seq_off, d_seq_len, nullptr};
   static DevBuf<unsigned long long> trace_buf;

@@ -1,5 +1,6 @@
 // Shared helpers for libb200tts (sm_100a only).
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -73,6 +74,22 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   B2_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 #endif
+
+// Function attributes (cudaFuncSetAttribute) belong to the CURRENT DEVICE: a process that drives several GPUs (session.get_engine(d))
+// must set them once per device, not once per process (ADVICE r01 flagged the same pattern in gpt2.cu). first() is true the first
+// time it is called with a given device current.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    std::lock_guard<std::mutex> g(mu);
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 // Bumped by every device (re)allocation / free of a DevBuf: captured CUDA graphs bake buffer addresses into their nodes,
 // so a cached graph is only replayed while the epoch it was captured under still holds (engine.cuh: GraphCache).

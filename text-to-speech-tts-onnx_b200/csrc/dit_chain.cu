@@ -581,18 +581,16 @@ dit_chain_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant_
 
 // CTA pairs that can be resident at once: one CTA per SM (shared memory), and clusters of two pack the TPCs exactly.
 int resident_pairs() {
-  static int pairs = -1;
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  if (once.first()) {
     B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
     B2_CUDA(cudaFuncSetAttribute(dit_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-    int dev = 0, sms = 0;
-    B2_CUDA(cudaGetDevice(&dev));
-    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    pairs = sms / 2;
-  });
-  return pairs;
+  }
+  int dev = 0, sms = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return sms / 2;
 }
 
 // pairs per row block: the split that finishes nrb row blocks soonest on `pairs` resident pairs (a pair's share of a block's

@@ -666,10 +666,9 @@ TcArgs make_args(const RowGemm& p, int BN) {
 template <int KIND, int ACT, bool BRES>
 void launch_one(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& a,
                 const Tc3Sched& sc) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  if (once.first())
     B2_CUDA(cudaFuncSetAttribute(rowgemm_tc3_kernel<KIND, ACT, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  });
   launch_pdl(rowgemm_tc3_kernel<KIND, ACT, BRES>, dim3(grid), dim3(NTHREADS3), (size_t)smem, stream, map_a, map_b, a, sc);
 }
 template <int KIND, int ACT>
@@ -682,10 +681,9 @@ void launch_kernel(int grid, int smem, cudaStream_t stream, const CUtensorMap& m
 template <int KIND, int ACT>
 void launch_2sm(int grid, int smem, cudaStream_t stream, const CUtensorMap& map_a, const CUtensorMap& map_b, const TcArgs& a,
                 const Tc3Sched& sc) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  if (once.first())
     B2_CUDA(cudaFuncSetAttribute(rowgemm_tc2sm_kernel<KIND, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  });
   launch_pdl(rowgemm_tc2sm_kernel<KIND, ACT>, dim3(grid), dim3(NTHREADS3), (size_t)smem, stream, map_a, map_b, a, sc);
 }
 
