@@ -123,6 +123,28 @@ def bigvgan_work(cfg, B, T):
             "aa_elems": B * aa_elems, "audio_s": B * cfg.out_samples(T) / cfg.sample_rate}
 
 
+def bigvgan_stage_table(cfg, B, T, profile_ms, pk, bytes_per_elem=2):
+    """Per upsampling stage: the resblock work against BOTH rooflines SURVEY.md 8(d) names. FLOPs = the 18 convs of the stage;
+    bytes = the survey's layer-fused model M1, 49 * C * L elements per stage (every conv reads its input and writes its output once,
+    the anti-aliased activations ride along, + the residual / accumulate reads); time = the stage's conv launches plus its
+    activation launches (`profile_ms`: the per-kernel event times of one serialised pass). `bound` = whichever floor is higher."""
+    rows, L, C = [], T, cfg.upsample_initial_channel
+    for i, u in enumerate(cfg.upsample_rates):
+        C //= 2
+        L *= u
+        ms = profile_ms.get(f"bigvgan.resconv.s{i}", 0.0) + profile_ms.get(f"bigvgan.aa_snake.s{i}", 0.0)
+        if ms <= 0:
+            continue
+        flops = B * sum(6 * 2.0 * C * C * rk * L for rk in cfg.resblock_kernel_sizes)
+        m1 = B * 49.0 * C * L * bytes_per_elem
+        t_tensor, t_hbm = flops / (pk["bf16_tflops_sustained"] * 1e12) * 1e3, m1 / (pk["hbm_gbs"] * 1e9) * 1e3
+        rows.append({"stage": i, "channels": C, "samples": L, "ms": round(ms, 4), "conv_ms": round(profile_ms.get(f"bigvgan.resconv.s{i}", 0.0), 4),
+                     "activation_ms": round(profile_ms.get(f"bigvgan.aa_snake.s{i}", 0.0), 4),
+                     "tensor_frac": round(t_tensor / ms, 4), "hbm_frac_m1": round(t_hbm / ms, 4),
+                     "bound": "tensor" if t_tensor >= t_hbm else "hbm", "floor_ms": round(max(t_tensor, t_hbm), 4)})
+    return rows
+
+
 def f5_work(cfg, N, ref_len):
     """Algorithmic FLOPs of the DiT loop for one utterance of N frames (both CFG rows)."""
     D, FF = cfg.dim, cfg.dim * cfg.ff_mult
@@ -347,6 +369,8 @@ def bench_bigvgan(args, H, eng, rank, B, T, prec, steps, warmup, sampler=None):
                            "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                            "avg_launch_ms": conv["ms"] / max(conv["launches"], 1),
                            "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
+    if prec != capi.F32:
+        res["stages"] = bigvgan_stage_table(cfg, B, T, res["profile_ms"], pk)
     if aa["ms"] > 0:
         per_elem = 4.0 if prec != capi.F32 else 8.0          # 16 bit in + 16 bit out on the fast path
         gbs = work["aa_elems"] * per_elem / (aa["ms"] / 1e3) / 1e9
