@@ -428,8 +428,12 @@ def _kind_of(path: str) -> str:
                 "bigvgan"):
         if key in base:
             return key
-    raise ValueError(f"cannot tell which hot-path graph '{path}' is (expected BigVGAN / F5_Preprocess / "
-                     "F5_Transformer / F5_Decode in the file name)")
+    if "indextts_a" in base:
+        raise NotImplementedError(f"'{path}': the IndexTTS conditioning graph A (Export_IndexTTS.py:74-200) is not part of this engine "
+                                  "(its conformer / perceiver / ECAPA modules are not in the reference tree, DESIGN.md 7): run it where the "
+                                  "reference runs it, once per voice, and feed its outputs to the IndexTTS_D / IndexTTS_F sessions")
+    raise ValueError(f"cannot tell which hot-path graph '{path}' is (expected BigVGAN / F5_Preprocess / F5_Transformer / F5_Decode / "
+                     "IndexTTS_B .. IndexTTS_F in the file name)")
 
 
 class InferenceSession:
