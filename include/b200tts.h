@@ -42,10 +42,11 @@ int b200tts_synchronize(b200tts_engine* e);
  *   "dit_chain"   1 (default): every F5 DiT block runs as attention + ONE fused row-block kernel; 0: seven launches per block
  *   "cuda_graphs" 1 (default): repeated calls of one shape replay a captured CUDA graph; 0: enqueue kernel by kernel
  *   "bigvgan_branches" 1 (default): the three resblocks of a BigVGAN stage run as concurrent branches; 0: one after the other
+ *   "ragged_embed" 1 (default): the input embedding of a ragged batch is one launch over all DiT rows; 0: two launches per utterance
  *   "dit_fp8"     0 (default); 1: ff1 and q|k|v of the fused chain take e4m3 operands (tcgen05 kind::f8f6f4); 2: ff2 as well.
  *                 Lower-fidelity modes (PCM SNR ~32 / ~30.5 dB against the fp32 reference instead of ~62 dB for fp16), 9 / 15 %
  *                 faster on eight utterances
- * Results do not depend on cuda_graphs or bigvgan_branches (bit-identical); dit_chain changes how the LayerNorm is applied
+ * Results do not depend on cuda_graphs or bigvgan_branches (bit-identical) nor on ragged_embed (same dot products per row); dit_chain changes how the LayerNorm is applied
  * (folded into the GEMM epilogues, same tolerance class). */
 int b200tts_set_option(b200tts_engine* e, const char* name, int value);
 /* Number of kernels this library has launched so far in this process (bench.py: gpu_launches). */

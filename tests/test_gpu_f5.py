@@ -371,6 +371,35 @@ def test_ragged_batch_equals_single_utterances(f5, g):
     assert snr_db(want_pcm.numpy().reshape(-1), vocs[0]) > 45.0
 
 
+def test_ragged_embed_option_changes_nothing(f5, g):
+    """b200tts_set_option("ragged_embed", 1): the input embedding of a ragged batch as ONE launch over all DiT rows (x gathered
+    into the row order) instead of two launches per utterance -- the same numbers (a row's dot products do not depend on the tile
+    it lands in), and still equal to single utterances."""
+    from b200tts import weights as W
+    f5.load_state("bigvgan", W.bigvgan_engine_tensors(synth.bigvgan_state(1234)))
+    f5.bigvgan_build()
+    specs = [(9000, 13, 36 + 41), (16384, 20, 130), (12345, 17, 49 + 70), (7000, 9, 61)]
+    audios, texts, Ns, noises = [], [], [], []
+    for i, (L, nt, N) in enumerate(specs):
+        a, t, _, _ = synth.f5_inputs(150 + i, audio_len=L, n_text=nt)
+        audios.append(a.reshape(-1)); texts.append(t.reshape(-1)); Ns.append(N)
+        noises.append(np.random.default_rng(190 + i).standard_normal((N, 100), dtype=np.float32))
+    runs = {}
+    try:
+        for flag in (0, 1):
+            f5.set_option("ragged_embed", flag)
+            runs[flag] = f5.f5_bigvgan_pipeline_ragged(audios, texts, Ns, noises, precision=capi.F16, n_steps=6, with_vocos=True, return_mel=True)
+        f5.set_option("ragged_embed", 1)
+        single = f5.f5_bigvgan_pipeline(audios[3][None], texts[3][None], Ns[3], noises[3][None], precision=capi.F16, n_steps=6,
+                                        with_vocos=True, return_mel=True)
+    finally:
+        f5.set_option("ragged_embed", 0 if os.environ.get("B200TTS_RAGGED_EMBED", "1") == "0" else 1)        # the default is on
+    for u in range(len(specs)):
+        np.testing.assert_allclose(runs[1][2][u], runs[0][2][u], rtol=0, atol=2e-5)
+        assert snr_db(runs[0][0][u], runs[1][0][u]) >= 60.0 and snr_db(runs[0][1][u], runs[1][1][u]) >= 60.0
+    np.testing.assert_allclose(runs[1][2][3], single[2][0], rtol=0, atol=2e-5)
+
+
 def test_frontend_wav_and_text_in_wav_out(f5, g, tmp_path):
     """The reference script's call surface (F5-TTS-ONNX-Inference.py:13-39,223-315): a wav file + reference text + text to speak in,
     a wav file out. The front end's ids / duration / noise drive the same engine call a direct caller would make."""

@@ -121,6 +121,8 @@ int b200tts_create(int device, b200tts_engine** out) {
     e->impl.graphs.enabled = !(g != nullptr && g[0] == '0');
     const char* ch = getenv("B200TTS_CHAIN");           // B200TTS_CHAIN=0: DiT blocks as separate launches (A/B of dit_chain.cu)
     e->impl.dit_chain = !(ch != nullptr && ch[0] == '0');
+    const char* re = getenv("B200TTS_RAGGED_EMBED");    // 0 / 1: per-utterance / one-launch input embedding of a ragged batch
+    if (re != nullptr) e->impl.ragged_embed = re[0] != '0';
     *out = e.release();
   });
 }
@@ -156,7 +158,8 @@ int b200tts_set_option(b200tts_engine* e, const char* name, int value) {
     else if (n == "cuda_graphs") E.graphs.enabled = value != 0;
     else if (n == "bigvgan_branches") E.bigvgan_branches = value != 0;
     else if (n == "dit_fp8") E.dit_fp8 = value < 0 ? 0 : (value > 2 ? 2 : value);
-    else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs, bigvgan_branches, dit_fp8)");
+    else if (n == "ragged_embed") E.ragged_embed = value != 0;
+    else fail("set_option: unknown option '" + n + "' (known: dit_chain, cuda_graphs, bigvgan_branches, dit_fp8, ragged_embed)");
     E.graphs.clear();                                    // captured graphs bake the code path in
   });
 }

@@ -609,7 +609,7 @@ void reserve_step(F5Model& m, bool fast) {
     m.chain_flags.reserve(dit_chain_flag_words((int)R) * (size_t)m.depth);
     m.qk16.reserve(R * 2 * m.D); m.vT16.reserve((size_t)2 * m.U * m.H * m.hd * m.Npad); m.ff16.reserve(R * m.FF);
     m.rope_cs16.reserve((size_t)m.N * m.hd);
-    m.x16.reserve((size_t)m.Ntot * round_up(m.n_mels, 8));
+    m.x16.reserve((m.ragged ? R : (size_t)m.Ntot) * round_up(m.n_mels, 8));    // ragged: one x row per DiT row (ragged_embed)
   } else {
     m.c32.reserve(R * m.D); m.n32.reserve(R * m.D); m.att32.reserve(R * m.D); m.qkv32.reserve(R * 3 * m.D);
     m.ff32.reserve(R * m.FF);
@@ -718,15 +718,31 @@ void f5_steps(Engine& e, int first, int count, int precision) {
       // tensor-core form: x of all U utterances as one batched A operand (16-bit, rows padded to 8), one launch per CFG row
       // (both rows share x); the epilogue adds the step-invariant half and also writes the 16-bit copy conv_pos reads
       const int ldx = (int)round_up(m.n_mels, 8);
-      { ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, m.Ntot, m.n_mels, ldx, s, f16); }
+      // ragged batch, option ragged_embed: the 1-tap embedding GEMM does not care where a sequence ends, so x is gathered into
+      // the DiT row order (both CFG sequences of an utterance read its tokens) and ALL 2 * Ntot rows are one launch instead of two
+      // per utterance; the grouped convolutions below keep their per-utterance launches (a sequence's length is their batch stride)
+      const bool one_embed = m.ragged && e.ragged_embed;
       lin_prepare_tc(e, m.wx, f16);
+      if (one_embed) {
+        { ProfScope ps(e.prof, "f5.cast", s); cast_pad_rows_ragged(m.noise.p, m.x16.p, m.rowinfo.p, m.seq_off.p, R, m.n_mels, ldx, s, f16); }
+        RowGemm p;
+        p.x = m.x16.p; p.x_bstride = (long)R * ldx; p.ldx = ldx; p.Lin = R;
+        p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = R; p.B = 1;
+        p.out = m.h.p; p.o_bstride = (long)R * D; p.ldo = D;
+        p.res = m.cproj.p;
+        p.out2 = m.h16.p; p.f16 = f16;
+        ProfScope ps(e.prof, "f5.embed_x", s);
+        rowgemm_tc(p, m.wx.tc[f16], s);
+      } else {
+        ProfScope ps(e.prof, "f5.cast", s); cast_pad_f32_to_bf16(m.noise.p, m.x16.p, m.Ntot, m.n_mels, ldx, s, f16);
+      }
       // uniform batch: one launch per CFG row over all utterances and one grouped conv over all 2U sequences; ragged batch:
       // the same per utterance (its two sequences), since a sequence's length is the batch stride of these launches
       const int groups = m.ragged ? m.U : 1;
       for (int gi = 0; gi < groups; ++gi) {
         const int Ng = m.ragged ? m.Nu[gi] : N, Ug = m.ragged ? 1 : m.U;
         const size_t t0 = m.ragged ? (size_t)m.tok_off[gi] : 0, r0 = 2 * t0;
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 2 && !one_embed; ++b) {
           RowGemm p;
           p.x = m.x16.p + t0 * ldx; p.x_bstride = (long)Ng * ldx; p.ldx = ldx; p.Lin = Ng;
           p.Cin = m.n_mels; p.N = D; p.taps = 1; p.M = Ng; p.B = Ug;

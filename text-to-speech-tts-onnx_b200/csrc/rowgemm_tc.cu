@@ -548,7 +548,29 @@ __global__ void cast_pad_kernel(const float* __restrict__ in, __nv_bfloat16* __r
   reinterpret_cast<uint16_t*>(out)[i] = pack16(c < C ? in[r * C + c] : 0.f, f16);
 }
 
+// the same for the 2 * Ntot DiT rows of a ragged batch: row r = (sequence, position) reads the token row of its utterance, which
+// both CFG sequences of the utterance share (sequence 2u starts at DiT row 2 * tok_off[u])
+__global__ void cast_pad_rows_ragged_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const int2* __restrict__ rowinfo,
+                                            const int* __restrict__ seq_off, long rows, int C, int ldo, int f16) {
+  pdl_trigger();
+  pdl_wait();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ldo) return;
+  const long r = i / ldo;
+  const int c = (int)(i - r * ldo);
+  const int2 ri = rowinfo[r];
+  const long tok = (long)(seq_off[ri.x & ~1] >> 1) + ri.y;
+  reinterpret_cast<uint16_t*>(out)[i] = pack16(c < C ? in[tok * C + c] : 0.f, f16);
+}
+
 }  // namespace
+
+void cast_pad_rows_ragged(const float* in, __nv_bfloat16* out, const int2* rowinfo, const int* seq_off, long rows, int C, int ldo,
+                          cudaStream_t s, int f16) {
+  if (rows <= 0) return;
+  launch_pdl(cast_pad_rows_ragged_kernel, dim3(ceil_div(rows * ldo, 256)), dim3(256), 0, s, in, out, rowinfo, seq_off, rows, C, ldo, f16);
+  B2_LAUNCH_CHECK(); count_launch();
+}
 
 void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t s, int f16) {
   if (n <= 0) return;

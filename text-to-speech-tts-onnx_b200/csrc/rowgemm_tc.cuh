@@ -40,5 +40,9 @@ void cast_f32_to_bf16(const float* in, __nv_bfloat16* out, long n, cudaStream_t 
 void cast_bf16_to_f32(const __nv_bfloat16* in, float* out, long n, cudaStream_t s, int f16 = 0);
 // (rows, C) fp32 -> (rows, ldo) bf16 with zero-filled padding columns
 void cast_pad_f32_to_bf16(const float* in, __nv_bfloat16* out, long rows, int C, int ldo, cudaStream_t s, int f16 = 0);
+// out[r][:] = in[token of DiT row r][:] (zero-padded to ldo) for a ragged batch: rowinfo[r] = (sequence, position), seq_off[sequence] =
+// first DiT row of the sequence; the two CFG sequences 2u, 2u+1 of utterance u read the same token rows seq_off[2u] / 2 + position
+void cast_pad_rows_ragged(const float* in, __nv_bfloat16* out, const int2* rowinfo, const int* seq_off, long rows, int C, int ldo,
+                          cudaStream_t s, int f16 = 0);
 
 }  // namespace b200tts
