@@ -115,8 +115,9 @@ class TextNormalizer:
         self._sub_zh = _table_substituter((("$", "."),) + _PUNCT_TABLE)
 
     def load(self):
-        """The reference's `load` (:225-234): WeTextProcessing on Linux / Windows, wetext on macOS. Normalisers passed to the
-        constructor are kept."""
+        """The reference's `load` (:225-234) picks WeTextProcessing (`tn`) on Linux / Windows and `wetext` on macOS, with the same
+        constructor arguments as here; this one takes whichever of the two imports, `tn` first, on any platform. Normalisers passed
+        to the constructor are kept."""
         if self.zh_normalizer is not None and self.en_normalizer is not None:
             return
         try:
