@@ -109,7 +109,7 @@ struct Engine {
   bool bigvgan_branches = true;
   // F5, ragged batches: the input embedding of ALL utterances as one launch over the 2 * Ntot DiT rows instead of two launches
   // per utterance (f5.cu): the profiled embedding time of configs[3] drops from 64 to 17 ms per batch, the step by 0.1-0.7 %
-  // (most of it was already hidden by programmatic dependent launch). b200tts_set_option("ragged_embed", 0) / B200TTS_RAGGED_EMBED=0
+  // (the profile pass weighs short launches more than the graph replay does). b200tts_set_option("ragged_embed", 0) / B200TTS_RAGGED_EMBED=0
   // at engine creation restore the per-utterance launches.
   bool ragged_embed = true;
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
