@@ -60,6 +60,25 @@ def test_text_to_ids_equals_the_reference_functions(tmp_path):
     np.testing.assert_array_equal(got_ids, want_ids)
 
 
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present")
+def test_text_to_symbols_random_strings_equal_the_reference(tmp_path):
+    """2 000 random strings over ASCII words, digits, quotes, CJK with and without toy pinyin, full-width and other non-ASCII
+    characters, through the port and through the reference's own function (both with the same segmenter / pinyin stand-ins)."""
+    import random
+    ref_convert, ref_to_idx = _reference_functions()
+    vocab = fe.load_vocab(_write_vocab(tmp_path))
+    rng = random.Random(17)
+    alphabet = ["a", "b", "hello", "World", " ", "  ", ",", ".", ";", ":", "'", '"', "“", "”", "‘", "’", "1", "23", "-", "!", "你", "好", "世", "界", "吗",
+                "，", "。", "é", "ü", "Ω", "ｱ", "？", "\n", "\t", "it's", "x"]
+    for polyphone in (True, False):
+        for _ in range(1000):
+            t = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 14)))
+            want = ref_convert([t], polyphone=polyphone)
+            got = fe.text_to_symbols([t], polyphone=polyphone, segmenter=fe._fallback_segments, to_pinyin=_toy_pinyin)
+            assert got == want, (t, polyphone, got, want)
+            np.testing.assert_array_equal(fe.symbols_to_ids(got, vocab), ref_to_idx(want, vocab).numpy())
+
+
 def test_text_to_symbols_fixed_cases(tmp_path):
     vocab = fe.load_vocab(_write_vocab(tmp_path))
     assert vocab[" "] == 0 and vocab["x"] == len(VOCAB) - 1
