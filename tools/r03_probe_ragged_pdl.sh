@@ -1,5 +1,7 @@
 #!/bin/bash
-# ragged_pdl option: parity tests with the option on, then configs[3] A/B on ONE box (B200TTS_RAGGED_PDL = 0 / 1).
+# ragged_pdl experiment (NOT KEPT: the switch is no longer in the code): parity tests with the option on, then configs[3] A/B on ONE box
+# (B200TTS_RAGGED_PDL = 0 / 1). The change was `PdlScope pdl_short(m.U == 1 || (m.ragged && e.ragged_pdl))` around the per-utterance conv-pos
+# launches of f5_steps and `PdlScope(e.ragged_pdl)` around the per-utterance Euler launches. Result: profiles/r02/probe_zp_ragged_pdl_experiment.log.
 OUT=gpurun_out/r03_probe_ragged_pdl.log
 : > $OUT
 echo "== pytest ragged tests, B200TTS_RAGGED_PDL=1" >> $OUT
